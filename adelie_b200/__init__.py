@@ -1,0 +1,20 @@
+"""adelie_b200 -- B200-native (sm_100a) group-elastic-net coordinate-descent path.
+
+Keeps the ``adelie.solver.grpnet`` / ``adelie.state`` / ``adelie.matrix`` / ``adelie.glm`` /
+``adelie.bcd`` / ``adelie.configs`` surface of JamesYang007/adelie for the naive-method path and
+runs it on hand-written CUDA kernels through the C ABI in ``include/adelie_b200.h``.
+There is no CPU fallback: every operator raises if ``libadelie_b200.so`` or a GPU is missing.
+"""
+from . import _lib
+from . import bcd
+from . import configs
+from . import data
+from . import diagnostic
+from . import glm
+from . import matrix
+from . import solver
+from . import state
+from .configs import set_configs
+from .solver import grpnet
+
+__version__ = "0.1.0"

@@ -1,0 +1,41 @@
+"""Process-global knobs (reference: adelie/configs.py:4-27, CORE/configs.hpp:6-20)."""
+from . import _lib
+import ctypes as C
+
+_DEFAULTS = {
+    "hessian_min": 1e-24,
+    "dbeta_tol": 1e-12,
+    "min_bytes": float(1 << 17),     # CPU threading threshold of the reference: accepted and ignored on the GPU
+    "max_solver_value": 1e100,
+    "project": 1.0,
+    # B200-specific
+    "sweep_ctas": 0.0,
+    "sweep_threads": 512.0,
+    "sweep_min_rows_per_cta": 1024.0,
+    "sweep_force_direct": 0.0,
+    "device_eigh": 1.0,
+}
+
+
+class Configs:
+    """Attribute view of the library configuration (``adelie.configs.Configs``)."""
+    def __getattr__(self, name):
+        if name.endswith("_def"):
+            return _DEFAULTS[name[:-4]]
+        if name not in _DEFAULTS:
+            raise AttributeError(name)
+        out = C.c_double()
+        _lib.check(_lib.load().ab_configs_get(name.encode(), C.byref(out)))
+        return out.value
+
+
+Configs = Configs()
+
+
+def set_configs(name: str, value=None):
+    """Sets a configuration; ``None`` restores the default (adelie/configs.py:4-27)."""
+    if name not in _DEFAULTS:
+        raise RuntimeError(f"adelie_core: unknown config {name}")
+    if value is None:
+        value = _DEFAULTS[name]
+    _lib.check(_lib.load().ab_configs_set(name.encode(), float(value)))

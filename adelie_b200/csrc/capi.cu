@@ -1,0 +1,547 @@
+// adelie_b200/csrc/capi.cu -- the single translation unit of libadelie_b200.so: extern "C"
+// entry points declared in include/adelie_b200.h on top of the templated host objects.
+#include "../../include/adelie_b200.h"
+#include "common.cuh"
+#include "device_prims.cuh"
+#include "sweep.cuh"
+#include "dense_kernels.cuh"
+#include "matrix.cuh"
+#include "glm.cuh"
+#include "solver.cuh"
+#include "solver_glm.cuh"
+#include <memory>
+
+using namespace ab;
+
+static thread_local std::string g_last_error;
+
+struct ab_matrix { int dtype; DenseMatrix<float>* f32 = nullptr; DenseMatrix<double>* f64 = nullptr; };
+struct ab_glm { int dtype; int family; Glm<float>* f32 = nullptr; Glm<double>* f64 = nullptr; };
+struct ab_state { int dtype; PathState<float>* f32 = nullptr; PathState<double>* f64 = nullptr; std::string error; double total_time = 0; };
+
+#define AB_TRY try {
+#define AB_CATCH                                                                                  \
+    } catch (const core_error& e) { g_last_error = e.what(); return AB_ERR_CORE; }                \
+    catch (const std::exception& e) { g_last_error = e.what(); return AB_ERR_CUDA; }              \
+    return AB_OK;
+
+template <class F32, class F64>
+static auto dispatch(int dtype, F32 f32, F64 f64) { return dtype == AB_F32 ? f32() : f64(); }
+
+extern "C" {
+
+const char* ab_last_error(void) { return g_last_error.c_str(); }
+int ab_version(void) { return 100; }
+int ab_device_count(int* count) { AB_TRY AB_CUDA(cudaGetDeviceCount(count)); AB_CATCH }
+int ab_set_device(int device) { AB_TRY AB_CUDA(cudaSetDevice(device)); AB_CATCH }
+int ab_get_device_info(int* sm_count, size_t* smem, size_t* total_mem) {
+    AB_TRY
+    const auto& di = DeviceInfo::get();
+    if (sm_count) *sm_count = di.sm_count;
+    if (smem) *smem = di.smem_optin;
+    if (total_mem) { size_t fr, tot; AB_CUDA(cudaMemGetInfo(&fr, &tot)); *total_mem = tot; }
+    AB_CATCH
+}
+int ab_device_synchronize(void) { AB_TRY AB_CUDA(cudaDeviceSynchronize()); AB_CATCH }
+
+int ab_configs_set(const char* name, double value) {
+    const std::string s(name);
+    if (s == "hessian_min") Configs::hessian_min = value;
+    else if (s == "dbeta_tol") Configs::dbeta_tol = value;
+    else if (s == "min_bytes") Configs::min_bytes = value;
+    else if (s == "max_solver_value") Configs::max_solver_value = value;
+    else if (s == "project") Configs::project = (int)value;
+    else if (s == "sweep_ctas") Configs::sweep_ctas = (int)value;
+    else if (s == "sweep_threads") Configs::sweep_threads = (int)value;
+    else if (s == "sweep_min_rows_per_cta") Configs::sweep_min_rows_per_cta = (int)value;
+    else if (s == "sweep_force_direct") Configs::sweep_force_direct = (int)value;
+    else if (s == "device_eigh") Configs::device_eigh = (int)value;
+    else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
+    return AB_OK;
+}
+int ab_configs_get(const char* name, double* value) {
+    const std::string s(name);
+    if (s == "hessian_min") *value = Configs::hessian_min;
+    else if (s == "dbeta_tol") *value = Configs::dbeta_tol;
+    else if (s == "min_bytes") *value = Configs::min_bytes;
+    else if (s == "max_solver_value") *value = Configs::max_solver_value;
+    else if (s == "project") *value = Configs::project;
+    else if (s == "sweep_ctas") *value = Configs::sweep_ctas;
+    else if (s == "sweep_threads") *value = Configs::sweep_threads;
+    else if (s == "sweep_min_rows_per_cta") *value = Configs::sweep_min_rows_per_cta;
+    else if (s == "sweep_force_direct") *value = Configs::sweep_force_direct;
+    else if (s == "device_eigh") *value = Configs::device_eigh;
+    else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
+    return AB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ matrix
+int ab_matrix_dense_alloc(int dtype, int64_t n, int64_t p, ab_matrix** out) {
+    AB_TRY
+    if (n < 1 || p < 1) throw core_error("matrix must have at least one row and one column.");
+    auto* m = new ab_matrix{dtype};
+    if (dtype == AB_F32) m->f32 = new DenseMatrix<float>(n, p); else m->f64 = new DenseMatrix<double>(n, p);
+    *out = m;
+    AB_CATCH
+}
+int ab_matrix_dense_create(int dtype, const void* host, int64_t n, int64_t p, int order, int64_t ldh, int n_threads, ab_matrix** out) {
+    AB_TRY
+    if (n_threads < 1) throw core_error("n_threads must be >= 1.");
+    ab_matrix* m = nullptr;
+    int rc = ab_matrix_dense_alloc(dtype, n, p, &m);
+    if (rc) return rc;
+    if (dtype == AB_F32) { m->f32->n_threads = n_threads; m->f32->upload((const float*)host, order, ldh); }
+    else { m->f64->n_threads = n_threads; m->f64->upload((const double*)host, order, ldh); }
+    *out = m;
+    AB_CATCH
+}
+int ab_matrix_dense_fill_normal(ab_matrix* m, uint64_t seed, int64_t row_offset) {
+    AB_TRY
+    if (m->dtype == AB_F32) m->f32->fill_normal(seed, row_offset); else m->f64->fill_normal(seed, row_offset);
+    AB_CUDA(cudaDeviceSynchronize());
+    AB_CATCH
+}
+int ab_matrix_dense_download(ab_matrix* m, void* host, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, int64_t ldh) {
+    AB_TRY
+    if (m->dtype == AB_F32) m->f32->download((float*)host, row0, nrows, col0, ncols, ldh);
+    else m->f64->download((double*)host, row0, nrows, col0, ncols, ldh);
+    AB_CATCH
+}
+int ab_matrix_free(ab_matrix* m) { if (m) { delete m->f32; delete m->f64; delete m; } return AB_OK; }
+int ab_matrix_rows(const ab_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->n : m->f64->n; return AB_OK; }
+int ab_matrix_cols(const ab_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->p : m->f64->p; return AB_OK; }
+
+} // extern "C"
+
+// shape checks with the reference's messages (matrix_naive_base.hpp:148-271)
+static void check_cmul(int64_t j, int64_t r, int64_t c) {
+    if (j < 0 || j >= c) throw core_error("cmul() is given inconsistent inputs! (j=" + std::to_string(j) + ", r=" + std::to_string(r) + ", c=" + std::to_string(c) + ")");
+}
+static void check_bmul(int64_t j, int64_t q, int64_t r, int64_t c) {
+    if (j < 0 || q < 0 || j + q > c) throw core_error("bmul() is given inconsistent inputs! (j=" + std::to_string(j) + ", q=" + std::to_string(q) + ", r=" + std::to_string(r) + ", c=" + std::to_string(c) + ")");
+}
+
+template <class T>
+struct HostOps {
+    // stage host vectors into padded device buffers
+    static DevBuf<T> up(const T* h, int64_t n, int64_t np) { DevBuf<T> d(np); d.upload(h, n); return d; }
+
+    static double cmul(DenseMatrix<T>& M, int64_t j, const T* v, const T* w) {
+        check_cmul(j, M.n, M.p);
+        auto dv = up(v, M.n, M.ld), dw = up(w, M.n, M.ld); DevBuf<T> o(1);
+        M.d_gemv_t(j, nullptr, 1, dv.p, dw.p, o.p);
+        T r; o.download(&r, 1); AB_CUDA(cudaStreamSynchronize(0));
+        return (double)r;
+    }
+    static void bmul(DenseMatrix<T>& M, int64_t j, int64_t q, const T* v, const T* w, T* out) {
+        check_bmul(j, q, M.n, M.p);
+        if (q == 0) return;
+        auto dv = up(v, M.n, M.ld), dw = up(w, M.n, M.ld); DevBuf<T> o(q);
+        M.d_gemv_t(j, nullptr, (int)q, dv.p, dw.p, o.p);
+        o.download(out, q); AB_CUDA(cudaStreamSynchronize(0));
+    }
+    static void btmul(DenseMatrix<T>& M, int64_t j, int64_t q, const T* v, T* out) {
+        check_bmul(j, q, M.n, M.p);
+        if (q == 0) return;
+        auto dv = up(v, q, q + 4), dout = up(out, M.n, M.ld);
+        M.d_btmul(j, (int)q, dv.p, dout.p);
+        dout.download(out, M.n); AB_CUDA(cudaStreamSynchronize(0));
+    }
+    static void mul(DenseMatrix<T>& M, const T* v, const T* w, T* out) {
+        auto dv = up(v, M.n, M.ld), dw = up(w, M.n, M.ld); DevBuf<T> o(M.p);
+        M.d_mul(dv.p, dw.p, o.p);
+        o.download(out, M.p); AB_CUDA(cudaStreamSynchronize(0));
+    }
+    static void sq_mul(DenseMatrix<T>& M, const T* w, T* out) {
+        auto dw = up(w, M.n, M.ld); DevBuf<T> o(M.p);
+        M.d_gemv_t(0, nullptr, (int)M.p, dw.p, dw.p, o.p, true);
+        o.download(out, M.p); AB_CUDA(cudaStreamSynchronize(0));
+    }
+    static void cov(DenseMatrix<T>& M, int64_t j, int64_t q, const T* sqrt_w, T* out) {
+        check_bmul(j, q, M.n, M.p);
+        if (q == 0) return;
+        auto dw = up(sqrt_w, M.n, M.ld);
+        CovItem it{(int32_t)j, (int32_t)q, 0};
+        DevBuf<CovItem> di(1); di.upload(&it, 1);
+        DevBuf<double> C((size_t)q * q);
+        M.d_cov(di.p, 1, q * q, dw.p, true, C.p);
+        std::vector<double> h((size_t)q * q);
+        C.download(h.data(), h.size()); AB_CUDA(cudaStreamSynchronize(0));
+        for (int64_t a = 0; a < q; ++a) for (int64_t b = 0; b < q; ++b) out[a + b * q] = (T)h[a * q + b];
+    }
+    static void sp_tmul(DenseMatrix<T>& M, int64_t L, const int64_t* indptr, const int64_t* indices, const T* values, T* out) {
+        // out[l, :] = sum_k values[k] * X[:, indices[k]]  -- one axpy launch per non-zero column
+        DevBuf<T> drow(M.ld), dv(4);
+        for (int64_t l = 0; l < L; ++l) {
+            AB_CUDA(cudaMemsetAsync(drow.p, 0, M.ld * sizeof(T), 0));
+            for (int64_t k = indptr[l]; k < indptr[l + 1]; ++k) {
+                if (indices[k] < 0 || indices[k] >= M.p) throw core_error("sp_tmul() is given inconsistent inputs!");
+                dv.upload(values + k, 1);
+                M.d_btmul(indices[k], 1, dv.p, drow.p);
+            }
+            drow.download(out + l * M.n, M.n);
+            AB_CUDA(cudaStreamSynchronize(0));
+        }
+    }
+};
+
+extern "C" {
+
+int ab_matrix_cmul(ab_matrix* m, int64_t j, const void* v, const void* w, double* out) {
+    AB_TRY
+    *out = m->dtype == AB_F32 ? HostOps<float>::cmul(*m->f32, j, (const float*)v, (const float*)w)
+                              : HostOps<double>::cmul(*m->f64, j, (const double*)v, (const double*)w);
+    AB_CATCH
+}
+int ab_matrix_ctmul(ab_matrix* m, int64_t j, double v, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) { check_cmul(j, m->f32->n, m->f32->p); float vv = (float)v; HostOps<float>::btmul(*m->f32, j, 1, &vv, (float*)out); }
+    else { check_cmul(j, m->f64->n, m->f64->p); HostOps<double>::btmul(*m->f64, j, 1, &v, (double*)out); }
+    AB_CATCH
+}
+int ab_matrix_bmul(ab_matrix* m, int64_t j, int64_t q, const void* v, const void* w, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) HostOps<float>::bmul(*m->f32, j, q, (const float*)v, (const float*)w, (float*)out);
+    else HostOps<double>::bmul(*m->f64, j, q, (const double*)v, (const double*)w, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_btmul(ab_matrix* m, int64_t j, int64_t q, const void* v, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) HostOps<float>::btmul(*m->f32, j, q, (const float*)v, (float*)out);
+    else HostOps<double>::btmul(*m->f64, j, q, (const double*)v, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_mul(ab_matrix* m, const void* v, const void* w, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) HostOps<float>::mul(*m->f32, (const float*)v, (const float*)w, (float*)out);
+    else HostOps<double>::mul(*m->f64, (const double*)v, (const double*)w, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_cov(ab_matrix* m, int64_t j, int64_t q, const void* sqrt_w, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) HostOps<float>::cov(*m->f32, j, q, (const float*)sqrt_w, (float*)out);
+    else HostOps<double>::cov(*m->f64, j, q, (const double*)sqrt_w, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_sq_mul(ab_matrix* m, const void* w, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) HostOps<float>::sq_mul(*m->f32, (const float*)w, (float*)out);
+    else HostOps<double>::sq_mul(*m->f64, (const double*)w, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_sp_tmul(ab_matrix* m, int64_t L, const int64_t* indptr, const int64_t* indices, const void* values, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) HostOps<float>::sp_tmul(*m->f32, L, indptr, indices, (const float*)values, (float*)out);
+    else HostOps<double>::sp_tmul(*m->f64, L, indptr, indices, (const double*)values, (double*)out);
+    AB_CATCH
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------ glm
+template <class T>
+static Glm<T>* make_glm(int family, int64_t n, int64_t K, const void* y, const void* w) {
+    switch (family) {
+        case AB_GLM_GAUSSIAN: return new GlmGaussian<T>((const T*)y, (const T*)w, n);
+        case AB_GLM_BINOMIAL_LOGIT: return new GlmBinomialLogit<T>((const T*)y, (const T*)w, n);
+        case AB_GLM_MULTIGAUSSIAN: return new GlmMultiGaussian<T>((const T*)y, (const T*)w, n, K);
+    }
+    throw core_error("unsupported GLM family.");
+}
+
+template <class T>
+struct GlmHost {
+    static int64_t padn(Glm<T>& g) { return g.is_multi ? pad_rows(g.n / g.K) * g.K : pad_rows(g.n); }
+    static DevBuf<T> up(Glm<T>& g, const void* h) { DevBuf<T> d(padn(g)); d.upload((const T*)h, g.n); return d; }
+    static void down(Glm<T>& g, DevBuf<T>& d, void* h) { d.download((T*)h, g.n); AB_CUDA(cudaStreamSynchronize(0)); }
+};
+
+extern "C" {
+
+int ab_glm_create(int dtype, int family, int64_t n, int64_t K, const void* y, const void* weights,
+                  const void* cox_start, const void* cox_stop, const int64_t* cox_strata, int cox_tie_efron, ab_glm** out) {
+    AB_TRY
+    (void)cox_start; (void)cox_stop; (void)cox_strata; (void)cox_tie_efron;
+    auto* g = new ab_glm{dtype, family};
+    if (dtype == AB_F32) g->f32 = make_glm<float>(family, n, K, y, weights); else g->f64 = make_glm<double>(family, n, K, y, weights);
+    *out = g;
+    AB_CATCH
+}
+int ab_glm_free(ab_glm* g) { if (g) { delete g->f32; delete g->f64; delete g; } return AB_OK; }
+
+#define GLM_CALL(BODY32, BODY64) AB_TRY if (g->dtype == AB_F32) { auto& G = *g->f32; using T = float; BODY32 } else { auto& G = *g->f64; using T = double; BODY64 } AB_CATCH
+#define GLM_BOTH(BODY) GLM_CALL(BODY, BODY)
+
+int ab_glm_gradient(ab_glm* g, const void* eta, void* grad) {
+    GLM_BOTH({ auto e = GlmHost<T>::up(G, eta); DevBuf<T> o(GlmHost<T>::padn(G)); G.gradient(e.p, o.p); GlmHost<T>::down(G, o, grad); })
+}
+int ab_glm_hessian(ab_glm* g, const void* eta, const void* grad, void* hess) {
+    GLM_BOTH({ auto e = GlmHost<T>::up(G, eta); auto gr = GlmHost<T>::up(G, grad); DevBuf<T> o(GlmHost<T>::padn(G)); G.hessian(e.p, gr.p, o.p); GlmHost<T>::down(G, o, hess); })
+}
+int ab_glm_inv_hessian_gradient(ab_glm* g, const void* eta, const void* grad, const void* hess, void* out) {
+    GLM_BOTH({ auto e = GlmHost<T>::up(G, eta); auto gr = GlmHost<T>::up(G, grad); auto h = GlmHost<T>::up(G, hess); DevBuf<T> o(GlmHost<T>::padn(G));
+               G.inv_hessian_gradient(e.p, gr.p, h.p, o.p); GlmHost<T>::down(G, o, out); })
+}
+int ab_glm_loss(ab_glm* g, const void* eta, double* out) {
+    GLM_BOTH({ auto e = GlmHost<T>::up(G, eta); *out = (double)G.loss(e.p); })
+}
+int ab_glm_loss_full(ab_glm* g, double* out) {
+    GLM_BOTH({ *out = (double)G.loss_full(); })
+}
+int ab_glm_inv_link(ab_glm* g, const void* eta, void* out) {
+    GLM_BOTH({ auto e = GlmHost<T>::up(G, eta); DevBuf<T> o(GlmHost<T>::padn(G)); G.inv_link(e.p, o.p); GlmHost<T>::down(G, o, out); })
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------ state
+template <class T>
+static PathState<T>* make_state(const ab_state_args* a, DenseMatrix<T>* X, Glm<T>* glm) {
+    auto st = std::make_unique<PathState<T>>();
+    auto& s = *st;
+    s.X = X; s.n = X->n; s.p = X->p; s.G = a->G;
+    if (a->G < 1) throw core_error("groups must be non-empty.");
+    s.groups.assign(a->groups, a->groups + a->G);
+    s.group_sizes.assign(a->group_sizes, a->group_sizes + a->G);
+    s.alpha = (T)a->alpha;
+    s.penalty.assign((const T*)a->penalty, (const T*)a->penalty + a->G);
+    s.is_glm = glm != nullptr; s.glm = glm;
+    s.min_ratio = (T)a->min_ratio; s.lmda_path_size = a->lmda_path_size; s.max_screen_size = a->max_screen_size; s.max_active_size = a->max_active_size;
+    s.pivot_subset_ratio = (T)a->pivot_subset_ratio; s.pivot_subset_min = a->pivot_subset_min; s.pivot_slack_ratio = (T)a->pivot_slack_ratio;
+    s.screen_rule = a->screen_rule; s.max_iters = a->max_iters; s.tol = (T)a->tol; s.adev_tol = (T)a->adev_tol; s.ddev_tol = (T)a->ddev_tol;
+    s.newton_tol = (T)a->newton_tol; s.newton_max_iters = a->newton_max_iters; s.early_exit = a->early_exit;
+    s.setup_lmda_max = a->setup_lmda_max; s.setup_lmda_path = a->setup_lmda_path; s.intercept = a->intercept; s.n_threads = a->n_threads;
+    s.lmda_max = (T)a->lmda_max; s.lmda = (T)a->lmda;
+    if (a->lmda_path && a->lmda_path_len > 0) s.lmda_path.assign((const T*)a->lmda_path, (const T*)a->lmda_path + a->lmda_path_len);
+    s.screen_set.assign(a->screen_set, a->screen_set + a->screen_set_size);
+    s.screen_beta.assign((const T*)a->screen_beta, (const T*)a->screen_beta + a->screen_beta_size);
+    s.screen_is_active.assign(a->screen_is_active, a->screen_is_active + a->screen_set_size);
+    s.active_set_size = a->active_set_size;
+    s.active_set.assign(a->active_set, a->active_set + a->G);
+    s.grad.assign((const T*)a->grad, (const T*)a->grad + s.p);
+    const int64_t np = X->n_pad();
+    s.d_resid.alloc(np); s.d_grad.alloc(s.p);
+    s.d_resid.upload((const T*)a->resid, s.n);
+    if (!s.is_glm) {
+        // state_gaussian_naive.ipp:9-28 shape checks are implied by the pointer/size contract of the C ABI
+        s.d_weights.alloc(np); s.d_weights.upload((const T*)a->weights, s.n);
+        s.d_resid_prev.alloc(np);
+        s.X_means.assign((const T*)a->X_means, (const T*)a->X_means + s.p);
+        s.d_X_means.alloc(s.p); s.d_X_means.upload(s.X_means.data(), s.p);
+        s.y_mean = (T)a->y_mean; s.y_var = (T)a->y_var; s.resid_sum = (T)a->resid_sum; s.rsq = (T)a->rsq;
+    } else {
+        if (glm->n != s.n) throw core_error("y must be (n,) where X is (n, p).");
+        s.d_offsets.alloc(np); s.d_offsets.upload((const T*)a->offsets, s.n);
+        s.d_eta.alloc(np); s.d_eta.upload((const T*)a->eta, s.n);
+        s.d_eta_prev.alloc(np); s.d_glm_resid_prev.alloc(np); s.d_hess.alloc(np); s.d_irls_w.alloc(np);
+        s.d_irls_y.alloc(np); s.d_irls_resid.alloc(np);
+        s.beta0 = (T)a->beta0; s.loss_null = (T)a->loss_null; s.loss_full = (T)a->loss_full; s.setup_loss_null = a->setup_loss_null;
+        s.irls_max_iters = a->irls_max_iters; s.irls_tol = (T)a->irls_tol;
+    }
+    AB_CUDA(cudaStreamSynchronize(0));
+    s.validate_and_init();
+    return st.release();
+}
+
+template <class T>
+static void get_betas(const PathState<T>& s, int64_t* indptr, int64_t* indices, double* values, int64_t* nnz, int64_t* L) {
+    int64_t tot = 0;
+    if (indptr) indptr[0] = 0;
+    for (size_t l = 0; l < s.betas.size(); ++l) {
+        const auto& b = s.betas[l];
+        for (size_t k = 0; k < b.idx.size(); ++k) {
+            if (indices) indices[tot + k] = b.idx[k];
+            if (values) values[tot + k] = b.val[k];
+        }
+        tot += (int64_t)b.idx.size();
+        if (indptr) indptr[l + 1] = tot;
+    }
+    *nnz = tot; *L = (int64_t)s.betas.size();
+}
+
+template <class T, class V>
+static int copy_vec(const V& v, double* out, int64_t cap, int64_t* len) {
+    *len = (int64_t)v.size();
+    if (out) for (int64_t i = 0; i < std::min<int64_t>(cap, *len); ++i) out[i] = (double)v[i];
+    return AB_OK;
+}
+template <class V>
+static int copy_ivec(const V& v, int64_t* out, int64_t cap, int64_t* len, int64_t limit = -1) {
+    *len = limit >= 0 ? limit : (int64_t)v.size();
+    if (out) for (int64_t i = 0; i < std::min<int64_t>(cap, *len); ++i) out[i] = (int64_t)v[i];
+    return AB_OK;
+}
+
+template <class T>
+static int state_vec_f64(const PathState<T>& s, const std::string& nm, double* out, int64_t cap, int64_t* len) {
+    if (nm == "lmda_path") return copy_vec<T>(s.lmda_path, out, cap, len);
+    if (nm == "screen_beta") return copy_vec<T>(s.screen_beta, out, cap, len);
+    if (nm == "grad") return copy_vec<T>(s.grad, out, cap, len);
+    if (nm == "abs_grad") return copy_vec<T>(s.abs_grad, out, cap, len);
+    if (nm == "devs") return copy_vec<T>(s.devs, out, cap, len);
+    if (nm == "lmdas") return copy_vec<T>(s.lmdas, out, cap, len);
+    if (nm == "intercepts") return copy_vec<T>(s.intercepts, out, cap, len);
+    if (nm == "X_means") return copy_vec<T>(s.X_means, out, cap, len);
+    if (nm == "screen_X_means") return copy_vec<T>(s.screen_X_means, out, cap, len);
+    if (nm == "screen_vars") return copy_vec<T>(s.screen_vars, out, cap, len);
+    if (nm == "penalty") return copy_vec<T>(s.penalty, out, cap, len);
+    if (nm == "benchmark_screen") return copy_vec<double>(s.benchmark_screen, out, cap, len);
+    if (nm == "benchmark_fit_screen") return copy_vec<double>(s.benchmark_fit_screen, out, cap, len);
+    if (nm == "benchmark_fit_active") return copy_vec<double>(s.benchmark_fit_active, out, cap, len);
+    if (nm == "benchmark_kkt") return copy_vec<double>(s.benchmark_kkt, out, cap, len);
+    if (nm == "benchmark_invariance") return copy_vec<double>(s.benchmark_invariance, out, cap, len);
+    if (nm == "resid" || nm == "eta") {
+        const DevBuf<T>& d = (nm == "resid") ? s.d_resid : s.d_eta;
+        const int64_t nn = s.is_glm ? s.glm->n : s.n;
+        *len = d.p ? nn : 0;
+        if (out && d.p) {
+            std::vector<T> h(nn);
+            d.download(h.data(), nn); AB_CUDA(cudaStreamSynchronize(0));
+            for (int64_t i = 0; i < std::min<int64_t>(cap, nn); ++i) out[i] = (double)h[i];
+        }
+        return AB_OK;
+    }
+    g_last_error = "adelie_core: unknown state vector " + nm;
+    return AB_ERR_ARG;
+}
+template <class T>
+static int state_vec_i64(const PathState<T>& s, const std::string& nm, int64_t* out, int64_t cap, int64_t* len) {
+    if (nm == "groups") return copy_ivec(s.groups, out, cap, len);
+    if (nm == "group_sizes") return copy_ivec(s.group_sizes, out, cap, len);
+    if (nm == "screen_set") return copy_ivec(s.screen_set, out, cap, len);
+    if (nm == "screen_begins") return copy_ivec(s.screen_begins, out, cap, len);
+    if (nm == "screen_is_active") return copy_ivec(s.screen_is_active, out, cap, len);
+    if (nm == "active_set") return copy_ivec(s.active_set, out, cap, len);
+    if (nm == "n_valid_solutions") return copy_ivec(s.n_valid_solutions, out, cap, len);
+    if (nm == "active_sizes") return copy_ivec(s.active_sizes, out, cap, len);
+    if (nm == "screen_sizes") return copy_ivec(s.screen_sizes, out, cap, len);
+    g_last_error = "adelie_core: unknown state vector " + nm;
+    return AB_ERR_ARG;
+}
+template <class T>
+static int state_scalar(const PathState<T>& s, const std::string& nm, double* out) {
+    if (nm == "lmda_max") *out = s.lmda_max; else if (nm == "lmda") *out = s.lmda;
+    else if (nm == "rsq") *out = s.rsq; else if (nm == "resid_sum") *out = s.resid_sum;
+    else if (nm == "y_mean") *out = s.y_mean; else if (nm == "y_var") *out = s.y_var;
+    else if (nm == "loss_null") *out = s.loss_null; else if (nm == "loss_full") *out = s.loss_full;
+    else if (nm == "beta0") *out = s.beta0; else if (nm == "active_set_size") *out = (double)s.active_set_size;
+    else if (nm == "alpha") *out = s.alpha; else if (nm == "tol") *out = s.tol;
+    else if (nm == "n_sweeps") *out = (double)s.n_sweeps; else if (nm == "n_group_updates") *out = (double)s.n_group_updates;
+    else if (nm == "n_irls") *out = (double)s.n_irls; else if (nm == "n_pin_solves") *out = (double)s.n_pin_solves;
+    else if (nm == "n_kernel_launches") *out = (double)s.n_kernel_launches;
+    else if (nm == "time_sweep_kernel") *out = s.time_sweep_kernel;
+    else if (nm == "sweep_ncta") *out = s.X->last_geom.ncta; else if (nm == "sweep_stages") *out = s.X->last_geom.n_stages;
+    else if (nm == "sweep_smem_bytes") *out = (double)s.X->last_geom.smem_bytes; else if (nm == "sweep_staged") *out = s.X->last_geom.smem ? 1 : 0;
+    else if (nm == "sweep_threads") *out = s.X->last_geom.threads;
+    else if (nm == "setup_lmda_max") *out = s.setup_lmda_max; else if (nm == "setup_lmda_path") *out = s.setup_lmda_path;
+    else { g_last_error = "adelie_core: unknown state scalar " + nm; return AB_ERR_ARG; }
+    return AB_OK;
+}
+
+extern "C" {
+
+int ab_state_create(const ab_state_args* args, ab_matrix* X, ab_glm* glm, ab_state** out) {
+    AB_TRY
+    if (X->dtype != args->dtype || (glm && glm->dtype != args->dtype)) throw core_error("dtype mismatch between state, matrix and glm.");
+    if (args->n_classes > 1) throw core_error("multi-response states are not implemented in this build.");
+    auto* s = new ab_state{args->dtype};
+    try {
+        if (args->dtype == AB_F32) s->f32 = make_state<float>(args, X->f32, glm ? glm->f32 : nullptr);
+        else s->f64 = make_state<double>(args, X->f64, glm ? glm->f64 : nullptr);
+    } catch (...) { delete s; throw; }
+    *out = s;
+    AB_CATCH
+}
+int ab_state_free(ab_state* s) { if (s) { delete s->f32; delete s->f64; delete s; } return AB_OK; }
+
+int ab_state_solve(ab_state* s, int display_progress_bar, int (*exit_cond)(void*), void* ctx, int (*check_signals)(void),
+                   char* err, size_t errlen, double* total_time) {
+    (void)display_progress_bar;
+    g_last_error.clear();
+    s->error.clear();
+    const double t0 = now_s();
+    auto run = [&](auto* ps) {
+        if (exit_cond) ps->exit_cond = [=]() { return exit_cond(ctx) != 0; };
+        if (check_signals) ps->check_interrupt = [=]() { if (check_signals() != 0) throw solver_error("interrupted."); };
+        try { ps->solve(); }
+        catch (const std::exception& e) { s->error = e.what(); }       // py_state.cpp:83-90: message returned, state stays valid
+        ps->exit_cond = nullptr; ps->check_interrupt = nullptr;
+    };
+    if (s->dtype == AB_F32) run(s->f32); else run(s->f64);
+    s->total_time = now_s() - t0;
+    if (total_time) *total_time = s->total_time;
+    if (err && errlen) { std::strncpy(err, s->error.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return AB_OK;
+}
+int ab_state_get_scalar(const ab_state* s, const char* name, double* out) {
+    AB_TRY
+    if (std::string(name) == "total_time") { *out = s->total_time; return AB_OK; }
+    return s->dtype == AB_F32 ? state_scalar(*s->f32, name, out) : state_scalar(*s->f64, name, out);
+    AB_CATCH
+}
+int ab_state_get_vec_f64(const ab_state* s, const char* name, double* out, int64_t cap, int64_t* len) {
+    AB_TRY
+    return s->dtype == AB_F32 ? state_vec_f64(*s->f32, name, out, cap, len) : state_vec_f64(*s->f64, name, out, cap, len);
+    AB_CATCH
+}
+int ab_state_get_vec_i64(const ab_state* s, const char* name, int64_t* out, int64_t cap, int64_t* len) {
+    AB_TRY
+    return s->dtype == AB_F32 ? state_vec_i64(*s->f32, name, out, cap, len) : state_vec_i64(*s->f64, name, out, cap, len);
+    AB_CATCH
+}
+int ab_state_get_betas(const ab_state* s, int64_t* indptr, int64_t* indices, double* values, int64_t* nnz, int64_t* L) {
+    AB_TRY
+    if (s->dtype == AB_F32) get_betas(*s->f32, indptr, indices, values, nnz, L); else get_betas(*s->f64, indptr, indices, values, nnz, L);
+    AB_CATCH
+}
+int ab_state_get_screen_transform(const ab_state* s, int64_t i, double* out, int64_t cap, int64_t* len) {
+    AB_TRY
+    auto get = [&](auto& st) {
+        if (i < 0 || i >= (int64_t)st.screen_transforms.size()) throw core_error("screen_transforms index out of range.");
+        const auto& v = st.screen_transforms[i];
+        *len = (int64_t)v.size();
+        if (out) for (int64_t k = 0; k < std::min<int64_t>(cap, *len); ++k) out[k] = (double)v[k];
+    };
+    if (s->dtype == AB_F32) get(*s->f32); else get(*s->f64);
+    AB_CATCH
+}
+
+// ------------------------------------------------------------------------------------------ bcd
+static int bcd_run(int mode, int64_t q, const double* L, const double* v, double l1, double l2, double tol, int64_t max_iters, double aux,
+                   double* x, double* scal) {
+    AB_TRY
+    if (q < 1) throw core_error("quad must be non-empty.");
+    DevBuf<double> dL(q), dv(q), dx(q), ds(1);
+    dL.upload(L, q); dv.upload(v, q);
+    bcd_kernel<<<1, 32, 4 * q * sizeof(double), 0>>>(mode, (int)q, dL.p, dv.p, l1, l2, tol, (int)std::min<int64_t>(max_iters, 1 << 30), aux, dx.p, ds.p);
+    AB_CUDA(cudaGetLastError());
+    if (x) dx.download(x, q);
+    ds.download(scal, 1);
+    AB_CUDA(cudaStreamSynchronize(0));
+    AB_CATCH
+}
+int ab_bcd_solve(int solver, int64_t q, const double* quad, const double* linear, double l1, double l2, double tol, int64_t max_iters,
+                 double* x, int64_t* iters) {
+    double it = 0;
+    int rc = bcd_run(solver == 1 ? 1 : 0, q, quad, linear, l1, l2, tol, max_iters, 0, x, &it);
+    if (iters) *iters = (int64_t)it;
+    return rc;
+}
+int ab_bcd_root_lower_bound(int64_t q, const double* quad, const double* linear, double l1, double* out) {
+    return bcd_run(2, q, quad, linear, l1, 0, 0, 0, 0, nullptr, out);
+}
+int ab_bcd_root_upper_bound(int64_t q, const double* quad, const double* linear, double l1, double zero_tol, double* out) {
+    return bcd_run(3, q, quad, linear, l1, 0, 0, 0, zero_tol, nullptr, out);
+}
+int ab_bcd_root_function(int64_t q, double h, const double* D, const double* v, double l1, double* out) {
+    return bcd_run(4, q, D, v, l1, 0, 0, 0, h, nullptr, out);
+}
+
+int ab_pin_naive_solve(ab_matrix* X, ab_pin_args* args, ab_state** out, char* err, size_t errlen) {
+    (void)X; (void)args; (void)out;
+    if (err && errlen) err[0] = 0;
+    g_last_error = "adelie_core: pin state API not implemented yet.";
+    return AB_ERR_ARG;
+}
+
+} // extern "C"

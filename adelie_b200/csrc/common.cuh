@@ -1,0 +1,129 @@
+// adelie_b200/csrc/common.cuh -- shared host/device helpers for the sm_100a library.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <chrono>
+
+namespace ab {
+
+// Mirrors the two exception classes of the reference (CORE/util/exceptions.hpp:8-56):
+// core_error  -> "adelie_core: ..."         (propagates to Python as RuntimeError)
+// solver_error-> "adelie_core solver: ..."  (caught inside solve, returned as `error`)
+struct core_error : std::runtime_error {
+    explicit core_error(const std::string& m) : std::runtime_error("adelie_core: " + m) {}
+    core_error(const std::string& prefix, const std::string& m) : std::runtime_error("adelie_core " + prefix + ": " + m) {}
+};
+struct solver_error : core_error {
+    explicit solver_error(const std::string& m) : core_error("solver", m) {}
+};
+
+#define AB_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            throw ::ab::core_error(std::string("CUDA error: ") + cudaGetErrorString(_e) +     \
+                                   " at " + __FILE__ + ":" + std::to_string(__LINE__));       \
+        }                                                                                     \
+    } while (0)
+
+inline double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Process-global knobs (CORE/configs.hpp:6-20).  min_bytes is a CPU threading
+// threshold: accepted and ignored on the GPU.
+struct Configs {
+    static inline double hessian_min = 1e-24;
+    static inline double dbeta_tol = 1e-12;
+    static inline double min_bytes = 1 << 17;
+    static inline double max_solver_value = 1e100;
+    static inline int project = 1;
+    // B200-specific knobs
+    static inline int sweep_ctas = 0;          // 0 = auto (one CTA per SM, capped by rows)
+    static inline int sweep_threads = 512;
+    static inline int sweep_min_rows_per_cta = 1024;
+    static inline int sweep_force_direct = 0;  // 1 = never stage X tiles in shared memory (debug / fallback path)
+    static inline int device_eigh = 1;         // batched Jacobi on device (0 = host Jacobi)
+};
+
+constexpr int kRowAlign = 32;     // rows of every device vector / matrix column are padded to this many elements
+inline int64_t pad_rows(int64_t n) { return (n + kRowAlign - 1) / kRowAlign * kRowAlign; }
+
+// Owning device buffer (zero-initialised).
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t n_) { alloc(n_); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { free(); }
+    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t n_) {
+        free();
+        n = n_;
+        if (n) { AB_CUDA(cudaMalloc(&p, n * sizeof(T))); AB_CUDA(cudaMemset(p, 0, n * sizeof(T))); }
+    }
+    // grow keeping contents (new tail zeroed)
+    void reserve_keep(size_t n_, cudaStream_t st = 0) {
+        if (n_ <= n) return;
+        size_t cap = std::max(n_, n * 2 + 64);
+        T* q = nullptr;
+        AB_CUDA(cudaMalloc(&q, cap * sizeof(T)));
+        AB_CUDA(cudaMemsetAsync(q, 0, cap * sizeof(T), st));
+        if (p && n) AB_CUDA(cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        AB_CUDA(cudaStreamSynchronize(st));
+        if (p) cudaFree(p);
+        p = q; n = cap;
+    }
+    void upload(const T* h, size_t cnt, size_t off = 0, cudaStream_t st = 0) {
+        if (cnt) AB_CUDA(cudaMemcpyAsync(p + off, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    void download(T* h, size_t cnt, size_t off = 0, cudaStream_t st = 0) const {
+        if (cnt) AB_CUDA(cudaMemcpyAsync(h, p + off, cnt * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+};
+
+// Pinned host buffer for small, frequent D2H reads.
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr; size_t n = 0;
+    PinnedBuf() = default;
+    explicit PinnedBuf(size_t n_) { alloc(n_); }
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void alloc(size_t n_) {
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = n_;
+        if (n) AB_CUDA(cudaMallocHost(&p, n * sizeof(T)));
+    }
+    void ensure(size_t n_) { if (n_ > n) alloc(n_ * 2); }
+};
+
+struct DeviceInfo {
+    int device = 0; int sm_count = 0; size_t smem_optin = 0; int coop = 0;
+    static const DeviceInfo& get() {
+        static thread_local DeviceInfo info;
+        static thread_local int cached_dev = -1;
+        int dev = 0;
+        AB_CUDA(cudaGetDevice(&dev));
+        if (dev != cached_dev) {
+            cudaDeviceProp prop;
+            AB_CUDA(cudaGetDeviceProperties(&prop, dev));
+            info.device = dev; info.sm_count = prop.multiProcessorCount;
+            info.smem_optin = prop.sharedMemPerBlockOptin; info.coop = prop.cooperativeLaunch;
+            cached_dev = dev;
+        }
+        return info;
+    }
+};
+
+} // namespace ab

@@ -1,0 +1,219 @@
+// adelie_b200/csrc/matrix.cuh -- host-side matrix objects that own device-resident data and
+// launch the kernels.  Mirrors the operator set of MatrixNaiveBase
+// (CORE/matrix/matrix_naive_base.hpp:57-143): cmul / ctmul / bmul / btmul / mul / cov / sq_mul.
+//
+// HBM layout of a dense matrix: column-major, leading dimension ld = n rounded up to 32 rows
+// (so every column starts 128-byte aligned and TMA bulk copies of any 32-row-aligned tile are
+// legal); the pad rows are zero.  Every device row-vector (resid, weights, ...) has the same
+// padded length with zero pad.
+#pragma once
+#include "common.cuh"
+#include "dense_kernels.cuh"
+#include "sweep.cuh"
+#include <cuda.h>
+#include <curand_kernel.h>
+
+namespace ab {
+
+// Per-device resources of the fused sweep kernel: LL exchange lines, epoch, abort flag.
+struct SweepContext {
+    DevBuf<dev::LLLine> ll; DevBuf<uint32_t> epoch; DevBuf<int> abort_flag;
+    int ncta_pad = 0; int ll_gs_cap = kGsMax;
+    static SweepContext& get() {
+        static thread_local SweepContext* ctx[64] = {nullptr};
+        int dev = 0; AB_CUDA(cudaGetDevice(&dev));
+        if (!ctx[dev]) {
+            auto* c = new SweepContext();
+            const int sms = DeviceInfo::get().sm_count;
+            c->ncta_pad = (sms + 31) / 32 * 32;
+            c->ll.alloc((size_t)2 * c->ll_gs_cap * c->ncta_pad);
+            c->epoch.alloc(1);
+            uint32_t one = 1;
+            c->epoch.upload(&one, 1);
+            c->abort_flag.alloc(1);
+            AB_CUDA(cudaDeviceSynchronize());
+            ctx[dev] = c;
+        }
+        return *ctx[dev];
+    }
+};
+
+// Inputs of one fused pin solve (all device pointers).
+template <class T>
+struct PinLaunch {
+    T* resid; const T* weights;
+    const GroupMeta* meta; int S; const T* grec;
+    T* screen_beta; int8_t* is_active; int32_t* active_set; PinScalars* sc;
+    double lmda, alpha, tol, newton_tol; long long max_iters; int newton_max_iters; int max_active_size; int intercept;
+    int gs_max; int rec_max;     // largest group size / record length (elements) in the screen set
+};
+
+struct SweepGeometry { int ncta, threads, n_stages, stage_elems, rows_stride, gs_cap, units_base, units_rem; bool smem; size_t smem_bytes; };
+
+template <class T>
+inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max) {
+    const auto& di = DeviceInfo::get();
+    SweepGeometry g{};
+    const int64_t units = n_pad / kRowAlign;
+    int ncta = Configs::sweep_ctas > 0 ? Configs::sweep_ctas
+                                       : (int)std::min<int64_t>(di.sm_count, std::max<int64_t>(1, units / std::max(1, Configs::sweep_min_rows_per_cta / kRowAlign)));
+    ncta = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ncta, units), di.sm_count));
+    g.ncta = ncta;
+    g.threads = std::min(std::max(64, Configs::sweep_threads / 32 * 32), kSweepThreadsMax);
+    g.units_base = (int)(units / ncta); g.units_rem = (int)(units % ncta);
+    g.rows_stride = (g.units_base + (g.units_rem ? 1 : 0)) * kRowAlign;
+    g.gs_cap = std::max(4, (gs_max + 3) / 4 * 4);
+    const int n_cwarps = g.threads / 32 - 1;
+    const size_t fixed = SweepSmem<T>::fixed_bytes(n_cwarps, g.gs_cap) + 2 * sizeof(T) * (size_t)g.rows_stride;
+    const int rec_pad = (rec_max + 3) / 4 * 4;
+    int stage_elems = g.rows_stride * std::max(gs_max, 1) + rec_pad;
+    stage_elems = (stage_elems + 31) / 32 * 32;
+    g.stage_elems = stage_elems;
+    const size_t avail = di.smem_optin > fixed ? di.smem_optin - fixed : 0;
+    int ns = (int)std::min<size_t>(kMaxStages, avail / (sizeof(T) * (size_t)stage_elems));
+    g.smem = (ns >= 2) && !Configs::sweep_force_direct;
+    if (g.smem) {
+        g.n_stages = ns;
+        g.smem_bytes = SweepSmem<T>::total(n_cwarps, g.gs_cap, g.rows_stride, ns, stage_elems);
+    } else {
+        g.n_stages = 1; g.stage_elems = 0;
+        // direct path: all warps are consumers; r / w stay in global memory
+        g.smem_bytes = SweepSmem<T>::fixed_bytes(g.threads / 32, g.gs_cap);
+        g.rows_stride = 0;
+    }
+    return g;
+}
+
+// xorshift-free counter based fill: X[i, j] ~ N(0,1) from Philox(seed, subsequence = column, offset = row)
+template <class T>
+__global__ void fill_normal_kernel(T* X, int64_t ld, int64_t n, int64_t p, unsigned long long seed, int64_t row_offset) {
+    const int64_t j = blockIdx.y;
+    for (int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (int64_t)gridDim.x * blockDim.x * 4) {
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)j, (unsigned long long)(row_offset + i4), &st);
+        const float4 z = curand_normal4(&st);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        for (int k = 0; k < 4 && i4 + k < n; ++k) X[j * ld + i4 + k] = (T)zz[k];
+    }
+}
+
+template <class T>
+struct DenseMatrix {
+    int64_t n = 0, p = 0, ld = 0;
+    DevBuf<T> store; T* X = nullptr;
+    int n_threads = 1;
+    DevBuf<double> part;        // scratch for two-phase reductions
+    DevBuf<T> ones;             // (n_pad,) ones with zero pad
+    cudaStream_t stream = 0;
+
+    DenseMatrix(int64_t n_, int64_t p_) : n(n_), p(p_), ld(pad_rows(n_)) {
+        store.alloc((size_t)ld * p);
+        X = store.p;
+    }
+    int64_t rows() const { return n; }
+    int64_t cols() const { return p; }
+    int64_t n_pad() const { return ld; }
+
+    // host column-major (ldh >= n) or row-major (order == 1, ldh >= p) source
+    void upload(const T* h, int order, int64_t ldh) {
+        if (order == 0) {
+            AB_CUDA(cudaMemcpy2D(X, ld * sizeof(T), h, ldh * sizeof(T), n * sizeof(T), p, cudaMemcpyHostToDevice));
+        } else {
+            // row-major host data: transpose through column chunks on the host side of the copy
+            const int64_t chunk = std::max<int64_t>(1, (64 << 20) / (int64_t)(n * sizeof(T)));
+            std::vector<T> buf((size_t)chunk * n);
+            for (int64_t j0 = 0; j0 < p; j0 += chunk) {
+                const int64_t jc = std::min(chunk, p - j0);
+                for (int64_t i = 0; i < n; ++i)
+                    for (int64_t j = 0; j < jc; ++j) buf[(size_t)j * n + i] = h[i * ldh + j0 + j];
+                AB_CUDA(cudaMemcpy2D(X + j0 * ld, ld * sizeof(T), buf.data(), n * sizeof(T), n * sizeof(T), jc, cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    void download(T* h, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, int64_t ldh) const {
+        AB_CUDA(cudaMemcpy2D(h, ldh * sizeof(T), X + col0 * ld + row0, ld * sizeof(T), nrows * sizeof(T), ncols, cudaMemcpyDeviceToHost));
+    }
+    void fill_normal(unsigned long long seed, int64_t row_offset) {
+        dim3 grid((unsigned)std::min<int64_t>(1024, (n + 1023) / 1024), (unsigned)p);
+        fill_normal_kernel<T><<<grid, 256, 0, stream>>>(X, ld, n, p, seed, row_offset);
+        AB_CUDA(cudaGetLastError());
+    }
+    const T* d_ones() {
+        if (ones.n == 0) {
+            std::vector<T> h(ld, T(0));
+            for (int64_t i = 0; i < n; ++i) h[i] = 1;
+            ones.alloc(ld); ones.upload(h.data(), ld);
+            AB_CUDA(cudaStreamSynchronize(0));
+        }
+        return ones.p;
+    }
+
+    // out[c] = X[:, cols(c)]^T (v o w) for c < q  (cols == nullptr: columns j0 .. j0+q-1); device pointers.
+    // sub / sub_scale: fused epilogue out -= scale * sub  (grad -= resid_sum * X_means, solver_gaussian_naive.hpp:388-391)
+    void d_gemv_t(int64_t j0, const int32_t* cols, int q, const T* v, const T* w, T* out, bool sq = false,
+                  const T* sub = nullptr, const double* sub_scale_ptr = nullptr, double sub_scale = 0) {
+        if (q <= 0) return;
+        const int n_rb = (int)((ld + kGemvRows - 1) / kGemvRows);
+        part.reserve_keep((size_t)n_rb * q, stream);
+        dim3 grid((q + kGemvColsPerCta - 1) / kGemvColsPerCta, n_rb);
+        if (sq) gemv_t_kernel<T, true><<<grid, kGemvThreads, 0, stream>>>(X, ld, ld, j0, cols, q, v, w, part.p);
+        else gemv_t_kernel<T, false><<<grid, kGemvThreads, 0, stream>>>(X, ld, ld, j0, cols, q, v, w, part.p);
+        gemv_t_reduce_kernel<T><<<(q + 255) / 256, 256, 0, stream>>>(part.p, n_rb, q, out, sub, sub_scale_ptr, sub_scale);
+        AB_CUDA(cudaGetLastError());
+    }
+    void d_mul(const T* v, const T* w, T* out, const T* sub = nullptr, const double* sub_scale_ptr = nullptr) {
+        d_gemv_t(0, nullptr, (int)p, v, w, out, false, sub, sub_scale_ptr);
+    }
+    void d_btmul(int64_t j, int q, const T* v_dev, T* out) {
+        constexpr int VN = VecT<T>::N;
+        const int64_t nv = ld / VN;
+        axpy_cols_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(X, ld, ld, j, q, v_dev, out);
+        AB_CUDA(cudaGetLastError());
+    }
+    // Batched Gram: C[out_off + a*gs + b] = X_g^T diag(w or w^2) X_g, device doubles (c_total entries)
+    void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out) {
+        if (n_items <= 0) return;
+        const int sms = DeviceInfo::get().sm_count;
+        int n_rb = std::max(1, std::min(sms, (4 * sms + n_items - 1) / n_items));
+        int rows_per_block = (int)((ld + n_rb - 1) / n_rb);
+        rows_per_block = (rows_per_block + kRowAlign - 1) / kRowAlign * kRowAlign;
+        n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
+        dim3 grid(n_items, n_rb);
+        if (n_rb == 1) {
+            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, C_out, c_total, rows_per_block);
+        } else {
+            part.reserve_keep((size_t)n_rb * c_total, stream);
+            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, part.p, c_total, rows_per_block);
+            sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
+        }
+        AB_CUDA(cudaGetLastError());
+    }
+
+    // The fused pin solve (sweep.cuh).
+    SweepGeometry last_geom{};
+    void pin_solve(const PinLaunch<T>& L) {
+        if (L.gs_max > kGsMax) throw core_error("group size " + std::to_string(L.gs_max) + " exceeds the fused sweep kernel's limit of " + std::to_string(kGsMax) + ".");
+        SweepContext& ctx = SweepContext::get();
+        SweepGeometry g = plan_sweep<T>(ld, L.gs_max, L.rec_max);
+        last_geom = g;
+        PinKernelArgs<T> a{};
+        a.X = X; a.ld = ld; a.n_pad = ld; a.resid = L.resid; a.weights = L.weights;
+        a.meta = L.meta; a.S = L.S; a.grec = L.grec; a.screen_beta = L.screen_beta; a.is_active = L.is_active;
+        a.active_set = L.active_set; a.sc = L.sc;
+        a.ll = ctx.ll.p; a.ll_gs_cap = ctx.ll_gs_cap; a.ncta_pad = ctx.ncta_pad; a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
+        a.lmda = L.lmda; a.alpha = L.alpha; a.tol = L.tol; a.newton_tol = L.newton_tol; a.dbeta_tol = Configs::dbeta_tol;
+        a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
+        a.units_base = g.units_base; a.units_rem = g.units_rem; a.rows_stride = g.rows_stride;
+        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.gs_max = std::max(L.gs_max, 1); a.gs_cap = g.gs_cap;
+        void* kargs[] = {&a};
+        const void* fn = g.smem ? (const void*)pin_solve_kernel<T, true> : (const void*)pin_solve_kernel<T, false>;
+        AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+        if (g.ncta > 1) {
+            AB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g.ncta), dim3(g.threads), kargs, g.smem_bytes, stream));
+        } else {
+            AB_CUDA(cudaLaunchKernel(fn, dim3(1), dim3(g.threads), kargs, g.smem_bytes, stream));
+        }
+    }
+};
+
+} // namespace ab

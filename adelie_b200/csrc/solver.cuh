@@ -1,0 +1,527 @@
+// adelie_b200/csrc/solver.cuh -- host-side path driver.  Control flow of the reference's
+// solve_core (CORE/solver/solver_base.hpp:435-687), Gaussian fit / update_screen_derived /
+// update_solutions (CORE/solver/solver_gaussian_naive.hpp:53-434) and GLM IRLS fit
+// (CORE/solver/solver_glm_naive.hpp:165-546); all O(n) and O(n*p) work runs in CUDA kernels on
+// device-resident data, only O(p)/O(G) bookkeeping (screening, KKT, lambda path) runs on the host.
+#pragma once
+#include "common.cuh"
+#include "matrix.cuh"
+#include "glm.cuh"
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <limits>
+#include <numeric>
+#include <unordered_set>
+
+namespace ab {
+
+// Host symmetric eigendecomposition (cyclic Jacobi, double).  Replaces
+// Eigen::SelfAdjointEigenSolver (solver_gaussian_naive.hpp:113); eigenvalues ascending,
+// eigenvectors in the columns of V (row-major V[r*q + c]).
+inline void host_jacobi_eigh(std::vector<double>& A, int q, std::vector<double>& D, std::vector<double>& V) {
+    V.assign((size_t)q * q, 0.0);
+    for (int i = 0; i < q; ++i) V[(size_t)i * q + i] = 1;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0, diag = 0;
+        for (int a = 0; a < q; ++a) for (int b = 0; b < q; ++b) { const double x = A[(size_t)a * q + b]; if (a == b) diag += x * x; else off += x * x; }
+        if (off <= 1e-34 * (diag + off) || off == 0) break;
+        for (int pi = 0; pi < q - 1; ++pi) for (int qi = pi + 1; qi < q; ++qi) {
+            const double apq = A[(size_t)pi * q + qi];
+            if (apq == 0) continue;
+            const double app = A[(size_t)pi * q + pi], aqq = A[(size_t)qi * q + qi];
+            const double theta = (aqq - app) / (2 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+            const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+            for (int k = 0; k < q; ++k) {
+                const double akp = A[(size_t)k * q + pi], akq = A[(size_t)k * q + qi];
+                A[(size_t)k * q + pi] = c * akp - s * akq; A[(size_t)k * q + qi] = s * akp + c * akq;
+            }
+            for (int k = 0; k < q; ++k) {
+                const double apk = A[(size_t)pi * q + k], aqk = A[(size_t)qi * q + k];
+                A[(size_t)pi * q + k] = c * apk - s * aqk; A[(size_t)qi * q + k] = s * apk + c * aqk;
+            }
+            for (int k = 0; k < q; ++k) {
+                const double vkp = V[(size_t)k * q + pi], vkq = V[(size_t)k * q + qi];
+                V[(size_t)k * q + pi] = c * vkp - s * vkq; V[(size_t)k * q + qi] = s * vkp + c * vkq;
+            }
+        }
+    }
+    std::vector<int> ord(q);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) { return A[(size_t)a * q + a] < A[(size_t)b * q + b]; });
+    std::vector<double> Vs((size_t)q * q);
+    D.resize(q);
+    for (int c = 0; c < q; ++c) {
+        D[c] = A[(size_t)ord[c] * q + ord[c]];
+        for (int k = 0; k < q; ++k) Vs[(size_t)k * q + c] = V[(size_t)k * q + ord[c]];
+    }
+    V.swap(Vs);
+}
+
+// search_pivot (CORE/optimization/search_pivot.hpp:7-62)
+template <class T>
+inline int search_pivot(const std::vector<T>& x, const std::vector<T>& y, std::vector<T>& mses) {
+    const int64_t n = (int64_t)x.size();
+    if (n <= 0) return -1;
+    mses[0] = std::numeric_limits<T>::infinity();
+    if (n == 1) return 0;
+    T y_mean = 0;
+    for (auto v : y) y_mean += v;
+    y_mean /= n;
+    T x_sum = x[0], xsq_sum = x[0] * x[0], y_sum = y[0], yx_sum = y[0] * x[0], min_mse = mses[0];
+    int argmin = 0;
+    for (int64_t i = 1; i < n; ++i) {
+        x_sum += x[i]; xsq_sum += x[i] * x[i]; y_sum += y[i]; yx_sum += y[i] * x[i];
+        const T t_bar = ((i + 1) * x[i] - x_sum) / n;
+        const T var_t = (i + 1) * x[i] * x[i] - 2 * x[i] * x_sum + xsq_sum - n * t_bar * t_bar;
+        const T cov_ty = x[i] * (y_sum - (i + 1) * y_mean) - (yx_sum - y_mean * x_sum);
+        const T b1 = cov_ty / var_t;
+        mses[i] = -b1 * b1 * var_t;
+        if (mses[i] < min_mse) { argmin = (int)i; min_mse = mses[i]; }
+    }
+    return argmin;
+}
+
+struct SparseRow { std::vector<int64_t> idx; std::vector<double> val; };
+
+// Output of one pin solve (the slice of StateGaussianPinNaive the path driver reads back)
+struct PinResult { SparseRow beta; double intercept = 0, rsq = 0; double screen_time = 0, active_time = 0; long long iters = 0; };
+
+template <class T>
+struct PathState {
+    using idx_t = int64_t;
+    // ---------------- static (state_base.hpp:59-95, state_gaussian_naive.hpp, state_glm_naive.hpp)
+    DenseMatrix<T>* X = nullptr;
+    idx_t n = 0, p = 0, G = 0;
+    std::vector<idx_t> groups, group_sizes;
+    T alpha = 1; std::vector<T> penalty;
+    bool is_glm = false;
+    Glm<T>* glm = nullptr;
+    T min_ratio = 1e-2; size_t lmda_path_size = 100, max_screen_size = 0, max_active_size = 0;
+    T pivot_subset_ratio = 0.1; size_t pivot_subset_min = 1; T pivot_slack_ratio = 1.25; int screen_rule = 1;
+    size_t max_iters = 100000; T tol = 1e-7, adev_tol = 0.9, ddev_tol = 0, newton_tol = 1e-12; size_t newton_max_iters = 1000;
+    bool early_exit = true, setup_lmda_max = true, setup_lmda_path = true, intercept = true;
+    size_t n_threads = 1;
+    size_t irls_max_iters = 10000; T irls_tol = 1e-7; bool setup_loss_null = true;
+    // ---------------- dynamic
+    T lmda_max = -1; std::vector<T> lmda_path;
+    std::unordered_set<idx_t> screen_hashset;
+    std::vector<idx_t> screen_set, screen_begins;
+    std::vector<T> screen_beta; std::vector<int8_t> screen_is_active;
+    size_t active_set_size = 0; std::vector<idx_t> active_set;
+    T lmda = std::numeric_limits<T>::infinity();
+    std::vector<T> grad, abs_grad;
+    // gaussian
+    std::vector<T> X_means; T y_mean = 0, y_var = 0, loss_null = 0, loss_full = 0, resid_sum = 0, rsq = 0;
+    std::vector<T> screen_X_means, screen_vars; std::vector<std::vector<T>> screen_transforms;
+    // glm
+    T beta0 = 0;
+    // ---------------- outputs
+    std::vector<SparseRow> betas; std::vector<T> intercepts, devs, lmdas;
+    std::vector<double> benchmark_screen, benchmark_fit_screen, benchmark_fit_active, benchmark_kkt, benchmark_invariance;
+    std::vector<int> n_valid_solutions, active_sizes, screen_sizes;
+    long long n_sweeps = 0, n_group_updates = 0, n_irls = 0, n_pin_solves = 0, n_kernel_launches = 0;
+    double sweep_bytes = 0;          // algorithmic HBM bytes of all sweeps: s*n*sum gs + 3*s*n per sweep (estimated)
+    double time_sweep_kernel = 0;    // CUDA-event time spent inside the fused kernel (s)
+    // ---------------- device
+    DevBuf<T> d_weights, d_weights_sqrt, d_resid, d_resid_prev, d_X_means, d_grad;
+    DevBuf<T> d_offsets, d_eta, d_eta_prev, d_glm_resid_prev, d_hess, d_irls_w, d_irls_wsqrt, d_irls_y, d_irls_resid;
+    DevBuf<T> d_glm_X_means;     // (p,) irls-weighted means on screen columns
+    DevBuf<GroupMeta> d_meta; DevBuf<T> d_grec, d_screen_beta; DevBuf<int8_t> d_is_active; DevBuf<int32_t> d_active_set;
+    DevBuf<PinScalars> d_sc; DevBuf<CovItem> d_cov_items; DevBuf<double> d_cov_out; DevBuf<int32_t> d_cols; DevBuf<T> d_tmp;
+    DevBuf<double> d_scal;       // small scalar scratch (device-side sub_scale etc.)
+    std::vector<GroupMeta> h_meta; std::vector<T> h_grec; size_t grec_uploaded = 0, meta_uploaded = 0;
+    int gs_max_screen = 1, rec_max_screen = 4;
+    PinnedBuf<PinScalars> h_sc;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::function<bool()> exit_cond;          // user early-exit callback
+    std::function<void()> check_interrupt;    // PyErr_CheckSignals hook
+
+    ~PathState() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); }
+
+    // ------------------------------------------------------------------ validation + init
+    // state_base.ipp:10-116 and state_gaussian_naive.ipp:9-28
+    void validate_and_init() {
+        if ((idx_t)group_sizes.size() != G) throw core_error("group_sizes must be (G,) where groups is (G,).");
+        if ((idx_t)penalty.size() != G) throw core_error("penalty must be (G,) where groups is (G,).");
+        if (alpha < 0 || alpha > 1) throw core_error("alpha must be in [0,1].");
+        if (tol < 0) throw core_error("tol must be >= 0.");
+        if (adev_tol < 0 || adev_tol > 1) throw core_error("adev_tol must be in [0,1].");
+        if (ddev_tol < 0 || ddev_tol > 1) throw core_error("ddev_tol must be in [0,1].");
+        if (newton_tol < 0) throw core_error("newton_tol must be >= 0.");
+        if (n_threads < 1) throw core_error("n_threads must be >= 1.");
+        if (min_ratio < 0 || min_ratio > 1) throw core_error("min_ratio must be in [0,1].");
+        if (pivot_subset_ratio <= 0 || pivot_subset_ratio > 1) throw core_error("pivot_subset_ratio must be in (0,1].");
+        if (pivot_subset_min < 1) throw core_error("pivot_subset_min must be >= 1.");
+        if (pivot_slack_ratio < 0) throw core_error("pivot_slack_ratio must be >= 0.");
+        if (screen_set.size() != screen_is_active.size()) throw core_error("screen_is_active must be (s,) where screen_set is (s,).");
+        if (screen_beta.size() < screen_set.size())
+            throw core_error("screen_beta must be (bs,) where bs >= s and screen_set is (s,). It is likely screen_beta has been initialized incorrectly. ");
+        if (active_set_size > (size_t)G) throw core_error("active_set_size must be <= G where groups is (G,).");
+        if ((idx_t)active_set.size() != G) throw core_error("active_set must be (G,) where groups is (G,).");
+        if ((idx_t)grad.size() != groups[G - 1] + group_sizes[G - 1])
+            throw core_error("grad.size() != groups[G-1] + group_sizes[G-1]. It is likely either grad has the wrong shape, or groups/group_sizes have been initialized incorrectly.");
+        if ((idx_t)grad.size() != p) throw core_error("grad must be (p,) where X is (n, p).");
+        abs_grad.assign(G, 0);
+        AB_CUDA(cudaEventCreate(&ev0)); AB_CUDA(cudaEventCreate(&ev1));
+        d_sc.alloc(1); h_sc.alloc(1); d_scal.alloc(8);
+        d_active_set.alloc(G);
+        update_screen_derived_base();
+        update_abs_grad(lmda);
+        if (!is_glm) {
+            loss_null = T(-0.5) * y_mean * y_mean;                  // state_gaussian_naive.hpp:143-144
+            loss_full = T(-0.5) * y_var + loss_null;
+            update_screen_derived_gaussian();
+        }
+    }
+
+    // ------------------------------------------------------------------ solver_base.hpp:20-110 (constraints == nullptr)
+    void update_abs_grad(T lmda_) {
+        for (size_t ss = 0; ss < screen_set.size(); ++ss) {
+            const idx_t i = screen_set[ss], b = screen_begins[ss], k = groups[i], sz = group_sizes[i];
+            const T regul = ((1 - alpha) * lmda_) * penalty[i];
+            T a = 0;
+            for (idx_t c = 0; c < sz; ++c) { const T e = grad[k + c] - regul * screen_beta[b + c]; a += e * e; }
+            abs_grad[i] = std::sqrt(a);
+        }
+        for (idx_t i = 0; i < G; ++i) {
+            if (screen_hashset.count(i)) continue;
+            const idx_t k = groups[i], sz = group_sizes[i];
+            T a = 0;
+            for (idx_t c = 0; c < sz; ++c) a += grad[k + c] * grad[k + c];
+            abs_grad[i] = std::sqrt(a);
+        }
+    }
+
+    // solver_base.hpp:120-153
+    void update_screen_derived_base() {
+        const size_t old = screen_begins.size();
+        for (size_t i = old; i < screen_set.size(); ++i) screen_hashset.insert(screen_set[i]);
+        size_t vs = (old == 0) ? 0 : (screen_begins.back() + group_sizes[screen_set[old - 1]]);
+        for (size_t i = old; i < screen_set.size(); ++i) { screen_begins.push_back(vs); vs += group_sizes[screen_set[i]]; }
+        screen_beta.resize(vs, 0);
+        screen_is_active.resize(screen_set.size(), 0);
+    }
+
+    // Computes (A, V, xm) for screen positions [begin, end) from the weighted Gram of each group
+    // (solver_gaussian_naive.hpp:53-125): device batched Gram -> host Jacobi -> packed records.
+    // `w` device weights (not sqrt), `xmeans_host(col)` gives the weighted column mean.
+    template <class MeanF>
+    void compute_screen_records(size_t begin, size_t end, const T* d_w, MeanF xmean,
+                                std::vector<T>& sXm, std::vector<T>& sv, std::vector<std::vector<T>>& st,
+                                std::vector<GroupMeta>& meta, std::vector<T>& grec)
+    {
+        const size_t S = screen_set.size();
+        const size_t vs = S ? (screen_begins.back() + group_sizes[screen_set.back()]) : 0;
+        sXm.resize(vs); st.resize(S); sv.resize(vs, 0);
+        if (begin >= end) return;
+        std::vector<CovItem> items; int64_t c_total = 0;
+        for (size_t i = begin; i < end; ++i) {
+            const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g];
+            items.push_back(CovItem{(int32_t)groups[g], gs, c_total});
+            c_total += (int64_t)gs * gs;
+        }
+        d_cov_items.reserve_keep(items.size()); d_cov_out.reserve_keep(c_total);
+        d_cov_items.upload(items.data(), items.size());
+        X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p);
+        std::vector<double> C(c_total);
+        d_cov_out.download(C.data(), c_total);
+        AB_CUDA(cudaStreamSynchronize(0));
+        n_kernel_launches += 2;
+        meta.resize(S);
+        std::vector<double> Cg, D, V;
+        for (size_t i = begin; i < end; ++i) {
+            const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g]; const idx_t sb = screen_begins[i];
+            const CovItem& it = items[i - begin];
+            for (int c = 0; c < gs; ++c) sXm[sb + c] = xmean(groups[g] + c);
+            Cg.assign(C.begin() + it.out_off, C.begin() + it.out_off + (size_t)gs * gs);
+            if (intercept)
+                for (int a = 0; a < gs; ++a) for (int b = 0; b < gs; ++b) Cg[(size_t)a * gs + b] -= (double)sXm[sb + a] * (double)sXm[sb + b];
+            if (gs == 1) {
+                st[i].assign(1, T(1));
+                sv[sb] = std::max<T>((T)Cg[0], 0);
+            } else {
+                host_jacobi_eigh(Cg, gs, D, V);
+                st[i].resize((size_t)gs * gs);
+                for (size_t k = 0; k < (size_t)gs * gs; ++k) st[i][k] = (T)V[k];
+                for (int c = 0; c < gs; ++c) { const T d = (T)D[c]; sv[sb + c] = d * T(d >= 0); }      // :122
+            }
+            // packed record [A | xm | V], 16-byte aligned
+            const size_t off = (grec.size() + 3) / 4 * 4;
+            const int rec = gs * (gs + 2);
+            const int rec_pad = (rec + 3) / 4 * 4;
+            grec.resize(off + rec_pad, T(0));
+            for (int c = 0; c < gs; ++c) { grec[off + c] = sv[sb + c]; grec[off + gs + c] = sXm[sb + c]; }
+            for (int k = 0; k < gs * gs; ++k) grec[off + 2 * gs + k] = st[i][k];
+            GroupMeta m{};
+            m.col = (int32_t)groups[g]; m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
+            m.pen = (double)penalty[g];
+            meta[i] = m;
+            gs_max_screen = std::max(gs_max_screen, gs); rec_max_screen = std::max(rec_max_screen, rec_pad);
+        }
+    }
+
+    // solver_gaussian_naive.hpp:134-176 (new screen positions only; weights are static)
+    void update_screen_derived_gaussian() {
+        const size_t old = screen_transforms.size();
+        update_screen_derived_base();
+        compute_screen_records(old, screen_set.size(), d_weights.p, [&](idx_t c) { return X_means[c]; },
+                               screen_X_means, screen_vars, screen_transforms, h_meta, h_grec);
+    }
+
+    void upload_screen_tables(const std::vector<GroupMeta>& meta, const std::vector<T>& grec, bool full) {
+        d_meta.reserve_keep(meta.size()); d_grec.reserve_keep(grec.size() + 4);
+        const size_t m0 = full ? 0 : meta_uploaded, g0 = full ? 0 : grec_uploaded;
+        if (meta.size() > m0) d_meta.upload(meta.data() + m0, meta.size() - m0, m0);
+        if (grec.size() > g0) d_grec.upload(grec.data() + g0, grec.size() - g0, g0);
+        if (!full) { meta_uploaded = meta.size(); grec_uploaded = grec.size(); }
+    }
+
+    // ------------------------------------------------------------------ the fused pin solve
+    // Runs pin::naive::solve (solver_gaussian_pin_naive.hpp:223-401) for one lambda on the device.
+    PinResult run_pin(T* d_r, const T* d_w, T lmda_, T tol_pin, T y_mean_, T& rsq_io, T& resid_sum_io) {
+        const size_t S = screen_set.size();
+        d_screen_beta.reserve_keep(screen_beta.size() + 4); d_is_active.reserve_keep(S + 4);
+        d_screen_beta.upload(screen_beta.data(), screen_beta.size());
+        d_is_active.upload(screen_is_active.data(), S);
+        std::vector<int32_t> act32(active_set_size);
+        for (size_t i = 0; i < active_set_size; ++i) act32[i] = (int32_t)active_set[i];
+        d_active_set.upload(act32.data(), active_set_size);
+        PinScalars sc{};
+        sc.rsq = (double)rsq_io; sc.resid_sum = (double)resid_sum_io; sc.active_set_size = (int)active_set_size;
+        *h_sc.p = sc;
+        d_sc.upload(h_sc.p, 1);
+        PinLaunch<T> L{};
+        L.resid = d_r; L.weights = d_w; L.meta = d_meta.p; L.S = (int)S; L.grec = d_grec.p;
+        L.screen_beta = d_screen_beta.p; L.is_active = d_is_active.p; L.active_set = d_active_set.p; L.sc = d_sc.p;
+        L.lmda = (double)lmda_; L.alpha = (double)alpha; L.tol = (double)tol_pin; L.newton_tol = (double)newton_tol;
+        L.max_iters = (long long)max_iters; L.newton_max_iters = (int)std::min<size_t>(newton_max_iters, 1u << 30);
+        L.max_active_size = (int)std::min<size_t>(max_active_size, (size_t)G); L.intercept = intercept ? 1 : 0;
+        L.gs_max = gs_max_screen; L.rec_max = rec_max_screen;
+        if (check_interrupt) check_interrupt();
+        AB_CUDA(cudaEventRecord(ev0, 0));
+        X->pin_solve(L);
+        AB_CUDA(cudaEventRecord(ev1, 0));
+        d_sc.download(h_sc.p, 1);
+        const size_t old_active = active_set_size;
+        d_screen_beta.download(screen_beta.data(), screen_beta.size());
+        d_is_active.download(screen_is_active.data(), S);
+        AB_CUDA(cudaStreamSynchronize(0));
+        ++n_pin_solves; ++n_kernel_launches;
+        float ms = 0; AB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        time_sweep_kernel += ms * 1e-3;
+        sc = *h_sc.p;
+        if (sc.error) {
+            if (sc.error == kErrAbort) {
+                int zero = 0; SweepContext::get().abort_flag.upload(&zero, 1); AB_CUDA(cudaStreamSynchronize(0));
+                throw solver_error("fused sweep kernel aborted (inter-CTA exchange timed out).");
+            }
+            if (sc.error == kErrMaxCds) throw solver_error("max coordinate descents reached at lambda index: 0.");
+            if (sc.error == kErrMaxActive) throw solver_error("Maximum number of active groups reached.");
+            if (sc.error == kErrNewton) throw solver_error("Newton-ABS max iterations reached! Try increasing newton_max_iters.");
+            throw solver_error("unknown device error.");
+        }
+        active_set_size = sc.active_set_size;
+        if (active_set_size > old_active) {
+            std::vector<int32_t> nw(active_set_size - old_active);
+            d_active_set.download(nw.data(), nw.size(), old_active);
+            AB_CUDA(cudaStreamSynchronize(0));
+            for (size_t i = 0; i < nw.size(); ++i) active_set[old_active + i] = nw[i];
+        }
+        rsq_io = (T)sc.rsq; resid_sum_io = (T)sc.resid_sum;
+        n_sweeps += sc.iters; n_group_updates += sc.n_group_updates;
+        PinResult R;
+        R.iters = sc.iters; R.rsq = sc.rsq;
+        R.active_time = ms * 1e-3; R.screen_time = 0;   // one fused launch: not separable without extra syncs
+        // active_order + sparsify_active_beta (solver_gaussian_pin_naive.hpp:360-391, pin_base.hpp:58-98)
+        std::vector<size_t> order(active_set_size);
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](size_t i, size_t j) {
+            return groups[screen_set[active_set[i]]] < groups[screen_set[active_set[j]]];
+        });
+        for (size_t i = 0; i < order.size(); ++i) {
+            const idx_t ss = active_set[order[i]], g = screen_set[ss], gs = group_sizes[g];
+            for (idx_t c = 0; c < gs; ++c) { R.beta.idx.push_back(groups[g] + c); R.beta.val.push_back((double)screen_beta[screen_begins[ss] + c]); }
+        }
+        R.intercept = (intercept ? 1.0 : 0.0) * ((double)y_mean_ + sc.resid_sum);      // :392
+        return R;
+    }
+
+    // ------------------------------------------------------------------ Gaussian fit (solver_gaussian_naive.hpp:215-349)
+    PinResult fit_gaussian(T lmda_) {
+        const int64_t np = X->n_pad();
+        AB_CUDA(cudaMemcpyAsync(d_resid_prev.p, d_resid.p, np * sizeof(T), cudaMemcpyDeviceToDevice, 0));
+        std::vector<T> beta_prev = screen_beta; std::vector<int8_t> act_prev = screen_is_active;
+        upload_screen_tables(h_meta, h_grec, false);
+        try {
+            return run_pin(d_resid.p, d_weights.p, lmda_, tol * y_var, y_mean, rsq, resid_sum);
+        } catch (...) {
+            std::swap(d_resid.p, d_resid_prev.p);
+            screen_beta.swap(beta_prev); screen_is_active.swap(act_prev);
+            throw;
+        }
+    }
+
+    // ------------------------------------------------------------------ GLM pieces (solver_glm_naive.hpp)
+    void update_loss_null();              // defined in solver_glm.cuh
+    PinResult fit_glm(T lmda_);           // defined in solver_glm.cuh
+
+    PinResult fit(T lmda_) { return is_glm ? fit_glm(lmda_) : fit_gaussian(lmda_); }
+
+    // update_invariance (solver_gaussian_naive.hpp:377-393 / solver_glm_naive.hpp:495-503)
+    void update_invariance(T lmda_) {
+        lmda = lmda_;
+        if (is_glm) {
+            X->d_mul(d_resid.p, X->d_ones(), d_grad.p);
+        } else {
+            // grad = X^T (w o r) - resid_sum * X_means, epilogue fused into the reduction kernel
+            const double rs = (double)resid_sum;
+            X->d_gemv_t(0, nullptr, (int)p, d_resid.p, d_weights.p, d_grad.p, false,
+                        intercept ? d_X_means.p : nullptr, nullptr, rs);
+        }
+        d_grad.download(grad.data(), p);
+        AB_CUDA(cudaStreamSynchronize(0));
+        n_kernel_launches += 2;
+        update_abs_grad(lmda_);
+    }
+
+    void update_solutions(PinResult& pr, T lmda_) {
+        betas.emplace_back(std::move(pr.beta));
+        intercepts.push_back((T)pr.intercept);
+        lmdas.push_back(lmda_);
+        if (is_glm) {
+            const T loss = glm->loss(d_eta.p);
+            devs.push_back((loss_null - loss) / (loss_null - loss_full));       // solver_glm_naive.hpp:153-157
+        } else {
+            devs.push_back((T)pr.rsq / y_var);                                  // solver_gaussian_naive.hpp:205-206
+        }
+    }
+
+    // screen (solver_base.hpp:273-403)
+    void screen(T lmda_next, bool all_kkt_passed, int n_new_active) {
+        const int old_size = (int)screen_set.size();
+        auto is_screen = [&](idx_t i) { return screen_hashset.count(i) > 0; };
+        if (screen_rule == 0) {
+            const T strong = (2 * lmda_next - lmda) * alpha;
+            for (idx_t i = 0; i < G; ++i) { if (is_screen(i)) continue; if (abs_grad[i] > strong * penalty[i]) screen_set.push_back(i); }
+        } else if (screen_rule == 1) {
+            if (n_new_active) {
+                std::vector<idx_t> order(G);
+                std::iota(order.begin(), order.end(), 0);
+                std::vector<T> wts(G);
+                for (idx_t i = 0; i < G; ++i) wts[i] = (penalty[i] <= 0) ? alpha * lmda : std::min(abs_grad[i] / penalty[i], alpha * lmda);
+                std::sort(order.begin(), order.end(), [&](idx_t i, idx_t j) { return wts[i] < wts[j]; });
+                const int subset_size = std::min<int>(std::max<int>((int)(old_size * (1 + pivot_subset_ratio)), (int)pivot_subset_min), (int)G);
+                std::vector<T> ws(subset_size), mses(subset_size), ind(subset_size);
+                for (int i = 0; i < subset_size; ++i) { ws[i] = wts[order[G - subset_size + i]]; ind[i] = (T)i; }
+                const int pivot_idx = search_pivot(ind, ws, mses);
+                const int full_pivot_idx = (int)G - subset_size + pivot_idx;
+                for (int ii = (int)G - 1; ii >= full_pivot_idx; --ii) { const idx_t i = order[ii]; if (is_screen(i)) continue; screen_set.push_back(i); }
+                int count = 0;
+                for (int ii = full_pivot_idx - 1; ii >= 0; --ii) {
+                    if (count >= pivot_slack_ratio * n_new_active) break;
+                    const idx_t i = order[ii];
+                    if (is_screen(i)) continue;
+                    screen_set.push_back(i); ++count;
+                }
+            }
+            if (((int)screen_set.size() == old_size) && !all_kkt_passed) {
+                for (idx_t i = 0; i < G; ++i) { if (is_screen(i)) continue; if (abs_grad[i] > lmda_next * penalty[i] * alpha) screen_set.push_back(i); }
+            }
+        } else throw solver_error("Unknown screen rule!");
+        if (screen_set.size() > max_screen_size) { screen_set.resize(old_size); throw solver_error("maximum screen set size reached."); }
+    }
+
+    bool kkt(T lmda_) {                                                         // solver_base.hpp:408-433
+        for (idx_t k = 0; k < G; ++k) { if (screen_hashset.count(k)) continue; if (abs_grad[k] > lmda_ * alpha * penalty[k]) return false; }
+        return true;
+    }
+
+    bool early_exit_f() {                                                       // solver_base.hpp:241-263 + user exit_cond
+        bool r = false;
+        if (early_exit && !devs.empty()) {
+            const T u = devs.back();
+            if (u >= adev_tol) r = true;
+            else if (devs.size() >= 2 && std::abs(u - devs[devs.size() - 2]) < ddev_tol) r = true;
+        }
+        return r || (exit_cond && exit_cond());
+    }
+
+    void screen_f(T lmda_, bool kkt_passed, int n_new_active) {
+        screen(lmda_, kkt_passed, n_new_active);
+        if (is_glm) update_screen_derived_base();
+        else update_screen_derived_gaussian();
+    }
+
+    // ------------------------------------------------------------------ solve_core (solver_base.hpp:435-687)
+    void solve() {
+        if (screen_set.size() > max_screen_size) throw solver_error("maximum screen set size reached.");
+        if (is_glm && setup_loss_null) update_loss_null();
+        if (setup_lmda_max) {
+            T pmax = penalty[0];
+            for (auto v : penalty) pmax = std::max(pmax, v);
+            const T large_lmda = T(1e-3 * std::numeric_limits<T>::max() / std::max<T>(1, pmax));
+            fit(large_lmda);
+            update_invariance(large_lmda);
+            const T factor = (alpha <= 0) ? T(1e-3) : alpha;                    // solver/utils.hpp:6-23
+            T m = -std::numeric_limits<T>::infinity();
+            for (idx_t i = 0; i < G; ++i) m = std::max<T>(m, (penalty[i] <= 0.0) ? T(0.0) : abs_grad[i] / penalty[i]);
+            lmda_max = m / factor;
+        }
+        if (setup_lmda_path) {
+            if (lmda_path_size <= 0) return;
+            lmda_path.resize(lmda_path_size);
+            const size_t L = lmda_path_size;
+            if (L > 1) {                                                        // solver/utils.hpp:25-41
+                const T log_factor = std::log(min_ratio) / (L - 1);
+                for (size_t i = 0; i < L; ++i) lmda_path[i] = lmda_max * std::exp(log_factor * T(i));
+            }
+            lmda_path[0] = lmda_max;
+        }
+        size_t large_sz = 0;
+        while (large_sz < lmda_path.size() && !(lmda_path[large_sz] <= lmda_max)) ++large_sz;
+        if (large_sz || setup_lmda_max) {
+            std::vector<T> large(lmda_path.begin(), lmda_path.begin() + large_sz);
+            large.push_back(lmda_max);
+            for (size_t i = 0; i < large.size(); ++i) {
+                PinResult pr = fit(large[i]);
+                if (i + 1 < large.size()) {
+                    update_solutions(pr, large[i]);
+                    if (early_exit_f()) return;
+                } else update_invariance(large[i]);
+            }
+        }
+        size_t idx = large_sz;
+        int current_active = (int)active_set_size;
+        bool kkt_passed = true;
+        int n_new_active = 0;
+        while (idx < lmda_path.size()) {
+            const T lmda_curr = lmda_path[idx];
+            while (1) {
+                double t0 = now_s();
+                screen_f(lmda_curr, kkt_passed, n_new_active);
+                benchmark_screen.push_back(now_s() - t0);
+                PinResult pr = fit(lmda_curr);
+                benchmark_fit_screen.push_back(pr.screen_time);
+                benchmark_fit_active.push_back(pr.active_time);
+                t0 = now_s();
+                update_invariance(lmda_curr);
+                benchmark_invariance.push_back(now_s() - t0);
+                t0 = now_s();
+                kkt_passed = kkt(lmda_curr);
+                n_valid_solutions.push_back(kkt_passed);
+                idx += kkt_passed;
+                if (kkt_passed) update_solutions(pr, lmda_curr);
+                benchmark_kkt.push_back(now_s() - t0);
+                if (kkt_passed) { active_sizes.push_back((int)active_set_size); screen_sizes.push_back((int)screen_set.size()); }
+                n_new_active = kkt_passed ? (active_sizes.back() - current_active) : n_new_active;
+                current_active = kkt_passed ? active_sizes.back() : current_active;
+                if (kkt_passed) break;
+            }
+            if (early_exit_f()) break;
+        }
+    }
+};
+
+} // namespace ab

@@ -1,0 +1,65 @@
+"""Synthetic data generators with the semantics of ``adelie.data`` (reference: adelie/data.py:13-219):
+``np.random.seed(seed)``; X ~ N(0,1) column-major; beta* ~ N(0,1) on a random (1-sparsity) support;
+gaussian y = eta + ||beta*|| N(0,1)/sqrt(snr); binomial y ~ Bernoulli(sigmoid(eta/||beta*||))."""
+import numpy as np
+
+from . import glm as _glm
+
+
+def _sample_y(glm, eta, beta, rho=0, snr=1):
+    n, K = eta.shape
+    is_multi = "multi" in glm
+    if not is_multi and K > 1:
+        eta = eta[:, 0][:, None]
+        K = 1
+    if "gaussian" in glm:
+        signal_scale = np.sqrt(rho * np.sum(beta) ** 2 + (1 - rho) * np.sum(beta ** 2))
+        noise_scale = signal_scale / np.sqrt(snr)
+        y = eta + noise_scale * np.random.normal(0, 1, eta.shape)
+        if is_multi:
+            return _glm.multigaussian(y=y)
+        return _glm.gaussian(y=y.ravel())
+    if glm == "binomial":
+        scale = np.sqrt(rho * np.sum(beta) ** 2 + (1 - rho) * np.sum(beta ** 2))
+        eta = eta / max(scale, 1e-300)
+        mu = 1 / (1 + np.exp(-eta))
+        y = np.random.binomial(1, mu).astype(np.float64)
+        return _glm.binomial(y=y.ravel())
+    if glm == "cox":
+        scale = np.sqrt(rho * np.sum(beta) ** 2 + (1 - rho) * np.sum(beta ** 2))
+        eta = (eta / max(scale, 1e-300)).ravel()
+        s = np.random.exponential(1, n)
+        t = s + 1 + np.random.exponential(np.exp(-eta))
+        c = s + 1 + np.random.exponential(1, n)
+        d = (t <= c).astype(np.float64)
+        t = np.minimum(t, c)
+        return _glm.cox(start=s, stop=t, status=d)
+    raise RuntimeError(f"unsupported glm {glm}")
+
+
+def dense(n, p, G, *, K=1, glm="gaussian", equal_groups=False, rho=0, sparsity=0.95, zero_penalty=0, snr=1, seed=0):
+    """Dense dataset (semantics of adelie/data.py:84-219)."""
+    assert n >= 1 and p >= 1 and G >= 1
+    np.random.seed(seed)
+    if equal_groups:
+        groups = (p // G) * np.arange(G)
+    else:
+        groups = np.concatenate([[0], np.random.choice(np.arange(1, p), size=G - 1, replace=False)])
+        groups = np.sort(groups).astype(int)
+    group_sizes = np.concatenate([groups, [p]], dtype=int)
+    group_sizes = group_sizes[1:] - group_sizes[:-1]
+    penalty = np.sqrt(group_sizes)
+    penalty[np.random.choice(G, int(zero_penalty * G), replace=False)] = 0
+    penalty /= np.linalg.norm(penalty) / np.sqrt(p)
+    X = np.random.normal(0, 1, (n, p))
+    Z = np.random.normal(0, 1, n)
+    X = np.sqrt(rho) * Z[:, None] + np.sqrt(1 - rho) * X
+    X = np.asfortranarray(X)
+    beta = np.random.normal(0, 1, (p, K))
+    beta_zero_indices = np.random.choice(p, int(sparsity * p), replace=False)
+    beta_nnz_indices = np.array(list(set(np.arange(p)) - set(beta_zero_indices)))
+    X_sub = X[:, beta_nnz_indices]
+    beta_sub = beta[beta_nnz_indices]
+    eta = X_sub @ beta_sub
+    glm_obj = _sample_y(glm=glm, eta=eta, beta=beta_sub, rho=rho, snr=snr)
+    return {"X": X, "glm": glm_obj, "groups": groups, "group_sizes": group_sizes, "penalty": penalty}

@@ -1,0 +1,250 @@
+"""Matrix objects (reference: adelie/matrix.py; operator set of MatrixNaiveBase,
+adelie/src/py_matrix.cpp:832-1071 = CORE/matrix/matrix_naive_base.hpp:57-143).
+
+A matrix keeps a reference to the host array it was built from and owns a device-resident copy
+(column-major, rows padded to 32, see csrc/matrix.cuh); the copy is made once, on first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+from scipy.sparse import csc_matrix, csr_matrix
+
+from . import _lib
+
+
+def _to_dtype(mat):
+    return mat.dtype
+
+
+class MatrixNaiveTranspose:
+    """adelie/matrix.py:52-80"""
+    def __init__(self, mat):
+        self._mat = mat
+        self.T = mat
+
+    def __matmul__(self, v):
+        dtype = _to_dtype(self._mat)
+        v = np.asarray(v, dtype=dtype)
+        if (len(v.shape) <= 0) or (len(v.shape) > 2):
+            raise ValueError("Right argument must be either 1 or 2-dimensional.")
+        n, p = self._mat.shape
+        ones = np.ones(n, dtype=dtype)
+        if len(v.shape) == 1:
+            out = np.empty(p, dtype=dtype)
+            self._mat.mul(np.ascontiguousarray(v), ones, out)
+            return out
+        v = np.asfortranarray(v)
+        out = np.empty((v.shape[1], p), dtype=dtype)
+        for i in range(out.shape[0]):
+            self._mat.mul(np.ascontiguousarray(v[:, i]), ones, out[i])
+        return out.T
+
+
+class MatrixNaiveBase:
+    """Python-side sugar shared by every naive matrix (adelie/matrix.py:83-190)."""
+    def __init__(self, n_threads=1):
+        if n_threads < 1:
+            raise RuntimeError("adelie_core: n_threads must be >= 1.")
+        self._n_threads = n_threads
+        self.T = MatrixNaiveTranspose(self)
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def shape(self):
+        return (self.rows(), self.cols())
+
+    def __matmul__(self, v):
+        dtype = _to_dtype(self)
+        n, p = self.shape
+        if isinstance(v, (csr_matrix, csc_matrix)):
+            v = v.tocsr().transpose().tocsr()
+            out = np.empty((v.shape[0], n), dtype=dtype)
+            self.sp_tmul(v, out)
+            return out.T
+        v = np.asarray(v, dtype=dtype)
+        if (len(v.shape) <= 0) or (len(v.shape) > 2):
+            raise ValueError("Right argument must be either 1 or 2-dimensional.")
+        if len(v.shape) == 1:
+            out = np.zeros(n, dtype=dtype)
+            self.btmul(0, p, np.ascontiguousarray(v), out)
+            return out
+        v = np.asfortranarray(v)
+        out = np.zeros((v.shape[1], n), dtype=dtype)
+        for i in range(out.shape[0]):
+            self.btmul(0, p, np.ascontiguousarray(v[:, i]), out[i])
+        return out.T
+
+
+class _DeviceMatrix(MatrixNaiveBase):
+    """Host-pointer operator front-end over an ``ab_matrix`` handle."""
+    def __init__(self, dtype, n, p, n_threads):
+        MatrixNaiveBase.__init__(self, n_threads)
+        self.dtype = np.dtype(dtype).type
+        self._n, self._p = int(n), int(p)
+        self._handle = None
+
+    def rows(self):
+        return self._n
+
+    def cols(self):
+        return self._p
+
+    def _make_handle(self):
+        raise NotImplementedError
+
+    def _core(self):
+        if self._handle is None:
+            self._handle = self._make_handle()
+        return self._handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.load().ab_matrix_free(self._handle)
+        except Exception:
+            pass
+
+    def _vec(self, a, size, name, fn):
+        if not isinstance(a, np.ndarray) or a.dtype != self.dtype or a.ndim != 1 or not a.flags.c_contiguous:
+            raise TypeError(f"{fn}(): {name} must be a 1-D contiguous array of dtype {np.dtype(self.dtype).name}")
+        return a
+
+    # ---- operators (semantics of matrix_naive_base.hpp:57-143; shape errors as :148-271)
+    def cmul(self, j, v, weights):
+        n, p = self.shape
+        v = self._vec(v, n, "v", "cmul"); weights = self._vec(weights, n, "weights", "cmul")
+        if j < 0 or j >= p or v.size != n or weights.size != n:
+            raise RuntimeError(f"adelie_core: cmul() is given inconsistent inputs! (j={j}, v={v.size}, w={weights.size}, r={n}, c={p})")
+        out = C.c_double()
+        _lib.check(_lib.load().ab_matrix_cmul(self._core(), j, _lib.ptr(v), _lib.ptr(weights), C.byref(out)))
+        return self.dtype(out.value)
+
+    cmul_safe = cmul
+
+    def ctmul(self, j, v, out):
+        n, p = self.shape
+        out = self._vec(out, n, "out", "ctmul")
+        if j < 0 or j >= p or out.size != n:
+            raise RuntimeError(f"adelie_core: ctmul() is given inconsistent inputs! (j={j}, o={out.size}, r={n}, c={p})")
+        _lib.check(_lib.load().ab_matrix_ctmul(self._core(), j, float(v), _lib.ptr(out)))
+
+    def bmul(self, j, q, v, weights, out):
+        n, p = self.shape
+        v = self._vec(v, n, "v", "bmul"); weights = self._vec(weights, n, "weights", "bmul"); out = self._vec(out, q, "out", "bmul")
+        if j < 0 or j > p - q or v.size != n or weights.size != n or out.size != q:
+            raise RuntimeError(f"adelie_core: bmul() is given inconsistent inputs! (j={j}, q={q}, v={v.size}, w={weights.size}, o={out.size}, r={n}, c={p})")
+        _lib.check(_lib.load().ab_matrix_bmul(self._core(), j, q, _lib.ptr(v), _lib.ptr(weights), _lib.ptr(out)))
+
+    bmul_safe = bmul
+
+    def btmul(self, j, q, v, out):
+        n, p = self.shape
+        v = self._vec(v, q, "v", "btmul"); out = self._vec(out, n, "out", "btmul")
+        if j < 0 or j > p - q or v.size != q or out.size != n:
+            raise RuntimeError(f"adelie_core: btmul() is given inconsistent inputs! (j={j}, q={q}, v={v.size}, o={out.size}, r={n}, c={p})")
+        _lib.check(_lib.load().ab_matrix_btmul(self._core(), j, q, _lib.ptr(v), _lib.ptr(out)))
+
+    def mul(self, v, weights, out):
+        n, p = self.shape
+        v = self._vec(v, n, "v", "mul"); weights = self._vec(weights, n, "weights", "mul"); out = self._vec(out, p, "out", "mul")
+        if v.size != n or weights.size != n or out.size != p:
+            raise RuntimeError(f"adelie_core: mul() is given inconsistent inputs! (v={v.size}, w={weights.size}, o={out.size}, r={n}, c={p})")
+        _lib.check(_lib.load().ab_matrix_mul(self._core(), _lib.ptr(v), _lib.ptr(weights), _lib.ptr(out)))
+
+    def cov(self, j, q, sqrt_weights, out):
+        n, p = self.shape
+        sqrt_weights = self._vec(sqrt_weights, n, "sqrt_weights", "cov")
+        if (j < 0 or j > p - q or sqrt_weights.size != n or out.shape != (q, q)):
+            raise RuntimeError(f"adelie_core: cov() is given inconsistent inputs! (j={j}, q={q}, w={sqrt_weights.size}, o_r={out.shape[0]}, o_c={out.shape[-1]}, r={n}, c={p})")
+        if out.dtype != self.dtype or not out.flags.f_contiguous:
+            raise TypeError("cov(): out must be an F-contiguous (q, q) array of the matrix dtype")
+        _lib.check(_lib.load().ab_matrix_cov(self._core(), j, q, _lib.ptr(sqrt_weights), _lib.ptr(out)))
+
+    def sq_mul(self, weights, out):
+        n, p = self.shape
+        weights = self._vec(weights, n, "weights", "sq_mul"); out = self._vec(out, p, "out", "sq_mul")
+        _lib.check(_lib.load().ab_matrix_sq_mul(self._core(), _lib.ptr(weights), _lib.ptr(out)))
+
+    def sp_tmul(self, v, out):
+        n, p = self.shape
+        v = csr_matrix(v)
+        if v.shape[1] != p or out.shape != (v.shape[0], n):
+            raise RuntimeError(f"adelie_core: sp_tmul() is given inconsistent inputs! (vr={v.shape[0]}, vc={v.shape[1]}, o_r={out.shape[0]}, o_c={out.shape[1]}, r={n}, c={p})")
+        if out.dtype != self.dtype or not out.flags.c_contiguous:
+            raise TypeError("sp_tmul(): out must be a C-contiguous (L, n) array of the matrix dtype")
+        indptr = np.ascontiguousarray(v.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(v.indices, dtype=np.int64)
+        values = np.ascontiguousarray(v.data, dtype=self.dtype)
+        _lib.check(_lib.load().ab_matrix_sp_tmul(self._core(), v.shape[0], _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values), _lib.ptr(out)))
+
+    def mean(self, weights, out):
+        """Weighted column means X^T w (reference: matrix base ``mean``)."""
+        self.mul(np.ones(self.rows(), dtype=self.dtype), weights, out)
+
+    def var(self, centers, weights, out):
+        """Weighted column variances around ``centers``."""
+        sq = np.empty(self.cols(), dtype=self.dtype)
+        self.sq_mul(weights, sq)
+        m = np.empty(self.cols(), dtype=self.dtype)
+        self.mean(weights, m)
+        out[...] = sq - 2 * centers * m + centers ** 2 * np.sum(weights)
+
+
+class _Dense(_DeviceMatrix):
+    def __init__(self, mat, n_threads):
+        _DeviceMatrix.__init__(self, mat.dtype, mat.shape[0], mat.shape[1], n_threads)
+        self._mat = mat          # keep the host array alive (adelie/matrix.py:674-678)
+
+    def _make_handle(self):
+        m = self._mat
+        h = C.c_void_p()
+        order = 0 if m.flags.f_contiguous else 1
+        ldh = m.shape[0] if order == 0 else m.shape[1]
+        _lib.check(_lib.load().ab_matrix_dense_create(_lib.dtype_code(self.dtype), _lib.ptr(m), m.shape[0], m.shape[1], order, ldh,
+                                                      self._n_threads, C.byref(h)))
+        return h
+
+
+class _DeviceDense(_DeviceMatrix):
+    """Dense matrix generated directly in HBM (bench / sharded synthetic data)."""
+    def __init__(self, dtype, n, p, seed, row_offset, n_threads=1):
+        _DeviceMatrix.__init__(self, dtype, n, p, n_threads)
+        h = C.c_void_p()
+        _lib.check(_lib.load().ab_matrix_dense_alloc(_lib.dtype_code(dtype), n, p, C.byref(h)))
+        self._handle = h
+        _lib.check(_lib.load().ab_matrix_dense_fill_normal(h, seed, row_offset))
+
+    def to_host(self, row0=0, nrows=None, col0=0, ncols=None):
+        nrows = self._n - row0 if nrows is None else nrows
+        ncols = self._p - col0 if ncols is None else ncols
+        out = np.empty((nrows, ncols), dtype=self.dtype, order="F")
+        _lib.check(_lib.load().ab_matrix_dense_download(self._handle, _lib.ptr(out), row0, nrows, col0, ncols, nrows))
+        return out
+
+
+def dense(mat: np.ndarray, *, method: str = "naive", copy: bool = False, n_threads: int = 1):
+    """Dense matrix (adelie/matrix.py:549-680).  Only ``method="naive"`` is on the hot path."""
+    if method != "naive":
+        raise RuntimeError("adelie_b200: only method='naive' is in scope (covariance matrices are not on the hot path).")
+    if not isinstance(mat, np.ndarray) or mat.ndim != 2:
+        raise RuntimeError("mat must be a 2-dimensional numpy array.")
+    if mat.dtype not in (np.float32, np.float64):
+        raise RuntimeError("mat must be of type numpy.float32 or numpy.float64.")
+    if not (mat.flags.f_contiguous or mat.flags.c_contiguous):
+        mat = np.asfortranarray(mat)
+    elif mat.flags.c_contiguous and not mat.flags.f_contiguous:
+        warnings.warn("Detected matrix to be C-contiguous. Performance may improve with F-contiguous matrix.")
+    if copy:
+        mat = mat.copy(order="K")
+    return _Dense(mat, n_threads)
+
+
+def dense_device_normal(n: int, p: int, *, dtype=np.float32, seed: int = 0, row_offset: int = 0):
+    """N(0,1) dense matrix generated in HBM with a counter-based RNG (no host copy)."""
+    return _DeviceDense(dtype, n, p, seed, row_offset)

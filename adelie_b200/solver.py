@@ -1,0 +1,149 @@
+"""``grpnet`` -- the user entry point (reference: adelie/solver.py:354-958).
+
+Builds the initial invariants exactly as the reference does (two ``X.mul`` passes and NumPy
+scalars, solver.py:848-950), constructs the matching naive state and solves it on the device.
+"""
+from __future__ import annotations
+
+from typing import Callable, Union
+
+import numpy as np
+
+from . import matrix
+from .state import gaussian_naive as state_gaussian_naive
+from .state import glm_naive as state_glm_naive
+
+
+def grpnet(
+    X, glm, *, constraints: list = None, groups: np.ndarray = None, alpha: float = 1, penalty: np.ndarray = None,
+    offsets: np.ndarray = None, lmda_path: np.ndarray = None, irls_max_iters: int = int(1e4), irls_tol: float = 1e-7,
+    max_iters: int = int(1e5), tol: float = 1e-7, adev_tol: float = 0.9, ddev_tol: float = 0, newton_tol: float = 1e-12,
+    newton_max_iters: int = 1000, n_threads: int = 1, early_exit: bool = True, intercept: bool = True,
+    screen_rule: str = "pivot", min_ratio: float = 1e-2, lmda_path_size: int = 100, max_screen_size: int = None,
+    max_active_size: int = None, pivot_subset_ratio: float = 0.1, pivot_subset_min: int = 1, pivot_slack_ratio: float = 1.25,
+    check_state: bool = False, progress_bar: bool = True, warm_start=None, exit_cond: Callable = None,
+):
+    """Solves the group elastic net via the naive method (adelie/solver.py:354-958)."""
+    X_raw = X
+    if isinstance(X, np.ndarray):
+        X = matrix.dense(X, method="naive", n_threads=n_threads)
+    assert isinstance(X, matrix.MatrixNaiveBase)
+    dtype = X.dtype
+    n, p = X.rows(), X.cols()
+
+    if offsets is not None:
+        if offsets.shape != glm.y.shape:
+            raise RuntimeError("offsets must be same shape as y if not None.")
+        offsets = np.asarray(offsets, order="C", dtype=dtype)
+    else:
+        offsets = np.zeros(glm.y.shape, dtype=dtype)
+
+    if lmda_path is not None:
+        lmda_path = np.array(np.flip(np.sort(lmda_path)), dtype=dtype)
+
+    solver_args = dict(
+        X=X, constraints=constraints, alpha=alpha, offsets=offsets, lmda_path=lmda_path, max_iters=max_iters, tol=tol,
+        adev_tol=adev_tol, ddev_tol=ddev_tol, newton_tol=newton_tol, newton_max_iters=newton_max_iters, n_threads=n_threads,
+        early_exit=early_exit, intercept=intercept, screen_rule=screen_rule, min_ratio=min_ratio, lmda_path_size=lmda_path_size,
+        max_screen_size=max_screen_size, max_active_size=max_active_size, pivot_subset_ratio=pivot_subset_ratio,
+        pivot_subset_min=pivot_subset_min, pivot_slack_ratio=pivot_slack_ratio,
+    )
+    is_gaussian_opt = (glm.name in ["gaussian", "multigaussian"]) and glm.opt
+    if not is_gaussian_opt:
+        solver_args["glm"] = glm
+        solver_args["irls_max_iters"] = irls_max_iters
+        solver_args["irls_tol"] = irls_tol
+    else:
+        solver_args["y"] = glm.y
+        solver_args["weights"] = glm.weights
+
+    if groups is None:
+        groups = np.arange(p, dtype=int)
+    groups = np.asarray(groups)
+
+    if glm.is_multi:
+        from .solver_multi import grpnet_multi
+        return grpnet_multi(X=X, X_raw=X_raw, glm=glm, groups=groups, penalty=penalty, warm_start=warm_start,
+                            solver_args=solver_args, is_gaussian_opt=is_gaussian_opt, check_state=check_state,
+                            progress_bar=progress_bar, exit_cond=exit_cond, dtype=dtype)
+
+    group_sizes = np.concatenate([groups, [p]], dtype=int)
+    group_sizes = group_sizes[1:] - group_sizes[:-1]
+    G = len(groups)
+    if penalty is None:
+        penalty = np.sqrt(group_sizes).astype(dtype)
+
+    if warm_start is None:
+        lmda = np.inf
+        lmda_max = None
+        screen_set = np.arange(G)[(penalty <= 0) | (alpha <= 0)]
+        screen_beta = np.zeros(np.sum(group_sizes[screen_set]), dtype=dtype)
+        screen_is_active = np.ones(screen_set.shape[0], dtype=bool)
+        active_set_size = screen_set.shape[0]
+        active_set = np.empty(groups.shape[0], dtype=int)
+        active_set[:active_set_size] = np.arange(active_set_size)
+    else:
+        lmda = warm_start.lmda
+        lmda_max = warm_start.lmda_max
+        screen_set = warm_start.screen_set
+        screen_beta = warm_start.screen_beta
+        screen_is_active = warm_start.screen_is_active
+        active_set_size = warm_start.active_set_size
+        active_set = warm_start.active_set
+
+    solver_args.update(groups=groups, group_sizes=group_sizes, penalty=penalty, lmda=lmda, lmda_max=lmda_max,
+                       screen_set=screen_set, screen_beta=screen_beta, screen_is_active=screen_is_active,
+                       active_set_size=active_set_size, active_set=active_set)
+
+    if is_gaussian_opt:
+        y = glm.y
+        weights = glm.weights
+        if warm_start is None:                                       # solver.py:887-904
+            ones = np.ones(n, dtype=dtype)
+            X_means = np.empty(p, dtype=dtype)
+            X.mul(ones, weights, X_means)
+            y_off = y - offsets
+            y_mean = np.sum(y_off * weights)
+            yc = y_off
+            if intercept:
+                yc = yc - y_mean
+            y_var = np.sum(weights * yc ** 2)
+            rsq = 0
+            resid = np.ascontiguousarray(yc, dtype=dtype)
+            resid_sum = np.sum(weights * resid)
+            grad = np.empty(p, dtype=dtype)
+            X.mul(resid, weights, grad)
+        else:
+            X_means = warm_start.X_means
+            y_mean = warm_start.y_mean
+            y_var = warm_start.y_var
+            rsq = warm_start.rsq
+            resid = warm_start.resid
+            resid_sum = warm_start.resid_sum
+            grad = warm_start.grad
+        solver_args.update(X_means=X_means, y_mean=y_mean, y_var=y_var, rsq=rsq, resid=resid, resid_sum=resid_sum, grad=grad)
+        state = state_gaussian_naive(**solver_args)
+    else:
+        if warm_start is None:                                       # solver.py:926-950
+            ones = np.ones(n, dtype=dtype)
+            beta0 = 0
+            eta = offsets
+            resid = np.empty(n, dtype=dtype)
+            glm.gradient(eta, resid)
+            grad = np.empty(p, dtype=dtype)
+            X.mul(resid, ones, grad)
+            loss_null = None
+            loss_full = glm.loss_full()
+        else:
+            beta0 = warm_start.beta0
+            eta = warm_start.eta
+            resid = warm_start.resid
+            grad = warm_start.grad
+            loss_null = warm_start.loss_null
+            loss_full = warm_start.loss_full
+        solver_args.update(beta0=beta0, grad=grad, eta=eta, resid=resid, loss_null=loss_null, loss_full=loss_full)
+        state = state_glm_naive(**solver_args)
+
+    if check_state:
+        state.check(method="assert")
+    return state.solve(progress_bar=progress_bar, exit_cond=exit_cond)

@@ -1,0 +1,145 @@
+/* include/adelie_b200.h -- C ABI of libadelie_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for the block-coordinate-descent path of JamesYang007/adelie:
+ * the entry points a binding of `adelie.adelie_core` would call for the naive-method
+ * group-elastic-net solver.  Plain pointers and sizes only; every function returns 0 on
+ * success and a non-zero code on failure, in which case ab_last_error() holds the message
+ * (the text matches the reference's adelie_core_error / adelie_core_solver_error strings).
+ *
+ * Each block cites the reference interface it replaces (paths relative to the reference root).
+ * dtype: 0 = float32, 1 = float64 -- the element type of every `void*` value array.
+ */
+#ifndef ADELIE_B200_H
+#define ADELIE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ab_matrix ab_matrix;   /* adelie_core.matrix.MatrixNaive* handle */
+typedef struct ab_glm ab_glm;         /* adelie_core.glm.Glm* handle */
+typedef struct ab_state ab_state;     /* adelie_core.state.State*Naive handle */
+
+enum { AB_F32 = 0, AB_F64 = 1 };
+enum { AB_OK = 0, AB_ERR_CORE = 1 /* adelie_core_error -> RuntimeError */, AB_ERR_CUDA = 2, AB_ERR_ARG = 3 };
+
+/* ---- library / device ---------------------------------------------------------------------- */
+const char* ab_last_error(void);
+int ab_version(void);
+int ab_device_count(int* count);
+int ab_set_device(int device);
+int ab_get_device_info(int* sm_count, size_t* smem_optin_bytes, size_t* total_mem_bytes);
+int ab_device_synchronize(void);
+
+/* ---- configs: adelie/src/py_configs.cpp:6-47, include/adelie_core/configs.hpp:6-20 ---------- */
+int ab_configs_set(const char* name, double value);
+int ab_configs_get(const char* name, double* value);
+
+/* ---- dense matrix: adelie/src/py_matrix.cpp:1940-1943 (MatrixNaiveDense{32,64}{C,F}),
+ *      operators adelie/src/py_matrix.cpp:832-1071 = matrix_naive_base.hpp:57-143 ------------- */
+/* order: 0 = column-major (F), 1 = row-major (C); ldh = leading dimension of the host array.
+ * The matrix is copied to HBM once (column-major, rows padded to 32) and stays resident. */
+int ab_matrix_dense_create(int dtype, const void* host, int64_t n, int64_t p, int order, int64_t ldh, int n_threads, ab_matrix** out);
+/* device-side allocation + synthetic fill (bench / sharded generation): X[i,j] ~ N(0,1) from
+ * Philox(seed, subsequence=j, offset=row_offset+i), identical for every shard layout */
+int ab_matrix_dense_alloc(int dtype, int64_t n, int64_t p, ab_matrix** out);
+int ab_matrix_dense_fill_normal(ab_matrix* m, uint64_t seed, int64_t row_offset);
+int ab_matrix_dense_download(ab_matrix* m, void* host, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, int64_t ldh);
+int ab_matrix_free(ab_matrix* m);
+int ab_matrix_rows(const ab_matrix* m, int64_t* out);
+int ab_matrix_cols(const ab_matrix* m, int64_t* out);
+/* host-pointer operators (v, w, out are host arrays of the matrix dtype; semantics of the reference) */
+int ab_matrix_cmul(ab_matrix* m, int64_t j, const void* v, const void* w, double* out);                 /* X[:,j]^T (v*w) */
+int ab_matrix_ctmul(ab_matrix* m, int64_t j, double v, void* out);                                       /* out += v X[:,j] */
+int ab_matrix_bmul(ab_matrix* m, int64_t j, int64_t q, const void* v, const void* w, void* out);        /* X[:,j:j+q]^T (v*w) */
+int ab_matrix_btmul(ab_matrix* m, int64_t j, int64_t q, const void* v, void* out);                      /* out += X[:,j:j+q] v */
+int ab_matrix_mul(ab_matrix* m, const void* v, const void* w, void* out);                               /* X^T (v*w) */
+int ab_matrix_cov(ab_matrix* m, int64_t j, int64_t q, const void* sqrt_w, void* out /* q*q col-major */);
+int ab_matrix_sq_mul(ab_matrix* m, const void* w, void* out);                                           /* (X*X)^T w */
+/* out (L x n, row-major) = v (L x p CSR) X^T : adelie/src/py_matrix.cpp sp_tmul */
+int ab_matrix_sp_tmul(ab_matrix* m, int64_t L, const int64_t* indptr, const int64_t* indices, const void* values, void* out);
+
+/* ---- GLM families: adelie/src/py_glm.cpp:101-234, 664-685 ---------------------------------- */
+enum { AB_GLM_GAUSSIAN = 1, AB_GLM_BINOMIAL_LOGIT = 2, AB_GLM_MULTIGAUSSIAN = 3, AB_GLM_COX = 4 };
+/* y: (n,) or (n,K) row-major; weights (n,) summing to 1.  Cox: y = status, plus start/stop/strata, tie 1 = efron, 0 = breslow */
+int ab_glm_create(int dtype, int family, int64_t n, int64_t K, const void* y, const void* weights,
+                  const void* cox_start, const void* cox_stop, const int64_t* cox_strata, int cox_tie_efron, ab_glm** out);
+int ab_glm_free(ab_glm* g);
+int ab_glm_gradient(ab_glm* g, const void* eta, void* grad);
+int ab_glm_hessian(ab_glm* g, const void* eta, const void* grad, void* hess);
+int ab_glm_inv_hessian_gradient(ab_glm* g, const void* eta, const void* grad, const void* hess, void* out);
+int ab_glm_loss(ab_glm* g, const void* eta, double* out);
+int ab_glm_loss_full(ab_glm* g, double* out);
+int ab_glm_inv_link(ab_glm* g, const void* eta, void* out);
+
+/* ---- states: constructors adelie/src/py_state.cpp:1054-1228 (StateGaussianNaive),
+ *      :1557-1720 (StateGlmNaive), :1230-1400 (StateMultiGaussianNaive), :1722-1900 (StateMultiGlmNaive);
+ *      keyword meaning as adelie/state.py:1966-2010, 2327-2377, 2694-2740 ---------------------- */
+typedef struct ab_state_args {
+    int32_t dtype;
+    /* groups */
+    const int64_t* groups; const int64_t* group_sizes; int64_t G; double alpha; const void* penalty;
+    /* Gaussian ("opt") states: weights, X_means, y_mean, y_var, resid, resid_sum, rsq.  GLM states: offsets, eta, resid, beta0,
+     * loss_null (NaN => setup_loss_null), loss_full, irls_* */
+    const void* weights; const void* X_means; double y_mean, y_var, resid_sum, rsq;
+    const void* resid; const void* offsets; const void* eta; double beta0, loss_null, loss_full;
+    int32_t setup_loss_null; int64_t irls_max_iters; double irls_tol;
+    /* multi-response: n_classes K (>1) and multi_intercept, else 1 / 0 */
+    int64_t n_classes; int32_t multi_intercept;
+    /* lambda path */
+    const void* lmda_path; int64_t lmda_path_len; double lmda_max, min_ratio; int64_t lmda_path_size;
+    int32_t setup_lmda_max, setup_lmda_path;
+    /* limits / screening */
+    int64_t max_screen_size, max_active_size; double pivot_subset_ratio; int64_t pivot_subset_min; double pivot_slack_ratio;
+    int32_t screen_rule;      /* 0 strong, 1 pivot */
+    /* convergence */
+    int64_t max_iters; double tol, adev_tol, ddev_tol, newton_tol; int64_t newton_max_iters;
+    int32_t early_exit, intercept; int64_t n_threads;
+    /* warm-start invariants */
+    const int64_t* screen_set; int64_t screen_set_size; const void* screen_beta; int64_t screen_beta_size;
+    const int8_t* screen_is_active; int64_t active_set_size; const int64_t* active_set;
+    double lmda; const void* grad;
+} ab_state_args;
+
+/* glm == NULL => Gaussian "opt" state (StateGaussianNaive / StateMultiGaussianNaive) */
+int ab_state_create(const ab_state_args* args, ab_matrix* X, ab_glm* glm, ab_state** out);
+int ab_state_free(ab_state* s);
+/* solve: adelie/src/py_state.cpp:62-145 (_solve) -- never throws: the solver error string is written to `err`
+ * (empty on success), the state is valid up to the last solved lambda; total_time in seconds.
+ * exit_cond(ctx) != 0 requests early exit after a solved lambda; check_signals() != 0 interrupts (PyErr_CheckSignals). */
+int ab_state_solve(ab_state* s, int display_progress_bar, int (*exit_cond)(void*), void* ctx, int (*check_signals)(void),
+                   char* err, size_t errlen, double* total_time);
+/* outputs (field names as the Python attribute surface) */
+int ab_state_get_scalar(const ab_state* s, const char* name, double* out);
+int ab_state_get_vec_f64(const ab_state* s, const char* name, double* out, int64_t cap, int64_t* len);
+int ab_state_get_vec_i64(const ab_state* s, const char* name, int64_t* out, int64_t cap, int64_t* len);
+/* betas as CSR (L x p): call with NULL arrays to size, then again to fill */
+int ab_state_get_betas(const ab_state* s, int64_t* indptr, int64_t* indices, double* values, int64_t* nnz, int64_t* L);
+/* screen_transforms[i] (row-major gs x gs) */
+int ab_state_get_screen_transform(const ab_state* s, int64_t i, double* out, int64_t cap, int64_t* len);
+
+/* ---- pin state in isolation: adelie/src/py_state.cpp StateGaussianPinNaive, solve = solver_gaussian_pin_naive.hpp:223-401 */
+typedef struct ab_pin_args {
+    int32_t dtype; double y_mean, y_var;
+    const int64_t* groups; const int64_t* group_sizes; int64_t G; double alpha; const void* penalty; const void* weights;
+    const int64_t* screen_set; int64_t S; const void* lmda_path; int64_t L;
+    int32_t intercept; int64_t max_active_size, max_iters; double tol, adev_tol, ddev_tol, newton_tol; int64_t newton_max_iters;
+    double rsq; void* resid; double resid_sum;                                            /* in/out (host) */
+    void* screen_beta; int8_t* screen_is_active; int64_t active_set_size; int64_t* active_set;   /* in/out (host) */
+} ab_pin_args;
+int ab_pin_naive_solve(ab_matrix* X, ab_pin_args* args, ab_state** out, char* err, size_t errlen);
+
+/* ---- bcd prox: adelie/src/py_bcd.cpp:15-243 (double only, like the reference) --------------- */
+/* solver: 0 newton, 1 newton_abs */
+int ab_bcd_solve(int solver, int64_t q, const double* quad, const double* linear, double l1, double l2, double tol, int64_t max_iters,
+                 double* x, int64_t* iters);
+int ab_bcd_root_lower_bound(int64_t q, const double* quad, const double* linear, double l1, double* out);
+int ab_bcd_root_upper_bound(int64_t q, const double* quad, const double* linear, double l1, double zero_tol, double* out);
+int ab_bcd_root_function(int64_t q, double h, const double* D, const double* v, double l1, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADELIE_B200_H */
