@@ -14,6 +14,7 @@ _DEFAULTS = {
     "sweep_min_rows_per_cta": 1024.0,
     "sweep_force_direct": 0.0,
     "device_eigh": 1.0,
+    "sweep_profile": 0.0,
 }
 
 

@@ -56,6 +56,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "sweep_min_rows_per_cta") Configs::sweep_min_rows_per_cta = (int)value;
     else if (s == "sweep_force_direct") Configs::sweep_force_direct = (int)value;
     else if (s == "device_eigh") Configs::device_eigh = (int)value;
+    else if (s == "sweep_profile") Configs::sweep_profile = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -71,6 +72,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "sweep_min_rows_per_cta") *value = Configs::sweep_min_rows_per_cta;
     else if (s == "sweep_force_direct") *value = Configs::sweep_force_direct;
     else if (s == "device_eigh") *value = Configs::device_eigh;
+    else if (s == "sweep_profile") *value = Configs::sweep_profile;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -390,6 +392,16 @@ static int state_vec_f64(const PathState<T>& s, const std::string& nm, double* o
     if (nm == "benchmark_fit_active") return copy_vec<double>(s.benchmark_fit_active, out, cap, len);
     if (nm == "benchmark_kkt") return copy_vec<double>(s.benchmark_kkt, out, cap, len);
     if (nm == "benchmark_invariance") return copy_vec<double>(s.benchmark_invariance, out, cap, len);
+    if (nm == "sweep_stats") {
+        const int64_t N = 32 + 8 * 160;
+        *len = N;
+        if (out) {
+            std::vector<long long> h(N, 0);
+            if (s.X->stats.n) { s.X->stats.download(h.data(), N); AB_CUDA(cudaStreamSynchronize(0)); }
+            for (int64_t i = 0; i < std::min<int64_t>(cap, N); ++i) out[i] = (double)h[i];
+        }
+        return AB_OK;
+    }
     if (nm == "resid" || nm == "eta") {
         const DevBuf<T>& d = (nm == "resid") ? s.d_resid : s.d_eta;
         const int64_t nn = s.is_glm ? s.glm->n : s.n;
@@ -513,7 +525,7 @@ static int bcd_run(int mode, int64_t q, const double* L, const double* v, double
     if (q < 1) throw core_error("quad must be non-empty.");
     DevBuf<double> dL(q), dv(q), dx(q), ds(1);
     dL.upload(L, q); dv.upload(v, q);
-    bcd_kernel<<<1, 32, 4 * q * sizeof(double), 0>>>(mode, (int)q, dL.p, dv.p, l1, l2, tol, (int)std::min<int64_t>(max_iters, 1 << 30), aux, dx.p, ds.p);
+    bcd_kernel<<<1, 32, (4 * q + 128) * sizeof(double), 0>>>(mode, (int)q, dL.p, dv.p, l1, l2, tol, (int)std::min<int64_t>(max_iters, 1 << 30), aux, dx.p, ds.p);
     AB_CUDA(cudaGetLastError());
     if (x) dx.download(x, q);
     ds.download(scal, 1);

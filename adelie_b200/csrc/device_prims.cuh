@@ -61,7 +61,7 @@ struct alignas(16) LLLine { uint32_t d0, f0, d1, f1; };
 
 __device__ __forceinline__ void ll_store(LLLine* line, double v, uint32_t epoch) {
     const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch) : "memory");
+    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch) : "memory");
 }
 // system-scope variant for lines that live in a peer GPU's memory (NVLink P2P store)
 __device__ __forceinline__ void ll_store_sys(LLLine* line, double v, uint32_t epoch) {
@@ -70,7 +70,7 @@ __device__ __forceinline__ void ll_store_sys(LLLine* line, double v, uint32_t ep
 }
 __device__ __forceinline__ bool ll_try_load(const LLLine* line, uint32_t epoch, double& out) {
     uint32_t d0, f0, d1, f1;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(line) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(line) : "memory");
     if (f0 == epoch && f1 == epoch) { out = __hiloint2double((int)d1, (int)d0); return true; }
     return false;
 }
@@ -88,14 +88,17 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // CTA-local (shared memory) shutdown flag, `abort_flag` the grid-wide one in global memory.
 struct SpinGuard {
     unsigned long long t0 = 0; uint32_t spin = 0;
+    // cold path, deliberately out of line: keeps the spin loops (and the kernel's instruction footprint) small
+    __device__ __noinline__ bool slow_check(volatile int* abort_flag) {
+        if (*abort_flag) return true;
+        const unsigned long long t = global_ns();
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > kSpinTimeoutNs) { *abort_flag = 1; return true; }
+        return false;
+    }
     __device__ __forceinline__ bool give_up(volatile int* abort_flag, volatile int* stop) {
         if (stop && *stop) return true;
-        if (((++spin) & kSpinCheck) == 0) {
-            if (*abort_flag) return true;
-            const unsigned long long t = global_ns();
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > kSpinTimeoutNs) { *abort_flag = 1; return true; }
-        }
+        if (((++spin) & kSpinCheck) == 0) return slow_check(abort_flag);
         return false;
     }
 };

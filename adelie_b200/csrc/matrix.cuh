@@ -17,7 +17,7 @@ namespace ab {
 
 // Per-device resources of the fused sweep kernel: LL exchange lines, epoch, abort flag.
 struct SweepContext {
-    DevBuf<dev::LLLine> ll; DevBuf<uint32_t> epoch; DevBuf<int> abort_flag;
+    DevBuf<dev::LLLine> ll, ll2; DevBuf<uint32_t> epoch; DevBuf<int> abort_flag;
     int ncta_pad = 0; int ll_gs_cap = kGsMax;
     static SweepContext& get() {
         static thread_local SweepContext* ctx[64] = {nullptr};
@@ -27,6 +27,7 @@ struct SweepContext {
             const int sms = DeviceInfo::get().sm_count;
             c->ncta_pad = (sms + 31) / 32 * 32;
             c->ll.alloc((size_t)2 * c->ll_gs_cap * c->ncta_pad);
+            c->ll2.alloc((size_t)2 * c->ll_gs_cap * 32);
             c->epoch.alloc(1);
             uint32_t one = 1;
             c->epoch.upload(&one, 1);
@@ -43,15 +44,16 @@ template <class T>
 struct PinLaunch {
     T* resid; const T* weights;
     const GroupMeta* meta; int S; const T* grec;
-    T* screen_beta; int8_t* is_active; int32_t* active_set; PinScalars* sc;
+    const T* beta_in; int beta_len; const int8_t* is_active_in; int32_t* active_set; PinScalars* sc;
     double lmda, alpha, tol, newton_tol; long long max_iters; int newton_max_iters; int max_active_size; int intercept;
     int gs_max; int rec_max;     // largest group size / record length (elements) in the screen set
 };
 
-struct SweepGeometry { int ncta, threads, n_stages, stage_elems, rows_stride, gs_cap, units_base, units_rem; bool smem; size_t smem_bytes; };
+struct SweepGeometry { int ncta, ncta_pad, threads, n_stages, stage_elems, rows_stride, gs_cap, units_base, units_rem; bool smem; size_t smem_bytes; };
 
 template <class T>
 inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max) {
+    // (ncta_pad of this launch = ncta rounded up to 32; the LL buffer is sized for the largest possible grid)
     const auto& di = DeviceInfo::get();
     SweepGeometry g{};
     const int64_t units = n_pad / kRowAlign;
@@ -64,7 +66,8 @@ inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max) {
     g.rows_stride = (g.units_base + (g.units_rem ? 1 : 0)) * kRowAlign;
     g.gs_cap = std::max(4, (gs_max + 3) / 4 * 4);
     const int n_cwarps = g.threads / 32 - 1;
-    const size_t fixed = SweepSmem<T>::fixed_bytes(n_cwarps, g.gs_cap) + 2 * sizeof(T) * (size_t)g.rows_stride;
+    g.ncta_pad = (ncta + 31) / 32 * 32;
+    const size_t fixed = SweepSmem<T>::fixed_bytes(n_cwarps, g.gs_cap, g.ncta_pad) + 2 * sizeof(T) * (size_t)g.rows_stride;
     const int rec_pad = (rec_max + 3) / 4 * 4;
     int stage_elems = g.rows_stride * std::max(gs_max, 1) + rec_pad;
     stage_elems = (stage_elems + 31) / 32 * 32;
@@ -74,11 +77,11 @@ inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max) {
     g.smem = (ns >= 2) && !Configs::sweep_force_direct;
     if (g.smem) {
         g.n_stages = ns;
-        g.smem_bytes = SweepSmem<T>::total(n_cwarps, g.gs_cap, g.rows_stride, ns, stage_elems);
+        g.smem_bytes = SweepSmem<T>::total(n_cwarps, g.gs_cap, g.ncta_pad, g.rows_stride, ns, stage_elems);
     } else {
         g.n_stages = 1; g.stage_elems = 0;
         // direct path: all warps are consumers; r / w stay in global memory
-        g.smem_bytes = SweepSmem<T>::fixed_bytes(g.threads / 32, g.gs_cap);
+        g.smem_bytes = SweepSmem<T>::fixed_bytes(g.threads / 32, g.gs_cap, g.ncta_pad);
         g.rows_stride = 0;
     }
     return g;
@@ -104,6 +107,10 @@ struct DenseMatrix {
     int n_threads = 1;
     DevBuf<double> part;        // scratch for two-phase reductions
     DevBuf<T> ones;             // (n_pad,) ones with zero pad
+    DevBuf<T> beta_rep;         // per-CTA coefficient replicas of the fused sweep (see sweep.cuh)
+    int64_t beta_stride = 0;
+    DevBuf<int8_t> act_rep; int64_t act_stride = 0;
+    DevBuf<long long> stats;    // per-phase cycle counters of the fused sweep (Configs::sweep_profile)
     cudaStream_t stream = 0;
 
     DenseMatrix(int64_t n_, int64_t p_) : n(n_), p(p_), ld(pad_rows(n_)) {
@@ -198,13 +205,23 @@ struct DenseMatrix {
         last_geom = g;
         PinKernelArgs<T> a{};
         a.X = X; a.ld = ld; a.n_pad = ld; a.resid = L.resid; a.weights = L.weights;
-        a.meta = L.meta; a.S = L.S; a.grec = L.grec; a.screen_beta = L.screen_beta; a.is_active = L.is_active;
+        a.meta = L.meta; a.S = L.S; a.grec = L.grec;
+        act_stride = ((int64_t)L.S + 127) / 128 * 128 + 128;
+        act_rep.reserve_keep((size_t)act_stride * g.ncta, stream);
+        a.is_active_in = L.is_active_in; a.is_active_rep = act_rep.p; a.act_stride = act_stride;
+        beta_stride = ((int64_t)L.beta_len + 31) / 32 * 32 + 32;
+        beta_rep.reserve_keep((size_t)beta_stride * g.ncta, stream);
+        a.beta_in = L.beta_in; a.beta_rep = beta_rep.p; a.beta_stride = beta_stride; a.beta_len = L.beta_len;
         a.active_set = L.active_set; a.sc = L.sc;
-        a.ll = ctx.ll.p; a.ll_gs_cap = ctx.ll_gs_cap; a.ncta_pad = ctx.ncta_pad; a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
+        a.ll = ctx.ll.p; a.ll_gs_cap = ctx.ll_gs_cap; a.ncta_pad = g.ncta_pad;
+        a.ll2 = ctx.ll2.p;
+        { int f = 1; while (f * f < g.ncta) ++f; a.fan = std::max(1, f); }      // fan = ceil(sqrt(ncta)) => n_groups <= fan + 1 <= 32
+        a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
         a.lmda = L.lmda; a.alpha = L.alpha; a.tol = L.tol; a.newton_tol = L.newton_tol; a.dbeta_tol = Configs::dbeta_tol;
         a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
         a.units_base = g.units_base; a.units_rem = g.units_rem; a.rows_stride = g.rows_stride;
         a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.gs_max = std::max(L.gs_max, 1); a.gs_cap = g.gs_cap;
+        if (Configs::sweep_profile) { if (!stats.n) stats.alloc(32 + 8 * 160); a.stats = stats.p; } else a.stats = nullptr;
         void* kargs[] = {&a};
         const void* fn = g.smem ? (const void*)pin_solve_kernel<T, true> : (const void*)pin_solve_kernel<T, false>;
         AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));

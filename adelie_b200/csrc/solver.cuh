@@ -247,13 +247,18 @@ struct PathState {
                 for (size_t k = 0; k < (size_t)gs * gs; ++k) st[i][k] = (T)V[k];
                 for (int c = 0; c < gs; ++c) { const T d = (T)D[c]; sv[sb + c] = d * T(d >= 0); }      // :122
             }
-            // packed record [A | xm | V], 16-byte aligned
+            // packed record [A | xm | V^T xm | V], 16-byte aligned
             const size_t off = (grec.size() + 3) / 4 * 4;
-            const int rec = gs * (gs + 2);
+            const int rec = gs * (gs + 3);
             const int rec_pad = (rec + 3) / 4 * 4;
             grec.resize(off + rec_pad, T(0));
-            for (int c = 0; c < gs; ++c) { grec[off + c] = sv[sb + c]; grec[off + gs + c] = sXm[sb + c]; }
-            for (int k = 0; k < gs * gs; ++k) grec[off + 2 * gs + k] = st[i][k];
+            for (int c = 0; c < gs; ++c) {
+                grec[off + c] = sv[sb + c]; grec[off + gs + c] = sXm[sb + c];
+                double xmt = 0;
+                for (int r = 0; r < gs; ++r) xmt += (double)sXm[sb + r] * (double)st[i][(size_t)r * gs + c];
+                grec[off + 2 * gs + c] = (T)xmt;
+            }
+            for (int k = 0; k < gs * gs; ++k) grec[off + 3 * gs + k] = st[i][k];
             GroupMeta m{};
             m.col = (int32_t)groups[g]; m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
             m.pen = (double)penalty[g];
@@ -294,7 +299,7 @@ struct PathState {
         d_sc.upload(h_sc.p, 1);
         PinLaunch<T> L{};
         L.resid = d_r; L.weights = d_w; L.meta = d_meta.p; L.S = (int)S; L.grec = d_grec.p;
-        L.screen_beta = d_screen_beta.p; L.is_active = d_is_active.p; L.active_set = d_active_set.p; L.sc = d_sc.p;
+        L.beta_in = d_screen_beta.p; L.beta_len = (int)screen_beta.size(); L.is_active_in = d_is_active.p; L.active_set = d_active_set.p; L.sc = d_sc.p;
         L.lmda = (double)lmda_; L.alpha = (double)alpha; L.tol = (double)tol_pin; L.newton_tol = (double)newton_tol;
         L.max_iters = (long long)max_iters; L.newton_max_iters = (int)std::min<size_t>(newton_max_iters, 1u << 30);
         L.max_active_size = (int)std::min<size_t>(max_active_size, (size_t)G); L.intercept = intercept ? 1 : 0;
@@ -305,8 +310,8 @@ struct PathState {
         AB_CUDA(cudaEventRecord(ev1, 0));
         d_sc.download(h_sc.p, 1);
         const size_t old_active = active_set_size;
-        d_screen_beta.download(screen_beta.data(), screen_beta.size());
-        d_is_active.download(screen_is_active.data(), S);
+        X->beta_rep.download(screen_beta.data(), screen_beta.size());     // replica 0
+        X->act_rep.download(screen_is_active.data(), S);                   // replica 0
         AB_CUDA(cudaStreamSynchronize(0));
         ++n_pin_solves; ++n_kernel_launches;
         float ms = 0; AB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));

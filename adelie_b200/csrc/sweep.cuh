@@ -55,9 +55,18 @@ struct PinKernelArgs {
     T* resid; const T* weights;
     const GroupMeta* meta; int S;
     const T* grec;
-    T* screen_beta; int8_t* is_active; int32_t* active_set;
+    // Coefficients: every CTA works on its OWN replica (beta_rep + cta * beta_stride), initialised from beta_in at
+    // kernel start; replica 0 is the output.  A single shared array would be racy: a slow CTA's (identical-valued but)
+    // delayed store of the previous sweep's coefficients could land after a fast CTA's newer store.
+    const T* beta_in; T* beta_rep; int64_t beta_stride; int beta_len;
+    // screen_is_active is replicated per CTA for the same reason (a fast CTA's 0 -> 1 transition must not be seen
+    // by a slower CTA that has not processed that group yet); replica 0 is the output.  active_set slots are written
+    // once per launch with identical values by every CTA, which is race-free.
+    const int8_t* is_active_in; int8_t* is_active_rep; int64_t act_stride;
+    int32_t* active_set;
     PinScalars* sc;
     dev::LLLine* ll; int ll_gs_cap; int ncta_pad;
+    dev::LLLine* ll2; int fan;       // two-level exchange: level-2 lines [2][ll_gs_cap][32]; fan = CTAs per level-1 group
     uint32_t* epoch; int* abort_flag;
     double lmda, alpha, tol, newton_tol, dbeta_tol;
     long long max_iters; int newton_max_iters; int max_active_size; int intercept;
@@ -66,6 +75,7 @@ struct PinKernelArgs {
     int n_stages; int stage_elems; // ring geometry (elements of T per stage)
     int gs_max;                    // largest group size in the screen set
     int gs_cap;                    // stride of the per-column shared-memory scratch arrays (>= gs_max, multiple of 4)
+    long long* stats;              // optional [16] per-phase cycle counters of CTA 0 / thread 0 (nullptr = off)
 };
 
 struct SweepCtrl {
@@ -95,35 +105,158 @@ template <> __device__ __forceinline__ void vec_store<double>(double* p, const d
     *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
 }
 
-// Shared-memory carve-up (host and device must agree).
+// Shared-memory carve-up (host and device must agree):
+//   header (barriers, ctrl) | vals1[gs_cap][32] + vals2[gs_cap][32] + gsum[gs_cap] (double) | wpart[n_cwarps][gs_cap] (double) |
+//   prox scratch 8 x [gs_cap] (double-sized slots) | del [gs_cap] | reduction scratch [4*32] | r tile | w tile | stages
 template <class T>
 struct SweepSmem {
-    static constexpr size_t kHeaderBytes = 512;                                // barriers + ctrl
-    __host__ __device__ static size_t fixed_bytes(int n_cwarps, int gs_cap) {
+    static constexpr size_t kHeaderBytes = 512;
+    __host__ __device__ static size_t fixed_bytes(int n_cwarps, int gs_cap, int ncta_pad) {
         size_t b = kHeaderBytes
-                 + sizeof(double) * (size_t)n_cwarps * gs_cap      // wpart
-                 + sizeof(double) * (size_t)gs_cap * kLLSeg        // wsum
-                 + sizeof(double) * (size_t)gs_cap * 8             // prox scratch
-                 + sizeof(T) * (size_t)gs_cap;                     // del
+                 + sizeof(double) * (size_t)gs_cap * (2 * 32 + 1)      // vals1 + vals2 + gsum  (ncta_pad unused: two-level exchange)
+                 + sizeof(double) * (size_t)n_cwarps * gs_cap         // wpart
+                 + sizeof(double) * (size_t)gs_cap * 8                // prox scratch
+                 + sizeof(double) * (size_t)gs_cap                    // del
+                 + sizeof(double) * 4 * 32;                           // reduction scratch of the control warp
         return (b + 127) / 128 * 128;
     }
-    static size_t total(int n_cwarps, int gs_cap, int rows_stride, int n_stages, int stage_elems) {
-        return fixed_bytes(n_cwarps, gs_cap) + 2 * sizeof(T) * (size_t)rows_stride + sizeof(T) * (size_t)n_stages * stage_elems;
+    static size_t total(int n_cwarps, int gs_cap, int ncta_pad, int rows_stride, int n_stages, int stage_elems) {
+        return fixed_bytes(n_cwarps, gs_cap, ncta_pad) + 2 * sizeof(T) * (size_t)rows_stride + sizeof(T) * (size_t)n_stages * stage_elems;
     }
 };
 
-// ------------------------------------------------------------------------------------------
-// Group proximal update, executed by the 32 lanes of the control warp (replicated in every CTA).
-// All scalars are double; for T = float the inputs convert exactly and the result is rounded
-// once.  Follows coordinate_descent (solver_gaussian_pin_naive.hpp:75-164) + update_coordinate
-// (solver_gaussian_pin_base.hpp:148-195) + newton_solver (newton.hpp:44-142, h0 = 0).
-// ------------------------------------------------------------------------------------------
+// Replicated solver scalars, held by the control warp of every CTA (identical in all CTAs).
 struct ProxState {
     double rsq, resid_sum, cm;
     int A;                    // active_set_size
     int error;
     int newton_iters_max;
 };
+
+// ---- multi-value warp reductions ---------------------------------------------------------------
+// Simultaneous butterfly all-reduce of N values (independent chains => the shuffles pipeline).
+template <int N, class P>
+__device__ __forceinline__ void warp_allsum(P (&v)[N]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        P t[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) t[i] = __shfl_xor_sync(0xffffffffu, v[i], o);
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] += t[i];
+    }
+}
+
+// "Transposed" reduction of 16 per-lane accumulators over the 32 lanes in 16 shuffles / 5 steps:
+// every step halves the number of live values per lane.  Returns, in every lane, the warp total of
+// column (lane >> 1) & 15.
+template <class P>
+__device__ __forceinline__ P warp_reduce16(P (&v)[16], int lane) {
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const P send = up ? v[i] : v[i + 8];
+            const P keep = up ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const P send = up ? v[i] : v[i + 4];
+            const P keep = up ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const P send = up ? v[i] : v[i + 2];
+            const P keep = up ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = (lane & 2) != 0;
+        const P send = up ? v[0] : v[1];
+        const P keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+// All-reduce of N per-lane values over the first n_src lanes of a warp through shared memory: every lane ends up with
+// the totals after n_src dependent adds (~4 cycles each) instead of a 5-step shuffle butterfly (~30 cycles per step).
+// Lanes >= n_src must pass zeros.  scratch: N * 32 elements, private to the warp.
+template <int N, class P>
+__device__ __forceinline__ void smem_allsum(P* scratch, P (&v)[N], int n_src, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < N; ++k) scratch[k * 32 + lane] = v[k];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = 0;
+#pragma unroll 4
+    for (int i = 0; i < n_src; ++i) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] += scratch[k * 32 + i];
+    }
+}
+
+template <class P> struct ProxEps;
+template <> struct ProxEps<double> { static __device__ __forceinline__ double floor_tol() { return 0.0; } };
+// float cannot resolve |phi(h)| below a few ulps of 1: the Newton tolerance is clamped at this floor
+template <> struct ProxEps<float> { static __device__ __forceinline__ float floor_tol() { return 4.8e-7f; } };
+
+// Warp-cooperative Newton solve in the compute type P (float for T = float, double for T = double), tuned for the
+// sweep's critical path: the ||v|| <= l1 test is folded into the first evaluation (phi(0) = ||v||^2 / l1^2 - 1) and
+// the two sums of every evaluation travel through one interleaved butterfly.  Same iteration as newton_solver
+// (newton.hpp:44-142, h0 = 0).  L, v, x: shared arrays of length >= gs.  Returns the iteration count.
+template <class P>
+__device__ __forceinline__ int warp_prox_fast(const P* L, const P* v, int gs, P l1, P l2, P tol, int max_iters, P* x, int lane, P* scratch)
+{
+    const int n_src = min(gs, 32);
+    if (l1 <= P(0)) {                                        // newton.hpp:72-75 (||v|| <= l1 = 0 only if v == 0 => x = 0 too)
+#pragma unroll 1
+        for (int c = lane; c < gs; c += 32) { const P d = L[c] + l2; x[c] = (v[c] == P(0)) ? P(0) : v[c] / d; }
+        __syncwarp();
+        return 0;
+    }
+    const P tol_eff = fmax(tol, ProxEps<P>::floor_tol());
+    P h = 0; int iters = 0;
+    while (true) {
+        P s[2] = {0, 0};
+#pragma unroll 1
+        for (int c = lane; c < gs; c += 32) {
+            const P D = L[c] + l2;
+            const P u = P(1) / (D * h + l1);
+            const P q = v[c] * u;
+            const P xx = q * q;
+            s[0] += xx; s[1] += xx * D * u;
+        }
+        smem_allsum<2>(scratch, s, n_src, lane);
+        const P t = s[0];
+        if (iters == 0 && !(t > P(1))) {                     // ||v|| <= l1  =>  x = 0   (newton.hpp:62-66)
+#pragma unroll 1
+            for (int c = lane; c < gs; c += 32) x[c] = 0;
+            __syncwarp();
+            return 0;
+        }
+        const P fh = t - P(1);
+        if (!(fabs(fh) > tol_eff) || iters >= max_iters) break;
+        const P dfh = -s[1] * (P(1) + sqrt(t)) / t;
+        h = fmax(h - fh / dfh, P(0));
+        ++iters;
+    }
+#pragma unroll 1
+    for (int c = lane; c < gs; c += 32) x[c] = h * v[c] / ((L[c] + l2) * h + l1);       // newton.hpp:109
+    __syncwarp();
+    return iters;
+}
 
 // Warp-cooperative group prox: minimiser of 0.5 x^T diag(L) x - v^T x + l1 ||x|| + 0.5 l2 ||x||^2
 // (newton_solver_base, CORE/bcd/unconstrained/newton.hpp:44-111 with newton_root_find,
@@ -218,7 +351,8 @@ static __global__ void bcd_kernel(int mode, int q, const double* __restrict__ Lg
     __syncwarp();
     if (mode <= 1) {
         int iters = 0;
-        warp_prox_newton(L, v, q, l1, l2, tol, max_iters, mode == 1, D, x, iters, lane);
+        if (mode == 0) iters = warp_prox_fast<double>(L, v, q, l1, l2, tol, max_iters, x, lane, sh + 4 * q);    // the sweep kernel's solver
+        else warp_prox_newton(L, v, q, l1, l2, tol, max_iters, true, D, x, iters, lane);
         for (int c = lane; c < q; c += 32) x_out[c] = x[c];
         if (lane == 0) scal_out[0] = (double)iters;
     } else if (mode == 2) {
@@ -255,6 +389,173 @@ static __global__ void bcd_kernel(int mode, int q, const double* __restrict__ Lg
     }
 }
 
+// ---- out-of-line phases of the sweep (kept out of line on purpose: the per-group loop of the kernel must stay
+// well inside the 32 KB instruction cache, otherwise the single control warp stalls on instruction fetch) ---------
+// Polls `count` lines (line q of this thread = first + q * stride, q = 0 .. while < count) until they carry `epoch` and
+// writes their payloads to out[line].  Returns false if the kernel was aborted.
+__device__ __forceinline__ bool ll_poll_lines(const dev::LLLine* lines, double* out, int first, int stride, int count, uint32_t epoch,
+                                              volatile int* abort_flag)
+{
+    bool ok = true;
+#pragma unroll 1
+    for (int i = first; i < count; i += stride) {
+        double v = 0.0;
+        dev::SpinGuard guard;
+        while (!dev::ll_try_load(lines + i, epoch, v)) {
+            if (guard.give_up(abort_flag, nullptr)) { ok = false; break; }
+        }
+        out[i] = v;
+    }
+    return ok;
+}
+
+template <class T, class P>
+struct ProxCtx { P *p_aold, *p_A, *p_gk, *p_gt, *p_atold, *p_at, *scratch; T* s_del; const double* gsum; T* my_beta; };
+
+// Group update for 1 < gs <= 32, one coefficient per lane of the control warp, written for the shortest possible
+// dependent-instruction chain (a lone warp issues ~1 instruction every 5 cycles): everything that does not depend on the
+// exchanged gradient (a_old V, A, xm, V^T xm) is computed by prox_small_pre() while the exchange is in flight.
+template <class P> struct ProxPre { P aold, A, xm, xmt, ao; };
+
+template <class T, class P>
+__device__ __forceinline__ ProxPre<P> prox_small_pre(const T* rec, int gs, const P* p_aold, int lane) {
+    ProxPre<P> r;
+    const bool on = lane < gs;
+    const int c = on ? lane : 0;
+    r.aold = on ? p_aold[c] : P(0);
+    r.A = on ? (P)rec[c] : P(0);
+    r.xm = on ? (P)rec[gs + c] : P(0);
+    r.xmt = on ? (P)rec[2 * gs + c] : P(0);
+    const T* V = rec + 3 * gs;
+    P ao = 0;
+#pragma unroll 4
+    for (int q = 0; q < gs; ++q) ao += p_aold[q] * (P)V[q * gs + c];
+    r.ao = on ? ao : P(0);
+    return r;
+}
+
+template <class T, class P>
+__device__ __forceinline__ int prox_small_post(const ProxCtx<T, P>& px, const ProxPre<P>& pre, const T* rec, int gs, int begin, P l1k, P l2k,
+                                               P tol, int max_iters, P dbeta_tol, int intercept, ProxState& ps, int lane, long long* nit_acc)
+{
+    const bool on = lane < gs;
+    const int c = on ? lane : 0;
+    const T* V = rec + 3 * gs;
+    P* p_gk = px.p_gk; P* p_at = px.p_at; P* scr = px.scratch;
+    // gradient in the original basis, then rotated: gt = gk V + A * (a_old V)
+    P gk = on ? (P)px.gsum[c] : P(0);
+    if (intercept) gk -= (P)ps.resid_sum * pre.xm;
+    p_gk[lane] = gk;
+    __syncwarp();
+    P gt0 = 0;
+#pragma unroll 4
+    for (int q = 0; q < gs; ++q) gt0 += p_gk[q] * (P)V[q * gs + c];
+    if (!on) gt0 = 0;
+    const P gt = gt0 + pre.A * pre.ao;
+    // ---- newton_solver (newton.hpp:44-142), h0 = 0, phi(0) doubles as the ||v|| <= l1 test
+    P at = 0; int nit = 0;
+    if (l1k <= P(0)) {
+        at = (on && gt != P(0)) ? gt / (pre.A + l2k) : P(0);
+    } else {
+        const P D = pre.A + l2k;
+        const P tol_eff = fmax(tol, ProxEps<P>::floor_tol());
+        P h = 0; bool zero = false;
+        while (true) {
+            const P u = P(1) / (D * h + l1k);
+            const P q = gt * u;
+            const P xx = q * q;
+            P sm[2] = {xx, xx * D * u};
+            smem_allsum<2>(scr, sm, gs, lane);
+            const P t = sm[0];
+            if (nit == 0 && !(t > P(1))) { zero = true; break; }
+            const P fh = t - P(1);
+            if (!(fabs(fh) > tol_eff) || nit >= max_iters) break;
+            const P dfh = -sm[1] * (P(1) + sqrt(t)) / t;
+            h = fmax(h - fh / dfh, P(0));
+            ++nit;
+        }
+        at = (zero || !on) ? P(0) : h * gt / (D * h + l1k);
+    }
+    ps.newton_iters_max = max(ps.newton_iters_max, nit);
+    if (nit_acc) *nit_acc += nit;
+    if (nit >= max_iters) ps.error = kErrNewton;
+    const P d = at - pre.ao;
+    P red[4] = {d * d, pre.A * d * d, d * (2 * gt0 - d * pre.A), -pre.xmt * d};
+    smem_allsum<4>(scr, red, gs, lane);
+    if (sqrt(red[0]) <= dbeta_tol * sqrt((P)gs)) return 0;       // :146-147
+    ps.cm = fmax(ps.cm, (double)(red[1] / gs));
+    ps.rsq += (double)red[2];
+    ps.resid_sum += (double)red[3];
+    p_at[lane] = at;
+    __syncwarp();
+    P an = 0;
+#pragma unroll 4
+    for (int q = 0; q < gs; ++q) an += p_at[q] * (P)V[c * gs + q];          // rotate back: a = at V^T
+    if (on) {
+        const T anT = (T)an;
+        px.my_beta[begin + c] = anT;
+        px.s_del[c] = (T)(pre.aold - (P)anT);
+    }
+    return 1;
+}
+
+// Group update for gs > 1 (solver_gaussian_pin_naive.hpp:109-164), executed by the control warp.
+// rec = [A | xm | V^T xm | V].  Returns 1 if the coefficients moved.
+template <class T, class P>
+__device__ __noinline__ int prox_group(const ProxCtx<T, P>& px, const T* rec, int gs, int begin, P l1k, P l2k, P tol,
+                                       int max_iters, P dbeta_tol, int intercept, ProxState& ps, int lane, long long* nit_acc)
+{
+    const T* Arec = rec; const T* xmrec = rec + gs; const T* xmtrec = rec + 2 * gs; const T* V = rec + 3 * gs;
+    P* p_aold = px.p_aold; P* p_A = px.p_A; P* p_gk = px.p_gk; P* p_gt = px.p_gt; P* p_atold = px.p_atold; P* p_at = px.p_at;
+    const P rsum_in = (P)ps.resid_sum;
+#pragma unroll 1
+    for (int c = lane; c < gs; c += 32) {
+        P gk = (P)px.gsum[c];
+        if (intercept) gk -= rsum_in * (P)xmrec[c];
+        p_gk[c] = gk; p_A[c] = (P)Arec[c];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int c = lane; c < gs; c += 32) {                   // rotate into the eigenbasis: gt = gk V, ao = a_old V
+        P gt = 0, ao = 0;
+#pragma unroll 2
+        for (int r = 0; r < gs; ++r) {
+            const P vrc = (P)V[r * gs + c];
+            gt += p_gk[r] * vrc; ao += p_aold[r] * vrc;
+        }
+        gt += p_A[c] * ao;
+        p_gt[c] = gt; p_atold[c] = ao;
+    }
+    __syncwarp();
+    const int nit = warp_prox_fast<P>(p_A, p_gt, gs, l1k, l2k, tol, max_iters, p_at, lane, px.scratch);
+    ps.newton_iters_max = max(ps.newton_iters_max, nit);
+    if (nit_acc) *nit_acc += nit;
+    if (nit >= max_iters) ps.error = kErrNewton;
+    P red[4] = {0, 0, 0, 0};                                 // ||dt||^2, sum A dt^2, rsq increment, resid_sum increment
+#pragma unroll 1
+    for (int c = lane; c < gs; c += 32) {
+        const P gt0 = p_gt[c] - p_A[c] * p_atold[c];
+        const P d = p_at[c] - p_atold[c];
+        red[0] += d * d; red[1] += p_A[c] * d * d; red[2] += d * (2 * gt0 - d * p_A[c]);
+        red[3] -= (P)xmtrec[c] * d;                          // sum_r xm_r (a_old - a)_r = (V^T xm) . (at_old - at)
+    }
+    smem_allsum<4>(px.scratch, red, min(gs, 32), lane);
+    if (sqrt(red[0]) <= dbeta_tol * sqrt((P)gs)) return 0;   // :146-147
+    ps.cm = fmax(ps.cm, (double)(red[1] / gs));
+    ps.rsq += (double)red[2];
+    ps.resid_sum += (double)red[3];
+#pragma unroll 1
+    for (int r = lane; r < gs; r += 32) {                   // rotate back: a = at V^T
+        P an = 0;
+#pragma unroll 2
+        for (int c = 0; c < gs; ++c) an += p_at[c] * (P)V[r * gs + c];
+        const T anT = (T)an;
+        px.my_beta[begin + r] = anT;
+        px.s_del[r] = (T)(p_aold[r] - (P)anT);
+    }
+    return 1;
+}
+
 template <class T, bool SMEM>
 __global__ void __launch_bounds__(kSweepThreadsMax, 1)
 pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
@@ -273,14 +574,17 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     uint64_t* empty_bar = full_bar + kMaxStages;                               // [kMaxStages]
     uint64_t* desc_bar = empty_bar + kMaxStages;                               // [1]
     SweepCtrl* ctrl = reinterpret_cast<SweepCtrl*>(smem_raw + 128);
+    using P = T;                                     // compute type of the replicated proximal update
     const int gsc = a.gs_cap;
-    double* wpart = reinterpret_cast<double*>(smem_raw + SweepSmem<T>::kHeaderBytes);     // [NW][gsc]
-    double* wsum = wpart + (size_t)NW * gsc;                                                // [gsc][kLLSeg]
-    double* px = wsum + (size_t)gsc * kLLSeg;                                               // 8 x [gsc] prox scratch
-    double* p_aold = px, *p_A = px + gsc, *p_xm = px + 2 * gsc, *p_gk = px + 3 * gsc,
-          *p_gt = px + 4 * gsc, *p_atold = px + 5 * gsc, *p_at = px + 6 * gsc, *p_D = px + 7 * gsc;
-    T* s_del = reinterpret_cast<T*>(px + 8 * gsc);                                          // [gsc]
-    unsigned char* tiles = smem_raw + SweepSmem<T>::fixed_bytes(NW, gsc);
+    double* vals1 = reinterpret_cast<double*>(smem_raw + SweepSmem<T>::kHeaderBytes);       // [gsc][32] level-1 partials (group leaders)
+    double* vals2 = vals1 + (size_t)gsc * 32;                                               // [gsc][32] level-2 partials
+    double* gsum = vals2 + (size_t)gsc * 32;                                                // [gsc] all-reduced gradient
+    double* wpart = gsum + gsc;                                                             // [NW][gsc]
+    P* px = reinterpret_cast<P*>(wpart + (size_t)NW * gsc);                                 // 8 x [gsc] prox scratch
+    P* p_aold = px, *p_A = px + gsc, *p_gk = px + 2 * gsc, *p_gt = px + 3 * gsc, *p_atold = px + 4 * gsc, *p_at = px + 5 * gsc;
+    T* s_del = reinterpret_cast<T*>(reinterpret_cast<double*>(px) + 8 * gsc);               // [gsc]
+    P* p_scr = reinterpret_cast<P*>(reinterpret_cast<double*>(px) + 9 * gsc);               // [4 * 32] reduction scratch
+    unsigned char* tiles = smem_raw + SweepSmem<T>::fixed_bytes(NW, gsc, a.ncta_pad);
     T* sr = reinterpret_cast<T*>(tiles);
     T* sw = sr + a.rows_stride;
     T* stages = sw + a.rows_stride;
@@ -347,7 +651,13 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     // consumer warps
     // =========================================================================================
     const int ctid = tid;                       // consumer thread id (consumer warps come first)
-    const double l1 = a.lmda * a.alpha, l2 = a.lmda * (1.0 - a.alpha);
+    const P l1 = (P)(a.lmda * a.alpha), l2 = (P)(a.lmda * (1.0 - a.alpha));
+    // polling pattern of the LL exchange: thread t owns lines t, t + NTC, ... (line = column * ncta_pad + cta)
+    // two-level exchange geometry: level-1 groups of `fan` consecutive CTAs, led by their first member
+    const int fan = a.fan;
+    const int my_group = cta / fan, n_groups = (ncta + fan - 1) / fan;
+    const int grp_first = my_group * fan, grp_size = min(fan, ncta - grp_first);
+    const bool is_leader = (cta == grp_first);
 
     // resident r / w tiles
     T* gr = a.resid + r0;
@@ -361,6 +671,12 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     }
     T* rr = SMEM ? sr : gr;
     const T* ww = SMEM ? sw : gw;
+    T* my_beta = a.beta_rep + (size_t)cta * a.beta_stride;
+    for (int i = ctid; i < a.beta_len; i += NTC) my_beta[i] = a.beta_in[i];
+    int8_t* my_active = a.is_active_rep + (size_t)cta * a.act_stride;
+    const ProxCtx<T, P> proxctx{p_aold, p_A, p_gk, p_gt, p_atold, p_at, p_scr, s_del, gsum, my_beta};
+    for (int i = ctid; i < a.S; i += NTC) my_active[i] = a.is_active_in[i];
+    // (visibility to the control warp is ordered by the named barrier at the top of the first sweep)
 
     ProxState ps;
     ps.rsq = a.sc->rsq; ps.resid_sum = a.sc->resid_sum; ps.cm = 0; ps.A = a.sc->active_set_size; ps.error = 0;
@@ -368,9 +684,14 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     long long iters = a.sc->iters, n_updates = a.sc->n_group_updates;
     uint32_t epoch = dev::ld_cg(a.epoch);
     uint32_t gitem = 0;
+    int pending_stage = -1;
     int phase = kSweepActive;
     int final_error = 0;
-    const int nseg = a.ncta_pad / 32;
+    // phase profiling (thread 0 of CTA 0 only): 0 wait-full, 1 dot, 2 bar1+store, 3 poll, 4 prox, 5 bar3, 6 update, 7 newton iters, 8 items
+    const bool prof = (a.stats != nullptr) && cta == 0 && ctid == 0;
+    long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tc = 0;
+#define AB_TICK(k) do { if (prof) { const long long t_ = clock64(); pt[k] += t_ - tc; tc = t_; } } while (0)
 
     while (true) {
         // ---- publish the sweep descriptor
@@ -392,15 +713,12 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             const uint32_t use = SMEM ? gitem / a.n_stages : 0;
 
             // control warp: start fetching the current coefficients (latency hidden behind the dot phase)
-            double aold_r[kGsMax / 32];
             if (warp == 0) {
-#pragma unroll
-                for (int e = 0; e < kGsMax / 32; ++e) {
-                    const int c = lane + 32 * e;
-                    aold_r[e] = (c < gs) ? (double)dev::ld_cg(a.screen_beta + m.begin + c) : 0.0;
-                }
+#pragma unroll 1
+                for (int c = lane; c < gs; c += 32) p_aold[c] = (P)my_beta[m.begin + c];
             }
 
+            if (prof) tc = clock64();
             const T* xs; const T* rec; int64_t cs;
             if (SMEM) {
                 if (!dev::mbar_wait(&full_bar[stage], use & 1, abort_flag)) ctrl->abort = 1;
@@ -413,12 +731,15 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 rec = a.grec + m.rec_off;
             }
 
+            AB_TICK(0);
             // ---- dot phase: partial[c] = sum_{i in tile} X[i, col+c] * w[i] * r[i]
-            constexpr int CB = 8;
+            constexpr int CB = 16;
+#pragma unroll 1
             for (int c0 = 0; c0 < gs; c0 += CB) {
                 T acc[CB];
 #pragma unroll
                 for (int cc = 0; cc < CB; ++cc) acc[cc] = 0;
+#pragma unroll 1
                 for (int v = ctid; v < rows / VN; v += NTC) {
                     T rv[VN], wv[VN];
                     vec_load<T>(rr + (size_t)v * VN, rv);
@@ -436,122 +757,123 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                         }
                     }
                 }
-#pragma unroll
-                for (int cc = 0; cc < CB; ++cc) {
-                    if (c0 + cc < gs) {
-                        const double s = dev::warp_sum((double)acc[cc]);
-                        if (lane == 0) wpart[(size_t)warp * gsc + c0 + cc] = s;
-                    }
-                }
+                const T tot = warp_reduce16<T>(acc, lane);       // lane holds the warp total of column c0 + ((lane >> 1) & 15)
+                const int col = c0 + ((lane >> 1) & 15);
+                if ((lane & 1) == 0 && col < gs) wpart[(size_t)warp * gsc + col] = (double)tot;
             }
+            AB_TICK(1);
+            long long* trace = (a.stats != nullptr && ctid == 0 && n_updates == a.sc->n_group_updates + 40) ? a.stats + 32 + 8 * cta : nullptr;
+            if (trace) { trace[0] = (long long)(dev::global_ns() & 0xffffffffffull); }
             dev::named_bar_sync(1, NTC);
             if (ctrl->abort) { final_error = kErrAbort; break; }      // uniform: flag was set before the barrier
 
-            // ---- exchange: CTA partial -> LL line; then every CTA sums all lines in a fixed order
+            // ---- two-level exchange.  Level 1: every CTA publishes its partial (one flagged line per column); the leader
+            // of each group of `fan` CTAs reads its members' lines, adds them in member order and publishes the group
+            // partial.  Level 2: every CTA reads the n_groups group partials and adds them in group order.  Every CTA thus
+            // obtains the bitwise identical gradient while reading O(sqrt(#CTAs)) lines instead of O(#CTAs).
             const uint32_t par = epoch & 1u;
             if (ctid < gs) {
                 double s = 0;
+#pragma unroll 5
                 for (int w = 0; w < NW; ++w) s += wpart[(size_t)w * gsc + ctid];
-                if (ncta == 1) wsum[ctid * kLLSeg] = s;
+                if (ncta == 1) gsum[ctid] = s;
                 else dev::ll_store(a.ll + ((size_t)(par * a.ll_gs_cap + ctid) * a.ncta_pad + cta), s, epoch);
             }
+            AB_TICK(2);
+            if (trace) { trace[1] = (long long)(dev::global_ns() & 0xffffffffffull); }
+            ProxPre<P> pre{};
+            const bool small_group = (gs > 1 && gs <= 32);
+            if (warp == 0 && small_group) pre = prox_small_pre<T, P>(rec, gs, p_aold, lane);      // overlaps the exchange latency
             if (ncta > 1) {
                 bool ok = true;
-                for (int idx = ctid; idx < gs * a.ncta_pad; idx += NTC) {
-                    const int c = idx / a.ncta_pad, j = idx - c * a.ncta_pad;
+                if (is_leader) {                                         // CTA-uniform
+                    // thread t < gs * grp_size reads line (column t / grp_size, member t % grp_size)
+#pragma unroll 1
+                    for (int t = ctid; t < gs * grp_size; t += NTC) {
+                        const int c = t / grp_size, mth = t - c * grp_size;
+                        double v = 0.0;
+                        dev::SpinGuard guard;
+                        const dev::LLLine* line = a.ll + ((size_t)(par * a.ll_gs_cap + c) * a.ncta_pad + grp_first + mth);
+                        while (!dev::ll_try_load(line, epoch, v)) { if (guard.give_up(abort_flag, nullptr)) { ok = false; break; } }
+                        vals1[c * 32 + mth] = v;
+                    }
+                    dev::named_bar_sync(1, NTC);
+                    if (ctid < gs) {
+                        double s = 0;
+#pragma unroll 1
+                        for (int mth = 0; mth < grp_size; ++mth) s += vals1[ctid * 32 + mth];
+                        dev::ll_store(a.ll2 + ((size_t)(par * a.ll_gs_cap + ctid) * 32 + my_group), s, epoch);
+                    }
+                }
+#pragma unroll 1
+                for (int t = ctid; t < gs * n_groups; t += NTC) {
+                    const int c = t / n_groups, g = t - c * n_groups;
                     double v = 0.0;
-                    if (j < ncta) ok = dev::ll_wait(a.ll + ((size_t)(par * a.ll_gs_cap + c) * a.ncta_pad + j), epoch, v, abort_flag) && ok;
-                    v = dev::warp_sum(v);
-                    if (lane == 0) wsum[c * kLLSeg + (j >> 5)] = v;
+                    dev::SpinGuard guard;
+                    const dev::LLLine* line = a.ll2 + ((size_t)(par * a.ll_gs_cap + c) * 32 + g);
+                    while (!dev::ll_try_load(line, epoch, v)) { if (guard.give_up(abort_flag, nullptr)) { ok = false; break; } }
+                    vals2[c * 32 + g] = v;
                 }
                 if (!ok) ctrl->abort = 1;
             }
             ++epoch;
+            if (trace) { trace[2] = (long long)(dev::global_ns() & 0xffffffffffull); }
             dev::named_bar_sync(1, NTC);
             if (ctrl->abort) { final_error = kErrAbort; break; }      // uniform
+            // Hand the PREVIOUS group's stage back to the TMA producer only now: its refill burst (tens of KB per SM)
+            // then overlaps the proximal update, when the SM's load path is idle, instead of delaying the polling loads.
+            if (SMEM && pending_stage >= 0) {
+                if (lane == 0) dev::mbar_arrive(&empty_bar[pending_stage]);
+                pending_stage = -1;
+            }
+            if (ncta > 1 && warp == 0) {                                 // control warp: add the group partials in group order
+#pragma unroll 1
+                for (int c = lane; c < gs; c += 32) {
+                    double s = 0;
+#pragma unroll 1
+                    for (int g = 0; g < n_groups; ++g) s += vals2[c * 32 + g];
+                    gsum[c] = s;
+                }
+                __syncwarp();
+            }
+            AB_TICK(3);
+            if (trace) { trace[3] = (long long)(dev::global_ns() & 0xffffffffffull); }
 
             // ---- proximal update (control warp), replicated bit-for-bit in every CTA
             if (warp == 0) {
-                const int nsg = (ncta == 1) ? 1 : nseg;
                 int changed = 0;
-                const double pk = m.pen;
+                const P pk = (P)m.pen;
                 if (gs == 1) {                                           // solver_gaussian_pin_naive.hpp:75-108
-                    double g = 0;
-                    for (int sgi = 0; sgi < nsg; ++sgi) g += wsum[sgi];
-                    const double ak_old = __shfl_sync(0xffffffffu, aold_r[0], 0);
-                    const double A_kk = (double)rec[0], xm = (double)rec[1];
-                    double gk = g - xm * ps.resid_sum * (double)a.intercept + ak_old * A_kk;
-                    const double vv = fabs(gk) - l1 * pk;                // update_coordinate, pin_base.hpp:181-195
-                    double ak = (vv > 0.0) ? copysign(vv, gk) / (A_kk + l2 * pk) : 0.0;
-                    ak = (double)(T)ak;                                  // coefficients live in T
+                    const double g = gsum[0];
+                    __syncwarp();
+                    const P ak_old = p_aold[0];
+                    const P A_kk = (P)rec[0], xm = (P)rec[1];
+                    P gk = (P)g - xm * (P)ps.resid_sum * (P)a.intercept + ak_old * A_kk;
+                    const P vv = fabs(gk) - l1 * pk;                     // update_coordinate, pin_base.hpp:181-195
+                    P ak = (vv > P(0)) ? copysign(vv, gk) / (A_kk + l2 * pk) : P(0);
+                    ak = (P)(T)ak;                                       // coefficients live in T
                     gk -= ak_old * A_kk;
                     if (ak != ak_old) {
-                        const double del = ak - ak_old;
-                        ps.cm = fmax(ps.cm, A_kk * del * del);
-                        ps.rsq += del * (2 * gk - del * A_kk);
-                        ps.resid_sum -= xm * del;
-                        if (lane == 0) { a.screen_beta[m.begin] = (T)ak; s_del[0] = (T)(-del); }
+                        const P del = ak - ak_old;
+                        ps.cm = fmax(ps.cm, (double)(A_kk * del * del));
+                        ps.rsq += (double)(del * (2 * gk - del * A_kk));
+                        ps.resid_sum -= (double)(xm * del);
+                        if (lane == 0) { my_beta[m.begin] = (T)ak; s_del[0] = (T)(-del); }
                         changed = 1;
                     }
-                } else {                                                 // :109-164
-                    const T* Arec = rec; const T* xmrec = rec + gs; const T* V = rec + 2 * gs;
-#pragma unroll
-                    for (int e = 0; e < kGsMax / 32; ++e) {
-                        const int c = lane + 32 * e;
-                        if (c < gs) {
-                            double g = 0;
-                            for (int sgi = 0; sgi < nsg; ++sgi) g += wsum[c * kLLSeg + sgi];
-                            const double xm = (double)xmrec[c];
-                            if (a.intercept) g -= ps.resid_sum * xm;
-                            p_gk[c] = g; p_aold[c] = aold_r[e]; p_A[c] = (double)Arec[c]; p_xm[c] = xm;
-                        }
-                    }
-                    __syncwarp();
-                    for (int c = lane; c < gs; c += 32) {
-                        double gt = 0, ao = 0;
-                        for (int r = 0; r < gs; ++r) {
-                            const double vrc = (double)V[r * gs + c];
-                            gt += p_gk[r] * vrc; ao += p_aold[r] * vrc;
-                        }
-                        gt += p_A[c] * ao;
-                        p_gt[c] = gt; p_atold[c] = ao;
-                    }
-                    const double l1k = l1 * pk, l2k = l2 * pk;
-                    __syncwarp();
-                    int nit = 0;
-                    warp_prox_newton(p_A, p_gt, gs, l1k, l2k, a.newton_tol, a.newton_max_iters, false, p_D, p_at, nit, lane);
-                    ps.newton_iters_max = max(ps.newton_iters_max, nit);
-                    if (nit >= a.newton_max_iters) ps.error = kErrNewton;
-                    __syncwarp();
-                    double dn = 0, cmv = 0, rs = 0;
-                    for (int c = lane; c < gs; c += 32) {
-                        const double gt0 = p_gt[c] - p_A[c] * p_atold[c];
-                        const double d = p_at[c] - p_atold[c];
-                        dn += d * d; cmv += p_A[c] * d * d; rs += d * (2 * gt0 - d * p_A[c]);
-                    }
-                    dn = dev::warp_sum(dn); cmv = dev::warp_sum(cmv); rs = dev::warp_sum(rs);
-                    if (!(sqrt(dn) <= a.dbeta_tol * sqrt((double)gs))) {  // :146-147
-                        ps.cm = fmax(ps.cm, cmv / gs);
-                        ps.rsq += rs;
-                        double rsum = 0;
-                        for (int r = lane; r < gs; r += 32) {
-                            double an = 0;
-                            for (int c = 0; c < gs; ++c) an += p_at[c] * (double)V[r * gs + c];
-                            const T anT = (T)an;
-                            a.screen_beta[m.begin + r] = anT;
-                            const double del = p_aold[r] - (double)anT;
-                            s_del[r] = (T)del;
-                            rsum += p_xm[r] * del;
-                        }
-                        ps.resid_sum += dev::warp_sum(rsum);
-                        changed = 1;
-                    }
+                } else if (small_group) {                                // :109-164, one coefficient per lane
+                    changed = prox_small_post<T, P>(proxctx, pre, rec, gs, m.begin, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters,
+                                                    (P)a.dbeta_tol, a.intercept, ps, lane, prof ? &pt[7] : nullptr);
+                } else {                                                 // :109-164, general group size
+                    changed = prox_group<T, P>(proxctx, rec, gs, m.begin, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters,
+                                               (P)a.dbeta_tol, a.intercept, ps, lane, prof ? &pt[7] : nullptr);
                 }
                 if (changed && kind == kSweepScreen) {                   // add_active_set (:294-304)
-                    if (!dev::ld_cg(a.is_active + ss)) {
+                    if (!my_active[ss]) {
                         if (ps.A >= a.max_active_size) ps.error = kErrMaxActive;
                         else {
-                            if (lane == 0) { a.is_active[ss] = 1; a.active_set[ps.A] = ss; }
+                            __syncwarp();
+                            if (lane == 0) { my_active[ss] = 1; a.active_set[ps.A] = ss; }
                             ++ps.A;
                         }
                     }
@@ -560,30 +882,48 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 __syncwarp();
             }
             ++n_updates;
+            AB_TICK(4);
+            if (trace) { trace[4] = (long long)(dev::global_ns() & 0xffffffffffull); }
             dev::named_bar_sync(1, NTC);
+            const int changed_now = ctrl->changed;
+            AB_TICK(5);
 
             // ---- residual update from the same X tile: r += X_g * del
-            if (ctrl->changed) {
-                for (int v = ctid; v < rows / VN; v += NTC) {
-                    T rv[VN];
-                    vec_load<T>(rr + (size_t)v * VN, rv);
-                    for (int c = 0; c < gs; ++c) {
-                        const T d = s_del[c];
-                        T xv[VN];
-                        vec_load<T>(xs + (int64_t)c * cs + (size_t)v * VN, xv);
+            if (changed_now) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < gs; c0 += CB) {
+                    T d[CB];
 #pragma unroll
-                        for (int k = 0; k < VN; ++k) rv[k] += xv[k] * d;
+                    for (int cc = 0; cc < CB; ++cc) d[cc] = (c0 + cc < gs) ? s_del[c0 + cc] : T(0);
+#pragma unroll 1
+                    for (int v = ctid; v < rows / VN; v += NTC) {
+                        T rv[VN];
+                        vec_load<T>(rr + (size_t)v * VN, rv);
+#pragma unroll
+                        for (int cc = 0; cc < CB; ++cc) {
+                            if (c0 + cc < gs) {
+                                T xv[VN];
+                                vec_load<T>(xs + (int64_t)(c0 + cc) * cs + (size_t)v * VN, xv);
+#pragma unroll
+                                for (int k = 0; k < VN; ++k) rv[k] += xv[k] * d[cc];
+                            }
+                        }
+                        vec_store<T>(rr + (size_t)v * VN, rv);
                     }
-                    vec_store<T>(rr + (size_t)v * VN, rv);
                 }
             }
             const int err_now = ctrl->error;
-            if (SMEM) {
-                __syncwarp();
-                if (lane == 0) dev::mbar_arrive(&empty_bar[stage]);
-            }
+            pending_stage = SMEM ? stage : -1;      // released after the NEXT exchange (see below)
             ++gitem;
+            AB_TICK(6);
+            if (trace) { trace[5] = (long long)(dev::global_ns() & 0xffffffffffull); }
+            if (prof) ++pt[8];
             if (err_now) { final_error = err_now; break; }
+        }
+        if (SMEM && pending_stage >= 0) {           // sweep finished (or failed): hand the last stage back right away
+            __syncwarp();
+            if (lane == 0) dev::mbar_arrive(&empty_bar[pending_stage]);
+            pending_stage = -1;
         }
         if (final_error) break;
 
@@ -621,6 +961,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
         a.sc->iters = iters; a.sc->n_group_updates = n_updates; a.sc->error = final_error;
         a.sc->newton_iters_max = ps.newton_iters_max;
         *a.epoch = epoch;
+        if (prof) for (int k = 0; k < 10; ++k) a.stats[k] += pt[k];
     }
 }
 

@@ -21,7 +21,7 @@ from . import matrix as _matrix
 logger = logging.getLogger("adelie_b200")
 
 _VEC_F = ["lmda_path", "screen_beta", "grad", "abs_grad", "devs", "lmdas", "X_means", "screen_X_means", "screen_vars",
-          "resid", "eta", "benchmark_screen", "benchmark_fit_screen", "benchmark_fit_active", "benchmark_kkt",
+          "resid", "eta", "sweep_stats", "benchmark_screen", "benchmark_fit_screen", "benchmark_fit_active", "benchmark_kkt",
           "benchmark_invariance"]
 _VEC_I = ["screen_set", "screen_begins", "screen_is_active", "active_set", "n_valid_solutions", "active_sizes", "screen_sizes"]
 _SCALARS = ["lmda_max", "lmda", "rsq", "resid_sum", "y_mean", "y_var", "loss_null", "loss_full", "beta0", "active_set_size",
@@ -82,7 +82,7 @@ class base:
         _lib.check(L.ab_state_get_vec_f64(self._handle, name.encode(), None, 0, C.byref(n)))
         buf = np.empty(n.value, dtype=np.float64)
         _lib.check(L.ab_state_get_vec_f64(self._handle, name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
-        if name.startswith("benchmark"):
+        if name.startswith("benchmark") or name == "sweep_stats":
             return buf
         return buf.astype(self._dtype if dtype is None else dtype)
 
