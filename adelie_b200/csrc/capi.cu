@@ -43,6 +43,26 @@ int ab_get_device_info(int* sm_count, size_t* smem, size_t* total_mem) {
     AB_CATCH
 }
 int ab_device_synchronize(void) { AB_TRY AB_CUDA(cudaDeviceSynchronize()); AB_CATCH }
+int ab_host_register(void* ptr, size_t bytes) { AB_TRY AB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); AB_CATCH }
+int ab_host_unregister(void* ptr) { AB_TRY AB_CUDA(cudaHostUnregister(ptr)); AB_CATCH }
+// CUDA-event stopwatch on the stream every kernel of this library is launched on (the default stream)
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+int ab_timer_start(void) {
+    AB_TRY
+    if (!g_ev0) { AB_CUDA(cudaEventCreate(&g_ev0)); AB_CUDA(cudaEventCreate(&g_ev1)); }
+    AB_CUDA(cudaDeviceSynchronize());
+    AB_CUDA(cudaEventRecord(g_ev0, 0));
+    AB_CATCH
+}
+int ab_timer_stop(double* ms) {
+    AB_TRY
+    if (!g_ev0) throw core_error("ab_timer_stop() without ab_timer_start().");
+    AB_CUDA(cudaEventRecord(g_ev1, 0));
+    AB_CUDA(cudaEventSynchronize(g_ev1));
+    float f = 0; AB_CUDA(cudaEventElapsedTime(&f, g_ev0, g_ev1));
+    *ms = f;
+    AB_CATCH
+}
 
 int ab_configs_set(const char* name, double value) {
     const std::string s(name);
@@ -439,6 +459,7 @@ static int state_scalar(const PathState<T>& s, const std::string& nm, double* ou
     else if (nm == "beta0") *out = s.beta0; else if (nm == "active_set_size") *out = (double)s.active_set_size;
     else if (nm == "alpha") *out = s.alpha; else if (nm == "tol") *out = s.tol;
     else if (nm == "n_sweeps") *out = (double)s.n_sweeps; else if (nm == "n_group_updates") *out = (double)s.n_group_updates;
+    else if (nm == "n_col_updates") *out = (double)s.n_col_updates;
     else if (nm == "n_irls") *out = (double)s.n_irls; else if (nm == "n_pin_solves") *out = (double)s.n_pin_solves;
     else if (nm == "n_kernel_launches") *out = (double)s.n_kernel_launches;
     else if (nm == "time_sweep_kernel") *out = s.time_sweep_kernel;

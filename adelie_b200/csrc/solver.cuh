@@ -121,7 +121,7 @@ struct PathState {
     std::vector<SparseRow> betas; std::vector<T> intercepts, devs, lmdas;
     std::vector<double> benchmark_screen, benchmark_fit_screen, benchmark_fit_active, benchmark_kkt, benchmark_invariance;
     std::vector<int> n_valid_solutions, active_sizes, screen_sizes;
-    long long n_sweeps = 0, n_group_updates = 0, n_irls = 0, n_pin_solves = 0, n_kernel_launches = 0;
+    long long n_sweeps = 0, n_group_updates = 0, n_col_updates = 0, n_irls = 0, n_pin_solves = 0, n_kernel_launches = 0;
     double sweep_bytes = 0;          // algorithmic HBM bytes of all sweeps: s*n*sum gs + 3*s*n per sweep (estimated)
     double time_sweep_kernel = 0;    // CUDA-event time spent inside the fused kernel (s)
     // ---------------- device
@@ -335,7 +335,7 @@ struct PathState {
             for (size_t i = 0; i < nw.size(); ++i) active_set[old_active + i] = nw[i];
         }
         rsq_io = (T)sc.rsq; resid_sum_io = (T)sc.resid_sum;
-        n_sweeps += sc.iters; n_group_updates += sc.n_group_updates;
+        n_sweeps += sc.iters; n_group_updates += sc.n_group_updates; n_col_updates += sc.n_col_updates;
         PinResult R;
         R.iters = sc.iters; R.rsq = sc.rsq;
         R.active_time = ms * 1e-3; R.screen_time = 0;   // one fused launch: not separable without extra syncs

@@ -42,7 +42,7 @@ struct GroupMeta {          // one per screen position (32 bytes)
 
 struct PinScalars {         // device-resident in/out scalars of one pin solve
     double rsq, resid_sum;
-    long long iters, n_group_updates;
+    long long iters, n_group_updates, n_col_updates;   // sweeps, group visits, sum of group sizes over the visits
     int active_set_size, error, newton_iters_max, pad;
 };
 
@@ -681,7 +681,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     ProxState ps;
     ps.rsq = a.sc->rsq; ps.resid_sum = a.sc->resid_sum; ps.cm = 0; ps.A = a.sc->active_set_size; ps.error = 0;
     ps.newton_iters_max = 0;
-    long long iters = a.sc->iters, n_updates = a.sc->n_group_updates;
+    long long iters = a.sc->iters, n_updates = a.sc->n_group_updates, n_cols = a.sc->n_col_updates;
     uint32_t epoch = dev::ld_cg(a.epoch);
     uint32_t gitem = 0;
     int pending_stage = -1;
@@ -881,7 +881,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 if (lane == 0) { ctrl->changed = changed; ctrl->error = ps.error; }
                 __syncwarp();
             }
-            ++n_updates;
+            ++n_updates; n_cols += gs;
             AB_TICK(4);
             if (trace) { trace[4] = (long long)(dev::global_ns() & 0xffffffffffull); }
             dev::named_bar_sync(1, NTC);
@@ -958,7 +958,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     }
     if (cta == 0 && ctid == 0) {
         a.sc->rsq = ps.rsq; a.sc->resid_sum = ps.resid_sum; a.sc->active_set_size = ps.A;
-        a.sc->iters = iters; a.sc->n_group_updates = n_updates; a.sc->error = final_error;
+        a.sc->iters = iters; a.sc->n_group_updates = n_updates; a.sc->n_col_updates = n_cols; a.sc->error = final_error;
         a.sc->newton_iters_max = ps.newton_iters_max;
         *a.epoch = epoch;
         if (prof) for (int k = 0; k < 10; ++k) a.stats[k] += pt[k];

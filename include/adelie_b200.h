@@ -32,6 +32,11 @@ int ab_device_count(int* count);
 int ab_set_device(int device);
 int ab_get_device_info(int* sm_count, size_t* smem_optin_bytes, size_t* total_mem_bytes);
 int ab_device_synchronize(void);
+/* pin / unpin a host buffer (bench: H2D from pinned memory); CUDA-event stopwatch on the library's stream */
+int ab_host_register(void* ptr, size_t bytes);
+int ab_host_unregister(void* ptr);
+int ab_timer_start(void);
+int ab_timer_stop(double* elapsed_ms);
 
 /* ---- configs: adelie/src/py_configs.cpp:6-47, include/adelie_core/configs.hpp:6-20 ---------- */
 int ab_configs_set(const char* name, double value);
