@@ -163,6 +163,7 @@ class base:
         _lib.check(L.ab_state_get_betas(self._handle, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values), C.byref(nnz), C.byref(nl)))
         p = self._p_cols
         B = scipy.sparse.csr_matrix((values.astype(self._dtype), indices, indptr), shape=(nl.value, p))
+        B.indices = B.indices.astype(np.int64); B.indptr = B.indptr.astype(np.int64)     # int64 like the reference (py_state.cpp:9-60)
         return B
 
     @property

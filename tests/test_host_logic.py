@@ -1,0 +1,73 @@
+"""CPU: Python host-side logic of the drop-in surface that needs no device."""
+import numpy as np
+import pytest
+
+import adelie_b200 as ad
+
+
+def test_glm_weight_normalisation_and_checks():          # adelie/glm.py:40-55
+    y = np.arange(5.0)
+    g = ad.glm.gaussian(y, weights=np.array([1.0, 1, 2, 0, 0]))
+    assert np.isclose(g.weights.sum(), 1) and g.weights[2] == 0.5
+    assert g.name == "gaussian" and g.opt and not g.is_multi and g.dtype == np.float64
+    assert np.allclose(ad.glm.gaussian(y).weights, 0.2)
+    with pytest.raises(RuntimeError):
+        ad.glm.gaussian(y, weights=np.ones(4))
+    with pytest.raises(RuntimeError):
+        ad.glm.gaussian(np.zeros((3, 2)))
+    with pytest.raises(RuntimeError):
+        ad.glm.gaussian(np.arange(5))                    # integer dtype without explicit dtype
+    m = ad.glm.multigaussian(np.zeros((4, 3)))
+    assert m.is_multi and m.name == "multigaussian"
+    b = ad.glm.binomial(np.array([0.0, 1, 1]), dtype=np.float32)
+    assert b.name == "binomial_logit" and b.dtype == np.float32 and b.y.dtype == np.float32
+    r = b.reweight(np.array([0.0, 1, 1]))
+    assert np.allclose(r.weights, [0, 0.5, 0.5])
+
+
+def test_dense_factory_checks():                         # adelie/matrix.py:549-680
+    X = np.zeros((4, 3))
+    with pytest.warns(UserWarning):
+        M = ad.matrix.dense(X)                           # C-contiguous -> warning
+    assert M.shape == (4, 3) and M.ndim == 2 and M.rows() == 4 and M.cols() == 3 and M.dtype == np.float64
+    with pytest.raises(RuntimeError):
+        ad.matrix.dense(X.astype(np.int32))
+    with pytest.raises(RuntimeError):
+        ad.matrix.dense(np.asfortranarray(X), n_threads=0)
+    with pytest.raises(RuntimeError):
+        ad.matrix.dense(np.asfortranarray(X), method="cov")
+    M = ad.matrix.dense(np.asfortranarray(X))
+    with pytest.raises(RuntimeError, match="cmul"):
+        M.cmul(7, np.zeros(4), np.zeros(4))              # out-of-range column: the reference's message, before touching the device
+    with pytest.raises(RuntimeError, match="bmul"):
+        M.bmul(2, 2, np.zeros(4), np.zeros(4), np.zeros(2))
+    with pytest.raises(RuntimeError, match="btmul"):
+        M.btmul(0, 2, np.zeros(3), np.zeros(4))
+
+
+def test_data_generator_semantics():                     # adelie/data.py:84-219
+    d = ad.data.dense(50, 20, 5, seed=0)
+    assert d["X"].shape == (50, 20) and d["X"].flags.f_contiguous
+    assert d["groups"][0] == 0 and len(d["groups"]) == 5 and d["group_sizes"].sum() == 20
+    assert np.isclose(np.linalg.norm(d["penalty"]), np.sqrt(20))
+    d2 = ad.data.dense(50, 20, 5, seed=0)
+    assert np.array_equal(d["X"], d2["X"]) and np.array_equal(d["glm"].y, d2["glm"].y)
+    e = ad.data.dense(30, 12, 4, equal_groups=True, glm="binomial", seed=1)
+    assert np.array_equal(e["groups"], [0, 3, 6, 9]) and set(np.unique(e["glm"].y)) <= {0.0, 1.0}
+
+
+def test_configs_defaults():
+    assert ad.configs.Configs.hessian_min_def == 1e-24 and ad.configs.Configs.dbeta_tol_def == 1e-12
+    with pytest.raises(RuntimeError):
+        ad.set_configs("nonexistent", 1)
+    ad.set_configs("hessian_min", 1e-20)
+    assert ad.configs.Configs.hessian_min == 1e-20
+    ad.set_configs("hessian_min", None)
+    assert ad.configs.Configs.hessian_min == 1e-24
+
+
+def test_constraints_rejected():
+    from adelie_b200.state import _check_constraints
+    _check_constraints(None); _check_constraints([None, None])
+    with pytest.raises(RuntimeError):
+        _check_constraints([object()])
