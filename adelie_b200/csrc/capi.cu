@@ -467,6 +467,10 @@ static int state_scalar(const PathState<T>& s, const std::string& nm, double* ou
     else if (nm == "sweep_smem_bytes") *out = (double)s.X->last_geom.smem_bytes; else if (nm == "sweep_staged") *out = s.X->last_geom.smem ? 1 : 0;
     else if (nm == "sweep_threads") *out = s.X->last_geom.threads;
     else if (nm == "setup_lmda_max") *out = s.setup_lmda_max; else if (nm == "setup_lmda_path") *out = s.setup_lmda_path;
+    else if (nm.rfind("t_", 0) == 0) {
+        *out = 0;
+        for (const auto& kv : s.timers.acc) if (kv.first == nm.substr(2)) *out = kv.second;
+    }
     else { g_last_error = "adelie_core: unknown state scalar " + nm; return AB_ERR_ARG; }
     return AB_OK;
 }

@@ -25,7 +25,7 @@ inline void host_jacobi_eigh(std::vector<double>& A, int q, std::vector<double>&
     for (int sweep = 0; sweep < 64; ++sweep) {
         double off = 0, diag = 0;
         for (int a = 0; a < q; ++a) for (int b = 0; b < q; ++b) { const double x = A[(size_t)a * q + b]; if (a == b) diag += x * x; else off += x * x; }
-        if (off <= 1e-34 * (diag + off) || off == 0) break;
+        if (off <= 1e-31 * (diag + off) || off == 0) break;     // off-diagonal mass below (eps)^2 of the total
         for (int pi = 0; pi < q - 1; ++pi) for (int qi = pi + 1; qi < q; ++qi) {
             const double apq = A[(size_t)pi * q + qi];
             if (apq == 0) continue;
@@ -85,6 +85,22 @@ inline int search_pivot(const std::vector<T>& x, const std::vector<T>& y, std::v
 
 struct SparseRow { std::vector<int64_t> idx; std::vector<double> val; };
 
+// Host wall-clock accounting of the path driver (exposed as state scalars "t_<label>")
+struct HostTimers {
+    std::vector<std::pair<std::string, double>> acc;
+    double& slot(const char* name) {
+        for (auto& kv : acc) if (kv.first == name) return kv.second;
+        acc.emplace_back(name, 0.0);
+        return acc.back().second;
+    }
+    struct Scope {
+        double& dst; double t0;
+        Scope(double& d) : dst(d), t0(now_s()) {}
+        ~Scope() { dst += now_s() - t0; }
+    };
+};
+#define AB_TIME(timers, name) ::ab::HostTimers::Scope _ab_scope_##__LINE__((timers).slot(name))
+
 // Output of one pin solve (the slice of StateGaussianPinNaive the path driver reads back)
 struct PinResult { SparseRow beta; double intercept = 0, rsq = 0; double screen_time = 0, active_time = 0; long long iters = 0; };
 
@@ -124,6 +140,7 @@ struct PathState {
     long long n_sweeps = 0, n_group_updates = 0, n_col_updates = 0, n_irls = 0, n_pin_solves = 0, n_kernel_launches = 0;
     double sweep_bytes = 0;          // algorithmic HBM bytes of all sweeps: s*n*sum gs + 3*s*n per sweep (estimated)
     double time_sweep_kernel = 0;    // CUDA-event time spent inside the fused kernel (s)
+    HostTimers timers;
     // ---------------- device
     DevBuf<T> d_weights, d_weights_sqrt, d_resid, d_resid_prev, d_X_means, d_grad;
     DevBuf<T> d_offsets, d_eta, d_eta_prev, d_glm_resid_prev, d_hess, d_irls_w, d_irls_wsqrt, d_irls_y, d_irls_resid;
@@ -178,6 +195,7 @@ struct PathState {
 
     // ------------------------------------------------------------------ solver_base.hpp:20-110 (constraints == nullptr)
     void update_abs_grad(T lmda_) {
+        AB_TIME(timers, "abs_grad");
         for (size_t ss = 0; ss < screen_set.size(); ++ss) {
             const idx_t i = screen_set[ss], b = screen_begins[ss], k = groups[i], sz = group_sizes[i];
             const T regul = ((1 - alpha) * lmda_) * penalty[i];
@@ -216,18 +234,21 @@ struct PathState {
         const size_t vs = S ? (screen_begins.back() + group_sizes[screen_set.back()]) : 0;
         sXm.resize(vs); st.resize(S); sv.resize(vs, 0);
         if (begin >= end) return;
+        AB_TIME(timers, "screen_records");
         std::vector<CovItem> items; int64_t c_total = 0;
         for (size_t i = begin; i < end; ++i) {
             const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g];
             items.push_back(CovItem{(int32_t)groups[g], gs, c_total});
             c_total += (int64_t)gs * gs;
         }
+        double t_cov0 = now_s();
         d_cov_items.reserve_keep(items.size()); d_cov_out.reserve_keep(c_total);
         d_cov_items.upload(items.data(), items.size());
         X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p);
         std::vector<double> C(c_total);
         d_cov_out.download(C.data(), c_total);
         AB_CUDA(cudaStreamSynchronize(0));
+        timers.slot("cov_device") += now_s() - t_cov0;
         n_kernel_launches += 2;
         meta.resize(S);
         std::vector<double> Cg, D, V;
@@ -286,6 +307,7 @@ struct PathState {
     // ------------------------------------------------------------------ the fused pin solve
     // Runs pin::naive::solve (solver_gaussian_pin_naive.hpp:223-401) for one lambda on the device.
     PinResult run_pin(T* d_r, const T* d_w, T lmda_, T tol_pin, T y_mean_, T& rsq_io, T& resid_sum_io) {
+        AB_TIME(timers, "run_pin");
         const size_t S = screen_set.size();
         d_screen_beta.reserve_keep(screen_beta.size() + 4); d_is_active.reserve_keep(S + 4);
         d_screen_beta.upload(screen_beta.data(), screen_beta.size());
@@ -376,6 +398,7 @@ struct PathState {
 
     // update_invariance (solver_gaussian_naive.hpp:377-393 / solver_glm_naive.hpp:495-503)
     void update_invariance(T lmda_) {
+        AB_TIME(timers, "invariance");
         lmda = lmda_;
         if (is_glm) {
             X->d_mul(d_resid.p, X->d_ones(), d_grad.p);
@@ -392,6 +415,7 @@ struct PathState {
     }
 
     void update_solutions(PinResult& pr, T lmda_) {
+        AB_TIME(timers, "update_solutions");
         betas.emplace_back(std::move(pr.beta));
         intercepts.push_back((T)pr.intercept);
         lmdas.push_back(lmda_);
@@ -405,6 +429,7 @@ struct PathState {
 
     // screen (solver_base.hpp:273-403)
     void screen(T lmda_next, bool all_kkt_passed, int n_new_active) {
+        AB_TIME(timers, "screen_host");
         const int old_size = (int)screen_set.size();
         auto is_screen = [&](idx_t i) { return screen_hashset.count(i) > 0; };
         if (screen_rule == 0) {

@@ -103,6 +103,8 @@ class base:
             return int(v) if name in ("active_set_size", "n_sweeps", "n_group_updates", "n_col_updates", "n_irls", "n_pin_solves",
                                       "n_kernel_launches", "sweep_ncta", "sweep_stages", "sweep_smem_bytes",
                                       "sweep_staged", "sweep_threads") else self._dtype(v) if name not in ("time_sweep_kernel",) else v
+        if name.startswith("t_"):
+            return self._scalar(name)
         if name in _VEC_F:
             return self._vec_f(name)
         if name in _VEC_I:

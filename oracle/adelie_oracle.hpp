@@ -419,7 +419,7 @@ inline void jacobi_eigh(T* A /*q x q col-major, destroyed*/, idx_t q, T* D, T* V
                 const double x = (double)A[a + b * q];
                 if (a == b) diag += x * x; else off += x * x;
             }
-        if (off <= 1e-34 * (diag + off) || off == 0) break;
+        if (off <= 1e-31 * (diag + off) || off == 0) break;     // off-diagonal mass below (eps)^2 of the total
         for (idx_t pI = 0; pI < q - 1; ++pI) {
             for (idx_t qI = pI + 1; qI < q; ++qI) {
                 const T apq = A[pI + qI * q];
