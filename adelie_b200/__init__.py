@@ -10,6 +10,7 @@ from . import bcd
 from . import configs
 from . import data
 from . import diagnostic
+from . import dist
 from . import glm
 from . import matrix
 from . import solver

@@ -52,6 +52,7 @@ _lib = None
 # every symbol declared in include/adelie_b200.h (checked by tests/test_cabi.py)
 SYMBOLS = [
     "ab_last_error", "ab_version", "ab_device_count", "ab_set_device", "ab_get_device_info", "ab_device_synchronize", "ab_host_register", "ab_host_unregister", "ab_timer_start", "ab_timer_stop",
+    "ab_dist_init", "ab_dist_connect", "ab_dist_allreduce_f64", "ab_dist_info",
     "ab_configs_set", "ab_configs_get",
     "ab_matrix_dense_create", "ab_matrix_dense_alloc", "ab_matrix_dense_fill_normal", "ab_matrix_dense_download",
     "ab_matrix_free", "ab_matrix_rows", "ab_matrix_cols", "ab_matrix_cmul", "ab_matrix_ctmul", "ab_matrix_bmul",
@@ -119,6 +120,10 @@ def load():
     L.ab_host_register.argtypes = [c_vp, C.c_size_t]
     L.ab_host_unregister.argtypes = [c_vp]
     L.ab_timer_stop.argtypes = [C.POINTER(C.c_double)]
+    L.ab_dist_init.argtypes = [C.c_int, C.c_int, c_vp]
+    L.ab_dist_connect.argtypes = [c_vp]
+    L.ab_dist_allreduce_f64.argtypes = [c_vp, c_i64]
+    L.ab_dist_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.ab_get_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L
     return L

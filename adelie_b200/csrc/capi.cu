@@ -6,6 +6,7 @@
 #include "sweep.cuh"
 #include "dense_kernels.cuh"
 #include "matrix.cuh"
+#include "dist.cuh"
 #include "glm.cuh"
 #include "solver.cuh"
 #include "solver_glm.cuh"
@@ -94,6 +95,34 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "device_eigh") *value = Configs::device_eigh;
     else if (s == "sweep_profile") *value = Configs::sweep_profile;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
+    return AB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU
+int ab_dist_init(int rank, int world, void* ipc_handle_out /* 64 bytes */) {
+    AB_TRY
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    DistContext::get().create(rank, world, (cudaIpcMemHandle_t*)ipc_handle_out);
+    // all ranks restart the sweep epoch together so that the flagged lines of the level-3 exchange agree
+    uint32_t one = 1; SweepContext::get().epoch.upload(&one, 1);
+    AB_CUDA(cudaMemset(SweepContext::get().ll.p, 0, SweepContext::get().ll.n * sizeof(dev::LLLine)));
+    AB_CUDA(cudaMemset(SweepContext::get().ll2.p, 0, SweepContext::get().ll2.n * sizeof(dev::LLLine)));
+    AB_CUDA(cudaDeviceSynchronize());
+    AB_CATCH
+}
+int ab_dist_connect(const void* all_handles /* world x 64 bytes, rank order */) {
+    AB_TRY
+    DistContext::get().connect((const cudaIpcMemHandle_t*)all_handles);
+    AB_CATCH
+}
+int ab_dist_allreduce_f64(double* host_buf, int64_t n) {
+    AB_TRY
+    DistContext::get().allreduce_host(host_buf, n);
+    AB_CATCH
+}
+int ab_dist_info(int* rank, int* world) {
+    *rank = DistContext::get().active() ? DistContext::get().rank : 0;
+    *world = DistContext::get().active() ? DistContext::get().world : 1;
     return AB_OK;
 }
 

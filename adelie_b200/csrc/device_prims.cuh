@@ -63,10 +63,16 @@ __device__ __forceinline__ void ll_store(LLLine* line, double v, uint32_t epoch)
     const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
     asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch) : "memory");
 }
-// system-scope variant for lines that live in a peer GPU's memory (NVLink P2P store)
+// system-scope variants for lines that live in / are written from a peer GPU's memory (NVLink P2P)
 __device__ __forceinline__ void ll_store_sys(LLLine* line, double v, uint32_t epoch) {
     const uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch) : "memory");
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(line), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load_sys(const LLLine* line, uint32_t epoch, double& out) {
+    uint32_t d0, f0, d1, f1;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(line) : "memory");
+    if (f0 == epoch && f1 == epoch) { out = __hiloint2double((int)d1, (int)d0); return true; }
+    return false;
 }
 __device__ __forceinline__ bool ll_try_load(const LLLine* line, uint32_t epoch, double& out) {
     uint32_t d0, f0, d1, f1;

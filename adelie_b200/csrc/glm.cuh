@@ -5,6 +5,7 @@
 #pragma once
 #include "common.cuh"
 #include "device_prims.cuh"
+#include "dist.cuh"
 
 namespace ab {
 
@@ -56,6 +57,7 @@ struct MapReduce {
         map_reduce_kernel<NS, F><<<nb, kMapThreads, 0, st>>>(n, f, part.p);
         if (NS > 0) {
             map_reduce_final_kernel<NS><<<1, 32, 0, st>>>(part.p, nb, out.p);
+            DistContext::get().allreduce<double>(out.p, NS, st);                // row-sharded: every sum is a sum over all ranks' rows
             out.download(h_out.p, NS, 0, st);
             AB_CUDA(cudaStreamSynchronize(st));
             for (int s = 0; s < NS; ++s) sums[s] = h_out.p[s];

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "dense_kernels.cuh"
 #include "sweep.cuh"
+#include "dist.cuh"
 #include <cuda.h>
 #include <curand_kernel.h>
 
@@ -217,6 +218,11 @@ struct DenseMatrix {
         a.ll2 = ctx.ll2.p;
         { int f = 1; while (f * f < g.ncta) ++f; a.fan = std::max(1, f); }      // fan = ceil(sqrt(ncta)) => n_groups <= fan + 1 <= 32
         a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
+        {
+            DistContext& dc = DistContext::get();
+            a.rank = dc.active() ? dc.rank : 0; a.world = dc.active() ? dc.world : 1;
+            for (int r = 0; r < kMaxRanksDev; ++r) a.ll3_peer[r] = (dc.active() && r < dc.world) ? dc.ll3(r) : nullptr;
+        }
         a.lmda = L.lmda; a.alpha = L.alpha; a.tol = L.tol; a.newton_tol = L.newton_tol; a.dbeta_tol = Configs::dbeta_tol;
         a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
         a.units_base = g.units_base; a.units_rem = g.units_rem; a.rows_stride = g.rows_stride;

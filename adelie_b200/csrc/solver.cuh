@@ -245,6 +245,7 @@ struct PathState {
         d_cov_items.reserve_keep(items.size()); d_cov_out.reserve_keep(c_total);
         d_cov_items.upload(items.data(), items.size());
         X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p);
+        DistContext::get().allreduce<double>(d_cov_out.p, c_total);            // row-sharded: sum the local Gram blocks over ranks
         std::vector<double> C(c_total);
         d_cov_out.download(C.data(), c_total);
         AB_CUDA(cudaStreamSynchronize(0));
@@ -327,6 +328,7 @@ struct PathState {
         L.max_active_size = (int)std::min<size_t>(max_active_size, (size_t)G); L.intercept = intercept ? 1 : 0;
         L.gs_max = gs_max_screen; L.rec_max = rec_max_screen;
         if (check_interrupt) check_interrupt();
+        if (DistContext::get().active()) DistContext::get().allreduce<double>(d_scal.p, 1);    // cheap rank barrier
         AB_CUDA(cudaEventRecord(ev0, 0));
         X->pin_solve(L);
         AB_CUDA(cudaEventRecord(ev1, 0));
@@ -400,16 +402,22 @@ struct PathState {
     void update_invariance(T lmda_) {
         AB_TIME(timers, "invariance");
         lmda = lmda_;
+        DistContext& dc = DistContext::get();
         if (is_glm) {
             X->d_mul(d_resid.p, X->d_ones(), d_grad.p);
-        } else {
+            dc.allreduce<T>(d_grad.p, p);
+        } else if (!dc.active()) {
             // grad = X^T (w o r) - resid_sum * X_means, epilogue fused into the reduction kernel
             const double rs = (double)resid_sum;
             X->d_gemv_t(0, nullptr, (int)p, d_resid.p, d_weights.p, d_grad.p, false,
                         intercept ? d_X_means.p : nullptr, nullptr, rs);
+        } else {
+            X->d_gemv_t(0, nullptr, (int)p, d_resid.p, d_weights.p, d_grad.p);
+            dc.allreduce<T>(d_grad.p, p);                                       // KKT scores: one all-reduce of p values per round
         }
         d_grad.download(grad.data(), p);
         AB_CUDA(cudaStreamSynchronize(0));
+        if (!is_glm && dc.active() && intercept) for (idx_t j = 0; j < p; ++j) grad[j] -= resid_sum * X_means[j];
         n_kernel_launches += 2;
         update_abs_grad(lmda_);
     }

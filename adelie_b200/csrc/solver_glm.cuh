@@ -100,6 +100,7 @@ PinResult PathState<T>::fit_glm(T lmda_) {
             d_cols.reserve_keep(vs); d_tmp.reserve_keep(vs);
             d_cols.upload(cols.data(), vs);
             X->d_gemv_t(0, d_cols.p, (int)vs, X->d_ones(), d_irls_w.p, d_tmp.p);
+            DistContext::get().allreduce<T>(d_tmp.p, (int64_t)vs);
             d_tmp.download(sx_means.data(), vs);
             AB_CUDA(cudaStreamSynchronize(0));
         }

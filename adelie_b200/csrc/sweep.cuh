@@ -29,6 +29,7 @@ namespace ab {
 constexpr int kGsMax = 128;            // largest group size handled by the fused kernel
 constexpr int kSweepThreadsMax = 512;
 constexpr int kMaxStages = 6;
+constexpr int kMaxRanksDev = 8;        // ranks of one NVSwitch box
 constexpr int kLLSeg = 8;              // max 32-CTA segments => up to 256 CTAs
 
 struct GroupMeta {          // one per screen position (32 bytes)
@@ -67,6 +68,8 @@ struct PinKernelArgs {
     PinScalars* sc;
     dev::LLLine* ll; int ll_gs_cap; int ncta_pad;
     dev::LLLine* ll2; int fan;       // two-level exchange: level-2 lines [2][ll_gs_cap][32]; fan = CTAs per level-1 group
+    // multi-GPU (row-sharded) level 3: ll3_peer[r] = rank r's line buffer [2][kGsMax][kMaxRanksDev] mapped over NVLink
+    dev::LLLine* ll3_peer[8]; int rank, world;
     uint32_t* epoch; int* abort_flag;
     double lmda, alpha, tol, newton_tol, dbeta_tol;
     long long max_iters; int newton_max_iters; int max_active_size; int intercept;
@@ -784,9 +787,11 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             ProxPre<P> pre{};
             const bool small_group = (gs > 1 && gs <= 32);
             if (warp == 0 && small_group) pre = prox_small_pre<T, P>(rec, gs, p_aold, lane);      // overlaps the exchange latency
-            if (ncta > 1) {
+            const bool multi_gpu = a.world > 1;
+            int n_final = n_groups;                                      // number of partials the control warp adds up
+            if (ncta > 1 || multi_gpu) {
                 bool ok = true;
-                if (is_leader) {                                         // CTA-uniform
+                if (ncta > 1 && is_leader) {                             // CTA-uniform
                     // thread t < gs * grp_size reads line (column t / grp_size, member t % grp_size)
 #pragma unroll 1
                     for (int t = ctid; t < gs * grp_size; t += NTC) {
@@ -805,14 +810,48 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                         dev::ll_store(a.ll2 + ((size_t)(par * a.ll_gs_cap + ctid) * 32 + my_group), s, epoch);
                     }
                 }
+                if (ncta > 1 && (!multi_gpu || cta == 0)) {              // level 2 (single GPU: every CTA; multi GPU: the GPU leader only)
 #pragma unroll 1
-                for (int t = ctid; t < gs * n_groups; t += NTC) {
-                    const int c = t / n_groups, g = t - c * n_groups;
-                    double v = 0.0;
-                    dev::SpinGuard guard;
-                    const dev::LLLine* line = a.ll2 + ((size_t)(par * a.ll_gs_cap + c) * 32 + g);
-                    while (!dev::ll_try_load(line, epoch, v)) { if (guard.give_up(abort_flag, nullptr)) { ok = false; break; } }
-                    vals2[c * 32 + g] = v;
+                    for (int t = ctid; t < gs * n_groups; t += NTC) {
+                        const int c = t / n_groups, g = t - c * n_groups;
+                        double v = 0.0;
+                        dev::SpinGuard guard;
+                        const dev::LLLine* line = a.ll2 + ((size_t)(par * a.ll_gs_cap + c) * 32 + g);
+                        while (!dev::ll_try_load(line, epoch, v)) { if (guard.give_up(abort_flag, nullptr)) { ok = false; break; } }
+                        vals2[c * 32 + g] = v;
+                    }
+                }
+                if (multi_gpu) {
+                    // level 3 over NVLink: the GPU leader (CTA 0) stores this GPU's partial into EVERY rank's line buffer
+                    // (peer-to-peer stores through NVSwitch); every CTA of every GPU then reads its own GPU's `world` lines.
+                    if (cta == 0) {
+                        dev::named_bar_sync(1, NTC);                     // vals2 (group partials) complete
+                        if (ctid < gs) {
+                            double s = 0;
+                            if (ncta > 1) {
+#pragma unroll 1
+                                for (int g = 0; g < n_groups; ++g) s += vals2[ctid * 32 + g];
+                            } else s = gsum[ctid];
+                            vals1[ctid * 32] = s;
+                        }
+                        dev::named_bar_sync(1, NTC);
+#pragma unroll 1
+                        for (int t = ctid; t < gs * a.world; t += NTC) {
+                            const int c = t / a.world, r = t - c * a.world;
+                            dev::ll_store_sys(a.ll3_peer[r] + ((size_t)(par * kGsMax + c) * kMaxRanksDev + a.rank), vals1[c * 32], epoch);
+                        }
+                        dev::named_bar_sync(1, NTC);                     // vals2 may be overwritten below
+                    }
+#pragma unroll 1
+                    for (int t = ctid; t < gs * a.world; t += NTC) {
+                        const int c = t / a.world, r = t - c * a.world;
+                        double v = 0.0;
+                        dev::SpinGuard guard;
+                        const dev::LLLine* line = a.ll3_peer[a.rank] + ((size_t)(par * kGsMax + c) * kMaxRanksDev + r);
+                        while (!dev::ll_try_load_sys(line, epoch, v)) { if (guard.give_up(abort_flag, nullptr)) { ok = false; break; } }
+                        vals2[c * 32 + r] = v;
+                    }
+                    n_final = a.world;
                 }
                 if (!ok) ctrl->abort = 1;
             }
@@ -826,12 +865,12 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 if (lane == 0) dev::mbar_arrive(&empty_bar[pending_stage]);
                 pending_stage = -1;
             }
-            if (ncta > 1 && warp == 0) {                                 // control warp: add the group partials in group order
+            if ((ncta > 1 || multi_gpu) && warp == 0) {                  // control warp: add the group / rank partials in fixed order
 #pragma unroll 1
                 for (int c = lane; c < gs; c += 32) {
                     double s = 0;
 #pragma unroll 1
-                    for (int g = 0; g < n_groups; ++g) s += vals2[c * 32 + g];
+                    for (int g = 0; g < n_final; ++g) s += vals2[c * 32 + g];
                     gsum[c] = s;
                 }
                 __syncwarp();

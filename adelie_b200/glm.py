@@ -12,6 +12,7 @@ from typing import Union
 import numpy as np
 
 from . import _lib
+from . import dist as _dist
 
 _FAMILY = {"gaussian": 1, "binomial_logit": 2, "multigaussian": 3, "cox": 4}
 
@@ -42,11 +43,11 @@ class GlmBase:
             weights = np.asarray(weights)
             if weights.shape != (n,):
                 raise RuntimeError("y and weights must have same length." if K == 1 else "y rows and weights must have same length.")
-            ws = np.sum(weights)
+            ws = _dist.allreduce(float(np.sum(weights)))      # row-sharded: the weights of ALL ranks sum to one
             if not np.allclose(ws, 1):
                 weights = weights / ws
         else:
-            weights = np.full(n, 1 / n, dtype=dtype)
+            weights = np.full(n, 1 / _dist.allreduce(float(n)), dtype=dtype)
         self.weights = np.array(weights, copy=True, dtype=dtype)
         self._K = K
         self._n = n

@@ -9,6 +9,7 @@ from typing import Callable, Union
 
 import numpy as np
 
+from . import dist as _dist
 from . import matrix
 from .state import gaussian_naive as state_gaussian_naive
 from .state import glm_naive as state_glm_naive
@@ -100,19 +101,22 @@ def grpnet(
         weights = glm.weights
         if warm_start is None:                                       # solver.py:887-904
             ones = np.ones(n, dtype=dtype)
+            # (row-sharded mode: every sum over observations is all-reduced over the ranks; identity otherwise)
             X_means = np.empty(p, dtype=dtype)
             X.mul(ones, weights, X_means)
+            X_means = np.asarray(_dist.allreduce(X_means), dtype=dtype)
             y_off = y - offsets
-            y_mean = np.sum(y_off * weights)
+            y_mean = _dist.allreduce(np.sum(y_off * weights))
             yc = y_off
             if intercept:
                 yc = yc - y_mean
-            y_var = np.sum(weights * yc ** 2)
+            y_var = _dist.allreduce(np.sum(weights * yc ** 2))
             rsq = 0
             resid = np.ascontiguousarray(yc, dtype=dtype)
-            resid_sum = np.sum(weights * resid)
+            resid_sum = _dist.allreduce(np.sum(weights * resid))
             grad = np.empty(p, dtype=dtype)
             X.mul(resid, weights, grad)
+            grad = np.asarray(_dist.allreduce(grad), dtype=dtype)
         else:
             X_means = warm_start.X_means
             y_mean = warm_start.y_mean
@@ -132,6 +136,7 @@ def grpnet(
             glm.gradient(eta, resid)
             grad = np.empty(p, dtype=dtype)
             X.mul(resid, ones, grad)
+            grad = np.asarray(_dist.allreduce(grad), dtype=dtype)
             loss_null = None
             loss_full = glm.loss_full()
         else:

@@ -38,6 +38,15 @@ int ab_host_unregister(void* ptr);
 int ab_timer_start(void);
 int ab_timer_stop(double* elapsed_ms);
 
+/* ---- multi-GPU row sharding (no counterpart in the reference, which is single-process): one process per GPU of one
+ *      NVSwitch box.  ab_dist_init allocates this rank's peer-visible slab and returns its 64-byte cudaIpc handle; the caller
+ *      all-gathers the handles (e.g. torch.distributed) and passes them, in rank order, to ab_dist_connect.  Afterwards every
+ *      matrix / GLM / state call is collective: each rank passes its row shard, results are identical on all ranks. */
+int ab_dist_init(int rank, int world, void* ipc_handle_out /* 64 bytes */);
+int ab_dist_connect(const void* all_handles /* world * 64 bytes */);
+int ab_dist_allreduce_f64(double* host_buf, int64_t n);      /* in-place sum over ranks of a host vector */
+int ab_dist_info(int* rank, int* world);
+
 /* ---- configs: adelie/src/py_configs.cpp:6-47, include/adelie_core/configs.hpp:6-20 ---------- */
 int ab_configs_set(const char* name, double value);
 int ab_configs_get(const char* name, double* value);
