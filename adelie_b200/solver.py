@@ -15,6 +15,28 @@ from .state import gaussian_naive as state_gaussian_naive
 from .state import glm_naive as state_glm_naive
 
 
+def _init_gaussian(X, y, weights, offsets, intercept, dtype):
+    """Initial invariants of the Gaussian state (adelie/solver.py:887-904).  In row-sharded mode every sum over
+    observations is all-reduced over the ranks (identity otherwise); X only needs ``rows/cols/mul``."""
+    n, p = X.rows(), X.cols()
+    ones = np.ones(n, dtype=dtype)
+    X_means = np.empty(p, dtype=dtype)
+    X.mul(ones, weights, X_means)
+    X_means = np.asarray(_dist.allreduce(X_means), dtype=dtype)
+    y_off = y - offsets
+    y_mean = _dist.allreduce(np.sum(y_off * weights))
+    yc = y_off
+    if intercept:
+        yc = yc - y_mean
+    y_var = _dist.allreduce(np.sum(weights * yc ** 2))
+    resid = np.ascontiguousarray(yc, dtype=dtype)
+    resid_sum = _dist.allreduce(np.sum(weights * resid))
+    grad = np.empty(p, dtype=dtype)
+    X.mul(resid, weights, grad)
+    grad = np.asarray(_dist.allreduce(grad), dtype=dtype)
+    return dict(X_means=X_means, y_mean=y_mean, y_var=y_var, rsq=0, resid=resid, resid_sum=resid_sum, grad=grad)
+
+
 def grpnet(
     X, glm, *, constraints: list = None, groups: np.ndarray = None, alpha: float = 1, penalty: np.ndarray = None,
     offsets: np.ndarray = None, lmda_path: np.ndarray = None, irls_max_iters: int = int(1e4), irls_tol: float = 1e-7,
@@ -100,23 +122,9 @@ def grpnet(
         y = glm.y
         weights = glm.weights
         if warm_start is None:                                       # solver.py:887-904
-            ones = np.ones(n, dtype=dtype)
-            # (row-sharded mode: every sum over observations is all-reduced over the ranks; identity otherwise)
-            X_means = np.empty(p, dtype=dtype)
-            X.mul(ones, weights, X_means)
-            X_means = np.asarray(_dist.allreduce(X_means), dtype=dtype)
-            y_off = y - offsets
-            y_mean = _dist.allreduce(np.sum(y_off * weights))
-            yc = y_off
-            if intercept:
-                yc = yc - y_mean
-            y_var = _dist.allreduce(np.sum(weights * yc ** 2))
-            rsq = 0
-            resid = np.ascontiguousarray(yc, dtype=dtype)
-            resid_sum = _dist.allreduce(np.sum(weights * resid))
-            grad = np.empty(p, dtype=dtype)
-            X.mul(resid, weights, grad)
-            grad = np.asarray(_dist.allreduce(grad), dtype=dtype)
+            inv = _init_gaussian(X, y, weights, offsets, intercept, dtype)
+            X_means, y_mean, y_var, rsq = inv["X_means"], inv["y_mean"], inv["y_var"], inv["rsq"]
+            resid, resid_sum, grad = inv["resid"], inv["resid_sum"], inv["grad"]
         else:
             X_means = warm_start.X_means
             y_mean = warm_start.y_mean
