@@ -350,7 +350,12 @@ template <class T>
 static PathState<T>* make_state(const ab_state_args* a, DenseMatrix<T>* X, Glm<T>* glm) {
     auto st = std::make_unique<PathState<T>>();
     auto& s = *st;
-    s.X = X; s.n = X->n; s.p = X->p; s.G = a->G;
+    s.X = X; s.n = X->n; s.G = a->G;
+    s.K = (int)std::max<int64_t>(1, a->n_classes);
+    if (s.K > 16) throw core_error("multi-response problems with more than 16 classes are not supported.");
+    s.n_int = (s.K > 1 && a->multi_intercept) ? s.K : 0;
+    s.p = X->p * s.K + s.n_int;
+    const int64_t nK = s.n * s.K;
     if (a->G < 1) throw core_error("groups must be non-empty.");
     s.groups.assign(a->groups, a->groups + a->G);
     s.group_sizes.assign(a->group_sizes, a->group_sizes + a->G);
@@ -361,7 +366,7 @@ static PathState<T>* make_state(const ab_state_args* a, DenseMatrix<T>* X, Glm<T
     s.pivot_subset_ratio = (T)a->pivot_subset_ratio; s.pivot_subset_min = a->pivot_subset_min; s.pivot_slack_ratio = (T)a->pivot_slack_ratio;
     s.screen_rule = a->screen_rule; s.max_iters = a->max_iters; s.tol = (T)a->tol; s.adev_tol = (T)a->adev_tol; s.ddev_tol = (T)a->ddev_tol;
     s.newton_tol = (T)a->newton_tol; s.newton_max_iters = a->newton_max_iters; s.early_exit = a->early_exit;
-    s.setup_lmda_max = a->setup_lmda_max; s.setup_lmda_path = a->setup_lmda_path; s.intercept = a->intercept; s.n_threads = a->n_threads;
+    s.setup_lmda_max = a->setup_lmda_max; s.setup_lmda_path = a->setup_lmda_path; s.intercept = a->intercept && s.K == 1; s.n_threads = a->n_threads;    // multi-response: intercepts are explicit columns (PY/state.py:2329-2330)
     s.lmda_max = (T)a->lmda_max; s.lmda = (T)a->lmda;
     if (a->lmda_path && a->lmda_path_len > 0) s.lmda_path.assign((const T*)a->lmda_path, (const T*)a->lmda_path + a->lmda_path_len);
     s.screen_set.assign(a->screen_set, a->screen_set + a->screen_set_size);
@@ -370,20 +375,20 @@ static PathState<T>* make_state(const ab_state_args* a, DenseMatrix<T>* X, Glm<T
     s.active_set_size = a->active_set_size;
     s.active_set.assign(a->active_set, a->active_set + a->G);
     s.grad.assign((const T*)a->grad, (const T*)a->grad + s.p);
-    const int64_t np = X->n_pad();
+    const int64_t np = X->n_pad() * s.K;
     s.d_resid.alloc(np); s.d_grad.alloc(s.p);
-    s.d_resid.upload((const T*)a->resid, s.n);
+    s.d_resid.upload((const T*)a->resid, nK);
     if (!s.is_glm) {
         // state_gaussian_naive.ipp:9-28 shape checks are implied by the pointer/size contract of the C ABI
-        s.d_weights.alloc(np); s.d_weights.upload((const T*)a->weights, s.n);
+        s.d_weights.alloc(np); s.d_weights.upload((const T*)a->weights, nK);
         s.d_resid_prev.alloc(np);
         s.X_means.assign((const T*)a->X_means, (const T*)a->X_means + s.p);
         s.d_X_means.alloc(s.p); s.d_X_means.upload(s.X_means.data(), s.p);
         s.y_mean = (T)a->y_mean; s.y_var = (T)a->y_var; s.resid_sum = (T)a->resid_sum; s.rsq = (T)a->rsq;
     } else {
-        if (glm->n != s.n) throw core_error("y must be (n,) where X is (n, p).");
-        s.d_offsets.alloc(np); s.d_offsets.upload((const T*)a->offsets, s.n);
-        s.d_eta.alloc(np); s.d_eta.upload((const T*)a->eta, s.n);
+        if (glm->n != nK) throw core_error("y must be (n,) (or (n, K)) where X is (n, p).");
+        s.d_offsets.alloc(np); s.d_offsets.upload((const T*)a->offsets, nK);
+        s.d_eta.alloc(np); s.d_eta.upload((const T*)a->eta, nK);
         s.d_eta_prev.alloc(np); s.d_glm_resid_prev.alloc(np); s.d_hess.alloc(np); s.d_irls_w.alloc(np);
         s.d_irls_y.alloc(np); s.d_irls_resid.alloc(np);
         s.beta0 = (T)a->beta0; s.loss_null = (T)a->loss_null; s.loss_full = (T)a->loss_full; s.setup_loss_null = a->setup_loss_null;
@@ -453,7 +458,7 @@ static int state_vec_f64(const PathState<T>& s, const std::string& nm, double* o
     }
     if (nm == "resid" || nm == "eta") {
         const DevBuf<T>& d = (nm == "resid") ? s.d_resid : s.d_eta;
-        const int64_t nn = s.is_glm ? s.glm->n : s.n;
+        const int64_t nn = s.n * s.K;
         *len = d.p ? nn : 0;
         if (out && d.p) {
             std::vector<T> h(nn);
@@ -509,7 +514,6 @@ extern "C" {
 int ab_state_create(const ab_state_args* args, ab_matrix* X, ab_glm* glm, ab_state** out) {
     AB_TRY
     if (X->dtype != args->dtype || (glm && glm->dtype != args->dtype)) throw core_error("dtype mismatch between state, matrix and glm.");
-    if (args->n_classes > 1) throw core_error("multi-response states are not implemented in this build.");
     auto* s = new ab_state{args->dtype};
     try {
         if (args->dtype == AB_F32) s->f32 = make_state<float>(args, X->f32, glm ? glm->f32 : nullptr);

@@ -70,6 +70,59 @@ gemv_t_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, int64_t j0, co
     }
 }
 
+// Multi-response transposed GEMV (the `mul` of kron(X, I_K), CORE/matrix/matrix_naive_kronecker_eye.ipp): v, w are (n, K) row-major,
+//   out_part[rb * q*K + c*K + l] = sum_{i in row block rb} X[i, j0+c] * v[i, l] * w[i, l]      (w == nullptr: weights 1)
+// Each X element is read from HBM once and used for all K classes; the K products per row are staged class-major in shared memory.
+// grid = (ceil(q / kGemvColsPerCta), n_row_blocks), dynamic smem = K * tile_rows * sizeof(T); tile_rows multiple of kRowAlign.
+constexpr int kMultiMaxK = 16;
+template <class T>
+__global__ void __launch_bounds__(kGemvThreads)
+gemv_t_multi_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, int64_t j0, int q, int K, int tile_rows,
+                    const T* __restrict__ v, const T* __restrict__ w, double* __restrict__ out_part)
+{
+    constexpr int VN = VecT<T>::N;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    T* s_vw = reinterpret_cast<T*>(s_raw);                       // [K][tile_rows]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t rb = blockIdx.y;
+    const int64_t row0 = rb * tile_rows;
+    const int rows = (int)min((long long)tile_rows, (long long)(n_pad - row0));
+    for (int e = tid; e < rows * K; e += kGemvThreads) {
+        const int i = e / K, l = e - i * K;
+        const T vv = v[row0 * K + e];
+        s_vw[l * tile_rows + i] = w ? vv * w[row0 * K + e] : vv;
+    }
+    __syncthreads();
+    const int c_begin = blockIdx.x * kGemvColsPerCta;
+    const int c_end = min(q, c_begin + kGemvColsPerCta);
+    for (int c = c_begin + warp; c < c_end; c += kGemvThreads / 32) {
+        const T* col = X + (j0 + c) * ld + row0;
+        T acc[kMultiMaxK];
+#pragma unroll
+        for (int l = 0; l < kMultiMaxK; ++l) acc[l] = 0;
+        for (int i = lane * VN; i < rows; i += 32 * VN) {
+            T x[VN];
+            vec_load<T>(col + i, x);
+#pragma unroll
+            for (int l = 0; l < kMultiMaxK; ++l) {
+                if (l < K) {
+                    T s[VN];
+                    vec_load<T>(s_vw + l * tile_rows + i, s);
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) acc[l] += x[k] * s[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < kMultiMaxK; ++l) {
+            if (l < K) {
+                const double tot = dev::warp_sum((double)acc[l]);
+                if (lane == 0) out_part[(size_t)rb * q * K + (size_t)c * K + l] = tot;
+            }
+        }
+    }
+}
+
 // out[c] = sum_rb part[rb*q + c]  (- scale * sub[c] if sub != nullptr), fixed summation order
 template <class T>
 __global__ void gemv_t_reduce_kernel(const double* __restrict__ part, int n_rb, int q, T* __restrict__ out,
@@ -107,12 +160,13 @@ axpy_cols_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, int64_t j0,
 //   C_part[rb][out_off + a*gs+b] = sum_{i in rb} X[i,col+a] X[i,col+b] w[i]
 // grid = (n_groups, n_row_blocks); each CTA streams its (rows x gs) tile once per 4x4 pair block
 // (re-reads hit L1/L2), so HBM traffic is one pass over X_g.
-struct CovItem { int32_t col, gs; int64_t out_off; };   // out_off: element offset of this group's gs*gs block
+struct CovItem { int32_t col, gs; int64_t out_off; int32_t cls, pad; };   // out_off: element offset of this group's gs*gs block; col < 0: the column of ones
+                                                                          // cls: class whose weights w[i*K + cls] are used (multi-response)
 
 template <class T>
 __global__ void __launch_bounds__(256)
 cov_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovItem* __restrict__ items,
-           const T* __restrict__ w, int w_is_sqrt, double* __restrict__ C_part, int64_t c_total, int rows_per_block)
+           const T* __restrict__ w, int w_is_sqrt, double* __restrict__ C_part, int64_t c_total, int rows_per_block, int K)
 {
     __shared__ double s_red[8][17];
     const CovItem it = items[blockIdx.x];
@@ -121,7 +175,8 @@ cov_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovItem* __
     const int64_t row0 = (int64_t)rb * rows_per_block;
     const int64_t row1 = min((long long)n_pad, (long long)(row0 + rows_per_block));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const T* Xg = X + (int64_t)it.col * ld;
+    const bool ones = it.col < 0;
+    const T* Xg = X + (int64_t)(ones ? 0 : it.col) * ld;
     double* Cout = C_part + (size_t)rb * c_total + it.out_off;
     for (int a0 = 0; a0 < gs; a0 += 4) {
         for (int b0 = 0; b0 <= a0; b0 += 4) {
@@ -131,13 +186,13 @@ cov_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovItem* __
 #pragma unroll
                 for (int y = 0; y < 4; ++y) acc[x][y] = 0;
             for (int64_t i = row0 + tid; i < row1; i += 256) {
-                T wi = w[i];
+                T wi = w[i * K + it.cls];
                 if (w_is_sqrt) wi = wi * wi;
                 T xa[4], xb[4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) xa[x] = (a0 + x < gs) ? Xg[(int64_t)(a0 + x) * ld + i] : T(0);
+                for (int x = 0; x < 4; ++x) xa[x] = (a0 + x < gs) ? (ones ? T(1) : Xg[(int64_t)(a0 + x) * ld + i]) : T(0);
 #pragma unroll
-                for (int y = 0; y < 4; ++y) xb[y] = (b0 + y < gs) ? Xg[(int64_t)(b0 + y) * ld + i] : T(0);
+                for (int y = 0; y < 4; ++y) xb[y] = (b0 + y < gs) ? (ones ? T(1) : Xg[(int64_t)(b0 + y) * ld + i]) : T(0);
 #pragma unroll
                 for (int x = 0; x < 4; ++x)
 #pragma unroll

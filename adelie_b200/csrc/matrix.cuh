@@ -48,12 +48,14 @@ struct PinLaunch {
     const T* beta_in; int beta_len; const int8_t* is_active_in; int32_t* active_set; PinScalars* sc;
     double lmda, alpha, tol, newton_tol; long long max_iters; int newton_max_iters; int max_active_size; int intercept;
     int gs_max; int rec_max;     // largest group size / record length (elements) in the screen set
+    int K = 1;                   // classes of a multi-response problem (resid / weights are (n, K) row-major)
+    int feat_max = 0;            // K > 1: most physical X columns behind one screen group (0: gs_max)
 };
 
-struct SweepGeometry { int ncta, ncta_pad, threads, n_stages, stage_elems, rows_stride, gs_cap, units_base, units_rem; bool smem; size_t smem_bytes; };
+struct SweepGeometry { int feat_max; int ncta, ncta_pad, threads, n_stages, stage_elems, rows_stride, gs_cap, units_base, units_rem; bool smem; size_t smem_bytes; };
 
 template <class T>
-inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max) {
+inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max, int K = 1, int feat_max = 0) {
     // (ncta_pad of this launch = ncta rounded up to 32; the LL buffer is sized for the largest possible grid)
     const auto& di = DeviceInfo::get();
     SweepGeometry g{};
@@ -68,9 +70,10 @@ inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max) {
     g.gs_cap = std::max(4, (gs_max + 3) / 4 * 4);
     const int n_cwarps = g.threads / 32 - 1;
     g.ncta_pad = (ncta + 31) / 32 * 32;
-    const size_t fixed = SweepSmem<T>::fixed_bytes(n_cwarps, g.gs_cap, g.ncta_pad) + 2 * sizeof(T) * (size_t)g.rows_stride;
+    const size_t fixed = SweepSmem<T>::fixed_bytes(n_cwarps, g.gs_cap, g.ncta_pad) + 2 * sizeof(T) * (size_t)g.rows_stride * K;
     const int rec_pad = (rec_max + 3) / 4 * 4;
-    int stage_elems = g.rows_stride * std::max(gs_max, 1) + rec_pad;
+    g.feat_max = std::max(1, feat_max > 0 ? feat_max : gs_max);
+    int stage_elems = g.rows_stride * g.feat_max + rec_pad;
     stage_elems = (stage_elems + 31) / 32 * 32;
     g.stage_elems = stage_elems;
     const size_t avail = di.smem_optin > fixed ? di.smem_optin - fixed : 0;
@@ -78,7 +81,7 @@ inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max) {
     g.smem = (ns >= 2) && !Configs::sweep_force_direct;
     if (g.smem) {
         g.n_stages = ns;
-        g.smem_bytes = SweepSmem<T>::total(n_cwarps, g.gs_cap, g.ncta_pad, g.rows_stride, ns, stage_elems);
+        g.smem_bytes = SweepSmem<T>::total(n_cwarps, g.gs_cap, g.ncta_pad, g.rows_stride * K, ns, stage_elems);
     } else {
         g.n_stages = 1; g.stage_elems = 0;
         // direct path: all warps are consumers; r / w stay in global memory
@@ -169,6 +172,33 @@ struct DenseMatrix {
         gemv_t_reduce_kernel<T><<<(q + 255) / 256, 256, 0, stream>>>(part.p, n_rb, q, out, sub, sub_scale_ptr, sub_scale);
         AB_CUDA(cudaGetLastError());
     }
+    // Multi-response `mul` of [kron(1, I_K) | kron(X, I_K)] (PY/solver.py:705-720 layout): v, w (n_pad, K) row-major (w nullable);
+    // out[l] = sum_i v[i,l] w[i,l] for l < n_int (the intercept columns), out[n_int + j*K + l] = sum_i X[i,j] v[i,l] w[i,l].
+    void d_mul_multi(int K, int n_int, const T* v, const T* w, T* out) {
+        if (K > kMultiMaxK) throw core_error("multi-response problems with more than 16 classes are not supported.");
+        int tile_rows = (int)std::min<int64_t>(ld, std::max<int64_t>(kRowAlign, (int64_t)(48 * 1024 / (K * sizeof(T))) / 128 * 128));
+        const int n_rb = (int)((ld + tile_rows - 1) / tile_rows);
+        const size_t smem = (size_t)K * tile_rows * sizeof(T);
+        part.reserve_keep((size_t)n_rb * (p + 1) * K, stream);
+        dim3 grid((unsigned)((p + kGemvColsPerCta - 1) / kGemvColsPerCta), n_rb);
+        gemv_t_multi_kernel<T><<<grid, kGemvThreads, smem, stream>>>(X, ld, ld, 0, (int)p, K, tile_rows, v, w, part.p);
+        gemv_t_reduce_kernel<T><<<(unsigned)((p * K + 255) / 256), 256, 0, stream>>>(part.p, n_rb, (int)(p * K), out + n_int, nullptr, nullptr, 0.0);
+        if (n_int) {
+            double* part1 = part.p + (size_t)n_rb * p * K;
+            gemv_t_multi_kernel<T><<<dim3(1, n_rb), kGemvThreads, smem, stream>>>(d_ones(), ld, ld, 0, 1, K, tile_rows, v, w, part1);
+            gemv_t_reduce_kernel<T><<<1, 256, 0, stream>>>(part1, n_rb, K, out, nullptr, nullptr, 0.0);
+        }
+        AB_CUDA(cudaGetLastError());
+    }
+    // out[l] = sum_i v[i,l] * w[i,l]  (w nullable), l < K: per-class sums of (n_pad, K) row-major arrays
+    void d_class_sums(int K, const T* v, const T* w, T* out) {
+        int tile_rows = (int)std::min<int64_t>(ld, std::max<int64_t>(kRowAlign, (int64_t)(48 * 1024 / (K * sizeof(T))) / 128 * 128));
+        const int n_rb = (int)((ld + tile_rows - 1) / tile_rows);
+        part.reserve_keep((size_t)n_rb * K, stream);
+        gemv_t_multi_kernel<T><<<dim3(1, n_rb), kGemvThreads, (size_t)K * tile_rows * sizeof(T), stream>>>(d_ones(), ld, ld, 0, 1, K, tile_rows, v, w, part.p);
+        gemv_t_reduce_kernel<T><<<1, 256, 0, stream>>>(part.p, n_rb, K, out, nullptr, nullptr, 0.0);
+        AB_CUDA(cudaGetLastError());
+    }
     void d_mul(const T* v, const T* w, T* out, const T* sub = nullptr, const double* sub_scale_ptr = nullptr) {
         d_gemv_t(0, nullptr, (int)p, v, w, out, false, sub, sub_scale_ptr);
     }
@@ -179,7 +209,7 @@ struct DenseMatrix {
         AB_CUDA(cudaGetLastError());
     }
     // Batched Gram: C[out_off + a*gs + b] = X_g^T diag(w or w^2) X_g, device doubles (c_total entries)
-    void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out) {
+    void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out, int K = 1) {
         if (n_items <= 0) return;
         const int sms = DeviceInfo::get().sm_count;
         int n_rb = std::max(1, std::min(sms, (4 * sms + n_items - 1) / n_items));
@@ -188,10 +218,10 @@ struct DenseMatrix {
         n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
         dim3 grid(n_items, n_rb);
         if (n_rb == 1) {
-            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, C_out, c_total, rows_per_block);
+            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, C_out, c_total, rows_per_block, K);
         } else {
             part.reserve_keep((size_t)n_rb * c_total, stream);
-            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, part.p, c_total, rows_per_block);
+            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, part.p, c_total, rows_per_block, K);
             sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
         }
         AB_CUDA(cudaGetLastError());
@@ -202,10 +232,11 @@ struct DenseMatrix {
     void pin_solve(const PinLaunch<T>& L) {
         if (L.gs_max > kGsMax) throw core_error("group size " + std::to_string(L.gs_max) + " exceeds the fused sweep kernel's limit of " + std::to_string(kGsMax) + ".");
         SweepContext& ctx = SweepContext::get();
-        SweepGeometry g = plan_sweep<T>(ld, L.gs_max, L.rec_max);
+        if (L.K > 16) throw core_error("multi-response problems with more than 16 classes are not supported by the fused sweep kernel.");
+        SweepGeometry g = plan_sweep<T>(ld, L.gs_max, L.rec_max, L.K, L.feat_max);
         last_geom = g;
         PinKernelArgs<T> a{};
-        a.X = X; a.ld = ld; a.n_pad = ld; a.resid = L.resid; a.weights = L.weights;
+        a.X = X; a.ld = ld; a.n_pad = ld; a.K = L.K; a.resid = L.resid; a.weights = L.weights;
         a.meta = L.meta; a.S = L.S; a.grec = L.grec;
         act_stride = ((int64_t)L.S + 127) / 128 * 128 + 128;
         act_rep.reserve_keep((size_t)act_stride * g.ncta, stream);
@@ -226,7 +257,7 @@ struct DenseMatrix {
         a.lmda = L.lmda; a.alpha = L.alpha; a.tol = L.tol; a.newton_tol = L.newton_tol; a.dbeta_tol = Configs::dbeta_tol;
         a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
         a.units_base = g.units_base; a.units_rem = g.units_rem; a.rows_stride = g.rows_stride;
-        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.gs_max = std::max(L.gs_max, 1); a.gs_cap = g.gs_cap;
+        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.gs_max = std::max(L.gs_max, 1); a.gs_cap = g.gs_cap; a.feat_max = g.feat_max;
         if (Configs::sweep_profile) { if (!stats.n) stats.alloc(32 + 8 * 160); a.stats = stats.p; } else a.stats = nullptr;
         void* kargs[] = {&a};
         const void* fn = g.smem ? (const void*)pin_solve_kernel<T, true> : (const void*)pin_solve_kernel<T, false>;

@@ -110,6 +110,9 @@ struct PathState {
     // ---------------- static (state_base.hpp:59-95, state_gaussian_naive.hpp, state_glm_naive.hpp)
     DenseMatrix<T>* X = nullptr;
     idx_t n = 0, p = 0, G = 0;
+    // multi-response (state_multigaussian_naive.hpp:33-142, PY/solver.py:705-720): the solver sees the n*K x (n_int + pX*K) matrix
+    // [kron(1, I_K) | kron(X, I_K)]; only X is stored, the kron/concatenate structure is a layout rule of the kernels.
+    int K = 1; idx_t n_int = 0;
     std::vector<idx_t> groups, group_sizes;
     T alpha = 1; std::vector<T> penalty;
     bool is_glm = false;
@@ -149,7 +152,7 @@ struct PathState {
     DevBuf<PinScalars> d_sc; DevBuf<CovItem> d_cov_items; DevBuf<double> d_cov_out; DevBuf<int32_t> d_cols; DevBuf<T> d_tmp;
     DevBuf<double> d_scal;       // small scalar scratch (device-side sub_scale etc.)
     std::vector<GroupMeta> h_meta; std::vector<T> h_grec; size_t grec_uploaded = 0, meta_uploaded = 0;
-    int gs_max_screen = 1, rec_max_screen = 4;
+    int gs_max_screen = 1, rec_max_screen = 4, feat_max_screen = 1;
     PinnedBuf<PinScalars> h_sc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::function<bool()> exit_cond;          // user early-exit callback
@@ -235,16 +238,36 @@ struct PathState {
         sXm.resize(vs); st.resize(S); sv.resize(vs, 0);
         if (begin >= end) return;
         AB_TIME(timers, "screen_records");
+        // one Gram item per (group, class present in the group): kron(X, I_K)^T W kron(X, I_K) is block diagonal over classes
+        struct GInfo { int f0, k0, nfeat; bool icpt; size_t item0; };
+        std::vector<GInfo> ginfo;
         std::vector<CovItem> items; int64_t c_total = 0;
         for (size_t i = begin; i < end; ++i) {
             const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g];
-            items.push_back(CovItem{(int32_t)groups[g], gs, c_total});
-            c_total += (int64_t)gs * gs;
+            GInfo gi{}; gi.item0 = items.size();
+            if (K == 1) {
+                gi.f0 = (int)groups[g]; gi.k0 = 0; gi.nfeat = gs; gi.icpt = false;
+                items.push_back(CovItem{(int32_t)groups[g], gs, c_total, 0, 0});
+                c_total += (int64_t)gs * gs;
+            } else if (groups[g] < n_int) {
+                if (gs != 1) throw core_error("multi-response intercept columns must be groups of size 1.");
+                gi.f0 = 0; gi.k0 = (int)groups[g]; gi.nfeat = 1; gi.icpt = true;
+                items.push_back(CovItem{-1, 1, c_total, (int32_t)groups[g], 0});
+                c_total += 1;
+            } else {
+                const idx_t c0 = groups[g] - n_int;
+                gi.f0 = (int)(c0 / K); gi.k0 = (int)(c0 % K); gi.nfeat = (gi.k0 + gs + K - 1) / K; gi.icpt = false;
+                for (int l = 0; l < K; ++l) {      // item for class l even when absent keeps the indexing simple (absent: skipped below)
+                    items.push_back(CovItem{(int32_t)gi.f0, gi.nfeat, c_total, l, 0});
+                    c_total += (int64_t)gi.nfeat * gi.nfeat;
+                }
+            }
+            ginfo.push_back(gi);
         }
         double t_cov0 = now_s();
         d_cov_items.reserve_keep(items.size()); d_cov_out.reserve_keep(c_total);
         d_cov_items.upload(items.data(), items.size());
-        X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p);
+        X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p, K);
         DistContext::get().allreduce<double>(d_cov_out.p, c_total);            // row-sharded: sum the local Gram blocks over ranks
         std::vector<double> C(c_total);
         d_cov_out.download(C.data(), c_total);
@@ -255,9 +278,18 @@ struct PathState {
         std::vector<double> Cg, D, V;
         for (size_t i = begin; i < end; ++i) {
             const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g]; const idx_t sb = screen_begins[i];
-            const CovItem& it = items[i - begin];
+            const GInfo& gi = ginfo[i - begin];
             for (int c = 0; c < gs; ++c) sXm[sb + c] = xmean(groups[g] + c);
-            Cg.assign(C.begin() + it.out_off, C.begin() + it.out_off + (size_t)gs * gs);
+            if (K == 1 || gi.icpt) {
+                const CovItem& it = items[gi.item0];
+                Cg.assign(C.begin() + it.out_off, C.begin() + it.out_off + (size_t)gs * gs);
+            } else {
+                Cg.assign((size_t)gs * gs, 0.0);
+                for (int a = 0; a < gs; ++a) for (int b = 0; b < gs; ++b) {
+                    const int fa = (gi.k0 + a) / K, ka = (gi.k0 + a) % K, fb = (gi.k0 + b) / K, kb = (gi.k0 + b) % K;
+                    if (ka == kb) Cg[(size_t)a * gs + b] = C[items[gi.item0 + ka].out_off + (size_t)fa * gi.nfeat + fb];
+                }
+            }
             if (intercept)
                 for (int a = 0; a < gs; ++a) for (int b = 0; b < gs; ++b) Cg[(size_t)a * gs + b] -= (double)sXm[sb + a] * (double)sXm[sb + b];
             if (gs == 1) {
@@ -282,10 +314,11 @@ struct PathState {
             }
             for (int k = 0; k < gs * gs; ++k) grec[off + 3 * gs + k] = st[i][k];
             GroupMeta m{};
-            m.col = (int32_t)groups[g]; m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
+            m.col = (K == 1) ? (int32_t)groups[g] : (gi.icpt ? -(int32_t)(groups[g] + 1) : (int32_t)(groups[g] - n_int)); m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
             m.pen = (double)penalty[g];
             meta[i] = m;
             gs_max_screen = std::max(gs_max_screen, gs); rec_max_screen = std::max(rec_max_screen, rec_pad);
+            feat_max_screen = std::max(feat_max_screen, gi.nfeat);
         }
     }
 
@@ -326,7 +359,7 @@ struct PathState {
         L.lmda = (double)lmda_; L.alpha = (double)alpha; L.tol = (double)tol_pin; L.newton_tol = (double)newton_tol;
         L.max_iters = (long long)max_iters; L.newton_max_iters = (int)std::min<size_t>(newton_max_iters, 1u << 30);
         L.max_active_size = (int)std::min<size_t>(max_active_size, (size_t)G); L.intercept = intercept ? 1 : 0;
-        L.gs_max = gs_max_screen; L.rec_max = rec_max_screen;
+        L.gs_max = gs_max_screen; L.rec_max = rec_max_screen; L.K = K; L.feat_max = feat_max_screen;
         if (check_interrupt) check_interrupt();
         if (DistContext::get().active()) DistContext::get().allreduce<double>(d_scal.p, 1);    // cheap rank barrier
         AB_CUDA(cudaEventRecord(ev0, 0));
@@ -379,7 +412,7 @@ struct PathState {
 
     // ------------------------------------------------------------------ Gaussian fit (solver_gaussian_naive.hpp:215-349)
     PinResult fit_gaussian(T lmda_) {
-        const int64_t np = X->n_pad();
+        const int64_t np = X->n_pad() * K;
         AB_CUDA(cudaMemcpyAsync(d_resid_prev.p, d_resid.p, np * sizeof(T), cudaMemcpyDeviceToDevice, 0));
         std::vector<T> beta_prev = screen_beta; std::vector<int8_t> act_prev = screen_is_active;
         upload_screen_tables(h_meta, h_grec, false);
@@ -394,6 +427,7 @@ struct PathState {
 
     // ------------------------------------------------------------------ GLM pieces (solver_glm_naive.hpp)
     void update_loss_null();              // defined in solver_glm.cuh
+    void update_loss_null_multi();
     PinResult fit_glm(T lmda_);           // defined in solver_glm.cuh
 
     PinResult fit(T lmda_) { return is_glm ? fit_glm(lmda_) : fit_gaussian(lmda_); }
@@ -403,7 +437,10 @@ struct PathState {
         AB_TIME(timers, "invariance");
         lmda = lmda_;
         DistContext& dc = DistContext::get();
-        if (is_glm) {
+        if (K > 1) {
+            X->d_mul_multi(K, (int)n_int, d_resid.p, is_glm ? nullptr : d_weights.p, d_grad.p);     // state-level intercept is always off
+            dc.allreduce<T>(d_grad.p, p);
+        } else if (is_glm) {
             X->d_mul(d_resid.p, X->d_ones(), d_grad.p);
             dc.allreduce<T>(d_grad.p, p);
         } else if (!dc.active()) {
@@ -417,7 +454,7 @@ struct PathState {
         }
         d_grad.download(grad.data(), p);
         AB_CUDA(cudaStreamSynchronize(0));
-        if (!is_glm && dc.active() && intercept) for (idx_t j = 0; j < p; ++j) grad[j] -= resid_sum * X_means[j];
+        if (K == 1 && !is_glm && dc.active() && intercept) for (idx_t j = 0; j < p; ++j) grad[j] -= resid_sum * X_means[j];
         n_kernel_launches += 2;
         update_abs_grad(lmda_);
     }

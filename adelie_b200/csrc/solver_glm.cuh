@@ -9,6 +9,7 @@ namespace ab {
 template <class T>
 void PathState<T>::update_loss_null() {
     const int64_t nn = glm->n;                 // n (or n*K)
+    if (K > 1) { update_loss_null_multi(); return; }
     if (!intercept) { loss_null = glm->loss(d_offsets.p); return; }
     const int64_t np = (int64_t)d_eta.n;
     DevBuf<T> eta(np), resid(np), eta_prev(np), resid_prev(np), hess(np), z(np);
@@ -41,6 +42,53 @@ void PathState<T>::update_loss_null() {
             glm->mr.template run<1>(nn, [=] __device__(int64_t i, double* acc) { acc[0] += (double)((r[i] - rp[i]) * (e[i] - ep[i])); }, &conv);
         }
         n_kernel_launches += 8;
+        if (std::abs(conv) <= (double)irls_tol) { loss_null = glm->loss(eta.p); return; }
+        ++it;
+    }
+}
+
+// multi-response update_loss_null (solver_multiglm_naive.hpp:99-186): one unpenalised intercept per class
+template <class T>
+void PathState<T>::update_loss_null_multi() {
+    const int64_t nn = glm->n;
+    if (n_int == 0) { loss_null = glm->loss(d_offsets.p); return; }
+    const int64_t np = (int64_t)d_eta.n;
+    DevBuf<T> eta(np), resid(np), eta_prev(np), resid_prev(np), hess(np), z(np), sums(2 * K), b0(K);
+    AB_CUDA(cudaMemcpyAsync(eta.p, d_eta.p, nn * sizeof(T), cudaMemcpyDeviceToDevice, 0));
+    AB_CUDA(cudaMemcpyAsync(resid.p, d_resid.p, nn * sizeof(T), cudaMemcpyDeviceToDevice, 0));
+    const T hmin = (T)Configs::hessian_min;
+    const int KK = K;
+    std::vector<T> hs(2 * K), hb0(K);
+    size_t it = 0;
+    while (1) {
+        if (it >= irls_max_iters) throw solver_error("Maximum IRLS iterations reached.");
+        glm->hessian(eta.p, resid.p, hess.p);
+        glm->inv_hessian_gradient(eta.p, resid.p, hess.p, z.p);
+        {
+            T* h = hess.p; T* zz = z.p; const T* e = eta.p; const T* off = d_offsets.p;
+            glm->mr.map(nn, [=] __device__(int64_t i, double*) {
+                h[i] = max(h[i], T(0)) + hmin * T(h[i] <= 0);
+                zz[i] += e[i] - off[i];
+            });
+        }
+        // per-class sums  num_k = sum_i h_ik y_ik,  den_k = sum_i h_ik  (the 1 / sum(h) normalisation of :137-141 cancels)
+        X->d_class_sums(K, z.p, hess.p, sums.p);
+        X->d_class_sums(K, hess.p, nullptr, sums.p + K);
+        DistContext::get().allreduce<T>(sums.p, 2 * K);
+        sums.download(hs.data(), 2 * K);
+        AB_CUDA(cudaStreamSynchronize(0));
+        for (int k = 0; k < K; ++k) hb0[k] = hs[k] / hs[K + k];
+        b0.upload(hb0.data(), K);
+        std::swap(eta.p, eta_prev.p);
+        { T* e = eta.p; const T* off = d_offsets.p; const T* bb = b0.p; glm->mr.map(nn, [=] __device__(int64_t i, double*) { e[i] = off[i] + bb[i % KK]; }); }
+        std::swap(resid.p, resid_prev.p);
+        glm->gradient(eta.p, resid.p);
+        double conv;
+        {
+            const T* r = resid.p; const T* rp = resid_prev.p; const T* e = eta.p; const T* ep = eta_prev.p;
+            glm->mr.template run<1>(nn, [=] __device__(int64_t i, double* acc) { acc[0] += (double)((r[i] - rp[i]) * (e[i] - ep[i])); }, &conv);
+        }
+        n_kernel_launches += 12;
         if (std::abs(conv) <= (double)irls_tol) { loss_null = glm->loss(eta.p); return; }
         ++it;
     }
@@ -96,7 +144,7 @@ PinResult PathState<T>::fit_glm(T lmda_) {
             for (idx_t c = 0; c < group_sizes[g]; ++c) cols[screen_begins[i] + c] = (int32_t)(groups[g] + c);
         }
         std::vector<T> sx_means(vs);
-        if (vs) {
+        if (vs && K == 1) {           // multi-response runs with the state-level intercept off: the means are never used (left 0)
             d_cols.reserve_keep(vs); d_tmp.reserve_keep(vs);
             d_cols.upload(cols.data(), vs);
             X->d_gemv_t(0, d_cols.p, (int)vs, X->d_ones(), d_irls_w.p, d_tmp.p);

@@ -33,7 +33,7 @@ constexpr int kMaxRanksDev = 8;        // ranks of one NVSwitch box
 constexpr int kLLSeg = 8;              // max 32-CTA segments => up to 256 CTAs
 
 struct GroupMeta {          // one per screen position (32 bytes)
-    int32_t col;            // first column of the group in X
+    int32_t col;            // first column of the group in X  (multi-response intercept column of class l: -(l + 1))
     int32_t gs;             // group size
     int32_t begin;          // offset into screen_beta
     int32_t rec_elems;      // padded length of the group's record
@@ -53,6 +53,11 @@ enum { kSweepActive = 0, kSweepScreen = 1, kSweepExit = 2 };
 template <class T>
 struct PinKernelArgs {
     const T* X; int64_t ld; int64_t n_pad;
+    // multi-response layout (kronecker_eye / concatenate of the reference as a LAYOUT RULE): resid and weights are
+    // (n, K) row-major and GroupMeta.col is the first column of the group in kron(X, I_K): coefficient a of the group <-> feature
+    // (col + a) / K of X, class (col + a) % K ("grouped": K classes of one feature; "ungrouped": a single (feature, class) pair).
+    // The K intercept columns kron(1, I_K) carry GroupMeta.col = -(class + 1), gs = 1.  K = 1: single response, col = X column.
+    int K;
     T* resid; const T* weights;
     const GroupMeta* meta; int S;
     const T* grec;
@@ -77,6 +82,7 @@ struct PinKernelArgs {
     int rows_stride;               // max rows per CTA (column stride inside a stage)
     int n_stages; int stage_elems; // ring geometry (elements of T per stage)
     int gs_max;                    // largest group size in the screen set
+    int feat_max;                  // largest number of physical X columns behind one group (= gs_max / K, at least 1)
     int gs_cap;                    // stride of the per-column shared-memory scratch arrays (>= gs_max, multiple of 4)
     long long* stats;              // optional [16] per-phase cycle counters of CTA 0 / thread 0 (nullptr = off)
 };
@@ -589,8 +595,8 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     P* p_scr = reinterpret_cast<P*>(reinterpret_cast<double*>(px) + 9 * gsc);               // [4 * 32] reduction scratch
     unsigned char* tiles = smem_raw + SweepSmem<T>::fixed_bytes(NW, gsc, a.ncta_pad);
     T* sr = reinterpret_cast<T*>(tiles);
-    T* sw = sr + a.rows_stride;
-    T* stages = sw + a.rows_stride;
+    T* sw = sr + (size_t)a.rows_stride * a.K;
+    T* stages = sw + (size_t)a.rows_stride * a.K;
 
     // ---- my row tile
     const int my_units = a.units_base + (cta < a.units_rem ? 1 : 0);
@@ -630,13 +636,15 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + it) : it;
                 const GroupMeta m = a.meta[ss];
                 T* xs = stages + (size_t)stage * a.stage_elems;
-                T* recs = xs + (size_t)a.rows_stride * a.gs_max;
+                T* recs = xs + (size_t)a.rows_stride * a.feat_max;
                 const uint32_t col_bytes = (uint32_t)rows * sizeof(T);
                 const uint32_t rec_bytes = (uint32_t)m.rec_elems * sizeof(T);
-                if (lane == 0) dev::mbar_arrive_expect_tx(&full_bar[stage], col_bytes * m.gs + rec_bytes);
+                const int f0 = (m.col >= 0) ? m.col / a.K : 0;               // physical X columns behind this group: [f0, f0 + nfeat)
+                const int nfeat = (m.col >= 0) ? (m.col - f0 * a.K + m.gs + a.K - 1) / a.K : 0;
+                if (lane == 0) dev::mbar_arrive_expect_tx(&full_bar[stage], col_bytes * nfeat + rec_bytes);
                 __syncwarp();
-                for (int c = lane; c < m.gs; c += 32)
-                    dev::tma_bulk_g2s(xs + (size_t)c * a.rows_stride, a.X + (int64_t)(m.col + c) * a.ld + r0, col_bytes, &full_bar[stage]);
+                for (int c = lane; c < nfeat; c += 32)
+                    dev::tma_bulk_g2s(xs + (size_t)c * a.rows_stride, a.X + (int64_t)(f0 + c) * a.ld + r0, col_bytes, &full_bar[stage]);
                 if (lane == 0) dev::tma_bulk_g2s(recs, a.grec + m.rec_off, rec_bytes, &full_bar[stage]);
             }
             ++sweepno;
@@ -663,10 +671,11 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     const bool is_leader = (cta == grp_first);
 
     // resident r / w tiles
-    T* gr = a.resid + r0;
-    const T* gw = a.weights + r0;
+    const int K = a.K;
+    T* gr = a.resid + r0 * K;
+    const T* gw = a.weights + r0 * K;
     if (SMEM) {
-        for (int v = ctid; v < rows / VN; v += NTC) {
+        for (int v = ctid; v < rows * K / VN; v += NTC) {
             T t[VN];
             vec_load<T>(gr + (size_t)v * VN, t); vec_store<T>(sr + (size_t)v * VN, t);
             vec_load<T>(gw + (size_t)v * VN, t); vec_store<T>(sw + (size_t)v * VN, t);
@@ -727,9 +736,9 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 if (!dev::mbar_wait(&full_bar[stage], use & 1, abort_flag)) ctrl->abort = 1;
                 xs = stages + (size_t)stage * a.stage_elems;
                 cs = a.rows_stride;
-                rec = xs + (size_t)a.rows_stride * a.gs_max;
+                rec = xs + (size_t)a.rows_stride * a.feat_max;
             } else {
-                xs = a.X + (int64_t)m.col * a.ld + r0;
+                xs = a.X + (int64_t)(m.col >= 0 ? m.col / a.K : 0) * a.ld + r0;
                 cs = a.ld;
                 rec = a.grec + m.rec_off;
             }
@@ -737,6 +746,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             AB_TICK(0);
             // ---- dot phase: partial[c] = sum_{i in tile} X[i, col+c] * w[i] * r[i]
             constexpr int CB = 16;
+            if (K == 1) {
 #pragma unroll 1
             for (int c0 = 0; c0 < gs; c0 += CB) {
                 T acc[CB];
@@ -763,6 +773,37 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 const T tot = warp_reduce16<T>(acc, lane);       // lane holds the warp total of column c0 + ((lane >> 1) & 15)
                 const int col = c0 + ((lane >> 1) & 15);
                 if ((lane & 1) == 0 && col < gs) wpart[(size_t)warp * gsc + col] = (double)tot;
+            }
+            } else {
+                // multi-response: coefficient a <-> kron column m.col + a = (feature, class); X[i, feature] * w[i, class] * r[i, class]
+                const bool icpt = m.col < 0;
+                const int kcls = icpt ? (-m.col - 1) : 0;
+                const int k0 = icpt ? 0 : m.col % K;
+#pragma unroll 1
+                for (int c0 = 0; c0 < gs; c0 += CB) {
+                    T acc[CB]; int fo[CB], ko[CB];
+#pragma unroll
+                    for (int cc = 0; cc < CB; ++cc) {
+                        acc[cc] = 0;
+                        const int ai = c0 + cc;
+                        const int f = icpt ? 0 : (k0 + ai) / K;
+                        fo[cc] = f; ko[cc] = icpt ? kcls : k0 + ai - f * K;
+                    }
+#pragma unroll 1
+                    for (int i = ctid; i < rows; i += NTC) {
+                        const T* rrow = rr + (size_t)i * K; const T* wrow = ww + (size_t)i * K;
+#pragma unroll
+                        for (int cc = 0; cc < CB; ++cc) {
+                            if (c0 + cc < gs) {
+                                const T wr = wrow[ko[cc]] * rrow[ko[cc]];
+                                acc[cc] += icpt ? wr : xs[(int64_t)fo[cc] * cs + i] * wr;
+                            }
+                        }
+                    }
+                    const T tot = warp_reduce16<T>(acc, lane);
+                    const int col = c0 + ((lane >> 1) & 15);
+                    if ((lane & 1) == 0 && col < gs) wpart[(size_t)warp * gsc + col] = (double)tot;
+                }
             }
             AB_TICK(1);
             long long* trace = (a.stats != nullptr && ctid == 0 && n_updates == a.sc->n_group_updates + 40) ? a.stats + 32 + 8 * cta : nullptr;
@@ -928,7 +969,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             AB_TICK(5);
 
             // ---- residual update from the same X tile: r += X_g * del
-            if (changed_now) {
+            if (changed_now && K == 1) {
 #pragma unroll 1
                 for (int c0 = 0; c0 < gs; c0 += CB) {
                     T d[CB];
@@ -948,6 +989,22 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                             }
                         }
                         vec_store<T>(rr + (size_t)v * VN, rv);
+                    }
+                }
+            }
+            if (changed_now && K > 1) {                                      // r[i, class] += X[i, feature] * del[feature * K + class]
+                const bool icpt = m.col < 0;
+                const int kcls = icpt ? (-m.col - 1) : 0;
+#pragma unroll 1
+                for (int i = ctid; i < rows; i += NTC) {
+                    T* rrow = rr + (size_t)i * K;
+                    if (icpt) { rrow[kcls] += s_del[0]; continue; }
+                    int f = 0, k = m.col % K;
+                    T x = xs[i];
+#pragma unroll 1
+                    for (int c = 0; c < gs; ++c) {
+                        rrow[k] += x * s_del[c];
+                        if (++k == K && c + 1 < gs) { k = 0; ++f; x = xs[(int64_t)f * cs + i]; }
                     }
                 }
             }
@@ -990,7 +1047,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             else { ctrl->p_kind = kSweepExit; ctrl->p_count = 0; dev::mbar_arrive(desc_bar); }
         }
         if (final_error == kErrAbort) *abort_flag = 1;
-        for (int v = ctid; v < rows / VN; v += NTC) {
+        for (int v = ctid; v < rows * K / VN; v += NTC) {
             T t[VN];
             vec_load<T>(sr + (size_t)v * VN, t); vec_store<T>(gr + (size_t)v * VN, t);
         }

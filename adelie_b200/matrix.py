@@ -248,3 +248,190 @@ def dense(mat: np.ndarray, *, method: str = "naive", copy: bool = False, n_threa
 def dense_device_normal(n: int, p: int, *, dtype=np.float32, seed: int = 0, row_offset: int = 0):
     """N(0,1) dense matrix generated in HBM with a counter-based RNG (no host copy)."""
     return _DeviceDense(dtype, n, p, seed, row_offset)
+
+
+class _KroneckerEye(MatrixNaiveBase):
+    """kron(mat, I_K) as a layout rule over the base operators (adelie/matrix.py kronecker_eye;
+    CORE/matrix/matrix_naive_kronecker_eye.ipp): column j <-> (feature j // K, class j % K), row r <-> (obs r // K, class r % K).
+    The fused solver never materialises this object -- it addresses the base matrix with (feature, class) arithmetic in the
+    kernels (csrc/sweep.cuh); this class exists for the user-facing operator API and the initial invariants."""
+    def __init__(self, mat, K, n_threads=1):
+        MatrixNaiveBase.__init__(self, n_threads)
+        if isinstance(mat, np.ndarray):
+            mat = dense(mat, method="naive", n_threads=n_threads)
+        self._mat = mat
+        self._K = int(K)
+        self.dtype = mat.dtype
+
+    def rows(self):
+        return self._mat.rows() * self._K
+
+    def cols(self):
+        return self._mat.cols() * self._K
+
+    def _sl(self, a, l):
+        return np.ascontiguousarray(a[l::self._K])
+
+    def cmul(self, j, v, weights):
+        i, l = divmod(int(j), self._K)
+        return self._mat.cmul(i, self._sl(v, l), self._sl(weights, l))
+
+    cmul_safe = cmul
+
+    def ctmul(self, j, v, out):
+        i, l = divmod(int(j), self._K)
+        tmp = np.zeros(self._mat.rows(), dtype=self.dtype)
+        self._mat.ctmul(i, v, tmp)
+        out[l::self._K] += tmp
+
+    def bmul(self, j, q, v, weights, out):
+        if j < 0 or j > self.cols() - q or v.size != self.rows() or weights.size != self.rows() or out.size != q:
+            raise RuntimeError(f"adelie_core: bmul() is given inconsistent inputs! (j={j}, q={q}, v={v.size}, w={weights.size}, o={out.size}, r={self.rows()}, c={self.cols()})")
+        for c in range(q):
+            out[c] = self.cmul(j + c, v, weights)
+
+    bmul_safe = bmul
+
+    def btmul(self, j, q, v, out):
+        if j < 0 or j > self.cols() - q or v.size != q or out.size != self.rows():
+            raise RuntimeError(f"adelie_core: btmul() is given inconsistent inputs! (j={j}, q={q}, v={v.size}, o={out.size}, r={self.rows()}, c={self.cols()})")
+        for c in range(q):
+            self.ctmul(j + c, v[c], out)
+
+    def mul(self, v, weights, out):
+        tmp = np.empty(self._mat.cols(), dtype=self.dtype)
+        for l in range(self._K):
+            self._mat.mul(self._sl(v, l), self._sl(weights, l), tmp)
+            out[l::self._K] = tmp
+
+    def cov(self, j, q, sqrt_weights, out):
+        K = self._K
+        out[...] = 0
+        i0, i1 = j // K, (j + q - 1) // K + 1
+        for l in range(K):
+            idx = [c for c in range(q) if (j + c) % K == l]
+            if not idx:
+                continue
+            sub = np.empty((i1 - i0, i1 - i0), dtype=self.dtype, order="F")
+            self._mat.cov(i0, i1 - i0, self._sl(sqrt_weights, l), sub)
+            f = [(j + c) // K - i0 for c in idx]
+            out[np.ix_(idx, idx)] = sub[np.ix_(f, f)]
+
+    def sq_mul(self, weights, out):
+        tmp = np.empty(self._mat.cols(), dtype=self.dtype)
+        for l in range(self._K):
+            self._mat.sq_mul(self._sl(weights, l), tmp)
+            out[l::self._K] = tmp
+
+    def sp_tmul(self, v, out):
+        v = csc_matrix(v)
+        tmp = np.empty((v.shape[0], self._mat.rows()), dtype=self.dtype)
+        for l in range(self._K):
+            self._mat.sp_tmul(csr_matrix(v[:, l::self._K]), tmp)
+            out[:, l::self._K] = tmp
+
+    def mean(self, weights, out):
+        self.mul(np.ones(self.rows(), dtype=self.dtype), weights, out)
+
+
+class _CConcatenate(MatrixNaiveBase):
+    """Column-wise concatenation as a dispatch rule (adelie/matrix.py concatenate(axis=1); CORE/matrix/matrix_naive_concatenate.ipp)."""
+    def __init__(self, mats, n_threads=1):
+        MatrixNaiveBase.__init__(self, n_threads)
+        if len(mats) == 0:
+            raise RuntimeError("adelie_core: mat_list must be non-empty.")
+        mats = [dense(m, method="naive", n_threads=n_threads) if isinstance(m, np.ndarray) else m for m in mats]
+        n = mats[0].rows()
+        if any(m.rows() != n for m in mats):
+            raise RuntimeError("adelie_core: All matrices must have the same number of rows.")
+        self._mats = mats
+        self.dtype = mats[0].dtype
+        self._offs = np.concatenate([[0], np.cumsum([m.cols() for m in mats])]).astype(int)
+
+    def rows(self):
+        return self._mats[0].rows()
+
+    def cols(self):
+        return int(self._offs[-1])
+
+    def _find(self, j):
+        k = int(np.searchsorted(self._offs, j, side="right") - 1)
+        return k, int(j - self._offs[k])
+
+    def cmul(self, j, v, weights):
+        if j < 0 or j >= self.cols():
+            raise RuntimeError(f"adelie_core: cmul() is given inconsistent inputs! (j={j}, v={v.size}, w={weights.size}, r={self.rows()}, c={self.cols()})")
+        k, jj = self._find(j)
+        return self._mats[k].cmul(jj, v, weights)
+
+    cmul_safe = cmul
+
+    def ctmul(self, j, v, out):
+        k, jj = self._find(j)
+        self._mats[k].ctmul(jj, v, out)
+
+    def bmul(self, j, q, v, weights, out):
+        if j < 0 or j > self.cols() - q or out.size != q:
+            raise RuntimeError(f"adelie_core: bmul() is given inconsistent inputs! (j={j}, q={q}, v={v.size}, w={weights.size}, o={out.size}, r={self.rows()}, c={self.cols()})")
+        c = 0
+        while c < q:
+            k, jj = self._find(j + c)
+            qq = min(q - c, self._mats[k].cols() - jj)
+            tmp = np.empty(qq, dtype=self.dtype)
+            self._mats[k].bmul(jj, qq, v, weights, tmp)
+            out[c:c + qq] = tmp
+            c += qq
+
+    bmul_safe = bmul
+
+    def btmul(self, j, q, v, out):
+        if j < 0 or j > self.cols() - q or v.size != q:
+            raise RuntimeError(f"adelie_core: btmul() is given inconsistent inputs! (j={j}, q={q}, v={v.size}, o={out.size}, r={self.rows()}, c={self.cols()})")
+        c = 0
+        while c < q:
+            k, jj = self._find(j + c)
+            qq = min(q - c, self._mats[k].cols() - jj)
+            self._mats[k].btmul(jj, qq, np.ascontiguousarray(v[c:c + qq]), out)
+            c += qq
+
+    def mul(self, v, weights, out):
+        for k, m in enumerate(self._mats):
+            tmp = np.empty(m.cols(), dtype=self.dtype)
+            m.mul(v, weights, tmp)
+            out[self._offs[k]:self._offs[k + 1]] = tmp
+
+    def cov(self, j, q, sqrt_weights, out):
+        k, jj = self._find(j)
+        if jj + q > self._mats[k].cols():
+            raise RuntimeError("adelie_core: MatrixNaiveCConcatenate::cov() only allows the block to be fully contained in one of the matrices in the list.")
+        self._mats[k].cov(jj, q, sqrt_weights, out)
+
+    def sq_mul(self, weights, out):
+        for k, m in enumerate(self._mats):
+            tmp = np.empty(m.cols(), dtype=self.dtype)
+            m.sq_mul(weights, tmp)
+            out[self._offs[k]:self._offs[k + 1]] = tmp
+
+    def sp_tmul(self, v, out):
+        v = csc_matrix(v)
+        out[...] = 0
+        tmp = np.empty(out.shape, dtype=self.dtype)
+        for k, m in enumerate(self._mats):
+            m.sp_tmul(csr_matrix(v[:, self._offs[k]:self._offs[k + 1]]), tmp)
+            out += tmp
+
+    def mean(self, weights, out):
+        self.mul(np.ones(self.rows(), dtype=self.dtype), weights, out)
+
+
+def kronecker_eye(mat, K: int = 1, *, n_threads: int = 1):
+    """kron(mat, I_K) (adelie/matrix.py kronecker_eye)."""
+    return _KroneckerEye(mat, K, n_threads)
+
+
+def concatenate(mats: list, axis: int = 0, *, n_threads: int = 1):
+    """Concatenation of naive matrices (adelie/matrix.py concatenate).  Only ``axis=1`` (the multi-response intercept layout,
+    adelie/state.py:1100-1125) is on the hot path."""
+    if axis != 1:
+        raise RuntimeError("adelie_b200: only axis=1 concatenation is in scope (row concatenation is not on the hot path).")
+    return _CConcatenate(mats, n_threads)

@@ -373,3 +373,125 @@ def glm_naive(*, X, glm, constraints, groups, group_sizes, alpha, penalty, offse
                newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=early_exit, intercept=intercept,
                n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float(lmda))
     return _Naive(X=X, glm_obj=glm, use_glm=True, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=X.cols())
+
+
+class _MultiNaive(_Naive):
+    """Multi-response states: the core solves the reformulated single-response problem; ``betas`` / ``intercepts`` are tidied as
+    solver_multigaussian_naive.hpp:31-43 / solver_multiglm_naive.hpp:205-224 do (first K coefficients -> (L, K) intercepts)."""
+    _is_multi = True
+
+    def _raw_betas(self):
+        return base.betas.fget(self)
+
+    @property
+    def betas(self):
+        B = self._raw_betas()
+        K = self._cfg["n_classes"]
+        if not self._cfg["multi_intercept"]:
+            return B
+        B = scipy.sparse.csr_matrix(B.tocsc()[:, K:])
+        B.indices = B.indices.astype(np.int64); B.indptr = B.indptr.astype(np.int64)
+        return B
+
+    @property
+    def intercepts(self):
+        K = self._cfg["n_classes"]
+        B = self._raw_betas()
+        if not self._cfg["multi_intercept"]:
+            return np.zeros((B.shape[0], K), dtype=self._dtype)
+        return np.asarray(B.tocsc()[:, :K].todense()).astype(self._dtype).reshape(B.shape[0], K)
+
+    @property
+    def X_expanded(self):
+        return self._X_expanded
+
+
+def _render_multi_inputs(*, X, offsets, intercept, n_threads, dtype):
+    """adelie/state.py:1100-1125"""
+    offsets = np.asarray(offsets, order="C", dtype=dtype)
+    n, K = offsets.shape
+    Xe = _matrix.kronecker_eye(X, K, n_threads=n_threads)
+    if intercept:
+        Xe = _matrix.concatenate([_matrix.kronecker_eye(np.ones((n, 1), dtype=dtype), K, n_threads=n_threads), Xe], axis=1,
+                                 n_threads=n_threads)
+    return Xe, offsets
+
+
+def multigaussian_naive(*, X, y, X_means, y_var, resid, resid_sum, constraints, groups, group_sizes, alpha, penalty, weights,
+                        offsets, screen_set, screen_beta, screen_is_active, active_set_size, active_set, rsq, lmda, grad,
+                        lmda_path=None, lmda_max=None, max_iters=int(1e5), tol=1e-7, adev_tol=0.9, ddev_tol=0, newton_tol=1e-12,
+                        newton_max_iters=1000, n_threads=1, early_exit=True, intercept=True, screen_rule="pivot", min_ratio=1e-2,
+                        lmda_path_size=100, max_screen_size=None, max_active_size=None, pivot_subset_ratio=0.1,
+                        pivot_subset_min=1, pivot_slack_ratio=1.25):
+    """Multi-response Gaussian naive state (adelie/state.py:2027-2391; core StateMultiGaussianNaive)."""
+    _check_constraints(constraints)
+    if isinstance(X, np.ndarray):
+        X = _matrix.dense(X, method="naive", n_threads=n_threads)
+    dtype = X.dtype
+    groups = np.asarray(groups)
+    (max_screen_size, max_active_size, lmda_path_size, setup_lmda_max, setup_lmda_path, lmda_max, lmda_path) = _render_inputs(
+        groups=groups, lmda_max=lmda_max, lmda_path=lmda_path, lmda_path_size=lmda_path_size,
+        max_screen_size=max_screen_size, max_active_size=max_active_size, dtype=dtype)
+    y = np.asarray(y, dtype=dtype)
+    K = y.shape[-1]
+    Xe, offsets = _render_multi_inputs(X=X, offsets=offsets, intercept=intercept, n_threads=n_threads, dtype=dtype)
+    assert np.asarray(X_means).shape[0] == Xe.cols(), "X_means must have the same length as the number of columns of X after reshaping."
+    glm_obj = _glm.multigaussian(y=y, weights=weights, dtype=dtype)
+    arrays = _common_arrays(groups=groups, group_sizes=group_sizes, penalty=penalty, lmda_path=lmda_path, screen_set=screen_set,
+                            screen_beta=screen_beta, screen_is_active=screen_is_active, active_set=active_set, grad=grad,
+                            resid=resid, dtype=dtype)
+    arrays["weights"] = np.ascontiguousarray(np.repeat(glm_obj.weights, K) / K, dtype=dtype)      # state.py:2315
+    arrays["X_means"] = np.array(X_means, copy=True, dtype=dtype)
+    arrays["offsets"] = np.array(offsets, copy=True, dtype=dtype)
+    arrays["X_expanded"] = Xe
+    # not the actual y_mean: a value that yields the right loss_null / loss_full (state.py:2339-2343)
+    y_mean = np.linalg.norm(np.asarray(_dist_sum(np.sum(glm_obj.weights[:, None] * (y - offsets), axis=0))) / K)
+    cfg = dict(alpha=float(alpha), y_mean=float(y_mean), y_var=float(y_var), resid_sum=float(resid_sum), rsq=float(rsq),
+               lmda_max=float(lmda_max), min_ratio=min_ratio, lmda_path_size=int(lmda_path_size), setup_lmda_max=setup_lmda_max,
+               setup_lmda_path=setup_lmda_path, max_screen_size=max_screen_size, max_active_size=max_active_size,
+               pivot_subset_ratio=pivot_subset_ratio, pivot_subset_min=pivot_subset_min, pivot_slack_ratio=pivot_slack_ratio,
+               screen_rule=screen_rule, max_iters=int(max_iters), tol=tol, adev_tol=adev_tol, ddev_tol=ddev_tol,
+               newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=early_exit, intercept=False,
+               n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float(lmda), n_classes=int(K),
+               multi_intercept=bool(intercept))
+    return _MultiNaive(X=X, glm_obj=glm_obj, use_glm=False, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=Xe.cols())
+
+
+def _dist_sum(v):
+    from . import dist as _dist
+    return _dist.allreduce(v)
+
+
+def multiglm_naive(*, X, glm, constraints, groups, group_sizes, alpha, penalty, offsets, screen_set, screen_beta,
+                   screen_is_active, active_set_size, active_set, lmda, grad, eta, resid, loss_full, loss_null=None,
+                   lmda_path=None, lmda_max=None, irls_max_iters=int(1e4), irls_tol=1e-7, max_iters=int(1e5), tol=1e-7,
+                   adev_tol=0.9, ddev_tol=0, newton_tol=1e-12, newton_max_iters=1000, n_threads=1, early_exit=True,
+                   intercept=True, screen_rule="pivot", min_ratio=1e-2, lmda_path_size=100, max_screen_size=None,
+                   max_active_size=None, pivot_subset_ratio=0.1, pivot_subset_min=1, pivot_slack_ratio=1.25):
+    """Multi-response GLM naive state (adelie/state.py:2756-3100; core StateMultiGlmNaive)."""
+    _check_constraints(constraints)
+    if isinstance(X, np.ndarray):
+        X = _matrix.dense(X, method="naive", n_threads=n_threads)
+    dtype = X.dtype
+    groups = np.asarray(groups)
+    (max_screen_size, max_active_size, lmda_path_size, setup_lmda_max, setup_lmda_path, lmda_max, lmda_path) = _render_inputs(
+        groups=groups, lmda_max=lmda_max, lmda_path=lmda_path, lmda_path_size=lmda_path_size,
+        max_screen_size=max_screen_size, max_active_size=max_active_size, dtype=dtype)
+    K = glm.y.shape[-1]
+    Xe, offsets = _render_multi_inputs(X=X, offsets=offsets, intercept=intercept, n_threads=n_threads, dtype=dtype)
+    arrays = _common_arrays(groups=groups, group_sizes=group_sizes, penalty=penalty, lmda_path=lmda_path, screen_set=screen_set,
+                            screen_beta=screen_beta, screen_is_active=screen_is_active, active_set=active_set, grad=grad,
+                            resid=resid, dtype=dtype)
+    arrays["offsets"] = np.array(np.asarray(offsets).ravel(), copy=True, dtype=dtype)
+    arrays["eta"] = np.array(np.asarray(eta).ravel(), copy=True, dtype=dtype)
+    arrays["X_expanded"] = Xe
+    cfg = dict(alpha=float(alpha), beta0=0.0, loss_null=None if loss_null is None else float(loss_null),
+               loss_full=float(loss_full), irls_max_iters=int(irls_max_iters), irls_tol=irls_tol,
+               lmda_max=float(lmda_max), min_ratio=min_ratio, lmda_path_size=int(lmda_path_size), setup_lmda_max=setup_lmda_max,
+               setup_lmda_path=setup_lmda_path, max_screen_size=max_screen_size, max_active_size=max_active_size,
+               pivot_subset_ratio=pivot_subset_ratio, pivot_subset_min=pivot_subset_min, pivot_slack_ratio=pivot_slack_ratio,
+               screen_rule=screen_rule, max_iters=int(max_iters), tol=tol, adev_tol=adev_tol, ddev_tol=ddev_tol,
+               newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=early_exit, intercept=False,
+               n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float(lmda), n_classes=int(K),
+               multi_intercept=bool(intercept))
+    return _MultiNaive(X=X, glm_obj=glm, use_glm=True, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=Xe.cols())
