@@ -78,6 +78,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "sweep_force_direct") Configs::sweep_force_direct = (int)value;
     else if (s == "device_eigh") Configs::device_eigh = (int)value;
     else if (s == "sweep_profile") Configs::sweep_profile = (int)value;
+    else if (s == "sweep_batch") Configs::sweep_batch = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -94,6 +95,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "sweep_force_direct") *value = Configs::sweep_force_direct;
     else if (s == "device_eigh") *value = Configs::device_eigh;
     else if (s == "sweep_profile") *value = Configs::sweep_profile;
+    else if (s == "sweep_batch") *value = Configs::sweep_batch;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -500,6 +502,8 @@ static int state_scalar(const PathState<T>& s, const std::string& nm, double* ou
     else if (nm == "sweep_ncta") *out = s.X->last_geom.ncta; else if (nm == "sweep_stages") *out = s.X->last_geom.n_stages;
     else if (nm == "sweep_smem_bytes") *out = (double)s.X->last_geom.smem_bytes; else if (nm == "sweep_staged") *out = s.X->last_geom.smem ? 1 : 0;
     else if (nm == "sweep_threads") *out = s.X->last_geom.threads;
+    else if (nm == "sweep_batch") *out = s.X->last_bgeom.ok ? s.X->last_bgeom.B : 1;
+    else if (nm == "n_panels_built") *out = (double)s.n_panels_built; else if (nm == "n_batched_launches") *out = (double)s.n_batched_launches;
     else if (nm == "setup_lmda_max") *out = s.setup_lmda_max; else if (nm == "setup_lmda_path") *out = s.setup_lmda_path;
     else if (nm.rfind("t_", 0) == 0) {
         *out = 0;

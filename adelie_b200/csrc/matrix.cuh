@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "dense_kernels.cuh"
 #include "sweep.cuh"
+#include "sweep_batched.cuh"
 #include "dist.cuh"
 #include <cuda.h>
 #include <curand_kernel.h>
@@ -90,6 +91,42 @@ inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max, int K = 
     }
     return g;
 }
+
+// Geometry of the batched look-ahead kernel (sweep_batched.cuh).  ok == false: use pin_solve_kernel instead.
+struct BatchGeometry { bool ok; int ncta, ncta_pad, B, Ccap, n_stages, stage_elems, rows_stride, units_base, units_rem, rec_stride, pslot_elems; size_t smem_bytes; };
+
+template <class T>
+inline BatchGeometry plan_batched(int64_t n_pad, int gs_max, int rec_max) {
+    const auto& di = DeviceInfo::get();
+    BatchGeometry g{};
+    g.ok = false;
+    if (Configs::sweep_batch == 1 || Configs::sweep_force_direct || gs_max > 32 || gs_max < 1) return g;
+    const int64_t units = n_pad / kRowAlign;
+    int ncta = Configs::sweep_ctas > 0 ? Configs::sweep_ctas
+                                       : (int)std::min<int64_t>(di.sm_count, std::max<int64_t>(1, units / std::max(1, Configs::sweep_min_rows_per_cta / kRowAlign)));
+    ncta = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ncta, units), di.sm_count));
+    g.ncta = ncta; g.ncta_pad = (ncta + 31) / 32 * 32;
+    g.units_base = (int)(units / ncta); g.units_rem = (int)(units % ncta);
+    g.rows_stride = (g.units_base + (g.units_rem ? 1 : 0)) * kRowAlign;
+    g.rec_stride = (rec_max + 3) / 4 * 4;
+    g.stage_elems = (g.rows_stride * gs_max + 31) / 32 * 32;
+    const int want = Configs::sweep_batch > 1 ? Configs::sweep_batch : 4;
+    for (int B = std::min(std::min(want, kBatchMax), kBatchColsMax / gs_max); B >= 2; --B) {
+        const int Ccap = (B * gs_max + 3) / 4 * 4;
+        const int pslot = Ccap * 2 * Ccap + B * g.rec_stride;
+        const size_t fixed = BatchSmem<T>::fixed_bytes(Ccap) + sizeof(T) * (2 * (size_t)g.rows_stride + 2 * (size_t)pslot);
+        if (fixed >= di.smem_optin) continue;
+        const int ns = (int)std::min<size_t>(kMaxStages, (di.smem_optin - fixed) / (sizeof(T) * (size_t)g.stage_elems));
+        if (ns < 2) continue;
+        g.ok = true; g.B = B; g.Ccap = Ccap; g.pslot_elems = pslot; g.n_stages = ns;
+        g.smem_bytes = fixed + sizeof(T) * (size_t)ns * g.stage_elems;
+        break;
+    }
+    return g;
+}
+
+template <class T>
+struct BatchLaunch { const T* panels_screen; const T* panels_active; int n_active_panelled; int start_phase; };
 
 // xorshift-free counter based fill: X[i, j] ~ N(0,1) from Philox(seed, subsequence = column, offset = row)
 template <class T>
@@ -225,6 +262,54 @@ struct DenseMatrix {
             sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
         }
         AB_CUDA(cudaGetLastError());
+    }
+
+    // Gram panels of the batched kernel: Q[out_off + a*ldq + b] = X[:, col_s+a]^T W X[:, col_t+b] for every item
+    void d_pair_gram(const PairItem* items_dev, int n_items, int64_t total, const T* w, T* Q, int ldq) {
+        if (n_items <= 0) return;
+        const int sms = DeviceInfo::get().sm_count;
+        int n_rb = std::max(1, std::min(sms, (8 * sms + n_items - 1) / n_items));
+        int rows_per_block = (int)((ld + n_rb - 1) / n_rb);
+        rows_per_block = (rows_per_block + kRowAlign - 1) / kRowAlign * kRowAlign;
+        n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
+        part.reserve_keep((size_t)n_rb * total, stream);
+        pair_gram_kernel<T><<<dim3(n_items, n_rb), 256, 0, stream>>>(X, ld, ld, items_dev, w, part.p, total, rows_per_block);
+        pair_gram_finalize_kernel<T><<<n_items, 128, 0, stream>>>(items_dev, part.p, n_rb, total, Q, ldq);
+        AB_CUDA(cudaGetLastError());
+    }
+
+    // The batched look-ahead pin solve (sweep_batched.cuh); single response, single GPU, static weights.
+    BatchGeometry last_bgeom{};
+    void pin_solve_batched(const PinLaunch<T>& L, const BatchGeometry& g, const BatchLaunch<T>& bl) {
+        SweepContext& ctx = SweepContext::get();
+        last_bgeom = g;
+        last_geom.ncta = g.ncta; last_geom.n_stages = g.n_stages; last_geom.smem = true; last_geom.smem_bytes = g.smem_bytes; last_geom.threads = 512;
+        BatchKernelArgs<T> a{};
+        a.X = X; a.ld = ld; a.resid = L.resid; a.weights = L.weights;
+        a.meta = L.meta; a.S = L.S; a.grec = L.grec;
+        act_stride = ((int64_t)L.S + 127) / 128 * 128 + 128;
+        act_rep.reserve_keep((size_t)act_stride * g.ncta, stream);
+        a.is_active_in = L.is_active_in; a.is_active_rep = act_rep.p; a.act_stride = act_stride;
+        beta_stride = ((int64_t)L.beta_len + 31) / 32 * 32 + 32;
+        beta_rep.reserve_keep((size_t)beta_stride * g.ncta, stream);
+        a.beta_in = L.beta_in; a.beta_rep = beta_rep.p; a.beta_stride = beta_stride; a.beta_len = L.beta_len;
+        a.active_set = L.active_set; a.sc = L.sc;
+        a.panels_screen = bl.panels_screen; a.panels_active = bl.panels_active; a.n_active_panelled = bl.n_active_panelled;
+        a.B = g.B; a.Ccap = g.Ccap;
+        a.ll1 = ctx.ll.p; a.ll2 = ctx.ll2.p; a.ncta_pad = g.ncta_pad;
+        { int f = 1; while (f * f < g.ncta) ++f; a.fan = std::max(1, f); }
+        a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
+        a.lmda = L.lmda; a.alpha = L.alpha; a.tol = L.tol; a.newton_tol = L.newton_tol; a.dbeta_tol = Configs::dbeta_tol;
+        a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
+        a.start_phase = bl.start_phase;
+        a.units_base = g.units_base; a.units_rem = g.units_rem; a.rows_stride = g.rows_stride;
+        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.rec_stride = g.rec_stride; a.pslot_elems = g.pslot_elems;
+        if (Configs::sweep_profile) { if (!stats.n) stats.alloc(32 + 8 * 160); a.stats = stats.p; } else a.stats = nullptr;
+        void* kargs[] = {&a};
+        const void* fn = !a.stats ? (const void*)pin_solve_batched_kernel<T, 0> : (Configs::sweep_profile >= 2 ? (const void*)pin_solve_batched_kernel<T, 2> : (const void*)pin_solve_batched_kernel<T, 1>);
+        AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+        if (g.ncta > 1) AB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g.ncta), dim3(512), kargs, g.smem_bytes, stream));
+        else AB_CUDA(cudaLaunchKernel(fn, dim3(1), dim3(512), kargs, g.smem_bytes, stream));
     }
 
     // The fused pin solve (sweep.cuh).

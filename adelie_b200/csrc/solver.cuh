@@ -152,6 +152,11 @@ struct PathState {
     DevBuf<PinScalars> d_sc; DevBuf<CovItem> d_cov_items; DevBuf<double> d_cov_out; DevBuf<int32_t> d_cols; DevBuf<T> d_tmp;
     DevBuf<double> d_scal;       // small scalar scratch (device-side sub_scale etc.)
     std::vector<GroupMeta> h_meta; std::vector<T> h_grec; size_t grec_uploaded = 0, meta_uploaded = 0;
+    // Gram panels of the batched look-ahead kernel (sweep_batched.cuh): one list per sweep order (screen positions, active list)
+    struct PanelList { DevBuf<T> Q; std::vector<int32_t> entries; int B = 0, Ccap = 0; };
+    PanelList pl_screen, pl_active;
+    DevBuf<PairItem> d_pair_items;
+    long long n_panels_built = 0, n_batched_launches = 0;
     int gs_max_screen = 1, rec_max_screen = 4, feat_max_screen = 1;
     PinnedBuf<PinScalars> h_sc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -338,9 +343,59 @@ struct PathState {
         if (!full) { meta_uploaded = meta.size(); grec_uploaded = grec.size(); }
     }
 
+    // ------------------------------------------------------------------ Gram panels (sweep_batched.cuh)
+    // Panel b of a list holds, for every source column of batch b, X_src^T W X_t against the later groups of batch b
+    // (targets [0, Ccap)) and all groups of batch b+1 (targets [Ccap, 2 Ccap)).  Lists only ever grow at the tail, so only the
+    // panels from the batch before the first new position onwards are (re)computed.
+    void ensure_panels(PanelList& pl, const std::vector<int32_t>& entries, int B, int Ccap, const T* d_w) {
+        if (pl.B != B || pl.Ccap != Ccap) { pl.entries.clear(); pl.B = B; pl.Ccap = Ccap; }
+        size_t prev = 0;
+        while (prev < pl.entries.size() && prev < entries.size() && pl.entries[prev] == entries[prev]) ++prev;
+        if (prev == entries.size() && prev == pl.entries.size()) return;
+        AB_TIME(timers, "panels");
+        const size_t N = entries.size();
+        const int ldq = 2 * Ccap;
+        const size_t pstride = (size_t)Ccap * ldq;
+        const size_t nb = (N + B - 1) / B;
+        const size_t b0 = (prev / B > 0) ? prev / B - 1 : 0;
+        pl.Q.reserve_keep(nb * pstride + 64);
+        if (nb > b0) AB_CUDA(cudaMemsetAsync(pl.Q.p + b0 * pstride, 0, (nb - b0) * pstride * sizeof(T), 0));
+        std::vector<PairItem> items; int64_t total = 0;
+        auto grp = [&](size_t pos, int& col, int& gs) { const idx_t g = screen_set[entries[pos]]; col = (int)groups[g]; gs = (int)group_sizes[g]; };
+        for (size_t b = b0; b < nb; ++b) {
+            const size_t p0 = b * B, p1 = std::min(N, p0 + B), p2 = std::min(N, p1 + B);
+            int off_k = 0;
+            for (size_t k = p0; k < p1; ++k) {
+                int ck, gk; grp(k, ck, gk);
+                int off_t = off_k + gk;
+                for (size_t k2 = k + 1; k2 < p1; ++k2) {
+                    int c2, g2; grp(k2, c2, g2);
+                    items.push_back(PairItem{ck, gk, c2, g2, (int64_t)(b * pstride + (size_t)off_k * ldq + off_t), total});
+                    total += (int64_t)gk * g2; off_t += g2;
+                }
+                off_t = 0;
+                for (size_t k2 = p1; k2 < p2; ++k2) {
+                    int c2, g2; grp(k2, c2, g2);
+                    items.push_back(PairItem{ck, gk, c2, g2, (int64_t)(b * pstride + (size_t)off_k * ldq + Ccap + off_t), total});
+                    total += (int64_t)gk * g2; off_t += g2;
+                }
+                off_k += gk;
+            }
+        }
+        if (!items.empty()) {
+            d_pair_items.reserve_keep(items.size());
+            d_pair_items.upload(items.data(), items.size());
+            X->d_pair_gram(d_pair_items.p, (int)items.size(), total, d_w, pl.Q.p, ldq);
+            AB_CUDA(cudaStreamSynchronize(0));           // `items` (pageable host memory) must outlive the upload
+            n_kernel_launches += 2;
+        }
+        n_panels_built += (long long)(nb - b0);
+        pl.entries = entries;
+    }
+
     // ------------------------------------------------------------------ the fused pin solve
     // Runs pin::naive::solve (solver_gaussian_pin_naive.hpp:223-401) for one lambda on the device.
-    PinResult run_pin(T* d_r, const T* d_w, T lmda_, T tol_pin, T y_mean_, T& rsq_io, T& resid_sum_io) {
+    PinResult run_pin(T* d_r, const T* d_w, T lmda_, T tol_pin, T y_mean_, T& rsq_io, T& resid_sum_io, bool static_weights = false) {
         AB_TIME(timers, "run_pin");
         const size_t S = screen_set.size();
         d_screen_beta.reserve_keep(screen_beta.size() + 4); d_is_active.reserve_keep(S + 4);
@@ -362,16 +417,54 @@ struct PathState {
         L.gs_max = gs_max_screen; L.rec_max = rec_max_screen; L.K = K; L.feat_max = feat_max_screen;
         if (check_interrupt) check_interrupt();
         if (DistContext::get().active()) DistContext::get().allreduce<double>(d_scal.p, 1);    // cheap rank barrier
-        AB_CUDA(cudaEventRecord(ev0, 0));
-        X->pin_solve(L);
-        AB_CUDA(cudaEventRecord(ev1, 0));
-        d_sc.download(h_sc.p, 1);
         const size_t old_active = active_set_size;
+        float ms = 0;
+        BatchGeometry bg{};
+        if (static_weights && K == 1 && !DistContext::get().active()) bg = plan_batched<T>(X->n_pad(), gs_max_screen, rec_max_screen);
+        if (!bg.ok) {
+            AB_CUDA(cudaEventRecord(ev0, 0));
+            X->pin_solve(L);
+            AB_CUDA(cudaEventRecord(ev1, 0));
+            d_sc.download(h_sc.p, 1);
+            AB_CUDA(cudaStreamSynchronize(0));
+            ++n_kernel_launches;
+            AB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        } else {
+            // batched look-ahead kernel: Gram panels for both sweep orders; the kernel hands control back when the active list
+            // outgrew its panels (after a screen sweep that added groups), everything else continues on the device
+            std::vector<int32_t> ent(S);
+            std::iota(ent.begin(), ent.end(), 0);
+            ensure_panels(pl_screen, ent, bg.B, bg.Ccap, d_w);
+            BatchLaunch<T> bl{};
+            bl.start_phase = kSweepActive;
+            size_t act_now = active_set_size;
+            while (true) {
+                ent.assign(act32.begin(), act32.begin() + act_now);
+                ensure_panels(pl_active, ent, bg.B, bg.Ccap, d_w);
+                bl.panels_screen = pl_screen.Q.p; bl.panels_active = pl_active.Q.p; bl.n_active_panelled = (int)act_now;
+                AB_CUDA(cudaEventRecord(ev0, 0));
+                X->pin_solve_batched(L, bg, bl);
+                AB_CUDA(cudaEventRecord(ev1, 0));
+                d_sc.download(h_sc.p, 1);
+                AB_CUDA(cudaStreamSynchronize(0));
+                ++n_kernel_launches; ++n_batched_launches;
+                float m1 = 0; AB_CUDA(cudaEventElapsedTime(&m1, ev0, ev1));
+                ms += m1;
+                if (h_sc.p->error || h_sc.p->pad != kBatchNeedPanels) break;
+                // the active list grew: fetch the new entries, make replica 0 the input of the next launch
+                const size_t act_new = (size_t)h_sc.p->active_set_size;
+                act32.resize(act_new);
+                d_active_set.download(act32.data() + act_now, act_new - act_now, act_now);
+                AB_CUDA(cudaMemcpyAsync(d_screen_beta.p, X->beta_rep.p, screen_beta.size() * sizeof(T), cudaMemcpyDeviceToDevice, 0));
+                AB_CUDA(cudaMemcpyAsync(d_is_active.p, X->act_rep.p, S, cudaMemcpyDeviceToDevice, 0));
+                AB_CUDA(cudaStreamSynchronize(0));
+                act_now = act_new;
+            }
+        }
         X->beta_rep.download(screen_beta.data(), screen_beta.size());     // replica 0
         X->act_rep.download(screen_is_active.data(), S);                   // replica 0
         AB_CUDA(cudaStreamSynchronize(0));
-        ++n_pin_solves; ++n_kernel_launches;
-        float ms = 0; AB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        ++n_pin_solves;
         time_sweep_kernel += ms * 1e-3;
         sc = *h_sc.p;
         if (sc.error) {
@@ -417,7 +510,7 @@ struct PathState {
         std::vector<T> beta_prev = screen_beta; std::vector<int8_t> act_prev = screen_is_active;
         upload_screen_tables(h_meta, h_grec, false);
         try {
-            return run_pin(d_resid.p, d_weights.p, lmda_, tol * y_var, y_mean, rsq, resid_sum);
+            return run_pin(d_resid.p, d_weights.p, lmda_, tol * y_var, y_mean, rsq, resid_sum, true);
         } catch (...) {
             std::swap(d_resid.p, d_resid_prev.p);
             screen_beta.swap(beta_prev); screen_is_active.swap(act_prev);

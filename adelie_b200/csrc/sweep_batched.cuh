@@ -1,0 +1,1003 @@
+// adelie_b200/csrc/sweep_batched.cuh -- the batched, look-ahead variant of the fused pin solve.
+//
+// Same algorithm and the same iterates (up to rounding) as pin_solve_kernel (sweep.cuh), i.e. pin::naive::solve /
+// coordinate_descent of the reference (CORE/solver/solver_gaussian_pin_naive.hpp:26-168, 181-215, 223-401), reorganised
+// so that the Gauss-Seidel dependency chain no longer contains a grid-wide exchange per group:
+//
+//   * the sweep list (screen positions or the active list) is cut into BATCHES of B consecutive groups; the partial
+//     gradients X_g^T (w o r) of all groups of a batch are computed against the SAME residual and all-reduced over the
+//     CTAs in ONE flagged-line exchange;
+//   * exactness of Gauss-Seidel is restored with small precomputed Gram panels: once group k of the batch moved by
+//     del_k = beta_old - beta_new (r += X_k del_k), the stale gradient of every later group k' is corrected by
+//     G[k', k] del_k with G[k', k] = X_k'^T W X_k (weights are static for the Gaussian path, so a panel is computed once
+//     when its batch is formed -- the lists are append-only over the whole path -- by pair_gram_kernel);
+//   * LOOK-AHEAD: the dot phase of batch b+1 runs against the residual that lacks batch b's update while the control warp
+//     is still solving batch b's proximal problems; the panel of batch b also holds the cross block X_b^T W X_{b+1},
+//     so the HBM stream of the next batch, its exchange and the serial prox chain overlap.
+//
+// Warp roles inside each of the persistent CTAs (one per SM, 512 threads):
+//   warp 0          control warp (CW): replicated proximal updates + gradient corrections, sweep control flow
+//   warp 4          TMA producer: streams column tiles (cp.async.bulk -> stage ring) and panels/records (panel ring)
+//   warps 8, 12     exchange warps (EW): two-level flagged-line all-reduce through L2, asynchronous to everything else
+//   other 12 warps  data warps (DW): dot phase D(b) from the staged tiles, residual update U(b) from L2 (the tile was
+//                   streamed through L2 one batch earlier), each thread owning a private set of residual rows.
+// Schedule of the data warps: D(0); for b: { D(b+1); U(b) }.  The control roles all sit on scheduler 0 so that the
+// latency-critical control warp does not compete with the data warps for issue slots.
+#pragma once
+#include "sweep.cuh"
+#include <type_traits>
+
+namespace ab {
+
+constexpr int kBatchMax = 8;           // most groups per batch
+constexpr int kBatchColsMax = 64;      // most columns per batch (Ccap <= 64): one pass of the 64 exchange threads
+constexpr int kBatchLLSlots = 4;       // exchange buffers are 4-deep (see the race analysis at ew_exchange)
+constexpr int kBatchDW = 12;           // data warps
+constexpr int kBatchNDT = kBatchDW * 32;
+
+enum { kBatchDone = 0, kBatchNeedPanels = 1 };
+
+template <class T>
+struct BatchKernelArgs {
+    const T* X; int64_t ld;
+    T* resid; const T* weights;
+    const GroupMeta* meta; int S; const T* grec;
+    const T* beta_in; T* beta_rep; int64_t beta_stride; int beta_len;
+    const int8_t* is_active_in; int8_t* is_active_rep; int64_t act_stride;
+    int32_t* active_set;
+    PinScalars* sc;
+    const T* panels_screen; const T* panels_active;      // [n_batches][Ccap][2 * Ccap]
+    int n_active_panelled;                               // active-list positions covered by panels_active
+    int B, Ccap;
+    dev::LLLine* ll1; dev::LLLine* ll2; int ncta_pad; int fan;
+    uint32_t* epoch; int* abort_flag;
+    double lmda, alpha, tol, newton_tol, dbeta_tol;
+    long long max_iters; int newton_max_iters; int max_active_size; int intercept;
+    int start_phase;
+    int units_base, units_rem, rows_stride;
+    int n_stages, stage_elems;
+    int rec_stride;                                      // elements between the records inside a panel slot
+    int pslot_elems;                                     // elements per panel slot = Ccap * 2 Ccap + B * rec_stride
+    long long* stats;
+};
+
+struct BatchCtrl {
+    int sw_seq;                   // number of published sweep descriptors
+    int sw_kind[4], sw_count[4];
+    int prox_done;                // groups completed by the control warp (monotone over the launch)
+    int gready;                   // batches whose all-reduced gradient is in gstale (monotone)
+    int halt;                     // CTA-local shutdown (error / abort)
+    int error;
+    int changed[2][kBatchMax];
+};
+
+namespace dev {
+__device__ __forceinline__ void st_release_cta(int* p, int v) {
+    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+// spin until *p >= target; false if the CTA was halted / the kernel aborted
+__device__ __forceinline__ bool wait_counter(const int* p, int target, volatile int* abort_flag, volatile int* halt) {
+    SpinGuard g;
+    while (ld_acquire_cta(p) < target) {
+        if (g.give_up(abort_flag, halt)) return false;
+        __nanosleep(64);                       // do not steal issue slots / shared-memory bandwidth from the control warp
+    }
+    return true;
+}
+} // namespace dev
+
+namespace dev {
+// L2 eviction-priority policies: the column tiles streamed for the dot phase are re-read by the residual update one
+// batch later (keep: evict_last); that second read is the last use (evict_first frees the lines for the next tiles).
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void ld_hint(const float* p, float (&v)[4], uint64_t pol) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void ld_hint(const double* p, double (&v)[2], uint64_t pol) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v[0]), "=d"(v[1]) : "l"(p), "l"(pol));
+}
+} // namespace dev
+
+// Branch-free reciprocal / square root for the Newton iteration of the control warp.  IEEE float division compiles to a
+// fast path + range check + slow-path call per use, which serialises the (independent) divisions of one evaluation of phi;
+// MUFU.RCP + one Newton refinement (<= 1 ulp) pipelines.  double keeps the IEEE operations.
+template <class P> struct FastMath;
+template <> struct FastMath<float> {
+    static __device__ __forceinline__ float rcp(float x) {
+        float u; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(x));
+        return fmaf(u, fmaf(-x, u, 1.0f), u);
+    }
+    static __device__ __forceinline__ float sqrt_(float x) { float u; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(x)); return u; }
+};
+template <> struct FastMath<double> {
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+};
+
+// Group update (solver_gaussian_pin_naive.hpp:109-164) for 1 < gs <= GSP <= 12 by the control warp, one coefficient per lane,
+// written for the FEWEST DEPENDENT SHARED-MEMORY ROUND TRIPS (the data warps keep the LSU pipe saturated, so every round trip
+// of the lone control warp costs hundreds of cycles): prox_pre() loads everything that does not depend on the gradient (it is
+// issued one group ahead, behind the previous group's corrections); prox_post() broadcasts the rotated gradient and the
+// shifted eigenvalues once, after which the whole Newton iteration on h = ||x|| (newton.hpp:44-142) runs in registers,
+// redundantly in every lane.  Start point: the previous norm ||beta_g|| when phi there is >= 0 (left of the root, from where
+// the iteration is monotone, like h0 = 0 of the reference), otherwise 0; only the converged root matters for parity.
+template <class P, int GSP> struct LanePre { P A, xm, xmt, aold_c, ao, h0sq; P vcol[GSP], vrow[GSP]; };
+
+template <class T, class P, int GSP>
+__device__ __forceinline__ void prox_pre(LanePre<P, GSP>& r, const T* rec, int gs, const P* aold_s, int lane) {
+    const bool on = lane < gs;
+    const int c = on ? lane : 0;
+    const T* V = rec + 3 * gs;
+    r.A = on ? (P)rec[c] : P(0); r.xm = on ? (P)rec[gs + c] : P(0); r.xmt = on ? (P)rec[2 * gs + c] : P(0);
+    r.aold_c = on ? aold_s[c] : P(0);
+    P ao = 0, h0sq = 0;
+#pragma unroll
+    for (int q = 0; q < GSP; ++q) {
+        const bool in = q < gs;
+        r.vcol[q] = in ? (P)V[q * gs + c] : P(0);
+        r.vrow[q] = in ? (P)V[c * gs + q] : P(0);
+        const P aq = in ? aold_s[q] : P(0);
+        ao += aq * r.vcol[q]; h0sq += aq * aq;
+    }
+    r.ao = on ? ao : P(0); r.h0sq = h0sq;
+}
+
+// bc: shared scratch of 5 * GSP elements.  Returns 1 if the coefficients moved; del (original basis) in dl[0..gs).
+template <class T, class P, int GSP>
+__device__ __forceinline__ int prox_post(const LanePre<P, GSP>& pre, int gs, double g_in, P l1k, P l2k, P tol, int max_iters,
+                                         P dbeta_tol, int intercept, ProxState& ps, int lane, P* bc, T* beta_g, T* dl, long long* pp)
+{
+    constexpr int VN = VecT<P>::N;
+    using FM = FastMath<P>;
+    long long tc_ = pp ? clock64() : 0;
+#define ABP_TICK(k) do { if (pp) { const long long t_ = clock64(); pp[k] += t_ - tc_; tc_ = t_; } } while (0)
+    const bool on = lane < gs;
+    // ---- gradient in the original basis, broadcast, rotated: gt = gk V + A (a_old V)
+    P gk = on ? (P)g_in : P(0);
+    if (intercept && on) gk -= (P)ps.resid_sum * pre.xm;
+    if (lane < GSP) bc[lane] = gk;
+    __syncwarp();
+    P gt0 = 0;
+    {
+        P gka[GSP];
+#pragma unroll
+        for (int q = 0; q < GSP; q += VN) vec_load<P>(bc + q, reinterpret_cast<P(&)[VN]>(gka[q]));
+#pragma unroll
+        for (int q = 0; q < GSP; ++q) gt0 += gka[q] * pre.vcol[q];
+    }
+    if (!on) gt0 = 0;
+    const P gt = gt0 + pre.A * pre.ao;
+    const P D = on ? pre.A + l2k : P(1);
+    if (lane < GSP) { bc[GSP + lane] = gt; bc[2 * GSP + lane] = D; }
+    __syncwarp();
+    P gta[GSP], Da[GSP];
+#pragma unroll
+    for (int q = 0; q < GSP; q += VN) { vec_load<P>(bc + GSP + q, reinterpret_cast<P(&)[VN]>(gta[q])); vec_load<P>(bc + 2 * GSP + q, reinterpret_cast<P(&)[VN]>(Da[q])); }
+    ABP_TICK(1);
+    // ---- root of phi(h) = sum (gt / (D h + l1))^2 - 1, in registers
+    P at = 0; int nit = 0;
+    if (l1k <= P(0)) {
+        at = (on && gt != P(0)) ? gt / (pre.A + l2k) : P(0);
+    } else {
+        const P tol_eff = fmax(tol, ProxEps<P>::floor_tol());
+        P t, sd;
+        auto eval = [&](P h) {
+            P t0 = 0, t1 = 0, s0 = 0, s1 = 0;
+#pragma unroll
+            for (int q = 0; q < GSP; q += 2) {
+                const P u0 = FM::rcp(Da[q] * h + l1k), u1 = FM::rcp(Da[q + 1] * h + l1k);
+                const P q0 = gta[q] * u0, q1 = gta[q + 1] * u1;
+                const P x0 = q0 * q0, x1 = q1 * q1;
+                t0 += x0; t1 += x1; s0 += x0 * Da[q] * u0; s1 += x1 * Da[q + 1] * u1;
+            }
+            t = t0 + t1; sd = s0 + s1;
+        };
+        // One evaluation site (code size: the control warp's path must stay inside the instruction cache).
+        // mode 0: phi(0), doubles as the ||v|| <= l1 test (newton.hpp:62-66); mode 1: warm start; mode 2: Newton iterations
+        const P hw = (pre.h0sq > P(0)) ? FM::sqrt_(pre.h0sq) : P(0);
+        P h = 0, t_keep = 0, sd_keep = 0;
+        int mode = 0; bool zero = false;
+#pragma unroll 1
+        while (true) {
+            eval(h);
+            if (mode == 0) {
+                if (!(t > P(1))) { zero = true; break; }
+                if (hw > P(0)) { t_keep = t; sd_keep = sd; h = hw; mode = 1; continue; }
+                mode = 2;
+            } else if (mode == 1) {
+                mode = 2;
+                if (!(t - P(1) >= -tol_eff)) { h = 0; t = t_keep; sd = sd_keep; }    // right of the root: restart from 0
+            }
+            if (!(fabs(t - P(1)) > tol_eff) || nit >= max_iters) break;
+            // h - fh / dfh with dfh = -sd (1 + sqrt t) / t   (optimization/newton.hpp:56-63), one reciprocal
+            const P hn = fmax(h + (t - P(1)) * t * FM::rcp(sd * (P(1) + FM::sqrt_(t))), P(0));
+            if (hn == h) break;                                   // no representable progress left
+            h = hn; ++nit;
+        }
+        at = (on && !zero) ? h * gt / (D * h + l1k) : P(0);
+    }
+    ps.newton_iters_max = max(ps.newton_iters_max, nit);
+    if (nit >= max_iters) ps.error = kErrNewton;
+    ABP_TICK(2);
+    if (pp) pp[5] += nit;
+    // ---- the four sums of the update test / bookkeeping and the broadcast of the new rotated coefficients: one round trip
+    const P d = at - pre.ao;
+    __syncwarp();
+    if (lane < GSP) {
+        bc[lane] = d * d; bc[GSP + lane] = pre.A * d * d; bc[2 * GSP + lane] = d * (2 * gt0 - d * pre.A); bc[3 * GSP + lane] = -pre.xmt * d; bc[4 * GSP + lane] = at;
+    }
+    __syncwarp();
+    P red[4] = {0, 0, 0, 0};
+    P ata[GSP];
+#pragma unroll
+    for (int q = 0; q < GSP; q += VN) {
+        P v0[VN], v1[VN], v2[VN], v3[VN];
+        vec_load<P>(bc + q, v0); vec_load<P>(bc + GSP + q, v1); vec_load<P>(bc + 2 * GSP + q, v2); vec_load<P>(bc + 3 * GSP + q, v3);
+        vec_load<P>(bc + 4 * GSP + q, reinterpret_cast<P(&)[VN]>(ata[q]));
+#pragma unroll
+        for (int k = 0; k < VN; ++k) { red[0] += v0[k]; red[1] += v1[k]; red[2] += v2[k]; red[3] += v3[k]; }
+    }
+    ABP_TICK(3);
+    if (sqrt(red[0]) <= dbeta_tol * sqrt((P)gs)) { if (pp) ++pp[6]; return 0; }      // :146-147
+    ps.cm = fmax(ps.cm, (double)(red[1] / gs));
+    ps.rsq += (double)red[2];
+    ps.resid_sum += (double)red[3];
+    P an0 = 0, an1 = 0;
+#pragma unroll
+    for (int q = 0; q < GSP; q += 2) { an0 += ata[q] * pre.vrow[q]; an1 += ata[q + 1] * pre.vrow[q + 1]; }     // rotate back: a = at V^T
+    if (on) {
+        const T anT = (T)(an0 + an1);
+        beta_g[lane] = anT;
+        dl[lane] = (T)(pre.aold_c - (P)anT);
+    }
+    ABP_TICK(4);
+#undef ABP_TICK
+    return 1;
+}
+
+// Gradient corrections after group (off, gs) of the current batch moved by dl: g[t] += sum_c Q[off + c][t] dl[c] for the later
+// columns of this batch (gc, columns lane and lane + 32) and all columns of the next batch (cn).  All loads are independent.
+template <class T, class P, int GSP>
+__device__ __forceinline__ void apply_corrections(const T* Q, int ldq, int Ccap, int off, int gs, const T* dl, int C_cur, int C_nxt,
+                                                  double (&gc)[2], P (&cn)[2], int lane)
+{
+    P acc[4] = {0, 0, 0, 0};
+    const bool has1 = lane + 32 < Ccap;
+    constexpr int NC = GSP > 0 ? GSP : 32;                 // GSP == 0: runtime loop (large groups)
+#pragma unroll (GSP > 0 ? GSP : 2)
+    for (int c = 0; c < NC; ++c) {
+        if (c < gs) {
+            const P dc = (P)dl[c];
+            const T* qrow = Q + (size_t)(off + c) * ldq + lane;
+            acc[0] += (P)qrow[0] * dc;
+            acc[2] += (P)qrow[Ccap] * dc;
+            if (has1) { acc[1] += (P)qrow[32] * dc; acc[3] += (P)qrow[Ccap + 32] * dc; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int t = lane + 32 * j;
+        if (t >= off + gs && t < C_cur) gc[j] += (double)acc[j];
+        if (t < C_nxt) cn[j] += acc[2 + j];
+    }
+}
+
+template <class T>
+struct BatchSmem {
+    static constexpr size_t kHeaderBytes = 512;
+    // header | gstale[2][Ccap] f64 | corr[2][Ccap] | gcur[32] f64 | del[2][Ccap] | aold[2][Ccap] | p_gk[32] p_at[32] scr[128] |
+    // wpart[2][DW][Ccap] f64 | r tile | w tile | panel slots [2] | stages
+    __host__ __device__ static size_t fixed_bytes(int Ccap) {
+        size_t b = kHeaderBytes + sizeof(double) * ((size_t)Ccap * 8 + 32 + 32 + 32 + 128 + (size_t)2 * kBatchDW * Ccap);
+        return (b + 127) / 128 * 128;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+template <class T, int PROF>      // PROF: 0 off, 1 stall/busy split per role (cheap), 2 per-phase counters (perturbs: spills)
+__global__ void __launch_bounds__(512, 1)
+pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int VN = VecT<T>::N;
+    using P = T;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cta = blockIdx.x, ncta = gridDim.x;
+    const int B = a.B, Ccap = a.Ccap, ldq = 2 * a.Ccap;
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);          // [kMaxStages]
+    uint64_t* empty_bar = full_bar + kMaxStages;                          // [kMaxStages]
+    uint64_t* pfull_bar = empty_bar + kMaxStages;                         // [2]
+    uint64_t* pempty_bar = pfull_bar + 2;                                 // [2]
+    uint64_t* prox_bar = pempty_bar + 2;                                  // [2][kBatchMax]: group k of a batch (by parity) is solved
+    uint64_t* gready_bar = prox_bar + 2 * kBatchMax;                      // [2]: all-reduced gradient of a batch (by parity) is in gstale
+    uint64_t* dbar = gready_bar + 2;                                      // [2]: every data warp has written its partials of a batch
+    BatchCtrl* ctrl = reinterpret_cast<BatchCtrl*>(smem_raw + 384);
+    double* gstale = reinterpret_cast<double*>(smem_raw + BatchSmem<T>::kHeaderBytes);   // [2][Ccap]
+    double* corr_raw = gstale + 2 * Ccap;                                 // [2][Ccap] (P)
+    double* gcur = corr_raw + 2 * Ccap;                                   // [32]
+    double* del_raw = gcur + 32;                                          // [2][Ccap] (T)
+    double* aold_raw = del_raw + 2 * Ccap;                                // [2][Ccap] (P)
+    double* pscr_raw = aold_raw + 2 * Ccap;                               // p_gk[32] p_at[32] scr[128]
+    double* wpart = pscr_raw + 32 + 32 + 128;                             // [2][DW][Ccap]
+    P* corr = reinterpret_cast<P*>(corr_raw);
+    T* del = reinterpret_cast<T*>(del_raw);
+    P* aold = reinterpret_cast<P*>(aold_raw);
+    P* p_gk = reinterpret_cast<P*>(pscr_raw);
+    P* p_at = reinterpret_cast<P*>(pscr_raw + 32);
+    P* p_scr = reinterpret_cast<P*>(pscr_raw + 64);
+    unsigned char* tiles = smem_raw + BatchSmem<T>::fixed_bytes(Ccap);
+    T* sr = reinterpret_cast<T*>(tiles);
+    T* sw = sr + a.rows_stride;
+    T* pslots = sw + a.rows_stride;                                       // [2][pslot_elems]
+    T* stages = pslots + (size_t)2 * a.pslot_elems;
+
+    const int my_units = a.units_base + (cta < a.units_rem ? 1 : 0);
+    const int64_t unit0 = (int64_t)cta * a.units_base + min(cta, a.units_rem);
+    const int64_t r0 = unit0 * kRowAlign;
+    const int rows = my_units * kRowAlign;
+
+    volatile int* abort_flag = a.abort_flag;
+    volatile int* halt = &ctrl->halt;
+
+    if (tid == 0) {
+        for (int s = 0; s < kMaxStages; ++s) { dev::mbar_init(&full_bar[s], 1); dev::mbar_init(&empty_bar[s], kBatchDW); }
+        for (int s = 0; s < 2; ++s) { dev::mbar_init(&pfull_bar[s], 1); dev::mbar_init(&pempty_bar[s], 1); dev::mbar_init(&gready_bar[s], 1); }
+        for (int s = 0; s < 2 * kBatchMax; ++s) dev::mbar_init(&prox_bar[s], 1);
+        for (int s = 0; s < 2; ++s) dev::mbar_init(&dbar[s], kBatchDW);
+        dev::fence_barrier_init();
+        ctrl->sw_seq = 0; ctrl->prox_done = 0; ctrl->gready = 0; ctrl->halt = 0; ctrl->error = 0;
+    }
+    for (int i = tid; i < 4 * Ccap; i += blockDim.x) corr_raw[i] = 0.0;        // corr + (unused tail): both slots start at zero
+    T* my_beta = a.beta_rep + (size_t)cta * a.beta_stride;
+    int8_t* my_active = a.is_active_rep + (size_t)cta * a.act_stride;
+    for (int i = tid; i < a.beta_len; i += blockDim.x) my_beta[i] = a.beta_in[i];
+    for (int i = tid; i < a.S; i += blockDim.x) my_active[i] = a.is_active_in[i];
+    // resident r / w tiles
+    {
+        T* gr = a.resid + r0; const T* gw = a.weights + r0;
+        for (int v = tid; v < rows / VN; v += blockDim.x) {
+            T t[VN];
+            vec_load<T>(gr + (size_t)v * VN, t); vec_store<T>(sr + (size_t)v * VN, t);
+            vec_load<T>(gw + (size_t)v * VN, t); vec_store<T>(sw + (size_t)v * VN, t);
+        }
+    }
+    const uint32_t epoch0 = dev::ld_cg(a.epoch);
+    __syncthreads();
+
+    const int role_cw = (warp == 0), role_prod = (warp == 4), role_ew = (warp == 8 || warp == 12);
+
+    // =====================================================================================================
+    // TMA producer
+    // =====================================================================================================
+    if (role_prod) {
+        uint32_t gitem = 0, pitem = 0;
+        int sweep = 0;
+        bool running = true;
+        const uint64_t pol_keep = dev::policy_evict_last();
+        while (running) {
+            if (!dev::wait_counter(&ctrl->sw_seq, sweep + 1, abort_flag, halt)) break;
+            const int kind = ctrl->sw_kind[sweep & 3], count = ctrl->sw_count[sweep & 3];
+            if (kind == kSweepExit) break;
+            const T* panels = (kind == kSweepActive) ? a.panels_active : a.panels_screen;
+            const int nb = (count + B - 1) / B;
+            for (int b = 0; b < nb && running; ++b) {
+                const int p0 = b * B, nbg = min(B, count - p0);
+                // ---- column tiles of the batch
+                for (int k = 0; k < nbg; ++k, ++gitem) {
+                    const int stage = gitem % a.n_stages;
+                    const uint32_t use = gitem / a.n_stages;
+                    if (!dev::mbar_wait(&empty_bar[stage], (use & 1) ^ 1, abort_flag, halt)) { running = false; break; }
+                    const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + k) : p0 + k;
+                    const GroupMeta m = a.meta[ss];
+                    T* xs = stages + (size_t)stage * a.stage_elems;
+                    const uint32_t col_bytes = (uint32_t)rows * sizeof(T);
+                    if (lane == 0) dev::mbar_arrive_expect_tx(&full_bar[stage], col_bytes * m.gs);
+                    __syncwarp();
+                    for (int c = lane; c < m.gs; c += 32)
+                        dev::tma_bulk_g2s_hint(xs + (size_t)c * a.rows_stride, a.X + (int64_t)(m.col + c) * a.ld + r0, col_bytes, &full_bar[stage], pol_keep);
+                }
+                if (!running) break;
+                // ---- panel + records of the batch
+                {
+                    const int slot = pitem & 1;
+                    const uint32_t use = pitem >> 1;
+                    if (!dev::mbar_wait(&pempty_bar[slot], (use & 1) ^ 1, abort_flag, halt)) { running = false; break; }
+                    T* ps_ = pslots + (size_t)slot * a.pslot_elems;
+                    const uint32_t q_bytes = (uint32_t)(Ccap * ldq) * sizeof(T);
+                    int rec_elems = 0; int64_t rec_off = 0;
+                    if (lane < nbg) {
+                        const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane;
+                        rec_elems = a.meta[ss].rec_elems; rec_off = a.meta[ss].rec_off;
+                    }
+                    uint32_t tot = (uint32_t)rec_elems * sizeof(T);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                    if (lane == 0) dev::mbar_arrive_expect_tx(&pfull_bar[slot], q_bytes + tot);
+                    __syncwarp();
+                    if (lane == 0) dev::tma_bulk_g2s(ps_, panels + (int64_t)b * Ccap * ldq, q_bytes, &pfull_bar[slot]);
+                    if (lane < nbg) dev::tma_bulk_g2s(ps_ + Ccap * ldq + lane * a.rec_stride, a.grec + rec_off, (uint32_t)rec_elems * sizeof(T), &pfull_bar[slot]);
+                    ++pitem;
+                }
+            }
+            ++sweep;
+        }
+        // never leave while bulk copies into this CTA's shared memory may still be in flight
+        for (uint32_t g = (gitem > (uint32_t)a.n_stages ? gitem - a.n_stages : 0); g < gitem; ++g)
+            dev::mbar_wait(&full_bar[g % a.n_stages], (g / a.n_stages) & 1, abort_flag, nullptr);
+        for (uint32_t g = (pitem > 2 ? pitem - 2 : 0); g < pitem; ++g)
+            dev::mbar_wait(&pfull_bar[g & 1], (g >> 1) & 1, abort_flag, nullptr);
+        return;
+    }
+
+    // exchange geometry: level-1 groups of `fan` consecutive CTAs led by their first member
+    const int fan = a.fan;
+    const int my_group = cta / fan, n_groups = (ncta + fan - 1) / fan;
+    const int grp_first = my_group * fan, grp_size = min(fan, ncta - grp_first);
+    const bool is_leader = (cta == grp_first);
+
+    // =====================================================================================================
+    // exchange warps: two-level all-reduce of the batch's partial gradients.
+    // Buffers are 4-deep in the batch epoch.  Why 4: a CTA publishes its level-1 lines of batch b+1 BEFORE it has read the
+    // level-2 lines of batch b (look-ahead), but it cannot publish batch b+2 before (its U(b) needs its own prox(b)).  A
+    // leader can therefore overwrite level-2 slot (b mod 4) with batch b+4 only after every CTA has published batch b+4's
+    // level-1 lines, i.e. finished prox(b+2), i.e. read the level-2 lines of b+2 of ALL groups, which their leaders publish
+    // only after every member published level-1 of b+2, which each member does only after reading level-2 of batch b.
+    // =====================================================================================================
+    if (role_ew) {
+        const int et = (warp == 8 ? 0 : 32) + lane;
+        int sweep = 0, bcount = 0;
+        bool running = true;
+        while (running) {
+            if (!dev::wait_counter(&ctrl->sw_seq, sweep + 1, abort_flag, halt)) break;
+            const int kind = ctrl->sw_kind[sweep & 3], count = ctrl->sw_count[sweep & 3];
+            if (kind == kSweepExit) break;
+            const int nb = (count + B - 1) / B;
+            for (int b = 0; b < nb; ++b, ++bcount) {
+                const int p0 = b * B, nbg = min(B, count - p0);
+                int gsz = 0;
+                if (lane < nbg) {
+                    const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane;
+                    gsz = a.meta[ss].gs;
+                }
+                int Cb = gsz;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) Cb += __shfl_xor_sync(0xffffffffu, Cb, o);
+                const uint32_t e = epoch0 + (uint32_t)bcount;
+                const int slot = (int)(e & (kBatchLLSlots - 1));
+                bool ok = dev::mbar_wait(&dbar[bcount & 1], (uint32_t)(bcount >> 1) & 1u, abort_flag, halt);
+                if (ok && et < Cb) {
+                    const int c = et;
+                    {
+                        const double* w0 = wpart + (size_t)(bcount & 1) * kBatchDW * Ccap + c;
+                        double s = 0;
+#pragma unroll
+                        for (int w = 0; w < kBatchDW; ++w) s += w0[(size_t)w * Ccap];
+                        dev::ll_store(a.ll1 + ((size_t)(slot * kBatchColsMax + c) * a.ncta_pad + cta), s, e);
+                    }
+                    if (is_leader) {
+                        const dev::LLLine* base = a.ll1 + ((size_t)(slot * kBatchColsMax + c) * a.ncta_pad + grp_first);
+                        double s = 0;
+#pragma unroll 1
+                        for (int m0 = 0; m0 < grp_size && ok; m0 += 8) {          // 8 polls in flight, summed in member order
+                            double v[8]; bool got[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { v[u] = 0; got[u] = (m0 + u >= grp_size); }
+                            dev::SpinGuard guard;
+                            while (ok) {
+                                bool all = true;
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) if (!got[u]) { got[u] = dev::ll_try_load(base + m0 + u, e, v[u]); all &= got[u]; }
+                                if (all) break;
+                                if (guard.give_up(abort_flag, halt)) ok = false;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) if (m0 + u < grp_size) s += v[u];
+                        }
+                        if (ok) dev::ll_store(a.ll2 + ((size_t)(slot * kBatchColsMax + c) * 32 + my_group), s, e);
+                    }
+                    const dev::LLLine* base2 = a.ll2 + ((size_t)(slot * kBatchColsMax + c) * 32);
+                    double s = 0;
+#pragma unroll 1
+                    for (int g0 = 0; g0 < n_groups && ok; g0 += 8) {
+                        double v[8]; bool got[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { v[u] = 0; got[u] = (g0 + u >= n_groups); }
+                        dev::SpinGuard guard;
+                        while (ok) {
+                            bool all = true;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) if (!got[u]) { got[u] = dev::ll_try_load(base2 + g0 + u, e, v[u]); all &= got[u]; }
+                            if (all) break;
+                            if (guard.give_up(abort_flag, halt)) ok = false;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) if (g0 + u < n_groups) s += v[u];
+                    }
+                    gstale[(bcount & 1) * Ccap + c] = s;
+                }
+                if (!ok) ctrl->halt = 1;
+                dev::named_bar_sync(2, 64);
+                if (*halt) { running = false; break; }
+                if (et == 0) dev::mbar_arrive(&gready_bar[bcount & 1]);
+            }
+            ++sweep;
+        }
+        return;
+    }
+
+    // =====================================================================================================
+    // data warps
+    // =====================================================================================================
+    if (!role_cw) {
+        const int dw = (warp >> 2) * 3 + (warp & 3) - 1;         // 0 .. 11
+        const int dt = dw * 32 + lane;                            // 0 .. 383
+        constexpr int CB = 16;
+        uint32_t gitem = 0;
+        int sweep = 0, bcount = 0, ucount = 0;                    // batches whose D phase ran / groups whose U phase ran
+        int ubatch = 0;                                            // batches whose U phase ran (parity of del / changed / prox_bar)
+        bool running = true;
+        const uint64_t pol_done = dev::policy_evict_first();
+        // phase profile (thread 0 of the first data warp of CTA 0): 8 wait-full, 9 dot, 10 barrier+publish, 11 wait-prox, 12 update, 13 sweep wait
+        const bool prof = PROF && (a.stats != nullptr) && cta == 0 && dt == 0;
+        long long pt[6] = {0, 0, 0, 0, 0, 0}; long long tc = prof ? clock64() : 0;
+#define ABB_TICK(k) do { if (PROF && prof) { const long long t_ = clock64(); pt[PROF == 1 ? (((k) == 0 || (k) == 3 || (k) == 5) ? 0 : 1) : (k)] += t_ - tc; tc = t_; } } while (0)
+
+        // D(b): partial gradients of the batch against the current residual tile
+        auto dphase = [&](int kind, int count, int b) -> bool {
+            const int p0 = b * B, nbg = min(B, count - p0);
+            double* wp = wpart + (size_t)(bcount & 1) * kBatchDW * Ccap + (size_t)dw * Ccap;
+            int gs_l = 0;                                          // lane k holds the size of group k (one load round per batch)
+            if (lane < nbg) gs_l = a.meta[(kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane].gs;
+            int off = 0;
+            for (int k = 0; k < nbg; ++k, ++gitem) {
+                const int gs = __shfl_sync(0xffffffffu, gs_l, k);
+                const int stage = (int)(gitem % a.n_stages);
+                const uint32_t use = gitem / a.n_stages;
+                if (!dev::mbar_wait(&full_bar[stage], use & 1, abort_flag, halt)) return false;
+                ABB_TICK(0);
+                const T* xs = stages + (size_t)stage * a.stage_elems;
+                const int64_t cs = a.rows_stride;
+#pragma unroll 1
+                for (int c0 = 0; c0 < gs; c0 += CB) {
+                    T acc[CB];
+#pragma unroll
+                    for (int cc = 0; cc < CB; ++cc) acc[cc] = 0;
+#pragma unroll 1
+                    for (int v = dt; v < rows / VN; v += kBatchNDT) {
+                        T rv[VN], wv[VN], wr[VN];
+                        vec_load<T>(sr + (size_t)v * VN, rv);
+                        vec_load<T>(sw + (size_t)v * VN, wv);
+#pragma unroll
+                        for (int q = 0; q < VN; ++q) wr[q] = wv[q] * rv[q];
+#pragma unroll
+                        for (int cc = 0; cc < CB; ++cc) {
+                            if (c0 + cc < gs) {
+                                T xv[VN];
+                                vec_load<T>(xs + (int64_t)(c0 + cc) * cs + (size_t)v * VN, xv);
+#pragma unroll
+                                for (int q = 0; q < VN; ++q) acc[cc] += xv[q] * wr[q];
+                            }
+                        }
+                    }
+                    const T tot = warp_reduce16<T>(acc, lane);
+                    const int col = c0 + ((lane >> 1) & 15);
+                    if ((lane & 1) == 0 && col < gs) wp[off + col] = (double)tot;
+                }
+                __syncwarp();
+                if (lane == 0) dev::mbar_arrive(&empty_bar[stage]);
+                off += gs;
+                ABB_TICK(1);
+            }
+            __syncwarp();
+            if (lane == 0) dev::mbar_arrive(&dbar[bcount & 1]);       // release: the exchange warps sum the partials and publish
+            ++bcount;
+            ABB_TICK(2);
+            return true;
+        };
+        // U(b): r += X_k del_k for the groups of the batch that moved; X comes from L2 (streamed one batch earlier)
+        auto uphase = [&](int kind, int count, int b, int upar) -> bool {
+            const int p0 = b * B, nbg = min(B, count - p0);
+            int gs_l = 0, col_l = 0;
+            if (lane < nbg) {
+                const GroupMeta mm = a.meta[(kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane];
+                gs_l = mm.gs; col_l = mm.col;
+            }
+            constexpr int CBU = 12;
+            int off = 0;
+            for (int k = 0; k < nbg; ++k, ++ucount) {
+                struct { int gs, col; } m{__shfl_sync(0xffffffffu, gs_l, k), __shfl_sync(0xffffffffu, col_l, k)};
+                if (!dev::mbar_wait(&prox_bar[upar * kBatchMax + k], (uint32_t)(ubatch >> 1) & 1u, abort_flag, halt)) return false;
+                ABB_TICK(3);
+                if (ctrl->changed[upar][k]) {
+                    const T* dl = del + (size_t)upar * Ccap + off;
+                    const T* xg = a.X + (int64_t)m.col * a.ld + r0;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < m.gs; c0 += CBU) {
+                        T d[CBU];
+#pragma unroll
+                        for (int cc = 0; cc < CBU; ++cc) d[cc] = (c0 + cc < m.gs) ? dl[c0 + cc] : T(0);
+#pragma unroll 1
+                        for (int v = dt; v < rows / VN; v += kBatchNDT) {
+                            T xv[CBU][VN];
+#pragma unroll
+                            for (int cc = 0; cc < CBU; ++cc) {
+                                if (c0 + cc < m.gs) dev::ld_hint(xg + (int64_t)(c0 + cc) * a.ld + (size_t)v * VN, xv[cc], pol_done);
+                            }
+                            T rv[VN];
+                            vec_load<T>(sr + (size_t)v * VN, rv);
+#pragma unroll
+                            for (int cc = 0; cc < CBU; ++cc) {
+                                if (c0 + cc < m.gs) {
+#pragma unroll
+                                    for (int q = 0; q < VN; ++q) rv[q] += xv[cc][q] * d[cc];
+                                }
+                            }
+                            vec_store<T>(sr + (size_t)v * VN, rv);
+                        }
+                    }
+                }
+                off += m.gs;
+                ABB_TICK(4);
+            }
+            return true;
+        };
+
+        while (running) {
+            if (!dev::wait_counter(&ctrl->sw_seq, sweep + 1, abort_flag, halt)) { running = false; break; }
+            ABB_TICK(5);
+            const int kind = ctrl->sw_kind[sweep & 3], count = ctrl->sw_count[sweep & 3];
+            if (kind == kSweepExit) break;
+            const int nb = (count + B - 1) / B;
+#pragma unroll 1
+            for (int b = -1; b < nb; ++b) {                        // rotated: D(b+1) then U(b), one call site each
+                if (b + 1 < nb && !dphase(kind, count, b + 1)) { running = false; break; }
+                if (b >= 0) {
+                    if (!uphase(kind, count, b, ubatch & 1)) { running = false; break; }
+                    ++ubatch;
+                }
+            }
+            ++sweep;
+        }
+        if (PROF && prof) for (int k = 0; k < 6; ++k) a.stats[8 + k] += pt[k];
+#undef ABB_TICK
+        // write the residual tile back (thread-private rows: no barrier needed; on errors the host discards it)
+        {
+            T* gr = a.resid + r0;
+            for (int v = dt; v < rows / VN; v += kBatchNDT) {
+                T t[VN];
+                vec_load<T>(sr + (size_t)v * VN, t); vec_store<T>(gr + (size_t)v * VN, t);
+            }
+        }
+        return;
+    }
+
+    // =====================================================================================================
+    // control warp
+    // =====================================================================================================
+    {
+        const P l1 = (P)(a.lmda * a.alpha), l2 = (P)(a.lmda * (1.0 - a.alpha));
+        ProxState ps;
+        ps.rsq = a.sc->rsq; ps.resid_sum = a.sc->resid_sum; ps.cm = 0; ps.A = a.sc->active_set_size; ps.error = 0; ps.newton_iters_max = 0;
+        long long iters = a.sc->iters, n_updates = a.sc->n_group_updates, n_cols = a.sc->n_col_updates;
+        int phase = a.start_phase;
+        int sweep = 0, bcount = 0, gcount = 0, pitem = 0;
+        int final_error = 0, status = kBatchDone;
+        const bool prof = PROF && (a.stats != nullptr) && cta == 0 && lane == 0;
+        long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tc = prof ? clock64() : 0;
+        long long ppx[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // prox sub-phases: 0 pre, 1 gradient rotate, 2 root find, 3 sums, 4 rotate back, 5 newton iterations, 6 unchanged
+#define ABB_TICK(k) do { if (PROF == 2 || (PROF == 1 && (k) != 2)) { if (prof) { const long long t_ = clock64(); pt[PROF == 1 ? (((k) == 0 || (k) == 1) ? 0 : 1) : (k)] += t_ - tc; tc = t_; } } } while (0)
+
+        // issues the loads of a batch's metas: lane k < nbg holds group k (consumed later: no stall here)
+        auto load_batch = [&](int kind, int count, int b, GroupMeta& m, int& ss) {
+            const int p0 = b * B, nbg = max(0, min(B, count - p0));
+            m = GroupMeta{}; ss = 0;
+            if (lane < nbg) {
+                ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane;
+                m = a.meta[ss];
+                // screen sweeps: fold "already active" into the sign of ss (a group's flag only changes when it is itself processed)
+                if (kind == kSweepScreen && my_active[ss]) ss = -ss - 1;
+            }
+        };
+        auto batch_cols = [&](const GroupMeta& m) -> int {
+            int C = m.gs;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) C += __shfl_xor_sync(0xffffffffu, C, o);
+            return C;
+        };
+        // issues the loads of a batch's current coefficients into registers: column t = lane + 32 j  ->  pa[j]
+        auto fetch_aold = [&](const GroupMeta& m, int nbg, P (&pa)[2]) {
+            int adr[2] = {-1, -1};
+            int off = 0;
+            for (int k = 0; k < nbg; ++k) {
+                const int gs = __shfl_sync(0xffffffffu, m.gs, k), begin = __shfl_sync(0xffffffffu, m.begin, k);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) { const int t = lane + 32 * j; if (t >= off && t < off + gs) adr[j] = begin + t - off; }
+                off += gs;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) pa[j] = (adr[j] >= 0) ? (P)my_beta[adr[j]] : P(0);
+        };
+        auto store_aold = [&](const P (&pa)[2], int par) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { const int t = lane + 32 * j; if (t < Ccap) aold[par * Ccap + t] = pa[j]; }
+        };
+
+        while (true) {
+            const int count = (phase == kSweepActive) ? ps.A : a.S;
+            ABB_TICK(5);
+            if (lane == 0) {
+                ctrl->sw_kind[sweep & 3] = phase; ctrl->sw_count[sweep & 3] = count;
+                dev::st_release_cta(&ctrl->sw_seq, sweep + 1);
+            }
+            ++iters;
+            ps.cm = 0;
+            const int kind = phase;
+            const int nb = (count + B - 1) / B;
+            GroupMeta m_cur, m_nxt, m_nn; int ss_cur = 0, ss_nxt = 0, ss_nn = 0;
+            double gc[2] = {0, 0}; P cn[2] = {0, 0};        // gradient of the current batch / cross corrections for the next (columns lane, lane + 32)
+            int C_cur = 0, C_nxt = 0;
+            if (nb > 0) {
+                load_batch(kind, count, 0, m_cur, ss_cur);
+                load_batch(kind, count, 1, m_nxt, ss_nxt);
+                C_cur = batch_cols(m_cur); C_nxt = batch_cols(m_nxt);
+                P pa[2];
+                fetch_aold(m_cur, min(B, count), pa);
+                store_aold(pa, bcount & 1);
+                __syncwarp();
+            }
+            for (int b = 0; b < nb; ++b, ++bcount, ++pitem) {
+                const int par = bcount & 1;
+                const int nbg = min(B, count - b * B);
+                load_batch(kind, count, b + 2, m_nn, ss_nn);                      // in flight during this batch
+                P pa_nxt[2];
+                fetch_aold(m_nxt, max(0, min(B, count - (b + 1) * B)), pa_nxt);   // in flight during this batch (disjoint groups)
+                const int pslot = pitem & 1;
+                const T* Q = pslots + (size_t)pslot * a.pslot_elems;
+                ABB_TICK(4);
+                if (!dev::mbar_wait(&pfull_bar[pslot], (pitem >> 1) & 1, abort_flag, halt)) { final_error = kErrAbort; break; }
+                ABB_TICK(0);
+                if (!dev::mbar_wait(&gready_bar[par], (uint32_t)(bcount >> 1) & 1u, abort_flag, halt)) { final_error = kErrAbort; break; }
+                ABB_TICK(1);
+                if (PROF && prof) ++pt[7];
+                __syncwarp();
+                // the batch's all-reduced gradient (+ the cross corrections collected during the previous batch) moves into
+                // registers: lane l holds columns l and l + 32
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int t = lane + 32 * j;
+                    gc[j] = (t < C_cur) ? gstale[par * Ccap + t] + (double)cn[j] : 0.0;
+                    cn[j] = 0;
+                }
+                int gs_max_b = m_cur.gs;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) gs_max_b = max(gs_max_b, __shfl_xor_sync(0xffffffffu, gs_max_b, o));
+
+                auto run_batch = [&](auto gsp_tag) {
+                    constexpr int GSP = decltype(gsp_tag)::value;           // GSP == 32: generic shared-memory prox (12 < gs <= 32)
+                    constexpr int GL = (GSP <= 16) ? GSP : 2;
+                    LanePre<P, GL> pre;
+                    int off = 0, gs = 0;
+                    // rotated loop (k = -1 only issues the static loads of group 0): one call site per phase
+#pragma unroll 1
+                    for (int k = -1; k < nbg; ++k) {
+                        int changed = 0, ss = 0; bool was_active = false;
+                        T* dl = del + (size_t)par * Ccap + off;
+                        if (k >= 0) {
+                            gs = __shfl_sync(0xffffffffu, m_cur.gs, k);
+                            const int begin = __shfl_sync(0xffffffffu, m_cur.begin, k);
+                            const int ss_enc = __shfl_sync(0xffffffffu, ss_cur, k);
+                            ss = ss_enc < 0 ? -ss_enc - 1 : ss_enc;
+                            was_active = ss_enc < 0;
+                            const P pk = (P)__shfl_sync(0xffffffffu, m_cur.pen, k);
+                            const T* rec = Q + Ccap * ldq + k * a.rec_stride;
+                            P* ao = aold + par * Ccap + off;
+                            const int idx = off + (lane < gs ? lane : 0);
+                            const double g0 = __shfl_sync(0xffffffffu, gc[0], idx & 31), g1 = __shfl_sync(0xffffffffu, gc[1], idx & 31);
+                            const double g_in = (idx >> 5) ? g1 : g0;
+                            if (gs == 1) {                                       // solver_gaussian_pin_naive.hpp:75-108
+                                const P ak_old = ao[0];
+                                const P A_kk = (P)rec[0], xm = (P)rec[1];
+                                P gk = (P)__shfl_sync(0xffffffffu, g_in, 0) - xm * (P)ps.resid_sum * (P)a.intercept + ak_old * A_kk;
+                                const P vv = fabs(gk) - l1 * pk;                 // update_coordinate, pin_base.hpp:181-195
+                                P ak = (vv > P(0)) ? copysign(vv, gk) / (A_kk + l2 * pk) : P(0);
+                                ak = (P)(T)ak;
+                                gk -= ak_old * A_kk;
+                                if (ak != ak_old) {
+                                    const P dd = ak - ak_old;
+                                    ps.cm = fmax(ps.cm, (double)(A_kk * dd * dd));
+                                    ps.rsq += (double)(dd * (2 * gk - dd * A_kk));
+                                    ps.resid_sum -= (double)(xm * dd);
+                                    if (lane == 0) { my_beta[begin] = (T)ak; dl[0] = (T)(-dd); }
+                                    changed = 1;
+                                }
+                            } else if (GSP <= 16) {
+                                changed = prox_post<T, P, GL>(pre, gs, g_in, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters, (P)a.dbeta_tol,
+                                                              a.intercept, ps, lane, p_gk, my_beta + begin, dl, (PROF == 2 && prof) ? ppx : nullptr);
+                            } else {                                             // 12 < gs <= 32: shared-memory reductions
+                                if (lane < gs) gcur[lane] = g_in;
+                                __syncwarp();
+                                const ProxCtx<T, P> px{ao, nullptr, p_gk, nullptr, nullptr, p_at, p_scr, dl, gcur, my_beta};
+                                const ProxPre<P> pre2 = prox_small_pre<T, P>(rec, gs, ao, lane);
+                                changed = prox_small_post<T, P>(px, pre2, rec, gs, begin, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters,
+                                                                (P)a.dbeta_tol, a.intercept, ps, lane, nullptr);
+                            }
+                            __syncwarp();
+                            if (lane == 0) {
+                                ctrl->changed[par][k] = changed;
+                                dev::mbar_arrive(&prox_bar[par * kBatchMax + k]); // release: del / changed are visible to the data warps
+                            }
+                            ABB_TICK(2);
+                            if (PROF && prof) ++pt[6];
+                        }
+                        // static loads of the next group, issued behind this group's corrections
+                        if (GSP <= 16 && k + 1 < nbg) {
+                            const int gs1 = __shfl_sync(0xffffffffu, m_cur.gs, k + 1);
+                            if (gs1 > 1) prox_pre<T, P, GL>(pre, Q + Ccap * ldq + (k + 1) * a.rec_stride, gs1, aold + par * Ccap + off + gs, lane);
+                        }
+                        if (changed) {
+                            if (GSP <= 16) apply_corrections<T, P, GL>(Q, ldq, Ccap, off, gs, dl, C_cur, C_nxt, gc, cn, lane);
+                            else apply_corrections<T, P, 0>(Q, ldq, Ccap, off, gs, dl, C_cur, C_nxt, gc, cn, lane);
+                            if (kind == kSweepScreen && !was_active) {           // add_active_set (:294-304)
+                                if (ps.A >= a.max_active_size) ps.error = kErrMaxActive;
+                                else {
+                                    if (lane == 0) { my_active[ss] = 1; a.active_set[ps.A] = ss; }
+                                    ++ps.A;
+                                }
+                            }
+                        }
+                        if (k >= 0) { ++n_updates; n_cols += gs; ++gcount; }
+                        off += gs;
+                        ABB_TICK(3);
+                        if (ps.error) break;
+                    }
+                };
+                // (one lane-local instantiation only: several of them blow the register budget of the whole kernel)
+                if (gs_max_b <= 12) run_batch(std::integral_constant<int, 12>{});
+                else run_batch(std::integral_constant<int, 32>{});
+                if (ps.error) { final_error = ps.error; break; }
+                if (lane >= nbg && lane < kBatchMax) dev::mbar_arrive(&prox_bar[par * kBatchMax + lane]);   // keep every barrier at one phase per batch
+                __syncwarp();
+                if (lane == 0) dev::mbar_arrive(&pempty_bar[pslot]);
+                store_aold(pa_nxt, par ^ 1);
+                m_cur = m_nxt; ss_cur = ss_nxt; C_cur = C_nxt;
+                m_nxt = m_nn; ss_nxt = ss_nn; C_nxt = batch_cols(m_nxt);
+                __syncwarp();
+            }
+            if (final_error) break;
+            ABB_TICK(4);
+            // ---- end of sweep (identical decision in every CTA)
+            const bool conv = ps.cm < a.tol;
+            int next;
+            if (kind == kSweepActive) next = conv ? kSweepScreen : ((iters >= a.max_iters) ? -kErrMaxCds : kSweepActive);
+            else if (conv) next = kSweepExit;
+            else if (iters >= a.max_iters) next = -kErrMaxCds;
+            else if (ps.A > a.n_active_panelled) { next = kSweepExit; status = kBatchNeedPanels; }
+            else next = kSweepActive;
+            ++sweep;
+            if (next < 0) { final_error = -next; break; }
+            if (next == kSweepExit) break;
+            phase = next;
+        }
+        if (final_error) {
+            if (lane == 0) { ctrl->error = final_error; ctrl->halt = 1; }
+            if (final_error == kErrAbort && lane == 0) *abort_flag = 1;
+        } else if (lane == 0) {
+            ctrl->sw_kind[sweep & 3] = kSweepExit; ctrl->sw_count[sweep & 3] = 0;
+            dev::st_release_cta(&ctrl->sw_seq, sweep + 1);
+        }
+        if (cta == 0 && lane == 0) {
+            a.sc->rsq = ps.rsq; a.sc->resid_sum = ps.resid_sum; a.sc->active_set_size = ps.A;
+            a.sc->iters = iters; a.sc->n_group_updates = n_updates; a.sc->n_col_updates = n_cols; a.sc->error = final_error;
+            a.sc->newton_iters_max = ps.newton_iters_max; a.sc->pad = status;
+            if (PROF && prof) for (int k = 0; k < 8; ++k) { a.stats[k] += pt[k]; if (PROF == 2) a.stats[16 + k] += ppx[k]; }
+#undef ABB_TICK
+            *a.epoch = epoch0 + (uint32_t)bcount + 8u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gram panels.  One item = one (source group, target group) block:
+//   out[a * ldq + b] = sum_i w_i X[i, col_s + a] X[i, col_t + b],   a < gs_s, b < gs_t
+// grid = (n_items, n_row_blocks); two-phase deterministic reduction through `part`.
+struct PairItem { int32_t col_s, gs_s, col_t, gs_t; int64_t out_off; int64_t part_off; };
+
+template <class T>
+__global__ void __launch_bounds__(256)
+pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairItem* __restrict__ items, const T* __restrict__ w,
+                 double* __restrict__ part, int64_t total, int rows_per_block)
+{
+    constexpr int VN = VecT<T>::N;
+    __shared__ double s_red[8][17];
+    const PairItem it = items[blockIdx.x];
+    const int rb = blockIdx.y;
+    const int64_t row0 = (int64_t)rb * rows_per_block;
+    const int64_t row1 = min((long long)n_pad, (long long)(row0 + rows_per_block));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const T* Xs = X + (int64_t)it.col_s * ld;
+    const T* Xt = X + (int64_t)it.col_t * ld;
+    double* out = part + (size_t)rb * total + it.part_off;
+    for (int a0 = 0; a0 < it.gs_s; a0 += 4) {
+        for (int b0 = 0; b0 < it.gs_t; b0 += 4) {
+            T acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = 0;
+            for (int64_t i = row0 + (int64_t)tid * VN; i < row1; i += 256 * VN) {
+                T wv[VN], xa[4][VN], xb[4][VN];
+                vec_load<T>(w + i, wv);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                    if (a0 + x < it.gs_s) {
+                        vec_load<T>(Xs + (int64_t)(a0 + x) * ld + i, xa[x]);
+#pragma unroll
+                        for (int q = 0; q < VN; ++q) xa[x][q] *= wv[q];
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < VN; ++q) xa[x][q] = 0;
+                    }
+                }
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    if (b0 + y < it.gs_t) vec_load<T>(Xt + (int64_t)(b0 + y) * ld + i, xb[y]);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < VN; ++q) xb[y][q] = 0;
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+#pragma unroll
+                        for (int q = 0; q < VN; ++q) acc[x][y] += xa[x][q] * xb[y][q];
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) {
+                    const double s = dev::warp_sum((double)acc[x][y]);
+                    if (lane == 0) s_red[warp][x * 4 + y] = s;
+                }
+            __syncthreads();
+            if (tid < 16) {
+                double s = 0;
+                for (int wi = 0; wi < 8; ++wi) s += s_red[wi][tid];
+                const int aa = a0 + tid / 4, bb = b0 + tid % 4;
+                if (aa < it.gs_s && bb < it.gs_t) out[aa * it.gs_t + bb] = s;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <class T>
+__global__ void pair_gram_finalize_kernel(const PairItem* __restrict__ items, const double* __restrict__ part, int n_rb, int64_t total,
+                                          T* __restrict__ Q, int ldq)
+{
+    const PairItem it = items[blockIdx.x];
+    for (int e = threadIdx.x; e < it.gs_s * it.gs_t; e += blockDim.x) {
+        double s = 0;
+        for (int rb = 0; rb < n_rb; ++rb) s += part[(size_t)rb * total + it.part_off + e];
+        Q[it.out_off + (int64_t)(e / it.gs_t) * ldq + (e % it.gs_t)] = (T)s;
+    }
+}
+
+} // namespace ab

@@ -26,7 +26,7 @@ _VEC_F = ["lmda_path", "screen_beta", "grad", "abs_grad", "devs", "lmdas", "X_me
 _VEC_I = ["screen_set", "screen_begins", "screen_is_active", "active_set", "n_valid_solutions", "active_sizes", "screen_sizes"]
 _SCALARS = ["lmda_max", "lmda", "rsq", "resid_sum", "y_mean", "y_var", "loss_null", "loss_full", "beta0", "active_set_size",
             "n_sweeps", "n_group_updates", "n_col_updates", "n_irls", "n_pin_solves", "n_kernel_launches", "time_sweep_kernel", "sweep_ncta",
-            "sweep_stages", "sweep_smem_bytes", "sweep_staged", "sweep_threads"]
+            "sweep_stages", "sweep_smem_bytes", "sweep_staged", "sweep_threads", "sweep_batch", "n_panels_built", "n_batched_launches"]
 
 
 def _render_inputs(*, groups, lmda_max, lmda_path, lmda_path_size, max_screen_size, max_active_size, dtype):
@@ -102,7 +102,7 @@ class base:
             v = self._scalar(name)
             return int(v) if name in ("active_set_size", "n_sweeps", "n_group_updates", "n_col_updates", "n_irls", "n_pin_solves",
                                       "n_kernel_launches", "sweep_ncta", "sweep_stages", "sweep_smem_bytes",
-                                      "sweep_staged", "sweep_threads") else self._dtype(v) if name not in ("time_sweep_kernel",) else v
+                                      "sweep_staged", "sweep_threads", "sweep_batch", "n_panels_built", "n_batched_launches") else self._dtype(v) if name not in ("time_sweep_kernel",) else v
         if name.startswith("t_"):
             return self._scalar(name)
         if name in _VEC_F:

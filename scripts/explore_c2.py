@@ -20,6 +20,7 @@ print("eta", time.time() - t)
 y = (eta + np.linalg.norm(beta) * rng.normal(size=n)).astype(dtype)
 groups = np.arange(0, p, gs)
 ad.set_configs("sweep_profile", int(os.environ.get("PROF", 0)))
+ad.set_configs("sweep_batch", int(os.environ.get("BATCH", 0)))
 for rep in range(2):
     t = time.time()
     st = ad.grpnet(X, ad.glm.gaussian(y, dtype=dtype), groups=groups, early_exit=False, lmda_path_size=L, progress_bar=False)
@@ -31,17 +32,31 @@ for rep in range(2):
     bytes_per_update = 4.0 * n * gs
     print(f"  sweep kernel: {st.n_group_updates / st.time_sweep_kernel:.0f} group-updates/s, "
           f"{st.n_group_updates * bytes_per_update / st.time_sweep_kernel / 1e9:.0f} GB/s algorithmic")
-    if int(os.environ.get("PROF", 0)):
+    print(f"  batch={st.sweep_batch} batched_launches={st.n_batched_launches} panels_built={st.n_panels_built} t_panels={st.t_panels:.3f}")
+    if int(os.environ.get("PROF", 0)) == 1 and st.sweep_batch > 1:
+        stt = st.sweep_stats.astype(np.float64)
+        groups_ = max(stt[6], 1)
+        print(f"  light profile (cycles/group, CTA0): CW stall={stt[0]/groups_:.0f} busy={stt[1]/groups_:.0f} | DW stall={stt[8]/groups_:.0f} busy={stt[9]/groups_:.0f} groups={groups_:.0f}")
+    elif int(os.environ.get("PROF", 0)) and st.sweep_batch > 1:
+        stt = st.sweep_stats.astype(np.float64)
+        groups_, batches_ = max(stt[6], 1), max(stt[7], 1)
+        cw = ["wait_panel", "wait_gready", "prox", "corr+book", "batch_ovh", "sweep_bdry"]
+        dw = ["wait_full", "dot", "bar+publish", "wait_prox", "update", "sweep_wait"]
+        print(f"  CW cycles/group (CTA0, cumulative): " + " ".join(f"{nm}={stt[i]/groups_:.0f}" for i, nm in enumerate(cw)) + f" groups={groups_:.0f} batches={batches_:.0f}")
+        px = ["pre", "grad_rot", "rootfind", "sums", "rot_back", "newton_its", "unchanged"]
+        print(f"  prox cycles/group: " + " ".join(f"{nm}={stt[16+i]/groups_:.2f}" for i, nm in enumerate(px)))
+        print(f"  DW cycles/group (CTA0, cumulative): " + " ".join(f"{nm}={stt[8+i]/groups_:.0f}" for i, nm in enumerate(dw)))
+    elif int(os.environ.get("PROF", 0)):
         stt = st.sweep_stats.astype(np.float64)
         names = ["wait_full", "dot", "bar1+store", "poll", "prox", "bar3", "update"]
         items = max(stt[8], 1)
         print("  cycles/item (cumulative over reps): " + " ".join(f"{nm}={stt[i]/items:.0f}" for i, nm in enumerate(names)) + f" newton_it/item={stt[7]/items:.2f} poll_retries/item={stt[9]/items:.1f} items={items:.0f}")
-    if int(os.environ.get("PROF", 0)) and rep == 1:
+    if int(os.environ.get("PROF", 0)) and rep == 1 and st.sweep_batch <= 1:
         tr = st.sweep_stats.astype(np.float64)[32:32 + 8 * 148].reshape(148, 8)
         t0 = tr[:, 0].min()
         names = ["dot_done", "ll_stored", "poll_done", "bar2_passed", "prox_done", "update_done"]
         for k, nm in enumerate(names):
             v = tr[:, k] - t0
             print(f"    trace {nm:12s}: min {v.min():8.0f} ns  median {np.median(v):8.0f}  max {v.max():8.0f}  (argmax cta {int(v.argmax())})")
-    print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["screen_records", "cov_device", "run_pin", "invariance", "screen_host", "abs_grad", "update_solutions"]))
+    print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["panels", "screen_records", "cov_device", "run_pin", "invariance", "screen_host", "abs_grad", "update_solutions"]))
     print("  phases: screen %.3f fit %.3f inv %.3f kkt %.3f" % (sum(st.benchmark_screen), sum(st.benchmark_fit_active), sum(st.benchmark_invariance), sum(st.benchmark_kkt)))
