@@ -49,41 +49,74 @@ struct Configs {
     static inline int sweep_min_rows_per_cta = 1024;
     static inline int sweep_force_direct = 0;  // 1 = never stage X tiles in shared memory (debug / fallback path)
     static inline int sweep_profile = 0;       // 1 = accumulate per-phase cycle counters in the fused sweep kernel
-    static inline int sweep_batch = 0;         // groups per batch of the look-ahead sweep kernel: 0 = auto (4), 1 = off (per-group kernel)
+    static inline int sweep_batch = 0;         // groups per batch of the look-ahead sweep kernel: 0 = auto (up to 6), 1 = off (per-group kernel)
     static inline int device_eigh = 1;         // batched Jacobi on device (0 = host Jacobi)
 };
 
 constexpr int kRowAlign = 32;     // rows of every device vector / matrix column are padded to this many elements
 inline int64_t pad_rows(int64_t n) { return (n + kRowAlign - 1) / kRowAlign * kRowAlign; }
 
+// Device allocations below this size come from the device's stream-ordered memory pool (cudaMallocAsync on the default
+// stream, pool configured to retain freed memory): a path solve creates and drops dozens of small buffers per state, and
+// cudaMalloc / cudaFree (a device-wide synchronisation each) used to cost ~0.25 s per state.  Large buffers (the design matrix)
+// keep plain cudaMalloc so that the pool never sits on tens of GB after the matrix is released.
+constexpr size_t kPoolAllocMaxBytes = (size_t)256 << 20;
+
+inline void configure_mem_pool_once() {
+    static thread_local int configured_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == configured_dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    configured_dev = dev;
+}
+
+inline cudaError_t dev_malloc(void** q, size_t bytes, bool& pooled) {
+    pooled = bytes <= kPoolAllocMaxBytes;
+    if (pooled) {
+        configure_mem_pool_once();
+        cudaError_t e = cudaMallocAsync(q, bytes, 0);
+        if (e == cudaSuccess) return e;
+        (void)cudaGetLastError();
+        pooled = false;
+    }
+    return cudaMalloc(q, bytes);
+}
+inline void dev_free(void* q, bool pooled) {
+    if (!q) return;
+    if (pooled) cudaFreeAsync(q, 0); else cudaFree(q);
+}
+
 // Owning device buffer (zero-initialised).
 template <class T>
 struct DevBuf {
-    T* p = nullptr; size_t n = 0;
+    T* p = nullptr; size_t n = 0; bool pooled = false;
     DevBuf() = default;
     explicit DevBuf(size_t n_) { alloc(n_); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), pooled(o.pooled) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { free(); p = o.p; n = o.n; pooled = o.pooled; o.p = nullptr; o.n = 0; } return *this; }
     ~DevBuf() { free(); }
-    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void free() { dev_free(p, pooled); p = nullptr; n = 0; }
     void alloc(size_t n_) {
         free();
         n = n_;
-        if (n) { AB_CUDA(cudaMalloc(&p, n * sizeof(T))); AB_CUDA(cudaMemset(p, 0, n * sizeof(T))); }
+        if (n) { AB_CUDA(dev_malloc((void**)&p, n * sizeof(T), pooled)); AB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), 0)); }
     }
     // grow keeping contents (new tail zeroed)
     void reserve_keep(size_t n_, cudaStream_t st = 0) {
         if (n_ <= n) return;
         size_t cap = std::max(n_, n * 2 + 64);
-        T* q = nullptr;
-        AB_CUDA(cudaMalloc(&q, cap * sizeof(T)));
-        AB_CUDA(cudaMemsetAsync(q, 0, cap * sizeof(T), st));
+        T* q = nullptr; bool qp = false;
+        AB_CUDA(dev_malloc((void**)&q, cap * sizeof(T), qp));
         if (p && n) AB_CUDA(cudaMemcpyAsync(q, p, n * sizeof(T), cudaMemcpyDeviceToDevice, st));
-        AB_CUDA(cudaStreamSynchronize(st));
-        if (p) cudaFree(p);
-        p = q; n = cap;
+        AB_CUDA(cudaMemsetAsync(q + n, 0, (cap - n) * sizeof(T), st));
+        dev_free(p, pooled);                 // stream ordered (pool) or synchronising (cudaFree): safe after the copy either way
+        p = q; n = cap; pooled = qp;
     }
     void upload(const T* h, size_t cnt, size_t off = 0, cudaStream_t st = 0) {
         if (cnt) AB_CUDA(cudaMemcpyAsync(p + off, h, cnt * sizeof(T), cudaMemcpyHostToDevice, st));

@@ -93,7 +93,7 @@ inline SweepGeometry plan_sweep(int64_t n_pad, int gs_max, int rec_max, int K = 
 }
 
 // Geometry of the batched look-ahead kernel (sweep_batched.cuh).  ok == false: use pin_solve_kernel instead.
-struct BatchGeometry { bool ok; int ncta, ncta_pad, B, Ccap, n_stages, stage_elems, rows_stride, units_base, units_rem, rec_stride, pslot_elems; size_t smem_bytes; };
+struct BatchGeometry { bool ok; int ncta, ncta_pad, B, Ccap, n_stages, stage_elems, rows_stride, units_base, units_rem, rec_stride, pslot_elems, ch; size_t smem_bytes; };
 
 template <class T>
 inline BatchGeometry plan_batched(int64_t n_pad, int gs_max, int rec_max) {
@@ -108,16 +108,22 @@ inline BatchGeometry plan_batched(int64_t n_pad, int gs_max, int rec_max) {
     g.ncta = ncta; g.ncta_pad = (ncta + 31) / 32 * 32;
     g.units_base = (int)(units / ncta); g.units_rem = (int)(units % ncta);
     g.rows_stride = (g.units_base + (g.units_rem ? 1 : 0)) * kRowAlign;
-    g.rec_stride = (rec_max + 3) / 4 * 4;
-    g.stage_elems = (g.rows_stride * gs_max + 31) / 32 * 32;
-    const int want = Configs::sweep_batch > 1 ? Configs::sweep_batch : 4;
+    {   // panel slots carry the extended records (lane-local prox, gs <= 12) or the base records (generic prox)
+        const int gsp = (gs_max + 3) / 4 * 4;
+        g.rec_stride = (gs_max <= 12) ? 3 * gsp + 2 * gs_max * gsp : (rec_max + 3) / 4 * 4;
+    }
+    // a group is streamed in ring items of at most ch columns (two items per group once groups have more than 4 columns): more,
+    // smaller stages keep both the HBM stream of the next batch and the L2 re-reads of the residual updates in flight
+    g.ch = (gs_max > 4) ? (gs_max + 1) / 2 : gs_max;
+    g.stage_elems = (g.rows_stride * g.ch + 31) / 32 * 32;
+    const int want = Configs::sweep_batch > 1 ? Configs::sweep_batch : 6;
     for (int B = std::min(std::min(want, kBatchMax), kBatchColsMax / gs_max); B >= 2; --B) {
         const int Ccap = (B * gs_max + 3) / 4 * 4;
         const int pslot = Ccap * 2 * Ccap + B * g.rec_stride;
         const size_t fixed = BatchSmem<T>::fixed_bytes(Ccap) + sizeof(T) * (2 * (size_t)g.rows_stride + 2 * (size_t)pslot);
         if (fixed >= di.smem_optin) continue;
-        const int ns = (int)std::min<size_t>(kMaxStages, (di.smem_optin - fixed) / (sizeof(T) * (size_t)g.stage_elems));
-        if (ns < 2) continue;
+        const int ns = (int)std::min<size_t>(kBatchStages, (di.smem_optin - fixed) / (sizeof(T) * (size_t)g.stage_elems));
+        if (ns < 3) continue;
         g.ok = true; g.B = B; g.Ccap = Ccap; g.pslot_elems = pslot; g.n_stages = ns;
         g.smem_bytes = fixed + sizeof(T) * (size_t)ns * g.stage_elems;
         break;
@@ -126,7 +132,7 @@ inline BatchGeometry plan_batched(int64_t n_pad, int gs_max, int rec_max) {
 }
 
 template <class T>
-struct BatchLaunch { const T* panels_screen; const T* panels_active; int n_active_panelled; int start_phase; };
+struct BatchLaunch { const T* panels_screen; const T* panels_active; int n_active_panelled; int start_phase; const T* beta_rot_in; };
 
 // xorshift-free counter based fill: X[i, j] ~ N(0,1) from Philox(seed, subsequence = column, offset = row)
 template <class T>
@@ -149,6 +155,7 @@ struct DenseMatrix {
     DevBuf<double> part;        // scratch for two-phase reductions
     DevBuf<T> ones;             // (n_pad,) ones with zero pad
     DevBuf<T> beta_rep;         // per-CTA coefficient replicas of the fused sweep (see sweep.cuh)
+    DevBuf<T> brot_rep;         // per-CTA replicas of the coefficients in the groups' eigenbases (sweep_batched.cuh)
     int64_t beta_stride = 0;
     DevBuf<int8_t> act_rep; int64_t act_stride = 0;
     DevBuf<long long> stats;    // per-phase cycle counters of the fused sweep (Configs::sweep_profile)
@@ -293,9 +300,11 @@ struct DenseMatrix {
         beta_stride = ((int64_t)L.beta_len + 31) / 32 * 32 + 32;
         beta_rep.reserve_keep((size_t)beta_stride * g.ncta, stream);
         a.beta_in = L.beta_in; a.beta_rep = beta_rep.p; a.beta_stride = beta_stride; a.beta_len = L.beta_len;
+        brot_rep.reserve_keep((size_t)beta_stride * g.ncta, stream);
+        a.brot_in = bl.beta_rot_in; a.brot_rep = brot_rep.p;
         a.active_set = L.active_set; a.sc = L.sc;
         a.panels_screen = bl.panels_screen; a.panels_active = bl.panels_active; a.n_active_panelled = bl.n_active_panelled;
-        a.B = g.B; a.Ccap = g.Ccap;
+        a.B = g.B; a.Ccap = g.Ccap; a.use_ext = (L.gs_max <= 12) ? 1 : 0;
         a.ll1 = ctx.ll.p; a.ll2 = ctx.ll2.p; a.ncta_pad = g.ncta_pad;
         { int f = 1; while (f * f < g.ncta) ++f; a.fan = std::max(1, f); }
         a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
@@ -303,7 +312,7 @@ struct DenseMatrix {
         a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
         a.start_phase = bl.start_phase;
         a.units_base = g.units_base; a.units_rem = g.units_rem; a.rows_stride = g.rows_stride;
-        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.rec_stride = g.rec_stride; a.pslot_elems = g.pslot_elems;
+        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.rec_stride = g.rec_stride; a.pslot_elems = g.pslot_elems; a.ch = g.ch;
         if (Configs::sweep_profile) { if (!stats.n) stats.alloc(32 + 8 * 160); a.stats = stats.p; } else a.stats = nullptr;
         void* kargs[] = {&a};
         const void* fn = !a.stats ? (const void*)pin_solve_batched_kernel<T, 0> : (Configs::sweep_profile >= 2 ? (const void*)pin_solve_batched_kernel<T, 2> : (const void*)pin_solve_batched_kernel<T, 1>);

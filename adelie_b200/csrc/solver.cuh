@@ -88,6 +88,7 @@ struct SparseRow { std::vector<int64_t> idx; std::vector<double> val; };
 // Host wall-clock accounting of the path driver (exposed as state scalars "t_<label>")
 struct HostTimers {
     std::vector<std::pair<std::string, double>> acc;
+    HostTimers() { acc.reserve(64); }          // scopes hold references into acc: it must never reallocate
     double& slot(const char* name) {
         for (auto& kv : acc) if (kv.first == name) return kv.second;
         acc.emplace_back(name, 0.0);
@@ -148,7 +149,7 @@ struct PathState {
     DevBuf<T> d_weights, d_weights_sqrt, d_resid, d_resid_prev, d_X_means, d_grad;
     DevBuf<T> d_offsets, d_eta, d_eta_prev, d_glm_resid_prev, d_hess, d_irls_w, d_irls_wsqrt, d_irls_y, d_irls_resid;
     DevBuf<T> d_glm_X_means;     // (p,) irls-weighted means on screen columns
-    DevBuf<GroupMeta> d_meta; DevBuf<T> d_grec, d_screen_beta; DevBuf<int8_t> d_is_active; DevBuf<int32_t> d_active_set;
+    DevBuf<GroupMeta> d_meta; DevBuf<T> d_grec, d_screen_beta, d_screen_beta_rot; DevBuf<int8_t> d_is_active; DevBuf<int32_t> d_active_set;
     DevBuf<PinScalars> d_sc; DevBuf<CovItem> d_cov_items; DevBuf<double> d_cov_out; DevBuf<int32_t> d_cols; DevBuf<T> d_tmp;
     DevBuf<double> d_scal;       // small scalar scratch (device-side sub_scale etc.)
     std::vector<GroupMeta> h_meta; std::vector<T> h_grec; size_t grec_uploaded = 0, meta_uploaded = 0;
@@ -229,6 +230,8 @@ struct PathState {
         screen_beta.resize(vs, 0);
         screen_is_active.resize(screen_set.size(), 0);
     }
+
+    static int batch_ext_len(int gs) { const int gsp = (gs + 3) / 4 * 4; return 3 * gsp + 2 * gs * gsp; }
 
     // Computes (A, V, xm) for screen positions [begin, end) from the weighted Gram of each group
     // (solver_gaussian_naive.hpp:53-125): device batched Gram -> host Jacobi -> packed records.
@@ -318,6 +321,20 @@ struct PathState {
                 grec[off + 2 * gs + c] = (T)xmt;
             }
             for (int k = 0; k < gs * gs; ++k) grec[off + 3 * gs + k] = st[i][k];
+            // extension for the batched kernel (sweep_batched.cuh), right behind the base record: vector-load friendly copies
+            //   [A(gsp) | xm(gsp) | V^T xm(gsp) | V rows padded to gsp | V^T rows padded to gsp],  gsp = gs rounded up to 4
+            {
+                const int gsp = (gs + 3) / 4 * 4;
+                const size_t e0 = grec.size();
+                grec.resize(e0 + batch_ext_len(gs), T(0));
+                for (int c = 0; c < gs; ++c) {
+                    grec[e0 + c] = grec[off + c]; grec[e0 + gsp + c] = grec[off + gs + c]; grec[e0 + 2 * gsp + c] = grec[off + 2 * gs + c];
+                    for (int r = 0; r < gs; ++r) {
+                        grec[e0 + 3 * gsp + (size_t)r * gsp + c] = st[i][(size_t)r * gs + c];                     // V[r][c]
+                        grec[e0 + 3 * gsp + (size_t)gs * gsp + (size_t)c * gsp + r] = st[i][(size_t)r * gs + c];  // V^T[c][r]
+                    }
+                }
+            }
             GroupMeta m{};
             m.col = (K == 1) ? (int32_t)groups[g] : (gi.icpt ? -(int32_t)(groups[g] + 1) : (int32_t)(groups[g] - n_int)); m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
             m.pen = (double)penalty[g];
@@ -358,10 +375,10 @@ struct PathState {
         const size_t pstride = (size_t)Ccap * ldq;
         const size_t nb = (N + B - 1) / B;
         const size_t b0 = (prev / B > 0) ? prev / B - 1 : 0;
-        pl.Q.reserve_keep(nb * pstride + 64);
-        if (nb > b0) AB_CUDA(cudaMemsetAsync(pl.Q.p + b0 * pstride, 0, (nb - b0) * pstride * sizeof(T), 0));
+        pl.Q.reserve_keep(nb * pstride + 64);          // (new tail zeroed; old panels keep their blocks)
         std::vector<PairItem> items; int64_t total = 0;
         auto grp = [&](size_t pos, int& col, int& gs) { const idx_t g = screen_set[entries[pos]]; col = (int)groups[g]; gs = (int)group_sizes[g]; };
+        // only the blocks with a NEW group on either side are computed: the others are already in place
         for (size_t b = b0; b < nb; ++b) {
             const size_t p0 = b * B, p1 = std::min(N, p0 + B), p2 = std::min(N, p1 + B);
             int off_k = 0;
@@ -370,23 +387,31 @@ struct PathState {
                 int off_t = off_k + gk;
                 for (size_t k2 = k + 1; k2 < p1; ++k2) {
                     int c2, g2; grp(k2, c2, g2);
-                    items.push_back(PairItem{ck, gk, c2, g2, (int64_t)(b * pstride + (size_t)off_k * ldq + off_t), total});
-                    total += (int64_t)gk * g2; off_t += g2;
+                    if (k2 >= prev) {
+                        items.push_back(PairItem{ck, gk, c2, g2, (int64_t)(b * pstride + (size_t)off_k * ldq + off_t), total});
+                        total += (int64_t)gk * g2;
+                    }
+                    off_t += g2;
                 }
                 off_t = 0;
                 for (size_t k2 = p1; k2 < p2; ++k2) {
                     int c2, g2; grp(k2, c2, g2);
-                    items.push_back(PairItem{ck, gk, c2, g2, (int64_t)(b * pstride + (size_t)off_k * ldq + Ccap + off_t), total});
-                    total += (int64_t)gk * g2; off_t += g2;
+                    if (k2 >= prev) {
+                        items.push_back(PairItem{ck, gk, c2, g2, (int64_t)(b * pstride + (size_t)off_k * ldq + Ccap + off_t), total});
+                        total += (int64_t)gk * g2;
+                    }
+                    off_t += g2;
                 }
                 off_k += gk;
             }
         }
         if (!items.empty()) {
-            d_pair_items.reserve_keep(items.size());
-            d_pair_items.upload(items.data(), items.size());
-            X->d_pair_gram(d_pair_items.p, (int)items.size(), total, d_w, pl.Q.p, ldq);
-            AB_CUDA(cudaStreamSynchronize(0));           // `items` (pageable host memory) must outlive the upload
+            { AB_TIME(timers, "panels_presync"); AB_CUDA(cudaStreamSynchronize(0)); }
+            { AB_TIME(timers, "panels_launch");
+              d_pair_items.reserve_keep(items.size());
+              d_pair_items.upload(items.data(), items.size());
+              X->d_pair_gram(d_pair_items.p, (int)items.size(), total, d_w, pl.Q.p, ldq); }
+            { AB_TIME(timers, "panels_sync"); AB_CUDA(cudaStreamSynchronize(0)); }          // `items` (pageable host memory) must outlive the upload
             n_kernel_launches += 2;
         }
         n_panels_built += (long long)(nb - b0);
@@ -401,6 +426,21 @@ struct PathState {
         d_screen_beta.reserve_keep(screen_beta.size() + 4); d_is_active.reserve_keep(S + 4);
         d_screen_beta.upload(screen_beta.data(), screen_beta.size());
         d_is_active.upload(screen_is_active.data(), S);
+        // coefficients in every group's eigenbasis (a V): the batched kernel keeps them up to date instead of rotating per visit
+        std::vector<T> beta_rot(screen_beta.size(), T(0));
+        if (static_weights && K == 1) {
+            for (size_t i = 0; i < S && i < screen_transforms.size(); ++i) {
+                const int gs = (int)group_sizes[screen_set[i]]; const idx_t sb = screen_begins[i];
+                const std::vector<T>& V = screen_transforms[i];
+                for (int c = 0; c < gs; ++c) {
+                    double acc = 0;
+                    for (int r = 0; r < gs; ++r) acc += (double)screen_beta[sb + r] * (double)V[(size_t)r * gs + c];
+                    beta_rot[sb + c] = (T)acc;
+                }
+            }
+            d_screen_beta_rot.reserve_keep(screen_beta.size() + 4);
+            d_screen_beta_rot.upload(beta_rot.data(), beta_rot.size());
+        }
         std::vector<int32_t> act32(active_set_size);
         for (size_t i = 0; i < active_set_size; ++i) act32[i] = (int32_t)active_set[i];
         d_active_set.upload(act32.data(), active_set_size);
@@ -434,19 +474,21 @@ struct PathState {
             // outgrew its panels (after a screen sweep that added groups), everything else continues on the device
             std::vector<int32_t> ent(S);
             std::iota(ent.begin(), ent.end(), 0);
+            { AB_TIME(timers, "pin_presync"); AB_CUDA(cudaStreamSynchronize(0)); }
             ensure_panels(pl_screen, ent, bg.B, bg.Ccap, d_w);
             BatchLaunch<T> bl{};
-            bl.start_phase = kSweepActive;
+            bl.start_phase = kSweepActive; bl.beta_rot_in = d_screen_beta_rot.p;
             size_t act_now = active_set_size;
             while (true) {
                 ent.assign(act32.begin(), act32.begin() + act_now);
                 ensure_panels(pl_active, ent, bg.B, bg.Ccap, d_w);
                 bl.panels_screen = pl_screen.Q.p; bl.panels_active = pl_active.Q.p; bl.n_active_panelled = (int)act_now;
-                AB_CUDA(cudaEventRecord(ev0, 0));
-                X->pin_solve_batched(L, bg, bl);
-                AB_CUDA(cudaEventRecord(ev1, 0));
-                d_sc.download(h_sc.p, 1);
-                AB_CUDA(cudaStreamSynchronize(0));
+                { AB_TIME(timers, "pin_launch");
+                  AB_CUDA(cudaEventRecord(ev0, 0));
+                  X->pin_solve_batched(L, bg, bl);
+                  AB_CUDA(cudaEventRecord(ev1, 0));
+                  d_sc.download(h_sc.p, 1); }
+                { AB_TIME(timers, "pin_sync"); AB_CUDA(cudaStreamSynchronize(0)); }
                 ++n_kernel_launches; ++n_batched_launches;
                 float m1 = 0; AB_CUDA(cudaEventElapsedTime(&m1, ev0, ev1));
                 ms += m1;
@@ -456,14 +498,16 @@ struct PathState {
                 act32.resize(act_new);
                 d_active_set.download(act32.data() + act_now, act_new - act_now, act_now);
                 AB_CUDA(cudaMemcpyAsync(d_screen_beta.p, X->beta_rep.p, screen_beta.size() * sizeof(T), cudaMemcpyDeviceToDevice, 0));
+                AB_CUDA(cudaMemcpyAsync(d_screen_beta_rot.p, X->brot_rep.p, screen_beta.size() * sizeof(T), cudaMemcpyDeviceToDevice, 0));
                 AB_CUDA(cudaMemcpyAsync(d_is_active.p, X->act_rep.p, S, cudaMemcpyDeviceToDevice, 0));
                 AB_CUDA(cudaStreamSynchronize(0));
                 act_now = act_new;
             }
         }
-        X->beta_rep.download(screen_beta.data(), screen_beta.size());     // replica 0
-        X->act_rep.download(screen_is_active.data(), S);                   // replica 0
-        AB_CUDA(cudaStreamSynchronize(0));
+        { AB_TIME(timers, "pin_download");
+          X->beta_rep.download(screen_beta.data(), screen_beta.size());     // replica 0
+          X->act_rep.download(screen_is_active.data(), S);                   // replica 0
+          AB_CUDA(cudaStreamSynchronize(0)); }
         ++n_pin_solves;
         time_sweep_kernel += ms * 1e-3;
         sc = *h_sc.p;

@@ -32,6 +32,7 @@ namespace ab {
 constexpr int kBatchMax = 8;           // most groups per batch
 constexpr int kBatchColsMax = 64;      // most columns per batch (Ccap <= 64): one pass of the 64 exchange threads
 constexpr int kBatchLLSlots = 4;       // exchange buffers are 4-deep (see the race analysis at ew_exchange)
+constexpr int kBatchStages = 8;        // most stages of the column-tile ring
 constexpr int kBatchDW = 12;           // data warps
 constexpr int kBatchNDT = kBatchDW * 32;
 
@@ -43,6 +44,8 @@ struct BatchKernelArgs {
     T* resid; const T* weights;
     const GroupMeta* meta; int S; const T* grec;
     const T* beta_in; T* beta_rep; int64_t beta_stride; int beta_len;
+    const T* brot_in; T* brot_rep;                       // coefficients in the groups' eigenbases (a V), same layout / replicas
+    int use_ext;                                         // 1: panel slots carry the extended records (all groups <= 12 columns)
     const int8_t* is_active_in; int8_t* is_active_rep; int64_t act_stride;
     int32_t* active_set;
     PinScalars* sc;
@@ -56,6 +59,7 @@ struct BatchKernelArgs {
     int start_phase;
     int units_base, units_rem, rows_stride;
     int n_stages, stage_elems;
+    int ch;                                              // columns per ring item (a group is streamed in ceil(gs / ch) <= 2 items)
     int rec_stride;                                      // elements between the records inside a panel slot
     int pslot_elems;                                     // elements per panel slot = Ccap * 2 Ccap + B * rec_stride
     long long* stats;
@@ -129,99 +133,108 @@ template <> struct FastMath<double> {
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
 };
 
-// Group update (solver_gaussian_pin_naive.hpp:109-164) for 1 < gs <= GSP <= 12 by the control warp, one coefficient per lane,
-// written for the FEWEST DEPENDENT SHARED-MEMORY ROUND TRIPS (the data warps keep the LSU pipe saturated, so every round trip
-// of the lone control warp costs hundreds of cycles): prox_pre() loads everything that does not depend on the gradient (it is
-// issued one group ahead, behind the previous group's corrections); prox_post() broadcasts the rotated gradient and the
-// shifted eigenvalues once, after which the whole Newton iteration on h = ||x|| (newton.hpp:44-142) runs in registers,
-// redundantly in every lane.  Start point: the previous norm ||beta_g|| when phi there is >= 0 (left of the root, from where
-// the iteration is monotone, like h0 = 0 of the reference), otherwise 0; only the converged root matters for parity.
+// Group update (solver_gaussian_pin_naive.hpp:109-164) for 1 < gs <= GSP <= 12 by the control warp.  A lone warp issues
+// roughly one instruction every 4-6 cycles, so the update is written for FEW INSTRUCTIONS and SHORT DEPENDENT CHAINS:
+// one coefficient per lane (lanes 16-31 mirror lanes 0-15 so that every decision is warp-uniform), 16-lane butterfly
+// reductions, MUFU reciprocals, and everything that does not depend on the gradient loaded one group ahead (prox_pre, issued
+// behind the previous group's corrections).  Newton iteration on h = ||x|| as newton_solver (newton.hpp:44-142); start point:
+// the previous norm ||beta_g|| when phi there is >= 0 (left of the root, from where the iteration is monotone, like h0 = 0 of
+// the reference), otherwise 0; only the converged root matters for parity.
 template <class P, int GSP> struct LanePre { P A, xm, xmt, aold_c, ao, h0sq; P vcol[GSP], vrow[GSP]; };
 
-template <class T, class P, int GSP>
-__device__ __forceinline__ void prox_pre(LanePre<P, GSP>& r, const T* rec, int gs, const P* aold_s, int lane) {
-    const bool on = lane < gs;
-    const int c = on ? lane : 0;
-    const T* V = rec + 3 * gs;
-    r.A = on ? (P)rec[c] : P(0); r.xm = on ? (P)rec[gs + c] : P(0); r.xmt = on ? (P)rec[2 * gs + c] : P(0);
-    r.aold_c = on ? aold_s[c] : P(0);
-    P ao = 0, h0sq = 0;
+template <int N, class P>
+__device__ __forceinline__ void seg16_allsum(P (&v)[N]) {
 #pragma unroll
-    for (int q = 0; q < GSP; ++q) {
-        const bool in = q < gs;
-        r.vcol[q] = in ? (P)V[q * gs + c] : P(0);
-        r.vrow[q] = in ? (P)V[c * gs + q] : P(0);
-        const P aq = in ? aold_s[q] : P(0);
-        ao += aq * r.vcol[q]; h0sq += aq * aq;
+    for (int o = 8; o > 0; o >>= 1) {
+        P t[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) t[i] = __shfl_xor_sync(0xffffffffu, v[i], o);
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] += t[i];
     }
-    r.ao = on ? ao : P(0); r.h0sq = h0sq;
 }
 
-// bc: shared scratch of 5 * GSP elements.  Returns 1 if the coefficients moved; del (original basis) in dl[0..gs).
+// ext: the group's extended record [A(gsp) | xm(gsp) | V^T xm(gsp) | V rows (gs x gsp) | V^T rows (gs x gsp)], gsp = gs rounded up
+// to 4 (zero padded), so that a lane's row of V / V^T comes in with 16-byte loads.  aold_s / arot_s: the group's current
+// coefficients in the original basis / in the eigenbasis.
 template <class T, class P, int GSP>
-__device__ __forceinline__ int prox_post(const LanePre<P, GSP>& pre, int gs, double g_in, P l1k, P l2k, P tol, int max_iters,
-                                         P dbeta_tol, int intercept, ProxState& ps, int lane, P* bc, T* beta_g, T* dl, long long* pp)
+__device__ __forceinline__ void prox_pre(LanePre<P, GSP>& r, const T* ext, int gs, const P* aold_s, const P* arot_s, int lane) {
+    constexpr int VN = VecT<T>::N;
+    const int l16 = lane & 15;
+    const bool on = l16 < gs;
+    const int c = on ? l16 : 0;
+    const int gsp = (gs + 3) & ~3;
+    r.A = on ? (P)ext[c] : P(0); r.xm = on ? (P)ext[gsp + c] : P(0); r.xmt = on ? (P)ext[2 * gsp + c] : P(0);
+    r.aold_c = on ? aold_s[c] : P(0);
+    r.ao = on ? arot_s[c] : P(0);
+    const T* vr = ext + 3 * gsp + c * gsp;                 // V[c][.]    (rotate back)
+    const T* vc = vr + gs * gsp;                           // V^T[c][.] = V[.][c]   (rotate the gradient)
+#pragma unroll
+    for (int q = 0; q < GSP; q += VN) {
+        if (q < gsp) {
+            vec_load<T>(vr + q, reinterpret_cast<T(&)[VN]>(r.vrow[q]));
+            vec_load<T>(vc + q, reinterpret_cast<T(&)[VN]>(r.vcol[q]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) { r.vrow[q + k] = 0; r.vcol[q + k] = 0; }
+        }
+    }
+    P v1[1] = {r.ao * r.ao};
+    seg16_allsum<1>(v1);
+    r.h0sq = v1[0];
+}
+
+// bc: shared scratch of 32 elements.  g_in: the group's gradient X_g^T (w o r), element (lane & 15).
+// Returns 1 if the coefficients moved; del (original basis) in dl[0..gs) and, per lane, in del_c.
+template <class T, class P, int GSP>
+__device__ __forceinline__ int prox_post(const LanePre<P, GSP>& pre, int gs, P g_in, P l1k, P l2k, P tol, int max_iters,
+                                         P dbeta_tol, int intercept, ProxState& ps, int lane, P* bc, T* beta_g, T* brot_g, T* dl, P& del_c, long long* pp)
 {
     constexpr int VN = VecT<P>::N;
     using FM = FastMath<P>;
-    long long tc_ = pp ? clock64() : 0;
-#define ABP_TICK(k) do { if (pp) { const long long t_ = clock64(); pp[k] += t_ - tc_; tc_ = t_; } } while (0)
-    const bool on = lane < gs;
+    const int l16 = lane & 15;
+    const bool on = l16 < gs;
     // ---- gradient in the original basis, broadcast, rotated: gt = gk V + A (a_old V)
-    P gk = on ? (P)g_in : P(0);
+    P gk = on ? g_in : P(0);
     if (intercept && on) gk -= (P)ps.resid_sum * pre.xm;
-    if (lane < GSP) bc[lane] = gk;
+    if (lane < 16) bc[lane] = gk;
     __syncwarp();
-    P gt0 = 0;
+    P gt0a = 0, gt0b = 0;
     {
         P gka[GSP];
 #pragma unroll
         for (int q = 0; q < GSP; q += VN) vec_load<P>(bc + q, reinterpret_cast<P(&)[VN]>(gka[q]));
 #pragma unroll
-        for (int q = 0; q < GSP; ++q) gt0 += gka[q] * pre.vcol[q];
+        for (int q = 0; q < GSP; q += 2) { gt0a += gka[q] * pre.vcol[q]; gt0b += gka[q + 1] * pre.vcol[q + 1]; }
     }
-    if (!on) gt0 = 0;
+    const P gt0 = on ? gt0a + gt0b : P(0);
     const P gt = gt0 + pre.A * pre.ao;
     const P D = on ? pre.A + l2k : P(1);
-    if (lane < GSP) { bc[GSP + lane] = gt; bc[2 * GSP + lane] = D; }
-    __syncwarp();
-    P gta[GSP], Da[GSP];
-#pragma unroll
-    for (int q = 0; q < GSP; q += VN) { vec_load<P>(bc + GSP + q, reinterpret_cast<P(&)[VN]>(gta[q])); vec_load<P>(bc + 2 * GSP + q, reinterpret_cast<P(&)[VN]>(Da[q])); }
-    ABP_TICK(1);
-    // ---- root of phi(h) = sum (gt / (D h + l1))^2 - 1, in registers
+    // ---- root of phi(h) = sum (gt / (D h + l1))^2 - 1
     P at = 0; int nit = 0;
     if (l1k <= P(0)) {
         at = (on && gt != P(0)) ? gt / (pre.A + l2k) : P(0);
     } else {
         const P tol_eff = fmax(tol, ProxEps<P>::floor_tol());
-        P t, sd;
-        auto eval = [&](P h) {
-            P t0 = 0, t1 = 0, s0 = 0, s1 = 0;
-#pragma unroll
-            for (int q = 0; q < GSP; q += 2) {
-                const P u0 = FM::rcp(Da[q] * h + l1k), u1 = FM::rcp(Da[q + 1] * h + l1k);
-                const P q0 = gta[q] * u0, q1 = gta[q + 1] * u1;
-                const P x0 = q0 * q0, x1 = q1 * q1;
-                t0 += x0; t1 += x1; s0 += x0 * Da[q] * u0; s1 += x1 * Da[q + 1] * u1;
-            }
-            t = t0 + t1; sd = s0 + s1;
-        };
-        // One evaluation site (code size: the control warp's path must stay inside the instruction cache).
-        // mode 0: phi(0), doubles as the ||v|| <= l1 test (newton.hpp:62-66); mode 1: warm start; mode 2: Newton iterations
+        // One evaluation site.  mode 0: phi(0), doubles as the ||v|| <= l1 test (newton.hpp:62-66); 1: warm start; 2: Newton
         const P hw = (pre.h0sq > P(0)) ? FM::sqrt_(pre.h0sq) : P(0);
-        P h = 0, t_keep = 0, sd_keep = 0;
+        P h = 0, t_keep = 0, sd_keep = 0, u = 0;
         int mode = 0; bool zero = false;
 #pragma unroll 1
         while (true) {
-            eval(h);
+            u = FM::rcp(D * h + l1k);
+            const P qq = gt * u;
+            const P xx = qq * qq;
+            P v2[2] = {xx, xx * D * u};
+            seg16_allsum<2>(v2);
+            P t = v2[0], sd = v2[1];
             if (mode == 0) {
                 if (!(t > P(1))) { zero = true; break; }
                 if (hw > P(0)) { t_keep = t; sd_keep = sd; h = hw; mode = 1; continue; }
                 mode = 2;
             } else if (mode == 1) {
                 mode = 2;
-                if (!(t - P(1) >= -tol_eff)) { h = 0; t = t_keep; sd = sd_keep; }    // right of the root: restart from 0
+                if (!(t - P(1) >= -tol_eff)) { h = 0; t = t_keep; sd = sd_keep; u = FM::rcp(l1k); }   // right of the root: restart from 0
             }
             if (!(fabs(t - P(1)) > tol_eff) || nit >= max_iters) break;
             // h - fh / dfh with dfh = -sd (1 + sqrt t) / t   (optimization/newton.hpp:56-63), one reciprocal
@@ -229,71 +242,62 @@ __device__ __forceinline__ int prox_post(const LanePre<P, GSP>& pre, int gs, dou
             if (hn == h) break;                                   // no representable progress left
             h = hn; ++nit;
         }
-        at = (on && !zero) ? h * gt / (D * h + l1k) : P(0);
+        at = (on && !zero) ? h * gt * u : P(0);                   // x = h v / (D h + l1)   (newton.hpp:109)
     }
     ps.newton_iters_max = max(ps.newton_iters_max, nit);
     if (nit >= max_iters) ps.error = kErrNewton;
-    ABP_TICK(2);
     if (pp) pp[5] += nit;
-    // ---- the four sums of the update test / bookkeeping and the broadcast of the new rotated coefficients: one round trip
+    // ---- update test / bookkeeping sums
     const P d = at - pre.ao;
+    P v4[4] = {d * d, pre.A * d * d, d * (2 * gt0 - d * pre.A), -pre.xmt * d};
+    seg16_allsum<4>(v4);
+    if (sqrt(v4[0]) <= dbeta_tol * sqrt((P)gs)) { if (pp) ++pp[6]; return 0; }      // :146-147
+    ps.cm = fmax(ps.cm, (double)(v4[1] / gs));
+    ps.rsq += (double)v4[2];
+    ps.resid_sum += (double)v4[3];
+    // ---- back to the original basis: del = a_old - a_new = V (ao - at) = -V d
     __syncwarp();
-    if (lane < GSP) {
-        bc[lane] = d * d; bc[GSP + lane] = pre.A * d * d; bc[2 * GSP + lane] = d * (2 * gt0 - d * pre.A); bc[3 * GSP + lane] = -pre.xmt * d; bc[4 * GSP + lane] = at;
-    }
+    if (lane < 16) bc[16 + lane] = d;
     __syncwarp();
-    P red[4] = {0, 0, 0, 0};
-    P ata[GSP];
+    P dea = 0, deb = 0;
+    {
+        P da[GSP];
 #pragma unroll
-    for (int q = 0; q < GSP; q += VN) {
-        P v0[VN], v1[VN], v2[VN], v3[VN];
-        vec_load<P>(bc + q, v0); vec_load<P>(bc + GSP + q, v1); vec_load<P>(bc + 2 * GSP + q, v2); vec_load<P>(bc + 3 * GSP + q, v3);
-        vec_load<P>(bc + 4 * GSP + q, reinterpret_cast<P(&)[VN]>(ata[q]));
+        for (int q = 0; q < GSP; q += VN) vec_load<P>(bc + 16 + q, reinterpret_cast<P(&)[VN]>(da[q]));
 #pragma unroll
-        for (int k = 0; k < VN; ++k) { red[0] += v0[k]; red[1] += v1[k]; red[2] += v2[k]; red[3] += v3[k]; }
+        for (int q = 0; q < GSP; q += 2) { dea -= da[q] * pre.vrow[q]; deb -= da[q + 1] * pre.vrow[q + 1]; }
     }
-    ABP_TICK(3);
-    if (sqrt(red[0]) <= dbeta_tol * sqrt((P)gs)) { if (pp) ++pp[6]; return 0; }      // :146-147
-    ps.cm = fmax(ps.cm, (double)(red[1] / gs));
-    ps.rsq += (double)red[2];
-    ps.resid_sum += (double)red[3];
-    P an0 = 0, an1 = 0;
-#pragma unroll
-    for (int q = 0; q < GSP; q += 2) { an0 += ata[q] * pre.vrow[q]; an1 += ata[q + 1] * pre.vrow[q + 1]; }     // rotate back: a = at V^T
-    if (on) {
-        const T anT = (T)(an0 + an1);
-        beta_g[lane] = anT;
-        dl[lane] = (T)(pre.aold_c - (P)anT);
-    }
-    ABP_TICK(4);
-#undef ABP_TICK
+    const T anT = (T)(pre.aold_c - (dea + deb));
+    del_c = on ? (P)(T)(pre.aold_c - (P)anT) : P(0);
+    if (lane < gs) { beta_g[lane] = anT; brot_g[lane] = (T)at; dl[lane] = (T)del_c; }
     return 1;
 }
 
-// Gradient corrections after group (off, gs) of the current batch moved by dl: g[t] += sum_c Q[off + c][t] dl[c] for the later
-// columns of this batch (gc, columns lane and lane + 32) and all columns of the next batch (cn).  All loads are independent.
+// Gradient corrections after group (off, gs) of the current batch moved by del: ga[j] += sum_c Q[off + c][4 lane + j] del[c] in
+// "panel column space" t = 4 lane + j: t < Ccap are the columns of this batch (only the later ones are used afterwards),
+// t >= Ccap the columns of the next batch.  One 16-byte load per source column.  del_c: lane c holds del[c]; GSP == 0: del
+// comes from dl (large groups).
 template <class T, class P, int GSP>
-__device__ __forceinline__ void apply_corrections(const T* Q, int ldq, int Ccap, int off, int gs, const T* dl, int C_cur, int C_nxt,
-                                                  double (&gc)[2], P (&cn)[2], int lane)
+__device__ __forceinline__ void apply_corrections(const T* Q, int ldq, int off, int gs, const T* dl, P del_c, P (&ga)[4], int lane)
 {
-    P acc[4] = {0, 0, 0, 0};
-    const bool has1 = lane + 32 < Ccap;
-    constexpr int NC = GSP > 0 ? GSP : 32;                 // GSP == 0: runtime loop (large groups)
+    const bool act = 4 * lane < ldq;
+    const T* qcol = Q + (size_t)off * ldq + (act ? 4 * lane : 0);
+    constexpr int NC = GSP > 0 ? GSP : 32;
 #pragma unroll (GSP > 0 ? GSP : 2)
     for (int c = 0; c < NC; ++c) {
-        if (c < gs) {
-            const P dc = (P)dl[c];
-            const T* qrow = Q + (size_t)(off + c) * ldq + lane;
-            acc[0] += (P)qrow[0] * dc;
-            acc[2] += (P)qrow[Ccap] * dc;
-            if (has1) { acc[1] += (P)qrow[32] * dc; acc[3] += (P)qrow[Ccap + 32] * dc; }
-        }
-    }
+        const P dc = GSP > 0 ? __shfl_sync(0xffffffffu, del_c, c) : (c < gs ? (P)dl[c] : P(0));
+        if (c < gs && act) {
+            if constexpr (sizeof(T) == 4) {
+                T q4[4];
+                vec_load<T>(qcol + (size_t)c * ldq, q4);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int t = lane + 32 * j;
-        if (t >= off + gs && t < C_cur) gc[j] += (double)acc[j];
-        if (t < C_nxt) cn[j] += acc[2 + j];
+                for (int j = 0; j < 4; ++j) ga[j] += (P)q4[j] * dc;
+            } else {
+                T q2[2], q3[2];
+                vec_load<T>(qcol + (size_t)c * ldq, q2); vec_load<T>(qcol + (size_t)c * ldq + 2, q3);
+                ga[0] += (P)q2[0] * dc; ga[1] += (P)q2[1] * dc; ga[2] += (P)q3[0] * dc; ga[3] += (P)q3[1] * dc;
+            }
+        }
     }
 }
 
@@ -303,7 +307,7 @@ struct BatchSmem {
     // header | gstale[2][Ccap] f64 | corr[2][Ccap] | gcur[32] f64 | del[2][Ccap] | aold[2][Ccap] | p_gk[32] p_at[32] scr[128] |
     // wpart[2][DW][Ccap] f64 | r tile | w tile | panel slots [2] | stages
     __host__ __device__ static size_t fixed_bytes(int Ccap) {
-        size_t b = kHeaderBytes + sizeof(double) * ((size_t)Ccap * 8 + 32 + 32 + 32 + 128 + (size_t)2 * kBatchDW * Ccap);
+        size_t b = kHeaderBytes + sizeof(double) * ((size_t)Ccap * 10 + 32 + 32 + 32 + 128 + (size_t)2 * kBatchDW * Ccap);
         return (b + 127) / 128 * 128;
     }
 };
@@ -320,9 +324,9 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
     const int cta = blockIdx.x, ncta = gridDim.x;
     const int B = a.B, Ccap = a.Ccap, ldq = 2 * a.Ccap;
 
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);          // [kMaxStages]
-    uint64_t* empty_bar = full_bar + kMaxStages;                          // [kMaxStages]
-    uint64_t* pfull_bar = empty_bar + kMaxStages;                         // [2]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);          // [kBatchStages]
+    uint64_t* empty_bar = full_bar + kBatchStages;                        // [kBatchStages]
+    uint64_t* pfull_bar = empty_bar + kBatchStages;                       // [2]
     uint64_t* pempty_bar = pfull_bar + 2;                                 // [2]
     uint64_t* prox_bar = pempty_bar + 2;                                  // [2][kBatchMax]: group k of a batch (by parity) is solved
     uint64_t* gready_bar = prox_bar + 2 * kBatchMax;                      // [2]: all-reduced gradient of a batch (by parity) is in gstale
@@ -333,11 +337,13 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
     double* gcur = corr_raw + 2 * Ccap;                                   // [32]
     double* del_raw = gcur + 32;                                          // [2][Ccap] (T)
     double* aold_raw = del_raw + 2 * Ccap;                                // [2][Ccap] (P)
-    double* pscr_raw = aold_raw + 2 * Ccap;                               // p_gk[32] p_at[32] scr[128]
+    double* arot_raw = aold_raw + 2 * Ccap;                               // [2][Ccap] (P)
+    double* pscr_raw = arot_raw + 2 * Ccap;                               // p_gk[32] p_at[32] scr[128]
     double* wpart = pscr_raw + 32 + 32 + 128;                             // [2][DW][Ccap]
     P* corr = reinterpret_cast<P*>(corr_raw);
     T* del = reinterpret_cast<T*>(del_raw);
     P* aold = reinterpret_cast<P*>(aold_raw);
+    P* arot = reinterpret_cast<P*>(arot_raw);
     P* p_gk = reinterpret_cast<P*>(pscr_raw);
     P* p_at = reinterpret_cast<P*>(pscr_raw + 32);
     P* p_scr = reinterpret_cast<P*>(pscr_raw + 64);
@@ -356,7 +362,7 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
     volatile int* halt = &ctrl->halt;
 
     if (tid == 0) {
-        for (int s = 0; s < kMaxStages; ++s) { dev::mbar_init(&full_bar[s], 1); dev::mbar_init(&empty_bar[s], kBatchDW); }
+        for (int s = 0; s < kBatchStages; ++s) { dev::mbar_init(&full_bar[s], 1); dev::mbar_init(&empty_bar[s], kBatchDW); }
         for (int s = 0; s < 2; ++s) { dev::mbar_init(&pfull_bar[s], 1); dev::mbar_init(&pempty_bar[s], 1); dev::mbar_init(&gready_bar[s], 1); }
         for (int s = 0; s < 2 * kBatchMax; ++s) dev::mbar_init(&prox_bar[s], 1);
         for (int s = 0; s < 2; ++s) dev::mbar_init(&dbar[s], kBatchDW);
@@ -366,7 +372,8 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
     for (int i = tid; i < 4 * Ccap; i += blockDim.x) corr_raw[i] = 0.0;        // corr + (unused tail): both slots start at zero
     T* my_beta = a.beta_rep + (size_t)cta * a.beta_stride;
     int8_t* my_active = a.is_active_rep + (size_t)cta * a.act_stride;
-    for (int i = tid; i < a.beta_len; i += blockDim.x) my_beta[i] = a.beta_in[i];
+    T* my_brot = a.brot_rep + (size_t)cta * a.beta_stride;
+    for (int i = tid; i < a.beta_len; i += blockDim.x) { my_beta[i] = a.beta_in[i]; my_brot[i] = a.brot_in[i]; }
     for (int i = tid; i < a.S; i += blockDim.x) my_active[i] = a.is_active_in[i];
     // resident r / w tiles
     {
@@ -387,34 +394,43 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
     // =====================================================================================================
     if (role_prod) {
         uint32_t gitem = 0, pitem = 0;
-        int sweep = 0;
+        int sweep = 0, ubatch = 0;
         bool running = true;
-        const uint64_t pol_keep = dev::policy_evict_last();
+        const uint64_t pol_keep = dev::policy_evict_last(), pol_done = dev::policy_evict_first();
         while (running) {
             if (!dev::wait_counter(&ctrl->sw_seq, sweep + 1, abort_flag, halt)) break;
             const int kind = ctrl->sw_kind[sweep & 3], count = ctrl->sw_count[sweep & 3];
             if (kind == kSweepExit) break;
             const T* panels = (kind == kSweepActive) ? a.panels_active : a.panels_screen;
             const int nb = (count + B - 1) / B;
-            for (int b = 0; b < nb && running; ++b) {
-                const int p0 = b * B, nbg = min(B, count - p0);
-                // ---- column tiles of the batch
-                for (int k = 0; k < nbg; ++k, ++gitem) {
-                    const int stage = gitem % a.n_stages;
-                    const uint32_t use = gitem / a.n_stages;
-                    if (!dev::mbar_wait(&empty_bar[stage], (use & 1) ^ 1, abort_flag, halt)) { running = false; break; }
-                    const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + k) : p0 + k;
-                    const GroupMeta m = a.meta[ss];
-                    T* xs = stages + (size_t)stage * a.stage_elems;
-                    const uint32_t col_bytes = (uint32_t)rows * sizeof(T);
-                    if (lane == 0) dev::mbar_arrive_expect_tx(&full_bar[stage], col_bytes * m.gs);
-                    __syncwarp();
-                    for (int c = lane; c < m.gs; c += 32)
-                        dev::tma_bulk_g2s_hint(xs + (size_t)c * a.rows_stride, a.X + (int64_t)(m.col + c) * a.ld + r0, col_bytes, &full_bar[stage], pol_keep);
-                }
-                if (!running) break;
-                // ---- panel + records of the batch
-                {
+            // ring order = consumption order of the data warps: D(0) | D(1) U(0) | D(2) U(1) | ... | U(nb-1); every group is
+            // streamed in items of at most `ch` columns.  D items keep their lines in L2 (evict_last): the U items of the same
+            // group re-read them one batch later (evict_first: last use).  U items wait for the group's proximal update.
+            auto issue_item = [&](int col0, int ncols, uint64_t pol) -> bool {
+                const int stage = gitem % a.n_stages;
+                const uint32_t use = gitem / a.n_stages;
+                if (!dev::mbar_wait(&empty_bar[stage], (use & 1) ^ 1, abort_flag, halt)) return false;
+                T* xs = stages + (size_t)stage * a.stage_elems;
+                const uint32_t col_bytes = (uint32_t)rows * sizeof(T);
+                if (lane == 0) dev::mbar_arrive_expect_tx(&full_bar[stage], col_bytes * ncols);
+                __syncwarp();
+                if (lane < ncols)
+                    dev::tma_bulk_g2s_hint(xs + (size_t)lane * a.rows_stride, a.X + (int64_t)(col0 + lane) * a.ld + r0, col_bytes, &full_bar[stage], pol);
+                ++gitem;
+                return true;
+            };
+#pragma unroll 1
+            for (int b = -1; b < nb && running; ++b) {
+                if (b + 1 < nb) {
+                    const int p0 = (b + 1) * B, nbg = min(B, count - p0);
+                    // ---- D items of batch b + 1
+                    for (int k = 0; k < nbg && running; ++k) {
+                        const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + k) : p0 + k;
+                        const GroupMeta m = a.meta[ss];
+                        for (int c0 = 0; c0 < m.gs && running; c0 += a.ch) running = issue_item(m.col + c0, min(a.ch, m.gs - c0), pol_keep);
+                    }
+                    if (!running) break;
+                    // ---- panel + records of batch b + 1
                     const int slot = pitem & 1;
                     const uint32_t use = pitem >> 1;
                     if (!dev::mbar_wait(&pempty_bar[slot], (use & 1) ^ 1, abort_flag, halt)) { running = false; break; }
@@ -423,16 +439,34 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                     int rec_elems = 0; int64_t rec_off = 0;
                     if (lane < nbg) {
                         const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane;
-                        rec_elems = a.meta[ss].rec_elems; rec_off = a.meta[ss].rec_off;
+                        const GroupMeta mm = a.meta[ss];
+                        rec_elems = mm.rec_elems; rec_off = mm.rec_off;
+                        if (a.use_ext) {                                         // the extension sits right behind the base record
+                            const int gsp = (mm.gs + 3) & ~3;
+                            rec_off += rec_elems; rec_elems = 3 * gsp + 2 * mm.gs * gsp;
+                        }
                     }
                     uint32_t tot = (uint32_t)rec_elems * sizeof(T);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
                     if (lane == 0) dev::mbar_arrive_expect_tx(&pfull_bar[slot], q_bytes + tot);
                     __syncwarp();
-                    if (lane == 0) dev::tma_bulk_g2s(ps_, panels + (int64_t)b * Ccap * ldq, q_bytes, &pfull_bar[slot]);
+                    if (lane == 0) dev::tma_bulk_g2s(ps_, panels + (int64_t)(b + 1) * Ccap * ldq, q_bytes, &pfull_bar[slot]);
                     if (lane < nbg) dev::tma_bulk_g2s(ps_ + Ccap * ldq + lane * a.rec_stride, a.grec + rec_off, (uint32_t)rec_elems * sizeof(T), &pfull_bar[slot]);
                     ++pitem;
+                }
+                if (b >= 0) {
+                    // ---- U items of batch b, each as soon as its group's proximal update is done (and only if it moved)
+                    const int p0 = b * B, nbg = min(B, count - p0);
+                    const int upar = ubatch & 1;
+                    for (int k = 0; k < nbg && running; ++k) {
+                        const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + k) : p0 + k;
+                        const GroupMeta m = a.meta[ss];
+                        if (!dev::mbar_wait(&prox_bar[upar * kBatchMax + k], (uint32_t)(ubatch >> 1) & 1u, abort_flag, halt)) { running = false; break; }
+                        if (*reinterpret_cast<volatile int*>(&ctrl->changed[upar][k]))
+                            for (int c0 = 0; c0 < m.gs && running; c0 += a.ch) running = issue_item(m.col + c0, min(a.ch, m.gs - c0), pol_done);
+                    }
+                    ++ubatch;
                 }
             }
             ++sweep;
@@ -552,11 +586,108 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
         int sweep = 0, bcount = 0, ucount = 0;                    // batches whose D phase ran / groups whose U phase ran
         int ubatch = 0;                                            // batches whose U phase ran (parity of del / changed / prox_bar)
         bool running = true;
-        const uint64_t pol_done = dev::policy_evict_first();
         // phase profile (thread 0 of the first data warp of CTA 0): 8 wait-full, 9 dot, 10 barrier+publish, 11 wait-prox, 12 update, 13 sweep wait
         const bool prof = PROF && (a.stats != nullptr) && cta == 0 && dt == 0;
         long long pt[6] = {0, 0, 0, 0, 0, 0}; long long tc = prof ? clock64() : 0;
 #define ABB_TICK(k) do { if (PROF && prof) { const long long t_ = clock64(); pt[PROF == 1 ? (((k) == 0 || (k) == 3 || (k) == 5) ? 0 : 1) : (k)] += t_ - tc; tc = t_; } } while (0)
+
+        // One ring item = up to `ch` columns of a group (rows of this CTA) in a stage.
+        // dot_item<CBW>: partial gradients of the item's columns against the current residual tile -> wp[0 .. ncols)
+        auto dot_item = [&](auto cbw_tag, const T* xs, int ncols, double* wp) {
+            constexpr int CBW = decltype(cbw_tag)::value;          // 8 or 16 accumulators
+            const int64_t cs = a.rows_stride;
+#pragma unroll 1
+            for (int c0 = 0; c0 < ncols; c0 += CBW) {
+                T acc[CBW];
+#pragma unroll
+                for (int cc = 0; cc < CBW; ++cc) acc[cc] = 0;
+#pragma unroll 1
+                for (int v = dt; v < rows / VN; v += kBatchNDT) {
+                    T rv[VN], wv[VN], wr[VN];
+                    vec_load<T>(sr + (size_t)v * VN, rv);
+                    vec_load<T>(sw + (size_t)v * VN, wv);
+#pragma unroll
+                    for (int q = 0; q < VN; ++q) wr[q] = wv[q] * rv[q];
+#pragma unroll
+                    for (int cc = 0; cc < CBW; ++cc) {
+                        if (c0 + cc < ncols) {
+                            T xv[VN];
+                            vec_load<T>(xs + (int64_t)(c0 + cc) * cs + (size_t)v * VN, xv);
+#pragma unroll
+                            for (int q = 0; q < VN; ++q) acc[cc] += xv[q] * wr[q];
+                        }
+                    }
+                }
+                if (CBW == 16) {
+                    T a16[16];
+#pragma unroll
+                    for (int cc = 0; cc < 16; ++cc) a16[cc] = acc[cc % CBW];
+                    const T tot = warp_reduce16<T>(a16, lane);     // lane holds the warp total of column c0 + ((lane >> 1) & 15)
+                    const int col = c0 + ((lane >> 1) & 15);
+                    if ((lane & 1) == 0 && col < ncols) wp[col] = (double)tot;
+                } else {
+                    // transposed reduction of 8 accumulators: 3 halving steps + 2 plain steps; lane holds column (lane >> 2) & 7
+                    T v8[8];
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) v8[cc] = acc[cc % CBW];
+                    {
+                        const bool up = (lane & 16) != 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const T send = up ? v8[i] : v8[i + 4], keep = up ? v8[i + 4] : v8[i]; v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+                    }
+                    {
+                        const bool up = (lane & 8) != 0;
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) { const T send = up ? v8[i] : v8[i + 2], keep = up ? v8[i + 2] : v8[i]; v8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+                    }
+                    {
+                        const bool up = (lane & 4) != 0;
+                        const T send = up ? v8[0] : v8[1], keep = up ? v8[1] : v8[0];
+                        v8[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 2);
+                    v8[0] += __shfl_xor_sync(0xffffffffu, v8[0], 1);
+                    const int col = c0 + ((lane >> 2) & 7);
+                    if ((lane & 3) == 0 && col < ncols) wp[col] = (double)v8[0];
+                }
+            }
+        };
+        // axpy_item: r += X_item del
+        auto axpy_item = [&](const T* xs, int ncols, const T* dl) {
+            const int64_t cs = a.rows_stride;
+            constexpr int CBU = 8;
+#pragma unroll 1
+            for (int c0 = 0; c0 < ncols; c0 += CBU) {
+                T d[CBU];
+#pragma unroll
+                for (int cc = 0; cc < CBU; ++cc) d[cc] = (c0 + cc < ncols) ? dl[c0 + cc] : T(0);
+#pragma unroll 1
+                for (int v = dt; v < rows / VN; v += kBatchNDT) {
+                    T rv[VN];
+                    vec_load<T>(sr + (size_t)v * VN, rv);
+#pragma unroll
+                    for (int cc = 0; cc < CBU; ++cc) {
+                        if (c0 + cc < ncols) {
+                            T xv[VN];
+                            vec_load<T>(xs + (int64_t)(c0 + cc) * cs + (size_t)v * VN, xv);
+#pragma unroll
+                            for (int q = 0; q < VN; ++q) rv[q] += xv[q] * d[cc];
+                        }
+                    }
+                    vec_store<T>(sr + (size_t)v * VN, rv);
+                }
+            }
+        };
+        // waits for the next ring item, returns its stage
+        auto next_item = [&](const T*& xs, int& stage) -> bool {
+            stage = (int)(gitem % a.n_stages);
+            const uint32_t use = gitem / a.n_stages;
+            if (!dev::mbar_wait(&full_bar[stage], use & 1, abort_flag, halt)) return false;
+            xs = stages + (size_t)stage * a.stage_elems;
+            ++gitem;
+            return true;
+        };
+        auto release_item = [&](int stage) { __syncwarp(); if (lane == 0) dev::mbar_arrive(&empty_bar[stage]); };
 
         // D(b): partial gradients of the batch against the current residual tile
         auto dphase = [&](int kind, int count, int b) -> bool {
@@ -565,44 +696,19 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
             int gs_l = 0;                                          // lane k holds the size of group k (one load round per batch)
             if (lane < nbg) gs_l = a.meta[(kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane].gs;
             int off = 0;
-            for (int k = 0; k < nbg; ++k, ++gitem) {
+            for (int k = 0; k < nbg; ++k) {
                 const int gs = __shfl_sync(0xffffffffu, gs_l, k);
-                const int stage = (int)(gitem % a.n_stages);
-                const uint32_t use = gitem / a.n_stages;
-                if (!dev::mbar_wait(&full_bar[stage], use & 1, abort_flag, halt)) return false;
-                ABB_TICK(0);
-                const T* xs = stages + (size_t)stage * a.stage_elems;
-                const int64_t cs = a.rows_stride;
-#pragma unroll 1
-                for (int c0 = 0; c0 < gs; c0 += CB) {
-                    T acc[CB];
-#pragma unroll
-                    for (int cc = 0; cc < CB; ++cc) acc[cc] = 0;
-#pragma unroll 1
-                    for (int v = dt; v < rows / VN; v += kBatchNDT) {
-                        T rv[VN], wv[VN], wr[VN];
-                        vec_load<T>(sr + (size_t)v * VN, rv);
-                        vec_load<T>(sw + (size_t)v * VN, wv);
-#pragma unroll
-                        for (int q = 0; q < VN; ++q) wr[q] = wv[q] * rv[q];
-#pragma unroll
-                        for (int cc = 0; cc < CB; ++cc) {
-                            if (c0 + cc < gs) {
-                                T xv[VN];
-                                vec_load<T>(xs + (int64_t)(c0 + cc) * cs + (size_t)v * VN, xv);
-#pragma unroll
-                                for (int q = 0; q < VN; ++q) acc[cc] += xv[q] * wr[q];
-                            }
-                        }
-                    }
-                    const T tot = warp_reduce16<T>(acc, lane);
-                    const int col = c0 + ((lane >> 1) & 15);
-                    if ((lane & 1) == 0 && col < gs) wp[off + col] = (double)tot;
+                for (int c0 = 0; c0 < gs; c0 += a.ch) {
+                    const T* xs; int stage;
+                    if (!next_item(xs, stage)) return false;
+                    ABB_TICK(0);
+                    const int ncols = min(a.ch, gs - c0);
+                    if (a.ch <= 8) dot_item(std::integral_constant<int, 8>{}, xs, ncols, wp + off + c0);
+                    else dot_item(std::integral_constant<int, 16>{}, xs, ncols, wp + off + c0);
+                    release_item(stage);
+                    ABB_TICK(1);
                 }
-                __syncwarp();
-                if (lane == 0) dev::mbar_arrive(&empty_bar[stage]);
                 off += gs;
-                ABB_TICK(1);
             }
             __syncwarp();
             if (lane == 0) dev::mbar_arrive(&dbar[bcount & 1]);       // release: the exchange warps sum the partials and publish
@@ -610,50 +716,28 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
             ABB_TICK(2);
             return true;
         };
-        // U(b): r += X_k del_k for the groups of the batch that moved; X comes from L2 (streamed one batch earlier)
+        // U(b): r += X_k del_k for the groups of the batch that moved (tiles re-streamed through the ring, normally from L2)
         auto uphase = [&](int kind, int count, int b, int upar) -> bool {
             const int p0 = b * B, nbg = min(B, count - p0);
-            int gs_l = 0, col_l = 0;
-            if (lane < nbg) {
-                const GroupMeta mm = a.meta[(kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane];
-                gs_l = mm.gs; col_l = mm.col;
-            }
-            constexpr int CBU = 12;
+            int gs_l = 0;
+            if (lane < nbg) gs_l = a.meta[(kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + lane) : p0 + lane].gs;
             int off = 0;
             for (int k = 0; k < nbg; ++k, ++ucount) {
-                struct { int gs, col; } m{__shfl_sync(0xffffffffu, gs_l, k), __shfl_sync(0xffffffffu, col_l, k)};
+                const int gs = __shfl_sync(0xffffffffu, gs_l, k);
                 if (!dev::mbar_wait(&prox_bar[upar * kBatchMax + k], (uint32_t)(ubatch >> 1) & 1u, abort_flag, halt)) return false;
                 ABB_TICK(3);
                 if (ctrl->changed[upar][k]) {
                     const T* dl = del + (size_t)upar * Ccap + off;
-                    const T* xg = a.X + (int64_t)m.col * a.ld + r0;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < m.gs; c0 += CBU) {
-                        T d[CBU];
-#pragma unroll
-                        for (int cc = 0; cc < CBU; ++cc) d[cc] = (c0 + cc < m.gs) ? dl[c0 + cc] : T(0);
-#pragma unroll 1
-                        for (int v = dt; v < rows / VN; v += kBatchNDT) {
-                            T xv[CBU][VN];
-#pragma unroll
-                            for (int cc = 0; cc < CBU; ++cc) {
-                                if (c0 + cc < m.gs) dev::ld_hint(xg + (int64_t)(c0 + cc) * a.ld + (size_t)v * VN, xv[cc], pol_done);
-                            }
-                            T rv[VN];
-                            vec_load<T>(sr + (size_t)v * VN, rv);
-#pragma unroll
-                            for (int cc = 0; cc < CBU; ++cc) {
-                                if (c0 + cc < m.gs) {
-#pragma unroll
-                                    for (int q = 0; q < VN; ++q) rv[q] += xv[cc][q] * d[cc];
-                                }
-                            }
-                            vec_store<T>(sr + (size_t)v * VN, rv);
-                        }
+                    for (int c0 = 0; c0 < gs; c0 += a.ch) {
+                        const T* xs; int stage;
+                        if (!next_item(xs, stage)) return false;
+                        ABB_TICK(0);
+                        axpy_item(xs, min(a.ch, gs - c0), dl + c0);
+                        release_item(stage);
+                        ABB_TICK(4);
                     }
                 }
-                off += m.gs;
-                ABB_TICK(4);
+                off += gs;
             }
             return true;
         };
@@ -721,7 +805,7 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
             return C;
         };
         // issues the loads of a batch's current coefficients into registers: column t = lane + 32 j  ->  pa[j]
-        auto fetch_aold = [&](const GroupMeta& m, int nbg, P (&pa)[2]) {
+        auto fetch_aold = [&](const GroupMeta& m, int nbg, P (&pa)[2], P (&pr)[2]) {
             int adr[2] = {-1, -1};
             int off = 0;
             for (int k = 0; k < nbg; ++k) {
@@ -731,11 +815,11 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                 off += gs;
             }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) pa[j] = (adr[j] >= 0) ? (P)my_beta[adr[j]] : P(0);
+            for (int j = 0; j < 2; ++j) { pa[j] = (adr[j] >= 0) ? (P)my_beta[adr[j]] : P(0); pr[j] = (adr[j] >= 0) ? (P)my_brot[adr[j]] : P(0); }
         };
-        auto store_aold = [&](const P (&pa)[2], int par) {
+        auto store_aold = [&](const P (&pa)[2], const P (&pr)[2], int par) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) { const int t = lane + 32 * j; if (t < Ccap) aold[par * Ccap + t] = pa[j]; }
+            for (int j = 0; j < 2; ++j) { const int t = lane + 32 * j; if (t < Ccap) { aold[par * Ccap + t] = pa[j]; arot[par * Ccap + t] = pr[j]; } }
         };
 
         while (true) {
@@ -750,23 +834,23 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
             const int kind = phase;
             const int nb = (count + B - 1) / B;
             GroupMeta m_cur, m_nxt, m_nn; int ss_cur = 0, ss_nxt = 0, ss_nn = 0;
-            double gc[2] = {0, 0}; P cn[2] = {0, 0};        // gradient of the current batch / cross corrections for the next (columns lane, lane + 32)
+            P ga[4] = {0, 0, 0, 0};                         // batch gradient + corrections in panel-column space (see below)
             int C_cur = 0, C_nxt = 0;
             if (nb > 0) {
                 load_batch(kind, count, 0, m_cur, ss_cur);
                 load_batch(kind, count, 1, m_nxt, ss_nxt);
                 C_cur = batch_cols(m_cur); C_nxt = batch_cols(m_nxt);
-                P pa[2];
-                fetch_aold(m_cur, min(B, count), pa);
-                store_aold(pa, bcount & 1);
+                P pa[2], pr[2];
+                fetch_aold(m_cur, min(B, count), pa, pr);
+                store_aold(pa, pr, bcount & 1);
                 __syncwarp();
             }
             for (int b = 0; b < nb; ++b, ++bcount, ++pitem) {
                 const int par = bcount & 1;
                 const int nbg = min(B, count - b * B);
                 load_batch(kind, count, b + 2, m_nn, ss_nn);                      // in flight during this batch
-                P pa_nxt[2];
-                fetch_aold(m_nxt, max(0, min(B, count - (b + 1) * B)), pa_nxt);   // in flight during this batch (disjoint groups)
+                P pa_nxt[2], pr_nxt[2];
+                fetch_aold(m_nxt, max(0, min(B, count - (b + 1) * B)), pa_nxt, pr_nxt);   // in flight during this batch (disjoint groups)
                 const int pslot = pitem & 1;
                 const T* Q = pslots + (size_t)pslot * a.pslot_elems;
                 ABB_TICK(4);
@@ -776,14 +860,18 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                 ABB_TICK(1);
                 if (PROF && prof) ++pt[7];
                 __syncwarp();
-                // the batch's all-reduced gradient (+ the cross corrections collected during the previous batch) moves into
-                // registers: lane l holds columns l and l + 32
+                // the batch's all-reduced gradient moves into registers in panel-column space (lane l holds t = 4 l .. 4 l + 3):
+                // t < Ccap are this batch's columns (gradient + the cross corrections collected during the previous batch, which sit
+                // Ccap columns higher), t >= Ccap collects the corrections for the next batch
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int t = lane + 32 * j;
-                    gc[j] = (t < C_cur) ? gstale[par * Ccap + t] + (double)cn[j] : 0.0;
-                    cn[j] = 0;
+                for (int j = 0; j < 4; ++j) { const int t = 4 * lane + j; if (t >= Ccap && t < ldq) corr[t - Ccap] = ga[j]; }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = 4 * lane + j;
+                    ga[j] = (t < C_cur) ? (P)gstale[par * Ccap + t] + corr[t] : P(0);
                 }
+                __syncwarp();
                 int gs_max_b = m_cur.gs;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) gs_max_b = max(gs_max_b, __shfl_xor_sync(0xffffffffu, gs_max_b, o));
@@ -796,7 +884,7 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                     // rotated loop (k = -1 only issues the static loads of group 0): one call site per phase
 #pragma unroll 1
                     for (int k = -1; k < nbg; ++k) {
-                        int changed = 0, ss = 0; bool was_active = false;
+                        int changed = 0, ss = 0; bool was_active = false; P del_c = 0;
                         T* dl = del + (size_t)par * Ccap + off;
                         if (k >= 0) {
                             gs = __shfl_sync(0xffffffffu, m_cur.gs, k);
@@ -807,13 +895,17 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                             const P pk = (P)__shfl_sync(0xffffffffu, m_cur.pen, k);
                             const T* rec = Q + Ccap * ldq + k * a.rec_stride;
                             P* ao = aold + par * Ccap + off;
-                            const int idx = off + (lane < gs ? lane : 0);
-                            const double g0 = __shfl_sync(0xffffffffu, gc[0], idx & 31), g1 = __shfl_sync(0xffffffffu, gc[1], idx & 31);
-                            const double g_in = (idx >> 5) ? g1 : g0;
+                            const int idx = off + ((lane & 15) < gs ? (lane & 15) : 0);      // panel column of this lane's element
+                            P g_in;
+                            {
+                                const P s0 = __shfl_sync(0xffffffffu, ga[0], idx >> 2), s1 = __shfl_sync(0xffffffffu, ga[1], idx >> 2);
+                                const P s2 = __shfl_sync(0xffffffffu, ga[2], idx >> 2), s3 = __shfl_sync(0xffffffffu, ga[3], idx >> 2);
+                                g_in = (idx & 2) ? ((idx & 1) ? s3 : s2) : ((idx & 1) ? s1 : s0);
+                            }
                             if (gs == 1) {                                       // solver_gaussian_pin_naive.hpp:75-108
                                 const P ak_old = ao[0];
-                                const P A_kk = (P)rec[0], xm = (P)rec[1];
-                                P gk = (P)__shfl_sync(0xffffffffu, g_in, 0) - xm * (P)ps.resid_sum * (P)a.intercept + ak_old * A_kk;
+                                const P A_kk = (P)rec[0], xm = (P)rec[a.use_ext ? 4 : 1];
+                                P gk = __shfl_sync(0xffffffffu, g_in, 0) - xm * (P)ps.resid_sum * (P)a.intercept + ak_old * A_kk;
                                 const P vv = fabs(gk) - l1 * pk;                 // update_coordinate, pin_base.hpp:181-195
                                 P ak = (vv > P(0)) ? copysign(vv, gk) / (A_kk + l2 * pk) : P(0);
                                 ak = (P)(T)ak;
@@ -823,14 +915,21 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                                     ps.cm = fmax(ps.cm, (double)(A_kk * dd * dd));
                                     ps.rsq += (double)(dd * (2 * gk - dd * A_kk));
                                     ps.resid_sum -= (double)(xm * dd);
-                                    if (lane == 0) { my_beta[begin] = (T)ak; dl[0] = (T)(-dd); }
+                                    if (lane == 0) { my_beta[begin] = (T)ak; my_brot[begin] = (T)ak; dl[0] = (T)(-dd); }
+                                    del_c = ((lane & 15) == 0) ? -dd : P(0);
                                     changed = 1;
                                 }
                             } else if (GSP <= 16) {
                                 changed = prox_post<T, P, GL>(pre, gs, g_in, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters, (P)a.dbeta_tol,
-                                                              a.intercept, ps, lane, p_gk, my_beta + begin, dl, (PROF == 2 && prof) ? ppx : nullptr);
+                                                              a.intercept, ps, lane, p_gk, my_beta + begin, my_brot + begin, dl, del_c, (PROF == 2 && prof) ? ppx : nullptr);
                             } else {                                             // 12 < gs <= 32: shared-memory reductions
-                                if (lane < gs) gcur[lane] = g_in;
+                                if (lane < 16 && lane < gs) gcur[lane] = (double)g_in;
+                                if (gs > 16) {                                   // columns 16 .. gs-1 of a large group
+                                    const int idx2 = off + 16 + ((lane & 15) < gs - 16 ? (lane & 15) : 0);
+                                    const P s0 = __shfl_sync(0xffffffffu, ga[0], idx2 >> 2), s1 = __shfl_sync(0xffffffffu, ga[1], idx2 >> 2);
+                                    const P s2 = __shfl_sync(0xffffffffu, ga[2], idx2 >> 2), s3 = __shfl_sync(0xffffffffu, ga[3], idx2 >> 2);
+                                    if (lane < 16 && 16 + lane < gs) gcur[16 + lane] = (double)((idx2 & 2) ? ((idx2 & 1) ? s3 : s2) : ((idx2 & 1) ? s1 : s0));
+                                }
                                 __syncwarp();
                                 const ProxCtx<T, P> px{ao, nullptr, p_gk, nullptr, nullptr, p_at, p_scr, dl, gcur, my_beta};
                                 const ProxPre<P> pre2 = prox_small_pre<T, P>(rec, gs, ao, lane);
@@ -848,11 +947,11 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                         // static loads of the next group, issued behind this group's corrections
                         if (GSP <= 16 && k + 1 < nbg) {
                             const int gs1 = __shfl_sync(0xffffffffu, m_cur.gs, k + 1);
-                            if (gs1 > 1) prox_pre<T, P, GL>(pre, Q + Ccap * ldq + (k + 1) * a.rec_stride, gs1, aold + par * Ccap + off + gs, lane);
+                            if (gs1 > 1) prox_pre<T, P, GL>(pre, Q + Ccap * ldq + (k + 1) * a.rec_stride, gs1, aold + par * Ccap + off + gs, arot + par * Ccap + off + gs, lane);
                         }
                         if (changed) {
-                            if (GSP <= 16) apply_corrections<T, P, GL>(Q, ldq, Ccap, off, gs, dl, C_cur, C_nxt, gc, cn, lane);
-                            else apply_corrections<T, P, 0>(Q, ldq, Ccap, off, gs, dl, C_cur, C_nxt, gc, cn, lane);
+                            if (GSP <= 16) apply_corrections<T, P, GL>(Q, ldq, off, gs, dl, del_c, ga, lane);
+                            else apply_corrections<T, P, 0>(Q, ldq, off, gs, dl, del_c, ga, lane);
                             if (kind == kSweepScreen && !was_active) {           // add_active_set (:294-304)
                                 if (ps.A >= a.max_active_size) ps.error = kErrMaxActive;
                                 else {
@@ -868,13 +967,13 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                     }
                 };
                 // (one lane-local instantiation only: several of them blow the register budget of the whole kernel)
-                if (gs_max_b <= 12) run_batch(std::integral_constant<int, 12>{});
+                if (a.use_ext) run_batch(std::integral_constant<int, 12>{});
                 else run_batch(std::integral_constant<int, 32>{});
                 if (ps.error) { final_error = ps.error; break; }
                 if (lane >= nbg && lane < kBatchMax) dev::mbar_arrive(&prox_bar[par * kBatchMax + lane]);   // keep every barrier at one phase per batch
                 __syncwarp();
                 if (lane == 0) dev::mbar_arrive(&pempty_bar[pslot]);
-                store_aold(pa_nxt, par ^ 1);
+                store_aold(pa_nxt, pr_nxt, par ^ 1);
                 m_cur = m_nxt; ss_cur = ss_nxt; C_cur = C_nxt;
                 m_nxt = m_nn; ss_nxt = ss_nn; C_nxt = batch_cols(m_nxt);
                 __syncwarp();
@@ -924,7 +1023,8 @@ pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairI
                  double* __restrict__ part, int64_t total, int rows_per_block)
 {
     constexpr int VN = VecT<T>::N;
-    __shared__ double s_red[8][17];
+    constexpr int TS = 5;                                  // 5 x 5 register tile: a 10 x 10 block takes 4 passes of 10 vector loads
+    __shared__ double s_red[8][TS * TS + 1];
     const PairItem it = items[blockIdx.x];
     const int rb = blockIdx.y;
     const int64_t row0 = (int64_t)rb * rows_per_block;
@@ -933,18 +1033,18 @@ pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairI
     const T* Xs = X + (int64_t)it.col_s * ld;
     const T* Xt = X + (int64_t)it.col_t * ld;
     double* out = part + (size_t)rb * total + it.part_off;
-    for (int a0 = 0; a0 < it.gs_s; a0 += 4) {
-        for (int b0 = 0; b0 < it.gs_t; b0 += 4) {
-            T acc[4][4];
+    for (int a0 = 0; a0 < it.gs_s; a0 += TS) {
+        for (int b0 = 0; b0 < it.gs_t; b0 += TS) {
+            T acc[TS][TS];
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int x = 0; x < TS; ++x)
 #pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = 0;
+                for (int y = 0; y < TS; ++y) acc[x][y] = 0;
             for (int64_t i = row0 + (int64_t)tid * VN; i < row1; i += 256 * VN) {
-                T wv[VN], xa[4][VN], xb[4][VN];
+                T wv[VN], xa[TS][VN], xb[TS][VN];
                 vec_load<T>(w + i, wv);
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
+                for (int x = 0; x < TS; ++x) {
                     if (a0 + x < it.gs_s) {
                         vec_load<T>(Xs + (int64_t)(a0 + x) * ld + i, xa[x]);
 #pragma unroll
@@ -955,7 +1055,7 @@ pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairI
                     }
                 }
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
+                for (int y = 0; y < TS; ++y) {
                     if (b0 + y < it.gs_t) vec_load<T>(Xt + (int64_t)(b0 + y) * ld + i, xb[y]);
                     else {
 #pragma unroll
@@ -963,24 +1063,24 @@ pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairI
                     }
                 }
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
+                for (int x = 0; x < TS; ++x)
 #pragma unroll
-                    for (int y = 0; y < 4; ++y)
+                    for (int y = 0; y < TS; ++y)
 #pragma unroll
                         for (int q = 0; q < VN; ++q) acc[x][y] += xa[x][q] * xb[y][q];
             }
 #pragma unroll
-            for (int x = 0; x < 4; ++x)
+            for (int x = 0; x < TS; ++x)
 #pragma unroll
-                for (int y = 0; y < 4; ++y) {
+                for (int y = 0; y < TS; ++y) {
                     const double s = dev::warp_sum((double)acc[x][y]);
-                    if (lane == 0) s_red[warp][x * 4 + y] = s;
+                    if (lane == 0) s_red[warp][x * TS + y] = s;
                 }
             __syncthreads();
-            if (tid < 16) {
+            if (tid < TS * TS) {
                 double s = 0;
                 for (int wi = 0; wi < 8; ++wi) s += s_red[wi][tid];
-                const int aa = a0 + tid / 4, bb = b0 + tid % 4;
+                const int aa = a0 + tid / TS, bb = b0 + tid % TS;
                 if (aa < it.gs_s && bb < it.gs_t) out[aa * it.gs_t + bb] = s;
             }
             __syncthreads();

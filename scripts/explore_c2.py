@@ -58,5 +58,5 @@ for rep in range(2):
         for k, nm in enumerate(names):
             v = tr[:, k] - t0
             print(f"    trace {nm:12s}: min {v.min():8.0f} ns  median {np.median(v):8.0f}  max {v.max():8.0f}  (argmax cta {int(v.argmax())})")
-    print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["panels", "screen_records", "cov_device", "run_pin", "invariance", "screen_host", "abs_grad", "update_solutions"]))
+    print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["pin_presync", "pin_launch", "pin_sync", "pin_download", "panels", "panels_presync", "panels_launch", "panels_sync", "screen_records", "cov_device", "run_pin", "invariance", "screen_host", "abs_grad", "update_solutions"]))
     print("  phases: screen %.3f fit %.3f inv %.3f kkt %.3f" % (sum(st.benchmark_screen), sum(st.benchmark_fit_active), sum(st.benchmark_invariance), sum(st.benchmark_kkt)))
