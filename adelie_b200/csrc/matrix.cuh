@@ -328,7 +328,7 @@ struct DenseMatrix {
         SweepContext& ctx = SweepContext::get();
         if (L.K > 16) throw core_error("multi-response problems with more than 16 classes are not supported by the fused sweep kernel.");
         SweepGeometry g = plan_sweep<T>(ld, L.gs_max, L.rec_max, L.K, L.feat_max);
-        last_geom = g;
+        last_geom = g; last_bgeom.ok = false;
         PinKernelArgs<T> a{};
         a.X = X; a.ld = ld; a.n_pad = ld; a.K = L.K; a.resid = L.resid; a.weights = L.weights;
         a.meta = L.meta; a.S = L.S; a.grec = L.grec;
