@@ -448,6 +448,9 @@ static int state_vec_f64(const PathState<T>& s, const std::string& nm, double* o
     if (nm == "benchmark_fit_active") return copy_vec<double>(s.benchmark_fit_active, out, cap, len);
     if (nm == "benchmark_kkt") return copy_vec<double>(s.benchmark_kkt, out, cap, len);
     if (nm == "benchmark_invariance") return copy_vec<double>(s.benchmark_invariance, out, cap, len);
+    if (nm == "launch_cols") return copy_vec<double>(s.launch_cols, out, cap, len);
+    if (nm == "launch_sweeps") return copy_vec<double>(s.launch_sweeps, out, cap, len);
+    if (nm == "launch_ms") return copy_vec<double>(s.launch_ms, out, cap, len);
     if (nm == "sweep_stats") {
         const int64_t N = 32 + 8 * 160;
         *len = N;

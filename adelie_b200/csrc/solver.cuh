@@ -158,6 +158,7 @@ struct PathState {
     PanelList pl_screen, pl_active;
     DevBuf<PairItem> d_pair_items;
     long long n_panels_built = 0, n_batched_launches = 0;
+    std::vector<double> launch_cols, launch_sweeps, launch_ms;      // per sweep-kernel launch: column visits, sweeps, CUDA-event time
     int gs_max_screen = 1, rec_max_screen = 4, feat_max_screen = 1;
     PinnedBuf<PinScalars> h_sc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -469,6 +470,7 @@ struct PathState {
             AB_CUDA(cudaStreamSynchronize(0));
             ++n_kernel_launches;
             AB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+            launch_cols.push_back((double)h_sc.p->n_col_updates); launch_sweeps.push_back((double)h_sc.p->iters); launch_ms.push_back(ms);
         } else {
             // batched look-ahead kernel: Gram panels for both sweep orders; the kernel hands control back when the active list
             // outgrew its panels (after a screen sweep that added groups), everything else continues on the device
@@ -479,6 +481,7 @@ struct PathState {
             BatchLaunch<T> bl{};
             bl.start_phase = kSweepActive; bl.beta_rot_in = d_screen_beta_rot.p;
             size_t act_now = active_set_size;
+            double cols_seen = 0, sweeps_seen = 0;
             while (true) {
                 ent.assign(act32.begin(), act32.begin() + act_now);
                 ensure_panels(pl_active, ent, bg.B, bg.Ccap, d_w);
@@ -492,6 +495,9 @@ struct PathState {
                 ++n_kernel_launches; ++n_batched_launches;
                 float m1 = 0; AB_CUDA(cudaEventElapsedTime(&m1, ev0, ev1));
                 ms += m1;
+                launch_cols.push_back((double)h_sc.p->n_col_updates - cols_seen); launch_sweeps.push_back((double)h_sc.p->iters - sweeps_seen);
+                launch_ms.push_back(m1);
+                cols_seen = (double)h_sc.p->n_col_updates; sweeps_seen = (double)h_sc.p->iters;
                 if (h_sc.p->error || h_sc.p->pad != kBatchNeedPanels) break;
                 // the active list grew: fetch the new entries, make replica 0 the input of the next launch
                 const size_t act_new = (size_t)h_sc.p->active_set_size;

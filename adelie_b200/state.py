@@ -22,7 +22,7 @@ logger = logging.getLogger("adelie_b200")
 
 _VEC_F = ["lmda_path", "screen_beta", "grad", "abs_grad", "devs", "lmdas", "X_means", "screen_X_means", "screen_vars",
           "resid", "eta", "sweep_stats", "benchmark_screen", "benchmark_fit_screen", "benchmark_fit_active", "benchmark_kkt",
-          "benchmark_invariance"]
+          "benchmark_invariance", "launch_cols", "launch_sweeps", "launch_ms"]
 _VEC_I = ["screen_set", "screen_begins", "screen_is_active", "active_set", "n_valid_solutions", "active_sizes", "screen_sizes"]
 _SCALARS = ["lmda_max", "lmda", "rsq", "resid_sum", "y_mean", "y_var", "loss_null", "loss_full", "beta0", "active_set_size",
             "n_sweeps", "n_group_updates", "n_col_updates", "n_irls", "n_pin_solves", "n_kernel_launches", "time_sweep_kernel", "sweep_ncta",

@@ -140,19 +140,25 @@ def run_ours(args):
     barrier()
     _lib.check(L.ab_timer_start())
     t0 = time.perf_counter()
-    sweeps = updates = cols = launches = 0; tk = 0.0; pins = 0
+    sweeps = updates = cols = launches = 0; tk = 0.0; pins = 0; klaunch = 0
     for _ in range(args.steps):
         st = solve_resident()
         assert st.error == "", st.error
         sweeps += st.n_sweeps; updates += st.n_group_updates; cols += st.n_col_updates; launches += st.n_kernel_launches
-        tk += st.time_sweep_kernel; pins += st.n_pin_solves
+        tk += st.time_sweep_kernel; pins += st.n_pin_solves; klaunch += len(st.launch_ms)
     barrier()
     ms = C.c_double(); _lib.check(L.ab_timer_stop(C.byref(ms)))
     t_res = ms.value * 1e-3
     clocks = sampler.stop()
     path_info = dict(n_lmdas=len(st.lmdas), dev_last=float(st.devs[-1]), active_last=int(st.active_sizes[-1]),
                      screen_last=int(st.screen_sizes[-1]), sweeps_per_path=sweeps // args.steps, group_updates_per_path=updates // args.steps,
-                     sweep_ctas=st.sweep_ncta, sweep_stages=st.sweep_stages, sweep_staged=st.sweep_staged)
+                     sweep_ctas=st.sweep_ncta, sweep_stages=st.sweep_stages, sweep_staged=st.sweep_staged, sweep_batch=st.sweep_batch)
+    if args.dump_launches and rank == 0:
+        # per-launch algorithmic bytes / CUDA-event times of the LAST timed path (to line an ncu capture up with its launch)
+        rows = [dict(i=i, algo_bytes=float(sz * n_local * (c + 3 * s)), sweeps=int(s), ms=float(m))
+                for i, (c, s, m) in enumerate(zip(st.launch_cols, st.launch_sweeps, st.launch_ms))]
+        with open(args.dump_launches, "w") as f:
+            json.dump(rows, f)
 
     # ---------------- e2e arm: host buffers, H2D of X from pinned memory + D2H of the solution inside the timed region
     e2e = None
@@ -198,6 +204,19 @@ def run_ours(args):
     peak, peak_src = peak_hbm_gbs()
     algo_bytes = sz * n_local * (cols + 3 * sweeps)           # per GPU: s*n_local*sum(gs) + 3*s*n_local per sweep
     achieved = algo_bytes / tk / 1e9 if tk > 0 else 0.0
+    kname = ("pin_solve_batched_kernel (fused look-ahead CD sweep, batches of %d groups), per GPU" % path_info["sweep_batch"]
+             if path_info["sweep_batch"] > 1 else "pin_solve_kernel (fused CD sweep), per GPU")
+    # DRAM traffic: measured dram bytes / algorithmic bytes of ONE captured launch (profiles/r1_traffic.json, from an
+    # `ncu --set full` capture lined up with --dump-launches), applied to the average launch of this run
+    traffic = args.traffic
+    if traffic is None:
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("kernel", "").split(" ")[0] == kname.split(" ")[0] and world == 1:
+                traffic = tj["dram_over_algorithmic"] * algo_bytes / max(klaunch, 1)
+        except Exception:
+            traffic = None
     out = {
         "metric": "cd_sweeps_per_sec", "value": sweeps_all / t_res, "unit": "sweeps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -208,10 +227,10 @@ def run_ours(args):
                    **path_info},
         "path_time_s": t_res / args.steps,
         "group_updates_per_sec": updates / t_res,
-        "roofline": {"bound": "hbm", "kernel": "pin_solve_kernel (fused CD sweep), per GPU", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0,
-                     "algorithmic_bytes_per_launch": algo_bytes / max(pins, 1), "avg_launch_ms": 1e3 * tk / max(pins, 1),
-                     "launches_timed": pins, "kernel_share_of_step": tk / t_res, "traffic": args.traffic},
+                     "algorithmic_bytes_per_launch": algo_bytes / max(klaunch, 1), "avg_launch_ms": 1e3 * tk / max(klaunch, 1),
+                     "launches_timed": klaunch, "kernel_share_of_step": tk / t_res, "traffic": traffic},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
     }
@@ -290,6 +309,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--dump-launches", type=str, default=None, help="write per-launch algorithmic bytes / times of the last timed path to this JSON file")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch of the sweep kernel from an ncu capture (profiles/)")
     args = ap.parse_args()
     if args.impl == "reference":
