@@ -279,9 +279,18 @@ struct DenseMatrix {
         int rows_per_block = (int)((ld + n_rb - 1) / n_rb);
         rows_per_block = (rows_per_block + kRowAlign - 1) / kRowAlign * kRowAlign;
         n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
-        part.reserve_keep((size_t)n_rb * total, stream);
+        part.reserve_keep((size_t)(n_rb + 1) * total, stream);
         pair_gram_kernel<T><<<dim3(n_items, n_rb), 256, 0, stream>>>(X, ld, ld, items_dev, w, part.p, total, rows_per_block);
-        pair_gram_finalize_kernel<T><<<n_items, 128, 0, stream>>>(items_dev, part.p, n_rb, total, Q, ldq);
+        DistContext& dc = DistContext::get();
+        if (dc.active()) {
+            // row-sharded: sum the row blocks, then the local blocks over the ranks, then scatter into the panels
+            double* tmp = part.p + (size_t)n_rb * total;
+            sum_parts_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, total, tmp);
+            dc.allreduce<double>(tmp, total, stream);
+            pair_gram_finalize_kernel<T><<<n_items, 128, 0, stream>>>(items_dev, tmp, 1, total, Q, ldq);
+        } else {
+            pair_gram_finalize_kernel<T><<<n_items, 128, 0, stream>>>(items_dev, part.p, n_rb, total, Q, ldq);
+        }
         AB_CUDA(cudaGetLastError());
     }
 
@@ -308,6 +317,11 @@ struct DenseMatrix {
         a.ll1 = ctx.ll.p; a.ll2 = ctx.ll2.p; a.ncta_pad = g.ncta_pad;
         { int f = 1; while (f * f < g.ncta) ++f; a.fan = std::max(1, f); }
         a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
+        {
+            DistContext& dc = DistContext::get();
+            a.rank = dc.active() ? dc.rank : 0; a.world = dc.active() ? dc.world : 1;
+            for (int r = 0; r < kMaxRanksDev; ++r) a.ll3_peer[r] = (dc.active() && r < dc.world) ? dc.ll3(r) : nullptr;
+        }
         a.lmda = L.lmda; a.alpha = L.alpha; a.tol = L.tol; a.newton_tol = L.newton_tol; a.dbeta_tol = Configs::dbeta_tol;
         a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
         a.start_phase = bl.start_phase;

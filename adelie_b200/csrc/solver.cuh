@@ -461,7 +461,7 @@ struct PathState {
         const size_t old_active = active_set_size;
         float ms = 0;
         BatchGeometry bg{};
-        if (static_weights && K == 1 && !DistContext::get().active()) bg = plan_batched<T>(X->n_pad(), gs_max_screen, rec_max_screen);
+        if (static_weights && K == 1) bg = plan_batched<T>(X->n_pad(), gs_max_screen, rec_max_screen);
         if (!bg.ok) {
             AB_CUDA(cudaEventRecord(ev0, 0));
             X->pin_solve(L);
@@ -487,6 +487,7 @@ struct PathState {
                 ensure_panels(pl_active, ent, bg.B, bg.Ccap, d_w);
                 bl.panels_screen = pl_screen.Q.p; bl.panels_active = pl_active.Q.p; bl.n_active_panelled = (int)act_now;
                 { AB_TIME(timers, "pin_launch");
+                  if (DistContext::get().active()) DistContext::get().allreduce<double>(d_scal.p, 1);    // rank barrier: the peers' exchange slots of the previous launch are free
                   AB_CUDA(cudaEventRecord(ev0, 0));
                   X->pin_solve_batched(L, bg, bl);
                   AB_CUDA(cudaEventRecord(ev1, 0));

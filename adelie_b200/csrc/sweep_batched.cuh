@@ -53,6 +53,8 @@ struct BatchKernelArgs {
     int n_active_panelled;                               // active-list positions covered by panels_active
     int B, Ccap;
     dev::LLLine* ll1; dev::LLLine* ll2; int ncta_pad; int fan;
+    // row-sharded multi-GPU (level 3 of the exchange): ll3_peer[r] = rank r's line buffer [4][64][8] mapped over NVLink
+    dev::LLLine* ll3_peer[8]; int rank, world;
     uint32_t* epoch; int* abort_flag;
     double lmda, alpha, tol, newton_tol, dbeta_tol;
     long long max_iters; int newton_max_iters; int max_active_size; int intercept;
@@ -546,22 +548,47 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                         if (ok) dev::ll_store(a.ll2 + ((size_t)(slot * kBatchColsMax + c) * 32 + my_group), s, e);
                     }
                     const dev::LLLine* base2 = a.ll2 + ((size_t)(slot * kBatchColsMax + c) * 32);
+                    const bool multi_gpu = a.world > 1;
                     double s = 0;
+                    if (!multi_gpu || cta == 0) {                // level 2: every CTA (one GPU) / the GPU's leader CTA (several GPUs)
 #pragma unroll 1
-                    for (int g0 = 0; g0 < n_groups && ok; g0 += 8) {
-                        double v[8]; bool got[8];
+                        for (int g0 = 0; g0 < n_groups && ok; g0 += 8) {
+                            double v[8]; bool got[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) { v[u] = 0; got[u] = (g0 + u >= n_groups); }
+                            for (int u = 0; u < 8; ++u) { v[u] = 0; got[u] = (g0 + u >= n_groups); }
+                            dev::SpinGuard guard;
+                            while (ok) {
+                                bool all = true;
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) if (!got[u]) { got[u] = dev::ll_try_load(base2 + g0 + u, e, v[u]); all &= got[u]; }
+                                if (all) break;
+                                if (guard.give_up(abort_flag, halt)) ok = false;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) if (g0 + u < n_groups) s += v[u];
+                        }
+                    }
+                    if (multi_gpu) {
+                        // level 3 over NVLink: the leader CTA stores this GPU's total into EVERY rank's line buffer (peer-to-peer
+                        // stores through NVSwitch); every CTA of every GPU then reads its own GPU's `world` lines, rank order
+                        if (cta == 0 && ok)
+                            for (int r = 0; r < a.world; ++r)
+                                dev::ll_store_sys(a.ll3_peer[r] + ((size_t)(slot * kBatchColsMax + c) * kMaxRanksDev + a.rank), s, e);
+                        const dev::LLLine* base3 = a.ll3_peer[a.rank] + (size_t)(slot * kBatchColsMax + c) * kMaxRanksDev;
+                        double v[kMaxRanksDev]; bool got[kMaxRanksDev];
+#pragma unroll
+                        for (int u = 0; u < kMaxRanksDev; ++u) { v[u] = 0; got[u] = (u >= a.world); }
                         dev::SpinGuard guard;
                         while (ok) {
                             bool all = true;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) if (!got[u]) { got[u] = dev::ll_try_load(base2 + g0 + u, e, v[u]); all &= got[u]; }
+                            for (int u = 0; u < kMaxRanksDev; ++u) if (!got[u]) { got[u] = dev::ll_try_load_sys(base3 + u, e, v[u]); all &= got[u]; }
                             if (all) break;
                             if (guard.give_up(abort_flag, halt)) ok = false;
                         }
+                        s = 0;
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) if (g0 + u < n_groups) s += v[u];
+                        for (int u = 0; u < kMaxRanksDev; ++u) if (u < a.world) s += v[u];
                     }
                     gstale[(bcount & 1) * Ccap + c] = s;
                 }

@@ -18,12 +18,16 @@ def main():
     _lib.check(_lib.load().ab_set_device(int(os.environ.get("LOCAL_RANK", rank))))
     results = []
     for (n, p, G, glm_name, dtype, kw) in [
+        (40_000, 200, 20, "gaussian", np.float32, dict(tol=1e-7, newton_tol=1e-6, equal_groups=True)),    # batched kernel + NVLink level 3
+        (16_000, 120, 12, "gaussian", np.float64, dict(tol=1e-12, equal_groups=True)),                    # batched kernel, float64
+        (6_000, 64, 64, "gaussian", np.float64, dict(tol=1e-12, equal_groups=True)),                      # lasso, batched
         (40_000, 120, 24, "gaussian", np.float64, dict(tol=1e-12)),
         (3_000, 60, 60, "gaussian", np.float64, dict(tol=1e-12, alpha=0.7)),           # few rows: single-CTA kernels + level 3
         (40_000, 100, 20, "binomial", np.float64, dict(tol=1e-12, irls_tol=1e-10, alpha=0.5)),
         (64_000, 200, 20, "gaussian", np.float32, dict(tol=1e-7, newton_tol=1e-6)),
     ]:
-        data = ad.data.dense(n, p, G, glm=glm_name, seed=11)
+        equal = kw.pop("equal_groups", False)
+        data = ad.data.dense(n, p, G, glm=glm_name, seed=11, equal_groups=equal)
         X = np.asfortranarray(data["X"], dtype=dtype); y = data["glm"].y.astype(dtype)
         mk = (lambda yy: ad.glm.gaussian(yy, dtype=dtype)) if glm_name == "gaussian" else (lambda yy: ad.glm.binomial(yy, dtype=dtype))
         common = dict(groups=data["groups"], penalty=data["penalty"].astype(dtype), early_exit=False, lmda_path_size=12, min_ratio=0.1,
@@ -46,7 +50,7 @@ def main():
         td.all_gather_object(blob, B.tobytes())
         same = all(b == blob[0] for b in blob)
         if rank == 0:
-            print(f"n={n} p={p} {glm_name} {np.dtype(dtype).name}: rows[{lo},{hi}) rel_beta={rel:.2e} rel_icpt={reli:.2e} identical_on_all_ranks={same} ncta={st.sweep_ncta} -> {'ok' if good and same else 'FAIL'}", flush=True)
+            print(f"n={n} p={p} {glm_name} {np.dtype(dtype).name}: rows[{lo},{hi}) rel_beta={rel:.2e} rel_icpt={reli:.2e} identical_on_all_ranks={same} ncta={st.sweep_ncta} batch={st.sweep_batch} batched_launches={st.n_batched_launches} -> {'ok' if good and same else 'FAIL'}", flush=True)
         ok = ok and good and same
     if rank == 0:
         print("DIST PASS" if ok else "DIST FAIL", flush=True)
