@@ -55,6 +55,7 @@ SYMBOLS = [
     "ab_dist_init", "ab_dist_connect", "ab_dist_allreduce_f64", "ab_dist_info",
     "ab_configs_set", "ab_configs_get",
     "ab_matrix_dense_create", "ab_matrix_dense_alloc", "ab_matrix_dense_fill_normal", "ab_matrix_dense_download",
+    "ab_matrix_sparse_create", "ab_matrix_sparse_alloc_random", "ab_matrix_sparse_nnz", "ab_matrix_sparse_download",
     "ab_matrix_free", "ab_matrix_rows", "ab_matrix_cols", "ab_matrix_cmul", "ab_matrix_ctmul", "ab_matrix_bmul",
     "ab_matrix_btmul", "ab_matrix_mul", "ab_matrix_cov", "ab_matrix_sq_mul", "ab_matrix_sp_tmul",
     "ab_glm_create", "ab_glm_free", "ab_glm_gradient", "ab_glm_hessian", "ab_glm_inv_hessian_gradient", "ab_glm_loss",

@@ -160,6 +160,50 @@ int ab_matrix_dense_download(ab_matrix* m, void* host, int64_t row0, int64_t nro
     else m->f64->download((double*)host, row0, nrows, col0, ncols, ldh);
     AB_CATCH
 }
+// sparse CSC (reference: adelie.matrix.sparse -> MatrixNaiveSparse{32,64}F, py_matrix.cpp:1878-1968; matrix_naive_sparse.ipp)
+int ab_matrix_sparse_create(int dtype, int64_t n, int64_t p, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
+                            int n_threads, ab_matrix** out) {
+    AB_TRY
+    if (n < 1 || p < 1) throw core_error("matrix must have at least one row and one column.");
+    if (n_threads < 1) throw core_error("n_threads must be >= 1.");
+    if (indptr[0] != 0 || indptr[p] != nnz) throw core_error("sparse matrix: inconsistent column pointers.");
+    for (int64_t j = 0; j < p; ++j) {
+        if (indptr[j + 1] < indptr[j]) throw core_error("sparse matrix: column pointers must be non-decreasing.");
+        for (int64_t k = indptr[j]; k < indptr[j + 1]; ++k) {
+            if (indices[k] < 0 || indices[k] >= n) throw core_error("sparse matrix: row index out of range.");
+            if (k > indptr[j] && indices[k] <= indices[k - 1]) throw core_error("sparse matrix: row indices must be sorted and unique inside every column.");
+        }
+    }
+    auto* m = new ab_matrix{dtype};
+    if (dtype == AB_F32) { m->f32 = new DenseMatrix<float>(n, p, true, nnz); m->f32->n_threads = n_threads; m->f32->upload_csc(indptr, indices, (const float*)values); }
+    else { m->f64 = new DenseMatrix<double>(n, p, true, nnz); m->f64->n_threads = n_threads; m->f64->upload_csc(indptr, indices, (const double*)values); }
+    *out = m;
+    AB_CATCH
+}
+// random sparse matrix generated in HBM: exactly nnz_per_col non-zeros per column at sorted random rows, N(0,1) values
+int ab_matrix_sparse_alloc_random(int dtype, int64_t n, int64_t p, int64_t nnz_per_col, uint64_t seed, ab_matrix** out) {
+    AB_TRY
+    if (n < 1 || p < 1 || nnz_per_col < 1 || nnz_per_col > n) throw core_error("sparse matrix: invalid shape.");
+    auto* m = new ab_matrix{dtype};
+    if (dtype == AB_F32) { m->f32 = new DenseMatrix<float>(n, p, true, p * nnz_per_col); m->f32->fill_sparse_random(nnz_per_col, seed); }
+    else { m->f64 = new DenseMatrix<double>(n, p, true, p * nnz_per_col); m->f64->fill_sparse_random(nnz_per_col, seed); }
+    AB_CUDA(cudaDeviceSynchronize());
+    *out = m;
+    AB_CATCH
+}
+int ab_matrix_sparse_nnz(const ab_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->nnz : m->f64->nnz; return AB_OK; }
+int ab_matrix_sparse_download(ab_matrix* m, int64_t* indptr, int32_t* indices, void* values) {
+    AB_TRY
+    if (m->dtype == AB_F32) {
+        auto& M = *m->f32; if (!M.sparse) throw core_error("not a sparse matrix.");
+        M.sp_indptr.download(indptr, M.p + 1); M.sp_indices.download(indices, M.nnz); M.sp_values.download((float*)values, M.nnz);
+    } else {
+        auto& M = *m->f64; if (!M.sparse) throw core_error("not a sparse matrix.");
+        M.sp_indptr.download(indptr, M.p + 1); M.sp_indices.download(indices, M.nnz); M.sp_values.download((double*)values, M.nnz);
+    }
+    AB_CUDA(cudaStreamSynchronize(0));
+    AB_CATCH
+}
 int ab_matrix_free(ab_matrix* m) { if (m) { delete m->f32; delete m->f64; delete m; } return AB_OK; }
 int ab_matrix_rows(const ab_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->n : m->f64->n; return AB_OK; }
 int ab_matrix_cols(const ab_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->p : m->f64->p; return AB_OK; }

@@ -11,6 +11,7 @@
 #include "dense_kernels.cuh"
 #include "sweep.cuh"
 #include "sweep_batched.cuh"
+#include "sparse_kernels.cuh"
 #include "dist.cuh"
 #include <cuda.h>
 #include <curand_kernel.h>
@@ -161,9 +162,24 @@ struct DenseMatrix {
     DevBuf<long long> stats;    // per-phase cycle counters of the fused sweep (Configs::sweep_profile)
     cudaStream_t stream = 0;
 
-    DenseMatrix(int64_t n_, int64_t p_) : n(n_), p(p_), ld(pad_rows(n_)) {
-        store.alloc((size_t)ld * p);
-        X = store.p;
+    // Second storage kind of the same device-matrix object: sparse CSC (MatrixNaiveSparse of the reference).  Every operator
+    // below dispatches on `sparse`; the path driver (solver.cuh) is storage agnostic.
+    bool sparse = false;
+    int64_t nnz = 0;
+    DevBuf<int64_t> sp_indptr; DevBuf<int32_t> sp_indices; DevBuf<T> sp_values;
+    CscView<T> csc() const { return CscView<T>{sp_indptr.p, sp_indices.p, sp_values.p}; }
+
+    DenseMatrix(int64_t n_, int64_t p_, bool sparse_ = false, int64_t nnz_ = 0) : n(n_), p(p_), ld(pad_rows(n_)), sparse(sparse_), nnz(nnz_) {
+        if (!sparse) { store.alloc((size_t)ld * p); X = store.p; }
+        else { sp_indptr.alloc(p + 1); sp_indices.alloc(std::max<int64_t>(nnz, 1)); sp_values.alloc(std::max<int64_t>(nnz, 1)); }
+    }
+    void upload_csc(const int64_t* indptr, const int32_t* indices, const T* values) {
+        sp_indptr.upload(indptr, p + 1); sp_indices.upload(indices, nnz); sp_values.upload(values, nnz);
+        AB_CUDA(cudaStreamSynchronize(0));
+    }
+    void fill_sparse_random(int64_t nnz_per_col, unsigned long long seed) {
+        sparse_fill_kernel<T><<<1184, 256, 0, stream>>>(sp_indptr.p, sp_indices.p, sp_values.p, n, p, nnz_per_col, seed);
+        AB_CUDA(cudaGetLastError());
     }
     int64_t rows() const { return n; }
     int64_t cols() const { return p; }
@@ -208,6 +224,13 @@ struct DenseMatrix {
     void d_gemv_t(int64_t j0, const int32_t* cols, int q, const T* v, const T* w, T* out, bool sq = false,
                   const T* sub = nullptr, const double* sub_scale_ptr = nullptr, double sub_scale = 0) {
         if (q <= 0) return;
+        if (sparse) {
+            const unsigned nblk = (unsigned)((q + 7) / 8);
+            if (sq) spmv_t_kernel<T, true><<<nblk, 256, 0, stream>>>(csc(), j0, cols, q, v, w, out, sub, sub_scale_ptr, sub_scale);
+            else spmv_t_kernel<T, false><<<nblk, 256, 0, stream>>>(csc(), j0, cols, q, v, w, out, sub, sub_scale_ptr, sub_scale);
+            AB_CUDA(cudaGetLastError());
+            return;
+        }
         const int n_rb = (int)((ld + kGemvRows - 1) / kGemvRows);
         part.reserve_keep((size_t)n_rb * q, stream);
         dim3 grid((q + kGemvColsPerCta - 1) / kGemvColsPerCta, n_rb);
@@ -219,6 +242,7 @@ struct DenseMatrix {
     // Multi-response `mul` of [kron(1, I_K) | kron(X, I_K)] (PY/solver.py:705-720 layout): v, w (n_pad, K) row-major (w nullable);
     // out[l] = sum_i v[i,l] w[i,l] for l < n_int (the intercept columns), out[n_int + j*K + l] = sum_i X[i,j] v[i,l] w[i,l].
     void d_mul_multi(int K, int n_int, const T* v, const T* w, T* out) {
+        if (sparse) throw core_error("multi-response problems are not supported on sparse matrices.");
         if (K > kMultiMaxK) throw core_error("multi-response problems with more than 16 classes are not supported.");
         int tile_rows = (int)std::min<int64_t>(ld, std::max<int64_t>(kRowAlign, (int64_t)(48 * 1024 / (K * sizeof(T))) / 128 * 128));
         const int n_rb = (int)((ld + tile_rows - 1) / tile_rows);
@@ -247,6 +271,12 @@ struct DenseMatrix {
         d_gemv_t(0, nullptr, (int)p, v, w, out, false, sub, sub_scale_ptr);
     }
     void d_btmul(int64_t j, int q, const T* v_dev, T* out) {
+        if (sparse) {
+            if (q <= 0) return;
+            spaxpy_kernel<T><<<dim3(8, (unsigned)q), 256, 0, stream>>>(csc(), j, v_dev, out);
+            AB_CUDA(cudaGetLastError());
+            return;
+        }
         constexpr int VN = VecT<T>::N;
         const int64_t nv = ld / VN;
         axpy_cols_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(X, ld, ld, j, q, v_dev, out);
@@ -255,6 +285,12 @@ struct DenseMatrix {
     // Batched Gram: C[out_off + a*gs + b] = X_g^T diag(w or w^2) X_g, device doubles (c_total entries)
     void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out, int K = 1) {
         if (n_items <= 0) return;
+        if (sparse) {
+            if (K != 1) throw core_error("multi-response problems are not supported on sparse matrices.");
+            spcov_kernel<T><<<n_items, 256, 0, stream>>>(csc(), items_dev, w, w_is_sqrt ? 1 : 0, C_out);
+            AB_CUDA(cudaGetLastError());
+            return;
+        }
         const int sms = DeviceInfo::get().sm_count;
         int n_rb = std::max(1, std::min(sms, (4 * sms + n_items - 1) / n_items));
         int rows_per_block = (int)((ld + n_rb - 1) / n_rb);
@@ -337,8 +373,30 @@ struct DenseMatrix {
 
     // The fused pin solve (sweep.cuh).
     SweepGeometry last_geom{};
+    void pin_solve_sparse(const PinLaunch<T>& L) {
+        if (L.K != 1) throw core_error("multi-response problems are not supported on sparse matrices.");
+        if (DistContext::get().active()) throw core_error("sparse matrices are not supported in row-sharded multi-GPU mode.");
+        last_geom = SweepGeometry{}; last_geom.ncta = 1; last_geom.threads = kSparseThreads; last_bgeom.ok = false;
+        SparsePinArgs<T> a{};
+        a.X = csc(); a.resid = L.resid; a.weights = L.weights; a.meta = L.meta; a.S = L.S; a.grec = L.grec;
+        act_stride = ((int64_t)L.S + 127) / 128 * 128 + 128; act_rep.reserve_keep((size_t)act_stride, stream);
+        beta_stride = ((int64_t)L.beta_len + 31) / 32 * 32 + 32; beta_rep.reserve_keep((size_t)beta_stride, stream);
+        a.beta_in = L.beta_in; a.beta_out = beta_rep.p; a.beta_len = L.beta_len; a.is_active_in = L.is_active_in; a.is_active_out = act_rep.p;
+        a.active_set = L.active_set; a.sc = L.sc;
+        a.lmda = L.lmda; a.alpha = L.alpha; a.tol = L.tol; a.newton_tol = L.newton_tol; a.dbeta_tol = Configs::dbeta_tol;
+        a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
+        a.gs_cap = std::max(4, (L.gs_max + 3) / 4 * 4);
+        const size_t smem = sizeof(double) * ((size_t)(kSparseThreads / 32 + 10) * a.gs_cap + 4 * 32 + 8);
+        last_geom.smem_bytes = smem;
+        const void* fn = (const void*)pin_solve_sparse_kernel<T>;
+        AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void* kargs[] = {&a};
+        AB_CUDA(cudaLaunchKernel(fn, dim3(1), dim3(kSparseThreads), kargs, smem, stream));
+    }
+
     void pin_solve(const PinLaunch<T>& L) {
         if (L.gs_max > kGsMax) throw core_error("group size " + std::to_string(L.gs_max) + " exceeds the fused sweep kernel's limit of " + std::to_string(kGsMax) + ".");
+        if (sparse) { pin_solve_sparse(L); return; }
         SweepContext& ctx = SweepContext::get();
         if (L.K > 16) throw core_error("multi-response problems with more than 16 classes are not supported by the fused sweep kernel.");
         SweepGeometry g = plan_sweep<T>(ld, L.gs_max, L.rec_max, L.K, L.feat_max);

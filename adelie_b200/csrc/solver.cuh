@@ -461,7 +461,7 @@ struct PathState {
         const size_t old_active = active_set_size;
         float ms = 0;
         BatchGeometry bg{};
-        if (static_weights && K == 1) bg = plan_batched<T>(X->n_pad(), gs_max_screen, rec_max_screen);
+        if (static_weights && K == 1 && !X->sparse) bg = plan_batched<T>(X->n_pad(), gs_max_screen, rec_max_screen);
         if (!bg.ok) {
             AB_CUDA(cudaEventRecord(ev0, 0));
             X->pin_solve(L);

@@ -228,6 +228,64 @@ class _DeviceDense(_DeviceMatrix):
         return out
 
 
+class _Sparse(_DeviceMatrix):
+    """Sparse CSC matrix resident in HBM (reference: adelie.matrix.sparse -> MatrixNaiveSparse, CORE/matrix/matrix_naive_sparse.ipp)."""
+    def __init__(self, mat, n_threads):
+        _DeviceMatrix.__init__(self, mat.dtype, mat.shape[0], mat.shape[1], n_threads)
+        self._mat = mat          # keep the host arrays alive (adelie/matrix.py keeps `_mat`)
+
+    def _make_handle(self):
+        m = self._mat
+        indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+        values = np.ascontiguousarray(m.data, dtype=self.dtype)
+        h = C.c_void_p()
+        _lib.check(_lib.load().ab_matrix_sparse_create(_lib.dtype_code(self.dtype), m.shape[0], m.shape[1], int(values.size), _lib.ptr(indptr),
+                                                       _lib.ptr(indices), _lib.ptr(values), self._n_threads, C.byref(h)))
+        return h
+
+
+class _DeviceSparse(_DeviceMatrix):
+    """Random sparse CSC matrix generated directly in HBM (bench): exactly ``nnz_per_col`` N(0,1) entries per column."""
+    def __init__(self, dtype, n, p, nnz_per_col, seed, n_threads=1):
+        _DeviceMatrix.__init__(self, dtype, n, p, n_threads)
+        h = C.c_void_p()
+        _lib.check(_lib.load().ab_matrix_sparse_alloc_random(_lib.dtype_code(dtype), n, p, nnz_per_col, seed, C.byref(h)))
+        self._handle = h
+        self._nnz = int(p) * int(nnz_per_col)
+
+    def to_host(self):
+        """scipy CSC copy of the device matrix."""
+        from scipy.sparse import csc_matrix as _csc
+        indptr = np.empty(self._p + 1, dtype=np.int64); indices = np.empty(self._nnz, dtype=np.int32); values = np.empty(self._nnz, dtype=self.dtype)
+        _lib.check(_lib.load().ab_matrix_sparse_download(self._handle, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values)))
+        return _csc((values, indices, indptr), shape=(self._n, self._p))
+
+
+def sparse(mat, *, method: str = "naive", copy: bool = False, n_threads: int = 1):
+    """Sparse matrix (adelie/matrix.py ``sparse``): a scipy CSC matrix (anything else is converted), float32 / float64."""
+    import scipy.sparse as _sp
+    if method != "naive":
+        raise RuntimeError("adelie_b200: only method='naive' is in scope (covariance matrices are not on the hot path).")
+    if not _sp.issparse(mat):
+        raise RuntimeError("mat must be a scipy sparse matrix.")
+    if mat.dtype not in (np.float32, np.float64):
+        raise RuntimeError("mat must be of type numpy.float32 or numpy.float64.")
+    if not _sp.isspmatrix_csc(mat):
+        warnings.warn("Converting to CSC format.")
+        mat = mat.tocsc(copy=True)
+    elif copy or not mat.has_sorted_indices or not mat.has_canonical_format:
+        mat = mat.copy()
+    mat.sum_duplicates()
+    mat.sort_indices()
+    return _Sparse(mat, n_threads)
+
+
+def sparse_device_random(n: int, p: int, nnz_per_col: int, *, dtype=np.float32, seed: int = 0):
+    """Random sparse CSC matrix generated in HBM with a counter-based RNG (no host copy)."""
+    return _DeviceSparse(dtype, n, p, nnz_per_col, seed)
+
+
 def dense(mat: np.ndarray, *, method: str = "naive", copy: bool = False, n_threads: int = 1):
     """Dense matrix (adelie/matrix.py:549-680).  Only ``method="naive"`` is on the hot path."""
     if method != "naive":

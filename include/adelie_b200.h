@@ -61,6 +61,14 @@ int ab_matrix_dense_create(int dtype, const void* host, int64_t n, int64_t p, in
 int ab_matrix_dense_alloc(int dtype, int64_t n, int64_t p, ab_matrix** out);
 int ab_matrix_dense_fill_normal(ab_matrix* m, uint64_t seed, int64_t row_offset);
 int ab_matrix_dense_download(ab_matrix* m, void* host, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols, int64_t ldh);
+/* adelie.matrix.sparse (PY/matrix.py sparse(); MatrixNaiveSparse{32,64}F, BIND/py_matrix.cpp:1878-1968; CORE/matrix/matrix_naive_sparse.ipp:10-262):
+ * CSC arrays as scipy holds them (column pointers widened to int64, int32 row indices sorted and unique inside every column). */
+int ab_matrix_sparse_create(int dtype, int64_t n, int64_t p, int64_t nnz, const int64_t* indptr, const int32_t* indices, const void* values,
+                            int n_threads, ab_matrix** out);
+/* bench helper: random sparse matrix generated in HBM (exactly nnz_per_col non-zeros per column, N(0,1) values) */
+int ab_matrix_sparse_alloc_random(int dtype, int64_t n, int64_t p, int64_t nnz_per_col, uint64_t seed, ab_matrix** out);
+int ab_matrix_sparse_nnz(const ab_matrix* m, int64_t* out);
+int ab_matrix_sparse_download(ab_matrix* m, int64_t* indptr, int32_t* indices, void* values);
 int ab_matrix_free(ab_matrix* m);
 int ab_matrix_rows(const ab_matrix* m, int64_t* out);
 int ab_matrix_cols(const ab_matrix* m, int64_t* out);
