@@ -166,7 +166,7 @@ struct DenseMatrix {
     // below dispatches on `sparse`; the path driver (solver.cuh) is storage agnostic.
     bool sparse = false;
     int64_t nnz = 0;
-    DevBuf<int64_t> sp_indptr; DevBuf<int32_t> sp_indices; DevBuf<T> sp_values;
+    DevBuf<int64_t> sp_indptr; DevBuf<int32_t> sp_indices; DevBuf<T> sp_values; DevBuf<T> sp_vw;
     CscView<T> csc() const { return CscView<T>{sp_indptr.p, sp_indices.p, sp_values.p}; }
 
     DenseMatrix(int64_t n_, int64_t p_, bool sparse_ = false, int64_t nnz_ = 0) : n(n_), p(p_), ld(pad_rows(n_)), sparse(sparse_), nnz(nnz_) {
@@ -226,8 +226,14 @@ struct DenseMatrix {
         if (q <= 0) return;
         if (sparse) {
             const unsigned nblk = (unsigned)((q + 7) / 8);
-            if (sq) spmv_t_kernel<T, true><<<nblk, 256, 0, stream>>>(csc(), j0, cols, q, v, w, out, sub, sub_scale_ptr, sub_scale);
-            else spmv_t_kernel<T, false><<<nblk, 256, 0, stream>>>(csc(), j0, cols, q, v, w, out, sub, sub_scale_ptr, sub_scale);
+            sp_vw.reserve_keep((size_t)ld, stream);
+            if (sq) {
+                sp_vw_kernel<T, true><<<(unsigned)((ld + 255) / 256), 256, 0, stream>>>(v, w, sp_vw.p, ld);
+                spmv_t_kernel<T, true><<<nblk, 256, 0, stream>>>(csc(), j0, cols, q, sp_vw.p, out, sub, sub_scale_ptr, sub_scale);
+            } else {
+                sp_vw_kernel<T, false><<<(unsigned)((ld + 255) / 256), 256, 0, stream>>>(v, w, sp_vw.p, ld);
+                spmv_t_kernel<T, false><<<nblk, 256, 0, stream>>>(csc(), j0, cols, q, sp_vw.p, out, sub, sub_scale_ptr, sub_scale);
+            }
             AB_CUDA(cudaGetLastError());
             return;
         }

@@ -15,10 +15,18 @@ namespace ab {
 template <class T>
 struct CscView { const int64_t* indptr; const int32_t* indices; const T* values; };
 
-// out[c] = sum_k X[k, col(c)]^(1 or 2) * v[k] * w[k]   (SQ: X^2 * w, as the dense kernel) [- scale * sub[c]]; one warp per column
+// vw[i] = v[i] * w[i]  (SQ: w[i]): one dense pass so that the column kernel gathers a single vector
+template <class T, bool SQ>
+__global__ void sp_vw_kernel(const T* __restrict__ v, const T* __restrict__ w, T* __restrict__ vw, int64_t n_pad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) vw[i] = SQ ? w[i] : v[i] * w[i];
+}
+
+// out[c] = sum_k X[k, col(c)]^(1 or 2) * vw[k]  [- scale * sub[c]]; one warp per column, 8 independent (index, value) loads and
+// gathers in flight per lane (the gathers hit L2: vw is n * s bytes)
 template <class T, bool SQ>
 __global__ void __launch_bounds__(256)
-spmv_t_kernel(CscView<T> X, int64_t j0, const int32_t* __restrict__ cols, int q, const T* __restrict__ v, const T* __restrict__ w,
+spmv_t_kernel(CscView<T> X, int64_t j0, const int32_t* __restrict__ cols, int q, const T* __restrict__ vw,
               T* __restrict__ out, const T* __restrict__ sub, const double* __restrict__ sub_scale_ptr, double sub_scale)
 {
     const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -26,11 +34,18 @@ spmv_t_kernel(CscView<T> X, int64_t j0, const int32_t* __restrict__ cols, int q,
     if (c >= q) return;
     const int64_t col = cols ? (int64_t)cols[c] : j0 + c;
     const int64_t k0 = X.indptr[col], k1 = X.indptr[col + 1];
+    constexpr int U = 8;
     double acc = 0;
-    for (int64_t k = k0 + lane; k < k1; k += 32) {
-        const int32_t i = X.indices[k];
-        const T x = X.values[k];
-        acc += SQ ? (double)(x * x * w[i]) : (double)(x * (v[i] * w[i]));
+    for (int64_t k = k0 + lane; k < k1; k += 32 * U) {
+        int32_t idx[U]; T x[U]; T g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int64_t kk = k + 32 * u; const bool in = kk < k1; idx[u] = in ? X.indices[kk] : 0; x[u] = in ? X.values[kk] : T(0); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) g[u] = vw[idx[u]];
+        T part = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) part += (SQ ? x[u] * x[u] : x[u]) * g[u];
+        acc += (double)part;
     }
     acc = dev::warp_sum(acc);
     if (lane == 0) {
@@ -179,9 +194,15 @@ pin_solve_sparse_kernel(const __grid_constant__ SparsePinArgs<T> a)
             for (int c = 0; c < gs; ++c) {
                 const int64_t k0 = a.X.indptr[m.col + c], k1 = a.X.indptr[m.col + c + 1];
                 T acc = 0;
-                for (int64_t k = k0 + tid; k < k1; k += kSparseThreads) {
-                    const int32_t i = a.X.indices[k];
-                    acc += a.X.values[k] * (a.weights[i] * a.resid[i]);
+                constexpr int U = 6;                                     // independent (index, value) loads + gathers in flight per thread
+                for (int64_t k = k0 + tid; k < k1; k += (int64_t)kSparseThreads * U) {
+                    int32_t idx[U]; T x[U], gw[U], gr[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { const int64_t kk = k + (int64_t)kSparseThreads * u; const bool in = kk < k1; idx[u] = in ? a.X.indices[kk] : 0; x[u] = in ? a.X.values[kk] : T(0); }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) { gw[u] = a.weights[idx[u]]; gr[u] = a.resid[idx[u]]; }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc += x[u] * (gw[u] * gr[u]);
                 }
                 const double tot = dev::warp_sum((double)acc);
                 if (lane == 0) wred[(size_t)warp * gsc + c] = tot;
@@ -248,7 +269,16 @@ pin_solve_sparse_kernel(const __grid_constant__ SparsePinArgs<T> a)
                 for (int c = 0; c < gs; ++c) {
                     const T d = s_del[c];
                     const int64_t k0 = a.X.indptr[m.col + c], k1 = a.X.indptr[m.col + c + 1];
-                    for (int64_t k = k0 + tid; k < k1; k += kSparseThreads) a.resid[a.X.indices[k]] += a.X.values[k] * d;
+                    constexpr int U = 6;
+                    for (int64_t k = k0 + tid; k < k1; k += (int64_t)kSparseThreads * U) {
+                        int32_t idx[U]; T x[U], gr[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { const int64_t kk = k + (int64_t)kSparseThreads * u; const bool in = kk < k1; idx[u] = in ? a.X.indices[kk] : -1; x[u] = in ? a.X.values[kk] : T(0); }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) gr[u] = idx[u] >= 0 ? a.resid[idx[u]] : T(0);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) if (idx[u] >= 0) a.resid[idx[u]] = gr[u] + x[u] * d;
+                    }
                     if (gs > 1) __syncthreads();
                 }
             }
