@@ -12,6 +12,7 @@ from . import data
 from . import diagnostic
 from . import dist
 from . import glm
+from . import io
 from . import matrix
 from . import solver
 from . import state

@@ -18,6 +18,7 @@ static thread_local std::string g_last_error;
 
 struct ab_matrix { int dtype; DenseMatrix<float>* f32 = nullptr; DenseMatrix<double>* f64 = nullptr; };
 struct ab_glm { int dtype; int family; Glm<float>* f32 = nullptr; Glm<double>* f64 = nullptr; };
+struct ab_io_snp { SnpUnphasedIO io; ab_io_snp(const char* f, const char* m) : io(f, m) {} };
 struct ab_state { int dtype; PathState<float>* f32 = nullptr; PathState<double>* f64 = nullptr; std::string error; double total_time = 0; };
 
 #define AB_TRY try {
@@ -204,6 +205,186 @@ int ab_matrix_sparse_download(ab_matrix* m, int64_t* indptr, int32_t* indices, v
     AB_CUDA(cudaStreamSynchronize(0));
     AB_CATCH
 }
+// ------------------------------------------------------------------------------------------ SNP unphased: IO + matrix
+// reference: adelie.io.snp_unphased (PY/io.py:114-196) -> IOSNPUnphased (BIND/py_io.cpp, CORE/io/io_snp_unphased.{hpp,ipp});
+//            adelie.matrix.snp_unphased (PY/matrix.py:1243-1298) -> MatrixNaiveSNPUnphased{32,64} (CORE/matrix/matrix_naive_snp_unphased.ipp)
+int ab_io_snp_unphased_create(const char* filename, const char* read_mode, ab_io_snp** out) {
+    AB_TRY
+    *out = new ab_io_snp(filename, read_mode);
+    AB_CATCH
+}
+int ab_io_snp_unphased_free(ab_io_snp* io) { delete io; return AB_OK; }
+int ab_io_snp_unphased_write(ab_io_snp* io, const int8_t* calldata, int64_t n, int64_t p, const char* impute_method, double* impute, int64_t impute_len,
+                             int n_threads, uint64_t* total_bytes) {
+    AB_TRY
+    (void)n_threads;
+    *total_bytes = io->io.write(calldata, (uint64_t)n, (uint64_t)p, impute_method, impute, (size_t)impute_len);
+    AB_CATCH
+}
+int ab_io_snp_unphased_read(ab_io_snp* io, uint64_t* total_bytes) {
+    AB_TRY
+    *total_bytes = io->io.read();
+    AB_CATCH
+}
+int ab_io_snp_unphased_info(const ab_io_snp* io, int* is_read, int64_t* rows, int64_t* snps) {
+    *is_read = io->io.is_read ? 1 : 0; *rows = (int64_t)io->io.rows; *snps = (int64_t)io->io.snps;
+    return AB_OK;
+}
+int ab_io_snp_unphased_get(const ab_io_snp* io, const char* name, void* out) {
+    AB_TRY
+    io->io.need_read();
+    const std::string s(name);
+    const auto& I = io->io;
+    if (s == "nnz") std::memcpy(out, I.nnz.data(), 8 * I.snps);
+    else if (s == "nnm") std::memcpy(out, I.nnm.data(), 8 * I.snps);
+    else if (s == "impute") std::memcpy(out, I.impute.data(), 8 * I.snps);
+    else if (s == "outer") std::memcpy(out, I.outer.data(), 8 * (I.snps + 1));
+    else throw core_error("unknown field " + s);
+    AB_CATCH
+}
+int ab_io_snp_unphased_to_dense(const ab_io_snp* io, int n_threads, int8_t* out) {
+    AB_TRY
+    (void)n_threads;
+    io->io.to_dense(out);
+    AB_CATCH
+}
+
+} // extern "C"
+
+template <class T>
+static DenseMatrix<T>* snp_from_io(const SnpUnphasedIO& I, int64_t row_lo, int64_t row_hi, int n_threads) {
+    I.need_read();
+    if (I.rows < 1 || I.snps < 1) throw core_error("matrix must have at least one row and one column.");
+    if (row_hi < 0) row_hi = (int64_t)I.rows;
+    if (row_lo < 0 || row_lo >= row_hi || row_hi > (int64_t)I.rows) throw core_error("snp_unphased: invalid row range.");
+    const int64_t p = (int64_t)I.snps;
+    auto M = std::unique_ptr<DenseMatrix<T>>(new DenseMatrix<T>(row_hi - row_lo, p, typename DenseMatrix<T>::SnpTag{}));
+    M->n_threads = n_threads;
+    std::vector<T> imp(p);
+    for (int64_t j = 0; j < p; ++j) imp[j] = (T)I.impute[j];
+    M->snp_impute.upload(imp.data(), p);
+    DevBuf<uint64_t> d_outer(p + 1); d_outer.upload(I.outer.data(), p + 1);
+    DevBuf<int> d_err(1);
+    // ship the chunk lists in column ranges of at most ~1 GB of file bytes and unpack them on the device
+    const uint64_t kMaxBytes = 1ull << 30;
+    DevBuf<uint8_t> d_file;
+    for (int64_t j0 = 0; j0 < p;) {
+        int64_t j1 = j0 + 1;
+        while (j1 < p && I.outer[j1 + 1] - I.outer[j0] <= kMaxBytes) ++j1;
+        const uint64_t bytes = I.outer[j1] - I.outer[j0];
+        if (d_file.n < bytes + 16) d_file.alloc(bytes + 16);
+        AB_CUDA(cudaMemcpyAsync(d_file.p, I.buf + I.outer[j0], bytes, cudaMemcpyHostToDevice, 0));
+        const int64_t items = (j1 - j0) * 3;
+        snpdat_unpack_kernel<<<(unsigned)((items + 7) / 8), 256>>>(d_file.p, d_outer.p, j0, j1 - j0, (int64_t)I.outer[j0], (int64_t)I.rows, row_lo, row_hi,
+                                                                  M->snp_packed.p, M->snp_ldw, d_err.p);
+        AB_CUDA(cudaGetLastError());
+        AB_CUDA(cudaStreamSynchronize(0));
+        j0 = j1;
+    }
+    int err = 0; d_err.download(&err, 1); AB_CUDA(cudaStreamSynchronize(0));
+    if (err) throw core_error("snp_unphased: the file holds a row index outside [0, rows).");
+    return M.release();
+}
+
+template <class T>
+static DenseMatrix<T>* snp_from_calldata(const int8_t* calldata, int64_t n, int64_t p, const double* impute, int n_threads) {
+    auto M = std::unique_ptr<DenseMatrix<T>>(new DenseMatrix<T>(n, p, typename DenseMatrix<T>::SnpTag{}));
+    M->n_threads = n_threads;
+    std::vector<T> imp(p);
+    for (int64_t j = 0; j < p; ++j) imp[j] = (T)impute[j];
+    M->snp_impute.upload(imp.data(), p);
+    DevBuf<int> d_err(1);
+    const int64_t cols_per = std::max<int64_t>(1, (int64_t)(256 << 20) / n);
+    DevBuf<int8_t> d_call((size_t)std::min(cols_per, p) * n);
+    for (int64_t j0 = 0; j0 < p; j0 += cols_per) {
+        const int64_t jc = std::min(cols_per, p - j0);
+        AB_CUDA(cudaMemcpyAsync(d_call.p, calldata + j0 * n, (size_t)jc * n, cudaMemcpyHostToDevice, 0));
+        snp_pack_kernel<<<dim3((unsigned)std::min<int64_t>(64, (M->snp_ldw + 255) / 256), (unsigned)jc), 256>>>(d_call.p, n, jc, M->snp_packed.p + j0 * M->snp_ldw, M->snp_ldw, d_err.p);
+        AB_CUDA(cudaGetLastError());
+        AB_CUDA(cudaStreamSynchronize(0));
+    }
+    int err = 0; d_err.download(&err, 1); AB_CUDA(cudaStreamSynchronize(0));
+    if (err) throw core_error("Detected a value greater than > 2. Make sure calldata only contains values <= 2. ");
+    return M.release();
+}
+
+template <class T>
+static DenseMatrix<T>* snp_random(int64_t n, int64_t p, uint64_t seed, int64_t row_offset, int64_t n_total, double one_ratio, double two_ratio, double missing_ratio) {
+    auto M = std::unique_ptr<DenseMatrix<T>>(new DenseMatrix<T>(n, p, typename DenseMatrix<T>::SnpTag{}));
+    DevBuf<unsigned long long> d_counts((size_t)3 * p);
+    snp_fill_random_kernel<<<dim3((unsigned)std::min<int64_t>(32, (M->snp_ldw + 255) / 256), (unsigned)p), 256>>>(
+        M->snp_packed.p, M->snp_ldw, n, p, seed, row_offset, (float)one_ratio, (float)two_ratio, (float)missing_ratio, d_counts.p);
+    AB_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> cnt((size_t)3 * p);
+    d_counts.download(cnt.data(), cnt.size()); AB_CUDA(cudaStreamSynchronize(0));
+    std::vector<double> c(cnt.begin(), cnt.end());
+    if (DistContext::get().active()) DistContext::get().allreduce_host(c.data(), (int64_t)c.size());      // column means are over ALL rows
+    std::vector<T> imp(p);
+    for (int64_t j = 0; j < p; ++j) imp[j] = (T)((c[3 * j] + 2.0 * c[3 * j + 1]) / std::max(1.0, (double)n_total - c[3 * j + 2]));
+    M->snp_impute.upload(imp.data(), p); AB_CUDA(cudaStreamSynchronize(0));
+    return M.release();
+}
+
+extern "C" {
+
+int ab_matrix_snp_unphased_create(int dtype, const ab_io_snp* io, int64_t row_lo, int64_t row_hi, int n_threads, ab_matrix** out) {
+    AB_TRY
+    if (n_threads < 1) throw core_error("n_threads must be >= 1.");
+    auto* m = new ab_matrix{dtype};
+    try {
+        if (dtype == AB_F32) m->f32 = snp_from_io<float>(io->io, row_lo, row_hi, n_threads); else m->f64 = snp_from_io<double>(io->io, row_lo, row_hi, n_threads);
+    } catch (...) { delete m; throw; }
+    *out = m;
+    AB_CATCH
+}
+int ab_matrix_snp_unphased_from_calldata(int dtype, const int8_t* calldata, int64_t n, int64_t p, const double* impute, int n_threads, ab_matrix** out) {
+    AB_TRY
+    if (n < 1 || p < 1) throw core_error("matrix must have at least one row and one column.");
+    if (n_threads < 1) throw core_error("n_threads must be >= 1.");
+    auto* m = new ab_matrix{dtype};
+    try {
+        if (dtype == AB_F32) m->f32 = snp_from_calldata<float>(calldata, n, p, impute, n_threads); else m->f64 = snp_from_calldata<double>(calldata, n, p, impute, n_threads);
+    } catch (...) { delete m; throw; }
+    *out = m;
+    AB_CATCH
+}
+int ab_matrix_snp_unphased_alloc_random(int dtype, int64_t n, int64_t p, uint64_t seed, int64_t row_offset, int64_t n_total,
+                                        double one_ratio, double two_ratio, double missing_ratio, ab_matrix** out) {
+    AB_TRY
+    if (n < 1 || p < 1 || n_total < n) throw core_error("snp_unphased: invalid shape.");
+    auto* m = new ab_matrix{dtype};
+    try {
+        if (dtype == AB_F32) m->f32 = snp_random<float>(n, p, seed, row_offset, n_total, one_ratio, two_ratio, missing_ratio);
+        else m->f64 = snp_random<double>(n, p, seed, row_offset, n_total, one_ratio, two_ratio, missing_ratio);
+    } catch (...) { delete m; throw; }
+    *out = m;
+    AB_CATCH
+}
+// calldata_out: column-major (n, p) int8 with -9 for missing; impute_out (p,) doubles
+int ab_matrix_snp_unphased_download(ab_matrix* m, int8_t* calldata_out, double* impute_out) {
+    AB_TRY
+    auto run = [&](auto& M) {
+        using T = std::remove_reference_t<decltype(M.snp_impute.p[0])>;
+        if (!M.snp) throw core_error("not a snp_unphased matrix.");
+        std::vector<uint32_t> h((size_t)M.snp_ldw * M.p); std::vector<T> imp(M.p);
+        M.snp_packed.download(h.data(), h.size()); M.snp_impute.download(imp.data(), M.p);
+        AB_CUDA(cudaStreamSynchronize(0));
+        for (int64_t j = 0; j < M.p; ++j) {
+            impute_out[j] = (double)imp[j];
+            for (int64_t i = 0; i < M.n; ++i) {
+                const uint32_t code = (h[(size_t)j * M.snp_ldw + (i >> 4)] >> (2 * (i & 15))) & 3u;
+                calldata_out[j * M.n + i] = code == 3u ? (int8_t)-9 : (int8_t)code;
+            }
+        }
+    };
+    if (m->dtype == AB_F32) run(*m->f32); else run(*m->f64);
+    AB_CATCH
+}
+int ab_matrix_snp_unphased_cache_info(const ab_matrix* m, int64_t* cached_cols, int64_t* packed_bytes) {
+    if (m->dtype == AB_F32) { *cached_cols = m->f32->cache_used; *packed_bytes = (int64_t)(m->f32->snp_packed.n * 4); }
+    else { *cached_cols = m->f64->cache_used; *packed_bytes = (int64_t)(m->f64->snp_packed.n * 4); }
+    return AB_OK;
+}
 int ab_matrix_free(ab_matrix* m) { if (m) { delete m->f32; delete m->f64; delete m; } return AB_OK; }
 int ab_matrix_rows(const ab_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->n : m->f64->n; return AB_OK; }
 int ab_matrix_cols(const ab_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->p : m->f64->p; return AB_OK; }
@@ -258,7 +439,7 @@ struct HostOps {
         check_bmul(j, q, M.n, M.p);
         if (q == 0) return;
         auto dw = up(sqrt_w, M.n, M.ld);
-        CovItem it{(int32_t)j, (int32_t)q, 0};
+        CovItem it{M.phys_col(j, (int)q), (int32_t)q, 0};
         DevBuf<CovItem> di(1); di.upload(&it, 1);
         DevBuf<double> C((size_t)q * q);
         M.d_cov(di.p, 1, q * q, dw.p, true, C.p);

@@ -12,6 +12,8 @@
 #include "sweep.cuh"
 #include "sweep_batched.cuh"
 #include "sparse_kernels.cuh"
+#include "snp.cuh"
+#include <unordered_map>
 #include "dist.cuh"
 #include <cuda.h>
 #include <curand_kernel.h>
@@ -169,6 +171,70 @@ struct DenseMatrix {
     DevBuf<int64_t> sp_indptr; DevBuf<int32_t> sp_indices; DevBuf<T> sp_values; DevBuf<T> sp_vw;
     CscView<T> csc() const { return CscView<T>{sp_indptr.p, sp_indices.p, sp_values.p}; }
 
+    // Third storage kind: SNP unphased genotypes (snp.cuh).  `snp_packed` holds the 2-bit codes of all p columns; `store` / `X` is
+    // the dense cache of decoded columns (physical columns), filled on demand by phys_col(); every kernel that takes a column
+    // index below takes a PHYSICAL column (dense / sparse: physical == logical).
+    bool snp = false;
+    DevBuf<uint32_t> snp_packed; int64_t snp_ldw = 0; DevBuf<T> snp_impute;
+    int64_t cache_cap = 0, cache_used = 0;
+    std::unordered_map<int64_t, std::pair<int32_t, int32_t>> cache_map;      // logical first column -> (first slot, columns decoded there)
+    long long n_decoded_cols = 0;
+    struct SnpTag {};
+    DenseMatrix(int64_t n_, int64_t p_, SnpTag) : n(n_), p(p_), ld(pad_rows(n_)), snp(true) {
+        snp_ldw = ld / 16; snp_packed.alloc((size_t)snp_ldw * p); snp_impute.alloc(p);
+    }
+    // Physical first column of the logical columns [col, col + count): for SNP storage the columns are decoded into consecutive
+    // slots of the dense cache the first time they are asked for.
+    int32_t phys_col(int64_t col, int count) {
+        if (!snp) return (int32_t)col;
+        auto it = cache_map.find(col);
+        if (it != cache_map.end() && it->second.second >= count) return it->second.first;
+        if (cache_used + count > cache_cap) {
+            int64_t want = std::max<int64_t>(cache_used + count, std::max<int64_t>(64, 2 * cache_cap));
+            size_t fr = 0, tot = 0; AB_CUDA(cudaMemGetInfo(&fr, &tot));
+            if ((double)want * ld * sizeof(T) > 0.8 * (double)fr) want = cache_used + count + std::min<int64_t>(256, cache_cap / 8);
+            DevBuf<T> bigger;
+            bigger.alloc((size_t)ld * want);
+            if (cache_used) AB_CUDA(cudaMemcpyAsync(bigger.p, store.p, (size_t)ld * cache_used * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+            AB_CUDA(cudaStreamSynchronize(stream));
+            store = std::move(bigger); X = store.p; cache_cap = want;
+        }
+        const int32_t slot = (int32_t)cache_used;
+        dim3 grid((unsigned)std::min<int64_t>(64, (snp_ldw + 255) / 256), (unsigned)count);
+        snp_decode_kernel<T><<<grid, 256, 0, stream>>>(snp_packed.p, snp_ldw, snp_impute.p, col, count, X + (int64_t)slot * ld, ld);
+        AB_CUDA(cudaGetLastError());
+        cache_used += count; n_decoded_cols += count;
+        cache_map[col] = std::make_pair(slot, (int32_t)count);
+        return slot;
+    }
+    // out_part layout of the packed transposed GEMV: [row block][q][K]; returns the number of row blocks
+    template <int KP, bool SQ>
+    int snp_gemv_launch(int64_t j0, int q, int K, const T* v, const T* w) {
+        constexpr int R = snp_gemv_rows_per_lane<KP>();
+        const int64_t rows_per_cta = (int64_t)(kSnpGemvThreads / 32) * 32 * R;
+        const int n_rb = (int)((ld + rows_per_cta - 1) / rows_per_cta);
+        constexpr int NB = 32 / KP;
+        const int sms = DeviceInfo::get().sm_count;
+        int col_chunks = std::max(1, std::min((q + NB - 1) / NB, (8 * sms + n_rb - 1) / n_rb));
+        int cols_per_cta = ((q + col_chunks - 1) / col_chunks + NB - 1) / NB * NB;
+        col_chunks = (q + cols_per_cta - 1) / cols_per_cta;
+        part.reserve_keep((size_t)n_rb * q * K, stream);
+        const size_t smem = snp_gemv_smem_bytes<T>();
+        auto fn = snp_gemv_t_kernel<T, KP, SQ>;
+        AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<dim3(col_chunks, n_rb), kSnpGemvThreads, smem, stream>>>(snp_packed.p, snp_ldw, ld, snp_impute.p, j0, q, cols_per_cta, K, v, w, part.p);
+        AB_CUDA(cudaGetLastError());
+        return n_rb;
+    }
+    int snp_gemv(int64_t j0, int q, int K, const T* v, const T* w, bool sq) {
+        if (sq) return snp_gemv_launch<1, true>(j0, q, 1, v, w);
+        if (K <= 1) return snp_gemv_launch<1, false>(j0, q, 1, v, w);
+        if (K <= 2) return snp_gemv_launch<2, false>(j0, q, K, v, w);
+        if (K <= 4) return snp_gemv_launch<4, false>(j0, q, K, v, w);
+        if (K <= 8) return snp_gemv_launch<8, false>(j0, q, K, v, w);
+        return snp_gemv_launch<16, false>(j0, q, K, v, w);
+    }
+
     DenseMatrix(int64_t n_, int64_t p_, bool sparse_ = false, int64_t nnz_ = 0) : n(n_), p(p_), ld(pad_rows(n_)), sparse(sparse_), nnz(nnz_) {
         if (!sparse) { store.alloc((size_t)ld * p); X = store.p; }
         else { sp_indptr.alloc(p + 1); sp_indices.alloc(std::max<int64_t>(nnz, 1)); sp_values.alloc(std::max<int64_t>(nnz, 1)); }
@@ -219,11 +285,18 @@ struct DenseMatrix {
         return ones.p;
     }
 
-    // out[c] = X[:, cols(c)]^T (v o w) for c < q  (cols == nullptr: columns j0 .. j0+q-1); device pointers.
+    // out[c] = X[:, cols(c)]^T (v o w) for c < q  (cols == nullptr: LOGICAL columns j0 .. j0+q-1; otherwise a device list of
+    // PHYSICAL columns); device pointers.
     // sub / sub_scale: fused epilogue out -= scale * sub  (grad -= resid_sum * X_means, solver_gaussian_naive.hpp:388-391)
     void d_gemv_t(int64_t j0, const int32_t* cols, int q, const T* v, const T* w, T* out, bool sq = false,
                   const T* sub = nullptr, const double* sub_scale_ptr = nullptr, double sub_scale = 0) {
         if (q <= 0) return;
+        if (snp && cols == nullptr) {          // logical columns j0 .. j0+q-1 straight from the packed bits
+            const int n_rb = snp_gemv(j0, q, 1, v, w, sq);
+            gemv_t_reduce_kernel<T><<<(q + 255) / 256, 256, 0, stream>>>(part.p, n_rb, q, out, sub, sub_scale_ptr, sub_scale);
+            AB_CUDA(cudaGetLastError());
+            return;
+        }
         if (sparse) {
             const unsigned nblk = (unsigned)((q + 7) / 8);
             sp_vw.reserve_keep((size_t)ld, stream);
@@ -250,6 +323,13 @@ struct DenseMatrix {
     void d_mul_multi(int K, int n_int, const T* v, const T* w, T* out) {
         if (sparse) throw core_error("multi-response problems are not supported on sparse matrices.");
         if (K > kMultiMaxK) throw core_error("multi-response problems with more than 16 classes are not supported.");
+        if (snp) {
+            const int n_rb = snp_gemv(0, (int)p, K, v, w, false);
+            gemv_t_reduce_kernel<T><<<(unsigned)((p * K + 255) / 256), 256, 0, stream>>>(part.p, n_rb, (int)(p * K), out + n_int, nullptr, nullptr, 0.0);
+            AB_CUDA(cudaGetLastError());
+            if (n_int) d_class_sums(K, v, w, out);
+            return;
+        }
         int tile_rows = (int)std::min<int64_t>(ld, std::max<int64_t>(kRowAlign, (int64_t)(48 * 1024 / (K * sizeof(T))) / 128 * 128));
         const int n_rb = (int)((ld + tile_rows - 1) / tile_rows);
         const size_t smem = (size_t)K * tile_rows * sizeof(T);
@@ -283,9 +363,10 @@ struct DenseMatrix {
             AB_CUDA(cudaGetLastError());
             return;
         }
+        if (q <= 0) return;
         constexpr int VN = VecT<T>::N;
         const int64_t nv = ld / VN;
-        axpy_cols_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(X, ld, ld, j, q, v_dev, out);
+        axpy_cols_kernel<T><<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>(X, ld, ld, phys_col(j, q), q, v_dev, out);
         AB_CUDA(cudaGetLastError());
     }
     // Batched Gram: C[out_off + a*gs + b] = X_g^T diag(w or w^2) X_g, device doubles (c_total entries)

@@ -1,0 +1,394 @@
+// adelie_b200/csrc/snp.cuh -- SNP unphased genotype matrices.
+//
+// Reference: `IOSNPUnphased` (CORE/io/io_snp_unphased.hpp:137-274, .ipp:9-305, base class CORE/io/io_snp_base.ipp:20-84) and
+// `MatrixNaiveSNPUnphased` (CORE/matrix/matrix_naive_snp_unphased.ipp:10-309).  A genotype is 0, 1, 2 or missing; a missing
+// entry of column j takes the column's imputed value impute[j], so the operator set is that of the dense matrix
+// X[i, j] in {0, 1, 2, impute[j]} (the reference's own tests compare against exactly that matrix, T/test_matrix.py:721-745,
+// T/test_solver.py:756-818).
+//
+// On-disk `.snpdat` (io_snp_unphased.ipp:88-110, 164-262), all little endian:
+//   [endian:1B][n:u64][p:u64][nnz:u64 x p][nnm:u64 x p][impute:f64 x p][outer:u64 x (p+1)]
+//   column j at byte outer[j]: [3 x u64 offsets of the categories, relative to the column start]
+//     category c (0 = missing, 1 = ones, 2 = twos): [n_chunks:u32] { [chunk_idx:u32][nnz-1:u8][row_in_chunk:u8 x nnz] }, chunk = 256 rows
+//
+// HBM layout (ours): 2 bits per genotype, column-major, 4 genotypes per byte (row i of column j = bits 2*(i%4).. of byte
+// j*ldb + i/4, ldb = n_pad/4), codes 0/1/2 and 3 = missing, plus impute (p,) in the value type.  12.5 GB at config 5
+// (n=500k, p=100k) against 200 GB for the same matrix in fp32.  The file bytes are shipped to the device as they are and a
+// kernel walks the chunk lists (one warp per (column, category)); the host only parses the header.
+//   * full-matrix `mul` / `sq_mul` (the KKT pass, every lambda) run on the packed bits (snp_gemv_t_kernel);
+//   * the columns of the screen set are decoded once into a dense column cache (snp_decode_kernel) the fused sweep, Gram and
+//     panel kernels read through TMA exactly like a dense matrix: a column enters the cache when its group enters the screen set.
+#pragma once
+#include "common.cuh"
+#include "device_prims.cuh"
+#include <curand_kernel.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <cmath>
+#include <algorithm>
+
+namespace ab {
+
+// ============================================================================================ host: .snpdat reader / writer
+struct SnpUnphasedIO {
+    static constexpr uint64_t kChunk = 256;
+    static constexpr int kCategories = 3;
+    std::string filename; int read_mode = 0;     // 0 = file, 1 = mmap
+    bool is_read = false;
+    std::vector<char> owned; const char* buf = nullptr; size_t buf_bytes = 0; void* map_addr = nullptr; size_t map_bytes = 0;
+    uint64_t rows = 0, snps = 0;
+    std::vector<uint64_t> nnz, nnm, outer; std::vector<double> impute;
+
+    SnpUnphasedIO(const std::string& f, const std::string& mode) : filename(f) {
+        // util::convert_read_mode + IOSNPBase::convert_read_mode (io_snp_base.hpp:123-139): "auto" means mmap on Linux
+        if (mode == "file") read_mode = 0;
+        else if (mode == "mmap" || mode == "auto") read_mode = 1;
+        else throw core_error("Invalid read mode type: " + mode);
+    }
+    ~SnpUnphasedIO() { release(); }
+    SnpUnphasedIO(const SnpUnphasedIO&) = delete;
+    SnpUnphasedIO& operator=(const SnpUnphasedIO&) = delete;
+    void release() { if (map_addr) { munmap(map_addr, map_bytes); map_addr = nullptr; } owned.clear(); owned.shrink_to_fit(); buf = nullptr; buf_bytes = 0; }
+    void need_read() const { if (!is_read) throw core_error("File is not read yet. Call read() first."); }
+    static bool big_endian() { const uint32_t one = 1; return reinterpret_cast<const char*>(&one)[0] != 1; }
+    template <class U> static U rd(const char* q) { U u; std::memcpy(&u, q, sizeof(U)); return u; }
+
+    // io_snp_base.ipp:20-84 + io_snp_unphased.ipp:9-41
+    size_t read() {
+        release();
+        is_read = true;
+        FILE* fp = std::fopen(filename.c_str(), "rb");
+        if (!fp) throw core_error("Cannot open file " + filename);
+        std::fseek(fp, 0, SEEK_END);
+        const size_t total = (size_t)std::ftell(fp);
+        std::fseek(fp, 0, SEEK_SET);
+        if (read_mode == 1) {
+            std::fclose(fp);
+            const int fd = open(filename.c_str(), O_RDONLY);
+            if (fd == -1) throw core_error("open failed.");
+            void* addr = mmap(nullptr, total, PROT_READ, MAP_PRIVATE | MAP_NORESERVE | MAP_POPULATE, fd, 0);
+            close(fd);
+            if (addr == MAP_FAILED) throw core_error("mmap failed.");
+            map_addr = addr; map_bytes = total; buf = static_cast<const char*>(addr);
+        } else {
+            owned.resize(total);
+            const size_t got = std::fread(owned.data(), 1, total, fp);
+            std::fclose(fp);
+            if (got != total) throw core_error("Could not read the whole file into buffer.");
+            buf = owned.data();
+        }
+        buf_bytes = total;
+        if (total < 1 + 2 * sizeof(uint64_t)) throw core_error("File is too short to be a .snpdat file.");
+        if ((buf[0] != 0) != big_endian())
+            throw core_error("Endianness is inconsistent! Regenerate the file on a machine with the same endianness.");
+        size_t idx = 1;
+        rows = rd<uint64_t>(buf + idx); idx += 8;
+        snps = rd<uint64_t>(buf + idx); idx += 8;
+        if (total < idx + snps * 24 + (snps + 1) * 8) throw core_error("File is too short for its header.");
+        nnz.resize(snps); std::memcpy(nnz.data(), buf + idx, 8 * snps); idx += 8 * snps;
+        nnm.resize(snps); std::memcpy(nnm.data(), buf + idx, 8 * snps); idx += 8 * snps;
+        impute.resize(snps); std::memcpy(impute.data(), buf + idx, 8 * snps); idx += 8 * snps;
+        outer.resize(snps + 1); std::memcpy(outer.data(), buf + idx, 8 * (snps + 1));
+        if (outer[snps] > total) throw core_error("Column offsets point past the end of the file.");
+        return total;
+    }
+
+    // Walks category c of column j: f(row).
+    template <class F> void for_each(uint64_t j, int c, F f) const {
+        const char* col = buf + outer[j];
+        const char* q = col + rd<uint64_t>(col + 8 * c);
+        const uint32_t n_chunks = rd<uint32_t>(q); q += 4;
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            const uint64_t base = (uint64_t)rd<uint32_t>(q) * kChunk; q += 4;
+            const unsigned cnt = (unsigned)(uint8_t)*q + 1u; q += 1;
+            for (unsigned e = 0; e < cnt; ++e) f(base + (uint8_t)q[e]);
+            q += cnt;
+        }
+    }
+
+    // io_snp_unphased.ipp:43-69: (n, p) row-major int8, missing = -9
+    void to_dense(int8_t* out) const {
+        need_read();
+        std::memset(out, 0, (size_t)rows * snps);
+        for (uint64_t j = 0; j < snps; ++j)
+            for (int c = 0; c < kCategories; ++c) {
+                const int8_t val = (c == 0) ? (int8_t)-9 : (int8_t)c;
+                for_each(j, c, [&](uint64_t i) { out[i * snps + j] = val; });
+            }
+    }
+
+    // io_snp_unphased.ipp:72-302.  calldata: column-major (n, p) int8 (negative = missing); impute (p,) in/out
+    // (filled with the column means of the non-missing entries when impute_method == "mean", CORE/io/utils.hpp:10-31, 71-97).
+    size_t write(const int8_t* calldata, uint64_t n, uint64_t p, const std::string& impute_method, double* impute_io, size_t impute_len) const {
+        const uint64_t max_chunks = (n + kChunk - 1) / kChunk;
+        if (max_chunks >= (1ull << 32)) throw core_error("calldata dimensions are too large! ");
+        if (impute_method != "mean" && impute_method != "user") throw core_error("Invalid impute method type: " + impute_method);
+        if (impute_len != p) throw core_error("impute must have length equal to the number of columns of the matrix.");
+        std::vector<uint64_t> v_nnz(p), v_nnm(p), col_bytes(p);
+        bool bad_value = false;
+        // pass 1: per-column statistics and encoded size
+        for (uint64_t j = 0; j < p; ++j) {
+            const int8_t* col = calldata + j * n;
+            uint64_t sum = 0, miss = 0, nz = 0, bytes = 3 * 8 + 3 * 4;
+            for (uint64_t k0 = 0; k0 < n; k0 += kChunk) {
+                const uint64_t k1 = std::min(n, k0 + kChunk);
+                unsigned cnt[3] = {0, 0, 0};
+                for (uint64_t i = k0; i < k1; ++i) {
+                    const int8_t x = col[i];
+                    if (x > 2) { bad_value = true; continue; }
+                    if (x < 0) { ++cnt[0]; ++miss; } else if (x > 0) { ++cnt[x]; sum += (uint64_t)x; }
+                    nz += (x != 0);
+                }
+                for (int c = 0; c < 3; ++c) if (cnt[c]) bytes += 4 + 1 + cnt[c];
+            }
+            v_nnz[j] = nz; v_nnm[j] = n - miss; col_bytes[j] = bytes;
+            if (impute_method == "mean") impute_io[j] = (double)sum / (double)std::max<uint64_t>(n - miss, 1);
+        }
+        if (bad_value) throw core_error("Detected a value greater than > 2. Make sure calldata only contains values <= 2. ");
+        const size_t preamble = 1 + 2 * 8 + p * 8 * 3 + (p + 1) * 8;
+        std::vector<uint64_t> v_outer(p + 1);
+        v_outer[0] = preamble;
+        for (uint64_t j = 0; j < p; ++j) v_outer[j + 1] = v_outer[j] + col_bytes[j];
+        std::vector<char> out(v_outer[p]);
+        size_t idx = 0;
+        out[idx++] = (char)big_endian();
+        std::memcpy(&out[idx], &n, 8); idx += 8;
+        std::memcpy(&out[idx], &p, 8); idx += 8;
+        if (p) {
+            std::memcpy(&out[idx], v_nnz.data(), 8 * p); idx += 8 * p;
+            std::memcpy(&out[idx], v_nnm.data(), 8 * p); idx += 8 * p;
+            std::memcpy(&out[idx], impute_io, 8 * p); idx += 8 * p;
+        }
+        std::memcpy(&out[idx], v_outer.data(), 8 * (p + 1));
+        // pass 2: emit the chunk lists, category by category
+        for (uint64_t j = 0; j < p; ++j) {
+            const int8_t* col = calldata + j * n;
+            char* base = out.data() + v_outer[j];
+            uint64_t pos = 3 * 8;
+            for (int c = 0; c < 3; ++c) {
+                std::memcpy(base + 8 * c, &pos, 8);
+                char* n_chunks_at = base + pos; pos += 4;
+                uint32_t n_chunks = 0;
+                for (uint64_t k = 0; k < max_chunks; ++k) {
+                    const uint64_t k0 = k * kChunk, k1 = std::min(n, k0 + kChunk);
+                    char* hdr = base + pos; unsigned cnt = 0;
+                    for (uint64_t i = k0; i < k1; ++i) {
+                        const int8_t x = col[i];
+                        const bool hit = (c == 0) ? (x < 0) : (x == (int8_t)c);
+                        if (hit) { hdr[5 + cnt] = (char)(uint8_t)(i - k0); ++cnt; }
+                    }
+                    if (cnt) {
+                        const uint32_t k32 = (uint32_t)k; std::memcpy(hdr, &k32, 4);
+                        hdr[4] = (char)(uint8_t)(cnt - 1);
+                        pos += 5 + cnt; ++n_chunks;
+                    }
+                }
+                std::memcpy(n_chunks_at, &n_chunks, 4);
+            }
+            if (pos != col_bytes[j]) throw core_error("Column index certificate does not match expected size. This is likely a bug in the code. Please report it! ");
+        }
+        FILE* fp = std::fopen(filename.c_str(), "wb");
+        if (!fp) throw core_error("Cannot open file " + filename);
+        const size_t wrote = std::fwrite(out.data(), 1, out.size(), fp);
+        std::fclose(fp);
+        if (wrote != out.size()) throw core_error("Could not write the full buffer.");
+        return wrote;
+    }
+};
+
+// ============================================================================================ device kernels
+__device__ __forceinline__ uint64_t snp_rd_u64(const uint8_t* q) { uint64_t u = 0; for (int b = 7; b >= 0; --b) u = (u << 8) | q[b]; return u; }
+__device__ __forceinline__ uint32_t snp_rd_u32(const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); }
+
+// `.snpdat` bytes -> 2-bit codes.  One warp per (column, category): the lanes walk the chunk list together (the header bytes
+// are a broadcast load) and OR the codes of up to 256 entries per chunk into the zeroed packed column.  Rows outside
+// [row_lo, row_hi) are skipped (row sharding: every rank reads the same file and keeps its rows).
+__global__ void __launch_bounds__(256)
+snpdat_unpack_kernel(const uint8_t* __restrict__ file, const uint64_t* __restrict__ outer, int64_t j0, int64_t ncols, int64_t col_base,
+                     int64_t n_total, int64_t row_lo, int64_t row_hi, uint32_t* __restrict__ packed, int64_t ldw, int* __restrict__ err)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= ncols * 3) return;
+    const int64_t jl = item / 3; const int c = (int)(item - jl * 3);
+    const uint8_t* col = file + (outer[j0 + jl] - (uint64_t)col_base);
+    const uint8_t* q = col + snp_rd_u64(col + 8 * c);
+    const uint32_t n_chunks = snp_rd_u32(q); q += 4;
+    const uint32_t code = (c == 0) ? 3u : (uint32_t)c;
+    uint32_t* dst = packed + (j0 + jl) * ldw;
+    for (uint32_t k = 0; k < n_chunks; ++k) {
+        const int64_t base = (int64_t)snp_rd_u32(q) * 256;
+        const int cnt = (int)q[4] + 1;
+        for (int e = lane; e < cnt; e += 32) {
+            const int64_t row = base + q[5 + e];
+            if (row >= n_total) { *err = 1; continue; }
+            if (row < row_lo || row >= row_hi) continue;
+            const int64_t r = row - row_lo;
+            atomicOr(dst + (r >> 4), code << (2 * (int)(r & 15)));
+        }
+        q += 5 + cnt;
+    }
+}
+
+// int8 calldata (column-major, negative = missing) -> 2-bit codes; one thread per 16 rows
+__global__ void snp_pack_kernel(const int8_t* __restrict__ calldata, int64_t n, int64_t p, uint32_t* __restrict__ packed, int64_t ldw, int* __restrict__ err)
+{
+    const int64_t j = blockIdx.y;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < ldw; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t word = 0;
+        for (int k = 0; k < 16; ++k) {
+            const int64_t i = w * 16 + k;
+            if (i >= n) break;
+            const int8_t x = calldata[j * n + i];
+            if (x > 2) { *err = 1; continue; }
+            word |= (uint32_t)(x < 0 ? 3 : x) << (2 * k);
+        }
+        packed[j * ldw + w] = word;
+    }
+}
+
+template <class T> __device__ __forceinline__ T snp_value(uint32_t code, T imp) {
+    return (code & 2u) ? ((code & 1u) ? imp : T(2)) : ((code & 1u) ? T(1) : T(0));
+}
+
+// Decodes `count` columns starting at logical column j0 into dense columns out[c * ld + i] (pad rows = 0 since their code is 0).
+template <class T>
+__global__ void snp_decode_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const T* __restrict__ impute, int64_t j0, int count,
+                                  T* __restrict__ out, int64_t ld)
+{
+    const int c = blockIdx.y;
+    const T imp = impute[j0 + c];
+    const uint32_t* src = packed + (j0 + c) * ldw;
+    T* dst = out + (int64_t)c * ld;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < ldw; w += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t word = src[w];
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+            T x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = snp_value<T>((word >> (2 * (4 * k4 + k))) & 3u, imp);
+            if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst + w * 16 + 4 * k4) = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
+            else {
+                *reinterpret_cast<double2*>(dst + w * 16 + 4 * k4) = make_double2((double)x[0], (double)x[1]);
+                *reinterpret_cast<double2*>(dst + w * 16 + 4 * k4 + 2) = make_double2((double)x[2], (double)x[3]);
+            }
+        }
+    }
+}
+
+// Transposed GEMV on the packed bits (the `mul` / `sq_mul` of MatrixNaiveSNPUnphased, and of kron(X, I_K) for multi-response):
+//   out_part[(rb * q + c) * K + l] = sum_{i in row block rb} f(X[i, j0+c]) * v[i, l] * w[i, l]      (SQ: X^2 * w; w == nullptr: 1)
+// Every lane keeps the products v*w of its R rows (x KP classes) in registers for the whole kernel and walks the columns: per
+// column a warp reads 8*R contiguous bytes (R/4 bytes per lane), decodes R genotypes per lane and issues R*KP FMAs.  The
+// per-lane partials of a batch of 32/KP columns go through a padded shared-memory transpose (conflict free both ways) so that
+// lane t ends up with the warp total of value t; the 8 warps (8 consecutive row tiles) are then added in double.
+// grid = (column chunks, row blocks of 8*32*R rows).
+constexpr int kSnpGemvThreads = 256;
+template <class T> __host__ __device__ constexpr size_t snp_gemv_smem_bytes() { return sizeof(double) * (kSnpGemvThreads / 32) * 32 + sizeof(T) * (kSnpGemvThreads / 32) * 32 * 33; }
+template <int KP> __host__ __device__ constexpr int snp_gemv_rows_per_lane() { return (KP <= 2) ? 32 : (KP == 4 ? 16 : (KP == 8 ? 8 : 4)); }
+template <class T, int KP, bool SQ>
+__global__ void __launch_bounds__(kSnpGemvThreads)
+snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pad, const T* __restrict__ impute, int64_t j0, int q, int cols_per_cta,
+                  int K, const T* __restrict__ v, const T* __restrict__ w, double* __restrict__ out_part)
+{
+    constexpr int R = snp_gemv_rows_per_lane<KP>();                              // rows per lane
+    constexpr int NB = 32 / KP;                                                  // columns per reduction batch
+    constexpr int NW = kSnpGemvThreads / 32;
+    extern __shared__ __align__(16) unsigned char s_snp_raw[];
+    double (*s_tot)[32] = reinterpret_cast<double (*)[32]>(s_snp_raw);                               // [NW][32]
+    T (*s_acc)[32 * 33] = reinterpret_cast<T (*)[32 * 33]>(s_snp_raw + sizeof(double) * NW * 32);      // [NW][32 * 33]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = ((int64_t)blockIdx.y * NW + warp) * (32 * R) + (int64_t)lane * R;      // first row of this lane
+    const bool live = row0 < n_pad;                                                             // n_pad % 32 == 0 and R | 32
+    T vw[R * KP];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int l = 0; l < KP; ++l) {
+            T a = 0;
+            if (live && row0 + r < n_pad && l < K) {
+                const int64_t e = (row0 + r) * K + l;
+                a = SQ ? w[e] : (w ? v[e] * w[e] : v[e]);
+            }
+            vw[r * KP + l] = a;
+        }
+    const int c_begin = blockIdx.x * cols_per_cta;
+    const int c_end = min(q, c_begin + cols_per_cta);
+    for (int cb = c_begin; cb < c_end; cb += NB) {
+#pragma unroll 1
+        for (int cc = 0; cc < NB; ++cc) {
+            const int c = cb + cc;
+            T acc[KP];
+#pragma unroll
+            for (int l = 0; l < KP; ++l) acc[l] = 0;
+            if (c < c_end && live) {
+                const T imp = impute[j0 + c];
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(packed + (j0 + c) * ldw) + row0 / 4;
+                uint64_t bits;
+                if (R == 32) bits = *reinterpret_cast<const uint64_t*>(src);
+                else if (R == 16) bits = *reinterpret_cast<const uint32_t*>(src);
+                else if (R == 8) bits = *reinterpret_cast<const uint16_t*>(src);
+                else bits = *src;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    T x = snp_value<T>((uint32_t)(bits >> (2 * r)) & 3u, imp);
+                    if (SQ) x *= x;
+#pragma unroll
+                    for (int l = 0; l < KP; ++l) acc[l] += x * vw[r * KP + l];
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < KP; ++l) s_acc[warp][(cc * KP + l) * 33 + lane] = acc[l];
+        }
+        __syncwarp();
+        double tot = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) tot += (double)s_acc[warp][lane * 33 + k];
+        s_tot[warp][lane] = tot;
+        __syncthreads();
+        if (warp == 0) {
+            double s = 0;
+#pragma unroll
+            for (int wq = 0; wq < NW; ++wq) s += s_tot[wq][lane];
+            const int c = cb + lane / KP, l = lane % KP;
+            if (c < c_end && l < K) out_part[((size_t)blockIdx.y * q + c) * K + l] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// Random genotype matrix generated in HBM (ad.data.snp_unphased proportions, PY/data.py:312-359): each entry is 1 w.p. one_ratio, 2 w.p.
+// two_ratio, then masked as missing w.p. missing_ratio; Philox(seed, subsequence = column, offset = global row) so that every
+// row sharding sees the same matrix.  counts[j] = {ones, twos, missing} over the non-masked / masked entries of this shard.
+__global__ void snp_fill_random_kernel(uint32_t* __restrict__ packed, int64_t ldw, int64_t n, int64_t p, unsigned long long seed, int64_t row_offset,
+                                       float one_ratio, float two_ratio, float missing_ratio, unsigned long long* __restrict__ counts)
+{
+    const int64_t j = blockIdx.y;
+    unsigned long long c1 = 0, c2 = 0, c3 = 0;
+    for (int64_t wd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wd < ldw; wd += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t word = 0;
+        for (int k4 = 0; k4 < 4; ++k4) {
+            const int64_t i0 = wd * 16 + 4 * k4;
+            if (i0 >= n) break;
+            curandStatePhilox4_32_10_t st;
+            curand_init(seed, (unsigned long long)j, (unsigned long long)(2 * (row_offset + i0)), &st);
+            const float4 u = curand_uniform4(&st), m = curand_uniform4(&st);
+            const float uu[4] = {u.x, u.y, u.z, u.w}, mm[4] = {m.x, m.y, m.z, m.w};
+            for (int k = 0; k < 4 && i0 + k < n; ++k) {
+                uint32_t code = uu[k] <= one_ratio ? 1u : (uu[k] <= one_ratio + two_ratio ? 2u : 0u);
+                if (mm[k] <= missing_ratio) code = 3u;
+                c1 += code == 1u; c2 += code == 2u; c3 += code == 3u;
+                word |= code << (2 * (4 * k4 + k));
+            }
+        }
+        packed[j * ldw + wd] = word;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o); c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(counts + 3 * j, c1); atomicAdd(counts + 3 * j + 1, c2); atomicAdd(counts + 3 * j + 2, c3); }
+}
+
+} // namespace ab

@@ -258,8 +258,8 @@ struct PathState {
             const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g];
             GInfo gi{}; gi.item0 = items.size();
             if (K == 1) {
-                gi.f0 = (int)groups[g]; gi.k0 = 0; gi.nfeat = gs; gi.icpt = false;
-                items.push_back(CovItem{(int32_t)groups[g], gs, c_total, 0, 0});
+                gi.f0 = (int)X->phys_col(groups[g], gs); gi.k0 = 0; gi.nfeat = gs; gi.icpt = false;      // physical column (SNP: slot of the decoded-column cache)
+                items.push_back(CovItem{(int32_t)gi.f0, gs, c_total, 0, 0});
                 c_total += (int64_t)gs * gs;
             } else if (groups[g] < n_int) {
                 if (gs != 1) throw core_error("multi-response intercept columns must be groups of size 1.");
@@ -268,7 +268,8 @@ struct PathState {
                 c_total += 1;
             } else {
                 const idx_t c0 = groups[g] - n_int;
-                gi.f0 = (int)(c0 / K); gi.k0 = (int)(c0 % K); gi.nfeat = (gi.k0 + gs + K - 1) / K; gi.icpt = false;
+                gi.k0 = (int)(c0 % K); gi.nfeat = (gi.k0 + gs + K - 1) / K; gi.icpt = false;
+                gi.f0 = (int)X->phys_col(c0 / K, gi.nfeat);
                 for (int l = 0; l < K; ++l) {      // item for class l even when absent keeps the indexing simple (absent: skipped below)
                     items.push_back(CovItem{(int32_t)gi.f0, gi.nfeat, c_total, l, 0});
                     c_total += (int64_t)gi.nfeat * gi.nfeat;
@@ -340,7 +341,7 @@ struct PathState {
                 }
             }
             GroupMeta m{};
-            m.col = (K == 1) ? (int32_t)groups[g] : (gi.icpt ? -(int32_t)(groups[g] + 1) : (int32_t)(groups[g] - n_int)); m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
+            m.col = (K == 1) ? (int32_t)gi.f0 : (gi.icpt ? -(int32_t)(groups[g] + 1) : (int32_t)(gi.f0 * K + gi.k0)); m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
             m.pen = (double)penalty[g];
             meta[i] = m;
             gs_max_screen = std::max(gs_max_screen, gs); rec_max_screen = std::max(rec_max_screen, rec_pad);
@@ -381,7 +382,7 @@ struct PathState {
         const size_t b0 = (prev / B > 0) ? prev / B - 1 : 0;
         pl.Q.reserve_keep(nb * pstride + 64);          // (new tail zeroed; old panels keep their blocks)
         std::vector<PairItem> items; int64_t total = 0;
-        auto grp = [&](size_t pos, int& col, int& gs) { const idx_t g = screen_set[entries[pos]]; col = (int)groups[g]; gs = (int)group_sizes[g]; };
+        auto grp = [&](size_t pos, int& col, int& gs) { const idx_t g = screen_set[entries[pos]]; gs = (int)group_sizes[g]; col = (int)X->phys_col(groups[g], gs); };
         // only the blocks with a NEW group on either side are computed: the others are already in place
         for (size_t b = b0; b < nb; ++b) {
             const size_t p0 = b * B, p1 = std::min(N, p0 + B), p2 = std::min(N, p1 + B);

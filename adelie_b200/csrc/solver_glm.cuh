@@ -138,15 +138,16 @@ PinResult PathState<T>::fit_glm(T lmda_) {
         // ---- IRLS-weighted column means of every screen column (:361-372), one batched launch
         const size_t S = screen_set.size();
         const size_t vs = S ? (screen_begins.back() + group_sizes[screen_set.back()]) : 0;
-        std::vector<int32_t> cols(vs);
+        std::vector<int32_t> cols(vs), pcols(vs);     // logical columns / physical columns (SNP: slots of the decoded-column cache)
         for (size_t i = 0; i < S; ++i) {
             const idx_t g = screen_set[i];
-            for (idx_t c = 0; c < group_sizes[g]; ++c) cols[screen_begins[i] + c] = (int32_t)(groups[g] + c);
+            const int32_t pc = (K == 1) ? X->phys_col(groups[g], (int)group_sizes[g]) : 0;
+            for (idx_t c = 0; c < group_sizes[g]; ++c) { cols[screen_begins[i] + c] = (int32_t)(groups[g] + c); pcols[screen_begins[i] + c] = pc + (int32_t)c; }
         }
         std::vector<T> sx_means(vs);
         if (vs && K == 1) {           // multi-response runs with the state-level intercept off: the means are never used (left 0)
             d_cols.reserve_keep(vs); d_tmp.reserve_keep(vs);
-            d_cols.upload(cols.data(), vs);
+            d_cols.upload(pcols.data(), vs);
             X->d_gemv_t(0, d_cols.p, (int)vs, X->d_ones(), d_irls_w.p, d_tmp.p);
             DistContext::get().allreduce<T>(d_tmp.p, (int64_t)vs);
             d_tmp.download(sx_means.data(), vs);

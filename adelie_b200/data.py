@@ -63,3 +63,31 @@ def dense(n, p, G, *, K=1, glm="gaussian", equal_groups=False, rho=0, sparsity=0
     eta = X_sub @ beta_sub
     glm_obj = _sample_y(glm=glm, eta=eta, beta=beta_sub, rho=rho, snr=snr)
     return {"X": X, "glm": glm_obj, "groups": groups, "group_sizes": group_sizes, "penalty": penalty}
+
+
+def snp_unphased(n, p, *, K=1, glm="gaussian", sparsity=0.95, missing_ratio=0.1, one_ratio=0.25, two_ratio=0.05, zero_penalty=0, snr=1, seed=0):
+    """SNP unphased dataset (semantics and RNG call order of adelie/data.py:222-359): int8 calldata with ``one_ratio`` ones,
+    ``two_ratio`` twos, the response drawn from the complete matrix, then ``missing_ratio`` of the entries masked as -9."""
+    assert n >= 1 and p >= 1 and snr > 0 and seed >= 0
+    for r in (sparsity, missing_ratio, one_ratio, two_ratio, zero_penalty):
+        assert 0 <= r <= 1
+    np.random.seed(seed)
+    nz_ratio = one_ratio + two_ratio
+    n_nz = int(nz_ratio * n * p)
+    where = np.random.permutation(np.random.choice(n * p, n_nz, replace=False))
+    n_ones = int(one_ratio / nz_ratio * n_nz)
+    X = np.zeros((n, p), dtype=np.int8)
+    X.ravel()[where[:n_ones]] = 1
+    X.ravel()[where[n_ones:]] = 2
+    groups = np.arange(p)
+    group_sizes = np.ones(p, dtype=int)
+    penalty = np.sqrt(group_sizes)
+    penalty[np.random.choice(p, int(zero_penalty * p), replace=False)] = 0
+    penalty /= np.linalg.norm(penalty) / np.sqrt(p)
+    beta = np.random.normal(0, 1, (p, K))
+    support = np.random.choice(p, int((1 - sparsity) * p), replace=False)
+    beta_sub = beta[support]
+    eta = X[:, support] @ beta_sub
+    glm_obj = _sample_y(glm=glm, eta=eta, beta=beta_sub, snr=snr)
+    X.ravel()[np.random.choice(n * p, int(missing_ratio * n * p), replace=False)] = -9
+    return {"X": np.asfortranarray(X), "glm": glm_obj, "groups": groups, "group_sizes": group_sizes, "penalty": penalty}

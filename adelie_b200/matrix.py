@@ -262,6 +262,79 @@ class _DeviceSparse(_DeviceMatrix):
         return _csc((values, indices, indptr), shape=(self._n, self._p))
 
 
+class _SnpUnphased(_DeviceMatrix):
+    """SNP unphased matrix resident in HBM at 2 bits per genotype (reference: adelie.matrix.snp_unphased -> MatrixNaiveSNPUnphased,
+    CORE/matrix/matrix_naive_snp_unphased.ipp): entries 0 / 1 / 2 / impute[j] for a missing value of column j."""
+    def __init__(self, dtype, n, p, n_threads, maker, io=None):
+        _DeviceMatrix.__init__(self, dtype, n, p, n_threads)
+        self._io = io            # keep the IO handler alive like the reference wrapper (adelie/matrix.py:1292-1296)
+        self._maker = maker
+
+    def _make_handle(self):
+        h = C.c_void_p()
+        self._maker(h)
+        return h
+
+    def mean(self, weights, out):
+        out[...] = 0             # matrix_naive_snp_unphased.ipp:290-298
+
+    def var(self, centers, weights, out):
+        out[...] = 1             # matrix_naive_snp_unphased.ipp:300-309
+
+    def to_host(self):
+        """``(calldata, impute)``: column-major (n, p) int8 with -9 for missing, and the (p,) imputed values."""
+        cd = np.empty((self._n, self._p), dtype=np.int8, order="F"); imp = np.empty(self._p)
+        _lib.check(_lib.load().ab_matrix_snp_unphased_download(self._core(), _lib.ptr(cd), _lib.ptr(imp)))
+        return cd, imp
+
+    def cache_info(self):
+        """``(decoded columns resident in the dense cache, bytes of the packed genotypes)``."""
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().ab_matrix_snp_unphased_cache_info(self._core(), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+
+def snp_unphased(io, *, n_threads: int = 1, dtype=np.float64, rows=None):
+    """SNP unphased matrix from an ``adelie_b200.io.snp_unphased`` handler (adelie/matrix.py:1243-1298).
+    ``rows=(lo, hi)`` (extension) keeps only that row range of the file: the ranks of a row-sharded run share one file."""
+    if n_threads < 1:
+        raise RuntimeError("adelie_core: n_threads must be >= 1.")
+    if not io.is_read:
+        io.read()
+    lo, hi = (0, io.rows) if rows is None else (int(rows[0]), int(rows[1]))
+
+    def maker(h):
+        _lib.check(_lib.load().ab_matrix_snp_unphased_create(_lib.dtype_code(dtype), io._handle, lo, hi, int(n_threads), C.byref(h)))
+    m = _SnpUnphased(dtype, hi - lo, io.cols, n_threads, maker, io=io)
+    m._core()
+    return m
+
+
+def snp_unphased_from_calldata(calldata: np.ndarray, impute: np.ndarray, *, n_threads: int = 1, dtype=np.float64):
+    """Same matrix from an in-memory (n, p) int8 calldata array (negative = missing) and the (p,) imputed values, without a file."""
+    cd = np.asfortranarray(calldata, dtype=np.int8); imp = np.ascontiguousarray(impute, dtype=np.float64)
+
+    def maker(h):
+        _lib.check(_lib.load().ab_matrix_snp_unphased_from_calldata(_lib.dtype_code(dtype), _lib.ptr(cd), cd.shape[0], cd.shape[1], _lib.ptr(imp),
+                                                                     int(n_threads), C.byref(h)))
+    m = _SnpUnphased(dtype, cd.shape[0], cd.shape[1], n_threads, maker)
+    m._core()
+    return m
+
+
+def snp_unphased_device_random(n: int, p: int, *, dtype=np.float32, seed: int = 0, row_offset: int = 0, n_total: int = None,
+                               one_ratio: float = 0.25, two_ratio: float = 0.05, missing_ratio: float = 0.1):
+    """Random genotypes generated in HBM with a counter-based RNG (proportions of ``adelie.data.snp_unphased``); mean-imputed."""
+    n_total = n if n_total is None else n_total
+
+    def maker(h):
+        _lib.check(_lib.load().ab_matrix_snp_unphased_alloc_random(_lib.dtype_code(dtype), n, p, seed, row_offset, n_total, one_ratio, two_ratio,
+                                                                    missing_ratio, C.byref(h)))
+    m = _SnpUnphased(dtype, n, p, 1, maker)
+    m._core()
+    return m
+
+
 def sparse(mat, *, method: str = "naive", copy: bool = False, n_threads: int = 1):
     """Sparse matrix (adelie/matrix.py ``sparse``): a scipy CSC matrix (anything else is converted), float32 / float64."""
     import scipy.sparse as _sp

@@ -21,6 +21,7 @@ extern "C" {
 typedef struct ab_matrix ab_matrix;   /* adelie_core.matrix.MatrixNaive* handle */
 typedef struct ab_glm ab_glm;         /* adelie_core.glm.Glm* handle */
 typedef struct ab_state ab_state;     /* adelie_core.state.State*Naive handle */
+typedef struct ab_io_snp ab_io_snp;   /* adelie_core.io.IOSNPUnphased handle */
 
 enum { AB_F32 = 0, AB_F64 = 1 };
 enum { AB_OK = 0, AB_ERR_CORE = 1 /* adelie_core_error -> RuntimeError */, AB_ERR_CUDA = 2, AB_ERR_ARG = 3 };
@@ -69,6 +70,29 @@ int ab_matrix_sparse_create(int dtype, int64_t n, int64_t p, int64_t nnz, const 
 int ab_matrix_sparse_alloc_random(int dtype, int64_t n, int64_t p, int64_t nnz_per_col, uint64_t seed, ab_matrix** out);
 int ab_matrix_sparse_nnz(const ab_matrix* m, int64_t* out);
 int ab_matrix_sparse_download(ab_matrix* m, int64_t* indptr, int32_t* indices, void* values);
+/* adelie.io.snp_unphased (PY/io.py:114-196; IOSNPUnphased: BIND/py_io.cpp, CORE/io/io_snp_unphased.hpp:137-274, .ipp:9-305, read(): CORE/io/io_snp_base.ipp:20-84).
+   `.snpdat` reader / writer on the host: read_mode "file" | "mmap" | "auto"; write() takes column-major (n, p) int8 calldata (negative = missing, values > 2
+   rejected), impute_method "mean" (impute[] is an output) or "user" (impute[] is an input); get(): name in {"nnz","nnm","outer"} -> uint64, "impute" -> double;
+   to_dense(): (n, p) row-major int8 with -9 for missing. */
+int ab_io_snp_unphased_create(const char* filename, const char* read_mode, ab_io_snp** out);
+int ab_io_snp_unphased_free(ab_io_snp* io);
+int ab_io_snp_unphased_write(ab_io_snp* io, const int8_t* calldata, int64_t n, int64_t p, const char* impute_method, double* impute, int64_t impute_len,
+                             int n_threads, uint64_t* total_bytes);
+int ab_io_snp_unphased_read(ab_io_snp* io, uint64_t* total_bytes);
+int ab_io_snp_unphased_info(const ab_io_snp* io, int* is_read, int64_t* rows, int64_t* snps);
+int ab_io_snp_unphased_get(const ab_io_snp* io, const char* name, void* out);
+int ab_io_snp_unphased_to_dense(const ab_io_snp* io, int n_threads, int8_t* out);
+/* adelie.matrix.snp_unphased (PY/matrix.py:1243-1298; MatrixNaiveSNPUnphased{32,64}: BIND/py_matrix.cpp:1878-1968, CORE/matrix/matrix_naive_snp_unphased.ipp:10-309):
+   entries 0 / 1 / 2 / impute[j] (missing).  The file bytes are unpacked on the device into 2 bits per genotype; rows [row_lo, row_hi) of the file are kept
+   (row_hi < 0: all rows) so that the ranks of a row-sharded run can share one file.  Every ab_matrix_* operator applies. */
+int ab_matrix_snp_unphased_create(int dtype, const ab_io_snp* io, int64_t row_lo, int64_t row_hi, int n_threads, ab_matrix** out);
+int ab_matrix_snp_unphased_from_calldata(int dtype, const int8_t* calldata, int64_t n, int64_t p, const double* impute, int n_threads, ab_matrix** out);
+/* bench helper: random genotypes generated in HBM (1 w.p. one_ratio, 2 w.p. two_ratio, masked as missing w.p. missing_ratio; Philox per (column, global row):
+   every row sharding sees the same matrix); impute = column mean of the non-missing entries over all n_total rows (all-reduced when row-sharded) */
+int ab_matrix_snp_unphased_alloc_random(int dtype, int64_t n, int64_t p, uint64_t seed, int64_t row_offset, int64_t n_total,
+                                        double one_ratio, double two_ratio, double missing_ratio, ab_matrix** out);
+int ab_matrix_snp_unphased_download(ab_matrix* m, int8_t* calldata_out, double* impute_out);   /* column-major (n, p) int8, -9 = missing */
+int ab_matrix_snp_unphased_cache_info(const ab_matrix* m, int64_t* cached_cols, int64_t* packed_bytes);
 int ab_matrix_free(ab_matrix* m);
 int ab_matrix_rows(const ab_matrix* m, int64_t* out);
 int ab_matrix_cols(const ab_matrix* m, int64_t* out);
