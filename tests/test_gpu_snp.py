@@ -105,11 +105,14 @@ def test_solve_gaussian_snp_vs_dense_and_oracle(tmp_path, n, p):
     y = data["glm"].y
     kw = dict(tol=1e-12, early_exit=False, lmda_path_size=15, min_ratio=0.1)
     st, st_d, ref = _solve_pair(cX, X, ad.glm.gaussian(y), orc.glm_spec("gaussian", y), kw)
+    # p >> n: the fit saturates and the minimiser is ill-conditioned at the small lambdas; the reference's own test accepts atol = 1e-3
+    # there (T/test_solver.py:745-746), we keep 1e-4 relative; 1e-6 relative everywhere else
+    rtol = 1e-4 if p > 10 * n else 1e-6
     for other in (st_d, ref):
         assert len(st.lmdas) == len(other.lmdas)
         B, Bo = np.asarray(st.betas.todense()), np.asarray(other.betas.todense())
-        assert _rel(B, Bo) < 1e-6, _rel(B, Bo)
-        assert _rel(st.intercepts, other.intercepts) < 1e-6
+        assert _rel(B, Bo) < rtol, _rel(B, Bo)
+        assert _rel(st.intercepts, other.intercepts) < rtol
     cached, packed_bytes = cX.cache_info()
     assert 0 < cached <= p and packed_bytes >= n * p // 4          # only screened columns are ever decoded
 
@@ -142,12 +145,13 @@ def test_solve_multigaussian_snp(tmp_path, dtype, rtol, K):
     n, p = 2500, 90
     data, h, cX, X = _make(tmp_path, n, p, dtype, sparsity=0.8, seed=6, K=K, glm="multigaussian")
     Y = np.ascontiguousarray(data["glm"].y, dtype=dtype)
-    tol = 1e-12 if dtype == np.float64 else 1e-7
+    # the sweep stops when max_g sum(A * dbeta^2) / gs < tol, i.e. coefficients are accurate to ~sqrt(tol): 1e-14 for a 1e-6 comparison
+    tol = 1e-14 if dtype == np.float64 else 1e-7
     kw = dict(tol=tol, newton_tol=1e-12 if dtype == np.float64 else 1e-5, early_exit=False, lmda_path_size=12, min_ratio=0.1)
     st, st_d, ref = _solve_pair(cX, X, ad.glm.multigaussian(Y, dtype=dtype), orc.glm_spec("multigaussian", Y, dtype=dtype), kw)
     assert st.betas.shape == (len(st.lmdas), p * K)
-    assert _rel(np.asarray(st.betas.todense()), np.asarray(st_d.betas.todense())) < rtol
-    assert _rel(np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())) < rtol
+    B, Bd, Br = (np.asarray(s_.betas.todense()) for s_ in (st, st_d, ref))
+    assert _rel(B, Bd) < rtol and _rel(B, Br) < rtol, (_rel(B, Bd), _rel(B, Br), _rel(Bd, Br))
     assert _rel(st.intercepts, ref.intercepts) < rtol
 
 
