@@ -8,6 +8,7 @@
 #include "matrix.cuh"
 #include "dist.cuh"
 #include "glm.cuh"
+#include "cox.cuh"
 #include "solver.cuh"
 #include "solver_glm.cuh"
 #include <memory>
@@ -518,8 +519,15 @@ int ab_matrix_sp_tmul(ab_matrix* m, int64_t L, const int64_t* indptr, const int6
 
 // ------------------------------------------------------------------------------------------ glm
 template <class T>
-static Glm<T>* make_glm(int family, int64_t n, int64_t K, const void* y, const void* w) {
+static Glm<T>* make_glm(int family, int64_t n, int64_t K, const void* y, const void* w,
+                        const void* cox_start = nullptr, const void* cox_stop = nullptr, const int64_t* cox_strata = nullptr, int cox_tie_efron = 1) {
     switch (family) {
+        case AB_GLM_COX: {
+            if (!cox_start) throw core_error("start must be (n,) where status is (n,).");
+            if (!cox_stop) throw core_error("stop must be (n,) where status is (n,).");
+            if (!cox_strata) throw core_error("strata must be (n,) where status is (n,).");
+            return new GlmCox<T>((const T*)cox_start, (const T*)cox_stop, (const T*)y, cox_strata, (const T*)w, n, cox_tie_efron != 0);
+        }
         case AB_GLM_GAUSSIAN: return new GlmGaussian<T>((const T*)y, (const T*)w, n);
         case AB_GLM_BINOMIAL_LOGIT: return new GlmBinomialLogit<T>((const T*)y, (const T*)w, n);
         case AB_GLM_MULTIGAUSSIAN: return new GlmMultiGaussian<T>((const T*)y, (const T*)w, n, K);
@@ -539,9 +547,11 @@ extern "C" {
 int ab_glm_create(int dtype, int family, int64_t n, int64_t K, const void* y, const void* weights,
                   const void* cox_start, const void* cox_stop, const int64_t* cox_strata, int cox_tie_efron, ab_glm** out) {
     AB_TRY
-    (void)cox_start; (void)cox_stop; (void)cox_strata; (void)cox_tie_efron;
     auto* g = new ab_glm{dtype, family};
-    if (dtype == AB_F32) g->f32 = make_glm<float>(family, n, K, y, weights); else g->f64 = make_glm<double>(family, n, K, y, weights);
+    try {
+        if (dtype == AB_F32) g->f32 = make_glm<float>(family, n, K, y, weights, cox_start, cox_stop, cox_strata, cox_tie_efron);
+        else g->f64 = make_glm<double>(family, n, K, y, weights, cox_start, cox_stop, cox_strata, cox_tie_efron);
+    } catch (...) { delete g; throw; }
     *out = g;
     AB_CATCH
 }
