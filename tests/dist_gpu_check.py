@@ -11,6 +11,71 @@ import torch.distributed as td
 import adelie_b200 as ad
 
 
+def extra_checks(rank, world):
+    """Row-sharded multi-response and SNP paths (config 5's ingredients): every rank solved the full problem before init() ran in
+    `_EXTRA_SINGLE`; here the ranks solve the sharded problem together."""
+    ok = True
+    for name, (full, make_sharded, tol) in _EXTRA_SINGLE.items():
+        st = make_sharded()
+        assert st.error == "" and full.error == "", (st.error, full.error)
+        B, Bs = np.asarray(st.betas.todense()), np.asarray(full.betas.todense())
+        rel = np.max(np.abs(B - Bs)) / np.max(np.abs(Bs))
+        reli = np.max(np.abs(np.asarray(st.intercepts) - np.asarray(full.intercepts))) / max(1e-300, np.max(np.abs(np.asarray(full.intercepts))))
+        blob = [None] * world
+        td.all_gather_object(blob, B.tobytes())
+        same = all(b == blob[0] for b in blob)
+        good = len(st.lmdas) == len(full.lmdas) and rel < tol and reli < tol
+        if rank == 0:
+            print(f"{name}: rel_beta={rel:.2e} rel_icpt={reli:.2e} identical_on_all_ranks={same} -> {'ok' if good and same else 'FAIL'}", flush=True)
+        ok = ok and good and same
+    return ok
+
+
+_EXTRA_SINGLE = {}
+
+
+def prepare_extra():
+    """single-GPU solutions of the extra cases + closures that solve the same problem row-sharded (called after dist.init())"""
+    # multigaussian K = 4 on a dense matrix
+    rng = np.random.default_rng(3)
+    n, p, K = 24_000, 60, 4
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Bt = np.zeros((p, K)); Bt[:6] = rng.standard_normal((6, K))
+    Y = np.ascontiguousarray(X @ Bt + 0.3 + rng.standard_normal((n, K)))
+    kw = dict(tol=1e-13, early_exit=False, lmda_path_size=10, min_ratio=0.1, progress_bar=False)
+    full = ad.grpnet(X, ad.glm.multigaussian(Y), **kw)
+
+    def sharded_multi():
+        lo, hi = ad.dist.shard_rows(n)
+        return ad.grpnet(np.asfortranarray(X[lo:hi]), ad.glm.multigaussian(np.ascontiguousarray(Y[lo:hi])), **kw)
+    _EXTRA_SINGLE["multigaussian K=4 dense f64"] = (full, sharded_multi, 1e-6)
+
+    # snp_unphased: gaussian lasso and multigaussian K = 8 (config 5 layout), every rank keeps its rows of the same calldata
+    data = ad.data.snp_unphased(20_000, 80, seed=2, sparsity=0.8)
+    cd = data["X"]; ys = data["glm"].y
+    imp = np.sum(np.where(cd > 0, cd, 0), axis=0) / np.maximum(np.sum(cd >= 0, axis=0), 1)
+    Xs = ad.matrix.snp_unphased_from_calldata(cd, imp)
+    kws = dict(tol=1e-13, early_exit=False, lmda_path_size=10, min_ratio=0.1, progress_bar=False)
+    full_s = ad.grpnet(Xs, ad.glm.gaussian(ys), **kws)
+
+    def sharded_snp():
+        lo, hi = ad.dist.shard_rows(cd.shape[0])
+        return ad.grpnet(ad.matrix.snp_unphased_from_calldata(np.asfortranarray(cd[lo:hi]), imp), ad.glm.gaussian(ys[lo:hi]), **kws)
+    _EXTRA_SINGLE["snp_unphased gaussian f64"] = (full_s, sharded_snp, 1e-6)
+
+    dk = ad.data.snp_unphased(16_000, 48, seed=5, sparsity=0.8, K=8, glm="multigaussian")
+    cdk = dk["X"]; Yk = np.ascontiguousarray(dk["glm"].y, dtype=np.float32)
+    impk = np.sum(np.where(cdk > 0, cdk, 0), axis=0) / np.maximum(np.sum(cdk >= 0, axis=0), 1)
+    kwk = dict(tol=1e-7, newton_tol=1e-5, early_exit=False, lmda_path_size=10, min_ratio=0.1, progress_bar=False)
+    full_k = ad.grpnet(ad.matrix.snp_unphased_from_calldata(cdk, impk, dtype=np.float32), ad.glm.multigaussian(Yk, dtype=np.float32), **kwk)
+
+    def sharded_snp_multi():
+        lo, hi = ad.dist.shard_rows(cdk.shape[0])
+        return ad.grpnet(ad.matrix.snp_unphased_from_calldata(np.asfortranarray(cdk[lo:hi]), impk, dtype=np.float32),
+                         ad.glm.multigaussian(np.ascontiguousarray(Yk[lo:hi]), dtype=np.float32), **kwk)
+    _EXTRA_SINGLE["snp_unphased multigaussian K=8 f32"] = (full_k, sharded_snp_multi, 2e-4)
+
+
 def main():
     td.init_process_group("gloo")
     rank, world = td.get_rank(), td.get_world_size()
@@ -33,6 +98,7 @@ def main():
         common = dict(groups=data["groups"], penalty=data["penalty"].astype(dtype), early_exit=False, lmda_path_size=12, min_ratio=0.1,
                       progress_bar=False, **kw)
         results.append((n, p, glm_name, dtype, X, y, mk, common, ad.grpnet(X, mk(y), **common)))
+    prepare_extra()
     ad.dist.init()
     assert ad.dist.is_active() and ad.dist.world() == world
     ok = True
@@ -52,6 +118,7 @@ def main():
         if rank == 0:
             print(f"n={n} p={p} {glm_name} {np.dtype(dtype).name}: rows[{lo},{hi}) rel_beta={rel:.2e} rel_icpt={reli:.2e} identical_on_all_ranks={same} ncta={st.sweep_ncta} batch={st.sweep_batch} batched_launches={st.n_batched_launches} -> {'ok' if good and same else 'FAIL'}", flush=True)
         ok = ok and good and same
+    ok = extra_checks(rank, world) and ok
     if rank == 0:
         print("DIST PASS" if ok else "DIST FAIL", flush=True)
     td.barrier()
