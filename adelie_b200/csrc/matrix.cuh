@@ -213,13 +213,12 @@ struct DenseMatrix {
         constexpr int R = snp_gemv_rows_per_lane<KP>();
         const int64_t rows_per_cta = (int64_t)(kSnpGemvThreads / 32) * 32 * R;
         const int n_rb = (int)((ld + rows_per_cta - 1) / rows_per_cta);
-        constexpr int NB = 32 / KP;
         const int sms = DeviceInfo::get().sm_count;
-        int col_chunks = std::max(1, std::min((q + NB - 1) / NB, (8 * sms + n_rb - 1) / n_rb));
-        int cols_per_cta = ((q + col_chunks - 1) / col_chunks + NB - 1) / NB * NB;
+        int col_chunks = std::max(1, std::min((q + 31) / 32, (16 * sms + n_rb - 1) / n_rb));
+        int cols_per_cta = ((q + col_chunks - 1) / col_chunks + 31) / 32 * 32;
         col_chunks = (q + cols_per_cta - 1) / cols_per_cta;
         part.reserve_keep((size_t)n_rb * q * K, stream);
-        const size_t smem = snp_gemv_smem_bytes<T>();
+        const size_t smem = snp_gemv_smem_bytes<T, KP>();
         auto fn = snp_gemv_t_kernel<T, KP, SQ>;
         AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<dim3(col_chunks, n_rb), kSnpGemvThreads, smem, stream>>>(snp_packed.p, snp_ldw, ld, snp_impute.p, j0, q, cols_per_cta, K, v, w, part.p);

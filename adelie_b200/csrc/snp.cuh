@@ -282,23 +282,32 @@ __global__ void snp_decode_kernel(const uint32_t* __restrict__ packed, int64_t l
 //   out_part[(rb * q + c) * K + l] = sum_{i in row block rb} f(X[i, j0+c]) * v[i, l] * w[i, l]      (SQ: X^2 * w; w == nullptr: 1)
 // Every lane keeps the products v*w of its R rows (x KP classes) in registers for the whole kernel and walks the columns: per
 // column a warp reads 8*R contiguous bytes (R/4 bytes per lane), decodes R genotypes per lane and issues R*KP FMAs.  The
-// per-lane partials of a batch of 32/KP columns go through a padded shared-memory transpose (conflict free both ways) so that
-// lane t ends up with the warp total of value t; the 8 warps (8 consecutive row tiles) are then added in double.
-// grid = (column chunks, row blocks of 8*32*R rows).
-constexpr int kSnpGemvThreads = 256;
-template <class T> __host__ __device__ constexpr size_t snp_gemv_smem_bytes() { return sizeof(double) * (kSnpGemvThreads / 32) * 32 + sizeof(T) * (kSnpGemvThreads / 32) * 32 * 33; }
+// per-lane partials of a sub-batch of 32/KP columns go through a padded shared-memory transpose (conflict free both ways) so that
+// lane t ends up with the warp total of value t; once per 32 columns the 4 warps (4 consecutive row tiles) are added in double.
+// grid = (column chunks, row blocks of 4*32*R rows).
+constexpr int kSnpGemvThreads = 128;
 template <int KP> __host__ __device__ constexpr int snp_gemv_rows_per_lane() { return (KP <= 2) ? 32 : (KP == 4 ? 16 : (KP == 8 ? 8 : 4)); }
+template <class T, int KP> __host__ __device__ constexpr size_t snp_gemv_smem_bytes() {
+    return sizeof(double) * (kSnpGemvThreads / 32) * 32 * KP + sizeof(T) * (kSnpGemvThreads / 32) * 32 * 33;
+}
+// genotype r of a 32-bit word of codes, straight from constant-mask bit tests (no shifts): 0 / 1 / 2 / impute
+template <class T, int r> __device__ __forceinline__ T snp_pick(uint32_t word, T imp) {
+    const bool b0 = (word & (1u << (2 * r))) != 0, b1 = (word & (2u << (2 * r))) != 0;
+    const T lo = b0 ? T(1) : T(0), hi = b0 ? imp : T(2);
+    return b1 ? hi : lo;
+}
 template <class T, int KP, bool SQ>
 __global__ void __launch_bounds__(kSnpGemvThreads)
 snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pad, const T* __restrict__ impute, int64_t j0, int q, int cols_per_cta,
                   int K, const T* __restrict__ v, const T* __restrict__ w, double* __restrict__ out_part)
 {
     constexpr int R = snp_gemv_rows_per_lane<KP>();                              // rows per lane
-    constexpr int NB = 32 / KP;                                                  // columns per reduction batch
+    constexpr int NB = 32 / KP;                                                  // columns per warp-level reduction (sub-batch)
     constexpr int NW = kSnpGemvThreads / 32;
+    constexpr int NV = 32 * KP;                                                  // values per block-level reduction: 32 columns x KP classes
     extern __shared__ __align__(16) unsigned char s_snp_raw[];
-    double (*s_tot)[32] = reinterpret_cast<double (*)[32]>(s_snp_raw);                               // [NW][32]
-    T (*s_acc)[32 * 33] = reinterpret_cast<T (*)[32 * 33]>(s_snp_raw + sizeof(double) * NW * 32);      // [NW][32 * 33]
+    double (*s_tot)[NV] = reinterpret_cast<double (*)[NV]>(s_snp_raw);                                // [NW][32 columns * KP]
+    T (*s_acc)[32 * 33] = reinterpret_cast<T (*)[32 * 33]>(s_snp_raw + sizeof(double) * NW * NV);       // [NW][32 * 33]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = ((int64_t)blockIdx.y * NW + warp) * (32 * R) + (int64_t)lane * R;      // first row of this lane
     const bool live = row0 < n_pad;                                                             // n_pad % 32 == 0 and R | 32
@@ -308,7 +317,7 @@ snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pa
 #pragma unroll
         for (int l = 0; l < KP; ++l) {
             T a = 0;
-            if (live && row0 + r < n_pad && l < K) {
+            if (live && l < K) {
                 const int64_t e = (row0 + r) * K + l;
                 a = SQ ? w[e] : (w ? v[e] * w[e] : v[e]);
             }
@@ -316,44 +325,73 @@ snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pa
         }
     const int c_begin = blockIdx.x * cols_per_cta;
     const int c_end = min(q, c_begin + cols_per_cta);
-    for (int cb = c_begin; cb < c_end; cb += NB) {
+    const uint8_t* lane_base = reinterpret_cast<const uint8_t*>(packed) + row0 / 4;
+    for (int cb = c_begin; cb < c_end; cb += 32) {
 #pragma unroll 1
-        for (int cc = 0; cc < NB; ++cc) {
-            const int c = cb + cc;
-            T acc[KP];
+        for (int sub = 0; sub < KP; ++sub) {
+            constexpr int PF = NB < 4 ? NB : 4;          // columns whose bits are fetched together (independent loads in flight)
+#pragma unroll 1
+            for (int cc0 = 0; cc0 < NB; cc0 += PF) {
+                uint32_t w0[PF], w1[PF]; T imp[PF];
 #pragma unroll
-            for (int l = 0; l < KP; ++l) acc[l] = 0;
-            if (c < c_end && live) {
-                const T imp = impute[j0 + c];
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(packed + (j0 + c) * ldw) + row0 / 4;
-                uint64_t bits;
-                if (R == 32) bits = *reinterpret_cast<const uint64_t*>(src);
-                else if (R == 16) bits = *reinterpret_cast<const uint32_t*>(src);
-                else if (R == 8) bits = *reinterpret_cast<const uint16_t*>(src);
-                else bits = *src;
+                for (int u = 0; u < PF; ++u) {
+                    const int c = cb + sub * NB + cc0 + u;
+                    w0[u] = 0; w1[u] = 0; imp[u] = 0;             // code 0 everywhere: a column past the end contributes exact zeros
+                    if (c < c_end && live) {
+                        imp[u] = impute[j0 + c];
+                        const uint8_t* src = lane_base + (j0 + c) * ldw * 4;
+                        if (R == 32) { const uint2 q2 = *reinterpret_cast<const uint2*>(src); w0[u] = q2.x; w1[u] = q2.y; }
+                        else if (R == 16) w0[u] = *reinterpret_cast<const uint32_t*>(src);
+                        else if (R == 8) w0[u] = *reinterpret_cast<const uint16_t*>(src);
+                        else w0[u] = *src;
+                    }
+                }
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    T x = snp_value<T>((uint32_t)(bits >> (2 * r)) & 3u, imp);
-                    if (SQ) x *= x;
+                for (int u = 0; u < PF; ++u) {
+                    T acc[KP];
 #pragma unroll
-                    for (int l = 0; l < KP; ++l) acc[l] += x * vw[r * KP + l];
+                    for (int l = 0; l < KP; ++l) acc[l] = 0;
+                    T x[R];
+#define AB_SNP_PICK(r) if (r < R) x[r < R ? r : 0] = (r < 16) ? snp_pick<T, (r & 15)>(w0[u], imp[u]) : snp_pick<T, (r & 15)>(w1[u], imp[u]);
+                    AB_SNP_PICK(0) AB_SNP_PICK(1) AB_SNP_PICK(2) AB_SNP_PICK(3) AB_SNP_PICK(4) AB_SNP_PICK(5) AB_SNP_PICK(6) AB_SNP_PICK(7)
+                    AB_SNP_PICK(8) AB_SNP_PICK(9) AB_SNP_PICK(10) AB_SNP_PICK(11) AB_SNP_PICK(12) AB_SNP_PICK(13) AB_SNP_PICK(14) AB_SNP_PICK(15)
+                    AB_SNP_PICK(16) AB_SNP_PICK(17) AB_SNP_PICK(18) AB_SNP_PICK(19) AB_SNP_PICK(20) AB_SNP_PICK(21) AB_SNP_PICK(22) AB_SNP_PICK(23)
+                    AB_SNP_PICK(24) AB_SNP_PICK(25) AB_SNP_PICK(26) AB_SNP_PICK(27) AB_SNP_PICK(28) AB_SNP_PICK(29) AB_SNP_PICK(30) AB_SNP_PICK(31)
+#undef AB_SNP_PICK
+                    if (KP == 1) {                  // two independent FMA chains per column
+                        T a0 = 0, a1 = 0;
+#pragma unroll
+                        for (int r = 0; r < R; r += 2) {
+                            const T x0 = SQ ? x[r] * x[r] : x[r], x1 = SQ ? x[r + 1] * x[r + 1] : x[r + 1];
+                            a0 += x0 * vw[r]; a1 += x1 * vw[r + 1];
+                        }
+                        acc[0] = a0 + a1;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const T xr = SQ ? x[r] * x[r] : x[r];
+#pragma unroll
+                            for (int l = 0; l < KP; ++l) acc[l] += xr * vw[r * KP + l];
+                        }
+                    }
+#pragma unroll
+                    for (int l = 0; l < KP; ++l) s_acc[warp][((cc0 + u) * KP + l) * 33 + lane] = acc[l];
                 }
             }
-#pragma unroll
-            for (int l = 0; l < KP; ++l) s_acc[warp][(cc * KP + l) * 33 + lane] = acc[l];
-        }
-        __syncwarp();
-        double tot = 0;
+            __syncwarp();
+            T tot = 0;
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) tot += (double)s_acc[warp][lane * 33 + k];
-        s_tot[warp][lane] = tot;
+            for (int k = 0; k < 32; ++k) tot += s_acc[warp][lane * 33 + k];
+            s_tot[warp][sub * 32 + lane] = (double)tot;
+            __syncwarp();
+        }
         __syncthreads();
-        if (warp == 0) {
-            double s = 0;
+        for (int idx = tid; idx < NV; idx += kSnpGemvThreads) {
+            double sum = 0;
 #pragma unroll
-            for (int wq = 0; wq < NW; ++wq) s += s_tot[wq][lane];
-            const int c = cb + lane / KP, l = lane % KP;
-            if (c < c_end && l < K) out_part[((size_t)blockIdx.y * q + c) * K + l] = s;
+            for (int wq = 0; wq < NW; ++wq) sum += s_tot[wq][idx];
+            const int c = cb + idx / KP, l = idx % KP;
+            if (c < c_end && l < K) out_part[((size_t)blockIdx.y * q + c) * K + l] = sum;
         }
         __syncthreads();
     }

@@ -779,6 +779,30 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                 const bool icpt = m.col < 0;
                 const int kcls = icpt ? (-m.col - 1) : 0;
                 const int k0 = icpt ? 0 : m.col % K;
+                if (!icpt && k0 == 0 && gs == K && (K % VN) == 0) {
+                    // one feature x all K classes (the snp_unphased / multigaussian layout of config 5): a row's K residuals and
+                    // weights are contiguous, so they come in with 16-byte loads and one X element serves all K products
+                    T acc[CB];
+#pragma unroll
+                    for (int cc = 0; cc < CB; ++cc) acc[cc] = 0;
+#pragma unroll 2
+                    for (int i = ctid; i < rows; i += NTC) {
+                        const T x = xs[i];
+                        const T* rrow = rr + (size_t)i * K; const T* wrow = ww + (size_t)i * K;
+#pragma unroll
+                        for (int kv = 0; kv < CB / VN; ++kv) {
+                            if (kv * VN < K) {
+                                T rv[VN], wv[VN];
+                                vec_load<T>(rrow + kv * VN, rv); vec_load<T>(wrow + kv * VN, wv);
+#pragma unroll
+                                for (int k = 0; k < VN; ++k) acc[kv * VN + k] += x * (wv[k] * rv[k]);
+                            }
+                        }
+                    }
+                    const T tot = warp_reduce16<T>(acc, lane);
+                    const int col = (lane >> 1) & 15;
+                    if ((lane & 1) == 0 && col < gs) wpart[(size_t)warp * gsc + col] = (double)tot;
+                } else
 #pragma unroll 1
                 for (int c0 = 0; c0 < gs; c0 += CB) {
                     T acc[CB]; int fo[CB], ko[CB];
@@ -995,6 +1019,26 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             if (changed_now && K > 1) {                                      // r[i, class] += X[i, feature] * del[feature * K + class]
                 const bool icpt = m.col < 0;
                 const int kcls = icpt ? (-m.col - 1) : 0;
+                if (!icpt && (m.col % K) == 0 && gs == K && (K % VN) == 0) {
+                    T d[CB];
+#pragma unroll
+                    for (int cc = 0; cc < CB; ++cc) d[cc] = (cc < gs) ? s_del[cc] : T(0);
+#pragma unroll 2
+                    for (int i = ctid; i < rows; i += NTC) {
+                        const T x = xs[i];
+                        T* rrow = rr + (size_t)i * K;
+#pragma unroll
+                        for (int kv = 0; kv < CB / VN; ++kv) {
+                            if (kv * VN < K) {
+                                T rv[VN];
+                                vec_load<T>(rrow + kv * VN, rv);
+#pragma unroll
+                                for (int k = 0; k < VN; ++k) rv[k] += x * d[kv * VN + k];
+                                vec_store<T>(rrow + kv * VN, rv);
+                            }
+                        }
+                    }
+                } else
 #pragma unroll 1
                 for (int i = ctid; i < rows; i += NTC) {
                     T* rrow = rr + (size_t)i * K;
