@@ -13,3 +13,6 @@ ncu --set full --clock-control none --import-source on -k regex:snp_decode_kerne
     python scripts/explore_c5.py > gpurun_out/${TAG}_decode.log 2>&1 || true
 tail -4 gpurun_out/${TAG}_launches.log
 ls -la gpurun_out | grep ${TAG}
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${TAG}_cox_launches.csv \
+    python scripts/cox_bench.py > gpurun_out/${TAG}_cox.log 2>&1 || true
+python scripts/cox_bench.py > gpurun_out/${TAG}_cox_unprofiled.log 2>&1 || true
