@@ -300,7 +300,7 @@ static DenseMatrix<T>* snp_from_calldata(const int8_t* calldata, int64_t n, int6
     for (int64_t j0 = 0; j0 < p; j0 += cols_per) {
         const int64_t jc = std::min(cols_per, p - j0);
         AB_CUDA(cudaMemcpyAsync(d_call.p, calldata + j0 * n, (size_t)jc * n, cudaMemcpyHostToDevice, 0));
-        snp_pack_kernel<<<dim3((unsigned)std::min<int64_t>(64, (M->snp_ldw + 255) / 256), (unsigned)jc), 256>>>(d_call.p, n, jc, M->snp_packed.p + j0 * M->snp_ldw, M->snp_ldw, d_err.p);
+        snp_pack_kernel<<<dim3((unsigned)jc, (unsigned)std::min<int64_t>(64, (M->snp_ldw + 255) / 256)), 256>>>(d_call.p, n, jc, M->snp_packed.p + j0 * M->snp_ldw, M->snp_ldw, d_err.p);
         AB_CUDA(cudaGetLastError());
         AB_CUDA(cudaStreamSynchronize(0));
     }
@@ -313,7 +313,7 @@ template <class T>
 static DenseMatrix<T>* snp_random(int64_t n, int64_t p, uint64_t seed, int64_t row_offset, int64_t n_total, double one_ratio, double two_ratio, double missing_ratio) {
     auto M = std::unique_ptr<DenseMatrix<T>>(new DenseMatrix<T>(n, p, typename DenseMatrix<T>::SnpTag{}));
     DevBuf<unsigned long long> d_counts((size_t)3 * p);
-    snp_fill_random_kernel<<<dim3((unsigned)std::min<int64_t>(32, (M->snp_ldw + 255) / 256), (unsigned)p), 256>>>(
+    snp_fill_random_kernel<<<dim3((unsigned)p, (unsigned)std::min<int64_t>(32, (M->snp_ldw + 255) / 256)), 256>>>(
         M->snp_packed.p, M->snp_ldw, n, p, seed, row_offset, (float)one_ratio, (float)two_ratio, (float)missing_ratio, d_counts.p);
     AB_CUDA(cudaGetLastError());
     std::vector<unsigned long long> cnt((size_t)3 * p);

@@ -140,8 +140,8 @@ struct BatchLaunch { const T* panels_screen; const T* panels_active; int n_activ
 // xorshift-free counter based fill: X[i, j] ~ N(0,1) from Philox(seed, subsequence = column, offset = row)
 template <class T>
 __global__ void fill_normal_kernel(T* X, int64_t ld, int64_t n, int64_t p, unsigned long long seed, int64_t row_offset) {
-    const int64_t j = blockIdx.y;
-    for (int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (int64_t)gridDim.x * blockDim.x * 4) {
+    const int64_t j = blockIdx.x;                     // columns on grid.x (no 65535 limit), row blocks on grid.y
+    for (int64_t i4 = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 4; i4 < n; i4 += (int64_t)gridDim.y * blockDim.x * 4) {
         curandStatePhilox4_32_10_t st;
         curand_init(seed, (unsigned long long)j, (unsigned long long)(row_offset + i4), &st);
         const float4 z = curand_normal4(&st);
@@ -200,7 +200,7 @@ struct DenseMatrix {
             store = std::move(bigger); X = store.p; cache_cap = want;
         }
         const int32_t slot = (int32_t)cache_used;
-        dim3 grid((unsigned)std::min<int64_t>(64, (snp_ldw + 255) / 256), (unsigned)count);
+        dim3 grid((unsigned)count, (unsigned)std::min<int64_t>(64, (snp_ldw + 255) / 256));
         snp_decode_kernel<T><<<grid, 256, 0, stream>>>(snp_packed.p, snp_ldw, snp_impute.p, col, count, X + (int64_t)slot * ld, ld);
         AB_CUDA(cudaGetLastError());
         cache_used += count; n_decoded_cols += count;
@@ -211,8 +211,10 @@ struct DenseMatrix {
     template <int KP, bool SQ>
     int snp_gemv_launch(int64_t j0, int q, int K, const T* v, const T* w) {
         constexpr int R = snp_gemv_rows_per_lane<KP>();
-        const int64_t rows_per_cta = (int64_t)(kSnpGemvThreads / 32) * 32 * R;
-        const int n_rb = (int)((ld + rows_per_cta - 1) / rows_per_cta);
+        const int64_t rows_per_tile = (int64_t)(kSnpGemvThreads / 32) * 32 * R;
+        const int n_tiles = (int)((ld + rows_per_tile - 1) / rows_per_tile);
+        const int tiles_per_cta = (n_tiles + 31) / 32;                            // at most 32 partial rows for the final reduction
+        const int n_rb = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
         const int sms = DeviceInfo::get().sm_count;
         int col_chunks = std::max(1, std::min((q + 31) / 32, (16 * sms + n_rb - 1) / n_rb));
         int cols_per_cta = ((q + col_chunks - 1) / col_chunks + 31) / 32 * 32;
@@ -221,7 +223,7 @@ struct DenseMatrix {
         const size_t smem = snp_gemv_smem_bytes<T, KP>();
         auto fn = snp_gemv_t_kernel<T, KP, SQ>;
         AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<dim3(col_chunks, n_rb), kSnpGemvThreads, smem, stream>>>(snp_packed.p, snp_ldw, ld, snp_impute.p, j0, q, cols_per_cta, K, v, w, part.p);
+        fn<<<dim3(col_chunks, n_rb), kSnpGemvThreads, smem, stream>>>(snp_packed.p, snp_ldw, ld, snp_impute.p, j0, q, cols_per_cta, tiles_per_cta, K, v, w, part.p);
         AB_CUDA(cudaGetLastError());
         return n_rb;
     }
@@ -270,7 +272,7 @@ struct DenseMatrix {
         AB_CUDA(cudaMemcpy2D(h, ldh * sizeof(T), X + col0 * ld + row0, ld * sizeof(T), nrows * sizeof(T), ncols, cudaMemcpyDeviceToHost));
     }
     void fill_normal(unsigned long long seed, int64_t row_offset) {
-        dim3 grid((unsigned)std::min<int64_t>(1024, (n + 1023) / 1024), (unsigned)p);
+        dim3 grid((unsigned)p, (unsigned)std::min<int64_t>(1024, (n + 1023) / 1024));
         fill_normal_kernel<T><<<grid, 256, 0, stream>>>(X, ld, n, p, seed, row_offset);
         AB_CUDA(cudaGetLastError());
     }

@@ -21,6 +21,7 @@
 #pragma once
 #include "common.cuh"
 #include "device_prims.cuh"
+#include "sweep.cuh"   // VecT / vec_load / vec_store
 #include <curand_kernel.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -235,8 +236,8 @@ snpdat_unpack_kernel(const uint8_t* __restrict__ file, const uint64_t* __restric
 // int8 calldata (column-major, negative = missing) -> 2-bit codes; one thread per 16 rows
 __global__ void snp_pack_kernel(const int8_t* __restrict__ calldata, int64_t n, int64_t p, uint32_t* __restrict__ packed, int64_t ldw, int* __restrict__ err)
 {
-    const int64_t j = blockIdx.y;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < ldw; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = blockIdx.x;                     // columns on grid.x (no 65535 limit), row blocks on grid.y
+    for (int64_t w = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; w < ldw; w += (int64_t)gridDim.y * blockDim.x) {
         uint32_t word = 0;
         for (int k = 0; k < 16; ++k) {
             const int64_t i = w * 16 + k;
@@ -258,11 +259,11 @@ template <class T>
 __global__ void snp_decode_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const T* __restrict__ impute, int64_t j0, int count,
                                   T* __restrict__ out, int64_t ld)
 {
-    const int c = blockIdx.y;
+    const int c = blockIdx.x;                          // columns on grid.x, row blocks on grid.y
     const T imp = impute[j0 + c];
     const uint32_t* src = packed + (j0 + c) * ldw;
     T* dst = out + (int64_t)c * ld;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < ldw; w += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t w = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; w < ldw; w += (int64_t)gridDim.y * blockDim.x) {
         const uint32_t word = src[w];
 #pragma unroll
         for (int k4 = 0; k4 < 4; ++k4) {
@@ -287,8 +288,12 @@ __global__ void snp_decode_kernel(const uint32_t* __restrict__ packed, int64_t l
 // grid = (column chunks, row blocks of 4*32*R rows).
 constexpr int kSnpGemvThreads = 128;
 template <int KP> __host__ __device__ constexpr int snp_gemv_rows_per_lane() { return (KP <= 2) ? 32 : (KP == 4 ? 16 : (KP == 8 ? 8 : 4)); }
+// per-warp scratch (elements): the 32 x 33 transpose of the partials, also used to stage the warp's v*w tile (32 lanes x (R*KP + 4 pad))
+template <int KP> __host__ __device__ constexpr int snp_gemv_warp_scratch() {
+    return (32 * (snp_gemv_rows_per_lane<KP>() * KP + 4) > 32 * 33) ? 32 * (snp_gemv_rows_per_lane<KP>() * KP + 4) : 32 * 33;
+}
 template <class T, int KP> __host__ __device__ constexpr size_t snp_gemv_smem_bytes() {
-    return sizeof(double) * (kSnpGemvThreads / 32) * 32 * KP + sizeof(T) * (kSnpGemvThreads / 32) * 32 * 33;
+    return sizeof(double) * (kSnpGemvThreads / 32) * 32 * KP + sizeof(T) * (kSnpGemvThreads / 32) * snp_gemv_warp_scratch<KP>();
 }
 // genotype r of a 32-bit word of codes, straight from constant-mask bit tests (no shifts): 0 / 1 / 2 / impute
 template <class T, int r> __device__ __forceinline__ T snp_pick(uint32_t word, T imp) {
@@ -299,7 +304,7 @@ template <class T, int r> __device__ __forceinline__ T snp_pick(uint32_t word, T
 template <class T, int KP, bool SQ>
 __global__ void __launch_bounds__(kSnpGemvThreads)
 snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pad, const T* __restrict__ impute, int64_t j0, int q, int cols_per_cta,
-                  int K, const T* __restrict__ v, const T* __restrict__ w, double* __restrict__ out_part)
+                  int tiles_per_cta, int K, const T* __restrict__ v, const T* __restrict__ w, double* __restrict__ out_part)
 {
     constexpr int R = snp_gemv_rows_per_lane<KP>();                              // rows per lane
     constexpr int NB = 32 / KP;                                                  // columns per warp-level reduction (sub-batch)
@@ -307,26 +312,67 @@ snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pa
     constexpr int NV = 32 * KP;                                                  // values per block-level reduction: 32 columns x KP classes
     extern __shared__ __align__(16) unsigned char s_snp_raw[];
     double (*s_tot)[NV] = reinterpret_cast<double (*)[NV]>(s_snp_raw);                                // [NW][32 columns * KP]
-    T (*s_acc)[32 * 33] = reinterpret_cast<T (*)[32 * 33]>(s_snp_raw + sizeof(double) * NW * NV);       // [NW][32 * 33]
+    constexpr int WS = snp_gemv_warp_scratch<KP>();
+    T (*s_acc)[WS] = reinterpret_cast<T (*)[WS]>(s_snp_raw + sizeof(double) * NW * NV);                 // [NW][warp scratch]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t row0 = ((int64_t)blockIdx.y * NW + warp) * (32 * R) + (int64_t)lane * R;      // first row of this lane
-    const bool live = row0 < n_pad;                                                             // n_pad % 32 == 0 and R | 32
-    T vw[R * KP];
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int l = 0; l < KP; ++l) {
-            T a = 0;
-            if (live && l < K) {
-                const int64_t e = (row0 + r) * K + l;
-                a = SQ ? w[e] : (w ? v[e] * w[e] : v[e]);
-            }
-            vw[r * KP + l] = a;
-        }
     const int c_begin = blockIdx.x * cols_per_cta;
     const int c_end = min(q, c_begin + cols_per_cta);
-    const uint8_t* lane_base = reinterpret_cast<const uint8_t*>(packed) + row0 / 4;
     for (int cb = c_begin; cb < c_end; cb += 32) {
+        for (int k = lane; k < NV; k += 32) s_tot[warp][k] = 0;
+        __syncwarp();
+        // the CTA walks `tiles_per_cta` row tiles (NW * 32 * R rows each) for the same 32 columns: the number of partial rows the
+        // final reduction has to read stays small at large n (the products v*w of a tile are re-read from L2 per tile: < 2 % of the work)
+#pragma unroll 1
+        for (int tile = 0; tile < tiles_per_cta; ++tile) {
+        const int64_t wrow0 = (((int64_t)blockIdx.y * tiles_per_cta + tile) * NW + warp) * (32 * R);    // first row of this warp's tile
+        if (wrow0 >= n_pad) break;                                                                     // warp uniform
+        const int64_t row0 = wrow0 + (int64_t)lane * R;                                                 // first row of this lane
+        const bool live = row0 < n_pad;                                                                 // n_pad % 32 == 0 and R | 32
+        // the warp's tile of v*w (32*R rows x K classes, contiguous in memory) comes in with coalesced loads and goes through the
+        // warp's scratch so that every lane ends up with ITS R rows x KP classes in registers (row stride padded by 4: the 16-byte
+        // reads below are bank-conflict free)
+        T vw[R * KP];
+        {
+            constexpr int RS = R * KP + 4;
+            T* st = s_acc[warp];
+            if (K != KP) { for (int k = lane; k < 32 * RS; k += 32) st[k] = 0; __syncwarp(); }
+            const int64_t e0 = wrow0 * K, e_end = n_pad * K;
+            const int cnt = 32 * R * K;
+            constexpr int VNS = 16 / sizeof(T);
+            if (K == KP) {                                   // power-of-two class count: 16-byte loads / stores, shifts instead of divisions
+                constexpr int RK = R * KP;
+                for (int g = lane * VNS; g < 32 * RK; g += 32 * VNS) {
+                    T a[VNS];
+#pragma unroll
+                    for (int k = 0; k < VNS; ++k) a[k] = 0;
+                    if (e0 + g < e_end) {
+                        if (SQ || w) vec_load<T>(w + e0 + g, a);
+                        if (!SQ) {
+                            T b[VNS];
+                            vec_load<T>(v + e0 + g, b);
+#pragma unroll
+                            for (int k = 0; k < VNS; ++k) a[k] = w ? a[k] * b[k] : b[k];
+                        }
+                    }
+                    vec_store<T>(st + (g / RK) * RS + (g % RK), a);
+                }
+            } else
+            for (int g = lane; g < cnt; g += 32) {
+                T a = 0;
+                if (e0 + g < e_end) a = SQ ? w[e0 + g] : (w ? v[e0 + g] * w[e0 + g] : v[e0 + g]);
+                const int row = g / K, l = g - row * K;
+                st[(row / R) * RS + (row % R) * KP + l] = a;
+            }
+            __syncwarp();
+            constexpr int VNL = 16 / sizeof(T);
+#pragma unroll
+            for (int k = 0; k < R * KP; k += VNL) {
+                if (sizeof(T) == 4) { const float4 t4 = *reinterpret_cast<const float4*>(st + lane * RS + k); vw[k] = t4.x; vw[k + 1] = t4.y; vw[k + 2] = t4.z; vw[k + 3] = t4.w; }
+                else { const double2 t2 = *reinterpret_cast<const double2*>(st + lane * RS + k); vw[k] = t2.x; vw[k + 1] = t2.y; }
+            }
+            __syncwarp();
+        }
+        const uint8_t* lane_base = reinterpret_cast<const uint8_t*>(packed) + row0 / 4;
 #pragma unroll 1
         for (int sub = 0; sub < KP; ++sub) {
             constexpr int PF = NB < 4 ? NB : 4;          // columns whose bits are fetched together (independent loads in flight)
@@ -382,9 +428,10 @@ snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pa
             T tot = 0;
 #pragma unroll 8
             for (int k = 0; k < 32; ++k) tot += s_acc[warp][lane * 33 + k];
-            s_tot[warp][sub * 32 + lane] = (double)tot;
+            s_tot[warp][sub * 32 + lane] += (double)tot;
             __syncwarp();
         }
+        }   // row tiles
         __syncthreads();
         for (int idx = tid; idx < NV; idx += kSnpGemvThreads) {
             double sum = 0;
@@ -403,9 +450,9 @@ snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pa
 __global__ void snp_fill_random_kernel(uint32_t* __restrict__ packed, int64_t ldw, int64_t n, int64_t p, unsigned long long seed, int64_t row_offset,
                                        float one_ratio, float two_ratio, float missing_ratio, unsigned long long* __restrict__ counts)
 {
-    const int64_t j = blockIdx.y;
+    const int64_t j = blockIdx.x;                     // columns on grid.x, row blocks on grid.y
     unsigned long long c1 = 0, c2 = 0, c3 = 0;
-    for (int64_t wd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wd < ldw; wd += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t wd = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; wd < ldw; wd += (int64_t)gridDim.y * blockDim.x) {
         uint32_t word = 0;
         for (int k4 = 0; k4 < 4; ++k4) {
             const int64_t i0 = wd * 16 + 4 * k4;
