@@ -443,7 +443,7 @@ struct HostOps {
         CovItem it{M.phys_col(j, (int)q), (int32_t)q, 0};
         DevBuf<CovItem> di(1); di.upload(&it, 1);
         DevBuf<double> C((size_t)q * q);
-        M.d_cov(di.p, 1, q * q, dw.p, true, C.p);
+        M.d_cov(di.p, 1, q * q, dw.p, true, C.p, 1, (int)q);
         std::vector<double> h((size_t)q * q);
         C.download(h.data(), h.size()); AB_CUDA(cudaStreamSynchronize(0));
         for (int64_t a = 0; a < q; ++a) for (int64_t b = 0; b < q; ++b) out[a + b * q] = (T)h[a * q + b];

@@ -218,6 +218,77 @@ cov_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovItem* __
     }
 }
 
+// Single-pass variant for groups of at most GSP <= 12 columns: a thread keeps all GSP (GSP + 1) / 2 pair accumulators in registers,
+// so every element of X_g is loaded exactly once (16-byte loads along the rows) instead of once per 4x4 pair block -- at config 3
+// (5000 groups of 10, all re-decomposed in every IRLS iteration) the pair-block kernel re-read each group 6 times out of L2.
+template <class T, int GSP>
+__global__ void __launch_bounds__(256)
+cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovItem* __restrict__ items,
+                 const T* __restrict__ w, int w_is_sqrt, double* __restrict__ C_part, int64_t c_total, int rows_per_block, int K)
+{
+    constexpr int VN = VecT<T>::N;
+    constexpr int NP = GSP * (GSP + 1) / 2;
+    __shared__ double s_red[8][NP];
+    const CovItem it = items[blockIdx.x];
+    const int gs = it.gs;
+    const int rb = blockIdx.y;
+    const int64_t row0 = (int64_t)rb * rows_per_block;
+    const int64_t row1 = min((long long)n_pad, (long long)(row0 + rows_per_block));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool ones = it.col < 0;
+    const T* Xg = X + (int64_t)(ones ? 0 : it.col) * ld;
+    double acc[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) acc[q] = 0;
+    for (int64_t i = row0 + (int64_t)tid * VN; i < row1; i += 256 * VN) {
+        T wv[VN];
+        if (K == 1) vec_load<T>(w + i, wv);
+        else {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) wv[k] = w[(i + k) * K + it.cls];
+        }
+        if (w_is_sqrt) {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) wv[k] *= wv[k];
+        }
+        T x[GSP][VN];
+#pragma unroll
+        for (int a = 0; a < GSP; ++a) {
+            if (a < gs && !ones) vec_load<T>(Xg + (int64_t)a * ld + i, x[a]);
+            else {
+#pragma unroll
+                for (int k = 0; k < VN; ++k) x[a][k] = (a < gs) ? T(1) : T(0);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+            int q = 0;
+#pragma unroll
+            for (int a = 0; a < GSP; ++a) {
+                const double xw = (double)(x[a][k] * wv[k]);
+#pragma unroll
+                for (int b = 0; b <= a; ++b, ++q) acc[q] += xw * (double)x[b][k];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const double t = dev::warp_sum(acc[q]);
+        if (lane == 0) s_red[warp][q] = t;
+    }
+    __syncthreads();
+    if (tid < NP) {
+        double t = 0;
+        for (int wi = 0; wi < 8; ++wi) t += s_red[wi][tid];
+        int a = 0; while ((a + 1) * (a + 2) / 2 <= tid) ++a;          // tid = a (a + 1) / 2 + b, b <= a
+        const int b = tid - a * (a + 1) / 2;
+        if (a < gs) {
+            double* Cout = C_part + (size_t)rb * c_total + it.out_off;
+            Cout[a * gs + b] = t; Cout[b * gs + a] = t;
+        }
+    }
+}
+
 // out[k] = sum_rb part[rb * total + k]
 __global__ void sum_parts_kernel(const double* __restrict__ part, int n_rb, int64_t total, double* __restrict__ out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -371,7 +371,12 @@ struct DenseMatrix {
         AB_CUDA(cudaGetLastError());
     }
     // Batched Gram: C[out_off + a*gs + b] = X_g^T diag(w or w^2) X_g, device doubles (c_total entries)
-    void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out, int K = 1) {
+    // gs_max: largest group among the items when the caller knows it (<= 12 selects the single-pass register kernel), 0 = unknown
+    template <int GSP>
+    void cov_small_launch(dim3 grid, const CovItem* items_dev, const T* w, bool w_is_sqrt, double* out, int64_t c_total, int rows_per_block, int K) {
+        cov_small_kernel<T, GSP><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, out, c_total, rows_per_block, K);
+    }
+    void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out, int K = 1, int gs_max = 0) {
         if (n_items <= 0) return;
         if (sparse) {
             if (K != 1) throw core_error("multi-response problems are not supported on sparse matrices.");
@@ -385,13 +390,13 @@ struct DenseMatrix {
         rows_per_block = (rows_per_block + kRowAlign - 1) / kRowAlign * kRowAlign;
         n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
         dim3 grid(n_items, n_rb);
-        if (n_rb == 1) {
-            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, C_out, c_total, rows_per_block, K);
-        } else {
-            part.reserve_keep((size_t)n_rb * c_total, stream);
-            cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, part.p, c_total, rows_per_block, K);
-            sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
-        }
+        double* out = C_out;
+        if (n_rb > 1) { part.reserve_keep((size_t)n_rb * c_total, stream); out = part.p; }
+        if (gs_max >= 1 && gs_max <= 4) cov_small_launch<4>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
+        else if (gs_max > 4 && gs_max <= 8) cov_small_launch<8>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
+        else if (gs_max > 8 && gs_max <= 12) cov_small_launch<12>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
+        else cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, out, c_total, rows_per_block, K);
+        if (n_rb > 1) sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
         AB_CUDA(cudaGetLastError());
     }
 

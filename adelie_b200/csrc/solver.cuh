@@ -59,6 +59,69 @@ inline void host_jacobi_eigh(std::vector<double>& A, int q, std::vector<double>&
     V.swap(Vs);
 }
 
+// Batched device version of host_jacobi_eigh: one warp per matrix (q <= 32), matrix and eigenvectors in shared memory, the same
+// cyclic order of rotations and the same arithmetic as the host routine; lanes own a row / column element of each rotation.
+// The GLM path recomputes the eigendecomposition of EVERY screen group in every IRLS iteration (solver_glm_naive.hpp:376-385):
+// at config 3 that is 5000 10x10 problems x ~400 iterations, 24 s of single-threaded host time against ~0.1 s here.
+struct EigItem { int64_t off; int64_t d_off; int32_t q; int32_t pad; };
+constexpr int kEigWarps = 4;
+__global__ void __launch_bounds__(kEigWarps * 32)
+jacobi_eigh_kernel(const EigItem* __restrict__ items, int n_items, const double* __restrict__ A_in, double* __restrict__ V_out, double* __restrict__ D_out, int q_max)
+{
+    extern __shared__ double s_eig[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kEigWarps + warp;
+    if (item >= n_items) return;
+    const EigItem it = items[item];
+    const int q = it.q;
+    double* As = s_eig + (size_t)warp * (2 * q_max * q_max + 32);
+    double* Vs = As + q_max * q_max;
+    int* ord = reinterpret_cast<int*>(Vs + q_max * q_max);
+    for (int e = lane; e < q * q; e += 32) { As[e] = A_in[it.off + e]; Vs[e] = ((e / q) == (e % q)) ? 1.0 : 0.0; }
+    __syncwarp();
+    const int k = lane;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0, diag = 0;
+        if (k < q) for (int b = 0; b < q; ++b) { const double x = As[k * q + b]; if (b == k) diag += x * x; else off += x * x; }
+        for (int o = 16; o > 0; o >>= 1) { off += __shfl_xor_sync(0xffffffffu, off, o); diag += __shfl_xor_sync(0xffffffffu, diag, o); }
+        if (off <= 1e-31 * (diag + off) || off == 0) break;
+        for (int pi = 0; pi < q - 1; ++pi) for (int qi = pi + 1; qi < q; ++qi) {
+            const double apq = As[pi * q + qi];
+            if (apq == 0) continue;                                   // warp uniform
+            const double app = As[pi * q + pi], aqq = As[qi * q + qi];
+            const double theta = (aqq - app) / (2 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+            const double c = 1 / sqrt(t * t + 1), sn = t * c;
+            __syncwarp();
+            if (k < q) {
+                const double akp = As[k * q + pi], akq = As[k * q + qi];
+                As[k * q + pi] = c * akp - sn * akq; As[k * q + qi] = sn * akp + c * akq;
+            }
+            __syncwarp();
+            if (k < q) {
+                const double apk = As[pi * q + k], aqk = As[qi * q + k];
+                As[pi * q + k] = c * apk - sn * aqk; As[qi * q + k] = sn * apk + c * aqk;
+                const double vkp = Vs[k * q + pi], vkq = Vs[k * q + qi];
+                Vs[k * q + pi] = c * vkp - sn * vkq; Vs[k * q + qi] = sn * vkp + c * vkq;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {                                                  // ascending eigenvalues (stable insertion sort, q <= 32)
+        for (int a = 0; a < q; ++a) ord[a] = a;
+        for (int a = 1; a < q; ++a) {
+            const int o = ord[a]; const double d = As[o * q + o];
+            int b = a - 1;
+            while (b >= 0 && As[ord[b] * q + ord[b]] > d) { ord[b + 1] = ord[b]; --b; }
+            ord[b + 1] = o;
+        }
+    }
+    __syncwarp();
+    if (k < q) D_out[it.d_off + k] = As[ord[k] * q + ord[k]];
+    for (int e = lane; e < q * q; e += 32) V_out[it.off + e] = Vs[(e / q) * q + ord[e % q]];
+}
+
 // search_pivot (CORE/optimization/search_pivot.hpp:7-62)
 template <class T>
 inline int search_pivot(const std::vector<T>& x, const std::vector<T>& y, std::vector<T>& mses) {
@@ -280,7 +343,8 @@ struct PathState {
         double t_cov0 = now_s();
         d_cov_items.reserve_keep(items.size()); d_cov_out.reserve_keep(c_total);
         d_cov_items.upload(items.data(), items.size());
-        X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p, K);
+        int cov_gs_max = 0; for (const CovItem& ci : items) cov_gs_max = std::max(cov_gs_max, (int)ci.gs);
+        X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p, K, cov_gs_max);
         DistContext::get().allreduce<double>(d_cov_out.p, c_total);            // row-sharded: sum the local Gram blocks over ranks
         std::vector<double> C(c_total);
         d_cov_out.download(C.data(), c_total);
@@ -289,10 +353,21 @@ struct PathState {
         n_kernel_launches += 2;
         meta.resize(S);
         std::vector<double> Cg, D, V;
+        // ---- phase 1: centred Gram of every group, packed back to back (eig_in), offsets per group
+        std::vector<double> eig_in, eig_V, eig_D; std::vector<EigItem> eig_items; std::vector<int64_t> eig_slot(end - begin, -1);
+        {
+            int64_t off = 0, d_off = 0;
+            for (size_t i = begin; i < end; ++i) {
+                const int gs = (int)group_sizes[screen_set[i]];
+                if (gs > 1) { eig_slot[i - begin] = (int64_t)eig_items.size(); eig_items.push_back(EigItem{off, d_off, gs, 0}); off += (int64_t)gs * gs; d_off += gs; }
+            }
+            eig_in.resize(off); eig_V.resize(off); eig_D.resize(d_off);
+        }
         for (size_t i = begin; i < end; ++i) {
             const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g]; const idx_t sb = screen_begins[i];
             const GInfo& gi = ginfo[i - begin];
             for (int c = 0; c < gs; ++c) sXm[sb + c] = xmean(groups[g] + c);
+            if (gs == 1) continue;
             if (K == 1 || gi.icpt) {
                 const CovItem& it = items[gi.item0];
                 Cg.assign(C.begin() + it.out_off, C.begin() + it.out_off + (size_t)gs * gs);
@@ -305,11 +380,47 @@ struct PathState {
             }
             if (intercept)
                 for (int a = 0; a < gs; ++a) for (int b = 0; b < gs; ++b) Cg[(size_t)a * gs + b] -= (double)sXm[sb + a] * (double)sXm[sb + b];
+            std::copy(Cg.begin(), Cg.end(), eig_in.begin() + eig_items[eig_slot[i - begin]].off);
+        }
+        // ---- phase 2: eigendecompositions -- one batched launch on the device (groups of <= 32 columns), host Jacobi otherwise
+        bool eig_on_device = false;
+        if (Configs::device_eigh && eig_items.size() >= 16) {
+            int q_max = 0; for (const EigItem& e : eig_items) q_max = std::max(q_max, (int)e.q);
+            if (q_max <= 32) {
+                AB_TIME(timers, "eigh_device");
+                DevBuf<EigItem> d_items(eig_items.size()); DevBuf<double> d_in(eig_in.size()), d_V(eig_in.size()), d_D(eig_D.size());
+                d_items.upload(eig_items.data(), eig_items.size()); d_in.upload(eig_in.data(), eig_in.size());
+                const size_t smem = sizeof(double) * (size_t)kEigWarps * (2 * q_max * q_max + 32);
+                AB_CUDA(cudaFuncSetAttribute(jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                jacobi_eigh_kernel<<<(unsigned)((eig_items.size() + kEigWarps - 1) / kEigWarps), kEigWarps * 32, smem, 0>>>(
+                    d_items.p, (int)eig_items.size(), d_in.p, d_V.p, d_D.p, q_max);
+                AB_CUDA(cudaGetLastError());
+                d_V.download(eig_V.data(), eig_V.size()); d_D.download(eig_D.data(), eig_D.size());
+                AB_CUDA(cudaStreamSynchronize(0));
+                eig_on_device = true; ++n_kernel_launches;
+            }
+        }
+        // ---- phase 3: records
+        for (size_t i = begin; i < end; ++i) {
+            const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g]; const idx_t sb = screen_begins[i];
+            const GInfo& gi = ginfo[i - begin];
+            if (gs == 1) {
+                if (K == 1 || gi.icpt) Cg.assign(1, C[items[gi.item0].out_off]);
+                else Cg.assign(1, C[items[gi.item0 + gi.k0].out_off]);
+                if (intercept) Cg[0] -= (double)sXm[sb] * (double)sXm[sb];
+            } else if (eig_on_device) {
+                const EigItem& e = eig_items[eig_slot[i - begin]];
+                D.assign(eig_D.begin() + e.d_off, eig_D.begin() + e.d_off + gs);
+                V.assign(eig_V.begin() + e.off, eig_V.begin() + e.off + (size_t)gs * gs);
+            } else {
+                const EigItem& e = eig_items[eig_slot[i - begin]];
+                Cg.assign(eig_in.begin() + e.off, eig_in.begin() + e.off + (size_t)gs * gs);
+            }
             if (gs == 1) {
                 st[i].assign(1, T(1));
                 sv[sb] = std::max<T>((T)Cg[0], 0);
             } else {
-                host_jacobi_eigh(Cg, gs, D, V);
+                if (!eig_on_device) host_jacobi_eigh(Cg, gs, D, V);
                 st[i].resize((size_t)gs * gs);
                 for (size_t k = 0; k < (size_t)gs * gs; ++k) st[i][k] = (T)V[k];
                 for (int c = 0; c < gs; ++c) { const T d = (T)D[c]; sv[sb + c] = d * T(d >= 0); }      // :122
