@@ -401,7 +401,7 @@ struct DenseMatrix {
     }
 
     // Gram panels of the batched kernel: Q[out_off + a*ldq + b] = X[:, col_s+a]^T W X[:, col_t+b] for every item
-    void d_pair_gram(const PairItem* items_dev, int n_items, int64_t total, const T* w, T* Q, int ldq) {
+    void d_pair_gram(const PairItem* items_dev, int n_items, int64_t total, const T* w, T* Q, int ldq, int gs_max = 0) {
         if (n_items <= 0) return;
         const int sms = DeviceInfo::get().sm_count;
         int n_rb = std::max(1, std::min(sms, (8 * sms + n_items - 1) / n_items));
@@ -409,7 +409,8 @@ struct DenseMatrix {
         rows_per_block = (rows_per_block + kRowAlign - 1) / kRowAlign * kRowAlign;
         n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
         part.reserve_keep((size_t)(n_rb + 1) * total, stream);
-        pair_gram_kernel<T><<<dim3(n_items, n_rb), 256, 0, stream>>>(X, ld, ld, items_dev, w, part.p, total, rows_per_block);
+        if (sizeof(T) == 4 && gs_max > 5 && gs_max <= 10) pair_gram_kernel<T, 10><<<dim3(n_items, n_rb), 256, 0, stream>>>(X, ld, ld, items_dev, w, part.p, total, rows_per_block);
+        else pair_gram_kernel<T, 5><<<dim3(n_items, n_rb), 256, 0, stream>>>(X, ld, ld, items_dev, w, part.p, total, rows_per_block);
         DistContext& dc = DistContext::get();
         if (dc.active()) {
             // row-sharded: sum the row blocks, then the local blocks over the ranks, then scatter into the panels

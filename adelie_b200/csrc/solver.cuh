@@ -526,7 +526,7 @@ struct PathState {
             { AB_TIME(timers, "panels_launch");
               d_pair_items.reserve_keep(items.size());
               d_pair_items.upload(items.data(), items.size());
-              X->d_pair_gram(d_pair_items.p, (int)items.size(), total, d_w, pl.Q.p, ldq); }
+              X->d_pair_gram(d_pair_items.p, (int)items.size(), total, d_w, pl.Q.p, ldq, gs_max_screen); }
             { AB_TIME(timers, "panels_sync"); AB_CUDA(cudaStreamSynchronize(0)); }          // `items` (pageable host memory) must outlive the upload
             n_kernel_launches += 2;
         }

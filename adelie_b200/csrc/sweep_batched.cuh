@@ -1044,13 +1044,14 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
 // grid = (n_items, n_row_blocks); two-phase deterministic reduction through `part`.
 struct PairItem { int32_t col_s, gs_s, col_t, gs_t; int64_t out_off; int64_t part_off; };
 
-template <class T>
+// TS x TS register tile: TS = 5 takes a 10 x 10 block in 4 passes of 10 vector loads; TS = 10 (groups of <= 10 columns, float) in ONE
+// pass of 20 -- every element of both groups is loaded once per block.
+template <class T, int TS>
 __global__ void __launch_bounds__(256)
 pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairItem* __restrict__ items, const T* __restrict__ w,
                  double* __restrict__ part, int64_t total, int rows_per_block)
 {
     constexpr int VN = VecT<T>::N;
-    constexpr int TS = 5;                                  // 5 x 5 register tile: a 10 x 10 block takes 4 passes of 10 vector loads
     __shared__ double s_red[8][TS * TS + 1];
     const PairItem it = items[blockIdx.x];
     const int rb = blockIdx.y;
@@ -1068,7 +1069,7 @@ pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairI
 #pragma unroll
                 for (int y = 0; y < TS; ++y) acc[x][y] = 0;
             for (int64_t i = row0 + (int64_t)tid * VN; i < row1; i += 256 * VN) {
-                T wv[VN], xa[TS][VN], xb[TS][VN];
+                T wv[VN], xa[TS][VN];
                 vec_load<T>(w + i, wv);
 #pragma unroll
                 for (int x = 0; x < TS; ++x) {
@@ -1081,20 +1082,21 @@ pair_gram_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const PairI
                         for (int q = 0; q < VN; ++q) xa[x][q] = 0;
                     }
                 }
+                // target columns one at a time (the compiler keeps a few of these loads in flight): 10 x 10 accumulators + 10 source
+                // vectors already fill most of the register file
 #pragma unroll
                 for (int y = 0; y < TS; ++y) {
-                    if (b0 + y < it.gs_t) vec_load<T>(Xt + (int64_t)(b0 + y) * ld + i, xb[y]);
+                    T xb[VN];
+                    if (b0 + y < it.gs_t) vec_load<T>(Xt + (int64_t)(b0 + y) * ld + i, xb);
                     else {
 #pragma unroll
-                        for (int q = 0; q < VN; ++q) xb[y][q] = 0;
+                        for (int q = 0; q < VN; ++q) xb[q] = 0;
                     }
+#pragma unroll
+                    for (int x = 0; x < TS; ++x)
+#pragma unroll
+                        for (int q = 0; q < VN; ++q) acc[x][y] += xa[x][q] * xb[q];
                 }
-#pragma unroll
-                for (int x = 0; x < TS; ++x)
-#pragma unroll
-                    for (int y = 0; y < TS; ++y)
-#pragma unroll
-                        for (int q = 0; q < VN; ++q) acc[x][y] += xa[x][q] * xb[y][q];
             }
 #pragma unroll
             for (int x = 0; x < TS; ++x)
