@@ -81,6 +81,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "device_eigh") Configs::device_eigh = (int)value;
     else if (s == "sweep_profile") Configs::sweep_profile = (int)value;
     else if (s == "sweep_batch") Configs::sweep_batch = (int)value;
+    else if (s == "sweep_xchg") Configs::sweep_xchg = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -98,6 +99,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "device_eigh") *value = Configs::device_eigh;
     else if (s == "sweep_profile") *value = Configs::sweep_profile;
     else if (s == "sweep_batch") *value = Configs::sweep_batch;
+    else if (s == "sweep_xchg") *value = Configs::sweep_xchg;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }

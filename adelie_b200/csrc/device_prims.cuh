@@ -81,6 +81,26 @@ __device__ __forceinline__ bool ll_try_load(const LLLine* line, uint32_t epoch, 
     return false;
 }
 
+// ---- one-hop exchange through L2 atomics -----------------------------------------------------
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+    asm volatile("red.relaxed.gpu.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double* p, double v) { asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 constexpr uint32_t kSpinCheck = 0x3ffu;               // look at the clock / abort flag every 1024 spins
 constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;   // give up (abort the kernel) after 4 s in one wait
 

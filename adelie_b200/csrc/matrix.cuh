@@ -23,6 +23,7 @@ namespace ab {
 // Per-device resources of the fused sweep kernel: LL exchange lines, epoch, abort flag.
 struct SweepContext {
     DevBuf<dev::LLLine> ll, ll2; DevBuf<uint32_t> epoch; DevBuf<int> abort_flag;
+    DevBuf<double> xs_sum; DevBuf<uint32_t> xs_cnt;      // one-hop atomic exchange (sweep.cuh): [4][ll_gs_cap] sums, [4][32] arrival counters
     int ncta_pad = 0; int ll_gs_cap = kGsMax;
     static SweepContext& get() {
         static thread_local SweepContext* ctx[64] = {nullptr};
@@ -37,6 +38,7 @@ struct SweepContext {
             uint32_t one = 1;
             c->epoch.upload(&one, 1);
             c->abort_flag.alloc(1);
+            c->xs_sum.alloc((size_t)4 * c->ll_gs_cap); c->xs_cnt.alloc(4 * 32);
             AB_CUDA(cudaDeviceSynchronize());
             ctx[dev] = c;
         }
@@ -507,6 +509,11 @@ struct DenseMatrix {
         a.active_set = L.active_set; a.sc = L.sc;
         a.ll = ctx.ll.p; a.ll_gs_cap = ctx.ll_gs_cap; a.ncta_pad = g.ncta_pad;
         a.ll2 = ctx.ll2.p;
+        a.xs_sum = ctx.xs_sum.p; a.xs_cnt = ctx.xs_cnt.p; a.xchg_atomic = Configs::sweep_xchg ? 1 : 0;
+        if (a.xchg_atomic && g.ncta > 1) {       // all four slots start clean (the batched kernel advances the shared epoch between launches)
+            AB_CUDA(cudaMemsetAsync(ctx.xs_sum.p, 0, ctx.xs_sum.n * sizeof(double), stream));
+            AB_CUDA(cudaMemsetAsync(ctx.xs_cnt.p, 0, ctx.xs_cnt.n * sizeof(uint32_t), stream));
+        }
         { int f = 1; while (f * f < g.ncta) ++f; a.fan = std::max(1, f); }      // fan = ceil(sqrt(ncta)) => n_groups <= fan + 1 <= 32
         a.epoch = ctx.epoch.p; a.abort_flag = ctx.abort_flag.p;
         {

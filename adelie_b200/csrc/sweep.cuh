@@ -73,6 +73,9 @@ struct PinKernelArgs {
     PinScalars* sc;
     dev::LLLine* ll; int ll_gs_cap; int ncta_pad;
     dev::LLLine* ll2; int fan;       // two-level exchange: level-2 lines [2][ll_gs_cap][32]; fan = CTAs per level-1 group
+    // one-hop exchange through L2 atomics (Configs::sweep_xchg == 1): xs_sum [4 slots][ll_gs_cap] doubles, xs_cnt [4 slots][32] arrival
+    // counters (one 128-byte line each); all zero at kernel start, slot = epoch & 3
+    double* xs_sum; uint32_t* xs_cnt; int xchg_atomic;
     // multi-GPU (row-sharded) level 3: ll3_peer[r] = rank r's line buffer [2][kGsMax][kMaxRanksDev] mapped over NVLink
     dev::LLLine* ll3_peer[8]; int rank, world;
     uint32_t* epoch; int* abort_flag;
@@ -667,6 +670,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
     // two-level exchange geometry: level-1 groups of `fan` consecutive CTAs, led by their first member
     const int fan = a.fan;
     const int my_group = cta / fan, n_groups = (ncta + fan - 1) / fan;
+    const bool xatomic = a.xchg_atomic != 0;
     const int grp_first = my_group * fan, grp_size = min(fan, ncta - grp_first);
     const bool is_leader = (cta == grp_first);
 
@@ -845,6 +849,11 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
 #pragma unroll 5
                 for (int w = 0; w < NW; ++w) s += wpart[(size_t)w * gsc + ctid];
                 if (ncta == 1) gsum[ctid] = s;
+                else if (xatomic) {
+                    // one hop: add the partial into the slot's accumulator at L2, then count the arrival (release: the add is performed first)
+                    dev::red_add_f64(a.xs_sum + (size_t)(epoch & 3u) * a.ll_gs_cap + ctid, s);
+                    dev::red_release_add_u32(a.xs_cnt + (size_t)(epoch & 3u) * 32, 1u);
+                }
                 else dev::ll_store(a.ll + ((size_t)(par * a.ll_gs_cap + ctid) * a.ncta_pad + cta), s, epoch);
             }
             AB_TICK(2);
@@ -853,10 +862,20 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             const bool small_group = (gs > 1 && gs <= 32);
             if (warp == 0 && small_group) pre = prox_small_pre<T, P>(rec, gs, p_aold, lane);      // overlaps the exchange latency
             const bool multi_gpu = a.world > 1;
-            int n_final = n_groups;                                      // number of partials the control warp adds up
+            const int n_red = xatomic ? 1 : n_groups;                    // partials per column a CTA holds after the intra-GPU exchange
+            int n_final = n_red;                                         // number of partials the control warp adds up
             if (ncta > 1 || multi_gpu) {
                 bool ok = true;
-                if (ncta > 1 && is_leader) {                             // CTA-uniform
+                if (xatomic && ncta > 1 && (!multi_gpu || cta == 0)) {   // wait until all ncta * gs arrivals are in, read the totals
+                    if (ctid < gs) {
+                        dev::SpinGuard guard;
+                        const uint32_t want = (uint32_t)ncta * (uint32_t)gs;
+                        const uint32_t* cnt = a.xs_cnt + (size_t)(epoch & 3u) * 32;
+                        while (dev::ld_acquire_u32(cnt) != want) { if (guard.give_up(abort_flag, nullptr)) { ok = false; break; } }
+                        vals2[ctid * 32] = dev::ld_relaxed_f64(a.xs_sum + (size_t)(epoch & 3u) * a.ll_gs_cap + ctid);
+                    }
+                }
+                if (!xatomic && ncta > 1 && is_leader) {                 // CTA-uniform
                     // thread t < gs * grp_size reads line (column t / grp_size, member t % grp_size)
 #pragma unroll 1
                     for (int t = ctid; t < gs * grp_size; t += NTC) {
@@ -875,7 +894,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                         dev::ll_store(a.ll2 + ((size_t)(par * a.ll_gs_cap + ctid) * 32 + my_group), s, epoch);
                     }
                 }
-                if (ncta > 1 && (!multi_gpu || cta == 0)) {              // level 2 (single GPU: every CTA; multi GPU: the GPU leader only)
+                if (!xatomic && ncta > 1 && (!multi_gpu || cta == 0)) {  // level 2 (single GPU: every CTA; multi GPU: the GPU leader only)
 #pragma unroll 1
                     for (int t = ctid; t < gs * n_groups; t += NTC) {
                         const int c = t / n_groups, g = t - c * n_groups;
@@ -895,7 +914,7 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
                             double s = 0;
                             if (ncta > 1) {
 #pragma unroll 1
-                                for (int g = 0; g < n_groups; ++g) s += vals2[ctid * 32 + g];
+                                for (int g = 0; g < n_red; ++g) s += vals2[ctid * 32 + g];
                             } else s = gsum[ctid];
                             vals1[ctid * 32] = s;
                         }
@@ -924,6 +943,13 @@ pin_solve_kernel(const __grid_constant__ PinKernelArgs<T> a)
             if (trace) { trace[2] = (long long)(dev::global_ns() & 0xffffffffffull); }
             dev::named_bar_sync(1, NTC);
             if (ctrl->abort) { final_error = kErrAbort; break; }      // uniform
+            if (xatomic && cta == 0 && ncta > 1) {
+                // CTA 0 has seen every CTA arrive at exchange e = epoch - 1, so every CTA is done with exchange e - 2: its slot
+                // (e + 2) & 3 is cleared for exchange e + 2 (nobody adds to it before CTA 0 itself has arrived at e + 1)
+                const uint32_t zs = (epoch + 1u) & 3u;
+                if (ctid < a.gs_cap) dev::st_relaxed_f64(a.xs_sum + (size_t)zs * a.ll_gs_cap + ctid, 0.0);
+                if (ctid == 0) dev::st_relaxed_u32(a.xs_cnt + (size_t)zs * 32, 0u);
+            }
             // Hand the PREVIOUS group's stage back to the TMA producer only now: its refill burst (tens of KB per SM)
             // then overlaps the proximal update, when the SM's load path is idle, instead of delaying the polling loads.
             if (SMEM && pending_stage >= 0) {

@@ -21,6 +21,7 @@ y = (eta + np.linalg.norm(beta) * rng.normal(size=n)).astype(dtype)
 groups = np.arange(0, p, gs)
 ad.set_configs("sweep_profile", int(os.environ.get("PROF", 0)))
 ad.set_configs("sweep_batch", int(os.environ.get("BATCH", 0)))
+ad.set_configs("sweep_xchg", int(os.environ.get("XCHG", 1)))
 for rep in range(2):
     t = time.time()
     st = ad.grpnet(X, ad.glm.gaussian(y, dtype=dtype), groups=groups, early_exit=False, lmda_path_size=L, progress_bar=False)
