@@ -289,6 +289,29 @@ cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovIt
     }
 }
 
+// Affine column transform of a dense matrix into a new one (matrix.standardize, CORE/matrix/matrix_naive_standardize.ipp:8-293):
+//   out[i, j] = (X[i, j] - centers[j]) / scales[j]   for i < n, pad rows stay 0.   grid = (columns, row blocks)
+template <class T>
+__global__ void standardize_cols_kernel(const T* __restrict__ X, int64_t ld, int64_t n, const T* __restrict__ centers, const T* __restrict__ scales,
+                                        T* __restrict__ out, int64_t ld_out)
+{
+    const int64_t j = blockIdx.x;
+    const T c = centers[j], sc = scales[j];
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.y * blockDim.x)
+        out[j * ld_out + i] = (X[j * ld + i] - c) / sc;
+}
+// Row / column gather into a new dense matrix (matrix.subset, CORE/matrix/matrix_naive_subset.ipp):
+//   out[i, j] = X[rows ? rows[i] : i, cols ? cols[j] : j]     grid = (output columns, row blocks)
+template <class T>
+__global__ void gather_kernel(const T* __restrict__ X, int64_t ld, const int64_t* __restrict__ rows, const int64_t* __restrict__ cols,
+                              int64_t n_out, T* __restrict__ out, int64_t ld_out)
+{
+    const int64_t j = blockIdx.x;
+    const T* src = X + (cols ? cols[j] : j) * ld;
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.y * blockDim.x)
+        out[j * ld_out + i] = src[rows ? rows[i] : i];
+}
+
 // out[k] = sum_rb part[rb * total + k]
 __global__ void sum_parts_kernel(const double* __restrict__ part, int n_rb, int64_t total, double* __restrict__ out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

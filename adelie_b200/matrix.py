@@ -110,6 +110,36 @@ class _DeviceMatrix(MatrixNaiveBase):
         except Exception:
             pass
 
+    def __getitem__(self, key):
+        """``mat[rows]`` / ``mat[:, cols]`` / ``mat[rows, cols]`` sugar over :func:`subset` (adelie/matrix.py:84-134): integers, slices, lists,
+        index or boolean arrays; with two list-like subsets at least one must be an integer or a slice."""
+        one = (int, np.integer, slice)
+        if isinstance(key, tuple):
+            if len(key) == 0:
+                return self
+            if len(key) > 2:
+                raise ValueError("Key must be of length 1 or 2 if it is a tuple.")
+            if len(key) == 2 and not isinstance(key[0], one) and not isinstance(key[1], one):
+                raise ValueError("If row and column subsets are provided, at least one must not be a list-like object. ")
+        elif isinstance(key, one + (list, np.ndarray)):
+            key = (key,)
+        else:
+            raise ValueError("Subsets must be integer, slice, list, or np.ndarray objects.")
+
+        def conv(sel, size):
+            if isinstance(sel, (int, np.integer)):
+                return np.array([sel])
+            if isinstance(sel, slice):
+                return None if sel == slice(None) else np.arange(size)[sel]
+            sel = np.asarray(sel)
+            return np.flatnonzero(sel) if sel.dtype == np.dtype("bool") else sel
+        out = self
+        for axis, sel in enumerate(key):
+            idx = conv(sel, out.shape[axis])
+            if idx is not None:
+                out = subset(out, idx, axis=axis, n_threads=self._n_threads)
+        return out
+
     def _vec(self, a, size, name, fn):
         if not isinstance(a, np.ndarray) or a.dtype != self.dtype or a.ndim != 1 or not a.flags.c_contiguous:
             raise TypeError(f"{fn}(): {name} must be a 1-D contiguous array of dtype {np.dtype(self.dtype).name}")
@@ -333,6 +363,72 @@ def snp_unphased_device_random(n: int, p: int, *, dtype=np.float32, seed: int = 
     m = _SnpUnphased(dtype, n, p, 1, maker)
     m._core()
     return m
+
+
+class _Derived(_DeviceMatrix):
+    """Dense device matrix materialised from another device matrix (standardize / subset); keeps the base alive like the reference wrappers."""
+    def __init__(self, base, n, p, n_threads, maker):
+        _DeviceMatrix.__init__(self, base.dtype, n, p, n_threads)
+        self._mat = base
+        self._maker = maker
+
+    def _make_handle(self):
+        h = C.c_void_p()
+        self._maker(h)
+        return h
+
+
+def standardize(mat, centers: np.ndarray = None, scales: np.ndarray = None, ddof: int = 0, *, n_threads: int = 1):
+    """Standardized matrix ``(Z - 1 c^T) diag(s)^-1`` (adelie/matrix.py:1414-1536).  ``centers`` / ``scales`` default to the column means and
+    standard deviations (``ddof`` degrees of freedom) of ``mat`` under equal weights.  A NumPy input returns a NumPy array like the
+    reference; a device matrix returns a new dense device matrix (the transform is materialised once, see csrc/capi.cu)."""
+    if isinstance(mat, (list, np.ndarray)):
+        mat = np.array(mat, order="F", copy=True)
+        if centers is None:
+            centers = np.mean(mat, axis=0)
+        mat -= centers[None]
+        if scales is None:
+            scales = np.sqrt(np.sum(mat ** 2, axis=0) / (mat.shape[0] - ddof))
+        mat /= scales[None]
+        return mat
+    if not isinstance(mat, _DeviceMatrix):
+        raise RuntimeError("adelie_b200: standardize() takes a numpy array or a dense device matrix.")
+    dtype = mat.dtype
+    n, p = mat.shape
+    weights = np.full(n, 1 / n, dtype=dtype)
+    if centers is None:
+        centers = np.empty(p, dtype=dtype)
+        mat.mean(weights, centers)
+    if scales is None:
+        v = np.empty(p, dtype=dtype)
+        mat.var(np.asarray(centers, dtype=dtype), weights, v)
+        scales = np.sqrt((n / (n - ddof)) * v)
+    centers = np.array(centers, copy=True, dtype=dtype); scales = np.array(scales, copy=True, dtype=dtype)
+
+    def maker(h):
+        _lib.check(_lib.load().ab_matrix_standardize_create(mat._core(), _lib.ptr(centers), centers.size, _lib.ptr(scales), scales.size,
+                                                            int(n_threads), C.byref(h)))
+    out = _Derived(mat, n, p, n_threads, maker)
+    out._centers, out._scales = centers, scales
+    out._core()
+    return out
+
+
+def subset(mat, indices: np.ndarray, *, axis: int = 0, n_threads: int = 1):
+    """``mat[indices]`` (axis 0) or ``mat[:, indices]`` (axis 1) (adelie/matrix.py:1539-1632); device matrices give a new dense device matrix."""
+    if isinstance(mat, np.ndarray):
+        return mat[indices] if axis == 0 else mat[:, indices]
+    if not isinstance(mat, _DeviceMatrix):
+        raise RuntimeError("adelie_b200: subset() takes a numpy array or a dense device matrix.")
+    idx = np.array(indices, copy=True, dtype=np.int64).ravel()
+    n, p = mat.shape
+
+    def maker(h):
+        _lib.check(_lib.load().ab_matrix_subset_create(mat._core(), _lib.ptr(idx), idx.size, int(axis), int(n_threads), C.byref(h)))
+    out = _Derived(mat, idx.size if axis == 0 else n, p if axis == 0 else idx.size, n_threads, maker)
+    out._indices = idx
+    out._core()
+    return out
 
 
 def sparse(mat, *, method: str = "naive", copy: bool = False, n_threads: int = 1):

@@ -93,6 +93,11 @@ int ab_matrix_snp_unphased_alloc_random(int dtype, int64_t n, int64_t p, uint64_
                                         double one_ratio, double two_ratio, double missing_ratio, ab_matrix** out);
 int ab_matrix_snp_unphased_download(ab_matrix* m, int8_t* calldata_out, double* impute_out);   /* column-major (n, p) int8, -9 = missing */
 int ab_matrix_snp_unphased_cache_info(const ab_matrix* m, int64_t* cached_cols, int64_t* packed_bytes);
+/* adelie.matrix.standardize (PY/matrix.py:1414-1536; MatrixNaiveStandardize{32,64}, CORE/matrix/matrix_naive_standardize.ipp:8-293): X = (Z - 1 c^T) diag(s)^-1,
+   and adelie.matrix.subset (PY/matrix.py:1539-1632; MatrixNaiveCSubset / MatrixNaiveRSubset, CORE/matrix/matrix_naive_subset.ipp): axis 0 = rows, 1 = columns.
+   Both materialise a new dense device matrix from a dense base matrix (centers / scales: host arrays of the matrix dtype). */
+int ab_matrix_standardize_create(ab_matrix* base, const void* centers, int64_t n_centers, const void* scales, int64_t n_scales, int n_threads, ab_matrix** out);
+int ab_matrix_subset_create(ab_matrix* base, const int64_t* indices, int64_t n_indices, int axis, int n_threads, ab_matrix** out);
 int ab_matrix_free(ab_matrix* m);
 int ab_matrix_rows(const ab_matrix* m, int64_t* out);
 int ab_matrix_cols(const ab_matrix* m, int64_t* out);

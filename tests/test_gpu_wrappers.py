@@ -1,0 +1,96 @@
+"""GPU tests of the `matrix.standardize` / `matrix.subset` wrappers (reference MatrixNaiveStandardize / MatrixNaiveCSubset /
+MatrixNaiveRSubset): every operator against dense NumPy like the reference's run_naive (T/test_matrix.py:251-411, 662-710, 413-480), the
+path solver on the wrapped matrix against the oracle on the NumPy equivalent, and the constructor error contract."""
+import numpy as np
+import pytest
+
+import adelie_b200 as ad
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_naive(cX, X, dtype, atol):
+    n, p = X.shape
+    assert cX.shape == (n, p)
+    rng = np.random.default_rng(n + p)
+    v = rng.normal(size=n).astype(dtype); w = rng.uniform(0, 1, size=n).astype(dtype)
+    out = np.empty(p, dtype=dtype)
+    cX.mul(v, w, out); np.testing.assert_allclose(out, X.T @ (v * w), atol=atol * n)
+    cX.sq_mul(w, out); np.testing.assert_allclose(out, (X ** 2).T @ w, atol=atol * n)
+    for j, q in [(0, 1), (p // 2, min(4, p - p // 2)), (p - 1, 1)]:
+        o = np.empty(q, dtype=dtype); cX.bmul(j, q, v, w, o)
+        np.testing.assert_allclose(o, X[:, j:j + q].T @ (v * w), atol=atol * n)
+        vv = rng.normal(size=q).astype(dtype); acc = rng.normal(size=n).astype(dtype); exp = acc + X[:, j:j + q] @ vv
+        cX.btmul(j, q, vv, acc); np.testing.assert_allclose(acc, exp, atol=atol * 20)
+        C = np.empty((q, q), dtype=dtype, order="F"); cX.cov(j, q, np.sqrt(w), C)
+        np.testing.assert_allclose(C, X[:, j:j + q].T @ (w[:, None] * X[:, j:j + q]), atol=atol * n)
+
+
+@pytest.mark.parametrize("dtype,atol", [(np.float64, 1e-13), (np.float32, 2e-5)])
+@pytest.mark.parametrize("n,p,ddof", [(100, 20, 0), (333, 7, 1), (2000, 64, 0)])
+def test_standardize_vs_numpy(dtype, atol, n, p, ddof):
+    rng = np.random.default_rng(0)
+    Z = np.asfortranarray(rng.normal(2.0, 3.0, (n, p)), dtype=dtype)
+    cX = ad.matrix.standardize(ad.matrix.dense(Z), ddof=ddof)
+    c = Z.mean(axis=0); s = np.sqrt(((Z - c) ** 2).sum(axis=0) / (n - ddof))
+    np.testing.assert_allclose(cX._centers, c, rtol=1e-5 if dtype == np.float32 else 1e-12)
+    np.testing.assert_allclose(cX._scales, s, rtol=1e-4 if dtype == np.float32 else 1e-12)
+    X = ((Z - cX._centers) / cX._scales).astype(dtype)
+    _run_naive(cX, X, dtype, atol)
+    np.testing.assert_allclose(ad.matrix.standardize(Z, ddof=ddof), (Z - c) / s, rtol=1e-4 if dtype == np.float32 else 1e-12, atol=1e-5)
+    # user-given centers / scales
+    c2 = rng.normal(size=p).astype(dtype); s2 = rng.uniform(0.5, 2, size=p).astype(dtype)
+    _run_naive(ad.matrix.standardize(ad.matrix.dense(Z), centers=c2, scales=s2), ((Z - c2) / s2).astype(dtype), dtype, atol)
+
+
+@pytest.mark.parametrize("dtype,atol", [(np.float64, 1e-13), (np.float32, 2e-5)])
+def test_subset_vs_numpy(dtype, atol):
+    rng = np.random.default_rng(1)
+    n, p = 500, 40
+    Z = np.asfortranarray(rng.normal(size=(n, p)), dtype=dtype)
+    M = ad.matrix.dense(Z)
+    rows = rng.choice(n, 123, replace=False); cols = rng.choice(p, 11, replace=False)
+    _run_naive(ad.matrix.subset(M, rows, axis=0), Z[rows], dtype, atol)
+    _run_naive(ad.matrix.subset(M, cols, axis=1), Z[:, cols], dtype, atol)
+    _run_naive(M[rows], Z[rows], dtype, atol)
+    _run_naive(M[:, cols], Z[:, cols], dtype, atol)
+    _run_naive(M[10:200:3, cols], Z[10:200:3][:, cols], dtype, atol)
+    mask = rng.uniform(size=n) < 0.3
+    _run_naive(M[mask], Z[mask], dtype, atol)
+    assert np.array_equal(ad.matrix.subset(Z, rows, axis=0), Z[rows])
+
+
+def test_wrapper_errors():
+    Z = np.asfortranarray(np.random.default_rng(2).normal(size=(50, 6)))
+    M = ad.matrix.dense(Z)
+    with pytest.raises(RuntimeError, match="centers must be \\(p,\\)"):
+        ad.matrix.standardize(M, centers=np.zeros(5), scales=np.ones(6))
+    with pytest.raises(RuntimeError, match="scales must be \\(p,\\)"):
+        ad.matrix.standardize(M, centers=np.zeros(6), scales=np.ones(7))
+    with pytest.raises(RuntimeError, match="n_threads must be >= 1"):
+        ad.matrix.standardize(M, n_threads=0)
+    with pytest.raises(RuntimeError, match="subset must be non-empty"):
+        ad.matrix.subset(M, np.array([], dtype=int))
+    with pytest.raises(RuntimeError, match="unique values in the range \\[0, p\\)"):
+        ad.matrix.subset(M, np.array([1, 6]), axis=1)
+    with pytest.raises(RuntimeError, match="unique values in the range \\[0, n\\)"):
+        ad.matrix.subset(M, np.array([3, 3]), axis=0)
+    with pytest.raises(ValueError):
+        M[[1, 2], [0, 1]]
+
+
+def test_grpnet_on_standardized_and_subset_matrix():
+    data = ad.data.dense(1500, 60, 12, seed=5)
+    Z = data["X"] * 3.0 + 1.5
+    y = data["glm"].y
+    rows = np.sort(np.random.default_rng(0).choice(1500, 1000, replace=False))
+    cX = ad.matrix.standardize(ad.matrix.dense(Z)[rows])
+    Xn = ad.matrix.standardize(np.asfortranarray(Z[rows]))
+    kw = dict(groups=data["groups"], penalty=data["penalty"], tol=1e-13, early_exit=False, lmda_path_size=12, min_ratio=0.1)
+    st = ad.grpnet(cX, ad.glm.gaussian(y[rows]), progress_bar=False, **kw)
+    ref = orc.grpnet(Xn, orc.glm_spec("gaussian", y[rows]), **kw)
+    assert st.error == "" and ref.error == ""
+    B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
+    assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
+    np.testing.assert_allclose(st.intercepts, ref.intercepts, rtol=1e-6, atol=1e-9)
