@@ -8,6 +8,7 @@ There is no CPU fallback: every operator raises if ``libadelie_b200.so`` or a GP
 from . import _lib
 from . import bcd
 from . import configs
+from . import cv
 from . import data
 from . import diagnostic
 from . import dist
@@ -18,5 +19,6 @@ from . import solver
 from . import state
 from .configs import set_configs
 from .solver import grpnet
+from .cv import cv_grpnet
 
 __version__ = "0.1.0"

@@ -2,14 +2,43 @@
 import numpy as np
 
 
-def predict(X, betas, intercepts, offsets=None):
-    """Linear predictions eta = X beta + intercept (+ offsets) for every lambda (diagnostic.py:30-121)."""
-    X = np.asarray(X)
-    B = np.asarray(betas.todense()) if hasattr(betas, "todense") else np.asarray(betas)
-    eta = B @ X.T + np.asarray(intercepts)[:, None]
+def predict(X, betas, intercepts, offsets=None, n_threads=1):
+    """Linear predictions eta = X beta + intercept (+ offsets) for every lambda (adelie/diagnostic.py:30-121).  ``X`` is a NumPy array or
+    a device matrix (then ``sp_tmul`` runs on the device); single-response."""
+    from . import matrix as _matrix
+    intercepts = np.atleast_1d(np.asarray(intercepts))
+    if isinstance(X, _matrix.MatrixNaiveBase):
+        from scipy.sparse import csr_matrix
+        B = csr_matrix(betas)
+        eta = np.empty((B.shape[0], X.rows()), dtype=X.dtype)
+        X.sp_tmul(B.astype(X.dtype), eta)
+        eta = eta + intercepts[:, None].astype(X.dtype)
+    else:
+        X = np.asarray(X)
+        B = np.asarray(betas.todense()) if hasattr(betas, "todense") else np.asarray(betas)
+        eta = B @ X.T + intercepts[:, None]
     if offsets is not None:
-        eta = eta + offsets[None]
+        eta = eta + np.asarray(offsets)[None]
     return eta
+
+
+def coefficient(*, lmda, betas, intercepts, lmdas):
+    """Coefficients at ``lmda`` by linear interpolation between the two neighbouring solutions of a (decreasing) path; the boundary
+    solution outside the range of ``lmdas`` (adelie/diagnostic.py:560-646)."""
+    lmdas = np.asarray(lmdas)
+    if lmdas.shape[0] == 0:
+        raise RuntimeError("lmdas must be non-empty!")
+    if lmdas.shape[0] == 1:
+        return betas, intercepts
+    order = np.argsort(lmdas)
+    idx = lmdas.shape[0] - int(np.searchsorted(lmdas, lmda, sorter=order))
+    if idx == 0 or idx == lmdas.shape[0]:
+        idx = int(np.clip(idx, 0, lmdas.shape[0] - 1))
+        return betas[idx], intercepts[idx]
+    weight = (lmda - lmdas[idx]) / (lmdas[idx - 1] - lmdas[idx])
+    beta = betas[idx - 1].multiply(weight) + betas[idx].multiply(1 - weight)
+    intercept = weight * intercepts[idx - 1] + (1 - weight) * intercepts[idx]
+    return beta, intercept
 
 
 def objective_gaussian(X, y, weights, beta, intercept, lmda, alpha, groups, group_sizes, penalty):

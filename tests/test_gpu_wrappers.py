@@ -94,3 +94,51 @@ def test_grpnet_on_standardized_and_subset_matrix():
     B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
     assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
     np.testing.assert_allclose(st.intercepts, ref.intercepts, rtol=1e-6, atol=1e-9)
+
+
+def _cv_reference(X, y, family, n_folds, seed, min_ratio, L, kw):
+    """The reference's CV procedure (adelie/cv.py:247-325) restated on the CPU oracle + NumPy losses (the checker)."""
+    n = X.shape[0]
+    np.random.seed(seed)
+    order = np.random.choice(n, n, replace=False)
+    fold_size, remaining = divmod(n, n_folds)
+    w = np.full(n, 1 / n)
+
+    def loss(eta, ww):
+        if family == "gaussian":
+            return np.sum(ww * (0.5 * eta ** 2 - y * eta))
+        return np.sum(ww * (np.logaddexp(0, eta) - y * eta))
+    lm0 = orc.grpnet(X, orc.glm_spec(family, y, w), lmda_path_size=1, **kw).lmda_max
+    full = lm0 * np.logspace(0, np.log10(min_ratio), L)
+    out = np.empty((n_folds, L))
+    for fold in range(n_folds):
+        begin = (fold_size + 1) * min(fold, remaining) + max(fold - remaining, 0) * fold_size
+        held = order[begin:begin + fold_size + (fold < remaining)]
+        wf = w.copy(); wf[held] = 0; ws = wf.sum(); wf /= ws
+        spec = orc.glm_spec(family, y, wf)
+        lmf = orc.grpnet(X, spec, lmda_path_size=1, **kw).lmda_max
+        cur = lmf * np.logspace(0, np.log10(min_ratio), L)
+        aug = np.sort(np.concatenate([full, cur[cur > full[0]]]))[::-1]
+        st = orc.grpnet(X, spec, lmda_path=aug, early_exit=False, **kw)
+        B = np.asarray(st.betas.todense()); b0 = np.asarray(st.intercepts); lm = np.asarray(st.lmdas)
+        for i, l in enumerate(full):
+            k = int(np.argmin(np.abs(lm - l)))                 # the common grid is part of the augmented path
+            eta = X @ B[k] + b0[k]
+            out[fold, i] = (loss(eta, w) - ws * loss(eta, wf)) / w[held].sum()
+    return full, out
+
+
+@pytest.mark.parametrize("family", ["gaussian", "binomial"])
+def test_cv_grpnet_vs_oracle_procedure(family):
+    data = ad.data.dense(600, 30, 10, glm=family, seed=7)
+    X, y = data["X"], data["glm"].y
+    kw = dict(groups=data["groups"], penalty=data["penalty"], tol=1e-12)
+    if family == "binomial":
+        kw["irls_tol"] = 1e-10
+    glm = ad.glm.gaussian(y) if family == "gaussian" else ad.glm.binomial(y)
+    res = ad.cv_grpnet(X, glm, n_folds=4, seed=3, min_ratio=0.2, lmda_path_size=12, **kw)
+    full, ref = _cv_reference(X, y, family, 4, 3, 0.2, 12, kw)
+    np.testing.assert_allclose(res.lmdas, full, rtol=1e-9)
+    np.testing.assert_allclose(res.losses, ref, rtol=1e-5, atol=1e-8)
+    assert res.best_idx == int(np.argmin(ref.mean(axis=0)))
+    np.testing.assert_allclose(res.avg_losses, ref.mean(axis=0), rtol=1e-5, atol=1e-8)
