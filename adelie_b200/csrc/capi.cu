@@ -370,7 +370,7 @@ int ab_matrix_snp_unphased_download(ab_matrix* m, int8_t* calldata_out, double* 
         using T = std::remove_reference_t<decltype(M.snp_impute.p[0])>;
         if (!M.snp) throw core_error("not a snp_unphased matrix.");
         std::vector<uint32_t> h((size_t)M.snp_ldw * M.p); std::vector<T> imp(M.p);
-        M.snp_packed.download(h.data(), h.size()); M.snp_impute.download(imp.data(), M.p);
+        AB_CUDA(cudaMemcpyAsync(h.data(), M.snp_bits, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, 0)); M.snp_impute.download(imp.data(), M.p);
         AB_CUDA(cudaStreamSynchronize(0));
         for (int64_t j = 0; j < M.p; ++j) {
             impute_out[j] = (double)imp[j];
@@ -396,7 +396,15 @@ int ab_matrix_snp_unphased_cache_info(const ab_matrix* m, int64_t* cached_cols, 
 } // extern "C"
 template <class T>
 static DenseMatrix<T>* make_standardized(DenseMatrix<T>& B, const T* centers, const T* scales, int n_threads) {
-    if (B.sparse || B.snp) throw core_error("standardize: only dense base matrices are supported on the device.");
+    if (B.sparse) throw core_error("standardize: sparse base matrices are not supported on the device.");
+    if (B.snp) {
+        // snp_unphased: nothing is materialised -- the view shares the packed genotypes and maps the four codes of column j to
+        // (0 - c_j) / s_j, (1 - c_j) / s_j, (2 - c_j) / s_j, (impute_j - c_j) / s_j inside the decode / packed-GEMV kernels
+        if (B.snp_center.n) throw core_error("standardize: the base matrix is already a standardized snp_unphased view.");
+        auto V = new DenseMatrix<T>(B, centers, scales, typename DenseMatrix<T>::SnpTag{});
+        V->n_threads = n_threads;
+        return V;
+    }
     auto M = std::unique_ptr<DenseMatrix<T>>(new DenseMatrix<T>(B.n, B.p));
     M->n_threads = n_threads;
     DevBuf<T> dc(B.p), ds(B.p); dc.upload(centers, B.p); ds.upload(scales, B.p);

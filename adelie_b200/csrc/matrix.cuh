@@ -178,12 +178,22 @@ struct DenseMatrix {
     // index below takes a PHYSICAL column (dense / sparse: physical == logical).
     bool snp = false;
     DevBuf<uint32_t> snp_packed; int64_t snp_ldw = 0; DevBuf<T> snp_impute;
+    const uint32_t* snp_bits = nullptr;                  // the packed genotypes the kernels read: snp_packed, or the base matrix's bits for a standardize view
+    DevBuf<T> snp_center, snp_scale;                     // standardize view: values (x - c_j) / s_j (empty: raw genotypes)
     int64_t cache_cap = 0, cache_used = 0;
     std::unordered_map<int64_t, std::pair<int32_t, int32_t>> cache_map;      // logical first column -> (first slot, columns decoded there)
     long long n_decoded_cols = 0;
     struct SnpTag {};
     DenseMatrix(int64_t n_, int64_t p_, SnpTag) : n(n_), p(p_), ld(pad_rows(n_)), snp(true) {
-        snp_ldw = ld / 16; snp_packed.alloc((size_t)snp_ldw * p); snp_impute.alloc(p);
+        snp_ldw = ld / 16; snp_packed.alloc((size_t)snp_ldw * p); snp_impute.alloc(p); snp_bits = snp_packed.p;
+    }
+    // standardize view of another SNP matrix: shares its packed bits (the caller keeps the base alive), own impute / centers / scales
+    DenseMatrix(const DenseMatrix& base, const T* h_centers, const T* h_scales, SnpTag) : n(base.n), p(base.p), ld(base.ld), snp(true) {
+        snp_ldw = base.snp_ldw; snp_bits = base.snp_bits;
+        snp_impute.alloc(p); snp_center.alloc(p); snp_scale.alloc(p);
+        AB_CUDA(cudaMemcpyAsync(snp_impute.p, base.snp_impute.p, sizeof(T) * p, cudaMemcpyDeviceToDevice, 0));
+        snp_center.upload(h_centers, p); snp_scale.upload(h_scales, p);
+        AB_CUDA(cudaStreamSynchronize(0));
     }
     // Physical first column of the logical columns [col, col + count): for SNP storage the columns are decoded into consecutive
     // slots of the dense cache the first time they are asked for.
@@ -203,7 +213,7 @@ struct DenseMatrix {
         }
         const int32_t slot = (int32_t)cache_used;
         dim3 grid((unsigned)count, (unsigned)std::min<int64_t>(64, (snp_ldw + 255) / 256));
-        snp_decode_kernel<T><<<grid, 256, 0, stream>>>(snp_packed.p, snp_ldw, snp_impute.p, col, count, X + (int64_t)slot * ld, ld);
+        snp_decode_kernel<T><<<grid, 256, 0, stream>>>(snp_bits, snp_ldw, snp_impute.p, snp_center.p, snp_scale.p, n, col, count, X + (int64_t)slot * ld, ld);
         AB_CUDA(cudaGetLastError());
         cache_used += count; n_decoded_cols += count;
         cache_map[col] = std::make_pair(slot, (int32_t)count);
@@ -225,7 +235,7 @@ struct DenseMatrix {
         const size_t smem = snp_gemv_smem_bytes<T, KP>();
         auto fn = snp_gemv_t_kernel<T, KP, SQ>;
         AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<dim3(col_chunks, n_rb), kSnpGemvThreads, smem, stream>>>(snp_packed.p, snp_ldw, ld, snp_impute.p, j0, q, cols_per_cta, tiles_per_cta, K, v, w, part.p);
+        fn<<<dim3(col_chunks, n_rb), kSnpGemvThreads, smem, stream>>>(snp_bits, snp_ldw, ld, snp_impute.p, snp_center.p, snp_scale.p, j0, q, cols_per_cta, tiles_per_cta, K, v, w, part.p);
         AB_CUDA(cudaGetLastError());
         return n_rb;
     }

@@ -253,14 +253,25 @@ __global__ void snp_pack_kernel(const int8_t* __restrict__ calldata, int64_t n, 
 template <class T> __device__ __forceinline__ T snp_value(uint32_t code, T imp) {
     return (code & 2u) ? ((code & 1u) ? imp : T(2)) : ((code & 1u) ? T(1) : T(0));
 }
+// The four values a genotype code of column j stands for: {0, 1, 2, impute[j]}, or their standardized images (x - c_j) / s_j when the
+// matrix is a `matrix.standardize` view of the packed bits (center != nullptr; same arithmetic as the dense standardize kernel).
+template <class T> struct SnpVals { T v0, v1, v2, v3; };
+template <class T> __device__ __forceinline__ SnpVals<T> snp_vals(const T* impute, const T* center, const T* scale, int64_t j) {
+    SnpVals<T> r{T(0), T(1), T(2), impute[j]};
+    if (center) { const T c = center[j], sc = scale[j]; r.v0 = (r.v0 - c) / sc; r.v1 = (r.v1 - c) / sc; r.v2 = (r.v2 - c) / sc; r.v3 = (r.v3 - c) / sc; }
+    return r;
+}
+template <class T> __device__ __forceinline__ T snp_value4(uint32_t code, const SnpVals<T>& t) {
+    return (code & 2u) ? ((code & 1u) ? t.v3 : t.v2) : ((code & 1u) ? t.v1 : t.v0);
+}
 
 // Decodes `count` columns starting at logical column j0 into dense columns out[c * ld + i] (pad rows = 0 since their code is 0).
 template <class T>
-__global__ void snp_decode_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const T* __restrict__ impute, int64_t j0, int count,
-                                  T* __restrict__ out, int64_t ld)
+__global__ void snp_decode_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const T* __restrict__ impute, const T* __restrict__ center,
+                                  const T* __restrict__ scale, int64_t n, int64_t j0, int count, T* __restrict__ out, int64_t ld)
 {
     const int c = blockIdx.x;                          // columns on grid.x, row blocks on grid.y
-    const T imp = impute[j0 + c];
+    const SnpVals<T> tv = snp_vals<T>(impute, center, scale, j0 + c);
     const uint32_t* src = packed + (j0 + c) * ldw;
     T* dst = out + (int64_t)c * ld;
     for (int64_t w = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; w < ldw; w += (int64_t)gridDim.y * blockDim.x) {
@@ -269,7 +280,7 @@ __global__ void snp_decode_kernel(const uint32_t* __restrict__ packed, int64_t l
         for (int k4 = 0; k4 < 4; ++k4) {
             T x[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) x[k] = snp_value<T>((word >> (2 * (4 * k4 + k))) & 3u, imp);
+            for (int k = 0; k < 4; ++k) x[k] = (w * 16 + 4 * k4 + k < n) ? snp_value4<T>((word >> (2 * (4 * k4 + k))) & 3u, tv) : T(0);   // pad rows stay 0
             if (sizeof(T) == 4) *reinterpret_cast<float4*>(dst + w * 16 + 4 * k4) = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
             else {
                 *reinterpret_cast<double2*>(dst + w * 16 + 4 * k4) = make_double2((double)x[0], (double)x[1]);
@@ -296,14 +307,15 @@ template <class T, int KP> __host__ __device__ constexpr size_t snp_gemv_smem_by
     return sizeof(double) * (kSnpGemvThreads / 32) * 32 * KP + sizeof(T) * (kSnpGemvThreads / 32) * snp_gemv_warp_scratch<KP>();
 }
 // genotype r of a 32-bit word of codes, straight from constant-mask bit tests (no shifts): 0 / 1 / 2 / impute
-template <class T, int r> __device__ __forceinline__ T snp_pick(uint32_t word, T imp) {
+template <class T, int r> __device__ __forceinline__ T snp_pick(uint32_t word, const SnpVals<T>& t) {
     const bool b0 = (word & (1u << (2 * r))) != 0, b1 = (word & (2u << (2 * r))) != 0;
-    const T lo = b0 ? T(1) : T(0), hi = b0 ? imp : T(2);
+    const T lo = b0 ? t.v1 : t.v0, hi = b0 ? t.v3 : t.v2;
     return b1 ? hi : lo;
 }
 template <class T, int KP, bool SQ>
 __global__ void __launch_bounds__(kSnpGemvThreads)
-snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pad, const T* __restrict__ impute, int64_t j0, int q, int cols_per_cta,
+snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pad, const T* __restrict__ impute, const T* __restrict__ center,
+                  const T* __restrict__ scale, int64_t j0, int q, int cols_per_cta,
                   int tiles_per_cta, int K, const T* __restrict__ v, const T* __restrict__ w, double* __restrict__ out_part)
 {
     constexpr int R = snp_gemv_rows_per_lane<KP>();                              // rows per lane
@@ -378,13 +390,13 @@ snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pa
             constexpr int PF = NB < 4 ? NB : 4;          // columns whose bits are fetched together (independent loads in flight)
 #pragma unroll 1
             for (int cc0 = 0; cc0 < NB; cc0 += PF) {
-                uint32_t w0[PF], w1[PF]; T imp[PF];
+                uint32_t w0[PF], w1[PF]; SnpVals<T> imp[PF];
 #pragma unroll
                 for (int u = 0; u < PF; ++u) {
                     const int c = cb + sub * NB + cc0 + u;
-                    w0[u] = 0; w1[u] = 0; imp[u] = 0;             // code 0 everywhere: a column past the end contributes exact zeros
+                    w0[u] = 0; w1[u] = 0; imp[u] = SnpVals<T>{T(0), T(0), T(0), T(0)};   // a column past the end contributes exact zeros
                     if (c < c_end && live) {
-                        imp[u] = impute[j0 + c];
+                        imp[u] = snp_vals<T>(impute, center, scale, j0 + c);
                         const uint8_t* src = lane_base + (j0 + c) * ldw * 4;
                         if (R == 32) { const uint2 q2 = *reinterpret_cast<const uint2*>(src); w0[u] = q2.x; w1[u] = q2.y; }
                         else if (R == 16) w0[u] = *reinterpret_cast<const uint32_t*>(src);

@@ -142,3 +142,32 @@ def test_cv_grpnet_vs_oracle_procedure(family):
     np.testing.assert_allclose(res.losses, ref, rtol=1e-5, atol=1e-8)
     assert res.best_idx == int(np.argmin(ref.mean(axis=0)))
     np.testing.assert_allclose(res.avg_losses, ref.mean(axis=0), rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("dtype,atol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+def test_standardize_snp_unphased_view(dtype, atol):
+    """standardize(snp_unphased): a view on the packed genotypes (nothing materialised), every operator and the path vs the NumPy equivalent"""
+    from oracle import snp_oracle as so
+    data = ad.data.snp_unphased(1200, 45, seed=4, sparsity=0.8)
+    cd = data["X"]
+    imp = np.sum(np.where(cd > 0, cd, 0), axis=0) / np.maximum(np.sum(cd >= 0, axis=0), 1)
+    base = ad.matrix.snp_unphased_from_calldata(cd, imp, dtype=dtype)
+    D = so.dense_equivalent(cd, imp, dtype)
+    c = D.mean(axis=0).astype(dtype); s = D.std(axis=0).astype(dtype)
+    cX = ad.matrix.standardize(base, centers=c, scales=s)
+    X = ((D - c) / s).astype(dtype)
+    _run_naive(cX, X, dtype, atol)
+    assert base.cache_info()[0] == 0                      # the view has its own decoded-column cache; the base decoded nothing
+    # default centers / scales follow the reference's snp_unphased quirk: mean() == 0, var() == 1  ->  identity
+    ident = ad.matrix.standardize(base)
+    np.testing.assert_array_equal(ident._centers, 0); np.testing.assert_array_equal(ident._scales, 1)
+    with pytest.raises(RuntimeError, match="already a standardized"):
+        ad.matrix.standardize(cX, centers=c, scales=s)
+    if dtype == np.float64:
+        y = data["glm"].y
+        kw = dict(tol=1e-13, early_exit=False, lmda_path_size=10, min_ratio=0.1)
+        st = ad.grpnet(cX, ad.glm.gaussian(y), progress_bar=False, **kw)
+        ref = orc.grpnet(X, orc.glm_spec("gaussian", y), **kw)
+        assert st.error == "" and ref.error == ""
+        B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
+        assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
