@@ -285,6 +285,7 @@ static DenseMatrix<T>* snp_from_io(const SnpUnphasedIO& I, int64_t row_lo, int64
         j0 = j1;
     }
     int err = 0; d_err.download(&err, 1); AB_CUDA(cudaStreamSynchronize(0));
+    if (err == 2) throw core_error("snp_unphased: malformed file (a chunk list runs past the end of its column).");
     if (err) throw core_error("snp_unphased: the file holds a row index outside [0, rows).");
     return M.release();
 }

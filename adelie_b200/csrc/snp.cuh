@@ -215,11 +215,16 @@ snpdat_unpack_kernel(const uint8_t* __restrict__ file, const uint64_t* __restric
     if (item >= ncols * 3) return;
     const int64_t jl = item / 3; const int c = (int)(item - jl * 3);
     const uint8_t* col = file + (outer[j0 + jl] - (uint64_t)col_base);
-    const uint8_t* q = col + snp_rd_u64(col + 8 * c);
+    const uint8_t* col_end = file + (outer[j0 + jl + 1] - (uint64_t)col_base);      // a malformed file must not send the walk out of its column
+    if (col + 24 > col_end) { *err = 2; return; }
+    const uint64_t coff = snp_rd_u64(col + 8 * c);
+    if (coff > (uint64_t)(col_end - col) || col + coff + 4 > col_end) { *err = 2; return; }
+    const uint8_t* q = col + coff;
     const uint32_t n_chunks = snp_rd_u32(q); q += 4;
     const uint32_t code = (c == 0) ? 3u : (uint32_t)c;
     uint32_t* dst = packed + (j0 + jl) * ldw;
     for (uint32_t k = 0; k < n_chunks; ++k) {
+        if (q + 5 > col_end || q + 5 + q[4] + 1 > col_end) { *err = 2; return; }
         const int64_t base = (int64_t)snp_rd_u32(q) * 256;
         const int cnt = (int)q[4] + 1;
         for (int e = lane; e < cnt; e += 32) {

@@ -78,6 +78,14 @@ def test_snp_construction_variants(tmp_path):
     bad = data["X"].copy(); bad[5, 5] = 3
     with pytest.raises(RuntimeError, match="greater than > 2"):
         ad.matrix.snp_unphased_from_calldata(bad, h.impute)
+    # a corrupted chunk count must be caught by the device walk, not run off the column
+    raw = bytearray(open(str(tmp_path / "m.snpdat"), "rb").read())
+    col0 = int(h.outer[0]); off1 = int.from_bytes(raw[col0 + 8:col0 + 16], "little")
+    raw[col0 + off1:col0 + off1 + 4] = (10 ** 6).to_bytes(4, "little")
+    open(str(tmp_path / "bad.snpdat"), "wb").write(bytes(raw))
+    hb = ad.io.snp_unphased(str(tmp_path / "bad.snpdat")); hb.read()
+    with pytest.raises(RuntimeError, match="malformed file|row index outside"):
+        ad.matrix.snp_unphased(hb)
 
 
 def test_snp_device_random_is_shard_invariant():
