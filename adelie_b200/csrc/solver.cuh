@@ -400,54 +400,69 @@ struct PathState {
                 eig_on_device = true; ++n_kernel_launches;
             }
         }
-        // ---- phase 3: records
-        for (size_t i = begin; i < end; ++i) {
+        // ---- phase 3: records.  Offsets first (sequential), then every group fills its own slice of grec / sv / st / meta: the loop is
+        // embarrassingly parallel over groups and runs on the host cores (OpenMP) -- on the GLM path it is executed for ALL screen
+        // groups in every IRLS iteration.
+        std::vector<size_t> rec_off_v(end - begin), ext_off_v(end - begin);
+        {
+            size_t sz = grec.size();
+            for (size_t i = begin; i < end; ++i) {
+                const int gs = (int)group_sizes[screen_set[i]];
+                const size_t off = (sz + 3) / 4 * 4;
+                const int rec_pad = (gs * (gs + 3) + 3) / 4 * 4;
+                rec_off_v[i - begin] = off; ext_off_v[i - begin] = off + rec_pad;
+                sz = off + rec_pad + batch_ext_len(gs);
+                gs_max_screen = std::max(gs_max_screen, gs); rec_max_screen = std::max(rec_max_screen, rec_pad);
+                feat_max_screen = std::max(feat_max_screen, ginfo[i - begin].nfeat);
+            }
+            grec.resize(sz, T(0));
+        }
+        const long long i_begin = (long long)begin, i_end = (long long)end;
+#pragma omp parallel for schedule(static) if (i_end - i_begin >= 256)
+        for (long long ii = i_begin; ii < i_end; ++ii) {
+            const size_t i = (size_t)ii;
             const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g]; const idx_t sb = screen_begins[i];
             const GInfo& gi = ginfo[i - begin];
+            const size_t off = rec_off_v[i - begin], e0 = ext_off_v[i - begin];
+            const int rec_pad = (gs * (gs + 3) + 3) / 4 * 4;
+            std::vector<T>& Vt = st[i];
             if (gs == 1) {
-                if (K == 1 || gi.icpt) Cg.assign(1, C[items[gi.item0].out_off]);
-                else Cg.assign(1, C[items[gi.item0 + gi.k0].out_off]);
-                if (intercept) Cg[0] -= (double)sXm[sb] * (double)sXm[sb];
-            } else if (eig_on_device) {
-                const EigItem& e = eig_items[eig_slot[i - begin]];
-                D.assign(eig_D.begin() + e.d_off, eig_D.begin() + e.d_off + gs);
-                V.assign(eig_V.begin() + e.off, eig_V.begin() + e.off + (size_t)gs * gs);
+                double c0 = (K == 1 || gi.icpt) ? C[items[gi.item0].out_off] : C[items[gi.item0 + gi.k0].out_off];
+                if (intercept) c0 -= (double)sXm[sb] * (double)sXm[sb];
+                Vt.assign(1, T(1));
+                sv[sb] = std::max<T>((T)c0, 0);
             } else {
                 const EigItem& e = eig_items[eig_slot[i - begin]];
-                Cg.assign(eig_in.begin() + e.off, eig_in.begin() + e.off + (size_t)gs * gs);
-            }
-            if (gs == 1) {
-                st[i].assign(1, T(1));
-                sv[sb] = std::max<T>((T)Cg[0], 0);
-            } else {
-                if (!eig_on_device) host_jacobi_eigh(Cg, gs, D, V);
-                st[i].resize((size_t)gs * gs);
-                for (size_t k = 0; k < (size_t)gs * gs; ++k) st[i][k] = (T)V[k];
-                for (int c = 0; c < gs; ++c) { const T d = (T)D[c]; sv[sb + c] = d * T(d >= 0); }      // :122
+                Vt.resize((size_t)gs * gs);
+                if (eig_on_device) {
+                    for (size_t k = 0; k < (size_t)gs * gs; ++k) Vt[k] = (T)eig_V[e.off + k];
+                    for (int c = 0; c < gs; ++c) { const T d = (T)eig_D[e.d_off + c]; sv[sb + c] = d * T(d >= 0); }      // :122
+                } else {
+                    std::vector<double> Cg_l(eig_in.begin() + e.off, eig_in.begin() + e.off + (size_t)gs * gs), D_l, V_l;
+                    host_jacobi_eigh(Cg_l, gs, D_l, V_l);
+                    for (size_t k = 0; k < (size_t)gs * gs; ++k) Vt[k] = (T)V_l[k];
+                    for (int c = 0; c < gs; ++c) { const T d = (T)D_l[c]; sv[sb + c] = d * T(d >= 0); }
+                }
             }
             // packed record [A | xm | V^T xm | V], 16-byte aligned
-            const size_t off = (grec.size() + 3) / 4 * 4;
-            const int rec = gs * (gs + 3);
-            const int rec_pad = (rec + 3) / 4 * 4;
-            grec.resize(off + rec_pad, T(0));
             for (int c = 0; c < gs; ++c) {
                 grec[off + c] = sv[sb + c]; grec[off + gs + c] = sXm[sb + c];
                 double xmt = 0;
-                for (int r = 0; r < gs; ++r) xmt += (double)sXm[sb + r] * (double)st[i][(size_t)r * gs + c];
+                for (int r = 0; r < gs; ++r) xmt += (double)sXm[sb + r] * (double)Vt[(size_t)r * gs + c];
                 grec[off + 2 * gs + c] = (T)xmt;
             }
-            for (int k = 0; k < gs * gs; ++k) grec[off + 3 * gs + k] = st[i][k];
+            for (int k = 0; k < gs * gs; ++k) grec[off + 3 * gs + k] = Vt[k];
+            for (size_t k = off + (size_t)gs * (gs + 3); k < off + rec_pad; ++k) grec[k] = T(0);
             // extension for the batched kernel (sweep_batched.cuh), right behind the base record: vector-load friendly copies
             //   [A(gsp) | xm(gsp) | V^T xm(gsp) | V rows padded to gsp | V^T rows padded to gsp],  gsp = gs rounded up to 4
             {
                 const int gsp = (gs + 3) / 4 * 4;
-                const size_t e0 = grec.size();
-                grec.resize(e0 + batch_ext_len(gs), T(0));
+                for (size_t k = e0; k < e0 + (size_t)batch_ext_len(gs); ++k) grec[k] = T(0);
                 for (int c = 0; c < gs; ++c) {
                     grec[e0 + c] = grec[off + c]; grec[e0 + gsp + c] = grec[off + gs + c]; grec[e0 + 2 * gsp + c] = grec[off + 2 * gs + c];
                     for (int r = 0; r < gs; ++r) {
-                        grec[e0 + 3 * gsp + (size_t)r * gsp + c] = st[i][(size_t)r * gs + c];                     // V[r][c]
-                        grec[e0 + 3 * gsp + (size_t)gs * gsp + (size_t)c * gsp + r] = st[i][(size_t)r * gs + c];  // V^T[c][r]
+                        grec[e0 + 3 * gsp + (size_t)r * gsp + c] = Vt[(size_t)r * gs + c];                     // V[r][c]
+                        grec[e0 + 3 * gsp + (size_t)gs * gsp + (size_t)c * gsp + r] = Vt[(size_t)r * gs + c];  // V^T[c][r]
                     }
                 }
             }
@@ -455,8 +470,6 @@ struct PathState {
             m.col = (K == 1) ? (int32_t)gi.f0 : (gi.icpt ? -(int32_t)(groups[g] + 1) : (int32_t)(gi.f0 * K + gi.k0)); m.gs = gs; m.begin = (int32_t)sb; m.rec_elems = rec_pad; m.rec_off = (int64_t)off;
             m.pen = (double)penalty[g];
             meta[i] = m;
-            gs_max_screen = std::max(gs_max_screen, gs); rec_max_screen = std::max(rec_max_screen, rec_pad);
-            feat_max_screen = std::max(feat_max_screen, gi.nfeat);
         }
     }
 
