@@ -82,6 +82,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "sweep_profile") Configs::sweep_profile = (int)value;
     else if (s == "sweep_batch") Configs::sweep_batch = (int)value;
     else if (s == "sweep_xchg") Configs::sweep_xchg = (int)value;
+    else if (s == "panel_gemm") Configs::panel_gemm = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -100,6 +101,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "sweep_profile") *value = Configs::sweep_profile;
     else if (s == "sweep_batch") *value = Configs::sweep_batch;
     else if (s == "sweep_xchg") *value = Configs::sweep_xchg;
+    else if (s == "panel_gemm") *value = Configs::panel_gemm;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }

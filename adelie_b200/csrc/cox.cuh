@@ -86,12 +86,24 @@ segscan_block_kernel(const double* __restrict__ in, const uint8_t* __restrict__ 
         blk_val[blockIdx.x] = bv; blk_flag[blockIdx.x] = (uint8_t)bf;
     }
 }
-// Pass 2: exclusive carries of the blocks (one thread; a few thousand blocks at most).
+// Pass 2: exclusive carries of the blocks.  One warp: lane l owns a contiguous chunk of blocks, the 32 chunk aggregates go through a
+// warp-level segmented scan, then every lane replays its chunk from its carry-in (two short serial loops of nb / 32 instead of one of nb).
 template <bool MAXOP>
 __global__ void segscan_carry_kernel(const double* __restrict__ blk_val, const uint8_t* __restrict__ blk_flag, int nb, double* __restrict__ carry) {
-    if (threadIdx.x || blockIdx.x) return;
-    double c = scan_identity<MAXOP>();
-    for (int b = 0; b < nb; ++b) { carry[b] = c; c = blk_flag[b] ? blk_val[b] : scan_op<MAXOP>(c, blk_val[b]); }
+    if (blockIdx.x || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int per = (nb + 31) / 32, b0 = min(nb, lane * per), b1 = min(nb, b0 + per);
+    double acc = scan_identity<MAXOP>(); int any = 0;
+    for (int b = b0; b < b1; ++b) { if (blk_flag[b]) { acc = blk_val[b]; any = 1; } else acc = scan_op<MAXOP>(acc, blk_val[b]); }
+    double tv = acc; int tf = any;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double ov = __shfl_up_sync(0xffffffffu, tv, d); const int of = __shfl_up_sync(0xffffffffu, tf, d);
+        if (lane >= d) { if (!tf) tv = scan_op<MAXOP>(ov, tv); tf |= of; }
+    }
+    double c = __shfl_up_sync(0xffffffffu, tv, 1);
+    if (lane == 0) c = scan_identity<MAXOP>();
+    for (int b = b0; b < b1; ++b) { carry[b] = c; c = blk_flag[b] ? blk_val[b] : scan_op<MAXOP>(c, blk_val[b]); }
 }
 // Pass 3: elements in front of the first head of their block take the carry.
 template <bool BACK, bool MAXOP>

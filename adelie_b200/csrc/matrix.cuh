@@ -436,6 +436,27 @@ struct DenseMatrix {
         AB_CUDA(cudaGetLastError());
     }
 
+    // Whole Gram panels in one pass per panel (panel_gram_kernel, fp32 dense columns): tmp must hold n_items * kPanelOut doubles
+    DevBuf<double> panel_tmp;
+    void d_panel_gram(const PanelItem* items_dev, int n_items, const float* w, float* Q, int ldq, int Ccap) {
+        if (n_items <= 0) return;
+        const int sms = DeviceInfo::get().sm_count;
+        int n_rb = std::max(1, std::min(sms, (2 * sms + n_items - 1) / n_items));
+        int rows_per_block = (int)((ld + n_rb - 1) / n_rb);
+        rows_per_block = (rows_per_block + kPanelRows - 1) / kPanelRows * kPanelRows;
+        n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
+        part.reserve_keep((size_t)n_rb * n_items * kPanelOut, stream);
+        panel_tmp.reserve_keep((size_t)n_items * kPanelOut, stream);
+        const size_t smem = sizeof(float) * (128 * kPanelStride + kPanelRows);
+        AB_CUDA(cudaFuncSetAttribute(panel_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        panel_gram_kernel<<<dim3(n_items, n_rb), 256, smem, stream>>>((const float*)X, ld, ld, items_dev, w, part.p, n_items, rows_per_block);
+        panel_gram_sum_kernel<<<n_items, 256, 0, stream>>>(items_dev, part.p, n_rb, n_items, panel_tmp.p);
+        DistContext& dc = DistContext::get();
+        if (dc.active()) dc.allreduce<double>(panel_tmp.p, (int64_t)n_items * kPanelOut, stream);      // row-sharded: sum the local panels over the ranks
+        panel_gram_scatter_kernel<float><<<n_items, 256, 0, stream>>>(items_dev, panel_tmp.p, Q, ldq, Ccap);
+        AB_CUDA(cudaGetLastError());
+    }
+
     // The batched look-ahead pin solve (sweep_batched.cuh); single response, single GPU, static weights.
     BatchGeometry last_bgeom{};
     void pin_solve_batched(const PinLaunch<T>& L, const BatchGeometry& g, const BatchLaunch<T>& bl) {

@@ -220,7 +220,7 @@ struct PathState {
     // Gram panels of the batched look-ahead kernel (sweep_batched.cuh): one list per sweep order (screen positions, active list)
     struct PanelList { DevBuf<T> Q; std::vector<int32_t> entries; int B = 0, Ccap = 0; };
     PanelList pl_screen, pl_active;
-    DevBuf<PairItem> d_pair_items;
+    DevBuf<PairItem> d_pair_items; DevBuf<PanelItem> d_panel_items;
     long long n_panels_built = 0, n_batched_launches = 0;
     std::vector<double> launch_cols, launch_sweeps, launch_ms;      // per sweep-kernel launch: column visits, sweeps, CUDA-event time
     int gs_max_screen = 1, rec_max_screen = 4, feat_max_screen = 1;
@@ -532,6 +532,36 @@ struct PathState {
                     off_t += g2;
                 }
                 off_k += gk;
+            }
+        }
+        if constexpr (std::is_same<T, float>::value) {
+            // Whole panels pay off when many blocks are new at once (a block costs ~5 us in pair_gram_kernel, a whole panel ~90 us
+            // + ~40 us of fixed cost): the usual incremental call (a few new groups at the tail) stays on the per-block kernel.
+            if (Configs::panel_gemm && !X->sparse && (double)items.size() * 5.0 > (double)(nb - b0) * 90.0 + 40.0) {
+                // whole panels b0 .. nb-1 in one pass each (panel_gram_kernel): every window column is read once per panel
+                std::vector<PanelItem> pitems;
+                for (size_t b = b0; b < nb; ++b) {
+                    const size_t p0 = b * B, p1 = std::min(N, p0 + B), p2 = std::min(N, p1 + B);
+                    PanelItem pi{}; pi.q_off = (int64_t)(b * pstride); pi.ncol = 0;
+                    for (size_t k = p0; k < p2; ++k) {
+                        int ck, gk; grp(k, ck, gk);
+                        for (int c = 0; c < gk; ++c) pi.cols[pi.ncol++] = ck + c;
+                        if (k + 1 == p1) pi.n_src = pi.ncol;
+                    }
+                    if (p1 == p0) continue;
+                    pitems.push_back(pi);
+                }
+                if (!pitems.empty()) {
+                    AB_CUDA(cudaStreamSynchronize(0));
+                    d_panel_items.reserve_keep(pitems.size());
+                    d_panel_items.upload(pitems.data(), pitems.size());
+                    X->d_panel_gram(d_panel_items.p, (int)pitems.size(), d_w, pl.Q.p, ldq, Ccap);
+                    AB_CUDA(cudaStreamSynchronize(0));          // `pitems` (pageable host memory) must outlive the upload
+                    n_kernel_launches += 3;
+                }
+                n_panels_built += (long long)(nb - b0);
+                pl.entries = entries;
+                return;
             }
         }
         if (!items.empty()) {

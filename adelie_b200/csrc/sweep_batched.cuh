@@ -1129,4 +1129,109 @@ __global__ void pair_gram_finalize_kernel(const PairItem* __restrict__ items, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Whole Gram panels (fp32): one item = one panel = X_b^T W [X_b | X_{b+1}] for the <= 64 columns of batch b against the <= 128 columns of
+// the window (batch b, then batch b + 1).  A CTA streams its row block in chunks of 64 rows: the window's columns are staged ONCE per
+// chunk in shared memory (column-major, row stride 68: 16-byte reads with at most the unavoidable 2-way bank conflict), every thread owns
+// a 4 x 8 tile of the 64 x 128 block (sources ty + 16 a, targets tx + 16 b) and reads 4 + 8 + 1 vectors per 128 FMAs.  Every column of
+// the window is read from HBM once per panel instead of once per (source group, target group) block: pair_gram_kernel moved
+// ~17 000 blocks x 16 MB per config-2 path.  Partial sums: fp32 inside a chunk, double across chunks and row blocks (deterministic).
+struct PanelItem { int64_t q_off; int32_t ncol, n_src; int32_t cols[128]; };
+constexpr int kPanelRows = 64;                 // rows per staged chunk
+constexpr int kPanelStride = kPanelRows + 4;   // shared-memory row stride of a column (floats)
+constexpr int kPanelOut = 64 * 128;            // compact outputs per panel: [source][window column]
+
+__global__ void __launch_bounds__(256)
+panel_gram_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, const PanelItem* __restrict__ items, const float* __restrict__ w,
+                  double* __restrict__ part, int n_panels, int rows_per_block)
+{
+    extern __shared__ __align__(16) float s_panel[];             // [128][kPanelStride] window tile, then w[kPanelRows]
+    float* s_w = s_panel + 128 * kPanelStride;
+    const PanelItem& it = items[blockIdx.x];
+    const int ncol = it.ncol, n_src = it.n_src;
+    const int rb = blockIdx.y;
+    const int64_t row0 = (int64_t)rb * rows_per_block;
+    const int64_t row1 = min((long long)n_pad, (long long)(row0 + rows_per_block));
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double accd[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) accd[a][b] = 0;
+    for (int e = tid; e < (128 - ncol) * kPanelStride; e += 256) s_panel[ncol * kPanelStride + e] = 0.f;      // unused window columns
+    for (int64_t r = row0; r < row1; r += kPanelRows) {
+        const int rows = (int)min((long long)kPanelRows, (long long)(row1 - r));      // multiple of 32
+        __syncthreads();
+        for (int e = tid; e < ncol * (kPanelRows / 4); e += 256) {
+            const int u = e / (kPanelRows / 4), q4 = e - u * (kPanelRows / 4);
+            float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * q4 < rows) x4 = *reinterpret_cast<const float4*>(X + (int64_t)it.cols[u] * ld + r + 4 * q4);
+            *reinterpret_cast<float4*>(s_panel + u * kPanelStride + 4 * q4) = x4;
+        }
+        if (tid < kPanelRows / 4) {
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (4 * tid < rows) w4 = *reinterpret_cast<const float4*>(w + r + 4 * tid);
+            *reinterpret_cast<float4*>(s_w + 4 * tid) = w4;
+        }
+        __syncthreads();
+        float acc[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
+        for (int q4 = 0; q4 < kPanelRows / 4; ++q4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_w + 4 * q4);
+            float4 xs[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                xs[a] = *reinterpret_cast<const float4*>(s_panel + (ty + 16 * a) * kPanelStride + 4 * q4);
+                xs[a].x *= w4.x; xs[a].y *= w4.y; xs[a].z *= w4.z; xs[a].w *= w4.w;
+            }
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const float4 xt = *reinterpret_cast<const float4*>(s_panel + (tx + 16 * b) * kPanelStride + 4 * q4);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) acc[a][b] += xs[a].x * xt.x + xs[a].y * xt.y + xs[a].z * xt.z + xs[a].w * xt.w;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) accd[a][b] += (double)acc[a][b];
+    }
+    double* out = part + ((size_t)rb * n_panels + blockIdx.x) * kPanelOut;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int s_ = ty + 16 * a, u = tx + 16 * b;
+            if (s_ < n_src && u < ncol) out[s_ * 128 + u] = accd[a][b];
+        }
+}
+
+// out: tmp[panel * kPanelOut + s * 128 + u] = sum over row blocks
+__global__ void panel_gram_sum_kernel(const PanelItem* __restrict__ items, const double* __restrict__ part, int n_rb, int n_panels, double* __restrict__ tmp)
+{
+    const PanelItem& it = items[blockIdx.x];
+    for (int e = threadIdx.x; e < it.n_src * 128; e += blockDim.x) {
+        if ((e & 127) >= it.ncol) continue;
+        double s_ = 0;
+        for (int rb = 0; rb < n_rb; ++rb) s_ += part[((size_t)rb * n_panels + blockIdx.x) * kPanelOut + e];
+        tmp[(size_t)blockIdx.x * kPanelOut + e] = s_;
+    }
+}
+// scatter into the panel: window column u < n_src -> panel column u, otherwise Ccap + (u - n_src)
+template <class T>
+__global__ void panel_gram_scatter_kernel(const PanelItem* __restrict__ items, const double* __restrict__ tmp, T* __restrict__ Q, int ldq, int Ccap)
+{
+    const PanelItem& it = items[blockIdx.x];
+    for (int e = threadIdx.x; e < it.n_src * 128; e += blockDim.x) {
+        const int s_ = e >> 7, u = e & 127;
+        if (u >= it.ncol) continue;
+        const int t = (u < it.n_src) ? u : Ccap + (u - it.n_src);
+        Q[it.q_off + (int64_t)s_ * ldq + t] = (T)tmp[(size_t)blockIdx.x * kPanelOut + e];
+    }
+}
+
 } // namespace ab
