@@ -225,7 +225,9 @@ struct DenseMatrix {
         constexpr int R = snp_gemv_rows_per_lane<KP>();
         const int64_t rows_per_tile = (int64_t)(kSnpGemvThreads / 32) * 32 * R;
         const int n_tiles = (int)((ld + rows_per_tile - 1) / rows_per_tile);
-        const int tiles_per_cta = (n_tiles + 31) / 32;                            // at most 32 partial rows for the final reduction
+        // partial rows for the final reduction: as many as 256 MB of partial sums allow (fewer re-stagings of v*w per CTA), at least 32
+        const int64_t rb_cap = std::max<int64_t>(32, ((int64_t)256 << 20) / ((int64_t)q * K * (int64_t)sizeof(double)));
+        const int tiles_per_cta = (int)((n_tiles + rb_cap - 1) / rb_cap);
         const int n_rb = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
         const int sms = DeviceInfo::get().sm_count;
         int col_chunks = std::max(1, std::min((q + 31) / 32, (16 * sms + n_rb - 1) / n_rb));
@@ -233,7 +235,7 @@ struct DenseMatrix {
         col_chunks = (q + cols_per_cta - 1) / cols_per_cta;
         part.reserve_keep((size_t)n_rb * q * K, stream);
         const size_t smem = snp_gemv_smem_bytes<T, KP>();
-        auto fn = snp_gemv_t_kernel<T, KP, SQ>;
+        auto fn = snp_center.n ? snp_gemv_t_kernel<T, KP, SQ, true> : snp_gemv_t_kernel<T, KP, SQ, false>;
         AB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<dim3(col_chunks, n_rb), kSnpGemvThreads, smem, stream>>>(snp_bits, snp_ldw, ld, snp_impute.p, snp_center.p, snp_scale.p, j0, q, cols_per_cta, tiles_per_cta, K, v, w, part.p);
         AB_CUDA(cudaGetLastError());

@@ -317,7 +317,8 @@ template <class T, int r> __device__ __forceinline__ T snp_pick(uint32_t word, c
     const T lo = b0 ? t.v1 : t.v0, hi = b0 ? t.v3 : t.v2;
     return b1 ? hi : lo;
 }
-template <class T, int KP, bool SQ>
+// STD: the matrix is a standardize view (values (k - c_j) / s_j from registers); otherwise the values 0 / 1 / 2 are immediates.
+template <class T, int KP, bool SQ, bool STD>
 __global__ void __launch_bounds__(kSnpGemvThreads)
 snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pad, const T* __restrict__ impute, const T* __restrict__ center,
                   const T* __restrict__ scale, int64_t j0, int q, int cols_per_cta,
@@ -399,9 +400,12 @@ snp_gemv_t_kernel(const uint32_t* __restrict__ packed, int64_t ldw, int64_t n_pa
 #pragma unroll
                 for (int u = 0; u < PF; ++u) {
                     const int c = cb + sub * NB + cc0 + u;
-                    w0[u] = 0; w1[u] = 0; imp[u] = SnpVals<T>{T(0), T(0), T(0), T(0)};   // a column past the end contributes exact zeros
+                    // a column past the end contributes exact zeros: all its codes are 0 and v0 is 0 (v1..v3 are never picked; the
+                    // non-STD values stay compile-time constants on both paths)
+                    w0[u] = 0; w1[u] = 0; imp[u] = SnpVals<T>{T(0), STD ? T(0) : T(1), STD ? T(0) : T(2), T(0)};
                     if (c < c_end && live) {
-                        imp[u] = snp_vals<T>(impute, center, scale, j0 + c);
+                        if (STD) imp[u] = snp_vals<T>(impute, center, scale, j0 + c);
+                        else imp[u] = SnpVals<T>{T(0), T(1), T(2), impute[j0 + c]};
                         const uint8_t* src = lane_base + (j0 + c) * ldw * 4;
                         if (R == 32) { const uint2 q2 = *reinterpret_cast<const uint2*>(src); w0[u] = q2.x; w1[u] = q2.y; }
                         else if (R == 16) w0[u] = *reinterpret_cast<const uint32_t*>(src);
