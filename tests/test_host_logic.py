@@ -71,3 +71,34 @@ def test_constraints_rejected():
     _check_constraints(None); _check_constraints([None, None])
     with pytest.raises(RuntimeError):
         _check_constraints([object()])
+
+
+def test_diagnostic_coefficient_interpolates_like_the_reference():
+    """adelie/diagnostic.py:560-646: linear interpolation in lambda between neighbouring solutions, boundary solution outside."""
+    import scipy.sparse as sp
+    from adelie_b200.diagnostic import coefficient, predict
+    lmdas = np.array([1.0, 0.5, 0.25])
+    betas = sp.csr_matrix(np.array([[0.0, 0.0], [1.0, 0.0], [2.0, 4.0]]))
+    icpt = np.array([0.0, 1.0, 3.0])
+    b, b0 = coefficient(lmda=0.75, betas=betas, intercepts=icpt, lmdas=lmdas)
+    np.testing.assert_allclose(np.asarray(b.todense()).ravel(), [0.5, 0.0]); assert b0 == pytest.approx(0.5)
+    b, b0 = coefficient(lmda=0.3, betas=betas, intercepts=icpt, lmdas=lmdas)
+    np.testing.assert_allclose(np.asarray(b.todense()).ravel(), [1.8, 3.2]); assert b0 == pytest.approx(2.6)
+    b, b0 = coefficient(lmda=2.0, betas=betas, intercepts=icpt, lmdas=lmdas)          # above the path: first solution
+    assert b0 == 0.0 and b.nnz == 0
+    b, b0 = coefficient(lmda=0.1, betas=betas, intercepts=icpt, lmdas=lmdas)          # below the path: last solution
+    assert b0 == 3.0
+    X = np.arange(6.0).reshape(3, 2)
+    eta = predict(X, betas, icpt, offsets=np.array([10.0, 20.0, 30.0]))
+    np.testing.assert_allclose(eta, betas.toarray() @ X.T + icpt[:, None] + np.array([10.0, 20.0, 30.0])[None])
+
+
+def test_standardize_and_subset_numpy_paths():
+    import adelie_b200 as ad
+    rng = np.random.default_rng(0)
+    Z = rng.normal(1.0, 2.0, (50, 4))
+    S = ad.matrix.standardize(Z, ddof=1)
+    np.testing.assert_allclose(S.mean(axis=0), 0, atol=1e-12)
+    np.testing.assert_allclose(S.std(axis=0, ddof=1), 1, atol=1e-12)
+    assert S.flags.f_contiguous and not np.shares_memory(S, Z)
+    assert np.array_equal(ad.matrix.subset(Z, [3, 1], axis=1), Z[:, [3, 1]])
