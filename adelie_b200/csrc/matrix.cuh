@@ -269,17 +269,6 @@ struct DenseMatrix {
     // host column-major (ldh >= n) or row-major (order == 1, ldh >= p) source
     void upload(const T* h, int order, int64_t ldh) {
         if (order == 0) {
-            if (ld == ldh && ld == n) {
-                // contiguous on both sides: a few large 1-D copies alternating between two streams keep the copy engines busy
-                // (a pitched 2-D copy of p rows measured ~44 GB/s from pinned memory)
-                cudaStream_t st[2]; AB_CUDA(cudaStreamCreate(&st[0])); AB_CUDA(cudaStreamCreate(&st[1]));
-                const size_t total = (size_t)n * p * sizeof(T), chunk = (size_t)256 << 20;
-                size_t k = 0;
-                for (size_t off = 0; off < total; off += chunk, ++k)
-                    AB_CUDA(cudaMemcpyAsync((char*)X + off, (const char*)h + off, std::min(chunk, total - off), cudaMemcpyHostToDevice, st[k & 1]));
-                AB_CUDA(cudaStreamSynchronize(st[0])); AB_CUDA(cudaStreamSynchronize(st[1]));
-                AB_CUDA(cudaStreamDestroy(st[0])); AB_CUDA(cudaStreamDestroy(st[1]));
-            } else
             AB_CUDA(cudaMemcpy2D(X, ld * sizeof(T), h, ldh * sizeof(T), n * sizeof(T), p, cudaMemcpyHostToDevice));
         } else {
             // row-major host data: transpose through column chunks on the host side of the copy
