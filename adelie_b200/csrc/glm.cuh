@@ -173,6 +173,39 @@ struct GlmBinomialLogit : Glm<T> {
     }
 };
 
+// glm_poisson.ipp:7-66 (log link)
+template <class T>
+struct GlmPoisson : Glm<T> {
+    using B = Glm<T>;
+    GlmPoisson(const T* hy, const T* hw, int64_t n_) {
+        B::name = "poisson"; B::n = n_;
+        B::y.alloc(pad_rows(n_)); B::w.alloc(pad_rows(n_));
+        B::y.upload(hy, n_); B::w.upload(hw, n_);
+        AB_CUDA(cudaStreamSynchronize(0));
+    }
+    void gradient(const T* eta, T* grad) override {
+        const T* y = B::y.p; const T* w = B::w.p;
+        B::mr.map(B::n, [=] __device__(int64_t i, double*) { grad[i] = w[i] * (y[i] - exp(eta[i])); });
+    }
+    void hessian(const T*, const T* grad, T* hess) override {
+        const T* y = B::y.p; const T* w = B::w.p;
+        B::mr.map(B::n, [=] __device__(int64_t i, double*) { hess[i] = w[i] * y[i] - grad[i]; });
+    }
+    T loss(const T* eta) override {
+        const T* y = B::y.p; const T* w = B::w.p; double s;
+        const T mx = std::numeric_limits<T>::max();
+        B::mr.template run<1>(B::n, [=] __device__(int64_t i, double* acc) { acc[0] += (double)(w[i] * (min(-eta[i], mx) * y[i] + exp(eta[i]))); }, &s);
+        return (T)s;
+    }
+    T loss_full() override {
+        const T* y = B::y.p; const T* w = B::w.p; double s;
+        const T mx = std::numeric_limits<T>::max();
+        B::mr.template run<1>(B::n, [=] __device__(int64_t i, double* acc) { acc[0] += (double)(w[i] * (min(-log(y[i]), mx) * y[i] + y[i])); }, &s);
+        return (T)s;
+    }
+    void inv_link(const T* eta, T* out) override { B::mr.map(B::n, [=] __device__(int64_t i, double*) { out[i] = exp(eta[i]); }); }
+};
+
 // glm_multigaussian.ipp:17-68: y, eta (n,K) row-major flattened; weights (n,); everything / K.
 template <class T>
 struct GlmMultiGaussian : Glm<T> {

@@ -25,6 +25,10 @@ def _sample_y(glm, eta, beta, rho=0, snr=1):
         mu = 1 / (1 + np.exp(-eta))
         y = np.random.binomial(1, mu).astype(np.float64)
         return _glm.binomial(y=y.ravel())
+    if glm == "poisson":                                   # mu = exp(eta / scale), y ~ Poisson(mu)  (adelie/data.py:63-81)
+        scale = np.sqrt(rho * np.sum(beta) ** 2 + (1 - rho) * np.sum(beta ** 2))
+        mu = np.exp(eta.ravel() / max(scale, 1e-300))
+        return _glm.poisson(y=np.random.poisson(mu).astype(np.float64))
     if glm == "cox":
         scale = np.sqrt(rho * np.sum(beta) ** 2 + (1 - rho) * np.sum(beta ** 2))
         eta = (eta / max(scale, 1e-300)).ravel()

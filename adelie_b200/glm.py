@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from . import dist as _dist
 
-_FAMILY = {"gaussian": 1, "binomial_logit": 2, "multigaussian": 3, "cox": 4}
+_FAMILY = {"gaussian": 1, "binomial_logit": 2, "multigaussian": 3, "cox": 4, "poisson": 5}
 
 
 def _coerce_dtype(y, dtype):
@@ -135,6 +135,16 @@ class _Binomial(GlmBase):
         return binomial(y=self.y, weights=self.weights if weights is None else weights, dtype=self.dtype)
 
 
+class _Poisson(GlmBase):
+    def __init__(self, y, weights, dtype):
+        if y.ndim != 1:
+            raise RuntimeError("y must be 1-dimensional.")
+        self._init_common("poisson", y, weights, dtype)
+
+    def reweight(self, weights=None):
+        return poisson(y=self.y, weights=self.weights if weights is None else weights, dtype=self.dtype)
+
+
 class _MultiGaussian(GlmMultiBase):
     def __init__(self, y, weights, dtype, opt):
         if y.ndim != 2:
@@ -180,6 +190,12 @@ def binomial(y: np.ndarray, *, weights: np.ndarray = None, link: str = "logit", 
         raise RuntimeError("adelie_b200: only the logit link is in scope (probit is not on the hot path).")
     y, dtype = _coerce_dtype(np.asarray(y), dtype)
     return _Binomial(y, weights, dtype)
+
+
+def poisson(y: np.ndarray, *, weights: np.ndarray = None, dtype: Union[np.float32, np.float64] = None):
+    """Poisson family, log link (adelie/glm.py ``poisson``; CORE/glm/glm_poisson.ipp:7-66) -- SURVEY 8f rank 4."""
+    y, dtype = _coerce_dtype(np.asarray(y), dtype)
+    return _Poisson(y, weights, dtype)
 
 
 def multigaussian(y: np.ndarray, *, weights: np.ndarray = None, dtype: Union[np.float32, np.float64] = None, opt: bool = True):

@@ -904,6 +904,28 @@ struct GlmBinomialLogit : GlmBase<T> {                                         /
     void inv_link(const T* eta, T* out) override { for (idx_t i = 0; i < B::n; ++i) out[i] = 1 / (1 + std::exp(-eta[i])); }
 };
 
+// Poisson, log link (glm_poisson.ipp:7-66)
+template <class T>
+struct GlmPoisson : GlmBase<T> {
+    using B = GlmBase<T>;
+    GlmPoisson(const T* y, const T* w, idx_t n) { B::name = "poisson"; B::y = y; B::w = w; B::n = n; }
+    void gradient(const T* eta, T* grad) override { for (idx_t i = 0; i < B::n; ++i) grad[i] = B::w[i] * (B::y[i] - std::exp(eta[i])); }
+    void hessian(const T*, const T* grad, T* hess) override { for (idx_t i = 0; i < B::n; ++i) hess[i] = B::w[i] * B::y[i] - grad[i]; }
+    T loss(const T* eta) override {                                             // stable when y == 0 and eta = -inf (:44-47)
+        constexpr T mx = std::numeric_limits<T>::max();
+        T s = 0;
+        for (idx_t i = 0; i < B::n; ++i) s += B::w[i] * (std::min(-eta[i], mx) * B::y[i] + std::exp(eta[i]));
+        return s;
+    }
+    T loss_full() override {
+        constexpr T mx = std::numeric_limits<T>::max();
+        T s = 0;
+        for (idx_t i = 0; i < B::n; ++i) s += B::w[i] * (std::min(-std::log(B::y[i]), mx) * B::y[i] + B::y[i]);
+        return s;
+    }
+    void inv_link(const T* eta, T* out) override { for (idx_t i = 0; i < B::n; ++i) out[i] = std::exp(eta[i]); }
+};
+
 // MultiGaussian (glm_multigaussian.ipp:17-68): y, eta are (n,K) row-major;
 // everything is the Gaussian family divided by K.
 template <class T>

@@ -129,7 +129,7 @@ def _dt(dtype):
     return 0 if np.dtype(dtype) == np.float32 else 1
 
 
-FAMILIES = {"gaussian_opt": 0, "gaussian": 1, "binomial": 2, "multigaussian": 3, "cox": 4}
+FAMILIES = {"gaussian_opt": 0, "gaussian": 1, "binomial": 2, "multigaussian": 3, "cox": 4, "poisson": 5}
 
 
 def set_config(name, value):
@@ -185,7 +185,7 @@ def _collect(h, p_cols, dtype):
 # GLM spec helpers
 # --------------------------------------------------------------------------
 def glm_spec(family, y, weights=None, dtype=np.float64, **kw):
-    """family in {gaussian, binomial, multigaussian, cox}; weights normalised to sum 1 (adelie/glm.py:46-55)."""
+    """family in {gaussian, binomial, multigaussian, cox, poisson}; weights normalised to sum 1 (adelie/glm.py:46-55)."""
     y = np.ascontiguousarray(y, dtype=dtype)
     n = y.shape[0]
     if weights is None:

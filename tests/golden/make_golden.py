@@ -5,7 +5,7 @@ Run in the build container only (needs /root/reference):  python tests/golden/ma
 The reference's compiled core cannot be built here (Eigen is not vendored), but its test-suite carries independent,
 pure-NumPy definitions of every family on the hot path (tests/test_glm.py: GlmTestGaussian :114-132,
 GlmTestBinomialLogit :158-181, GlmTestCoxPack :458-593 / GlmTestCox :596-661 with exact O(n^2) at-risk sums,
-GlmTestMultiGaussian :711-732).  We import those classes from the reference tree (with the compiled `adelie` package
+GlmTestMultiGaussian :711-732, GlmTestPoisson :252-272).  We import those classes from the reference tree (with the compiled `adelie` package
 stubbed out), feed them the seeded inputs of the reference's own test functions, and commit the outputs as golden vectors.
 """
 import os
@@ -106,6 +106,12 @@ def main():
             eta = np.random.normal(0, 1, (n, K))
             r = evaluate(ns["GlmTestMultiGaussian"](y=y, weights=w), eta, (n, K))
             out.update({f"multigaussian_{n}_{K}_{k}": v for k, v in dict(y=y, w=w, eta=eta, **r).items()})
+    for n in sizes:                                   # test_poisson (:275-290)
+        np.random.seed(0)
+        y = np.random.poisson(1, n).astype(float); w = weights_like_reference(n)
+        eta = np.random.normal(0, 1, n)
+        r = evaluate(ns["GlmTestPoisson"](y=y, weights=w), eta, (n,))
+        out.update({f"poisson_{n}_{k}": v for k, v in dict(y=y, w=w, eta=eta, **r).items()})
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, len(out), "arrays")
 

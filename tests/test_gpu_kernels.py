@@ -97,6 +97,8 @@ def test_glm_families_vs_reference_golden(dtype, rtol, atol, n):
     for K in (1, 2, 3, 4):
         pre = f"multigaussian_{n}_{K}_"
         _glm_check(ad.glm.multigaussian(G[pre + "y"], weights=G[pre + "w"], dtype=dtype), pre, dtype, rtol, atol)
+    pre = f"poisson_{n}_"
+    _glm_check(ad.glm.poisson(G[pre + "y"], weights=G[pre + "w"], dtype=dtype), pre, dtype, rtol, atol)
 
 
 def test_glm_large_vs_oracle():
@@ -136,3 +138,18 @@ def test_bcd_solve_vs_oracle(p, sparsity, l2, solver):
     assert abs(hi - orc.root_upper_bound(quad + l2, linear, l1, 0.0)) < 1e-9 * max(1, hi)
     assert ad.bcd.root_function(lo, D=quad + l2, v=linear, l1=l1) >= -1e-9
     assert ad.bcd.root_function(hi, D=quad + l2, v=linear, l1=l1) <= 1e-9
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.5])
+def test_poisson_path_vs_oracle(alpha):
+    """the poisson family through the generic IRLS driver."""
+    data = ad.data.dense(800, 30, 10, glm="poisson", seed=6)
+    y = data["glm"].y
+    kw = dict(groups=data["groups"], penalty=data["penalty"], alpha=alpha, tol=1e-13, irls_tol=1e-11, early_exit=False, lmda_path_size=10, min_ratio=0.2)
+    st = ad.grpnet(data["X"], ad.glm.poisson(y), progress_bar=False, **kw)
+    ref = orc.grpnet(data["X"], orc.glm_spec("poisson", y), **kw)
+    assert st.error == "" and ref.error == "", (st.error, ref.error)
+    B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
+    assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
+    np.testing.assert_allclose(st.intercepts, ref.intercepts, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(st.devs, ref.devs, rtol=1e-6, atol=1e-8)

@@ -51,3 +51,9 @@ def test_cox(n, tie):
 def test_multigaussian(n, K):
     pre = f"multigaussian_{n}_{K}_"
     _check(orc.glm_spec("multigaussian", G[pre + "y"], G[pre + "w"]), pre)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_poisson(n):
+    pre = f"poisson_{n}_"
+    _check(orc.glm_spec("poisson", G[pre + "y"], G[pre + "w"]), pre)
