@@ -173,6 +173,55 @@ struct GlmBinomialLogit : Glm<T> {
     }
 };
 
+// glm_binomial.ipp:100-190 (probit link); loss_full is the binomial one (:14-35)
+template <class T> __device__ __forceinline__ T probit_cdf(T x) { return T(0.5) * (T(1) + erf(x * T(0.70710678118654752440))); }
+template <class T> __device__ __forceinline__ T probit_pdf(T x) { return T(0.39894228040143267794) * exp(T(-0.5) * x * x); }
+template <class T>
+struct GlmBinomialProbit : Glm<T> {
+    using B = Glm<T>;
+    GlmBinomialProbit(const T* hy, const T* hw, int64_t n_) {
+        B::name = "binomial_probit"; B::n = n_;
+        B::y.alloc(pad_rows(n_)); B::w.alloc(pad_rows(n_));
+        B::y.upload(hy, n_); B::w.upload(hw, n_);
+        AB_CUDA(cudaStreamSynchronize(0));
+    }
+    void gradient(const T* eta, T* grad) override {
+        const T* y = B::y.p; const T* w = B::w.p; const T mx = std::numeric_limits<T>::max();
+        B::mr.map(B::n, [=] __device__(int64_t i, double*) {
+            const T P = probit_cdf<T>(eta[i]);
+            grad[i] = w[i] * probit_pdf<T>(eta[i]) * (y[i] * min(T(1) / P, mx) - (T(1) - y[i]) * min(T(1) / (T(1) - P), mx));
+        });
+    }
+    void hessian(const T* eta, const T* grad, T* hess) override {
+        const T* y = B::y.p; const T* w = B::w.p; const T mx = std::numeric_limits<T>::max();
+        B::mr.map(B::n, [=] __device__(int64_t i, double*) {
+            const T P = probit_cdf<T>(eta[i]), ph = probit_pdf<T>(eta[i]);
+            hess[i] = w[i] * (y[i] * min(T(1) / (P * P), mx) + (T(1) - y[i]) * min(T(1) / ((T(1) - P) * (T(1) - P)), mx)) * ph * ph + eta[i] * grad[i];
+        });
+    }
+    T loss(const T* eta) override {
+        const T* y = B::y.p; const T* w = B::w.p; const T mx = std::numeric_limits<T>::max(); double s;
+        B::mr.template run<1>(B::n, [=] __device__(int64_t i, double* acc) {
+            const T P = probit_cdf<T>(eta[i]);
+            acc[0] -= (double)(w[i] * (y[i] * max(log(P), -mx) + (T(1) - y[i]) * max(log(T(1) - P), -mx)));
+        }, &s);
+        return (T)s;
+    }
+    T loss_full() override {
+        const T* y = B::y.p; const T* w = B::w.p; double s;
+        B::mr.template run<1>(B::n, [=] __device__(int64_t i, double* acc) {
+            const T yi = y[i];
+            const T ly = log(yi), l1 = log(T(1) - yi);
+            T v = 0;
+            if (!(isinf(ly) || isnan(ly))) v -= w[i] * yi * ly;
+            if (!(isinf(l1) || isnan(l1))) v -= w[i] * (T(1) - yi) * l1;
+            acc[0] += (double)v;
+        }, &s);
+        return (T)s;
+    }
+    void inv_link(const T* eta, T* out) override { B::mr.map(B::n, [=] __device__(int64_t i, double*) { out[i] = probit_cdf<T>(eta[i]); }); }
+};
+
 // glm_poisson.ipp:7-66 (log link)
 template <class T>
 struct GlmPoisson : Glm<T> {

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from . import dist as _dist
 
-_FAMILY = {"gaussian": 1, "binomial_logit": 2, "multigaussian": 3, "cox": 4, "poisson": 5}
+_FAMILY = {"gaussian": 1, "binomial_logit": 2, "multigaussian": 3, "cox": 4, "poisson": 5, "binomial_probit": 6}
 
 
 def _coerce_dtype(y, dtype):
@@ -126,13 +126,14 @@ class _Gaussian(GlmBase):
 
 
 class _Binomial(GlmBase):
-    def __init__(self, y, weights, dtype):
+    def __init__(self, y, weights, dtype, link="logit"):
         if y.ndim != 1:
             raise RuntimeError("y must be 1-dimensional.")
-        self._init_common("binomial_logit", y, weights, dtype)
+        self.link = link
+        self._init_common("binomial_" + link, y, weights, dtype)
 
     def reweight(self, weights=None):
-        return binomial(y=self.y, weights=self.weights if weights is None else weights, dtype=self.dtype)
+        return binomial(y=self.y, weights=self.weights if weights is None else weights, link=self.link, dtype=self.dtype)
 
 
 class _Poisson(GlmBase):
@@ -185,11 +186,11 @@ def gaussian(y: np.ndarray, *, weights: np.ndarray = None, dtype: Union[np.float
 
 
 def binomial(y: np.ndarray, *, weights: np.ndarray = None, link: str = "logit", dtype: Union[np.float32, np.float64] = None):
-    """Binomial family, logit link (adelie/glm.py:83-196; CORE/glm/glm_binomial.ipp:47-98)."""
-    if link != "logit":
-        raise RuntimeError("adelie_b200: only the logit link is in scope (probit is not on the hot path).")
+    """Binomial family, logit or probit link (adelie/glm.py:83-196; CORE/glm/glm_binomial.ipp:47-98, probit :100-190)."""
+    if link not in ("logit", "probit"):
+        raise RuntimeError("link must be one of 'logit', 'probit'.")
     y, dtype = _coerce_dtype(np.asarray(y), dtype)
-    return _Binomial(y, weights, dtype)
+    return _Binomial(y, weights, dtype, link)
 
 
 def poisson(y: np.ndarray, *, weights: np.ndarray = None, dtype: Union[np.float32, np.float64] = None):

@@ -904,6 +904,40 @@ struct GlmBinomialLogit : GlmBase<T> {                                         /
     void inv_link(const T* eta, T* out) override { for (idx_t i = 0; i < B::n; ++i) out[i] = 1 / (1 + std::exp(-eta[i])); }
 };
 
+// Binomial, probit link (glm_binomial.ipp:100-190): Phi = 0.5 (1 + erf(eta / sqrt 2)), phi = exp(-eta^2 / 2) / sqrt(2 pi)
+template <class T>
+struct GlmBinomialProbit : GlmBase<T> {
+    using B = GlmBase<T>;
+    GlmBinomialProbit(const T* y, const T* w, idx_t n) { B::name = "binomial_probit"; B::y = y; B::w = w; B::n = n; }
+    static T cdf(T x) { return T(0.5) * (1 + std::erf(x / T(M_SQRT2))); }
+    static T pdf(T x) { return T(0.5 * M_2_SQRTPI / M_SQRT2) * std::exp(T(-0.5) * x * x); }
+    void gradient(const T* eta, T* grad) override {
+        constexpr T mx = std::numeric_limits<T>::max();
+        for (idx_t i = 0; i < B::n; ++i) {
+            const T P = cdf(eta[i]);
+            grad[i] = B::w[i] * pdf(eta[i]) * (B::y[i] * std::min(1 / P, mx) - (1 - B::y[i]) * std::min(1 / (1 - P), mx));
+        }
+    }
+    void hessian(const T* eta, const T* grad, T* hess) override {
+        constexpr T mx = std::numeric_limits<T>::max();
+        for (idx_t i = 0; i < B::n; ++i) {
+            const T P = cdf(eta[i]), ph = pdf(eta[i]);
+            hess[i] = B::w[i] * (B::y[i] * std::min(1 / (P * P), mx) + (1 - B::y[i]) * std::min(1 / ((1 - P) * (1 - P)), mx)) * ph * ph + eta[i] * grad[i];
+        }
+    }
+    T loss(const T* eta) override {
+        constexpr T mx = std::numeric_limits<T>::max();
+        T s = 0;
+        for (idx_t i = 0; i < B::n; ++i) {
+            const T P = cdf(eta[i]);
+            s += B::w[i] * (B::y[i] * std::max(std::log(P), -mx) + (1 - B::y[i]) * std::max(std::log(1 - P), -mx));
+        }
+        return -s;
+    }
+    T loss_full() override { return binomial_loss_full(B::y, B::w, B::n); }
+    void inv_link(const T* eta, T* out) override { for (idx_t i = 0; i < B::n; ++i) out[i] = cdf(eta[i]); }
+};
+
 // Poisson, log link (glm_poisson.ipp:7-66)
 template <class T>
 struct GlmPoisson : GlmBase<T> {

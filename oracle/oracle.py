@@ -129,7 +129,7 @@ def _dt(dtype):
     return 0 if np.dtype(dtype) == np.float32 else 1
 
 
-FAMILIES = {"gaussian_opt": 0, "gaussian": 1, "binomial": 2, "multigaussian": 3, "cox": 4, "poisson": 5}
+FAMILIES = {"gaussian_opt": 0, "gaussian": 1, "binomial": 2, "multigaussian": 3, "cox": 4, "poisson": 5, "probit": 6}
 
 
 def set_config(name, value):

@@ -88,6 +88,8 @@ def main():
             eta = np.random.normal(0, 1, n)
             r = evaluate(ns["GlmTestBinomialLogit"](y=y, weights=w), eta, (n,))
             out.update({f"binomial_{n}_{int(binary)}_{k}": v for k, v in dict(y=y, w=w, eta=eta, **r).items()})
+            r = evaluate(ns["GlmTestBinomialProbit"](y=y, weights=w), eta, (n,))          # probit link (GlmTestBinomialProbit :184-217)
+            out.update({f"probit_{n}_{int(binary)}_{k}": v for k, v in dict(y=y, w=w, eta=eta, **r).items()})
     for n in sizes:                                   # test_cox (:663-705): discrete times => ties, 3 strata, zero weights
         for tie in ("efron", "breslow"):
             np.random.seed(0)

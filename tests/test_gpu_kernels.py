@@ -97,6 +97,9 @@ def test_glm_families_vs_reference_golden(dtype, rtol, atol, n):
     for K in (1, 2, 3, 4):
         pre = f"multigaussian_{n}_{K}_"
         _glm_check(ad.glm.multigaussian(G[pre + "y"], weights=G[pre + "w"], dtype=dtype), pre, dtype, rtol, atol)
+    for binary in (0, 1):
+        pre = f"probit_{n}_{binary}_"
+        _glm_check(ad.glm.binomial(G[pre + "y"], weights=G[pre + "w"], link="probit", dtype=dtype), pre, dtype, rtol * 5, atol * 5)
     pre = f"poisson_{n}_"
     _glm_check(ad.glm.poisson(G[pre + "y"], weights=G[pre + "w"], dtype=dtype), pre, dtype, rtol, atol)
 
@@ -152,4 +155,16 @@ def test_poisson_path_vs_oracle(alpha):
     B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
     assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
     np.testing.assert_allclose(st.intercepts, ref.intercepts, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(st.devs, ref.devs, rtol=1e-6, atol=1e-8)
+
+
+def test_probit_path_vs_oracle():
+    data = ad.data.dense(800, 30, 10, glm="binomial", seed=8)
+    y = data["glm"].y
+    kw = dict(groups=data["groups"], penalty=data["penalty"], alpha=0.7, tol=1e-13, irls_tol=1e-11, early_exit=False, lmda_path_size=10, min_ratio=0.2)
+    st = ad.grpnet(data["X"], ad.glm.binomial(y, link="probit"), progress_bar=False, **kw)
+    ref = orc.grpnet(data["X"], orc.glm_spec("probit", y), **kw)
+    assert st.error == "" and ref.error == "", (st.error, ref.error)
+    B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
+    assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
     np.testing.assert_allclose(st.devs, ref.devs, rtol=1e-6, atol=1e-8)

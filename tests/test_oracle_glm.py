@@ -57,3 +57,10 @@ def test_multigaussian(n, K):
 def test_poisson(n):
     pre = f"poisson_{n}_"
     _check(orc.glm_spec("poisson", G[pre + "y"], G[pre + "w"]), pre)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("binary", [0, 1])
+def test_binomial_probit(n, binary):
+    pre = f"probit_{n}_{binary}_"
+    _check(orc.glm_spec("probit", G[pre + "y"], G[pre + "w"]), pre)
