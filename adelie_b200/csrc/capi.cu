@@ -606,6 +606,7 @@ static Glm<T>* make_glm(int family, int64_t n, int64_t K, const void* y, const v
         case AB_GLM_GAUSSIAN: return new GlmGaussian<T>((const T*)y, (const T*)w, n);
         case AB_GLM_BINOMIAL_LOGIT: return new GlmBinomialLogit<T>((const T*)y, (const T*)w, n);
         case AB_GLM_MULTIGAUSSIAN: return new GlmMultiGaussian<T>((const T*)y, (const T*)w, n, K);
+        case AB_GLM_MULTINOMIAL: return new GlmMultinomial<T>((const T*)y, (const T*)w, n, K);
         case AB_GLM_POISSON: return new GlmPoisson<T>((const T*)y, (const T*)w, n);
         case AB_GLM_BINOMIAL_PROBIT: return new GlmBinomialProbit<T>((const T*)y, (const T*)w, n);
     }

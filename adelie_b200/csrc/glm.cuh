@@ -286,4 +286,65 @@ struct GlmMultiGaussian : Glm<T> {
     void inv_link(const T* eta, T* out) override { B::mr.map(B::n, [=] __device__(int64_t i, double*) { out[i] = eta[i]; }); }
 };
 
+// glm_multinomial.ipp:6-132: y, eta (n,K) row-major flattened, weights (n,); one thread per observation, K <= 16 classes in registers.
+template <class T>
+struct GlmMultinomial : Glm<T> {
+    using B = Glm<T>;
+    int64_t rows = 0;
+    GlmMultinomial(const T* hy, const T* hw, int64_t n_rows, int64_t K_) : rows(n_rows) {
+        if (K_ <= 1) throw core_error("y must have at least 2 columns (classes).");
+        if (K_ > 16) throw core_error("multi-response problems with more than 16 classes are not supported.");
+        B::name = "multinomial"; B::is_multi = true; B::K = K_; B::n = n_rows * K_;
+        B::y.alloc(pad_rows(n_rows) * K_); B::w.alloc(pad_rows(n_rows));
+        B::y.upload(hy, n_rows * K_); B::w.upload(hw, n_rows);
+        AB_CUDA(cudaStreamSynchronize(0));
+    }
+    void gradient(const T* eta, T* grad) override {
+        const T* y = B::y.p; const T* w = B::w.p; const int K = (int)B::K;
+        B::mr.map(rows, [=] __device__(int64_t i, double*) {
+            const T* e = eta + i * K;
+            T m = e[0]; for (int k = 1; k < K; ++k) m = max(m, e[k]);
+            T sum = 0; for (int k = 0; k < K; ++k) sum += exp(e[k] - m);
+            for (int k = 0; k < K; ++k) grad[i * K + k] = (y[i * K + k] - exp(e[k] - m) / sum) * w[i] / T(K);
+        });
+    }
+    void hessian(const T*, const T* grad, T* hess) override {
+        const T* y = B::y.p; const T* w = B::w.p; const int K = (int)B::K;
+        B::mr.map(B::n, [=] __device__(int64_t e, double*) {
+            const int64_t i = e / K;
+            const T h = y[e] * w[i] / T(K) - grad[e];
+            hess[e] = h * T(2) * (T(1) - T(K) * (h / (w[i] + T(w[i] <= 0))));
+        });
+    }
+    T loss(const T* eta) override {
+        const T* y = B::y.p; const T* w = B::w.p; const int K = (int)B::K; double s;
+        B::mr.template run<1>(rows, [=] __device__(int64_t i, double* acc) {
+            const T* e = eta + i * K;
+            T m = e[0]; for (int k = 1; k < K; ++k) m = max(m, e[k]);
+            T ye = 0, se = 0;
+            for (int k = 0; k < K; ++k) { ye += y[i * K + k] * (e[k] - m); se += exp(e[k] - m); }
+            acc[0] += (double)(w[i] * (-ye + log(se)));
+        }, &s);
+        return (T)(s / K);
+    }
+    T loss_full() override {
+        const T* y = B::y.p; const T* w = B::w.p; const int K = (int)B::K; double s;
+        B::mr.template run<1>(rows, [=] __device__(int64_t i, double* acc) {
+            T sum = 0;
+            for (int k = 0; k < K; ++k) { const T yk = y[i * K + k]; const T l = log(yk); if (!(isinf(l) || isnan(l))) sum += yk * l; }
+            acc[0] -= (double)(sum * w[i]);
+        }, &s);
+        return (T)(s / K);
+    }
+    void inv_link(const T* eta, T* out) override {
+        const int K = (int)B::K;
+        B::mr.map(rows, [=] __device__(int64_t i, double*) {
+            const T* e = eta + i * K;
+            T m = e[0]; for (int k = 1; k < K; ++k) m = max(m, e[k]);
+            T sum = 0; for (int k = 0; k < K; ++k) sum += exp(e[k] - m);
+            for (int k = 0; k < K; ++k) out[i * K + k] = exp(e[k] - m) / sum;
+        });
+    }
+};
+
 } // namespace ab

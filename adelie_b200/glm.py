@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from . import dist as _dist
 
-_FAMILY = {"gaussian": 1, "binomial_logit": 2, "multigaussian": 3, "cox": 4, "poisson": 5, "binomial_probit": 6}
+_FAMILY = {"gaussian": 1, "binomial_logit": 2, "multigaussian": 3, "cox": 4, "poisson": 5, "binomial_probit": 6, "multinomial": 7}
 
 
 def _coerce_dtype(y, dtype):
@@ -158,6 +158,21 @@ class _MultiGaussian(GlmMultiBase):
         return multigaussian(y=self.y, weights=self.weights if weights is None else weights, dtype=self.dtype, opt=self.opt)
 
 
+class _Multinomial(GlmMultiBase):
+    opt = False
+
+    def __init__(self, y, weights, dtype):
+        if y.ndim != 2:
+            raise RuntimeError("y must be 2-dimensional.")
+        if y.shape[1] <= 1:
+            raise RuntimeError("adelie_core: y must have at least 2 columns (classes).")
+        y = np.ascontiguousarray(y)
+        self._init_common("multinomial", y, weights, dtype, K=y.shape[1])
+
+    def reweight(self, weights=None):
+        return multinomial(y=self.y, weights=self.weights if weights is None else weights, dtype=self.dtype)
+
+
 class _Cox(GlmBase):
     def __init__(self, start, stop, status, strata, weights, tie_method, dtype):
         if status.ndim != 1:
@@ -203,6 +218,12 @@ def multigaussian(y: np.ndarray, *, weights: np.ndarray = None, dtype: Union[np.
     """MultiGaussian family (adelie/glm.py:456-538; CORE/glm/glm_multigaussian.ipp:17-68)."""
     y, dtype = _coerce_dtype(np.asarray(y), dtype)
     return _MultiGaussian(y, weights, dtype, opt)
+
+
+def multinomial(y: np.ndarray, *, weights: np.ndarray = None, dtype: Union[np.float32, np.float64] = None):
+    """Multinomial family (adelie/glm.py ``multinomial``; CORE/glm/glm_multinomial.ipp:6-132) -- SURVEY 8f rank 4."""
+    y, dtype = _coerce_dtype(np.asarray(y), dtype)
+    return _Multinomial(y, weights, dtype)
 
 
 def cox(start: np.ndarray, stop: np.ndarray, status: np.ndarray, *, strata: np.ndarray = None, weights: np.ndarray = None,

@@ -114,7 +114,8 @@ int ab_matrix_sp_tmul(ab_matrix* m, int64_t L, const int64_t* indptr, const int6
 
 /* ---- GLM families: adelie/src/py_glm.cpp:101-234, 664-685 ---------------------------------- */
 enum { AB_GLM_GAUSSIAN = 1, AB_GLM_BINOMIAL_LOGIT = 2, AB_GLM_MULTIGAUSSIAN = 3, AB_GLM_COX = 4, AB_GLM_POISSON = 5 /* GlmPoisson, CORE/glm/glm_poisson.ipp:7-66 */,
-       AB_GLM_BINOMIAL_PROBIT = 6 /* GlmBinomialProbit, CORE/glm/glm_binomial.ipp:100-190 */ };
+       AB_GLM_BINOMIAL_PROBIT = 6 /* GlmBinomialProbit, CORE/glm/glm_binomial.ipp:100-190 */,
+       AB_GLM_MULTINOMIAL = 7 /* GlmMultinomial, CORE/glm/glm_multinomial.ipp:6-132; y (n, K) row-major */ };
 /* y: (n,) or (n,K) row-major; weights (n,) summing to 1.  Cox: y = status, plus start/stop/strata, tie 1 = efron, 0 = breslow */
 int ab_glm_create(int dtype, int family, int64_t n, int64_t K, const void* y, const void* weights,
                   const void* cox_start, const void* cox_stop, const int64_t* cox_strata, int cox_tie_efron, ab_glm** out);

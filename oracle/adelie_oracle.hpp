@@ -904,6 +904,62 @@ struct GlmBinomialLogit : GlmBase<T> {                                         /
     void inv_link(const T* eta, T* out) override { for (idx_t i = 0; i < B::n; ++i) out[i] = 1 / (1 + std::exp(-eta[i])); }
 };
 
+// Multinomial (glm_multinomial.ipp:6-132): y, eta (n,K) row-major; softmax with the row maximum subtracted; the hessian is the
+// diagonal majorant 2 K^-1 w p (1 - p) written through the gradient as in the reference (:52-63).
+template <class T>
+struct GlmMultinomial : GlmBase<T> {
+    using B = GlmBase<T>;
+    idx_t K;
+    GlmMultinomial(const T* y, const T* w, idx_t n, idx_t K_) : K(K_) {
+        B::name = "multinomial"; B::y = y; B::w = w; B::n = n; B::is_multi = true;
+        if (K_ <= 1) throw std::runtime_error("adelie_core: y must have at least 2 columns (classes).");
+    }
+    void softmax_row(const T* e, T* p) const {
+        T m = e[0]; for (idx_t k = 1; k < K; ++k) m = std::max(m, e[k]);
+        T sum = 0; for (idx_t k = 0; k < K; ++k) { p[k] = std::exp(e[k] - m); sum += p[k]; }
+        for (idx_t k = 0; k < K; ++k) p[k] /= sum;
+    }
+    void gradient(const T* eta, T* grad) override {
+        std::vector<T> p(K);
+        for (idx_t i = 0; i < B::n; ++i) {
+            softmax_row(eta + i * K, p.data());
+            for (idx_t k = 0; k < K; ++k) grad[i * K + k] = (B::y[i * K + k] - p[k]) * B::w[i] / K;
+        }
+    }
+    void hessian(const T*, const T* grad, T* hess) override {
+        for (idx_t i = 0; i < B::n; ++i)
+            for (idx_t k = 0; k < K; ++k) {
+                const T h = B::y[i * K + k] * B::w[i] / K - grad[i * K + k];
+                hess[i * K + k] = h * 2 * (1 - K * (h / (B::w[i] + T(B::w[i] <= 0))));
+            }
+    }
+    void inv_hessian_gradient(const T*, const T* grad, const T* hess, T* out) override {     // glm_multibase.ipp:25-37
+        for (idx_t i = 0; i < B::n * K; ++i)
+            out[i] = grad[i] / (std::max<T>(hess[i], 0) + T(Configs::hessian_min) * T(hess[i] <= 0));
+    }
+    T loss(const T* eta) override {
+        T s = 0;
+        for (idx_t i = 0; i < B::n; ++i) {
+            const T* e = eta + i * K;
+            T m = e[0]; for (idx_t k = 1; k < K; ++k) m = std::max(m, e[k]);
+            T ye = 0, se = 0;
+            for (idx_t k = 0; k < K; ++k) { ye += B::y[i * K + k] * (e[k] - m); se += std::exp(e[k] - m); }
+            s += B::w[i] * (-ye + std::log(se));
+        }
+        return s / K;
+    }
+    T loss_full() override {
+        T loss = 0;
+        for (idx_t i = 0; i < B::n; ++i) {
+            T sum = 0;
+            for (idx_t k = 0; k < K; ++k) { const T l = std::log(B::y[i * K + k]); if (!(std::isinf(l) || std::isnan(l))) sum += B::y[i * K + k] * l; }
+            loss -= sum * B::w[i] / K;
+        }
+        return loss;
+    }
+    void inv_link(const T* eta, T* out) override { for (idx_t i = 0; i < B::n; ++i) softmax_row(eta + i * K, out + i * K); }
+};
+
 // Binomial, probit link (glm_binomial.ipp:100-190): Phi = 0.5 (1 + erf(eta / sqrt 2)), phi = exp(-eta^2 / 2) / sqrt(2 pi)
 template <class T>
 struct GlmBinomialProbit : GlmBase<T> {

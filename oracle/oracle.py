@@ -129,7 +129,7 @@ def _dt(dtype):
     return 0 if np.dtype(dtype) == np.float32 else 1
 
 
-FAMILIES = {"gaussian_opt": 0, "gaussian": 1, "binomial": 2, "multigaussian": 3, "cox": 4, "poisson": 5, "probit": 6}
+FAMILIES = {"gaussian_opt": 0, "gaussian": 1, "binomial": 2, "multigaussian": 3, "cox": 4, "poisson": 5, "probit": 6, "multinomial": 7}
 
 
 def set_config(name, value):
@@ -379,7 +379,7 @@ def grpnet(X, glm, *, groups=None, alpha=1.0, penalty=None, offsets=None, lmda_p
         Xmul = lambda v, w: (Xd.T @ (v * w)).astype(dtype)
     y = glm["y"]; weights = glm["weights"]
     family = glm["family"]
-    is_multi = family == "multigaussian"
+    is_multi = family in ("multigaussian", "multinomial")
     K = y.shape[1] if is_multi else 1
     is_opt = family in ("gaussian", "multigaussian") and glm.get("opt", True)
     if offsets is None:

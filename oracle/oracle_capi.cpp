@@ -31,6 +31,7 @@ std::unique_ptr<GlmBase<T>> make_glm(int family, idx_t n, idx_t K, const void* y
         case ORC_FAM_BINOMIAL: return std::make_unique<GlmBinomialLogit<T>>((const T*)y, (const T*)w, n);
         case ORC_FAM_MULTIGAUSSIAN: return std::make_unique<GlmMultiGaussian<T>>((const T*)y, (const T*)w, n, K);
         case ORC_FAM_BINOMIAL_PROBIT: return std::make_unique<GlmBinomialProbit<T>>((const T*)y, (const T*)w, n);
+        case ORC_FAM_MULTINOMIAL: return std::make_unique<GlmMultinomial<T>>((const T*)y, (const T*)w, n, K);
         case ORC_FAM_POISSON: return std::make_unique<GlmPoisson<T>>((const T*)y, (const T*)w, n);
         case ORC_FAM_COX: return std::make_unique<GlmCox<T>>((const T*)cs, (const T*)ce, (const T*)cst, strata, (const T*)w, n, efron != 0);
     }

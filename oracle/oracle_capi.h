@@ -12,7 +12,7 @@ enum { ORC_F32 = 0, ORC_F64 = 1 };
 enum { ORC_MAT_DENSE = 0, ORC_MAT_SPARSE = 1 };
 /* families: 0 = gaussian "opt" path (state_gaussian_naive / multigaussian_naive),
  * 1 = gaussian through IRLS, 2 = binomial logit, 3 = multigaussian through IRLS, 4 = cox */
-enum { ORC_FAM_GAUSSIAN_OPT = 0, ORC_FAM_GAUSSIAN = 1, ORC_FAM_BINOMIAL = 2, ORC_FAM_MULTIGAUSSIAN = 3, ORC_FAM_COX = 4, ORC_FAM_POISSON = 5, ORC_FAM_BINOMIAL_PROBIT = 6 };
+enum { ORC_FAM_GAUSSIAN_OPT = 0, ORC_FAM_GAUSSIAN = 1, ORC_FAM_BINOMIAL = 2, ORC_FAM_MULTIGAUSSIAN = 3, ORC_FAM_COX = 4, ORC_FAM_POISSON = 5, ORC_FAM_BINOMIAL_PROBIT = 6, ORC_FAM_MULTINOMIAL = 7 };
 
 typedef struct orc_path_args {
     int32_t dtype;            /* ORC_F32 / ORC_F64: type of every void* array below */

@@ -108,6 +108,15 @@ def main():
             eta = np.random.normal(0, 1, (n, K))
             r = evaluate(ns["GlmTestMultiGaussian"](y=y, weights=w), eta, (n, K))
             out.update({f"multigaussian_{n}_{K}_{k}": v for k, v in dict(y=y, w=w, eta=eta, **r).items()})
+    for n in sizes:                                   # test_multinomial (:790-803): one-hot and Dirichlet responses
+        for K in (2, 3, 4):
+            for binary in (True, False):
+                np.random.seed(0)
+                y = np.random.multinomial(1, np.full(K, 1 / K), n).astype(float) if binary else np.random.dirichlet(np.ones(K), n)
+                w = weights_like_reference(n)
+                eta = np.random.normal(0, 1, (n, K))
+                r = evaluate(ns["GlmTestMultinomial"](y=y, weights=w), eta, (n, K))
+                out.update({f"multinomial_{n}_{K}_{int(binary)}_{k}": v for k, v in dict(y=y, w=w, eta=eta, **r).items()})
     for n in sizes:                                   # test_poisson (:275-290)
         np.random.seed(0)
         y = np.random.poisson(1, n).astype(float); w = weights_like_reference(n)

@@ -97,6 +97,10 @@ def test_glm_families_vs_reference_golden(dtype, rtol, atol, n):
     for K in (1, 2, 3, 4):
         pre = f"multigaussian_{n}_{K}_"
         _glm_check(ad.glm.multigaussian(G[pre + "y"], weights=G[pre + "w"], dtype=dtype), pre, dtype, rtol, atol)
+    for K in (2, 3, 4):
+        for binary in (0, 1):
+            pre = f"multinomial_{n}_{K}_{binary}_"
+            _glm_check(ad.glm.multinomial(G[pre + "y"], weights=G[pre + "w"], dtype=dtype), pre, dtype, rtol * 5, atol * 5)
     for binary in (0, 1):
         pre = f"probit_{n}_{binary}_"
         _glm_check(ad.glm.binomial(G[pre + "y"], weights=G[pre + "w"], link="probit", dtype=dtype), pre, dtype, rtol * 5, atol * 5)
@@ -167,4 +171,24 @@ def test_probit_path_vs_oracle():
     assert st.error == "" and ref.error == "", (st.error, ref.error)
     B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
     assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
+    np.testing.assert_allclose(st.devs, ref.devs, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("K,intercept", [(3, True), (4, False)])
+def test_multinomial_path_vs_oracle(K, intercept):
+    """the multinomial family through the multi-response IRLS driver (solver_multiglm_naive.hpp)."""
+    rng = np.random.default_rng(K)
+    n, p = 600, 20
+    X = np.asfortranarray(rng.normal(size=(n, p)))
+    Bt = np.zeros((p, K)); Bt[:4] = rng.normal(size=(4, K))
+    eta = X @ Bt; P = np.exp(eta - eta.max(1, keepdims=True)); P /= P.sum(1, keepdims=True)
+    Y = np.array([rng.multinomial(1, pp) for pp in P]).astype(np.float64)
+    kw = dict(tol=1e-13, irls_tol=1e-11, early_exit=False, lmda_path_size=8, min_ratio=0.3, intercept=intercept)
+    st = ad.grpnet(X, ad.glm.multinomial(Y), progress_bar=False, **kw)
+    ref = orc.grpnet(X, orc.glm_spec("multinomial", Y), **kw)
+    assert st.error == "" and ref.error == "", (st.error, ref.error)
+    B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
+    assert B.shape == Br.shape == (len(st.lmdas), p * K)
+    assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
+    np.testing.assert_allclose(np.asarray(st.intercepts), np.asarray(ref.intercepts), rtol=1e-6, atol=1e-8)
     np.testing.assert_allclose(st.devs, ref.devs, rtol=1e-6, atol=1e-8)

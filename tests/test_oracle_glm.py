@@ -64,3 +64,11 @@ def test_poisson(n):
 def test_binomial_probit(n, binary):
     pre = f"probit_{n}_{binary}_"
     _check(orc.glm_spec("probit", G[pre + "y"], G[pre + "w"]), pre)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("K", [2, 3, 4])
+@pytest.mark.parametrize("binary", [0, 1])
+def test_multinomial(n, K, binary):
+    pre = f"multinomial_{n}_{K}_{binary}_"
+    _check(orc.glm_spec("multinomial", G[pre + "y"], G[pre + "w"]), pre)
