@@ -60,6 +60,8 @@ SYMBOLS = [
     "ab_io_snp_unphased_get", "ab_io_snp_unphased_to_dense",
     "ab_matrix_snp_unphased_create", "ab_matrix_snp_unphased_from_calldata", "ab_matrix_snp_unphased_alloc_random", "ab_matrix_snp_unphased_download",
     "ab_matrix_snp_unphased_cache_info", "ab_matrix_standardize_create", "ab_matrix_subset_create",
+    "ab_io_snp_phased_ancestry_create", "ab_io_snp_phased_ancestry_free", "ab_io_snp_phased_ancestry_write", "ab_io_snp_phased_ancestry_read",
+    "ab_io_snp_phased_ancestry_info", "ab_io_snp_phased_ancestry_get", "ab_io_snp_phased_ancestry_to_dense", "ab_matrix_snp_phased_ancestry_create",
     "ab_matrix_free", "ab_matrix_rows", "ab_matrix_cols", "ab_matrix_cmul", "ab_matrix_ctmul", "ab_matrix_bmul",
     "ab_matrix_btmul", "ab_matrix_mul", "ab_matrix_cov", "ab_matrix_sq_mul", "ab_matrix_sp_tmul",
     "ab_glm_create", "ab_glm_free", "ab_glm_gradient", "ab_glm_hessian", "ab_glm_inv_hessian_gradient", "ab_glm_loss",
@@ -102,6 +104,14 @@ def load():
     L.ab_matrix_snp_unphased_cache_info.argtypes = [c_vp, C.POINTER(c_i64), C.POINTER(c_i64)]
     L.ab_matrix_standardize_create.argtypes = [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_int, C.POINTER(c_vp)]
     L.ab_matrix_subset_create.argtypes = [c_vp, c_vp, c_i64, C.c_int, C.c_int, C.POINTER(c_vp)]
+    L.ab_io_snp_phased_ancestry_create.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(c_vp)]
+    L.ab_io_snp_phased_ancestry_free.argtypes = [c_vp]
+    L.ab_io_snp_phased_ancestry_write.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, C.c_int, C.POINTER(C.c_uint64)]
+    L.ab_io_snp_phased_ancestry_read.argtypes = [c_vp, C.POINTER(C.c_uint64)]
+    L.ab_io_snp_phased_ancestry_info.argtypes = [c_vp, C.POINTER(C.c_int), C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]
+    L.ab_io_snp_phased_ancestry_get.argtypes = [c_vp, C.c_char_p, c_vp]
+    L.ab_io_snp_phased_ancestry_to_dense.argtypes = [c_vp, C.c_int, c_vp]
+    L.ab_matrix_snp_phased_ancestry_create.argtypes = [C.c_int, c_vp, c_i64, c_i64, C.c_int, C.POINTER(c_vp)]
     L.ab_matrix_rows.argtypes = [c_vp, C.POINTER(c_i64)]
     L.ab_matrix_cols.argtypes = [c_vp, C.POINTER(c_i64)]
     L.ab_matrix_cmul.argtypes = [c_vp, c_i64, c_vp, c_vp, C.POINTER(C.c_double)]

@@ -20,6 +20,7 @@ static thread_local std::string g_last_error;
 struct ab_matrix { int dtype; DenseMatrix<float>* f32 = nullptr; DenseMatrix<double>* f64 = nullptr; };
 struct ab_glm { int dtype; int family; Glm<float>* f32 = nullptr; Glm<double>* f64 = nullptr; };
 struct ab_io_snp { SnpUnphasedIO io; ab_io_snp(const char* f, const char* m) : io(f, m) {} };
+struct ab_io_snp_pa { SnpPhasedAncestryIO io; ab_io_snp_pa(const char* f, const char* m) : io(f, m) {} };
 struct ab_state { int dtype; PathState<float>* f32 = nullptr; PathState<double>* f64 = nullptr; std::string error; double total_time = 0; };
 
 #define AB_TRY try {
@@ -390,6 +391,92 @@ int ab_matrix_snp_unphased_cache_info(const ab_matrix* m, int64_t* cached_cols, 
     if (m->dtype == AB_F32) { *cached_cols = m->f32->cache_used; *packed_bytes = (int64_t)(m->f32->snp_packed.n * 4); }
     else { *cached_cols = m->f64->cache_used; *packed_bytes = (int64_t)(m->f64->snp_packed.n * 4); }
     return AB_OK;
+}
+// ------------------------------------------------------------------------------------------ SNP phased ancestry: IO + matrix
+// reference: adelie.io.snp_phased_ancestry (PY/io.py:6-111) -> IOSNPPhasedAncestry (CORE/io/io_snp_phased_ancestry.{hpp,ipp});
+//            adelie.matrix.snp_phased_ancestry -> MatrixNaiveSNPPhasedAncestry{32,64} (CORE/matrix/matrix_naive_snp_phased_ancestry.ipp)
+int ab_io_snp_phased_ancestry_create(const char* filename, const char* read_mode, ab_io_snp_pa** out) {
+    AB_TRY
+    *out = new ab_io_snp_pa(filename, read_mode);
+    AB_CATCH
+}
+int ab_io_snp_phased_ancestry_free(ab_io_snp_pa* io) { delete io; return AB_OK; }
+int ab_io_snp_phased_ancestry_write(ab_io_snp_pa* io, const int8_t* calldata, const int8_t* ancestries, int64_t n, int64_t two_s, int64_t A,
+                                    int n_threads, uint64_t* total_bytes) {
+    AB_TRY
+    (void)n_threads;
+    if (A < 0) throw core_error("Number of ancestries A must be >= 0.");
+    *total_bytes = io->io.write(calldata, ancestries, (uint64_t)n, (uint64_t)two_s, (uint64_t)A);
+    AB_CATCH
+}
+int ab_io_snp_phased_ancestry_read(ab_io_snp_pa* io, uint64_t* total_bytes) {
+    AB_TRY
+    *total_bytes = io->io.read();
+    AB_CATCH
+}
+int ab_io_snp_phased_ancestry_info(const ab_io_snp_pa* io, int* is_read, int64_t* rows, int64_t* snps, int64_t* ancestries) {
+    *is_read = io->io.is_read ? 1 : 0; *rows = (int64_t)io->io.rows; *snps = (int64_t)io->io.snps; *ancestries = (int64_t)io->io.ancestries;
+    return AB_OK;
+}
+int ab_io_snp_phased_ancestry_get(const ab_io_snp_pa* io, const char* name, void* out) {
+    AB_TRY
+    io->io.need_read();
+    const std::string s(name);
+    const auto& I = io->io;
+    if (s == "nnz0") std::memcpy(out, I.nnz0.data(), 8 * I.cols);
+    else if (s == "nnz1") std::memcpy(out, I.nnz1.data(), 8 * I.cols);
+    else if (s == "outer") std::memcpy(out, I.outer.data(), 8 * (I.snps + 1));
+    else throw core_error("unknown field " + s);
+    AB_CATCH
+}
+int ab_io_snp_phased_ancestry_to_dense(const ab_io_snp_pa* io, int n_threads, int8_t* out) {
+    AB_TRY
+    (void)n_threads;
+    io->io.to_dense(out);
+    AB_CATCH
+}
+} // extern "C"
+template <class T>
+static DenseMatrix<T>* snp_pa_from_io(const SnpPhasedAncestryIO& I, int64_t row_lo, int64_t row_hi, int n_threads) {
+    I.need_read();
+    if (I.rows < 1 || I.cols < 1) throw core_error("matrix must have at least one row and one column.");
+    if (row_hi < 0) row_hi = (int64_t)I.rows;
+    if (row_lo < 0 || row_lo >= row_hi || row_hi > (int64_t)I.rows) throw core_error("snp_phased_ancestry: invalid row range.");
+    const int64_t s_ = (int64_t)I.snps; const int A = (int)I.ancestries;
+    auto M = std::unique_ptr<DenseMatrix<T>>(new DenseMatrix<T>(row_hi - row_lo, s_ * A, typename DenseMatrix<T>::SnpTag{}));   // impute stays 0: code 3 never occurs
+    M->n_threads = n_threads;
+    DevBuf<uint64_t> d_outer(s_ + 1); d_outer.upload(I.outer.data(), s_ + 1);
+    DevBuf<int> d_err(1);
+    const uint64_t kMaxBytes = 1ull << 30;
+    DevBuf<uint8_t> d_file;
+    for (int64_t j0 = 0; j0 < s_;) {
+        int64_t j1 = j0 + 1;
+        while (j1 < s_ && I.outer[j1 + 1] - I.outer[j0] <= kMaxBytes) ++j1;
+        const uint64_t bytes = I.outer[j1] - I.outer[j0];
+        if (d_file.n < bytes + 16) d_file.alloc(bytes + 16);
+        AB_CUDA(cudaMemcpyAsync(d_file.p, I.buf + I.outer[j0], bytes, cudaMemcpyHostToDevice, 0));
+        const int64_t items = (j1 - j0) * A * 2;
+        snpdat_phased_unpack_kernel<<<(unsigned)((items + 7) / 8), 256>>>(d_file.p, d_outer.p, j0, j1 - j0, (int64_t)I.outer[j0], A, (int64_t)I.rows, row_lo, row_hi,
+                                                                         M->snp_packed.p, M->snp_ldw, d_err.p);
+        AB_CUDA(cudaGetLastError());
+        AB_CUDA(cudaStreamSynchronize(0));
+        j0 = j1;
+    }
+    int err = 0; d_err.download(&err, 1); AB_CUDA(cudaStreamSynchronize(0));
+    if (err == 2) throw core_error("snp_phased_ancestry: malformed file (a chunk list runs past the end of its SNP).");
+    if (err) throw core_error("snp_phased_ancestry: the file holds a row index outside [0, rows).");
+    return M.release();
+}
+extern "C" {
+int ab_matrix_snp_phased_ancestry_create(int dtype, const ab_io_snp_pa* io, int64_t row_lo, int64_t row_hi, int n_threads, ab_matrix** out) {
+    AB_TRY
+    if (n_threads < 1) throw core_error("n_threads must be >= 1.");
+    auto* m = new ab_matrix{dtype};
+    try {
+        if (dtype == AB_F32) m->f32 = snp_pa_from_io<float>(io->io, row_lo, row_hi, n_threads); else m->f64 = snp_pa_from_io<double>(io->io, row_lo, row_hi, n_threads);
+    } catch (...) { delete m; throw; }
+    *out = m;
+    AB_CATCH
 }
 // ------------------------------------------------------------------------------------------ standardize / subset
 // reference: adelie.matrix.standardize (PY/matrix.py:1414-1536; MatrixNaiveStandardize, matrix_naive_standardize.ipp:8-293) and

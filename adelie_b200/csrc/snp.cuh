@@ -199,6 +199,159 @@ struct SnpUnphasedIO {
     }
 };
 
+// -------------------------------------------------------------------------------------------- phased, ancestry-labelled genotypes
+// `IOSNPPhasedAncestry` (CORE/io/io_snp_phased_ancestry.hpp, .ipp:9-363).  X is (n, s*A): column j*A + a counts, over the two
+// haplotypes of SNP j, those that carry the mutation AND are labelled with ancestry a -- entries 0 / 1 / 2, no missing values.
+// `.snpdat` layout (ipp:170-186, 268-342), little endian:
+//   [endian:1B][n:u64][s:u64][A:u8][nnz0:u64 x s*A][nnz1:u64 x s*A][outer:u64 x (s+1)]
+//   SNP j at byte outer[j]: [A x u64 offsets of the ancestry blocks, relative to the SNP start]
+//     ancestry block: [2 x u64 offsets of the haplotypes, relative to the block start]
+//       haplotype: [n_chunks:u32] { [chunk_idx:u32][nnz-1:u8][row_in_chunk:u8 x nnz] }, chunk = 256 rows
+// On the device the matrix is the SAME 2-bit packed storage as snp_unphased (codes 0 / 1 / 2, code 3 never occurs), so every
+// kernel and the whole solver path are shared; only the unpack kernel differs (it ADDS one per haplotype hit).
+struct SnpPhasedAncestryIO {
+    static constexpr uint64_t kChunk = 256;
+    std::string filename; int read_mode = 0; bool is_read = false;
+    std::vector<char> owned; const char* buf = nullptr; size_t buf_bytes = 0; void* map_addr = nullptr; size_t map_bytes = 0;
+    uint64_t rows = 0, snps = 0, ancestries = 0, cols = 0;
+    std::vector<uint64_t> nnz0, nnz1, outer;
+
+    SnpPhasedAncestryIO(const std::string& f, const std::string& mode) : filename(f) {
+        if (mode == "file") read_mode = 0;
+        else if (mode == "mmap" || mode == "auto") read_mode = 1;
+        else throw core_error("Invalid read mode type: " + mode);
+    }
+    ~SnpPhasedAncestryIO() { release(); }
+    SnpPhasedAncestryIO(const SnpPhasedAncestryIO&) = delete;
+    SnpPhasedAncestryIO& operator=(const SnpPhasedAncestryIO&) = delete;
+    void release() { if (map_addr) { munmap(map_addr, map_bytes); map_addr = nullptr; } owned.clear(); owned.shrink_to_fit(); buf = nullptr; buf_bytes = 0; }
+    void need_read() const { if (!is_read) throw core_error("File is not read yet. Call read() first."); }
+    template <class U> static U rd(const char* q) { U u; std::memcpy(&u, q, sizeof(U)); return u; }
+
+    size_t read() {                                                   // io_snp_base.ipp:20-84 + io_snp_phased_ancestry.ipp:9-43
+        release();
+        is_read = true;
+        FILE* fp = std::fopen(filename.c_str(), "rb");
+        if (!fp) throw core_error("Cannot open file " + filename);
+        std::fseek(fp, 0, SEEK_END);
+        const size_t total = (size_t)std::ftell(fp);
+        std::fseek(fp, 0, SEEK_SET);
+        if (read_mode == 1) {
+            std::fclose(fp);
+            const int fd = open(filename.c_str(), O_RDONLY);
+            if (fd == -1) throw core_error("open failed.");
+            void* addr = mmap(nullptr, total, PROT_READ, MAP_PRIVATE | MAP_NORESERVE | MAP_POPULATE, fd, 0);
+            close(fd);
+            if (addr == MAP_FAILED) throw core_error("mmap failed.");
+            map_addr = addr; map_bytes = total; buf = static_cast<const char*>(addr);
+        } else {
+            owned.resize(total);
+            const size_t got = std::fread(owned.data(), 1, total, fp);
+            std::fclose(fp);
+            if (got != total) throw core_error("Could not read the whole file into buffer.");
+            buf = owned.data();
+        }
+        buf_bytes = total;
+        if (total < 18) throw core_error("File is too short to be a .snpdat file.");
+        if ((buf[0] != 0) != SnpUnphasedIO::big_endian())
+            throw core_error("Endianness is inconsistent! Regenerate the file on a machine with the same endianness.");
+        size_t idx = 1;
+        rows = rd<uint64_t>(buf + idx); idx += 8;
+        snps = rd<uint64_t>(buf + idx); idx += 8;
+        ancestries = (uint64_t)(uint8_t)buf[idx]; idx += 1;
+        cols = snps * ancestries;
+        if (total < idx + cols * 16 + (snps + 1) * 8) throw core_error("File is too short for its header.");
+        nnz0.resize(cols); std::memcpy(nnz0.data(), buf + idx, 8 * cols); idx += 8 * cols;
+        nnz1.resize(cols); std::memcpy(nnz1.data(), buf + idx, 8 * cols); idx += 8 * cols;
+        outer.resize(snps + 1); std::memcpy(outer.data(), buf + idx, 8 * (snps + 1));
+        if (outer[snps] > total) throw core_error("Column offsets point past the end of the file.");
+        return total;
+    }
+    template <class F> void for_each(uint64_t j, uint64_t a, int hap, F f) const {
+        const char* snp = buf + outer[j];
+        const char* blk = snp + rd<uint64_t>(snp + 8 * a);
+        const char* q = blk + rd<uint64_t>(blk + 8 * hap);
+        const uint32_t n_chunks = rd<uint32_t>(q); q += 4;
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            const uint64_t base = (uint64_t)rd<uint32_t>(q) * kChunk; q += 4;
+            const unsigned cnt = (unsigned)(uint8_t)*q + 1u; q += 1;
+            for (unsigned e = 0; e < cnt; ++e) f(base + (uint8_t)q[e]);
+            q += cnt;
+        }
+    }
+    void to_dense(int8_t* out) const {                                // ipp:45-71: (n, s*A) row-major
+        need_read();
+        std::memset(out, 0, (size_t)rows * cols);
+        for (uint64_t j = 0; j < snps; ++j)
+            for (uint64_t a = 0; a < ancestries; ++a)
+                for (int hap = 0; hap < 2; ++hap) for_each(j, a, hap, [&](uint64_t i) { out[i * cols + j * ancestries + a] += 1; });
+    }
+    // ipp:73-363.  calldata, anc: column-major (n, 2 s) int8; calldata in {0, 1}, anc in [0, A)
+    size_t write(const int8_t* calldata, const int8_t* anc, uint64_t n, uint64_t two_s, uint64_t A) const {
+        if (two_s % 2) throw core_error("calldata and ancestries must have shape (n, 2*s).");
+        if (A >= kChunk) throw core_error("Number of ancestries A must be < 256.");
+        const uint64_t s_ = two_s / 2, max_chunks = (n + kChunk - 1) / kChunk;
+        if (max_chunks >= (1ull << 32)) throw core_error("calldata dimensions are too large! ");
+        for (uint64_t k = 0; k < two_s * n; ++k) {
+            if (anc[k] < 0 || (uint64_t)anc[k] >= A) throw core_error("Detected an ancestry not in the range [0, A). Make sure ancestries only contains values in [0, A). ");
+            if (calldata[k] != 0 && calldata[k] != 1) throw core_error("Detected a non-binary value. Make sure calldata only contains 0 or 1 values. ");
+        }
+        // one haplotype list: [n_chunks] + per non-empty chunk [idx][cnt-1][rows]
+        auto emit = [&](const int8_t* cal, const int8_t* an, int8_t a, std::vector<char>& dst) -> uint64_t {
+            const size_t at = dst.size(); dst.resize(at + 4);
+            uint32_t n_chunks = 0; uint64_t hits = 0;
+            for (uint64_t k = 0; k < max_chunks; ++k) {
+                const uint64_t k0 = k * kChunk, k1 = std::min(n, k0 + kChunk);
+                size_t hdr = 0; unsigned cnt = 0;
+                for (uint64_t i = k0; i < k1; ++i) {
+                    if (an[i] == a && cal[i] == 1) {
+                        if (!cnt) { hdr = dst.size(); dst.resize(hdr + 5); }
+                        dst.push_back((char)(uint8_t)(i - k0)); ++cnt;
+                    }
+                }
+                if (cnt) { const uint32_t k32 = (uint32_t)k; std::memcpy(&dst[hdr], &k32, 4); dst[hdr + 4] = (char)(uint8_t)(cnt - 1); ++n_chunks; hits += cnt; }
+            }
+            std::memcpy(&dst[at], &n_chunks, 4);
+            return hits;
+        };
+        std::vector<uint64_t> v_nnz0(s_ * A), v_nnz1(s_ * A), v_outer(s_ + 1);
+        std::vector<std::vector<char>> snp_bytes(s_);
+        for (uint64_t j = 0; j < s_; ++j) {
+            std::vector<char>& sb = snp_bytes[j];
+            sb.assign(8 * A, 0);
+            for (uint64_t a = 0; a < A; ++a) {
+                const uint64_t blk = sb.size();
+                std::memcpy(&sb[8 * a], &blk, 8);
+                sb.resize(blk + 16);
+                for (int hap = 0; hap < 2; ++hap) {
+                    const uint64_t rel = sb.size() - blk;
+                    std::memcpy(&sb[blk + 8 * hap], &rel, 8);
+                    const uint64_t hits = emit(calldata + (2 * j + hap) * n, anc + (2 * j + hap) * n, (int8_t)a, sb);
+                    (hap == 0 ? v_nnz0 : v_nnz1)[j * A + a] = hits;
+                }
+            }
+        }
+        const size_t preamble = 1 + 16 + 1 + 16 * s_ * A + 8 * (s_ + 1);
+        v_outer[0] = preamble;
+        for (uint64_t j = 0; j < s_; ++j) v_outer[j + 1] = v_outer[j] + snp_bytes[j].size();
+        std::vector<char> out(preamble);
+        size_t idx = 0;
+        out[idx++] = (char)SnpUnphasedIO::big_endian();
+        std::memcpy(&out[idx], &n, 8); idx += 8;
+        std::memcpy(&out[idx], &s_, 8); idx += 8;
+        out[idx++] = (char)(uint8_t)A;
+        if (s_ * A) { std::memcpy(&out[idx], v_nnz0.data(), 8 * s_ * A); idx += 8 * s_ * A; std::memcpy(&out[idx], v_nnz1.data(), 8 * s_ * A); idx += 8 * s_ * A; }
+        std::memcpy(&out[idx], v_outer.data(), 8 * (s_ + 1));
+        FILE* fp = std::fopen(filename.c_str(), "wb");
+        if (!fp) throw core_error("Cannot open file " + filename);
+        size_t wrote = std::fwrite(out.data(), 1, out.size(), fp);
+        for (uint64_t j = 0; j < s_; ++j) wrote += std::fwrite(snp_bytes[j].data(), 1, snp_bytes[j].size(), fp);
+        std::fclose(fp);
+        if (wrote != v_outer[s_]) throw core_error("Could not write the full buffer.");
+        return wrote;
+    }
+};
+
 // ============================================================================================ device kernels
 __device__ __forceinline__ uint64_t snp_rd_u64(const uint8_t* q) { uint64_t u = 0; for (int b = 7; b >= 0; --b) u = (u << 8) | q[b]; return u; }
 __device__ __forceinline__ uint32_t snp_rd_u32(const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); }
@@ -233,6 +386,42 @@ snpdat_unpack_kernel(const uint8_t* __restrict__ file, const uint64_t* __restric
             if (row < row_lo || row >= row_hi) continue;
             const int64_t r = row - row_lo;
             atomicOr(dst + (r >> 4), code << (2 * (int)(r & 15)));
+        }
+        q += 5 + cnt;
+    }
+}
+
+// Phased-ancestry chunk lists -> 2-bit counts.  One warp per (SNP, ancestry, haplotype): every hit ADDS one to the 2-bit field of
+// column SNP * A + ancestry (two haplotypes: at most 2, no carry into the neighbouring field).
+__global__ void __launch_bounds__(256)
+snpdat_phased_unpack_kernel(const uint8_t* __restrict__ file, const uint64_t* __restrict__ outer, int64_t j0, int64_t nsnps, int64_t col_base, int A,
+                            int64_t n_total, int64_t row_lo, int64_t row_hi, uint32_t* __restrict__ packed, int64_t ldw, int* __restrict__ err)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= nsnps * A * 2) return;
+    const int64_t jl = item / (2 * A); const int a = (int)((item - jl * 2 * A) >> 1), hap = (int)(item & 1);
+    const uint8_t* snp = file + (outer[j0 + jl] - (uint64_t)col_base);
+    const uint8_t* snp_end = file + (outer[j0 + jl + 1] - (uint64_t)col_base);
+    if (snp + 8 * A > snp_end) { *err = 2; return; }
+    const uint64_t boff = snp_rd_u64(snp + 8 * a);
+    if (boff > (uint64_t)(snp_end - snp) || snp + boff + 16 > snp_end) { *err = 2; return; }
+    const uint8_t* blk = snp + boff;
+    const uint64_t hoff = snp_rd_u64(blk + 8 * hap);
+    if (hoff > (uint64_t)(snp_end - blk) || blk + hoff + 4 > snp_end) { *err = 2; return; }
+    const uint8_t* q = blk + hoff;
+    const uint32_t n_chunks = snp_rd_u32(q); q += 4;
+    uint32_t* dst = packed + ((j0 + jl) * A + a) * ldw;
+    for (uint32_t k = 0; k < n_chunks; ++k) {
+        if (q + 5 > snp_end || q + 5 + q[4] + 1 > snp_end) { *err = 2; return; }
+        const int64_t base = (int64_t)snp_rd_u32(q) * 256;
+        const int cnt = (int)q[4] + 1;
+        for (int e = lane; e < cnt; e += 32) {
+            const int64_t row = base + q[5 + e];
+            if (row >= n_total) { *err = 1; continue; }
+            if (row < row_lo || row >= row_hi) continue;
+            const int64_t r = row - row_lo;
+            atomicAdd(dst + (r >> 4), 1u << (2 * (int)(r & 15)));
         }
         q += 5 + cnt;
     }

@@ -95,3 +95,40 @@ def snp_unphased(n, p, *, K=1, glm="gaussian", sparsity=0.95, missing_ratio=0.1,
     glm_obj = _sample_y(glm=glm, eta=eta, beta=beta_sub, snr=snr)
     X.ravel()[np.random.choice(n * p, int(missing_ratio * n * p), replace=False)] = -9
     return {"X": np.asfortranarray(X), "glm": glm_obj, "groups": groups, "group_sizes": group_sizes, "penalty": penalty}
+
+
+def snp_phased_ancestry(n, s, A, *, K=1, glm="gaussian", sparsity=0.95, one_ratio=0.25, two_ratio=0.05, zero_penalty=0, snr=1, seed=0):
+    """SNP phased, ancestry dataset (semantics of adelie/data.py ``snp_phased_ancestry``): int8 ``X`` (n, 2 s) with mutation indicators
+    such that a fraction ``one_ratio`` / ``two_ratio`` of the (individual, SNP) pairs carries 1 / 2 mutations, uniform random ancestry labels
+    ``ancestries`` (n, 2 s) in [0, A), groups = one group of A ancestry columns per SNP, response drawn from the dense (n, s A) matrix."""
+    assert n >= 1 and s >= 1 and A >= 1 and snr > 0 and seed >= 0
+    np.random.seed(seed)
+    nz_ratio = one_ratio + two_ratio
+    n_nz = int(nz_ratio * n * s)
+    where = np.random.permutation(np.random.choice(n * s, n_nz, replace=False))
+    n_ones = int(one_ratio / nz_ratio * n_nz)
+    X = np.zeros((n, s), dtype=np.int8)
+    X.ravel()[where[:n_ones]] = 1
+    X.ravel()[where[n_ones:]] = 2
+    caldata = np.zeros((n, 2 * s), dtype=np.int8)
+    caldata[:, ::2] = X >= 1
+    caldata[:, 1::2] = X >= 2
+    ancestries = np.zeros((n, 2 * s), dtype=np.int8)
+    ancestries[:, ::2] = np.random.choice(A, (n, s), replace=True)
+    ancestries[:, 1::2] = np.random.choice(A, (n, s), replace=True)
+    groups = A * np.arange(s)
+    group_sizes = np.full(s, A)
+    penalty = np.sqrt(group_sizes.astype(float))
+    penalty[np.random.choice(s, int(zero_penalty * s), replace=False)] = 0
+    penalty /= np.linalg.norm(penalty) / np.sqrt(s * A)
+    dense = np.zeros((n, s * A), dtype=np.int8)
+    for k in range(2):
+        rows_i, snp_j = np.nonzero(caldata[:, k::2])
+        np.add.at(dense, (rows_i, snp_j * A + ancestries[:, k::2][rows_i, snp_j]), 1)
+    beta = np.random.normal(0, 1, (s * A, K))
+    support = np.random.choice(s * A, int((1 - sparsity) * s * A), replace=False)
+    beta_sub = beta[support]
+    eta = dense[:, support].astype(float) @ beta_sub
+    glm_obj = _sample_y(glm=glm, eta=eta, beta=beta_sub, snr=snr)
+    return {"X": np.asfortranarray(caldata), "ancestries": np.asfortranarray(ancestries), "glm": glm_obj, "groups": groups,
+            "group_sizes": group_sizes, "penalty": penalty, "dense": dense}

@@ -115,3 +115,84 @@ class snp_unphased:
         out = np.empty((n, p), dtype=np.int8)
         _lib.check(_lib.load().ab_io_snp_unphased_to_dense(self._handle, int(n_threads), _lib.ptr(out)))
         return out
+
+
+class snp_phased_ancestry:
+    """IO handler for a SNP phased, ancestry matrix in ``.snpdat`` format (adelie/io.py:6-111; IOSNPPhasedAncestry,
+    adelie_core/io/io_snp_phased_ancestry.{hpp,ipp}).  ``calldata[i, 2 j + k]`` in {0, 1} is the mutation indicator of individual i, SNP j,
+    haplotype k and ``ancestries[i, 2 j + k]`` in [0, A) its ancestry label; the matrix is (n, s A) with entry (i, j A + a) = number
+    of haplotypes of SNP j that carry the mutation and are labelled a."""
+    def __init__(self, filename: str, read_mode: str = "file"):
+        self._filename = str(filename)
+        h = C.c_void_p()
+        _lib.check(_lib.load().ab_io_snp_phased_ancestry_create(self._filename.encode(), str(read_mode).encode(), C.byref(h)))
+        self._handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None:
+                _lib.load().ab_io_snp_phased_ancestry_free(self._handle)
+        except Exception:
+            pass
+
+    def write(self, calldata: np.ndarray, ancestries: np.ndarray, A: int, n_threads: int = 1):
+        """Serialises dense (n, 2 s) int8 calldata / ancestries; returns ``(total_bytes, benchmark)``."""
+        for nm, a in (("calldata", calldata), ("ancestries", ancestries)):
+            if not isinstance(a, np.ndarray) or a.ndim != 2 or a.dtype != np.int8:
+                raise TypeError(f"{nm} must be a 2-dimensional int8 numpy array.")
+        if calldata.shape != ancestries.shape:
+            raise RuntimeError("adelie_core: calldata and ancestries must have shape (n, 2*s).")
+        cd = np.asfortranarray(calldata); an = np.asfortranarray(ancestries)
+        total = C.c_uint64()
+        _lib.check(_lib.load().ab_io_snp_phased_ancestry_write(self._handle, _lib.ptr(cd), _lib.ptr(an), cd.shape[0], cd.shape[1], int(A),
+                                                               int(n_threads), C.byref(total)))
+        return int(total.value), {}
+
+    def read(self) -> int:
+        total = C.c_uint64()
+        _lib.check(_lib.load().ab_io_snp_phased_ancestry_read(self._handle, C.byref(total)))
+        return int(total.value)
+
+    def _info(self):
+        r, n, s, a = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().ab_io_snp_phased_ancestry_info(self._handle, C.byref(r), C.byref(n), C.byref(s), C.byref(a)))
+        return bool(r.value), int(n.value), int(s.value), int(a.value)
+
+    def _need_read(self):
+        if not self._info()[0]:
+            raise RuntimeError("adelie_core: File is not read yet. Call read() first.")
+
+    def _get(self, name, size):
+        self._need_read()
+        out = np.empty(size, dtype=np.uint64)
+        _lib.check(_lib.load().ab_io_snp_phased_ancestry_get(self._handle, name.encode(), _lib.ptr(out)))
+        return out
+
+    is_read = property(lambda self: self._info()[0])
+
+    @property
+    def rows(self):
+        self._need_read(); return self._info()[1]
+
+    @property
+    def snps(self):
+        self._need_read(); return self._info()[2]
+
+    @property
+    def ancestries(self):
+        self._need_read(); return self._info()[3]
+
+    @property
+    def cols(self):
+        return self.snps * self.ancestries
+
+    nnz0 = property(lambda self: self._get("nnz0", self.cols))
+    nnz1 = property(lambda self: self._get("nnz1", self.cols))
+    outer = property(lambda self: self._get("outer", self.snps + 1))
+
+    def to_dense(self, n_threads: int = 1):
+        """(n, s A) int8 array of the matrix entries (0, 1 or 2)."""
+        self._need_read()
+        out = np.empty((self.rows, self.cols), dtype=np.int8)
+        _lib.check(_lib.load().ab_io_snp_phased_ancestry_to_dense(self._handle, int(n_threads), _lib.ptr(out)))
+        return out

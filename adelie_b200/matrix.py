@@ -340,6 +340,23 @@ def snp_unphased(io, *, n_threads: int = 1, dtype=np.float64, rows=None):
     return m
 
 
+def snp_phased_ancestry(io, *, n_threads: int = 1, dtype=np.float64, rows=None):
+    """SNP phased, ancestry matrix from an ``adelie_b200.io.snp_phased_ancestry`` handler (adelie/matrix.py ``snp_phased_ancestry``;
+    MatrixNaiveSNPPhasedAncestry).  On the device it is the same 2-bit storage as ``snp_unphased`` (entries 0 / 1 / 2), so every kernel
+    and the solver path are shared; ``rows=(lo, hi)`` keeps a row window of the file (row-sharded runs)."""
+    if n_threads < 1:
+        raise RuntimeError("adelie_core: n_threads must be >= 1.")
+    if not io.is_read:
+        io.read()
+    lo, hi = (0, io.rows) if rows is None else (int(rows[0]), int(rows[1]))
+
+    def maker(h):
+        _lib.check(_lib.load().ab_matrix_snp_phased_ancestry_create(_lib.dtype_code(dtype), io._handle, lo, hi, int(n_threads), C.byref(h)))
+    m = _SnpUnphased(dtype, hi - lo, io.cols, n_threads, maker, io=io)
+    m._core()
+    return m
+
+
 def snp_unphased_from_calldata(calldata: np.ndarray, impute: np.ndarray, *, n_threads: int = 1, dtype=np.float64):
     """Same matrix from an in-memory (n, p) int8 calldata array (negative = missing) and the (p,) imputed values, without a file."""
     cd = np.asfortranarray(calldata, dtype=np.int8); imp = np.ascontiguousarray(impute, dtype=np.float64)

@@ -22,6 +22,7 @@ typedef struct ab_matrix ab_matrix;   /* adelie_core.matrix.MatrixNaive* handle 
 typedef struct ab_glm ab_glm;         /* adelie_core.glm.Glm* handle */
 typedef struct ab_state ab_state;     /* adelie_core.state.State*Naive handle */
 typedef struct ab_io_snp ab_io_snp;   /* adelie_core.io.IOSNPUnphased handle */
+typedef struct ab_io_snp_pa ab_io_snp_pa; /* adelie_core.io.IOSNPPhasedAncestry handle */
 
 enum { AB_F32 = 0, AB_F64 = 1 };
 enum { AB_OK = 0, AB_ERR_CORE = 1 /* adelie_core_error -> RuntimeError */, AB_ERR_CUDA = 2, AB_ERR_ARG = 3 };
@@ -93,6 +94,19 @@ int ab_matrix_snp_unphased_alloc_random(int dtype, int64_t n, int64_t p, uint64_
                                         double one_ratio, double two_ratio, double missing_ratio, ab_matrix** out);
 int ab_matrix_snp_unphased_download(ab_matrix* m, int8_t* calldata_out, double* impute_out);   /* column-major (n, p) int8, -9 = missing */
 int ab_matrix_snp_unphased_cache_info(const ab_matrix* m, int64_t* cached_cols, int64_t* packed_bytes);
+/* adelie.io.snp_phased_ancestry (PY/io.py:6-111; IOSNPPhasedAncestry: CORE/io/io_snp_phased_ancestry.hpp, .ipp:9-363) and adelie.matrix.snp_phased_ancestry
+   (MatrixNaiveSNPPhasedAncestry{32,64}, CORE/matrix/matrix_naive_snp_phased_ancestry.ipp): calldata / ancestries are column-major (n, 2 s) int8 (calldata in
+   {0,1}, ancestries in [0, A)); the matrix is (n, s*A) with entries 0 / 1 / 2 and shares the 2-bit device storage and every kernel of snp_unphased.
+   get(): name in {"nnz0","nnz1","outer"} -> uint64; to_dense(): (n, s*A) row-major int8. */
+int ab_io_snp_phased_ancestry_create(const char* filename, const char* read_mode, ab_io_snp_pa** out);
+int ab_io_snp_phased_ancestry_free(ab_io_snp_pa* io);
+int ab_io_snp_phased_ancestry_write(ab_io_snp_pa* io, const int8_t* calldata, const int8_t* ancestries, int64_t n, int64_t two_s, int64_t A,
+                                    int n_threads, uint64_t* total_bytes);
+int ab_io_snp_phased_ancestry_read(ab_io_snp_pa* io, uint64_t* total_bytes);
+int ab_io_snp_phased_ancestry_info(const ab_io_snp_pa* io, int* is_read, int64_t* rows, int64_t* snps, int64_t* ancestries);
+int ab_io_snp_phased_ancestry_get(const ab_io_snp_pa* io, const char* name, void* out);
+int ab_io_snp_phased_ancestry_to_dense(const ab_io_snp_pa* io, int n_threads, int8_t* out);
+int ab_matrix_snp_phased_ancestry_create(int dtype, const ab_io_snp_pa* io, int64_t row_lo, int64_t row_hi, int n_threads, ab_matrix** out);
 /* adelie.matrix.standardize (PY/matrix.py:1414-1536; MatrixNaiveStandardize{32,64}, CORE/matrix/matrix_naive_standardize.ipp:8-293): X = (Z - 1 c^T) diag(s)^-1,
    and adelie.matrix.subset (PY/matrix.py:1539-1632; MatrixNaiveCSubset / MatrixNaiveRSubset, CORE/matrix/matrix_naive_subset.ipp): axis 0 = rows, 1 = columns.
    Both materialise a new dense device matrix from a dense base matrix (centers / scales: host arrays of the matrix dtype). */

@@ -149,3 +149,51 @@ class SnpMatrix:
             for i2 in range(i1 + 1):
                 out[i1, i2] = self._dot(j + i1, w, lambda x: x * x) if i1 == i2 else self._dot(j + i2, w * col1)
                 out[i2, i1] = out[i1, i2]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SNP phased, ancestry (IOSNPPhasedAncestry, adelie_core/io/io_snp_phased_ancestry.ipp:9-363)
+def phased_dense(calldata, ancestries, A):
+    """The (n, s A) matrix the format stands for: entry (i, j A + a) = #{k in {0, 1}: calldata[i, 2j+k] == 1 and ancestries[i, 2j+k] == a}
+    (to_dense, ipp:45-71)."""
+    cd = np.asarray(calldata); an = np.asarray(ancestries)
+    n, two_s = cd.shape
+    out = np.zeros((n, (two_s // 2) * A), dtype=np.int8)
+    for k in range(2):
+        ii, jj = np.nonzero(cd[:, k::2])
+        np.add.at(out, (ii, jj * A + an[:, k::2][ii, jj]), 1)
+    return out
+
+
+def _chunk_list(rows):
+    body = bytearray()
+    uniq, starts = np.unique(rows // CHUNK, return_index=True)
+    ends = list(starts[1:]) + [rows.size]
+    for k, s_, e in zip(uniq, starts, ends):
+        body += struct.pack("<IB", int(k), e - s_ - 1) + bytes((rows[s_:e] - k * CHUNK).astype(np.uint8))
+    return struct.pack("<I", len(uniq)) + bytes(body)
+
+
+def write_snpdat_phased(calldata, ancestries, A):
+    """File bytes for (n, 2 s) int8 calldata / ancestries (write, ipp:73-363)."""
+    cd = np.asarray(calldata); an = np.asarray(ancestries)
+    n, two_s = cd.shape
+    s_ = two_s // 2
+    nnz0 = np.zeros(s_ * A, dtype=np.uint64); nnz1 = np.zeros(s_ * A, dtype=np.uint64)
+    snps = []
+    for j in range(s_):
+        blocks = []
+        for a in range(A):
+            haps = []
+            for k in range(2):
+                rows = np.flatnonzero((cd[:, 2 * j + k] == 1) & (an[:, 2 * j + k] == a))
+                (nnz0 if k == 0 else nnz1)[j * A + a] = rows.size
+                haps.append(_chunk_list(rows))
+            blocks.append(struct.pack("<2Q", 16, 16 + len(haps[0])) + haps[0] + haps[1])
+        offs, pos = [], 8 * A
+        for b in blocks:
+            offs.append(pos); pos += len(b)
+        snps.append(struct.pack("<%dQ" % A, *offs) + b"".join(blocks))
+    preamble = 1 + 16 + 1 + 16 * s_ * A + 8 * (s_ + 1)
+    outer = np.concatenate([[preamble], preamble + np.cumsum([len(x) for x in snps])]).astype(np.uint64)
+    return struct.pack("<?QQB", False, n, s_, A) + nnz0.tobytes() + nnz1.tobytes() + outer.tobytes() + b"".join(snps)

@@ -178,3 +178,37 @@ def test_packed_mul_large_vs_decoded_columns():
     cX.btmul(p - 24, 24, np.ones(24, dtype=np.float32), acc)          # decodes 24 columns into the dense cache
     assert _rel(acc, D[:, 24:].sum(axis=1)) < 1e-6
     assert cX.cache_info()[0] == 24
+
+
+@pytest.mark.parametrize("dtype,atol", [(np.float64, 1e-12), (np.float32, 1e-4)])
+@pytest.mark.parametrize("n,s,A", [(10, 20, 4), (1, 13, 3), (777, 11, 8), (5000, 9, 2)])
+def test_snp_phased_ancestry_operators_and_path(tmp_path, dtype, atol, n, s, A):
+    """the phased-ancestry chunk lists unpacked on the device into the shared 2-bit storage; operators vs NumPy as the
+    reference's test does (T/test_matrix.py test_naive_snp_phased_ancestry), group-lasso path (one group of A columns per SNP) vs the oracle."""
+    data = ad.data.snp_phased_ancestry(n, s, A, seed=1, sparsity=0.6)
+    h = ad.io.snp_phased_ancestry(str(tmp_path / "pa.snpdat"), "mmap")
+    h.write(data["X"], data["ancestries"], A)
+    cX = ad.matrix.snp_phased_ancestry(h, dtype=dtype, n_threads=3)
+    X = data["dense"].astype(dtype)
+    assert cX.shape == (n, s * A)
+    cd, _ = cX.to_host()
+    assert np.array_equal(cd, data["dense"])                     # device unpack (adds per haplotype) is bit exact
+    rng = np.random.default_rng(n + s)
+    v = rng.normal(size=n).astype(dtype); w = rng.uniform(0, 1, size=n).astype(dtype)
+    scale = atol * max(1.0, n / 100)
+    out = np.empty(s * A, dtype=dtype)
+    cX.mul(v, w, out); np.testing.assert_allclose(out, X.T @ (v * w), atol=scale)
+    cX.sq_mul(w, out); np.testing.assert_allclose(out, (X ** 2).T @ w, atol=scale)
+    j, q = A * (s // 2), A
+    o = np.empty(q, dtype=dtype); cX.bmul(j, q, v, w, o); np.testing.assert_allclose(o, X[:, j:j + q].T @ (v * w), atol=scale)
+    vv = rng.normal(size=q).astype(dtype); acc = rng.normal(size=n).astype(dtype); exp = acc + X[:, j:j + q] @ vv
+    cX.btmul(j, q, vv, acc); np.testing.assert_allclose(acc, exp, atol=atol * 10)
+    C = np.empty((q, q), dtype=dtype, order="F"); cX.cov(j, q, np.sqrt(w), C)
+    np.testing.assert_allclose(C, X[:, j:j + q].T @ (w[:, None] * X[:, j:j + q]), atol=scale)
+    if dtype == np.float64 and n >= 100:
+        y = data["glm"].y
+        kw = dict(groups=data["groups"], penalty=data["penalty"], tol=1e-13, early_exit=False, lmda_path_size=10, min_ratio=0.1)
+        st = ad.grpnet(cX, ad.glm.gaussian(y), progress_bar=False, **kw)
+        ref = orc.grpnet(X, orc.glm_spec("gaussian", y), **kw)
+        assert st.error == "" and ref.error == "", (st.error, ref.error)
+        assert _rel(np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())) < 1e-6

@@ -140,3 +140,63 @@ def test_data_generator_proportions():
     assert d["glm"].y.shape == (400,)
     dk = ad.data.snp_unphased(100, 30, K=3, glm="multigaussian", seed=1)
     assert dk["glm"].y.shape == (100, 3)
+
+
+# ---------------------------------------------------------------------------------------------------- phased ancestry
+PA_CD = np.asfortranarray(np.array([[1, 0], [1, 1], [0, 1]], dtype=np.int8))
+PA_AN = np.asfortranarray(np.array([[0, 1], [1, 1], [0, 0]], dtype=np.int8))
+
+
+def _golden_phased():
+    with open(os.path.join(HERE, "golden", "snp_phased_tiny.snpdat.hex")) as f:
+        return bytes.fromhex(f.read().strip())
+
+
+@pytest.mark.parametrize("read_mode", ["file", "mmap"])
+def test_phased_io_matches_hand_derived_golden(tmp_path, read_mode):
+    assert so.write_snpdat_phased(PA_CD, PA_AN, 2) == _golden_phased()
+    assert np.array_equal(so.phased_dense(PA_CD, PA_AN, 2), [[1, 0], [0, 2], [1, 0]])
+    fn = str(tmp_path / "pa.snpdat")
+    h = ad.io.snp_phased_ancestry(fn, read_mode=read_mode)
+    w, _ = h.write(PA_CD, PA_AN, 2)
+    with open(fn, "rb") as f:
+        assert f.read() == _golden_phased()
+    assert h.read() == w == 154
+    assert (h.rows, h.snps, h.ancestries, h.cols) == (3, 1, 2, 2)
+    assert list(h.nnz0) == [1, 1] and list(h.nnz1) == [1, 1] and list(h.outer) == [66, 154]
+    assert np.array_equal(h.to_dense(), [[1, 0], [0, 2], [1, 0]])
+
+
+@pytest.mark.parametrize("n,s,A", [(1, 1, 1), (200, 32, 4), (1421, 97, 8), (513, 3, 7), (256, 5, 2)])
+def test_phased_io_reference_expectations(tmp_path, n, s, A):
+    """T/test_io.py:63-110 for the product's handler + byte-for-byte agreement with the oracle's independent writer."""
+    data = ad.data.snp_phased_ancestry(n, s, A, seed=0)
+    cd, an = data["X"], data["ancestries"]
+    fn = str(tmp_path / "x.snpdat")
+    h = ad.io.snp_phased_ancestry(fn)
+    w, _ = h.write(cd, an, A, n_threads=2)
+    r = h.read()
+    assert w == r and (h.rows, h.snps, h.ancestries, h.cols) == (n, s, A, s * A)
+    dense = so.phased_dense(cd, an, A)
+    assert np.array_equal(dense, data["dense"])
+    assert np.array_equal(h.to_dense(), dense)
+    with open(fn, "rb") as f:
+        assert f.read() == so.write_snpdat_phased(cd, an, A)
+    for k, nz in ((0, h.nnz0), (1, h.nnz1)):
+        exp = np.array([[np.sum((cd[:, 2 * j + k] == 1) & (an[:, 2 * j + k] == a)) for a in range(A)] for j in range(s)]).ravel()
+        assert np.array_equal(nz, exp)
+
+
+def test_phased_io_errors(tmp_path):
+    h = ad.io.snp_phased_ancestry(str(tmp_path / "e.snpdat"))
+    cd = np.zeros((4, 4), dtype=np.int8); an = np.zeros((4, 4), dtype=np.int8)
+    bad = cd.copy(); bad[1, 1] = 2
+    with pytest.raises(RuntimeError, match="non-binary value"):
+        h.write(bad, an, 2)
+    bad = an.copy(); bad[0, 0] = 2
+    with pytest.raises(RuntimeError, match="ancestry not in the range"):
+        h.write(cd, bad, 2)
+    with pytest.raises(RuntimeError, match="shape \\(n, 2\\*s\\)"):
+        h.write(np.zeros((4, 3), dtype=np.int8), np.zeros((4, 3), dtype=np.int8), 2)
+    with pytest.raises(RuntimeError, match="File is not read yet"):
+        h.rows
