@@ -16,6 +16,7 @@ from . import glm
 from . import io
 from . import matrix
 from . import solver
+from . import sklearn
 from . import state
 from .configs import set_configs
 from .solver import grpnet

@@ -7,6 +7,16 @@ def predict(X, betas, intercepts, offsets=None, n_threads=1):
     a device matrix (then ``sp_tmul`` runs on the device); single-response."""
     from . import matrix as _matrix
     intercepts = np.atleast_1d(np.asarray(intercepts))
+    if intercepts.ndim == 2:
+        # multi-response: coefficient (feature j, class l) sits at column j * K + l of kron(X, I_K); class l uses the columns l::K
+        from scipy.sparse import csr_matrix
+        K = intercepts.shape[1]
+        B = csr_matrix(betas)
+        per_class = [predict(X, B[:, l::K], intercepts[:, l]) for l in range(K)]
+        eta = np.stack(per_class, axis=-1)                    # (L, n, K)
+        if offsets is not None:
+            eta = eta + np.asarray(offsets)[None]
+        return eta
     if isinstance(X, _matrix.MatrixNaiveBase):
         from scipy.sparse import csr_matrix
         B = csr_matrix(betas)

@@ -171,3 +171,30 @@ def test_standardize_snp_unphased_view(dtype, atol):
         assert st.error == "" and ref.error == ""
         B, Br = np.asarray(st.betas.todense()), np.asarray(ref.betas.todense())
         assert np.max(np.abs(B - Br)) <= 1e-6 * np.max(np.abs(Br))
+
+
+def test_sklearn_group_elastic_net():
+    """adelie/sklearn.py GroupElasticNet over grpnet / cv_grpnet on the device."""
+    from adelie_b200.sklearn import GroupElasticNet
+    data = ad.data.dense(500, 20, 5, seed=1)
+    X, y = data["X"], data["glm"].y
+    m = GroupElasticNet().fit(X, y, groups=data["groups"], lmda_path_size=10, min_ratio=0.1, early_exit=False)
+    ref = orc.grpnet(X, orc.glm_spec("gaussian", y), groups=data["groups"], lmda_path_size=10, min_ratio=0.1, early_exit=False)
+    np.testing.assert_allclose(np.asarray(m.coef_.todense()), np.asarray(ref.betas.todense()), rtol=1e-4, atol=1e-6)
+    pred = m.predict(X)
+    np.testing.assert_allclose(pred, np.asarray(ref.betas.todense()) @ X.T + np.asarray(ref.intercepts)[:, None], rtol=1e-4, atol=1e-5)
+    assert 0.0 < m.score(X, y) <= 1.0
+    mc = GroupElasticNet(solver="cv_grpnet").fit(X, y, groups=data["groups"], n_folds=3, seed=0, lmda_path_size=8, min_ratio=0.2)
+    assert mc.coef_.shape == (1, 20) and mc.lambda_.shape == (1,) and mc.predict(X).shape == (500,)
+    db = ad.data.dense(400, 15, 15, glm="binomial", seed=2)
+    mb = GroupElasticNet(family="binomial").fit(db["X"], db["glm"].y, lmda_path_size=6, min_ratio=0.3, early_exit=False)
+    proba = mb.predict_proba(db["X"])
+    assert proba.shape == (6, 400, 2) and np.allclose(proba.sum(axis=-1), 1)
+    assert set(np.unique(mb.predict(db["X"]))) <= {0, 1}
+    rng = np.random.default_rng(0)
+    Y = np.eye(3)[rng.integers(0, 3, 300)]
+    mm = GroupElasticNet(family="multinomial").fit(db["X"][:300], Y, lmda_path_size=4, min_ratio=0.5, early_exit=False)
+    pm = mm.predict_proba(db["X"][:300])
+    assert pm.shape == (4, 300, 3) and np.allclose(pm.sum(axis=-1), 1)
+    with pytest.raises(RuntimeError, match="not been fitted"):
+        GroupElasticNet().predict(X)
