@@ -60,3 +60,40 @@ def objective_gaussian(X, y, weights, beta, intercept, lmda, alpha, groups, grou
         bn = np.linalg.norm(beta[g:g + gs])
         pen += pk * (alpha * bn + 0.5 * (1 - alpha) * bn ** 2)
     return loss + lmda * pen
+
+
+def compute_penalty(groups, group_sizes, penalty, alpha, betas):
+    """``sum_g penalty_g (alpha ||beta_g||_2 + (1 - alpha) / 2 ||beta_g||_2^2)`` for every row of ``betas`` (dense or CSR)
+    (reference: solver.compute_penalty_{dense,sparse}, adelie/src/py_solver.cpp:81-88, adelie_core/solver/utils.hpp)."""
+    B = np.asarray(betas.todense()) if hasattr(betas, "todense") else np.atleast_2d(np.asarray(betas))
+    out = np.zeros(B.shape[0], dtype=B.dtype)
+    for g, gs, pk in zip(groups, group_sizes, penalty):
+        nrm = np.linalg.norm(B[:, g:g + gs], axis=1)
+        out += pk * (alpha * nrm + 0.5 * (1 - alpha) * nrm ** 2)
+    return out
+
+
+def objective(X, glm, betas, intercepts, lmdas, *, groups=None, alpha=1, penalty=None, offsets=None, relative=True, add_penalty=True,
+              n_threads=1):
+    """Group elastic net objective ``loss(eta) [- loss_full] + lmda * penalty(beta)`` at every lambda (adelie/diagnostic.py:124-276);
+    ``X`` is a NumPy array or a device matrix, the loss is evaluated by the GLM object (on the device)."""
+    from . import matrix as _matrix
+    intercepts = np.atleast_1d(np.asarray(intercepts))
+    K = intercepts.shape[1] if intercepts.ndim == 2 else 1
+    p = (X.shape[1] if isinstance(X, np.ndarray) else X.cols()) * K
+    if groups is None:
+        groups = np.arange(p // K) if K == 1 else K * np.arange(p // K)
+    elif K > 1:
+        groups = np.asarray(groups) * K
+    groups = np.asarray(groups, dtype=int)
+    group_sizes = np.diff(np.concatenate([groups, [p]]))
+    if penalty is None:
+        penalty = np.sqrt(group_sizes)
+    Xd = _matrix.dense(np.asfortranarray(X, dtype=glm.dtype), n_threads=n_threads) if isinstance(X, np.ndarray) else X
+    etas = predict(Xd, betas, intercepts, offsets=offsets, n_threads=n_threads)
+    objs = np.array([glm.loss(np.ascontiguousarray(eta, dtype=glm.dtype)) for eta in etas], dtype=np.float64)
+    if relative:
+        objs -= glm.loss_full()
+    if add_penalty:
+        objs += np.asarray(lmdas) * compute_penalty(groups, group_sizes, penalty, alpha, betas)
+    return objs

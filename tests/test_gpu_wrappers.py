@@ -198,3 +198,23 @@ def test_sklearn_group_elastic_net():
     assert pm.shape == (4, 300, 3) and np.allclose(pm.sum(axis=-1), 1)
     with pytest.raises(RuntimeError, match="not been fitted"):
         GroupElasticNet().predict(X)
+
+
+def test_diagnostic_objective_matches_numpy():
+    """adelie/diagnostic.py:124-276: loss on the device + penalty, and the reference's acceptance rule objective(ours) <= (1 + eps) objective(oracle)."""
+    from adelie_b200.diagnostic import objective
+    data = ad.data.dense(400, 24, 6, seed=3)
+    X, y = data["X"], data["glm"].y
+    kw = dict(groups=data["groups"], penalty=data["penalty"], alpha=0.6, lmda_path_size=8, min_ratio=0.2, early_exit=False)
+    st = ad.grpnet(X, ad.glm.gaussian(y), progress_bar=False, **kw)
+    ref = orc.grpnet(X, orc.glm_spec("gaussian", y), **kw)
+    okw = dict(groups=data["groups"], alpha=0.6, penalty=data["penalty"])
+    o1 = objective(X, ad.glm.gaussian(y), st.betas, st.intercepts, st.lmdas, **okw)
+    o2 = objective(X, ad.glm.gaussian(y), ref.betas, np.asarray(ref.intercepts), np.asarray(ref.lmdas), **okw)
+    w = np.full(400, 1 / 400)
+    B = np.asarray(st.betas.todense())
+    exp = np.array([0.5 * np.sum(w * (y - X @ B[l] - st.intercepts[l]) ** 2) for l in range(B.shape[0])])
+    gs = data["group_sizes"]
+    pen = np.array([sum(pk * (0.6 * np.linalg.norm(b[g:g + s_]) + 0.2 * np.linalg.norm(b[g:g + s_]) ** 2) for g, s_, pk in zip(data["groups"], gs, data["penalty"])) for b in B])
+    np.testing.assert_allclose(o1, exp + st.lmdas * pen, rtol=1e-9, atol=1e-12)
+    assert np.all(o1 <= o2 * (1 + 1e-6) + 1e-12)

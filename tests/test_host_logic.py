@@ -102,3 +102,13 @@ def test_standardize_and_subset_numpy_paths():
     np.testing.assert_allclose(S.std(axis=0, ddof=1), 1, atol=1e-12)
     assert S.flags.f_contiguous and not np.shares_memory(S, Z)
     assert np.array_equal(ad.matrix.subset(Z, [3, 1], axis=1), Z[:, [3, 1]])
+
+
+def test_compute_penalty():
+    import scipy.sparse as sp
+    from adelie_b200.diagnostic import compute_penalty
+    B = np.array([[3.0, 4.0, 0.0, 1.0], [0.0, 0.0, 2.0, 0.0]])
+    groups = np.array([0, 2, 3]); gsz = np.array([2, 1, 1]); pen = np.array([1.0, 2.0, 0.5])
+    exp = np.array([1.0 * (0.7 * 5 + 0.15 * 25) + 0.5 * (0.7 * 1 + 0.15 * 1), 2.0 * (0.7 * 2 + 0.15 * 4)])
+    np.testing.assert_allclose(compute_penalty(groups, gsz, pen, 0.7, B), exp)
+    np.testing.assert_allclose(compute_penalty(groups, gsz, pen, 0.7, sp.csr_matrix(B)), exp)
