@@ -16,10 +16,17 @@ from . import glm
 from . import io
 from . import matrix
 from . import solver
-from . import sklearn
 from . import state
 from .configs import set_configs
 from .solver import grpnet
 from .cv import cv_grpnet
 
 __version__ = "0.1.0"
+
+
+def __getattr__(name):
+    # `adelie_b200.sklearn` needs scikit-learn: imported on first use so that the package itself does not depend on it
+    if name == "sklearn":
+        import importlib
+        return importlib.import_module(".sklearn", __name__)
+    raise AttributeError(name)
