@@ -33,31 +33,30 @@
 namespace ab {
 
 // ============================================================================================ host: .snpdat reader / writer
-struct SnpUnphasedIO {
+// What both formats share (IOSNPBase, CORE/io/io_snp_base.hpp:17-141, .ipp:20-84): file name, read mode, the bytes (read or mapped),
+// the endianness byte.
+struct SnpFileBase {
     static constexpr uint64_t kChunk = 256;
-    static constexpr int kCategories = 3;
     std::string filename; int read_mode = 0;     // 0 = file, 1 = mmap
     bool is_read = false;
     std::vector<char> owned; const char* buf = nullptr; size_t buf_bytes = 0; void* map_addr = nullptr; size_t map_bytes = 0;
-    uint64_t rows = 0, snps = 0;
-    std::vector<uint64_t> nnz, nnm, outer; std::vector<double> impute;
 
-    SnpUnphasedIO(const std::string& f, const std::string& mode) : filename(f) {
+    SnpFileBase(const std::string& f, const std::string& mode) : filename(f) {
         // util::convert_read_mode + IOSNPBase::convert_read_mode (io_snp_base.hpp:123-139): "auto" means mmap on Linux
         if (mode == "file") read_mode = 0;
         else if (mode == "mmap" || mode == "auto") read_mode = 1;
         else throw core_error("Invalid read mode type: " + mode);
     }
-    ~SnpUnphasedIO() { release(); }
-    SnpUnphasedIO(const SnpUnphasedIO&) = delete;
-    SnpUnphasedIO& operator=(const SnpUnphasedIO&) = delete;
+    ~SnpFileBase() { release(); }
+    SnpFileBase(const SnpFileBase&) = delete;
+    SnpFileBase& operator=(const SnpFileBase&) = delete;
     void release() { if (map_addr) { munmap(map_addr, map_bytes); map_addr = nullptr; } owned.clear(); owned.shrink_to_fit(); buf = nullptr; buf_bytes = 0; }
     void need_read() const { if (!is_read) throw core_error("File is not read yet. Call read() first."); }
     static bool big_endian() { const uint32_t one = 1; return reinterpret_cast<const char*>(&one)[0] != 1; }
     template <class U> static U rd(const char* q) { U u; std::memcpy(&u, q, sizeof(U)); return u; }
 
-    // io_snp_base.ipp:20-84 + io_snp_unphased.ipp:9-41
-    size_t read() {
+    // io_snp_base.ipp:20-84: reads or maps the whole file, checks the endianness byte; returns the number of bytes
+    size_t load(size_t min_bytes) {
         release();
         is_read = true;
         FILE* fp = std::fopen(filename.c_str(), "rb");
@@ -81,9 +80,22 @@ struct SnpUnphasedIO {
             buf = owned.data();
         }
         buf_bytes = total;
-        if (total < 1 + 2 * sizeof(uint64_t)) throw core_error("File is too short to be a .snpdat file.");
+        if (total < min_bytes) throw core_error("File is too short to be a .snpdat file.");
         if ((buf[0] != 0) != big_endian())
             throw core_error("Endianness is inconsistent! Regenerate the file on a machine with the same endianness.");
+        return total;
+    }
+};
+
+struct SnpUnphasedIO : SnpFileBase {
+    static constexpr int kCategories = 3;
+    uint64_t rows = 0, snps = 0;
+    std::vector<uint64_t> nnz, nnm, outer; std::vector<double> impute;
+    using SnpFileBase::SnpFileBase;
+
+    // io_snp_base.ipp:20-84 + io_snp_unphased.ipp:9-41
+    size_t read() {
+        const size_t total = load(1 + 2 * sizeof(uint64_t));
         size_t idx = 1;
         rows = rd<uint64_t>(buf + idx); idx += 8;
         snps = rd<uint64_t>(buf + idx); idx += 8;
@@ -209,52 +221,13 @@ struct SnpUnphasedIO {
 //       haplotype: [n_chunks:u32] { [chunk_idx:u32][nnz-1:u8][row_in_chunk:u8 x nnz] }, chunk = 256 rows
 // On the device the matrix is the SAME 2-bit packed storage as snp_unphased (codes 0 / 1 / 2, code 3 never occurs), so every
 // kernel and the whole solver path are shared; only the unpack kernel differs (it ADDS one per haplotype hit).
-struct SnpPhasedAncestryIO {
-    static constexpr uint64_t kChunk = 256;
-    std::string filename; int read_mode = 0; bool is_read = false;
-    std::vector<char> owned; const char* buf = nullptr; size_t buf_bytes = 0; void* map_addr = nullptr; size_t map_bytes = 0;
+struct SnpPhasedAncestryIO : SnpFileBase {
     uint64_t rows = 0, snps = 0, ancestries = 0, cols = 0;
     std::vector<uint64_t> nnz0, nnz1, outer;
-
-    SnpPhasedAncestryIO(const std::string& f, const std::string& mode) : filename(f) {
-        if (mode == "file") read_mode = 0;
-        else if (mode == "mmap" || mode == "auto") read_mode = 1;
-        else throw core_error("Invalid read mode type: " + mode);
-    }
-    ~SnpPhasedAncestryIO() { release(); }
-    SnpPhasedAncestryIO(const SnpPhasedAncestryIO&) = delete;
-    SnpPhasedAncestryIO& operator=(const SnpPhasedAncestryIO&) = delete;
-    void release() { if (map_addr) { munmap(map_addr, map_bytes); map_addr = nullptr; } owned.clear(); owned.shrink_to_fit(); buf = nullptr; buf_bytes = 0; }
-    void need_read() const { if (!is_read) throw core_error("File is not read yet. Call read() first."); }
-    template <class U> static U rd(const char* q) { U u; std::memcpy(&u, q, sizeof(U)); return u; }
+    using SnpFileBase::SnpFileBase;
 
     size_t read() {                                                   // io_snp_base.ipp:20-84 + io_snp_phased_ancestry.ipp:9-43
-        release();
-        is_read = true;
-        FILE* fp = std::fopen(filename.c_str(), "rb");
-        if (!fp) throw core_error("Cannot open file " + filename);
-        std::fseek(fp, 0, SEEK_END);
-        const size_t total = (size_t)std::ftell(fp);
-        std::fseek(fp, 0, SEEK_SET);
-        if (read_mode == 1) {
-            std::fclose(fp);
-            const int fd = open(filename.c_str(), O_RDONLY);
-            if (fd == -1) throw core_error("open failed.");
-            void* addr = mmap(nullptr, total, PROT_READ, MAP_PRIVATE | MAP_NORESERVE | MAP_POPULATE, fd, 0);
-            close(fd);
-            if (addr == MAP_FAILED) throw core_error("mmap failed.");
-            map_addr = addr; map_bytes = total; buf = static_cast<const char*>(addr);
-        } else {
-            owned.resize(total);
-            const size_t got = std::fread(owned.data(), 1, total, fp);
-            std::fclose(fp);
-            if (got != total) throw core_error("Could not read the whole file into buffer.");
-            buf = owned.data();
-        }
-        buf_bytes = total;
-        if (total < 18) throw core_error("File is too short to be a .snpdat file.");
-        if ((buf[0] != 0) != SnpUnphasedIO::big_endian())
-            throw core_error("Endianness is inconsistent! Regenerate the file on a machine with the same endianness.");
+        const size_t total = load(18);
         size_t idx = 1;
         rows = rd<uint64_t>(buf + idx); idx += 8;
         snps = rd<uint64_t>(buf + idx); idx += 8;
@@ -336,7 +309,7 @@ struct SnpPhasedAncestryIO {
         for (uint64_t j = 0; j < s_; ++j) v_outer[j + 1] = v_outer[j] + snp_bytes[j].size();
         std::vector<char> out(preamble);
         size_t idx = 0;
-        out[idx++] = (char)SnpUnphasedIO::big_endian();
+        out[idx++] = (char)big_endian();
         std::memcpy(&out[idx], &n, 8); idx += 8;
         std::memcpy(&out[idx], &s_, 8); idx += 8;
         out[idx++] = (char)(uint8_t)A;

@@ -352,7 +352,7 @@ struct PathState {
         timers.slot("cov_device") += now_s() - t_cov0;
         n_kernel_launches += 2;
         meta.resize(S);
-        std::vector<double> Cg, D, V;
+        std::vector<double> Cg;
         // ---- phase 1: centred Gram of every group, packed back to back (eig_in), offsets per group
         std::vector<double> eig_in, eig_V, eig_D; std::vector<EigItem> eig_items; std::vector<int64_t> eig_slot(end - begin, -1);
         {
