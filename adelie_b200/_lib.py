@@ -51,7 +51,7 @@ _lib = None
 
 # every symbol declared in include/adelie_b200.h (checked by tests/test_cabi.py)
 SYMBOLS = [
-    "ab_last_error", "ab_version", "ab_device_count", "ab_set_device", "ab_get_device_info", "ab_device_synchronize", "ab_host_register", "ab_host_unregister", "ab_timer_start", "ab_timer_stop",
+    "ab_last_error", "ab_version", "ab_device_count", "ab_set_device", "ab_get_device_info", "ab_mem_info", "ab_device_synchronize", "ab_host_register", "ab_host_unregister", "ab_timer_start", "ab_timer_stop",
     "ab_dist_init", "ab_dist_connect", "ab_dist_allreduce_f64", "ab_dist_info",
     "ab_configs_set", "ab_configs_get",
     "ab_matrix_dense_create", "ab_matrix_dense_alloc", "ab_matrix_dense_fill_normal", "ab_matrix_dense_download",
@@ -153,6 +153,7 @@ def load():
     L.ab_dist_connect.argtypes = [c_vp]
     L.ab_dist_allreduce_f64.argtypes = [c_vp, c_i64]
     L.ab_dist_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ab_mem_info.argtypes = [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.ab_get_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     _lib = L
     return L

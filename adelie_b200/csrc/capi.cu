@@ -46,6 +46,13 @@ int ab_get_device_info(int* sm_count, size_t* smem, size_t* total_mem) {
     if (total_mem) { size_t fr, tot; AB_CUDA(cudaMemGetInfo(&fr, &tot)); *total_mem = tot; }
     AB_CATCH
 }
+int ab_mem_info(size_t* free_bytes, size_t* total_bytes) {
+    AB_TRY
+    size_t fr, tot; AB_CUDA(cudaMemGetInfo(&fr, &tot));
+    if (free_bytes) *free_bytes = fr;
+    if (total_bytes) *total_bytes = tot;
+    AB_CATCH
+}
 int ab_device_synchronize(void) { AB_TRY AB_CUDA(cudaDeviceSynchronize()); AB_CATCH }
 int ab_host_register(void* ptr, size_t bytes) { AB_TRY AB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault)); AB_CATCH }
 int ab_host_unregister(void* ptr) { AB_TRY AB_CUDA(cudaHostUnregister(ptr)); AB_CATCH }

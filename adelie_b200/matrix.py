@@ -20,10 +20,15 @@ def _to_dtype(mat):
 
 
 class MatrixNaiveTranspose:
-    """adelie/matrix.py:52-80"""
+    """adelie/matrix.py:52-80.  Built on access by ``mat.T`` (a property): the matrix itself holds no reference to its transpose view,
+    so a matrix is never part of a reference cycle and its device copy is freed by reference counting as soon as the last user
+    drops it (a cycle would leave the free to the cyclic GC, which does not see HBM pressure)."""
     def __init__(self, mat):
         self._mat = mat
-        self.T = mat
+
+    @property
+    def T(self):
+        return self._mat
 
     def __matmul__(self, v):
         dtype = _to_dtype(self._mat)
@@ -49,7 +54,10 @@ class MatrixNaiveBase:
         if n_threads < 1:
             raise RuntimeError("adelie_core: n_threads must be >= 1.")
         self._n_threads = n_threads
-        self.T = MatrixNaiveTranspose(self)
+
+    @property
+    def T(self):
+        return MatrixNaiveTranspose(self)
 
     @property
     def ndim(self):
@@ -100,15 +108,37 @@ class _DeviceMatrix(MatrixNaiveBase):
 
     def _core(self):
         if self._handle is None:
-            self._handle = self._make_handle()
+            try:
+                self._handle = self._make_handle()
+            except RuntimeError as e:
+                if "out of memory" not in str(e):
+                    raise
+                # device copies are freed by reference counting; objects that user code left in a cycle only die in the cyclic GC,
+                # which does not see HBM pressure: collect once and retry
+                import gc
+                gc.collect()
+                self._handle = self._make_handle()
         return self._handle
 
+    def close(self):
+        """Frees the device copy now (extension; the reference's matrices are host views).  The matrix stays usable: the copy is
+        rebuilt on the next operator call when the matrix still has its host source."""
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                _lib.load().ab_matrix_free(h)
+            except Exception:
+                pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
     def __del__(self):
-        try:
-            if getattr(self, "_handle", None) is not None:
-                _lib.load().ab_matrix_free(self._handle)
-        except Exception:
-            pass
+        self.close()
 
     def __getitem__(self, key):
         """``mat[rows]`` / ``mat[:, cols]`` / ``mat[rows, cols]`` sugar over :func:`subset` (adelie/matrix.py:84-134): integers, slices, lists,

@@ -63,25 +63,38 @@ class base:
         del keep
         return h
 
+    def _core(self):
+        """The core handle; (re)built from the stored inputs when ``solve()`` handed the previous one to the returned state."""
+        if self._handle is None:
+            if not self.__dict__.get("_pristine", True):
+                raise RuntimeError("adelie_b200: this solved state was closed; its results are gone.")
+            self._handle = self._build_core()
+        return self._handle
+
+    def close(self):
+        """Frees the core state's device buffers now (extension; otherwise freed when the last reference is dropped)."""
+        h, self._handle = self.__dict__.get("_handle"), None
+        if h is not None:
+            try:
+                _lib.load().ab_state_free(h)
+            except Exception:
+                pass
+
     def __del__(self):
-        try:
-            if getattr(self, "_handle", None) is not None:
-                _lib.load().ab_state_free(self._handle)
-        except Exception:
-            pass
+        self.close()
 
     # ---- output accessors ------------------------------------------------------------------
     def _scalar(self, name):
         out = C.c_double()
-        _lib.check(_lib.load().ab_state_get_scalar(self._handle, name.encode(), C.byref(out)))
+        _lib.check(_lib.load().ab_state_get_scalar(self._core(), name.encode(), C.byref(out)))
         return out.value
 
     def _vec_f(self, name, dtype=None):
         L = _lib.load()
         n = C.c_int64()
-        _lib.check(L.ab_state_get_vec_f64(self._handle, name.encode(), None, 0, C.byref(n)))
+        _lib.check(L.ab_state_get_vec_f64(self._core(), name.encode(), None, 0, C.byref(n)))
         buf = np.empty(n.value, dtype=np.float64)
-        _lib.check(L.ab_state_get_vec_f64(self._handle, name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
+        _lib.check(L.ab_state_get_vec_f64(self._core(), name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
         if name.startswith("benchmark") or name == "sweep_stats":
             return buf
         return buf.astype(self._dtype if dtype is None else dtype)
@@ -89,9 +102,9 @@ class base:
     def _vec_i(self, name):
         L = _lib.load()
         n = C.c_int64()
-        _lib.check(L.ab_state_get_vec_i64(self._handle, name.encode(), None, 0, C.byref(n)))
+        _lib.check(L.ab_state_get_vec_i64(self._core(), name.encode(), None, 0, C.byref(n)))
         buf = np.empty(n.value, dtype=np.int64)
-        _lib.check(L.ab_state_get_vec_i64(self._handle, name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
+        _lib.check(L.ab_state_get_vec_i64(self._core(), name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
         return buf
 
     def __getattr__(self, name):
@@ -146,9 +159,9 @@ class base:
         out = []
         for i in range(self.screen_set.shape[0]):
             n = C.c_int64()
-            _lib.check(L.ab_state_get_screen_transform(self._handle, i, None, 0, C.byref(n)))
+            _lib.check(L.ab_state_get_screen_transform(self._core(), i, None, 0, C.byref(n)))
             buf = np.empty(n.value, dtype=np.float64)
-            _lib.check(L.ab_state_get_screen_transform(self._handle, i, _lib.ptr(buf), n.value, C.byref(n)))
+            _lib.check(L.ab_state_get_screen_transform(self._core(), i, _lib.ptr(buf), n.value, C.byref(n)))
             gs = int(round(np.sqrt(n.value)))
             out.append(buf.astype(self._dtype).reshape(gs, gs))
         return out
@@ -158,11 +171,11 @@ class base:
         """(L, p) scipy CSR with int64 indices (py_state.cpp:9-60)."""
         L = _lib.load()
         nnz, nl = C.c_int64(), C.c_int64()
-        _lib.check(L.ab_state_get_betas(self._handle, None, None, None, C.byref(nnz), C.byref(nl)))
+        _lib.check(L.ab_state_get_betas(self._core(), None, None, None, C.byref(nnz), C.byref(nl)))
         indptr = np.empty(nl.value + 1, dtype=np.int64)
         indices = np.empty(nnz.value, dtype=np.int64)
         values = np.empty(nnz.value, dtype=np.float64)
-        _lib.check(L.ab_state_get_betas(self._handle, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values), C.byref(nnz), C.byref(nl)))
+        _lib.check(L.ab_state_get_betas(self._core(), _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values), C.byref(nnz), C.byref(nl)))
         p = self._p_cols
         B = scipy.sparse.csr_matrix((values.astype(self._dtype), indices, indptr), shape=(nl.value, p))
         B.indices = B.indices.astype(np.int64); B.indptr = B.indptr.astype(np.int64)     # int64 like the reference (py_state.cpp:9-60)
@@ -184,8 +197,21 @@ class base:
         cb_exit = None
         if exit_cond is not None:
             cb_exit = _lib.EXIT_COND_T(lambda ctx: int(bool(exit_cond(new))))
-        rc = L.ab_state_solve(new._handle, int(progress_bar), C.cast(cb_exit, C.c_void_p) if cb_exit else None, None, None,
-                              err, len(err), C.byref(total))
+        # interrupt polling (py_state.cpp:70-74): the core calls back once per pin solve; a pending KeyboardInterrupt (or any
+        # exception raised by a Python signal handler) stops the solve and is re-raised here
+        pending = []
+        def _poll():
+            try:
+                C.pythonapi.PyErr_CheckSignals()
+            except BaseException as e:          # noqa: BLE001 -- whatever the signal handler raised
+                pending.append(e)
+                return 1
+            return 0
+        cb_sig = _lib.CHECK_SIGNALS_T(_poll)
+        rc = L.ab_state_solve(new._handle, int(progress_bar), C.cast(cb_exit, C.c_void_p) if cb_exit else None, None,
+                              C.cast(cb_sig, C.c_void_p), err, len(err), C.byref(total))
+        if pending:
+            raise pending[0]
         _lib.check(rc)
         new.error = err.value.decode()
         new.total_time = total.value
@@ -197,12 +223,19 @@ class base:
         return new
 
     def _clone(self):
+        """The copy ``solve`` works on (py_state.cpp:62-145 takes the state by value).  The core state of ``self`` is pristine -- every
+        accessor is read-only -- so it is *moved* into the copy instead of building a second one (screen-derived Grams, uploads); ``self``
+        rebuilds its own lazily if it is read again."""
         obj = object.__new__(type(self))
         for k, v in self.__dict__.items():
             if k != "_handle":
                 setattr(obj, k, v)
         obj._handle = None
-        obj._handle = obj._build_core()
+        if self.__dict__.get("_pristine", True):
+            obj._handle, self._handle = self._handle, None
+        if obj._handle is None:
+            obj._handle = obj._build_core()      # a solved state re-solves from its stored inputs; its own results stay
+        obj._pristine = False
         return obj
 
     def check(self, method=None, logger=logger):

@@ -33,6 +33,7 @@ int ab_version(void);
 int ab_device_count(int* count);
 int ab_set_device(int device);
 int ab_get_device_info(int* sm_count, size_t* smem_optin_bytes, size_t* total_mem_bytes);
+int ab_mem_info(size_t* free_bytes, size_t* total_bytes);   /* cudaMemGetInfo of the current device (leak regression tests, bench) */
 int ab_device_synchronize(void);
 /* pin / unpin a host buffer (bench: H2D from pinned memory); CUDA-event stopwatch on the library's stream */
 int ab_host_register(void* ptr, size_t bytes);

@@ -116,3 +116,61 @@ def test_property_path_at_scale():
                 assert np.max(np.abs(g[j:j + gs] - lam_p * b[j:j + gs] / bn)) < 2e-3 * lam_p
             else:
                 assert gn <= lam_p * (1 + 1e-3)
+
+
+def _free_hbm():
+    import ctypes as C
+    from adelie_b200 import _lib
+    fr, tot = C.c_size_t(), C.c_size_t()
+    _lib.check(_lib.load().ab_device_synchronize())
+    _lib.check(_lib.load().ab_mem_info(C.byref(fr), C.byref(tot)))
+    return fr.value
+
+
+def test_no_hbm_leak_over_repeated_grpnet_calls():
+    """30 x grpnet(ndarray): every call uploads its own 160 MB copy of X; free HBM must stay flat (round-1 leak: the copies were only
+    released by the cyclic GC).  Automatic garbage collection is switched off to make the test deterministic."""
+    import gc
+    rng = np.random.default_rng(0)
+    n, p = 20000, 2000
+    X = np.asfortranarray(rng.standard_normal((n, p), dtype=np.float32))
+    y = (X[:, :5] @ np.ones(5, dtype=np.float32) + rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+    kw = dict(groups=np.arange(0, p, 10), progress_bar=False, lmda_path_size=5, min_ratio=0.5, newton_tol=1e-6)
+    ad.grpnet(X, ad.glm.gaussian(y, dtype=np.float32), **kw)            # warm the memory pool
+    gc.collect(); gc.disable()
+    try:
+        free0 = _free_hbm()
+        for _ in range(30):
+            st = ad.grpnet(X, ad.glm.gaussian(y, dtype=np.float32), **kw)
+            assert st.error == ""
+        del st
+        free1 = _free_hbm()
+    finally:
+        gc.enable()
+    assert free0 - free1 < (1 << 30), f"HBM leak: {(free0 - free1) / 2**20:.0f} MiB over 30 solves"
+
+
+def test_solve_moves_the_core_state_and_the_input_state_stays_usable():
+    X, y, groups, penalty = _data()
+    kw = dict(groups=groups, penalty=penalty, progress_bar=False, lmda_path_size=6, min_ratio=0.3)
+    ref = ad.grpnet(X, ad.glm.gaussian(y), **kw)
+    # an unsolved state: solve() works on a copy; the pristine core is moved into the copy, not built twice ...
+    w = np.full(X.shape[0], 1 / X.shape[0]); Xm = ad.matrix.dense(X)
+    yc = y - np.sum(w * y); grad = np.empty(X.shape[1]); Xm.mul(yc, w, grad); xm = np.empty(X.shape[1]); Xm.mul(np.ones_like(yc), w, xm)
+    G = len(groups)
+    st0 = ad.state.gaussian_naive(X=Xm, y=y, X_means=xm, y_mean=np.sum(w * y), y_var=np.sum(w * yc ** 2), resid=yc, resid_sum=np.sum(w * yc),
+                                  constraints=None, groups=groups, group_sizes=np.diff(np.append(groups, X.shape[1])), alpha=1, penalty=penalty,
+                                  weights=w, offsets=np.zeros_like(y), screen_set=np.zeros(0, dtype=int), screen_beta=np.zeros(0),
+                                  screen_is_active=np.zeros(0, dtype=bool), active_set_size=0, active_set=np.zeros(G, dtype=int), rsq=0,
+                                  lmda=np.inf, grad=grad, lmda_path_size=6, min_ratio=0.3)
+    assert st0._handle is not None
+    st1 = st0.solve(progress_bar=False)
+    assert st1.error == "" and st0._handle is None
+    np.testing.assert_allclose(st1.betas.toarray(), ref.betas.toarray(), atol=1e-12)
+    assert len(st0.lmdas) == 0 and st0._handle is not None        # ... and rebuilt lazily from the stored inputs when read again
+    # a solved state keeps its results when it is solved again
+    st2 = st1.solve(progress_bar=False)
+    assert len(st1.lmdas) == len(st2.lmdas) == len(ref.lmdas)
+    st1.close()
+    with pytest.raises(RuntimeError, match="closed"):
+        st1.betas

@@ -112,3 +112,25 @@ def test_compute_penalty():
     exp = np.array([1.0 * (0.7 * 5 + 0.15 * 25) + 0.5 * (0.7 * 1 + 0.15 * 1), 2.0 * (0.7 * 2 + 0.15 * 4)])
     np.testing.assert_allclose(compute_penalty(groups, gsz, pen, 0.7, B), exp)
     np.testing.assert_allclose(compute_penalty(groups, gsz, pen, 0.7, sp.csr_matrix(B)), exp)
+
+
+def test_matrices_are_freed_by_refcount_not_by_the_cyclic_gc():
+    """Round-1 bug: `self.T = MatrixNaiveTranspose(self)` put every matrix in a reference cycle, so the device copy of X was
+    only freed when the cyclic GC happened to run (an HBM leak of one X per `grpnet(ndarray)` call)."""
+    import gc
+    import weakref
+    import scipy.sparse as sp
+    X = np.asfortranarray(np.random.default_rng(0).normal(size=(40, 6)))
+    gc.disable()
+    try:
+        makers = [lambda: ad.matrix.dense(X), lambda: ad.matrix.sparse(sp.csc_matrix(X)), lambda: ad.matrix.kronecker_eye(X, 3),
+                  lambda: ad.matrix.concatenate([ad.matrix.dense(X), ad.matrix.dense(X)], axis=1)]
+        for mk in makers:
+            m = mk()
+            t = m.T
+            assert t.T is m and t._mat is m
+            w = weakref.ref(m)
+            del m, t
+            assert w() is None
+    finally:
+        gc.enable()
