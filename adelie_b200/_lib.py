@@ -133,6 +133,7 @@ def load():
     L.ab_state_create.argtypes = [C.POINTER(StateArgs), c_vp, c_vp, C.POINTER(c_vp)]
     L.ab_state_free.argtypes = [c_vp]
     L.ab_state_solve.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_double)]
+    L.ab_pin_naive_solve.argtypes = [c_vp, c_vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_double)]
     L.ab_state_get_scalar.argtypes = [c_vp, C.c_char_p, C.POINTER(C.c_double)]
     L.ab_state_get_vec_f64.argtypes = [c_vp, C.c_char_p, c_vp, c_i64, C.POINTER(c_i64)]
     L.ab_state_get_vec_i64.argtypes = [c_vp, C.c_char_p, c_vp, c_i64, C.POINTER(c_i64)]

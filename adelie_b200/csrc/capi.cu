@@ -845,6 +845,7 @@ static int state_vec_f64(const PathState<T>& s, const std::string& nm, double* o
     if (nm == "abs_grad") return copy_vec<T>(s.abs_grad, out, cap, len);
     if (nm == "devs") return copy_vec<T>(s.devs, out, cap, len);
     if (nm == "lmdas") return copy_vec<T>(s.lmdas, out, cap, len);
+    if (nm == "rsqs") return copy_vec<T>(s.rsqs, out, cap, len);
     if (nm == "intercepts") return copy_vec<T>(s.intercepts, out, cap, len);
     if (nm == "X_means") return copy_vec<T>(s.X_means, out, cap, len);
     if (nm == "screen_X_means") return copy_vec<T>(s.screen_X_means, out, cap, len);
@@ -1021,11 +1022,21 @@ int ab_bcd_root_function(int64_t q, double h, const double* D, const double* v, 
     return bcd_run(4, q, D, v, l1, 0, 0, 0, h, nullptr, out);
 }
 
-int ab_pin_naive_solve(ab_matrix* X, ab_pin_args* args, ab_state** out, char* err, size_t errlen) {
-    (void)X; (void)args; (void)out;
-    if (err && errlen) err[0] = 0;
-    g_last_error = "adelie_core: pin state API not implemented yet.";
-    return AB_ERR_ARG;
+int ab_pin_naive_solve(ab_state* s, int (*check_signals)(void), char* err, size_t errlen, double* total_time) {
+    g_last_error.clear();
+    s->error.clear();
+    const double t0 = now_s();
+    auto run = [&](auto* ps) {
+        if (check_signals) ps->check_interrupt = [=]() { if (check_signals() != 0) throw solver_error("interrupted."); };
+        try { ps->solve_pin(); }
+        catch (const std::exception& e) { s->error = e.what(); }       // py_state.cpp:83-90: message returned, state stays valid
+        ps->check_interrupt = nullptr;
+    };
+    if (s->dtype == AB_F32) run(s->f32); else run(s->f64);
+    s->total_time = now_s() - t0;
+    if (total_time) *total_time = s->total_time;
+    if (err && errlen) { std::strncpy(err, s->error.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return AB_OK;
 }
 
 } // extern "C"

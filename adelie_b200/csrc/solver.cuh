@@ -838,6 +838,40 @@ struct PathState {
         else update_screen_derived_gaussian();
     }
 
+    // ------------------------------------------------------------------ the pin state in isolation
+    // pin::naive::solve over the state's own lmda_path on a FIXED screen set (solver_gaussian_pin_naive.hpp:223-401; the core of
+    // StateGaussianPinNaive, adelie/src/py_state.cpp:389-411).  `tol` is used as given (the path driver passes tol * y_var, :314),
+    // `iters` and max_iters are cumulative over the lambdas (:201, :327), outputs are betas / intercepts / rsqs / lmdas and the
+    // per-lambda timers (benchmark_screen / benchmark_active live in benchmark_fit_screen / benchmark_fit_active).
+    std::vector<T> rsqs;
+    void solve_pin() {
+        if (is_glm) throw core_error("the pin state is a Gaussian state.");
+        upload_screen_tables(h_meta, h_grec, false);
+        const size_t max_iters_total = max_iters;
+        for (size_t l = 0; l < lmda_path.size(); ++l) {
+            max_iters = (size_t)n_sweeps >= max_iters_total ? 0 : max_iters_total - (size_t)n_sweeps;
+            PinResult pr;
+            try { pr = run_pin(d_resid.p, d_weights.p, lmda_path[l], tol, y_mean, rsq, resid_sum, true); }
+            catch (const solver_error& e) {
+                max_iters = max_iters_total;
+                if (std::string(e.what()).find("max coordinate descents") != std::string::npos)
+                    throw solver_error("max coordinate descents reached at lambda index: " + std::to_string(l) + ".");
+                throw;
+            }
+            catch (...) { max_iters = max_iters_total; throw; }
+            max_iters = max_iters_total;
+            betas.emplace_back(std::move(pr.beta));
+            intercepts.push_back((T)pr.intercept);
+            rsqs.push_back(rsq);
+            lmdas.push_back(lmda_path[l]);
+            benchmark_fit_screen.push_back(pr.screen_time);
+            benchmark_fit_active.push_back(pr.active_time);
+            lmda = lmda_path[l];
+            if (rsq >= adev_tol * y_var) break;                                             // :398
+            if (l >= 1 && rsqs[l] - rsqs[l - 1] <= ddev_tol * y_var) break;                  // :399
+        }
+    }
+
     // ------------------------------------------------------------------ solve_core (solver_base.hpp:435-687)
     void solve() {
         if (screen_set.size() > max_screen_size) throw solver_error("maximum screen set size reached.");

@@ -20,7 +20,7 @@ from . import matrix as _matrix
 
 logger = logging.getLogger("adelie_b200")
 
-_VEC_F = ["lmda_path", "screen_beta", "grad", "abs_grad", "devs", "lmdas", "X_means", "screen_X_means", "screen_vars",
+_VEC_F = ["rsqs", "lmda_path", "screen_beta", "grad", "abs_grad", "devs", "lmdas", "X_means", "screen_X_means", "screen_vars",
           "resid", "eta", "sweep_stats", "benchmark_screen", "benchmark_fit_screen", "benchmark_fit_active", "benchmark_kkt",
           "benchmark_invariance", "launch_cols", "launch_sweeps", "launch_ms"]
 _VEC_I = ["screen_set", "screen_begins", "screen_is_active", "active_set", "n_valid_solutions", "active_sizes", "screen_sizes"]
@@ -238,8 +238,44 @@ class base:
         obj._pristine = False
         return obj
 
+    def _check(self, passed, msg, method, logger):
+        """adelie/state.py:84-90: every check is logged; method="assert" also asserts."""
+        if passed:
+            logger.info(msg)
+        else:
+            logger.error(msg)
+            if method == "assert":
+                assert False, msg
+
+    def _check_layout(self, method, logger, p):
+        """Index-structure invariants shared by every state (adelie/state.py:1434-1548, 186-300): groups / group_sizes / penalty /
+        screen_set / screen_begins / screen_beta sizes and dtypes."""
+        c = lambda ok, msg: self._check(bool(ok), msg, method, logger)
+        groups, gsz, S = self.groups, self.group_sizes, self.screen_set
+        G = len(groups)
+        c(np.all((0 <= groups) & (groups <= p)), "check groups is in [0, p)")
+        c(len(groups) == len(np.unique(groups)), "check groups has unique values")
+        c(groups.dtype == np.dtype("int"), "check groups dtype is int")
+        c(len(gsz) == G, "check groups and group_sizes have same length")
+        c(np.sum(gsz) == p, "check sum of group_sizes is p")
+        c(np.all((0 < gsz) & (gsz <= p)), "check group_sizes is in (0, p]")
+        c(gsz.dtype == np.dtype("int"), "check group_sizes dtype is int")
+        c(np.array_equal(groups, np.cumsum(np.concatenate([[0], gsz]))[:-1]), "check groups and group_sizes consistency")
+        c(np.all(self.penalty >= 0), "check penalty is non-negative")
+        c(len(self.penalty) == G, "check penalty and groups have same length")
+        c(np.all((0 <= S) & (S < G)), "check screen_set is a subset of [0, G)")
+        c(len(S) == len(np.unique(S)), "check screen_set has unique values")
+        c(S.dtype == np.dtype("int"), "check screen_set dtype is int")
+        begins = np.cumsum(np.concatenate([[0], gsz[S]]).astype(int))
+        sb = self.screen_begins
+        c(np.array_equal(sb, begins[:-1]), "check screen_begins is [0, g1, g2, ...] where gi is the group size of (i-1)th screen group.")
+        c(sb.dtype == np.dtype("int"), "check screen_begins dtype is int")
+        return begins[-1]
+
     def check(self, method=None, logger=logger):
-        return
+        """Checks consistency of the members; every check is logged, ``method="assert"`` also asserts (adelie/state.py:92-116).
+        Subclasses re-derive every invariant of their state from X, y and the coefficients."""
+        self._check_layout(method, logger, self._p_cols)
 
 
 class _Naive(base):
@@ -310,6 +346,79 @@ class _Naive(base):
     @property
     def offsets(self):
         return self._offsets
+
+    def check(self, method=None, logger=logger):
+        """Re-derives every invariant of a Gaussian naive state from X, y and ``screen_beta`` (adelie/state.py:1422-1674): layout,
+        screen_is_active vs the non-zero blocks, rsq, grad, abs_grad, resid, resid_sum, screen_X_means, and for every screen group that
+        V^T (X_g^T W X_g - xbar xbar^T) V is diagonal with diagonal screen_vars.  float32 states are compared at float32 resolution
+        (the reference's np.allclose defaults assume float64).  GLM / multi-response states check the layout only."""
+        WS = self._check_layout(method, logger, self._p_cols)
+        if self._use_glm or self._is_multi or _dist_active():
+            return
+        c = lambda ok, msg: self._check(bool(ok), msg, method, logger)
+        f32 = np.dtype(self._dtype) == np.float32
+        close = (lambda a, b: np.allclose(a, b, rtol=2e-4, atol=2e-5)) if f32 else np.allclose
+        X, w = self._X, np.asarray(self.weights, dtype=self._dtype)
+        n, p = X.rows(), X.cols()
+        groups, gsz, S, sb = self.groups, self.group_sizes, self.screen_set, self.screen_begins
+        beta = self.screen_beta
+        c(np.all(w >= 0), "check weights is non-negative")
+        c(np.allclose(np.sum(w, dtype=np.float64), 1), "check weights sum to 1")
+        c(len(beta) == WS, "check screen_beta size")
+        nnz = np.array([i for i in range(len(S)) if np.any(beta[sb[i]:sb[i] + gsz[S[i]]] != 0)], dtype=int)
+        c(np.all(self.screen_is_active[nnz]), "check screen_is_active is only active on non-zeros of screen_beta")
+        yc = np.asarray(self._glm.y, dtype=np.float64) - np.asarray(self._offsets, dtype=np.float64)
+        w64 = w.astype(np.float64)
+        if self.intercept:
+            yc = yc - np.sum(yc * w64)
+        Xbeta = np.zeros(n, dtype=self._dtype)
+        cols = []
+        for i in range(len(S)):
+            g, gs = int(groups[S[i]]), int(gsz[S[i]])
+            cols.append(np.arange(g, g + gs))
+            X.btmul(g, gs, np.ascontiguousarray(beta[sb[i]:sb[i] + gs]), Xbeta)
+        cols = np.concatenate(cols).astype(int) if cols else np.zeros(0, dtype=int)
+        resid = yc - Xbeta
+        grad = np.empty(p, dtype=self._dtype)
+        X.mul(np.ascontiguousarray(resid, dtype=self._dtype), w, grad)
+        grad = grad.astype(np.float64)
+        X_means = self.X_means.astype(np.float64)
+        if self.intercept:
+            grad -= X_means * np.sum(w64 * resid)
+        sXm = self.screen_X_means.astype(np.float64)
+        WXcbeta = w64 * (Xbeta - (sXm @ beta if self.intercept else 0.0))      # the reference subtracts the means unconditionally (:1573)
+        pos = w64 > 0
+        expected = 2 * np.sum(yc * WXcbeta) - np.sum(WXcbeta[pos] ** 2 / w64[pos])
+        c(close(self.rsq, expected), "check rsq")
+        c(close(self.grad, grad), "check grad")
+        lmda = 1e35 if np.isinf(self.lmda) else float(self.lmda)
+        gc_ = grad.copy()
+        for i in range(len(S)):
+            g, gs = int(groups[S[i]]), int(gsz[S[i]])
+            gc_[g:g + gs] -= lmda * (1 - self.alpha) * float(self.penalty[S[i]]) * beta[sb[i]:sb[i] + gs]
+        abs_grad = np.sqrt(np.add.reduceat(gc_ ** 2, groups)) if len(groups) else np.zeros(0)
+        c((self.lmda_max == -1) or close(self.abs_grad, abs_grad), "check abs_grad")
+        c(close(self.resid, resid), "check resid")
+        c(close(self.resid_sum, np.sum(w64 * resid)) or abs(self.resid_sum - np.sum(w64 * resid)) < (1e-5 if f32 else 1e-10), "check resid_sum")
+        c(close(sXm, X_means[cols]), "check screen_X_means")
+        sqrt_w = np.sqrt(w)
+        sv, st = self.screen_vars, self.screen_transforms
+        c(len(sv) == WS and np.all(sv >= 0), "check screen_vars size and sign")
+        c(len(st) == len(S), "check screen_transforms size")
+        for i in range(len(S)):
+            g, gs = int(groups[S[i]]), int(gsz[S[i]])
+            C_ = np.empty((gs, gs), dtype=self._dtype, order="F")
+            X.cov(g, gs, sqrt_w, C_)
+            C_ = C_.astype(np.float64)
+            if self.intercept:
+                C_ -= np.outer(X_means[g:g + gs], X_means[g:g + gs])
+            V = st[i].astype(np.float64)
+            D = V.T @ C_ @ V
+            scale = max(1.0, float(np.max(np.abs(np.diag(C_))))) if gs else 1.0
+            tol_d = (2e-4 if f32 else 1e-8) * scale
+            c(np.allclose(np.maximum(np.diag(D), 0), sv[sb[i]:sb[i] + gs], rtol=2e-4 if f32 else 1e-5, atol=tol_d), f"check screen_vars[{sb[i]}:{sb[i]}+{gs}]")
+            np.fill_diagonal(D, 0)
+            c(np.all(np.abs(D) <= tol_d), "check VT Xi V is nearly 0 after zeroing the diagonal")
 
     @property
     def constraints(self):
@@ -495,6 +604,11 @@ def _dist_sum(v):
     return _dist.allreduce(v)
 
 
+def _dist_active():
+    from . import dist as _dist
+    return _dist.is_active()
+
+
 def multiglm_naive(*, X, glm, constraints, groups, group_sizes, alpha, penalty, offsets, screen_set, screen_beta,
                    screen_is_active, active_set_size, active_set, lmda, grad, eta, resid, loss_full, loss_null=None,
                    lmda_path=None, lmda_max=None, irls_max_iters=int(1e4), irls_tol=1e-7, max_iters=int(1e5), tol=1e-7,
@@ -528,3 +642,122 @@ def multiglm_naive(*, X, glm, constraints, groups, group_sizes, alpha, penalty, 
                n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float(lmda), n_classes=int(K),
                multi_intercept=bool(intercept))
     return _MultiNaive(X=X, glm_obj=glm, use_glm=True, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=Xe.cols())
+
+
+class _Pin(_Naive):
+    """Gaussian pin state (adelie/state.py:179-420 gaussian_pin_base / gaussian_pin_naive_base + :421-720; core StateGaussianPinNaive,
+    adelie/src/py_state.cpp:389-411): solves its own ``lmda_path`` on a FIXED screen set (pin::naive::solve)."""
+
+    def solve(self, progress_bar: bool = False, exit_cond=None):
+        new = self._clone()
+        L = _lib.load()
+        err = C.create_string_buffer(4096)
+        total = C.c_double()
+        pending = []
+        def _poll():
+            try:
+                C.pythonapi.PyErr_CheckSignals()
+            except BaseException as e:          # noqa: BLE001
+                pending.append(e)
+                return 1
+            return 0
+        cb_sig = _lib.CHECK_SIGNALS_T(_poll)
+        rc = L.ab_pin_naive_solve(new._handle, C.cast(cb_sig, C.c_void_p), err, len(err), C.byref(total))
+        if pending:
+            raise pending[0]
+        _lib.check(rc)
+        new.error = err.value.decode()
+        new.total_time = total.value
+        if new.error != "":
+            (logger.error if new.error.startswith("adelie_core solver: ") else logger.warning)(RuntimeError(new.error))
+        return new
+
+    @property
+    def rsqs(self):
+        return self._vec_f("rsqs")
+
+    @property
+    def iters(self):
+        return self.n_sweeps
+
+    @property
+    def benchmark_screen(self):
+        return self._vec_f("benchmark_fit_screen")
+
+    @property
+    def benchmark_active(self):
+        return self._vec_f("benchmark_fit_active")
+
+    @property
+    def active_order(self):
+        a = self.active_set[: self.active_set_size]
+        return np.argsort(self.groups[self.screen_set[a]], kind="stable").astype(int)
+
+    @property
+    def active_begins(self):
+        a = self.active_set[: self.active_set_size]
+        return np.cumsum(np.concatenate([[0], self.group_sizes[self.screen_set[a]]]).astype(int))[:-1]
+
+    def check(self, method=None, logger=logger):
+        """adelie/state.py:180-420: layout, lmda_path, screen_is_active vs active_set, active_begins / active_order, output shapes."""
+        WS = self._check_layout(method, logger, self._p_cols)
+        c = lambda ok, msg: self._check(bool(ok), msg, method, logger)
+        S = len(self.screen_set)
+        sv = self.screen_vars
+        c(len(sv) == WS, "check screen_vars size")
+        c(np.all(sv >= 0), "check screen_vars is non-negative")
+        c(len(self.screen_transforms) == S, "check screen_transforms size")
+        c(np.all(self.lmda_path >= 0), "check lmda_path is non-negative")
+        a = self.active_set[: self.active_set_size]
+        c(np.array_equal(np.arange(S)[self.screen_is_active], np.sort(a)), "check screen_is_active is consistent with active_set")
+        c(self.screen_is_active.dtype == np.dtype("bool"), "check screen_is_active dtype is bool")
+        c(np.all((0 <= a) & (a < S)), "check active_set is in [0, S)")
+        c(len(a) == len(np.unique(a)), "check active_set is unique")
+        c(a.dtype == np.dtype("int"), "check active_set dtype is int")
+        order = self.groups[self.screen_set[a[self.active_order]]]
+        c(np.array_equal(order, np.sort(order)), "check active_order orders active_set such that groups is ordered")
+        B = self.betas
+        c(B.shape[0] <= self.lmda_path.shape[0], "check betas rows is no more than the number of lmda_path")
+        c(isinstance(B, scipy.sparse.csr_matrix), "check betas type")
+        c(B.shape[1] == self._p_cols, "check betas shape")
+        c(self.rsqs.shape == (B.shape[0],), "check rsqs shape")
+        c(np.all(self.rsqs >= 0), "check rsqs is non-negative")
+        c(self.lmdas.shape == (B.shape[0],), "check lmdas shape")
+        c(self.resid.shape[0] == self._X.rows(), "check resid shape")
+
+
+def gaussian_pin_naive(*, X, y_mean, y_var, constraints, groups, alpha, penalty, weights, screen_set, lmda_path, rsq, resid, screen_beta,
+                       screen_is_active, active_set_size, active_set, intercept=True, max_active_size=None, max_iters=int(1e5), tol=1e-7,
+                       adev_tol=0.9, ddev_tol=0, newton_tol=1e-12, newton_max_iters=1000, n_threads=1):
+    """Gaussian pin naive-method state (adelie/state.py:421-720; core StateGaussianPinNaive{32,64}).  As in the reference wrapper the
+    column means come from one ``X.mul`` pass; the screen groups' Grams and eigendecompositions are computed on the device when the
+    core state is built; ``tol`` is used unscaled (the path driver passes ``tol * y_var``, solver_gaussian_naive.hpp:314)."""
+    _check_constraints(constraints)
+    if not isinstance(X, _matrix.MatrixNaiveBase):
+        raise ValueError("X must be an instance of MatrixNaiveBase32 or MatrixNaiveBase64.")
+    dtype = X.dtype
+    n, p = X.rows(), X.cols()
+    groups = np.asarray(groups)
+    G = groups.shape[0]
+    group_sizes = np.concatenate([groups, [p]], dtype=int)
+    group_sizes = group_sizes[1:] - group_sizes[:-1]
+    weights = np.array(weights, copy=True, dtype=dtype)
+    glm_obj = _glm.gaussian(y=np.zeros(n, dtype=dtype), weights=weights, dtype=dtype)     # carrier of the weights only (the pin state has no y)
+    X_means = np.empty(p, dtype=dtype)
+    X.mul(np.ones(n, dtype=dtype), glm_obj.weights, X_means)
+    X_means = np.asarray(_dist_sum(X_means), dtype=dtype)
+    resid = np.array(resid, copy=True, dtype=dtype)
+    arrays = _common_arrays(groups=groups, group_sizes=group_sizes, penalty=penalty, lmda_path=np.array(lmda_path, copy=True, dtype=dtype),
+                            screen_set=screen_set, screen_beta=screen_beta, screen_is_active=screen_is_active, active_set=active_set,
+                            grad=np.zeros(p, dtype=dtype), resid=resid, dtype=dtype)
+    arrays["weights"] = glm_obj.weights
+    arrays["X_means"] = X_means
+    arrays["offsets"] = np.zeros(n, dtype=dtype)
+    max_active_size = G if max_active_size is None else int(np.minimum(max_active_size, G))
+    cfg = dict(alpha=float(alpha), y_mean=float(y_mean), y_var=float(y_var), resid_sum=float(_dist_sum(np.sum(glm_obj.weights * resid))),
+               rsq=float(rsq), lmda_max=-1.0, min_ratio=1e-2, lmda_path_size=len(arrays["lmda_path"]), setup_lmda_max=False,
+               setup_lmda_path=False, max_screen_size=G, max_active_size=max_active_size, pivot_subset_ratio=0.1, pivot_subset_min=1,
+               pivot_slack_ratio=1.25, screen_rule="pivot", max_iters=int(max_iters), tol=tol, adev_tol=adev_tol, ddev_tol=ddev_tol,
+               newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=False, intercept=intercept,
+               n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float("inf"))
+    return _Pin(X=X, glm_obj=glm_obj, use_glm=False, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=p)

@@ -188,16 +188,14 @@ int ab_state_get_betas(const ab_state* s, int64_t* indptr, int64_t* indices, dou
 /* screen_transforms[i] (row-major gs x gs) */
 int ab_state_get_screen_transform(const ab_state* s, int64_t i, double* out, int64_t cap, int64_t* len);
 
-/* ---- pin state in isolation: adelie/src/py_state.cpp StateGaussianPinNaive, solve = solver_gaussian_pin_naive.hpp:223-401 */
-typedef struct ab_pin_args {
-    int32_t dtype; double y_mean, y_var;
-    const int64_t* groups; const int64_t* group_sizes; int64_t G; double alpha; const void* penalty; const void* weights;
-    const int64_t* screen_set; int64_t S; const void* lmda_path; int64_t L;
-    int32_t intercept; int64_t max_active_size, max_iters; double tol, adev_tol, ddev_tol, newton_tol; int64_t newton_max_iters;
-    double rsq; void* resid; double resid_sum;                                            /* in/out (host) */
-    void* screen_beta; int8_t* screen_is_active; int64_t active_set_size; int64_t* active_set;   /* in/out (host) */
-} ab_pin_args;
-int ab_pin_naive_solve(ab_matrix* X, ab_pin_args* args, ab_state** out, char* err, size_t errlen);
+/* ---- pin state in isolation: StateGaussianPinNaive{32,64} (adelie/src/py_state.cpp:389-411; adelie/state.py:421-720), solve =
+ *      pin::naive::solve (adelie_core/solver/solver_gaussian_pin_naive.hpp:223-401).  The state is an ab_state created by
+ *      ab_state_create with glm == NULL: screen_set / screen_beta / screen_is_active / active_set / resid / rsq / resid_sum are the
+ *      pin state's inputs, lmda_path the lambdas to solve (setup_lmda_max = setup_lmda_path = 0), `tol` is used unscaled, `grad`
+ *      is ignored (zeros).  Solves every lambda of lmda_path on the FIXED screen set; outputs through the ab_state getters
+ *      ("betas", "intercepts", "rsqs", "lmdas", "screen_beta", "screen_is_active", "active_set", "resid", "rsq", "resid_sum",
+ *      "n_sweeps" = iters, "benchmark_fit_screen" / "benchmark_fit_active" = benchmark_screen / benchmark_active). */
+int ab_pin_naive_solve(ab_state* s, int (*check_signals)(void), char* err, size_t errlen, double* total_time);
 
 /* ---- bcd prox: adelie/src/py_bcd.cpp:15-243 (double only, like the reference) --------------- */
 /* solver: 0 newton, 1 newton_abs */

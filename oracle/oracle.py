@@ -141,7 +141,7 @@ def set_config(name, value):
 # --------------------------------------------------------------------------
 _VEC_NAMES = ["lmda_path", "lmdas", "devs", "intercepts", "screen_beta", "grad", "abs_grad", "resid", "eta",
               "screen_vars", "screen_X_means", "benchmark_screen", "benchmark_fit_screen", "benchmark_fit_active",
-              "benchmark_kkt", "benchmark_invariance", "rsqs", "screen_grad", "benchmark_active"]
+              "benchmark_kkt", "benchmark_invariance", "rsqs", "screen_grad", "benchmark_active", "screen_transforms_flat"]
 _IVEC_NAMES = ["screen_set", "screen_begins", "screen_is_active", "active_set", "n_valid_solutions", "active_sizes",
                "screen_sizes"]
 _SCALAR_NAMES = ["total_time", "lmda_max", "lmda", "rsq", "resid_sum", "y_mean", "y_var", "loss_null", "loss_full", "beta0",

@@ -173,6 +173,7 @@ void run_path(const orc_path_args* a, Result& R) {
     R.vecs["intercepts"] = to_d<T>(s.intercepts); R.vecs["screen_beta"] = to_d<T>(s.screen_beta);
     R.vecs["grad"] = to_d<T>(s.grad); R.vecs["abs_grad"] = to_d<T>(s.abs_grad); R.vecs["resid"] = to_d<T>(s.resid);
     R.vecs["eta"] = to_d<T>(s.eta); R.vecs["screen_vars"] = to_d<T>(s.screen_vars); R.vecs["screen_X_means"] = to_d<T>(s.screen_X_means);
+    { std::vector<double> flat; for (const auto& V : s.screen_transforms) flat.insert(flat.end(), V.begin(), V.end()); R.vecs["screen_transforms_flat"] = flat; }
     R.vecs["benchmark_screen"] = s.benchmark_screen; R.vecs["benchmark_fit_screen"] = s.benchmark_fit_screen;
     R.vecs["benchmark_fit_active"] = s.benchmark_fit_active; R.vecs["benchmark_kkt"] = s.benchmark_kkt;
     R.vecs["benchmark_invariance"] = s.benchmark_invariance;
@@ -221,6 +222,7 @@ void run_pin(orc_pin_args* a, Result& R) {
     R.scalars["active_set_size"] = (double)ps.active_set_size; R.scalars["n_group_updates"] = (double)ps.n_group_updates;
     R.vecs["rsqs"] = to_d<T>(ps.rsqs); R.vecs["lmdas"] = to_d<T>(ps.lmdas); R.vecs["intercepts"] = to_d<T>(ps.intercepts);
     R.vecs["screen_grad"] = to_d<T>(ps.screen_grad); R.vecs["screen_vars"] = to_d<T>(s.screen_vars); R.vecs["screen_X_means"] = to_d<T>(s.screen_X_means);
+    { std::vector<double> flat; for (const auto& V : s.screen_transforms) flat.insert(flat.end(), V.begin(), V.end()); R.vecs["screen_transforms_flat"] = flat; }
     R.vecs["benchmark_screen"] = ps.benchmark_screen; R.vecs["benchmark_active"] = ps.benchmark_active;
     R.ivecs["screen_begins"] = std::vector<int64_t>(s.screen_begins.begin(), s.screen_begins.end());
     R.indptr.push_back(0);

@@ -1,6 +1,8 @@
-"""Multi-GPU parity check (run under torchrun with >= 2 ranks on one box):
-every rank first solves the FULL problem on its own GPU (single-GPU mode), then the ranks solve the row-sharded problem together;
-the sharded path must reproduce the single-GPU path on every rank.  Prints 'DIST PASS' on rank 0."""
+"""Multi-GPU parity check (run under torchrun with >= 2 ranks on one box; driven by tests/test_gpu_dist.py):
+every rank first solves the FULL problem on its own GPU (single-GPU mode) and rank 0 also solves it with the CPU oracle; then the
+ranks solve the row-sharded problem together, once per kernel / exchange setting (batched look-ahead kernel, per-group kernel, one-hop
+atomic exchange, two-level flagged-line exchange).  The sharded path must reproduce the single-GPU path AND the oracle on every rank,
+bit-identically across ranks.  Prints 'DIST PASS' on rank 0."""
 import os
 import sys
 
@@ -97,27 +99,47 @@ def main():
         mk = (lambda yy: ad.glm.gaussian(yy, dtype=dtype)) if glm_name == "gaussian" else (lambda yy: ad.glm.binomial(yy, dtype=dtype))
         common = dict(groups=data["groups"], penalty=data["penalty"].astype(dtype), early_exit=False, lmda_path_size=12, min_ratio=0.1,
                       progress_bar=False, **kw)
-        results.append((n, p, glm_name, dtype, X, y, mk, common, ad.grpnet(X, mk(y), **common)))
+        oracle_B = None
+        if rank == 0:
+            from oracle import oracle as orc
+            okw = dict(common); okw.pop("progress_bar")
+            ref = orc.grpnet(X, orc.glm_spec(glm_name, y, dtype=dtype), **okw)
+            assert ref.error == "", ref.error
+            oracle_B = np.asarray(ref.betas.todense())
+        results.append((n, p, glm_name, dtype, X, y, mk, common, ad.grpnet(X, mk(y), **common), oracle_B))
     prepare_extra()
     ad.dist.init()
     assert ad.dist.is_active() and ad.dist.world() == world
     ok = True
-    for (n, p, glm_name, dtype, X, y, mk, common, single) in results:
-        lo, hi = ad.dist.shard_rows(n)
-        st = ad.grpnet(np.asfortranarray(X[lo:hi]), mk(y[lo:hi]), **common)
-        assert st.error == "" and single.error == "", (st.error, single.error)
-        B, Bs = np.asarray(st.betas.todense()), np.asarray(single.betas.todense())
-        rel = np.max(np.abs(B - Bs)) / np.max(np.abs(Bs))
-        reli = np.max(np.abs(st.intercepts - single.intercepts)) / max(1e-300, np.max(np.abs(single.intercepts)))
-        tol = 1e-6 if dtype == np.float64 else 1e-4
-        good = (len(st.lmdas) == len(single.lmdas)) and rel < tol and reli < tol and np.allclose(st.devs, single.devs, rtol=10 * tol, atol=10 * tol)
-        # every rank must hold the identical solution
-        blob = [None] * world
-        td.all_gather_object(blob, B.tobytes())
-        same = all(b == blob[0] for b in blob)
-        if rank == 0:
-            print(f"n={n} p={p} {glm_name} {np.dtype(dtype).name}: rows[{lo},{hi}) rel_beta={rel:.2e} rel_icpt={reli:.2e} identical_on_all_ranks={same} ncta={st.sweep_ncta} batch={st.sweep_batch} batched_launches={st.n_batched_launches} -> {'ok' if good and same else 'FAIL'}", flush=True)
-        ok = ok and good and same
+    # kernel / exchange settings: defaults (batched look-ahead kernel where it applies, one-hop atomic exchange), the two-level
+    # flagged-line exchange, and the per-group kernel forced
+    for setting in [dict(), dict(sweep_xchg=0), dict(sweep_batch=1), dict(sweep_batch=1, sweep_xchg=0)]:
+        for k, v in setting.items():
+            ad.set_configs(k, v)
+        for (n, p, glm_name, dtype, X, y, mk, common, single, oracle_B) in results:
+            lo, hi = ad.dist.shard_rows(n)
+            st = ad.grpnet(np.asfortranarray(X[lo:hi]), mk(y[lo:hi]), **common)
+            assert st.error == "" and single.error == "", (st.error, single.error)
+            B, Bs = np.asarray(st.betas.todense()), np.asarray(single.betas.todense())
+            rel = np.max(np.abs(B - Bs)) / np.max(np.abs(Bs))
+            reli = np.max(np.abs(st.intercepts - single.intercepts)) / max(1e-300, np.max(np.abs(single.intercepts)))
+            tol = 1e-6 if dtype == np.float64 else 1e-4
+            good = (len(st.lmdas) == len(single.lmdas)) and rel < tol and reli < tol and np.allclose(st.devs, single.devs, rtol=10 * tol, atol=10 * tol)
+            relo = -1.0
+            if rank == 0:
+                relo = np.max(np.abs(B - oracle_B)) / np.max(np.abs(oracle_B))
+                good = good and relo < tol
+            # every rank must hold the identical solution
+            blob = [None] * world
+            td.all_gather_object(blob, B.tobytes())
+            same = all(b == blob[0] for b in blob)
+            if rank == 0:
+                print(f"{setting or 'defaults'} n={n} p={p} {glm_name} {np.dtype(dtype).name}: rows[{lo},{hi}) rel_beta_vs_1gpu={rel:.2e} rel_beta_vs_oracle={relo:.2e} rel_icpt={reli:.2e} identical_on_all_ranks={same} ncta={st.sweep_ncta} batch={st.sweep_batch} batched_launches={st.n_batched_launches} -> {'ok' if good and same else 'FAIL'}", flush=True)
+            flag = [None] * world
+            td.all_gather_object(flag, bool(good and same))
+            ok = ok and all(flag)
+        for k in setting:
+            ad.set_configs(k, None)
     ok = extra_checks(rank, world) and ok
     if rank == 0:
         print("DIST PASS" if ok else "DIST FAIL", flush=True)
