@@ -91,6 +91,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "sweep_batch") Configs::sweep_batch = (int)value;
     else if (s == "sweep_xchg") Configs::sweep_xchg = (int)value;
     else if (s == "panel_gemm") Configs::panel_gemm = (int)value;
+    else if (s == "panel_tc") Configs::panel_tc = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -110,6 +111,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "sweep_batch") *value = Configs::sweep_batch;
     else if (s == "sweep_xchg") *value = Configs::sweep_xchg;
     else if (s == "panel_gemm") *value = Configs::panel_gemm;
+    else if (s == "panel_tc") *value = Configs::panel_tc;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -663,6 +665,21 @@ int ab_matrix_mul(ab_matrix* m, const void* v, const void* w, void* out) {
     AB_TRY
     if (m->dtype == AB_F32) HostOps<float>::mul(*m->f32, (const float*)v, (const float*)w, (float*)out);
     else HostOps<double>::mul(*m->f64, (const double*)v, (const double*)w, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_window_gram(ab_matrix* m, const int32_t* cols, int ncol, int n_src, const void* w, int use_tc, double* out) {
+    AB_TRY
+    if (m->dtype != AB_F32 || m->f32->sparse) throw core_error("window_gram() needs a dense float32 matrix.");
+    if (ncol < 1 || ncol > 128 || n_src < 1 || n_src > 64 || n_src > ncol) throw core_error("window_gram() is given inconsistent inputs!");
+    auto& X = *m->f32;
+    PanelItem it{}; it.q_off = 0; it.ncol = ncol; it.n_src = n_src;
+    for (int c = 0; c < ncol; ++c) { if (cols[c] < 0 || cols[c] >= X.p) throw core_error("window_gram(): column out of range."); it.cols[c] = X.phys_col(cols[c], 1); }
+    DevBuf<PanelItem> d_it(1); d_it.upload(&it, 1);
+    DevBuf<float> d_w(X.ld); d_w.upload((const float*)w, X.n);
+    std::vector<double> tmp(kPanelOut);
+    X.d_panel_gram(d_it.p, 1, d_w.p, nullptr, 0, 0, use_tc, tmp.data());
+    X.check_tc_error();
+    for (int s_ = 0; s_ < n_src; ++s_) for (int u = 0; u < ncol; ++u) out[(size_t)s_ * ncol + u] = tmp[(size_t)s_ * 128 + u];
     AB_CATCH
 }
 int ab_matrix_cov(ab_matrix* m, int64_t j, int64_t q, const void* sqrt_w, void* out) {

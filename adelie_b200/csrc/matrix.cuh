@@ -438,25 +438,44 @@ struct DenseMatrix {
         AB_CUDA(cudaGetLastError());
     }
 
-    // Whole Gram panels in one pass per panel (panel_gram_kernel, fp32 dense columns): tmp must hold n_items * kPanelOut doubles
-    DevBuf<double> panel_tmp;
-    void d_panel_gram(const PanelItem* items_dev, int n_items, const float* w, float* Q, int ldq, int Ccap) {
+    // Whole Gram panels in one pass per panel (fp32 dense columns): panel_gram_tc_kernel on the tensor cores (tcgen05, TF32 operands,
+    // Configs::panel_tc) or panel_gram_kernel on the CUDA cores; panel_tmp holds n_items * kPanelOut doubles.
+    DevBuf<double> panel_tmp; DevBuf<float> part_f; DevBuf<int> tc_err;
+    void d_panel_gram(const PanelItem* items_dev, int n_items, const float* w, float* Q, int ldq, int Ccap, int use_tc = -1, double* tmp_out = nullptr) {
         if (n_items <= 0) return;
+        if (use_tc < 0) use_tc = Configs::panel_tc;
         const int sms = DeviceInfo::get().sm_count;
         int n_rb = std::max(1, std::min(sms, (2 * sms + n_items - 1) / n_items));
         int rows_per_block = (int)((ld + n_rb - 1) / n_rb);
         rows_per_block = (rows_per_block + kPanelRows - 1) / kPanelRows * kPanelRows;
         n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
-        part.reserve_keep((size_t)n_rb * n_items * kPanelOut, stream);
         panel_tmp.reserve_keep((size_t)n_items * kPanelOut, stream);
-        const size_t smem = sizeof(float) * (128 * kPanelStride + kPanelRows);
-        AB_CUDA(cudaFuncSetAttribute(panel_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        panel_gram_kernel<<<dim3(n_items, n_rb), 256, smem, stream>>>((const float*)X, ld, ld, items_dev, w, part.p, n_items, rows_per_block);
-        panel_gram_sum_kernel<<<n_items, 256, 0, stream>>>(items_dev, part.p, n_rb, n_items, panel_tmp.p);
+        if (use_tc) {
+            static_assert(kTcKC == kPanelRows, "row blocks are cut in chunks of kTcKC rows");
+            part_f.reserve_keep((size_t)n_rb * n_items * kPanelOut, stream);
+            if (!tc_err.n) tc_err.alloc(1);
+            AB_CUDA(cudaFuncSetAttribute(panel_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
+            panel_gram_tc_kernel<<<dim3(n_items, n_rb), kTcThreads, kTcSmemBytes, stream>>>((const float*)X, ld, ld, items_dev, w, part_f.p, n_items,
+                                                                                        rows_per_block, tc_err.p);
+            panel_gram_sum_kernel<float><<<n_items, 256, 0, stream>>>(items_dev, part_f.p, n_rb, n_items, panel_tmp.p);
+        } else {
+            part.reserve_keep((size_t)n_rb * n_items * kPanelOut, stream);
+            const size_t smem = sizeof(float) * (128 * kPanelStride + kPanelRows);
+            AB_CUDA(cudaFuncSetAttribute(panel_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            panel_gram_kernel<<<dim3(n_items, n_rb), 256, smem, stream>>>((const float*)X, ld, ld, items_dev, w, part.p, n_items, rows_per_block);
+            panel_gram_sum_kernel<double><<<n_items, 256, 0, stream>>>(items_dev, part.p, n_rb, n_items, panel_tmp.p);
+        }
         DistContext& dc = DistContext::get();
         if (dc.active()) dc.allreduce<double>(panel_tmp.p, (int64_t)n_items * kPanelOut, stream);      // row-sharded: sum the local panels over the ranks
-        panel_gram_scatter_kernel<float><<<n_items, 256, 0, stream>>>(items_dev, panel_tmp.p, Q, ldq, Ccap);
+        if (Q) panel_gram_scatter_kernel<float><<<n_items, 256, 0, stream>>>(items_dev, panel_tmp.p, Q, ldq, Ccap);
         AB_CUDA(cudaGetLastError());
+        if (tmp_out) { AB_CUDA(cudaMemcpyAsync(tmp_out, panel_tmp.p, sizeof(double) * (size_t)n_items * kPanelOut, cudaMemcpyDeviceToHost, stream)); AB_CUDA(cudaStreamSynchronize(stream)); }
+    }
+    // the tensor-core kernel bounds every wait and raises this flag instead of hanging; checked at the caller's next synchronisation
+    void check_tc_error() {
+        if (!tc_err.n) return;
+        int e = 0; tc_err.download(&e, 1); AB_CUDA(cudaStreamSynchronize(stream));
+        if (e) { int z = 0; tc_err.upload(&z, 1); throw solver_error("tensor-core Gram kernel timed out (pipeline protocol error)."); }
     }
 
     // The batched look-ahead pin solve (sweep_batched.cuh); single response, single GPU, static weights.

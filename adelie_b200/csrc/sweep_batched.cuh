@@ -25,6 +25,7 @@
 // latency-critical control warp does not compete with the data warps for issue slots.
 #pragma once
 #include "sweep.cuh"
+#include "gram_tc.cuh"
 #include <type_traits>
 
 namespace ab {
@@ -1136,10 +1137,9 @@ __global__ void pair_gram_finalize_kernel(const PairItem* __restrict__ items, co
 // a 4 x 8 tile of the 64 x 128 block (sources ty + 16 a, targets tx + 16 b) and reads 4 + 8 + 1 vectors per 128 FMAs.  Every column of
 // the window is read from HBM once per panel instead of once per (source group, target group) block: pair_gram_kernel moved
 // ~17 000 blocks x 16 MB per config-2 path.  Partial sums: fp32 inside a chunk, double across chunks and row blocks (deterministic).
-struct PanelItem { int64_t q_off; int32_t ncol, n_src; int32_t cols[128]; };
+// (PanelItem and kPanelOut live in gram_tc.cuh, shared with the tensor-core version of this kernel)
 constexpr int kPanelRows = 64;                 // rows per staged chunk
 constexpr int kPanelStride = kPanelRows + 4;   // shared-memory row stride of a column (floats)
-constexpr int kPanelOut = 64 * 128;            // compact outputs per panel: [source][window column]
 
 __global__ void __launch_bounds__(256)
 panel_gram_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, const PanelItem* __restrict__ items, const float* __restrict__ w,
@@ -1211,13 +1211,14 @@ panel_gram_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, const 
 }
 
 // out: tmp[panel * kPanelOut + s * 128 + u] = sum over row blocks
-__global__ void panel_gram_sum_kernel(const PanelItem* __restrict__ items, const double* __restrict__ part, int n_rb, int n_panels, double* __restrict__ tmp)
+template <class P>
+__global__ void panel_gram_sum_kernel(const PanelItem* __restrict__ items, const P* __restrict__ part, int n_rb, int n_panels, double* __restrict__ tmp)
 {
     const PanelItem& it = items[blockIdx.x];
     for (int e = threadIdx.x; e < it.n_src * 128; e += blockDim.x) {
         if ((e & 127) >= it.ncol) continue;
         double s_ = 0;
-        for (int rb = 0; rb < n_rb; ++rb) s_ += part[((size_t)rb * n_panels + blockIdx.x) * kPanelOut + e];
+        for (int rb = 0; rb < n_rb; ++rb) s_ += (double)part[((size_t)rb * n_panels + blockIdx.x) * kPanelOut + e];
         tmp[(size_t)blockIdx.x * kPanelOut + e] = s_;
     }
 }

@@ -122,6 +122,11 @@ int ab_matrix_ctmul(ab_matrix* m, int64_t j, double v, void* out);              
 int ab_matrix_bmul(ab_matrix* m, int64_t j, int64_t q, const void* v, const void* w, void* out);        /* X[:,j:j+q]^T (v*w) */
 int ab_matrix_btmul(ab_matrix* m, int64_t j, int64_t q, const void* v, void* out);                      /* out += X[:,j:j+q] v */
 int ab_matrix_mul(ab_matrix* m, const void* v, const void* w, void* out);                               /* X^T (v*w) */
+/* Weighted Gram of a window of columns, out[s * ncol + u] = sum_i w_i X[i, cols[s]] X[i, cols[u]] for s < n_src <= 64, u < ncol <= 128
+ * (row-major n_src x ncol, double): the Gram-panel kernel of the batched sweep exposed for parity tests.  Generalises cov()
+ * (matrix_naive_base.hpp:101-105) to a column list.  use_tc = 1: tcgen05 tensor cores with TF32 operands, 0: fp32 CUDA cores.
+ * Dense float32 matrices only. */
+int ab_matrix_window_gram(ab_matrix* m, const int32_t* cols, int ncol, int n_src, const void* w, int use_tc, double* out);
 int ab_matrix_cov(ab_matrix* m, int64_t j, int64_t q, const void* sqrt_w, void* out /* q*q col-major */);
 int ab_matrix_sq_mul(ab_matrix* m, const void* w, void* out);                                           /* (X*X)^T w */
 /* out (L x n, row-major) = v (L x p CSR) X^T : adelie/src/py_matrix.cpp sp_tmul */
