@@ -118,20 +118,24 @@ inline BatchGeometry plan_batched(int64_t n_pad, int gs_max, int rec_max) {
         g.rec_stride = (gs_max <= 12) ? 3 * gsp + 2 * gs_max * gsp : (rec_max + 3) / 4 * 4;
     }
     // a group is streamed in ring items of at most ch columns (two items per group once groups have more than 4 columns): more,
-    // smaller stages keep both the HBM stream of the next batch and the L2 re-reads of the residual updates in flight
-    g.ch = (gs_max > 4) ? (gs_max + 1) / 2 : gs_max;
-    g.stage_elems = (g.rows_stride * g.ch + 31) / 32 * 32;
+    // smaller stages keep both the HBM stream of the next batch and the L2 re-reads of the residual updates in flight.  When a CTA
+    // owns many rows (few GPUs for a tall matrix: n = 1M on 2 GPUs is 3.4k rows per CTA) the default item does not fit the ring
+    // any more: the item is narrowed (down to 2 columns) before the batch is shortened.
+    const int ch0 = (gs_max > 4) ? (gs_max + 1) / 2 : gs_max;
     const int want = Configs::sweep_batch > 1 ? Configs::sweep_batch : 6;
-    for (int B = std::min(std::min(want, kBatchMax), kBatchColsMax / gs_max); B >= 2; --B) {
+    for (int B = std::min(std::min(want, kBatchMax), kBatchColsMax / gs_max); B >= 2 && !g.ok; --B) {
         const int Ccap = (B * gs_max + 3) / 4 * 4;
         const int pslot = Ccap * 2 * Ccap + B * g.rec_stride;
         const size_t fixed = BatchSmem<T>::fixed_bytes(Ccap) + sizeof(T) * (2 * (size_t)g.rows_stride + 2 * (size_t)pslot);
         if (fixed >= di.smem_optin) continue;
-        const int ns = (int)std::min<size_t>(kBatchStages, (di.smem_optin - fixed) / (sizeof(T) * (size_t)g.stage_elems));
-        if (ns < 3) continue;
-        g.ok = true; g.B = B; g.Ccap = Ccap; g.pslot_elems = pslot; g.n_stages = ns;
-        g.smem_bytes = fixed + sizeof(T) * (size_t)ns * g.stage_elems;
-        break;
+        for (int ch = ch0; ch >= std::min(ch0, 2); --ch) {
+            const int stage_elems = (g.rows_stride * ch + 31) / 32 * 32;
+            const int ns = (int)std::min<size_t>(kBatchStages, (di.smem_optin - fixed) / (sizeof(T) * (size_t)stage_elems));
+            if (ns < (ch == ch0 ? 3 : 4)) continue;
+            g.ok = true; g.B = B; g.Ccap = Ccap; g.pslot_elems = pslot; g.n_stages = ns; g.ch = ch; g.stage_elems = stage_elems;
+            g.smem_bytes = fixed + sizeof(T) * (size_t)ns * stage_elems;
+            break;
+        }
     }
     return g;
 }

@@ -493,7 +493,7 @@ struct PathState {
     // Panel b of a list holds, for every source column of batch b, X_src^T W X_t against the later groups of batch b
     // (targets [0, Ccap)) and all groups of batch b+1 (targets [Ccap, 2 Ccap)).  Lists only ever grow at the tail, so only the
     // panels from the batch before the first new position onwards are (re)computed.
-    void ensure_panels(PanelList& pl, const std::vector<int32_t>& entries, int B, int Ccap, const T* d_w) {
+    void ensure_panels(PanelList& pl, const std::vector<int32_t>& entries, int B, int Ccap, const T* d_w, bool whole_panels = false) {
         if (pl.B != B || pl.Ccap != Ccap) { pl.entries.clear(); pl.B = B; pl.Ccap = Ccap; }
         size_t prev = 0;
         while (prev < pl.entries.size() && prev < entries.size() && pl.entries[prev] == entries[prev]) ++prev;
@@ -537,7 +537,8 @@ struct PathState {
         if constexpr (std::is_same<T, float>::value) {
             // Whole panels pay off when many blocks are new at once (a block costs ~5 us in pair_gram_kernel, a whole panel ~90 us
             // + ~40 us of fixed cost): the usual incremental call (a few new groups at the tail) stays on the per-block kernel.
-            if (Configs::panel_gemm && !X->sparse && (double)items.size() * 5.0 > (double)(nb - b0) * 90.0 + 40.0) {
+            // IRLS (whole_panels): the weights changed, every panel of the list is rebuilt -- one tensor-core pass per panel.
+            if (!X->sparse && (whole_panels || (Configs::panel_gemm && (double)items.size() * 5.0 > (double)(nb - b0) * 90.0 + 40.0))) {
                 // whole panels b0 .. nb-1 in one pass each (panel_gram_kernel): every window column is read once per panel
                 std::vector<PanelItem> pitems;
                 for (size_t b = b0; b < nb; ++b) {
@@ -557,6 +558,7 @@ struct PathState {
                     d_panel_items.upload(pitems.data(), pitems.size());
                     X->d_panel_gram(d_panel_items.p, (int)pitems.size(), d_w, pl.Q.p, ldq, Ccap);
                     AB_CUDA(cudaStreamSynchronize(0));          // `pitems` (pageable host memory) must outlive the upload
+                    X->check_tc_error();
                     n_kernel_launches += 3;
                 }
                 n_panels_built += (long long)(nb - b0);
@@ -579,18 +581,26 @@ struct PathState {
 
     // ------------------------------------------------------------------ the fused pin solve
     // Runs pin::naive::solve (solver_gaussian_pin_naive.hpp:223-401) for one lambda on the device.
-    PinResult run_pin(T* d_r, const T* d_w, T lmda_, T tol_pin, T y_mean_, T& rsq_io, T& resid_sum_io, bool static_weights = false) {
+    // static_weights: the Gaussian path (weights fixed, panels extended incrementally).  Otherwise (IRLS) the batched kernel is used when
+    // Configs::glm_batched allows it, with every Gram panel rebuilt for the weights of this IRLS iteration; `transforms` are the screen
+    // groups' eigenvector matrices that belong to `d_w` (the state's own on the Gaussian path, the IRLS iteration's on the GLM path).
+    PinResult run_pin(T* d_r, const T* d_w, T lmda_, T tol_pin, T y_mean_, T& rsq_io, T& resid_sum_io, bool static_weights = false,
+                      const std::vector<std::vector<T>>* transforms = nullptr) {
         AB_TIME(timers, "run_pin");
+        if (!transforms) transforms = &screen_transforms;
+        const bool glm_batched = !static_weights && K == 1 && !X->sparse &&
+                                 (Configs::glm_batched >= 2 || (Configs::glm_batched == 1 && std::is_same<T, float>::value));
+        const bool want_batched = (static_weights || glm_batched) && K == 1 && !X->sparse;
         const size_t S = screen_set.size();
         d_screen_beta.reserve_keep(screen_beta.size() + 4); d_is_active.reserve_keep(S + 4);
         d_screen_beta.upload(screen_beta.data(), screen_beta.size());
         d_is_active.upload(screen_is_active.data(), S);
         // coefficients in every group's eigenbasis (a V): the batched kernel keeps them up to date instead of rotating per visit
         std::vector<T> beta_rot(screen_beta.size(), T(0));
-        if (static_weights && K == 1) {
-            for (size_t i = 0; i < S && i < screen_transforms.size(); ++i) {
+        if (want_batched) {
+            for (size_t i = 0; i < S && i < transforms->size(); ++i) {
                 const int gs = (int)group_sizes[screen_set[i]]; const idx_t sb = screen_begins[i];
-                const std::vector<T>& V = screen_transforms[i];
+                const std::vector<T>& V = (*transforms)[i];
                 for (int c = 0; c < gs; ++c) {
                     double acc = 0;
                     for (int r = 0; r < gs; ++r) acc += (double)screen_beta[sb + r] * (double)V[(size_t)r * gs + c];
@@ -619,7 +629,9 @@ struct PathState {
         const size_t old_active = active_set_size;
         float ms = 0;
         BatchGeometry bg{};
-        if (static_weights && K == 1 && !X->sparse) bg = plan_batched<T>(X->n_pad(), gs_max_screen, rec_max_screen);
+        if (want_batched) bg = plan_batched<T>(X->n_pad(), gs_max_screen, rec_max_screen);
+        const bool whole = !static_weights && std::is_same<T, float>::value;        // IRLS: all panels are rebuilt, whole-panel (tensor-core) passes
+        if (bg.ok && !static_weights) { pl_screen.entries.clear(); pl_active.entries.clear(); }
         if (!bg.ok) {
             AB_CUDA(cudaEventRecord(ev0, 0));
             X->pin_solve(L);
@@ -635,14 +647,14 @@ struct PathState {
             std::vector<int32_t> ent(S);
             std::iota(ent.begin(), ent.end(), 0);
             { AB_TIME(timers, "pin_presync"); AB_CUDA(cudaStreamSynchronize(0)); }
-            ensure_panels(pl_screen, ent, bg.B, bg.Ccap, d_w);
+            ensure_panels(pl_screen, ent, bg.B, bg.Ccap, d_w, whole);
             BatchLaunch<T> bl{};
             bl.start_phase = kSweepActive; bl.beta_rot_in = d_screen_beta_rot.p;
             size_t act_now = active_set_size;
             double cols_seen = 0, sweeps_seen = 0;
             while (true) {
                 ent.assign(act32.begin(), act32.begin() + act_now);
-                ensure_panels(pl_active, ent, bg.B, bg.Ccap, d_w);
+                ensure_panels(pl_active, ent, bg.B, bg.Ccap, d_w, whole);
                 bl.panels_screen = pl_screen.Q.p; bl.panels_active = pl_active.Q.p; bl.n_active_panelled = (int)act_now;
                 { AB_TIME(timers, "pin_launch");
                   if (DistContext::get().active()) DistContext::get().allreduce<double>(d_scal.p, 1);    // rank barrier: the peers' exchange slots of the previous launch are free

@@ -171,7 +171,7 @@ PinResult PathState<T>::fit_glm(T lmda_) {
         T rsq_dummy = 0;
         PinResult pr;
         try {
-            pr = run_pin(d_irls_resid.p, d_irls_w.p, lmda_adj, tol * (loss_null - loss_full) / hess_sum, ym, rsq_dummy, rs);
+            pr = run_pin(d_irls_resid.p, d_irls_w.p, lmda_adj, tol * (loss_null - loss_full) / hess_sum, ym, rsq_dummy, rs, false, &stv);
         } catch (...) {
             screen_beta.swap(beta_prev); screen_is_active.swap(act_prev);
             throw;

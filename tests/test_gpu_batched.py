@@ -133,3 +133,90 @@ def test_full_grid_kkt_and_residual_invariants_fp32():
     r_dev = np.asarray(st.resid, dtype=np.float64)
     r_ref = yd - (yd @ w) - Xd @ B[-1]                        # the kernel's residual is centred by y_mean, intercept kept apart
     np.testing.assert_allclose(r_dev, r_ref, atol=5e-4 * np.max(np.abs(r_ref)))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# GLM / IRLS on the batched kernel: every Gram panel is rebuilt for the weights of each IRLS iteration (tensor-core panel kernel
+# for float32, TF32 operands).  The fixed point of the sweep does not depend on the panels' precision: paths must match the per-group
+# kernel (glm_batched = 0) and the oracle at the same tolerances as everything else.
+# ------------------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def _restore_glm_configs():
+    yield
+    for k in ("glm_batched", "panel_tc", "sweep_ctas", "sweep_batch"):
+        ad.set_configs(k, None)
+
+
+def _glm_problem(n, p, gs, dtype, seed):
+    rng = np.random.default_rng(seed)
+    X = np.asfortranarray(rng.normal(size=(n, p)), dtype=dtype)
+    beta = np.zeros(p); supp = rng.choice(p, max(1, p // 8), replace=False); beta[supp] = rng.normal(size=supp.size)
+    eta = X @ beta / np.linalg.norm(beta)
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-eta))).astype(dtype)
+    groups = np.arange(0, p, gs)
+    return X, y, groups
+
+
+@pytest.mark.parametrize("dtype,mode,tc,tol_k,tol_o", [(np.float64, 2, 0, 1e-8, 1e-6), (np.float32, 1, 1, 1e-4, 1e-4), (np.float32, 1, 0, 1e-4, 1e-4)])
+@pytest.mark.parametrize("n,p,gs,ctas", [(4096, 120, 10, 4), (3000, 64, 1, 2), (4000, 96, 6, 2)])
+def test_irls_on_the_batched_kernel_matches_per_group_kernel_and_oracle(_restore_glm_configs, dtype, mode, tc, tol_k, tol_o, n, p, gs, ctas):
+    X, y, groups = _glm_problem(n, p, gs, dtype, seed=n + gs)
+    f64 = dtype == np.float64
+    kw = dict(groups=groups, alpha=0.5, tol=1e-12 if f64 else 1e-7, irls_tol=1e-10 if f64 else 1e-7, newton_tol=1e-12 if f64 else 1e-6,
+              early_exit=False, lmda_path_size=10, min_ratio=0.1)
+    ad.set_configs("sweep_ctas", ctas)
+    ad.set_configs("glm_batched", 0)
+    ref = ad.grpnet(X, ad.glm.binomial(y, dtype=dtype), progress_bar=False, **kw)
+    ad.set_configs("glm_batched", mode); ad.set_configs("panel_tc", tc)
+    st = ad.grpnet(X, ad.glm.binomial(y, dtype=dtype), progress_bar=False, **kw)
+    assert ref.error == "" and st.error == "", (ref.error, st.error)
+    assert ref.n_batched_launches == 0 and st.n_batched_launches >= st.n_irls > 0, "IRLS did not run on the batched kernel"
+    B, Br = st.betas.toarray(), ref.betas.toarray()
+    assert _rel(B, Br) <= tol_k, _rel(B, Br)
+    o = orc.grpnet(X, orc.glm_spec("binomial", y, dtype=dtype), **kw)
+    assert o.error == ""
+    assert _rel(B, o.betas.toarray()) <= tol_o, _rel(B, o.betas.toarray())
+    assert _rel(np.asarray(st.intercepts), np.asarray(o.intercepts)) <= tol_o
+    np.testing.assert_allclose(st.devs, o.devs, rtol=10 * tol_o, atol=10 * tol_o)
+
+
+@pytest.mark.parametrize("family", ["gaussian", "binomial"])
+def test_full_grid_fp32_against_the_oracle(_restore_glm_configs, family):
+    """> 100 CTAs (one per SM), float32, compared with the ORACLE (not just properties): Gaussian on the incremental panels, binomial
+    on the per-IRLS-iteration tensor-core panels.  A short path keeps the CPU oracle at a few seconds."""
+    n, gs, G = 160_000, 10, 24
+    p = gs * G
+    rng = np.random.default_rng(21)
+    X = np.asfortranarray(rng.standard_normal((n, p), dtype=np.float32))
+    beta = np.zeros(p); beta[rng.choice(p, 30, replace=False)] = rng.normal(size=30)
+    eta = X @ beta
+    if family == "gaussian":
+        y = (eta + np.linalg.norm(beta) * rng.normal(size=n)).astype(np.float32)
+        mk, spec = ad.glm.gaussian, "gaussian"
+    else:
+        y = (rng.uniform(size=n) < 1 / (1 + np.exp(-eta / np.linalg.norm(beta)))).astype(np.float32)
+        mk, spec = ad.glm.binomial, "binomial"
+    kw = dict(groups=np.arange(0, p, gs), alpha=1.0 if family == "gaussian" else 0.5, tol=1e-7, irls_tol=1e-7, newton_tol=1e-6, early_exit=False,
+              lmda_path_size=8, min_ratio=0.2)
+    st = ad.grpnet(X, mk(y, dtype=np.float32), progress_bar=False, **kw)
+    assert st.error == "" and st.sweep_ncta > 100 and st.sweep_batch > 1 and st.n_batched_launches > 0
+    o = orc.grpnet(X, orc.glm_spec(spec, y, dtype=np.float32), n_threads=8, **kw)
+    assert o.error == ""
+    assert _rel(st.betas.toarray(), o.betas.toarray()) <= 1e-4
+    # the intercept is ~0 here (balanced classes): it is compared on the scale of the coefficients (both are linear-predictor units)
+    scale = max(np.max(np.abs(o.intercepts)), np.max(np.abs(o.betas.toarray())))
+    assert np.max(np.abs(np.asarray(st.intercepts) - np.asarray(o.intercepts))) <= 1e-4 * scale
+
+
+def test_tall_row_tiles_narrow_the_ring_items():
+    """3392 rows per CTA (n = 1M on 2 GPUs): the default 5-column ring item no longer fits shared memory next to the residual tile and
+    the panel slots; the planner narrows the item to 2 columns instead of falling back to the per-group kernel."""
+    sizes = [10] * 14
+    groups = _groups_from_sizes(sizes); p = int(np.sum(sizes))
+    X, y, pen = _problem(3392 * 2, p, groups, np.float32, seed=13)
+    ref = _solve(X, y, groups, pen, np.float32, batch=1, ctas=2)
+    st = _solve(X, y, groups, pen, np.float32, batch=0, ctas=2)
+    assert st.error == "" and st.sweep_batch > 1 and st.n_batched_launches > 0
+    assert _rel(st.betas.toarray(), ref.betas.toarray()) <= 5e-5
+    o = _solve(X, y, groups, pen, np.float32, batch=0, ctas=2, use_oracle=True)
+    assert _rel(st.betas.toarray(), o.betas.toarray()) <= 1e-4
