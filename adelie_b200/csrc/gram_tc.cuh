@@ -14,15 +14,17 @@
 // convergence.  TF32 operands (10-bit mantissa, round-to-nearest) are therefore exact enough: the fixed point of the sweep does not
 // depend on them.  The groups' own Gram blocks (eigen-decomposed for the proximal step) stay on the fp32/fp64 CUDA-core kernel.
 //
-// Warp roles (320 threads, one CTA per SM):
-//   warp 0      producer: cp.async.bulk (1-D TMA, one copy per window column + one for the weights) of 64-row chunks into a
-//               3-stage ring of raw column-major tiles, mbarrier complete_tx;
-//   warp 1      MMA issuer: one elected lane issues 8 x tcgen05.mma.cta_group::1.kind::tf32 (M = N = 128, K = 8) per chunk, A and B
+// Warp roles (544 threads, one CTA per SM):
+//   warp 0      MMA issuer: one elected lane issues 8 x tcgen05.mma.cta_group::1.kind::tf32 (M = N = 128, K = 8) per 64-row chunk, A and B
 //               descriptors pointing at the SAME shared-memory tile (K-major, 128-byte swizzle), tcgen05.commit on the tile's
 //               "empty" mbarrier; allocates / frees the 128 TMEM columns of the accumulator;
-//   warps 2-9   transform: scale the raw chunk by sqrt(w), round to TF32 and store it in the canonical UMMA K-major SWIZZLE_128B
-//               layout (8-column x 128-byte atoms, 16-byte chunks XOR-ed with the column index), two tile buffers;
-//               afterwards warps 2-5 read the accumulator back (tcgen05.ld 32x32b) and write the panel's rows.
+//   warps 1-16  loaders: 16-byte coalesced global loads of the chunk (two chunks ahead, in registers), scaled by sqrt(w), rounded to
+//               TF32 and stored in the canonical UMMA K-major SWIZZLE_128B layout (8-column x 128-byte atoms, 16-byte chunks XOR-ed
+//               with the column index) of one of four tile buffers; afterwards warps 1-4 read the accumulator back (tcgen05.ld
+//               32x32b) and write the panel's rows.
+// The first version staged the chunk through cp.async.bulk (one 256-byte copy per window column and chunk) and transformed it from
+// shared memory: 35 s of panel time per config-3 shard path (86 ms per IRLS iteration) -- the copy engine is made for few large copies,
+// not 120 small ones per 30 KB; the register path needs no staging buffer and leaves room for four tile buffers.
 // Every wait is bounded by %globaltimer: a protocol bug reports an error instead of hanging the GPU.
 #pragma once
 #include "device_prims.cuh"
@@ -35,12 +37,12 @@ struct PanelItem { int64_t q_off; int32_t ncol, n_src; int32_t cols[128]; };
 constexpr int kPanelOut = 64 * 128;            // compact outputs per panel: [source][window column]
 
 constexpr int kTcKC = 64;                        // rows per chunk (two 32-row = 128-byte K blocks)
-constexpr int kTcStages = 3;                     // raw ring stages
-constexpr int kTcXformWarps = 8;
-constexpr int kTcThreads = 64 + 32 * kTcXformWarps;
+constexpr int kTcNB = 4;                         // UMMA tile buffers
+constexpr int kTcLoadWarps = 16;
+constexpr int kTcThreads = 32 + 32 * kTcLoadWarps;
+constexpr int kTcNI = 128 * (kTcKC / 4) / (32 * kTcLoadWarps);     // 16-byte vectors per loader thread and chunk (4)
 constexpr int kTcTileBytes = 2 * 16384;          // one UMMA tile: 2 K blocks x (128 columns x 128 bytes)
-constexpr int kTcRawBytes = 128 * kTcKC * 4;     // one raw stage
-constexpr size_t kTcSmemBytes = 1024 + 2 * kTcTileBytes + kTcStages * (kTcRawBytes + kTcKC * 4) + 2 * kTcKC * 4 + 128 * 4 + 256;
+constexpr size_t kTcSmemBytes = 1024 + kTcNB * kTcTileBytes + 128 * 4 + 256;
 
 namespace tc {
 __device__ __forceinline__ bool wait_bounded(uint64_t* bar, uint32_t parity, volatile int* err) {
@@ -76,26 +78,19 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a_desc, uint6
 __device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
 }  // namespace tc
 
-// part[(rb * n_panels + panel) * 64 * 128 + s * 128 + u] = sum over the rows of block rb of w * X[:, cols[s]] * X[:, cols[u]]
+// part[(rb * n_panels + panel) * 64 * 128 + s * 128 + u] = sum over the rows of block rb of wsqrt^2 * X[:, cols[s]] * X[:, cols[u]]
 __global__ void __launch_bounds__(kTcThreads, 1)
-panel_gram_tc_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, const PanelItem* __restrict__ items, const float* __restrict__ w,
+panel_gram_tc_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, const PanelItem* __restrict__ items, const float* __restrict__ wsqrt,
                      float* __restrict__ part, int n_panels, int rows_per_block, int* __restrict__ err_flag)
 {
     extern __shared__ uint8_t tc_smem_raw[];
-    // carve: [tiles 2 x 32 KB, 1024-byte aligned][raw stages][w stages][sqrt(w) x 2][cols][barriers]
+    // carve: [tile buffers kTcNB x 32 KB, 1024-byte aligned][cols][barriers]
     const uint32_t base_u32 = dev::smem_u32(tc_smem_raw);
-    uint8_t* sm = tc_smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);
-    uint8_t* tiles = sm;
-    float* raw = reinterpret_cast<float*>(sm + 2 * kTcTileBytes);
-    float* wraw = raw + kTcStages * 128 * kTcKC;
-    float* wsq = wraw + kTcStages * kTcKC;                    // [2][kTcKC] sqrt(w) of the chunk being transformed (by tile buffer)
-    int* cols_s = reinterpret_cast<int*>(wsq + 2 * kTcKC);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cols_s + 128);
-    uint64_t* raw_full = bars;                                // [kTcStages] producer -> transform (complete_tx)
-    uint64_t* raw_empty = raw_full + kTcStages;               // [kTcStages] transform -> producer (one arrive per transform warp)
-    uint64_t* tile_full = raw_empty + kTcStages;              // [2] transform -> MMA (one arrive per transform warp)
-    uint64_t* tile_empty = tile_full + 2;                     // [2] MMA -> transform (tcgen05.commit)
-    uint64_t* accum_full = tile_empty + 2;                    // [1] MMA -> epilogue (tcgen05.commit)
+    uint8_t* tiles = tc_smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);
+    int* cols_s = reinterpret_cast<int*>(tiles + kTcNB * kTcTileBytes);
+    uint64_t* tile_full = reinterpret_cast<uint64_t*>(cols_s + 128);      // [kTcNB] loaders -> MMA (one arrive per loader warp)
+    uint64_t* tile_empty = tile_full + kTcNB;                             // [kTcNB] MMA -> loaders (tcgen05.commit)
+    uint64_t* accum_full = tile_empty + kTcNB;                            // [1] MMA -> epilogue (tcgen05.commit)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
     volatile int* s_err = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
@@ -108,16 +103,15 @@ panel_gram_tc_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kTcStages; ++s) { dev::mbar_init(&raw_full[s], 1); dev::mbar_init(&raw_empty[s], kTcXformWarps); }
-        for (int b = 0; b < 2; ++b) { dev::mbar_init(&tile_full[b], kTcXformWarps); dev::mbar_init(&tile_empty[b], 1); }
+        for (int b = 0; b < kTcNB; ++b) { dev::mbar_init(&tile_full[b], kTcLoadWarps); dev::mbar_init(&tile_empty[b], 1); }
         dev::mbar_init(accum_full, 1);
         *s_err = 0;
         dev::fence_barrier_init();
     }
     for (int e = tid; e < 128; e += kTcThreads) cols_s[e] = (e < ncol) ? it.cols[e] : 0;
-    // window columns that do not exist stay zero in both tile buffers for the whole kernel (their outputs are never read)
-    for (int e = tid; e < 2 * kTcTileBytes / 16; e += kTcThreads) reinterpret_cast<uint4*>(tiles)[e] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == 1) {
+    // window columns that do not exist stay zero in every tile buffer for the whole kernel (their outputs are never read)
+    for (int e = tid; e < kTcNB * kTcTileBytes / 16; e += kTcThreads) reinterpret_cast<uint4*>(tiles)[e] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dev::smem_u32(tmem_slot)), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -128,25 +122,10 @@ panel_gram_tc_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, con
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        // ================= producer
-        for (int c = 0; c < nchunks; ++c) {
-            const int stage = c % kTcStages; const uint32_t use = (uint32_t)(c / kTcStages);
-            if (!tc::wait_bounded(&raw_empty[stage], (use & 1u) ^ 1u, s_err)) break;
-            const int64_t r = row0 + (int64_t)c * kTcKC;
-            const int rows = (int)min((long long)kTcKC, (long long)(row1 - r));          // multiple of 32
-            const uint32_t col_bytes = (uint32_t)rows * 4u;
-            if (lane == 0) dev::mbar_arrive_expect_tx(&raw_full[stage], col_bytes * (uint32_t)(ncol + 1));
-            __syncwarp();
-            float* dst = raw + (size_t)stage * 128 * kTcKC;
-            for (int u = lane; u < ncol; u += 32)
-                dev::tma_bulk_g2s(dst + (size_t)u * kTcKC, X + (int64_t)cols_s[u] * ld + r, col_bytes, &raw_full[stage]);
-            if (lane == 0) dev::tma_bulk_g2s(wraw + (size_t)stage * kTcKC, w + r, col_bytes, &raw_full[stage]);
-        }
-    } else if (warp == 1) {
         // ================= MMA issuer (one lane)
         if (lane == 0) {
             for (int c = 0; c < nchunks; ++c) {
-                const int buf = c & 1; const uint32_t use = (uint32_t)(c >> 1);
+                const int buf = c % kTcNB; const uint32_t use = (uint32_t)(c / kTcNB);
                 if (!tc::wait_bounded(&tile_full[buf], use & 1u, s_err)) break;
                 tc::fence_after();
                 const uint32_t tile_addr = dev::smem_u32(tiles + (size_t)buf * kTcTileBytes);
@@ -164,38 +143,51 @@ panel_gram_tc_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, con
             tc::commit(accum_full);
         }
     } else {
-        // ================= transform warps
-        const int xt = tid - 64;                                                   // 0 .. 255
-        const int xw = warp - 2;
-        bool ok = true;
-        for (int c = 0; c < nchunks && ok; ++c) {
-            const int stage = c % kTcStages; const uint32_t suse = (uint32_t)(c / kTcStages);
-            const int buf = c & 1; const uint32_t buse = (uint32_t)(c >> 1);
+        // ================= loader warps: thread xt owns the 16-byte row vector q of columns u0, u0 + 32, u0 + 64, u0 + 96
+        const int xt = tid - 32;
+        const int q = xt & 15, u0 = xt >> 4;
+        const float* colp[kTcNI];
+#pragma unroll
+        for (int i = 0; i < kTcNI; ++i) colp[i] = X + (int64_t)cols_s[min(u0 + 32 * i, 127)] * ld + 4 * q;
+        const int kb = q >> 3, ch = q & 7;
+        uint32_t toff[kTcNI];
+#pragma unroll
+        for (int i = 0; i < kTcNI; ++i) { const int u = u0 + 32 * i; toff[i] = (uint32_t)(kb * 16384 + (u >> 3) * 1024 + (u & 7) * 128 + ((ch ^ (u & 7)) << 4)); }
+        auto load = [&](int c, float4 (&x)[kTcNI], float4& wv) {
             const int64_t r = row0 + (int64_t)c * kTcKC;
-            const int rows = (int)min((long long)kTcKC, (long long)(row1 - r));
-            if (!tc::wait_bounded(&raw_full[stage], suse & 1u, s_err)) { ok = false; break; }
-            if (!tc::wait_bounded(&tile_empty[buf], (buse & 1u) ^ 1u, s_err)) { ok = false; break; }
-            float* wq = wsq + buf * kTcKC;
-            if (xt < kTcKC) wq[xt] = (xt < rows) ? sqrtf(fmaxf(wraw[(size_t)stage * kTcKC + xt], 0.f)) : 0.f;
-            dev::named_bar_sync(1, 32 * kTcXformWarps);
-            const float* src = raw + (size_t)stage * 128 * kTcKC;
+            const bool live = c < nchunks && r + 4 * q < row1;
+            wv = live ? __ldg(reinterpret_cast<const float4*>(wsqrt + r + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < kTcNI; ++i)
+                x[i] = (live && u0 + 32 * i < ncol) ? __ldg(reinterpret_cast<const float4*>(colp[i] + r)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        bool ok = true;
+        auto store = [&](int c, const float4 (&x)[kTcNI], const float4& wv) {
+            if (!ok || c >= nchunks) return;
+            const int buf = c % kTcNB; const uint32_t use = (uint32_t)(c / kTcNB);
+            if (!tc::wait_bounded(&tile_empty[buf], (use & 1u) ^ 1u, s_err)) { ok = false; return; }
             uint8_t* tile = tiles + (size_t)buf * kTcTileBytes;
-            for (int e = xt; e < ncol * (kTcKC / 4); e += 32 * kTcXformWarps) {
-                const int u = e / (kTcKC / 4), q = e - u * (kTcKC / 4);            // column, 16-byte chunk along the rows
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (4 * q < rows) x = *reinterpret_cast<const float4*>(src + (size_t)u * kTcKC + 4 * q);
-                const float4 s4 = *reinterpret_cast<const float4*>(wq + 4 * q);
-                uint4 y;
-                y.x = tc::to_tf32(x.x * s4.x); y.y = tc::to_tf32(x.y * s4.y); y.z = tc::to_tf32(x.z * s4.z); y.w = tc::to_tf32(x.w * s4.w);
-                const int kb = q >> 3, ch = q & 7;
-                *reinterpret_cast<uint4*>(tile + kb * 16384 + (u >> 3) * 1024 + (u & 7) * 128 + ((ch ^ (u & 7)) << 4)) = y;
+#pragma unroll
+            for (int i = 0; i < kTcNI; ++i) {
+                if (u0 + 32 * i < ncol) {
+                    uint4 y;
+                    y.x = tc::to_tf32(x[i].x * wv.x); y.y = tc::to_tf32(x[i].y * wv.y); y.z = tc::to_tf32(x[i].z * wv.z); y.w = tc::to_tf32(x[i].w * wv.w);
+                    *reinterpret_cast<uint4*>(tile + toff[i]) = y;
+                }
             }
             dev::fence_proxy_async();                                              // generic-proxy stores -> visible to the MMA
             __syncwarp();
-            if (lane == 0) { dev::mbar_arrive(&tile_full[buf]); dev::mbar_arrive(&raw_empty[stage]); }
+            if (lane == 0) dev::mbar_arrive(&tile_full[buf]);
+        };
+        float4 xa[kTcNI], xb[kTcNI], xc[kTcNI], wa, wb, wc;
+        load(0, xa, wa); load(1, xb, wb);
+        for (int c = 0; c < nchunks; c += 3) {
+            load(c + 2, xc, wc); store(c, xa, wa);
+            load(c + 3, xa, wa); store(c + 1, xb, wb);
+            load(c + 4, xb, wb); store(c + 2, xc, wc);
         }
-        // ================= epilogue: TMEM -> registers -> the panel's rows (warps 2..5 cover the four 32-lane quadrants)
-        if (ok && xw < 4 && nchunks > 0) {
+        // ================= epilogue: TMEM -> registers -> the panel's rows (warps 1..4 cover the four 32-lane quadrants)
+        if (ok && warp <= 4 && nchunks > 0) {
             const int quad = warp & 3;                                             // a warp may only touch TMEM lanes [32 quad, 32 quad + 32)
             if (quad * 32 < n_src && tc::wait_bounded(accum_full, 0u, s_err)) {
                 tc::fence_after();
@@ -228,11 +220,17 @@ panel_gram_tc_kernel(const float* __restrict__ X, int64_t ld, int64_t n_pad, con
     if (nchunks == 0) for (int e = tid; e < n_src * 128; e += kTcThreads) part[((size_t)rb * n_panels + blockIdx.x) * kPanelOut + e] = 0.f;
     tc::fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 0) {
         tc::fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128u) : "memory");
     }
     if (tid == 0 && *s_err) atomicExch(err_flag, 1);
+}
+
+// wsqrt = sqrt(max(w, 0)) (the operand scaling of the Gram: D = Y^T Y with Y = sqrt(w) o X)
+__global__ void sqrt_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sqrtf(fmaxf(w[i], 0.f));
 }
 
 }  // namespace ab

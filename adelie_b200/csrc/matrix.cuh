@@ -444,7 +444,7 @@ struct DenseMatrix {
 
     // Whole Gram panels in one pass per panel (fp32 dense columns): panel_gram_tc_kernel on the tensor cores (tcgen05, TF32 operands,
     // Configs::panel_tc) or panel_gram_kernel on the CUDA cores; panel_tmp holds n_items * kPanelOut doubles.
-    DevBuf<double> panel_tmp; DevBuf<float> part_f; DevBuf<int> tc_err;
+    DevBuf<double> panel_tmp; DevBuf<float> part_f, wsqrt_f; DevBuf<int> tc_err;
     void d_panel_gram(const PanelItem* items_dev, int n_items, const float* w, float* Q, int ldq, int Ccap, int use_tc = -1, double* tmp_out = nullptr) {
         if (n_items <= 0) return;
         if (use_tc < 0) use_tc = Configs::panel_tc;
@@ -459,7 +459,9 @@ struct DenseMatrix {
             part_f.reserve_keep((size_t)n_rb * n_items * kPanelOut, stream);
             if (!tc_err.n) tc_err.alloc(1);
             AB_CUDA(cudaFuncSetAttribute(panel_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
-            panel_gram_tc_kernel<<<dim3(n_items, n_rb), kTcThreads, kTcSmemBytes, stream>>>((const float*)X, ld, ld, items_dev, w, part_f.p, n_items,
+            wsqrt_f.reserve_keep((size_t)ld, stream);
+            sqrt_weights_kernel<<<(unsigned)((ld + 255) / 256), 256, 0, stream>>>(w, wsqrt_f.p, ld);
+            panel_gram_tc_kernel<<<dim3(n_items, n_rb), kTcThreads, kTcSmemBytes, stream>>>((const float*)X, ld, ld, items_dev, wsqrt_f.p, part_f.p, n_items,
                                                                                         rows_per_block, tc_err.p);
             panel_gram_sum_kernel<float><<<n_items, 256, 0, stream>>>(items_dev, part_f.p, n_rb, n_items, panel_tmp.p);
         } else {

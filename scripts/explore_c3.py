@@ -30,6 +30,9 @@ else:
     glm = ad.glm.gaussian(y, dtype=dtype)
 if rank == 0:
     print(f"gen {time.time() - t:.1f}s  {family} alpha={alpha} rows[{lo},{hi}) of {n_total} p={p} groups of {gs}  X shard = {4.0 * n * p / 1e9:.1f} GB", flush=True)
+for kv in os.environ.get("CFG", "").split(","):          # e.g. CFG=glm_batched=0,panel_tc=0
+    if "=" in kv:
+        k, v = kv.split("="); ad.set_configs(k, float(v))
 for rep in range(int(os.environ.get("REPS", 2))):
     t = time.time()
     st = ad.grpnet(X, glm, groups=np.arange(0, p, gs), alpha=alpha, early_exit=False, lmda_path_size=L, min_ratio=float(os.environ.get("MINR", 1e-2)),
@@ -39,4 +42,5 @@ for rep in range(int(os.environ.get("REPS", 2))):
         print(f"rep {rep}: wall {wall:.3f}s solve {st.total_time:.3f}s err='{st.error}' nl={len(st.lmdas)} sweeps={st.n_sweeps} updates={st.n_group_updates} "
               f"irls={getattr(st, 'n_irls', 0)} kernel_time={st.time_sweep_kernel:.3f}s sweeps/s={st.n_sweeps / st.total_time:.1f} "
               f"active_last={st.active_sizes[-1] if len(st.active_sizes) else 0} screen_last={st.screen_sizes[-1] if len(st.screen_sizes) else 0} dev_last={st.devs[-1]:.4f}", flush=True)
-        print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["run_pin", "invariance", "screen_records", "cov_device", "screen_host"]), flush=True)
+        print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["run_pin", "invariance", "screen_records", "cov_device", "eigh_device", "panels", "pin_launch", "pin_sync", "pin_download", "screen_host"])
+              + f" batched_launches={st.n_batched_launches} batch={st.sweep_batch} ctas={st.sweep_ncta} stages={st.sweep_stages}", flush=True)
