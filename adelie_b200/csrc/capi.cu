@@ -92,6 +92,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "sweep_xchg") Configs::sweep_xchg = (int)value;
     else if (s == "panel_gemm") Configs::panel_gemm = (int)value;
     else if (s == "panel_tc") Configs::panel_tc = (int)value;
+    else if (s == "kkt_skip_screen") Configs::kkt_skip_screen = (int)value;
     else if (s == "glm_batched") Configs::glm_batched = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
@@ -113,6 +114,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "sweep_xchg") *value = Configs::sweep_xchg;
     else if (s == "panel_gemm") *value = Configs::panel_gemm;
     else if (s == "panel_tc") *value = Configs::panel_tc;
+    else if (s == "kkt_skip_screen") *value = Configs::kkt_skip_screen;
     else if (s == "glm_batched") *value = Configs::glm_batched;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
@@ -969,6 +971,8 @@ int ab_state_solve(ab_state* s, int display_progress_bar, int (*exit_cond)(void*
         if (check_signals) ps->check_interrupt = [=]() { if (check_signals() != 0) throw solver_error("interrupted."); };
         try { ps->solve(); }
         catch (const std::exception& e) { s->error = e.what(); }       // py_state.cpp:83-90: message returned, state stays valid
+        try { ps->finalize_invariance(); }
+        catch (const std::exception& e) { if (s->error.empty()) s->error = e.what(); }
         ps->exit_cond = nullptr; ps->check_interrupt = nullptr;
     };
     if (s->dtype == AB_F32) run(s->f32); else run(s->f64);

@@ -538,7 +538,12 @@ struct PathState {
             // Whole panels pay off when many blocks are new at once (a block costs ~5 us in pair_gram_kernel, a whole panel ~90 us
             // + ~40 us of fixed cost): the usual incremental call (a few new groups at the tail) stays on the per-block kernel.
             // IRLS (whole_panels): the weights changed, every panel of the list is rebuilt -- one tensor-core pass per panel.
-            if (!X->sparse && (whole_panels || (Configs::panel_gemm && (double)items.size() * 5.0 > (double)(nb - b0) * 90.0 + 40.0))) {
+            // Gaussian path (incremental): whole tail panels pay off when many blocks are new at once.  Costs in us at n rows (measured at
+            // n = 200k: ~5 per block in pair_gram_kernel; a whole panel ~35 on the tensor cores, ~90 on the CUDA cores, + launch overhead).
+            const double sc_n = (double)X->n_pad() / 200000.0;
+            const double t_pairs = (double)items.size() * 5.0 * sc_n;
+            const double t_panels = (double)(nb - b0) * ((Configs::panel_tc ? 35.0 : 90.0) * sc_n + 10.0) + 40.0;
+            if (!X->sparse && (whole_panels || ((Configs::panel_gemm || Configs::panel_tc) && t_pairs > t_panels))) {
                 // whole panels b0 .. nb-1 in one pass each (panel_gram_kernel): every window column is read once per panel
                 std::vector<PanelItem> pitems;
                 for (size_t b = b0; b < nb; ++b) {
@@ -746,11 +751,47 @@ struct PathState {
 
     PinResult fit(T lmda_) { return is_glm ? fit_glm(lmda_) : fit_gaussian(lmda_); }
 
-    // update_invariance (solver_gaussian_naive.hpp:377-393 / solver_glm_naive.hpp:495-503)
-    void update_invariance(T lmda_) {
+    // update_invariance (solver_gaussian_naive.hpp:377-393 / solver_glm_naive.hpp:495-503): grad = X^T (w o r) (- resid_sum * X_means),
+    // abs_grad.  During the path only the scores of NON-screen groups are ever read (kkt :408-433 and screen :273-403 skip the screen
+    // set), so once part of X is screened the pass streams only the other columns (Configs::kkt_skip_screen; late in a path that is
+    // a small fraction of X, and the pass is the second largest item of a step).  The full gradient -- an output of the state -- is
+    // brought up to date once, when the solve ends (finalize_invariance).
+    bool grad_partial = false;
+    DevBuf<int32_t> d_ns_cols; std::vector<int32_t> ns_cols, ns_logical; size_t ns_for_screen = (size_t)-1;
+    void update_invariance(T lmda_, bool force_full = false) {
         AB_TIME(timers, "invariance");
         lmda = lmda_;
         DistContext& dc = DistContext::get();
+        const bool can_skip = Configs::kkt_skip_screen && !force_full && K == 1 && !X->sparse && !X->snp && !screen_set.empty();
+        if (can_skip) {
+            if (ns_for_screen != screen_set.size()) {                  // the screen set only grows: rebuild the list when it did
+                ns_cols.clear(); ns_logical.clear();
+                const bool flat = (idx_t)in_screen.size() == G;
+                for (idx_t g = 0; g < G; ++g) {
+                    if (flat ? in_screen[g] : (uint8_t)screen_hashset.count(g)) continue;
+                    const int32_t pc = X->phys_col(groups[g], (int)group_sizes[g]);
+                    for (idx_t c = 0; c < group_sizes[g]; ++c) { ns_cols.push_back(pc + (int32_t)c); ns_logical.push_back((int32_t)(groups[g] + c)); }
+                }
+                d_ns_cols.reserve_keep(ns_cols.size() + 4);
+                if (!ns_cols.empty()) d_ns_cols.upload(ns_cols.data(), ns_cols.size());
+                ns_for_screen = screen_set.size();
+            }
+            const size_t q = ns_cols.size();
+            if (q) {
+                d_tmp.reserve_keep(q);
+                X->d_gemv_t(0, d_ns_cols.p, (int)q, d_resid.p, is_glm ? X->d_ones() : d_weights.p, d_tmp.p);
+                dc.allreduce<T>(d_tmp.p, (int64_t)q);
+                std::vector<T> h(q);
+                d_tmp.download(h.data(), q);
+                AB_CUDA(cudaStreamSynchronize(0));
+                const bool sub = !is_glm && intercept;
+                for (size_t k = 0; k < q; ++k) { const int32_t j = ns_logical[k]; grad[j] = sub ? h[k] - resid_sum * X_means[j] : h[k]; }
+                n_kernel_launches += 2;
+            }
+            grad_partial = true;
+            update_abs_grad(lmda_);
+            return;
+        }
         if (K > 1) {
             X->d_mul_multi(K, (int)n_int, d_resid.p, is_glm ? nullptr : d_weights.p, d_grad.p);     // state-level intercept is always off
             dc.allreduce<T>(d_grad.p, p);
@@ -770,7 +811,13 @@ struct PathState {
         AB_CUDA(cudaStreamSynchronize(0));
         if (K == 1 && !is_glm && dc.active() && intercept) for (idx_t j = 0; j < p; ++j) grad[j] -= resid_sum * X_means[j];
         n_kernel_launches += 2;
+        grad_partial = false;
         update_abs_grad(lmda_);
+    }
+    // the state's grad / abs_grad are outputs: complete them after a solve that skipped the screen columns
+    void finalize_invariance() {
+        if (!grad_partial) return;
+        update_invariance(lmda, true);
     }
 
     void update_solutions(PinResult& pr, T lmda_) {
