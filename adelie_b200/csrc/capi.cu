@@ -92,6 +92,8 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "sweep_xchg") Configs::sweep_xchg = (int)value;
     else if (s == "panel_gemm") Configs::panel_gemm = (int)value;
     else if (s == "panel_tc") Configs::panel_tc = (int)value;
+    else if (s == "snp_tc") Configs::snp_tc = (int)value;
+    else if (s == "snp_tc_min_k") Configs::snp_tc_min_k = (int)value;
     else if (s == "kkt_skip_screen") Configs::kkt_skip_screen = (int)value;
     else if (s == "glm_batched") Configs::glm_batched = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
@@ -114,6 +116,8 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "sweep_xchg") *value = Configs::sweep_xchg;
     else if (s == "panel_gemm") *value = Configs::panel_gemm;
     else if (s == "panel_tc") *value = Configs::panel_tc;
+    else if (s == "snp_tc") *value = Configs::snp_tc;
+    else if (s == "snp_tc_min_k") *value = Configs::snp_tc_min_k;
     else if (s == "kkt_skip_screen") *value = Configs::kkt_skip_screen;
     else if (s == "glm_batched") *value = Configs::glm_batched;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }

@@ -13,6 +13,7 @@
 #include "sweep_batched.cuh"
 #include "sparse_kernels.cuh"
 #include "snp.cuh"
+#include "snp_tc.cuh"
 #include <unordered_map>
 #include "dist.cuh"
 #include <cuda.h>
@@ -245,7 +246,37 @@ struct DenseMatrix {
         AB_CUDA(cudaGetLastError());
         return n_rb;
     }
+    // tensor-core path (snp_tc.cuh): float32, 2 <= K <= 8 classes (Configs::snp_tc_min_k), exact integer accumulation
+    DevBuf<uint8_t> stc_bq; DevBuf<double> stc_partial, stc_stats; DevBuf<int> stc_err;
+    int snp_gemv_tc(int64_t j0, int q, int K, const float* v, const float* w) {
+        const int n_chunks = (int)((ld + kStcKC - 1) / kStcKC);
+        stc_bq.reserve_keep((size_t)n_chunks * kStcBTile, stream);
+        stc_partial.reserve_keep((size_t)kStcStatBlocks * 16, stream);
+        if (!stc_stats.n) stc_stats.alloc(32);
+        if (!stc_err.n) stc_err.alloc(1);
+        snp_tc_stats_kernel<<<kStcStatBlocks, 256, 0, stream>>>(v, w, (int64_t)ld * K, K, stc_partial.p);
+        snp_tc_stats_finish_kernel<<<1, 32, 0, stream>>>(stc_partial.p, kStcStatBlocks, stc_stats.p);
+        const int64_t n_groups16 = (int64_t)n_chunks * 16;
+        snp_tc_quant_kernel<<<(unsigned)((n_groups16 * 32 + 255) / 256), 256, 0, stream>>>(v, w, ld, K, n_groups16, stc_stats.p, stc_bq.p);
+        const int sms = DeviceInfo::get().sm_count;
+        const int n_tiles = (q + kStcCols - 1) / kStcCols;
+        int n_rb = std::max(1, std::min(n_chunks, (2 * sms + n_tiles - 1) / n_tiles));
+        const int chunks_per_rb = (n_chunks + n_rb - 1) / n_rb;
+        n_rb = (n_chunks + chunks_per_rb - 1) / chunks_per_rb;
+        const bool stdv = snp_center.n != 0;
+        part.reserve_keep((size_t)(n_rb + (stdv ? 1 : 0)) * q * K, stream);
+        AB_CUDA(cudaFuncSetAttribute(snp_gemv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStcSmemBytes));
+        snp_gemv_tc_kernel<<<dim3(n_tiles, n_rb), kStcThreads, kStcSmemBytes, stream>>>(snp_bits, snp_ldw, (const float*)snp_impute.p, (const float*)snp_center.p,
+            (const float*)snp_scale.p, j0, q, K, stc_bq.p, n_chunks, chunks_per_rb, stc_stats.p, part.p, stc_err.p);
+        if (stdv) snp_tc_const_kernel<<<(unsigned)(((int64_t)q * K + 255) / 256), 256, 0, stream>>>((const float*)snp_center.p, (const float*)snp_scale.p, j0, q, K,
+                                                                                           stc_stats.p, part.p + (size_t)n_rb * q * K);
+        AB_CUDA(cudaGetLastError());
+        return n_rb + (stdv ? 1 : 0);
+    }
     int snp_gemv(int64_t j0, int q, int K, const T* v, const T* w, bool sq) {
+        if constexpr (std::is_same<T, float>::value) {
+            if (!sq && Configs::snp_tc && K >= Configs::snp_tc_min_k && K <= 8) return snp_gemv_tc(j0, q, K, v, w);
+        }
         if (sq) return snp_gemv_launch<1, true>(j0, q, 1, v, w);
         if (K <= 1) return snp_gemv_launch<1, false>(j0, q, 1, v, w);
         if (K <= 2) return snp_gemv_launch<2, false>(j0, q, K, v, w);
@@ -479,9 +510,14 @@ struct DenseMatrix {
     }
     // the tensor-core kernel bounds every wait and raises this flag instead of hanging; checked at the caller's next synchronisation
     void check_tc_error() {
-        if (!tc_err.n) return;
-        int e = 0; tc_err.download(&e, 1); AB_CUDA(cudaStreamSynchronize(stream));
-        if (e) { int z = 0; tc_err.upload(&z, 1); throw solver_error("tensor-core Gram kernel timed out (pipeline protocol error)."); }
+        int e = 0, e2 = 0;
+        if (tc_err.n) tc_err.download(&e, 1);
+        if (stc_err.n) stc_err.download(&e2, 1);
+        if (tc_err.n || stc_err.n) AB_CUDA(cudaStreamSynchronize(stream));
+        if (e || e2) {
+            int z = 0; if (tc_err.n) tc_err.upload(&z, 1); if (stc_err.n) stc_err.upload(&z, 1);
+            throw solver_error("tensor-core kernel timed out (pipeline protocol error).");
+        }
     }
 
     // The batched look-ahead pin solve (sweep_batched.cuh); single response, single GPU, static weights.

@@ -39,7 +39,7 @@ def _compare(st, ref, rtol):
     np.testing.assert_allclose(st.devs, ref.devs, rtol=10 * rtol, atol=10 * rtol)
 
 
-@pytest.mark.parametrize("dtype,rtol", [(np.float64, 1e-6), (np.float32, 2e-4)])
+@pytest.mark.parametrize("dtype,rtol", [(np.float64, 1e-6), (np.float32, 1e-4)])
 @pytest.mark.parametrize("n,p,K,alpha,intercept", [
     (300, 40, 3, 1.0, True),
     (300, 40, 4, 0.6, False),
@@ -48,8 +48,8 @@ def _compare(st, ref, rtol):
 ])
 def test_multigaussian_path_vs_oracle(dtype, rtol, n, p, K, alpha, intercept):
     X, Y = _multi_data(n, p, K, 11, dtype)
-    tol = 1e-12 if dtype == np.float64 else 1e-7
-    newton_tol = 1e-12 if dtype == np.float64 else 1e-5
+    tol = 1e-12 if dtype == np.float64 else 1e-10        # float32: converge past sqrt(tol) ~ 1e-4 so that rounding is what is compared
+    newton_tol = 1e-12 if dtype == np.float64 else 1e-6
     kw = dict(alpha=alpha, intercept=intercept, tol=tol, early_exit=False, lmda_path_size=20, min_ratio=0.05, newton_tol=newton_tol)
     st = ad.grpnet(X, ad.glm.multigaussian(Y, dtype=dtype), progress_bar=False, **kw)
     ref = orc.grpnet(X, orc.glm_spec("multigaussian", Y, dtype=dtype), **kw)

@@ -49,15 +49,17 @@ def test_gaussian_path_vs_oracle(dtype, rtol, n, p, G, alpha, intercept):
     _compare_paths(st, ref, rtol)
 
 
-@pytest.mark.parametrize("dtype,rtol", [(np.float64, 1e-6), (np.float32, 2e-4)])
+@pytest.mark.parametrize("dtype,rtol", [(np.float64, 1e-6), (np.float32, 1e-4)])
 @pytest.mark.parametrize("n,p,G,alpha", [(400, 60, 60, 1.0), (600, 90, 18, 0.5)])
 def test_binomial_path_vs_oracle(dtype, rtol, n, p, G, alpha):
     data = ad.data.dense(n, p, G, glm="binomial", seed=5)
     X = np.asfortranarray(data["X"], dtype=dtype)
     y = data["glm"].y.astype(dtype)
-    tol = 1e-12 if dtype == np.float64 else 1e-7
-    newton_tol = 1e-12 if dtype == np.float64 else 1e-5
-    irls_tol = 1e-10 if dtype == np.float64 else 1e-6
+    # the sweep stops when max_g sum(A dbeta^2) / gs < tol: coefficients are only accurate to ~sqrt(tol).  For a 1e-4 comparison of two
+    # float32 implementations both sides converge to 1e-10 / 1e-9 (float32 resolves that), so that rounding, not the stopping rule, is compared
+    tol = 1e-12 if dtype == np.float64 else 1e-10
+    newton_tol = 1e-12 if dtype == np.float64 else 1e-6
+    irls_tol = 1e-10 if dtype == np.float64 else 1e-9
     kw = dict(groups=data["groups"], alpha=alpha, penalty=data["penalty"].astype(dtype), tol=tol, irls_tol=irls_tol,
               early_exit=False, lmda_path_size=20, min_ratio=0.1, newton_tol=newton_tol)
     st = ad.grpnet(X, ad.glm.binomial(y, dtype=dtype), progress_bar=False, **kw)

@@ -23,7 +23,7 @@ def _rand_csc(n, p, density, dtype, seed):
     return M.astype(dtype)
 
 
-@pytest.mark.parametrize("dtype,atol", [(np.float64, 1e-12), (np.float32, 2e-4)])
+@pytest.mark.parametrize("dtype,atol", [(np.float64, 1e-12), (np.float32, 1e-4)])      # the reference's own float32 operator tolerance (T/test_matrix.py: atol 1e-4)
 @pytest.mark.parametrize("n,p,density", [(200, 50, 0.3), (1500, 120, 0.05), (64, 7, 1.0)])
 def test_sparse_operators_vs_numpy(dtype, atol, n, p, density):
     M = _rand_csc(n, p, density, dtype, seed=n + p)
@@ -33,24 +33,24 @@ def test_sparse_operators_vs_numpy(dtype, atol, n, p, density):
     v = rng.normal(size=n).astype(dtype); w = rng.uniform(0.1, 1, size=n).astype(dtype)
     out = np.empty(p, dtype=dtype)
     X.mul(v, w, out)
-    np.testing.assert_allclose(out, D.T @ (v * w), atol=atol * n)
+    np.testing.assert_allclose(out, D.T @ (v * w), rtol=atol, atol=atol)
     X.sq_mul(w, out)
-    np.testing.assert_allclose(out, (D ** 2).T @ w, atol=atol * n)
+    np.testing.assert_allclose(out, (D ** 2).T @ w, rtol=atol, atol=atol)
     for j, q in [(0, 1), (p // 3, min(5, p - p // 3)), (p - 1, 1), (0, p if p <= 10 else 9)]:
         o = np.empty(q, dtype=dtype)
         X.bmul(j, q, v, w, o)
-        np.testing.assert_allclose(o, D[:, j:j + q].T @ (v * w), atol=atol * n)
-        assert abs(X.cmul(j, v, w) - D[:, j] @ (v * w)) <= atol * n
+        np.testing.assert_allclose(o, D[:, j:j + q].T @ (v * w), rtol=atol, atol=atol)
+        assert abs(X.cmul(j, v, w) - D[:, j] @ (v * w)) <= atol * (1 + abs(D[:, j] @ (v * w)))
         vv = rng.normal(size=q).astype(dtype)
         acc = rng.normal(size=n).astype(dtype); expect = acc + D[:, j:j + q] @ vv
         X.btmul(j, q, vv, acc)
-        np.testing.assert_allclose(acc, expect, atol=atol * q * 10)
+        np.testing.assert_allclose(acc, expect, rtol=atol, atol=atol)
         acc = np.zeros(n, dtype=dtype)
         X.ctmul(j, 1.5, acc)
-        np.testing.assert_allclose(acc, 1.5 * D[:, j], atol=atol * 10)
+        np.testing.assert_allclose(acc, 1.5 * D[:, j], rtol=atol, atol=atol)
         C = np.empty((q, q), dtype=dtype, order="F")
         X.cov(j, q, np.sqrt(w), C)
-        np.testing.assert_allclose(C, D[:, j:j + q].T @ (w[:, None] * D[:, j:j + q]), atol=atol * n)
+        np.testing.assert_allclose(C, D[:, j:j + q].T @ (w[:, None] * D[:, j:j + q]), rtol=atol, atol=atol)
     with pytest.raises(RuntimeError, match="bmul"):
         X.bmul(p - 1, 2, v, w, np.empty(2, dtype=dtype))
 
