@@ -31,6 +31,9 @@ noise = np.random.default_rng(1000 + rank).normal(size=(n, K)) * np.linalg.norm(
 Y = np.ascontiguousarray(Y + noise, dtype=dtype)
 if rank == 0:
     print(f"y ready {time.time() - t:.1f}s", flush=True)
+for kv in os.environ.get("CFG", "").split(","):          # e.g. CFG=snp_tc=0
+    if "=" in kv:
+        k_, v_ = kv.split("="); ad.set_configs(k_, float(v_))
 for rep in range(int(os.environ.get("REPS", 2))):
     t = time.time()
     st = ad.grpnet(X, ad.glm.multigaussian(Y, dtype=dtype), early_exit=False, lmda_path_size=L, min_ratio=float(os.environ.get("MINR", 1e-2)),

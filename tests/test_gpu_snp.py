@@ -234,11 +234,11 @@ def test_multi_response_mul_tensor_core_vs_numpy(n, p, K, std):
     cd, imp = cX.to_host()
     D = so.dense_equivalent(cd, imp, np.float64)
     M = cX
-    if std:
-        M = ad.matrix.standardize(cX)
+    if std:                                  # (snp_unphased reports mean 0 / var 1 like the reference: the view needs explicit centres and scales)
         w1 = np.full(n, 1.0 / n)
-        c = D.T @ w1; s = np.sqrt(np.maximum((D ** 2).T @ w1 - c ** 2, 0))
-        D = (D - c[None]) / s[None]
+        c = (D.T @ w1).astype(np.float32); s = np.sqrt(np.maximum((D ** 2).T @ w1 - c.astype(np.float64) ** 2, 1e-3)).astype(np.float32)
+        M = ad.matrix.standardize(cX, centers=c, scales=s)
+        D = (D - c[None].astype(np.float64)) / s[None].astype(np.float64)
     rng = np.random.default_rng(1)
     V = rng.normal(size=(n, K)).astype(np.float32); W = rng.uniform(0, 2.0 / n, size=(n, K)).astype(np.float32)
     ref = (D.T @ (V.astype(np.float64) * W.astype(np.float64)))                      # (p, K)
