@@ -57,6 +57,12 @@ __device__ __forceinline__ bool wait_bounded(uint64_t* bar, uint32_t parity, vol
     }
     return true;
 }
+// one lane of a converged warp (the compiler keeps warp-uniform operands of the instructions it guards in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void commit(uint64_t* bar) {

@@ -261,7 +261,8 @@ struct DenseMatrix {
         const int sms = DeviceInfo::get().sm_count;
         const int n_tiles = (q + kStcCols - 1) / kStcCols;
         int n_rb = std::max(1, std::min(n_chunks, (2 * sms + n_tiles - 1) / n_tiles));
-        const int chunks_per_rb = (n_chunks + n_rb - 1) / n_rb;
+        // int32 accumulators: |code * digit| <= 3 * 128 per row, so a row block stays below 2^31 / 384 = 5.5M rows (16384 chunks = 4.2M)
+        const int chunks_per_rb = std::min(16384, (n_chunks + n_rb - 1) / n_rb);
         n_rb = (n_chunks + chunks_per_rb - 1) / chunks_per_rb;
         const bool stdv = snp_center.n != 0;
         part.reserve_keep((size_t)(n_rb + (stdv ? 1 : 0)) * q * K, stream);

@@ -19,8 +19,9 @@
 //     standardized images, which are affine in the code for codes 0-2); v0 * sum_i V[i, l] is added once per column as one more partial.
 // The result differs from exact arithmetic only by the fixed-point quantisation of V (2^-31 of the class maximum per element).
 //
-// Warp roles (544 threads): warp 0 = MMA issuer (+ TMEM allocation); warps 1-16 = loaders (one packed word per thread and K block,
-// four chunks ahead in registers); warp 1 lane 0 also issues the B-tile bulk copies; warps 1-4 run the epilogue.
+// Warp roles (544 threads): warp 0 = MMA issuer (+ TMEM allocation); warps 9-16 = fetch (16-byte loads of the packed words, six chunks
+// ahead in registers, handed over through an 8-stage shared-memory ring); warps 1-8 = expand (codes / missing flags -> A tile, proxy
+// fence); warp 1 lane 0 also issues the B-tile bulk copies; warps 1-4 run the epilogue.
 // Every wait is bounded by %globaltimer.
 #pragma once
 #include "device_prims.cuh"
@@ -31,12 +32,14 @@ namespace ab {
 
 constexpr int kStcCols = 64;                         // SNP columns per CTA
 constexpr int kStcKC = 256;                          // rows per chunk: two K blocks of 128 rows (128 bytes of int8 per A row)
-constexpr int kStcNB = 3;                            // tile buffers
+constexpr int kStcNB = 4;                            // tile buffers (the loaders run this many chunks ahead of the MMA completions)
 constexpr int kStcLoadWarps = 16;
 constexpr int kStcThreads = 32 + 32 * kStcLoadWarps;
 constexpr int kStcATile = 2 * 16384;                 // 2 K blocks x (128 rows x 128 bytes)
 constexpr int kStcBTile = 2 * 4096;                  // 2 K blocks x (32 rows x 128 bytes)
-constexpr size_t kStcSmemBytes = 1024 + kStcNB * (kStcATile + kStcBTile) + 256;
+constexpr int kStcRawStages = 8;                     // raw packed-word stages (64 columns x 64 bytes each) between the fetch and the expand warps
+constexpr int kStcRawBytes = kStcCols * 64;
+constexpr size_t kStcSmemBytes = 1024 + kStcNB * (kStcATile + kStcBTile) + kStcRawStages * kStcRawBytes + 512;
 constexpr int kStcStatBlocks = 256;
 
 namespace stc {
@@ -142,11 +145,14 @@ snp_gemv_tc_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const float
     const uint32_t base_u32 = dev::smem_u32(stc_smem_raw);
     uint8_t* atiles = stc_smem_raw + (((base_u32 + 1023u) & ~1023u) - base_u32);        // [kStcNB][kStcATile]
     uint8_t* btiles = atiles + kStcNB * kStcATile;                                       // [kStcNB][kStcBTile]
-    uint64_t* tile_full = reinterpret_cast<uint64_t*>(btiles + kStcNB * kStcBTile);      // [kStcNB] loaders -> MMA
+    uint8_t* rawst = btiles + kStcNB * kStcBTile;                                        // [kStcRawStages][kStcRawBytes]
+    uint64_t* tile_full = reinterpret_cast<uint64_t*>(rawst + kStcRawStages * kStcRawBytes);   // [kStcNB] expand warps -> MMA
     uint64_t* b_full = tile_full + kStcNB;                                               // [kStcNB] bulk copy of the B tile -> MMA
     uint64_t* tile_empty = b_full + kStcNB;                                              // [kStcNB] MMA -> loaders (tcgen05.commit)
     uint64_t* accum_full = tile_empty + kStcNB;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+    uint64_t* raw_full = accum_full + 1;                                                 // [kStcRawStages] fetch warps -> expand warps
+    uint64_t* raw_empty = raw_full + kStcRawStages;                                      // [kStcRawStages] expand warps -> fetch warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kStcRawStages);
     volatile int* s_err = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,13 +162,14 @@ snp_gemv_tc_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const float
     const int nch = max(0, ch1 - ch0);
 
     if (tid == 0) {
-        for (int b = 0; b < kStcNB; ++b) { dev::mbar_init(&tile_full[b], kStcLoadWarps); dev::mbar_init(&b_full[b], 1); dev::mbar_init(&tile_empty[b], 1); }
+        for (int b = 0; b < kStcNB; ++b) { dev::mbar_init(&tile_full[b], kStcLoadWarps / 2); dev::mbar_init(&b_full[b], 1); dev::mbar_init(&tile_empty[b], 1); }
+        for (int b = 0; b < kStcRawStages; ++b) { dev::mbar_init(&raw_full[b], kStcLoadWarps / 2); dev::mbar_init(&raw_empty[b], kStcLoadWarps / 2); }
         dev::mbar_init(accum_full, 1);
         *s_err = 0;
         dev::fence_barrier_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dev::smem_u32(tmem_slot)), "r"(32u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dev::smem_u32(tmem_slot)), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc::fence_before();
@@ -171,70 +178,106 @@ snp_gemv_tc_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const float
     const uint32_t tmem_d = *tmem_slot;
 
     if (warp == 0) {
-        // ================= MMA issuer
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp walks the chunks (converged), one elected lane issues
+        {
+            int buf = 0; uint32_t ph = 0u;
+            bool okw = true;
             for (int c = 0; c < nch; ++c) {
-                const int buf = c % kStcNB; const uint32_t use = (uint32_t)(c / kStcNB);
-                if (!tc::wait_bounded(&tile_full[buf], use & 1u, s_err)) break;
-                if (!tc::wait_bounded(&b_full[buf], use & 1u, s_err)) break;
+                okw = tc::wait_bounded(&tile_full[buf], ph, s_err) && tc::wait_bounded(&b_full[buf], ph, s_err);
+                okw = __all_sync(0xffffffffu, okw);
+                if (!okw) break;
                 tc::fence_after();
                 const uint32_t a_addr = dev::smem_u32(atiles + (size_t)buf * kStcATile), b_addr = dev::smem_u32(btiles + (size_t)buf * kStcBTile);
+                if (tc::elect_one()) {
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-                    const uint64_t da = tc::smem_desc_k_sw128(a_addr + (uint32_t)kb * 16384u), db = tc::smem_desc_k_sw128(b_addr + (uint32_t)kb * 4096u);
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t da = tc::smem_desc_k_sw128(a_addr + (uint32_t)kb * 16384u), db = tc::smem_desc_k_sw128(b_addr + (uint32_t)kb * 4096u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)                                       // K = 32 bytes per instruction inside the 128-byte atom
-                        stc::mma_i8(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), stc::kIdescI8, (c | kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)                                   // K = 32 bytes per instruction inside the 128-byte atom
+                            // four independent accumulators (TMEM columns 32 k ..): with N = 32 an MMA is far shorter than the latency of
+                            // a dependent accumulation into the same tile (one accumulator: ~130 cycles per MMA, 1080 per chunk)
+                            stc::mma_i8(tmem_d + (uint32_t)(32 * k), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), stc::kIdescI8, (c | kb) != 0 ? 1u : 0u);
+                    }
+                    tc::commit(&tile_empty[buf]);
                 }
-                tc::commit(&tile_empty[buf]);
+                __syncwarp();
+                if (++buf == kStcNB) { buf = 0; ph ^= 1u; }
             }
-            tc::commit(accum_full);
+            if (tc::elect_one()) tc::commit(accum_full);
+            __syncwarp();
         }
     } else {
-        // ================= loaders: thread -> (column u, word qw of a K block)
-        const int xt = tid - 32;
-        const int u = xt >> 3, qw = xt & 7;
-        const int col = tile_c0 + u;
-        const uint32_t* src = packed + (int64_t)(j0 + min(col, q - 1)) * ldw;
-        const bool col_ok = col < q;
-        const uint32_t aoff = (uint32_t)((u >> 3) * 1024 + (u & 7) * 128 + ((qw ^ (u & 7)) << 4));
-        auto fetch = [&](int c, uint32_t& w0, uint32_t& w1) {
-            w0 = 0u; w1 = 0u;
-            if (c < nch && col_ok) {
-                const int64_t wi = (int64_t)(ch0 + c) * 16 + qw;
-                if (wi < ldw) w0 = __ldg(src + wi);
-                if (wi + 8 < ldw) w1 = __ldg(src + wi + 8);
-            }
-        };
+        // ================= warps 1-8: expand (raw packed words -> A tile), warps 9-16: fetch (global -> raw stage).  The two jobs sit in
+        // different warps because the proxy fence the expand threads need (fence.proxy.async = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) waits
+        // for ALL of a thread's outstanding memory operations: in the first version the same threads also held the packed words of the next
+        // chunks in flight, and every fence drained that prefetch queue (ncu: 1.06 TB/s, long-scoreboard stalls at the fence).
+        const bool is_fetch = warp > kStcLoadWarps / 2;
+        const int xt = is_fetch ? tid - 32 - 16 * kStcLoadWarps : tid - 32;          // 0 .. 255 inside the role
+        const int u = xt >> 2, qq = xt & 3;                                           // column of the tile, quarter (4 words = 64 rows) of the chunk
         bool ok = true;
-        auto put = [&](uint8_t* dst, uint32_t wd) {
-            const uint32_t mw = wd & (wd >> 1) & 0x55555555u;
-            const uint4 y = make_uint4(wd & 0x03030303u, (wd >> 2) & 0x03030303u, (wd >> 4) & 0x03030303u, (wd >> 6) & 0x03030303u);
-            const uint4 m = make_uint4(mw & 0x01010101u, (mw >> 2) & 0x01010101u, (mw >> 4) & 0x01010101u, (mw >> 6) & 0x01010101u);
-            *reinterpret_cast<uint4*>(dst) = y;
-            *reinterpret_cast<uint4*>(dst + 8 * 1024) = m;
-        };
-        auto store = [&](int c, uint32_t w0, uint32_t w1) {
-            if (!ok || c >= nch) return;
-            const int buf = c % kStcNB; const uint32_t use = (uint32_t)(c / kStcNB);
-            if (!tc::wait_bounded(&tile_empty[buf], (use & 1u) ^ 1u, s_err)) { ok = false; return; }
-            if (xt == 0) {                                                            // the chunk's B tile: one bulk copy
-                dev::mbar_arrive_expect_tx(&b_full[buf], (uint32_t)kStcBTile);
-                dev::tma_bulk_g2s(btiles + (size_t)buf * kStcBTile, Bq + (size_t)(ch0 + c) * kStcBTile, (uint32_t)kStcBTile, &b_full[buf]);
+        if (is_fetch) {
+            const int col = tile_c0 + u;
+            // (8-byte loads: a column starts at a multiple of ldw words and ldw is only guaranteed to be even)
+            const uint2* src = reinterpret_cast<const uint2*>(packed + (int64_t)(j0 + min(col, q - 1)) * ldw + (int64_t)ch0 * 16) + 2 * qq;
+            const long long words_left = (long long)ldw - (long long)ch0 * 16 - 4 * qq;     // words from this thread's first word to the column's end
+            const int c_lo = (col < q) ? (int)max(0LL, min((long long)nch, (words_left + 14) / 16)) : 0;      // chunks whose words 0-1 exist
+            const int c_hi = (col < q) ? (int)max(0LL, min((long long)nch, (words_left + 12) / 16)) : 0;      // chunks whose words 2-3 exist
+            auto fetch = [&](int c, uint4& wv) {
+                const uint2 a = (c < c_lo) ? __ldg(src + (size_t)c * 8) : make_uint2(0u, 0u);
+                const uint2 b = (c < c_hi) ? __ldg(src + (size_t)c * 8 + 1) : make_uint2(0u, 0u);
+                wv = make_uint4(a.x, a.y, b.x, b.y);
+            };
+            int st = 0; uint32_t ph = 1u;
+            auto push = [&](int c, const uint4& wv) {
+                if (!ok || c >= nch) return;
+                if (!tc::wait_bounded(&raw_empty[st], ph, s_err)) { ok = false; return; }
+                *reinterpret_cast<uint4*>(rawst + (size_t)st * kStcRawBytes + u * 64 + qq * 16) = wv;
+                __syncwarp();
+                if (lane == 0) dev::mbar_arrive(&raw_full[st]);                        // release: the warp's stores are visible to the waiter
+                if (++st == kStcRawStages) { st = 0; ph ^= 1u; }
+            };
+            constexpr int kAhead = 6;                                                 // chunks of packed words in flight per thread (4 registers each)
+            uint4 wq[kAhead];
+#pragma unroll
+            for (int s_ = 0; s_ < kAhead - 1; ++s_) fetch(s_, wq[s_]);
+            for (int c = 0; c < nch; c += kAhead) {
+#pragma unroll
+                for (int s_ = 0; s_ < kAhead; ++s_) {
+                    fetch(c + s_ + kAhead - 1, wq[(s_ + kAhead - 1) % kAhead]);
+                    push(c + s_, wq[s_]);
+                }
             }
-            uint8_t* at = atiles + (size_t)buf * kStcATile + aoff;
-            put(at, w0); put(at + 16384, w1);
-            dev::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) dev::mbar_arrive(&tile_full[buf]);
-        };
-        uint32_t a0, a1, b0, b1, c0, c1, d0, d1;
-        fetch(0, a0, a1); fetch(1, b0, b1); fetch(2, c0, c1);
-        for (int c = 0; c < nch; c += 4) {
-            fetch(c + 3, d0, d1); store(c, a0, a1);
-            fetch(c + 4, a0, a1); store(c + 1, b0, b1);
-            fetch(c + 5, b0, b1); store(c + 2, c0, c1);
-            fetch(c + 6, c0, c1); store(c + 3, d0, d1);
+        } else {
+            auto put = [&](uint8_t* dst, uint32_t wd) {
+                const uint32_t mw = wd & (wd >> 1) & 0x55555555u;
+                const uint4 y = make_uint4(wd & 0x03030303u, (wd >> 2) & 0x03030303u, (wd >> 4) & 0x03030303u, (wd >> 6) & 0x03030303u);
+                const uint4 m = make_uint4(mw & 0x01010101u, (mw >> 2) & 0x01010101u, (mw >> 4) & 0x01010101u, (mw >> 6) & 0x01010101u);
+                *reinterpret_cast<uint4*>(dst) = y;
+                *reinterpret_cast<uint4*>(dst + 8 * 1024) = m;
+            };
+            // words 4 qq .. 4 qq + 3 of the chunk: K block qq >> 1, 16-byte positions 4 (qq & 1) .. + 3 of the row's 128-byte line
+            const uint32_t arow = (uint32_t)((qq >> 1) * 16384 + (u >> 3) * 1024 + (u & 7) * 128);
+            const int p0 = 4 * (qq & 1), sw = u & 7;
+            int buf = 0; uint32_t ph = 1u;                                            // tile_empty parity expected for the next use of `buf`
+            int st = 0; uint32_t rph = 0u;
+            const uint8_t* bq = Bq + (size_t)ch0 * kStcBTile;
+            for (int c = 0; c < nch && ok; ++c) {
+                if (!tc::wait_bounded(&raw_full[st], rph, s_err)) { ok = false; break; }
+                const uint4 wv = *reinterpret_cast<const uint4*>(rawst + (size_t)st * kStcRawBytes + u * 64 + qq * 16);
+                if (!tc::wait_bounded(&tile_empty[buf], ph, s_err)) { ok = false; break; }
+                if (xt == 0) {                                                        // the chunk's B tile: one bulk copy
+                    dev::mbar_arrive_expect_tx(&b_full[buf], (uint32_t)kStcBTile);
+                    dev::tma_bulk_g2s(btiles + (size_t)buf * kStcBTile, bq + (size_t)c * kStcBTile, (uint32_t)kStcBTile, &b_full[buf]);
+                }
+                uint8_t* at = atiles + (size_t)buf * kStcATile + arow;
+                put(at + (((p0 + 0) ^ sw) << 4), wv.x); put(at + (((p0 + 1) ^ sw) << 4), wv.y);
+                put(at + (((p0 + 2) ^ sw) << 4), wv.z); put(at + (((p0 + 3) ^ sw) << 4), wv.w);
+                dev::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { dev::mbar_arrive(&tile_full[buf]); dev::mbar_arrive(&raw_empty[st]); }
+                if (++buf == kStcNB) { buf = 0; ph ^= 1u; }
+                if (++st == kStcRawStages) { st = 0; rph ^= 1u; }
+            }
         }
         // ================= epilogue (warps 1-4): digits -> double, then sum_y / sum_m -> values
         if (warp <= 4) {
@@ -244,16 +287,25 @@ snp_gemv_tc_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const float
             bool have = ok && nch > 0 && tc::wait_bounded(accum_full, 0u, s_err);
             if (have) {
                 tc::fence_after();
-                uint32_t vv[32];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                             : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3]), "=r"(vv[4]), "=r"(vv[5]), "=r"(vv[6]), "=r"(vv[7]),
-                               "=r"(vv[8]), "=r"(vv[9]), "=r"(vv[10]), "=r"(vv[11]), "=r"(vv[12]), "=r"(vv[13]), "=r"(vv[14]), "=r"(vv[15]),
-                               "=r"(vv[16]), "=r"(vv[17]), "=r"(vv[18]), "=r"(vv[19]), "=r"(vv[20]), "=r"(vv[21]), "=r"(vv[22]), "=r"(vv[23]),
-                               "=r"(vv[24]), "=r"(vv[25]), "=r"(vv[26]), "=r"(vv[27]), "=r"(vv[28]), "=r"(vv[29]), "=r"(vv[30]), "=r"(vv[31])
-                             : "r"(tmem_d + ((uint32_t)(quad * 32) << 16)));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                int32_t acc[32];
+#pragma unroll
+                for (int e2 = 0; e2 < 32; ++e2) acc[e2] = 0;
+#pragma unroll 1
+                for (int a4 = 0; a4 < 4; ++a4) {                                      // the four accumulators add up exactly (int32)
+                    uint32_t vv[32];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                                 : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3]), "=r"(vv[4]), "=r"(vv[5]), "=r"(vv[6]), "=r"(vv[7]),
+                                   "=r"(vv[8]), "=r"(vv[9]), "=r"(vv[10]), "=r"(vv[11]), "=r"(vv[12]), "=r"(vv[13]), "=r"(vv[14]), "=r"(vv[15]),
+                                   "=r"(vv[16]), "=r"(vv[17]), "=r"(vv[18]), "=r"(vv[19]), "=r"(vv[20]), "=r"(vv[21]), "=r"(vv[22]), "=r"(vv[23]),
+                                   "=r"(vv[24]), "=r"(vv[25]), "=r"(vv[26]), "=r"(vv[27]), "=r"(vv[28]), "=r"(vv[29]), "=r"(vv[30]), "=r"(vv[31])
+                                 : "r"(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * a4)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int e2 = 0; e2 < 32; ++e2) acc[e2] += (int32_t)vv[e2];
+                }
+                const int32_t* vv = acc;
 #pragma unroll
                 for (int l = 0; l < 8; ++l)
                     comb[r * 8 + l] = (double)(int32_t)vv[l] + 256.0 * ((double)(int32_t)vv[8 + l] + 256.0 * ((double)(int32_t)vv[16 + l] + 256.0 * (double)(int32_t)vv[24 + l]));
@@ -283,7 +335,7 @@ snp_gemv_tc_kernel(const uint32_t* __restrict__ packed, int64_t ldw, const float
     __syncthreads();
     if (warp == 0) {
         tc::fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(32u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128u) : "memory");
     }
     if (tid == 0 && *s_err) atomicExch(err_flag, 1);
 }
