@@ -63,7 +63,7 @@ SYMBOLS = [
     "ab_io_snp_phased_ancestry_create", "ab_io_snp_phased_ancestry_free", "ab_io_snp_phased_ancestry_write", "ab_io_snp_phased_ancestry_read",
     "ab_io_snp_phased_ancestry_info", "ab_io_snp_phased_ancestry_get", "ab_io_snp_phased_ancestry_to_dense", "ab_matrix_snp_phased_ancestry_create",
     "ab_matrix_free", "ab_matrix_rows", "ab_matrix_cols", "ab_matrix_cmul", "ab_matrix_ctmul", "ab_matrix_bmul",
-    "ab_matrix_btmul", "ab_matrix_mul", "ab_matrix_cov", "ab_matrix_window_gram", "ab_matrix_sq_mul", "ab_matrix_sp_tmul",
+    "ab_matrix_btmul", "ab_matrix_mul", "ab_matrix_cov", "ab_matrix_window_gram", "ab_matrix_mul_multi", "ab_matrix_sq_mul", "ab_matrix_sp_tmul",
     "ab_glm_create", "ab_glm_free", "ab_glm_gradient", "ab_glm_hessian", "ab_glm_inv_hessian_gradient", "ab_glm_loss",
     "ab_glm_loss_full", "ab_glm_inv_link",
     "ab_state_create", "ab_state_free", "ab_state_solve", "ab_state_get_scalar", "ab_state_get_vec_f64",
@@ -120,6 +120,7 @@ def load():
     L.ab_matrix_btmul.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp]
     L.ab_matrix_mul.argtypes = [c_vp, c_vp, c_vp, c_vp]
     L.ab_matrix_cov.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp]
+    L.ab_matrix_mul_multi.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp]
     L.ab_matrix_window_gram.argtypes = [c_vp, c_vp, C.c_int, C.c_int, c_vp, C.c_int, c_vp]
     L.ab_matrix_sq_mul.argtypes = [c_vp, c_vp, c_vp]
     L.ab_matrix_sp_tmul.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]

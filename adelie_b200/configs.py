@@ -18,7 +18,7 @@ _DEFAULTS = {
     "glm_batched": 1.0,              # GLM / IRLS pin solves on the batched look-ahead kernel: 0 = off, 1 = float32 states, 2 = every dtype
     "kkt_skip_screen": 1.0,          # invariance / KKT pass streams only the non-screen columns during a path (grad completed at the end)
     "snp_tc": 1.0,                   # packed-genotype multi-response GEMV on the tensor cores (INT8 tcgen05): 1 = on
-    "snp_tc_min_k": 2.0,             # ... for at least this many classes
+    "snp_tc_min_k": 1.0,             # ... for at least this many classes
     "panel_tc": 1.0,                 # whole Gram panels on the tensor cores (tcgen05 / TMEM, TF32 operands): 1 = on, 0 = CUDA-core panel kernel
     "panel_gemm": 0.0,               # Gram panels: 1 = whole panels in one pass (fp32; experimental, currently slower), 0 = one block per pair of groups
     "sweep_xchg": 1.0,               # per-group kernel's intra-GPU exchange: 1 = one hop through L2 atomics, 0 = two-level flagged lines

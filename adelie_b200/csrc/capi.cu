@@ -294,6 +294,7 @@ static DenseMatrix<T>* snp_from_io(const SnpUnphasedIO& I, int64_t row_lo, int64
     for (int64_t j0 = 0; j0 < p;) {
         int64_t j1 = j0 + 1;
         while (j1 < p && I.outer[j1 + 1] - I.outer[j0] <= kMaxBytes) ++j1;
+        if (I.outer[j1] < I.outer[j0] || I.outer[j1] > I.buf_bytes) throw core_error("snp_unphased: malformed file (column offsets).");   // (read() checked this already)
         const uint64_t bytes = I.outer[j1] - I.outer[j0];
         if (d_file.n < bytes + 16) d_file.alloc(bytes + 16);
         AB_CUDA(cudaMemcpyAsync(d_file.p, I.buf + I.outer[j0], bytes, cudaMemcpyHostToDevice, 0));
@@ -469,6 +470,7 @@ static DenseMatrix<T>* snp_pa_from_io(const SnpPhasedAncestryIO& I, int64_t row_
     for (int64_t j0 = 0; j0 < s_;) {
         int64_t j1 = j0 + 1;
         while (j1 < s_ && I.outer[j1 + 1] - I.outer[j0] <= kMaxBytes) ++j1;
+        if (I.outer[j1] < I.outer[j0] || I.outer[j1] > I.buf_bytes) throw core_error("snp_unphased: malformed file (column offsets).");   // (read() checked this already)
         const uint64_t bytes = I.outer[j1] - I.outer[j0];
         if (d_file.n < bytes + 16) d_file.alloc(bytes + 16);
         AB_CUDA(cudaMemcpyAsync(d_file.p, I.buf + I.outer[j0], bytes, cudaMemcpyHostToDevice, 0));
@@ -673,6 +675,23 @@ int ab_matrix_mul(ab_matrix* m, const void* v, const void* w, void* out) {
     AB_TRY
     if (m->dtype == AB_F32) HostOps<float>::mul(*m->f32, (const float*)v, (const float*)w, (float*)out);
     else HostOps<double>::mul(*m->f64, (const double*)v, (const double*)w, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_mul_multi(ab_matrix* m, int64_t K, const void* v, const void* w, void* out) {
+    AB_TRY
+    if (K < 1 || K > kMultiMaxK) throw core_error("mul_multi(): the number of classes must be in [1, 16].");
+    auto run = [&](auto& M, auto* vv, auto* ww, auto* oo) {
+        using T = std::remove_cv_t<std::remove_pointer_t<decltype(oo)>>;
+        if (M.sparse) throw core_error("multi-response problems are not supported on sparse matrices.");
+        const int64_t nk = M.n * K, ldk = M.ld * K;
+        DevBuf<T> dv(ldk), dw(ldk), o(M.p * K);                         // (n_pad, K) row-major, pad rows zero
+        dv.upload(vv, nk); dw.upload(ww, nk);
+        M.d_mul_multi((int)K, 0, dv.p, dw.p, o.p);
+        M.check_tc_error();
+        o.download(oo, M.p * K); AB_CUDA(cudaStreamSynchronize(0));
+    };
+    if (m->dtype == AB_F32) run(*m->f32, (const float*)v, (const float*)w, (float*)out);
+    else run(*m->f64, (const double*)v, (const double*)w, (double*)out);
     AB_CATCH
 }
 int ab_matrix_window_gram(ab_matrix* m, const int32_t* cols, int ncol, int n_src, const void* w, int use_tc, double* out) {

@@ -53,7 +53,7 @@ struct Configs {
     static inline int glm_batched = 1;         // GLM / IRLS pin solves on the batched look-ahead kernel (panels rebuilt per IRLS iteration): 0 = off (per-group kernel), 1 = float32 states, 2 = every dtype
     static inline int kkt_skip_screen = 1;     // KKT / invariance pass over the non-screen columns only (full gradient completed when the solve ends)
     static inline int snp_tc = 1;              // packed-genotype multi-response GEMV on the tensor cores (INT8, snp_tc.cuh)
-    static inline int snp_tc_min_k = 2;        // ... for at least this many classes (K = 1 stays on the CUDA-core kernel)
+    static inline int snp_tc_min_k = 1;        // ... for at least this many classes (K = 1: 10.9 vs 14.4 ms per 5e10-genotype pass)
     static inline int panel_tc = 1;            // whole Gram panels on the tensor cores (tcgen05, TF32 operands; gram_tc.cuh): 1 = on, 0 = CUDA-core panel kernel
     static inline int panel_gemm = 0;          // Gram panels of the batched kernel: 1 = whole panels in one pass (fp32; parity-tested but measured slower), 0 = one block per pair of groups
     static inline int sweep_batch = 0;         // groups per batch of the look-ahead sweep kernel: 0 = auto (up to 6), 1 = off (per-group kernel)

@@ -85,6 +85,43 @@ struct SnpFileBase {
             throw core_error("Endianness is inconsistent! Regenerate the file on a machine with the same endianness.");
         return total;
     }
+    // A crafted / truncated header must not be able to overflow a size computation or point outside the buffer: the counts are checked
+    // against the file size BEFORE anything is multiplied, the column offsets must start behind the preamble, be non-decreasing and end
+    // inside the file.
+    static void check_counts(uint64_t total, uint64_t idx, uint64_t n_items, uint64_t bytes_per_item, uint64_t n_off) {
+        const uint64_t left = total > idx ? total - idx : 0;
+        if (bytes_per_item && n_items > left / bytes_per_item) throw core_error("File is too short for its header.");
+        const uint64_t left2 = left - n_items * bytes_per_item;
+        if (n_off > left2 / 8) throw core_error("File is too short for its header.");
+    }
+    static void check_offsets(const std::vector<uint64_t>& outer, uint64_t preamble, uint64_t total) {
+        if (outer.empty() || outer[0] < preamble) throw core_error("Column offsets point into the header.");
+        for (size_t j = 0; j + 1 < outer.size(); ++j)
+            if (outer[j] > outer[j + 1]) throw core_error("Column offsets are not monotone.");
+        if (outer.back() > total) throw core_error("Column offsets point past the end of the file.");
+    }
+    // bounds-checked cursor over one column's bytes [lo, hi)
+    struct Cursor {
+        const char* base; uint64_t pos, hi;
+        void need(uint64_t n) const { if (n > hi - pos) throw core_error("malformed file (a chunk list runs past the end of its column)."); }
+        template <class V> V get() { need(sizeof(V)); V v; std::memcpy(&v, base + pos, sizeof(V)); pos += sizeof(V); return v; }
+        void seek(uint64_t lo, uint64_t off) { if (off > hi - lo) throw core_error("malformed file (an offset points outside its column)."); pos = lo + off; }
+    };
+    // walks one chunk list starting at `cur`: f(row); rows must be < n_rows
+    template <class F> static void walk_chunks(Cursor cur, uint64_t n_rows, F f) {
+        const uint32_t n_chunks = cur.get<uint32_t>();
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            const uint64_t base = (uint64_t)cur.get<uint32_t>() * kChunk;
+            const unsigned cnt = (unsigned)cur.get<uint8_t>() + 1u;
+            cur.need(cnt);
+            for (unsigned e = 0; e < cnt; ++e) {
+                const uint64_t row = base + (uint8_t)cur.base[cur.pos + e];
+                if (row >= n_rows) throw core_error("malformed file (a row index is out of range).");
+                f(row);
+            }
+            cur.pos += cnt;
+        }
+    }
 };
 
 struct SnpUnphasedIO : SnpFileBase {
@@ -99,26 +136,23 @@ struct SnpUnphasedIO : SnpFileBase {
         size_t idx = 1;
         rows = rd<uint64_t>(buf + idx); idx += 8;
         snps = rd<uint64_t>(buf + idx); idx += 8;
-        if (total < idx + snps * 24 + (snps + 1) * 8) throw core_error("File is too short for its header.");
+        if (snps == UINT64_MAX) throw core_error("File is too short for its header.");
+        check_counts(total, idx, snps, 24, snps + 1);
         nnz.resize(snps); std::memcpy(nnz.data(), buf + idx, 8 * snps); idx += 8 * snps;
         nnm.resize(snps); std::memcpy(nnm.data(), buf + idx, 8 * snps); idx += 8 * snps;
         impute.resize(snps); std::memcpy(impute.data(), buf + idx, 8 * snps); idx += 8 * snps;
-        outer.resize(snps + 1); std::memcpy(outer.data(), buf + idx, 8 * (snps + 1));
-        if (outer[snps] > total) throw core_error("Column offsets point past the end of the file.");
+        outer.resize(snps + 1); std::memcpy(outer.data(), buf + idx, 8 * (snps + 1)); idx += 8 * (snps + 1);
+        check_offsets(outer, idx, total);
         return total;
     }
 
-    // Walks category c of column j: f(row).
+    // Walks category c of column j: f(row).  Every offset and count is checked against the column's byte range and the row count.
     template <class F> void for_each(uint64_t j, int c, F f) const {
-        const char* col = buf + outer[j];
-        const char* q = col + rd<uint64_t>(col + 8 * c);
-        const uint32_t n_chunks = rd<uint32_t>(q); q += 4;
-        for (uint32_t k = 0; k < n_chunks; ++k) {
-            const uint64_t base = (uint64_t)rd<uint32_t>(q) * kChunk; q += 4;
-            const unsigned cnt = (unsigned)(uint8_t)*q + 1u; q += 1;
-            for (unsigned e = 0; e < cnt; ++e) f(base + (uint8_t)q[e]);
-            q += cnt;
-        }
+        Cursor cur{buf, outer[j], outer[j + 1]};
+        cur.need(8 * kCategories);
+        const uint64_t off = rd<uint64_t>(buf + outer[j] + 8 * c);
+        cur.seek(outer[j], off);
+        walk_chunks(cur, rows, f);
     }
 
     // io_snp_unphased.ipp:43-69: (n, p) row-major int8, missing = -9
@@ -232,25 +266,25 @@ struct SnpPhasedAncestryIO : SnpFileBase {
         rows = rd<uint64_t>(buf + idx); idx += 8;
         snps = rd<uint64_t>(buf + idx); idx += 8;
         ancestries = (uint64_t)(uint8_t)buf[idx]; idx += 1;
+        if (snps == UINT64_MAX || (ancestries && snps > UINT64_MAX / ancestries)) throw core_error("File is too short for its header.");
         cols = snps * ancestries;
-        if (total < idx + cols * 16 + (snps + 1) * 8) throw core_error("File is too short for its header.");
+        check_counts(total, idx, cols, 16, snps + 1);
         nnz0.resize(cols); std::memcpy(nnz0.data(), buf + idx, 8 * cols); idx += 8 * cols;
         nnz1.resize(cols); std::memcpy(nnz1.data(), buf + idx, 8 * cols); idx += 8 * cols;
-        outer.resize(snps + 1); std::memcpy(outer.data(), buf + idx, 8 * (snps + 1));
-        if (outer[snps] > total) throw core_error("Column offsets point past the end of the file.");
+        outer.resize(snps + 1); std::memcpy(outer.data(), buf + idx, 8 * (snps + 1)); idx += 8 * (snps + 1);
+        check_offsets(outer, idx, total);
         return total;
     }
     template <class F> void for_each(uint64_t j, uint64_t a, int hap, F f) const {
-        const char* snp = buf + outer[j];
-        const char* blk = snp + rd<uint64_t>(snp + 8 * a);
-        const char* q = blk + rd<uint64_t>(blk + 8 * hap);
-        const uint32_t n_chunks = rd<uint32_t>(q); q += 4;
-        for (uint32_t k = 0; k < n_chunks; ++k) {
-            const uint64_t base = (uint64_t)rd<uint32_t>(q) * kChunk; q += 4;
-            const unsigned cnt = (unsigned)(uint8_t)*q + 1u; q += 1;
-            for (unsigned e = 0; e < cnt; ++e) f(base + (uint8_t)q[e]);
-            q += cnt;
-        }
+        Cursor cur{buf, outer[j], outer[j + 1]};
+        cur.need(8 * ancestries);
+        const uint64_t off_a = rd<uint64_t>(buf + outer[j] + 8 * a);
+        cur.seek(outer[j], off_a);
+        const uint64_t blk = cur.pos;
+        cur.need(16);
+        const uint64_t off_h = rd<uint64_t>(buf + blk + 8 * hap);
+        cur.seek(blk, off_h);
+        walk_chunks(cur, rows, f);
     }
     void to_dense(int8_t* out) const {                                // ipp:45-71: (n, s*A) row-major
         need_read();

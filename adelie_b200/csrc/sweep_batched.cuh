@@ -281,24 +281,63 @@ __device__ __forceinline__ int prox_post(const LanePre<P, GSP>& pre, int gs, P g
 // t >= Ccap the columns of the next batch.  One 16-byte load per source column.  del_c: lane c holds del[c]; GSP == 0: del
 // comes from dl (large groups).
 template <class T, class P, int GSP>
-__device__ __forceinline__ void apply_corrections(const T* Q, int ldq, int off, int gs, const T* dl, P del_c, P (&ga)[4], int lane)
+__device__ __forceinline__ void apply_corrections(const T* Q, int ldq, int off, int gs, const T* dl, P del_c, P (&ga)[4], int lane, P* bc)
 {
     const bool act = 4 * lane < ldq;
     const T* qcol = Q + (size_t)off * ldq + (act ? 4 * lane : 0);
-    constexpr int NC = GSP > 0 ? GSP : 32;
-#pragma unroll (GSP > 0 ? GSP : 2)
-    for (int c = 0; c < NC; ++c) {
-        const P dc = GSP > 0 ? __shfl_sync(0xffffffffu, del_c, c) : (c < gs ? (P)dl[c] : P(0));
-        if (c < gs && act) {
-            if constexpr (sizeof(T) == 4) {
-                T q4[4];
-                vec_load<T>(qcol + (size_t)c * ldq, q4);
+    if constexpr (GSP > 0) {
+        // Round 2: in-kernel counters put this routine at 1880 cycles per group update -- one shuffle + one dependent 16-byte load + 4 FMAs
+        // per source column, and at the kernel's register cap the compiler does not hoist the loads over the FMAs, so a lone warp pays the
+        // full shared-memory latency twelve times in a row.  Now: del of the whole group reaches every lane through shared memory (one
+        // store + GSP / VN broadcast loads instead of GSP shuffles), the panel rows come in waves of four independent loads, and two
+        // accumulator sets halve the FMA chain.
+        constexpr int VNP = VecT<P>::N;
+        P dall[GSP < 4 ? 4 : GSP];          // (GSP = 2 only exists as dead code of the generic instantiation)
+        __syncwarp();
+        if (lane < 16) bc[lane] = del_c;
+        __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) ga[j] += (P)q4[j] * dc;
-            } else {
-                T q2[2], q3[2];
-                vec_load<T>(qcol + (size_t)c * ldq, q2); vec_load<T>(qcol + (size_t)c * ldq + 2, q3);
-                ga[0] += (P)q2[0] * dc; ga[1] += (P)q2[1] * dc; ga[2] += (P)q3[0] * dc; ga[3] += (P)q3[1] * dc;
+        for (int q = 0; q < GSP; q += VNP) vec_load<P>(bc + q, reinterpret_cast<P(&)[VNP]>(dall[q]));
+        P gb[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int c0 = 0; c0 < GSP; c0 += 4) {
+            T qv[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (c0 + i < gs && act) {
+                    if constexpr (sizeof(T) == 4) vec_load<T>(qcol + (size_t)(c0 + i) * ldq, qv[i]);
+                    else {
+                        vec_load<T>(qcol + (size_t)(c0 + i) * ldq, reinterpret_cast<T(&)[2]>(qv[i][0]));
+                        vec_load<T>(qcol + (size_t)(c0 + i) * ldq + 2, reinterpret_cast<T(&)[2]>(qv[i][2]));
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) qv[i][j] = T(0);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ga[j] += (P)qv[0][j] * dall[c0] + (P)qv[2][j] * dall[c0 + 2];
+                gb[j] += (P)qv[1][j] * dall[c0 + 1] + (P)qv[3][j] * dall[c0 + 3];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ga[j] += gb[j];
+    } else {
+#pragma unroll 2
+        for (int c = 0; c < 32; ++c) {
+            const P dc = (c < gs ? (P)dl[c] : P(0));
+            if (c < gs && act) {
+                if constexpr (sizeof(T) == 4) {
+                    T q4[4];
+                    vec_load<T>(qcol + (size_t)c * ldq, q4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ga[j] += (P)q4[j] * dc;
+                } else {
+                    T q2[2], q3[2];
+                    vec_load<T>(qcol + (size_t)c * ldq, q2); vec_load<T>(qcol + (size_t)c * ldq + 2, q3);
+                    ga[0] += (P)q2[0] * dc; ga[1] += (P)q2[1] * dc; ga[2] += (P)q3[0] * dc; ga[3] += (P)q3[1] * dc;
+                }
             }
         }
     }
@@ -973,13 +1012,16 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                             if (PROF && prof) ++pt[6];
                         }
                         // static loads of the next group, issued behind this group's corrections
+                        long long tq = (PROF == 2 && prof) ? clock64() : 0;
                         if (GSP <= 16 && k + 1 < nbg) {
                             const int gs1 = __shfl_sync(0xffffffffu, m_cur.gs, k + 1);
                             if (gs1 > 1) prox_pre<T, P, GL>(pre, Q + Ccap * ldq + (k + 1) * a.rec_stride, gs1, aold + par * Ccap + off + gs, arot + par * Ccap + off + gs, lane);
                         }
+                        if (PROF == 2 && prof) { const long long t_ = clock64(); ppx[0] += t_ - tq; tq = t_; }
                         if (changed) {
-                            if (GSP <= 16) apply_corrections<T, P, GL>(Q, ldq, off, gs, dl, del_c, ga, lane);
-                            else apply_corrections<T, P, 0>(Q, ldq, off, gs, dl, del_c, ga, lane);
+                            if (GSP <= 16) apply_corrections<T, P, GL>(Q, ldq, off, gs, dl, del_c, ga, lane, p_gk);
+                            else apply_corrections<T, P, 0>(Q, ldq, off, gs, dl, del_c, ga, lane, p_gk);
+                            if (PROF == 2 && prof) { const long long t_ = clock64(); ppx[7] += t_ - tq; tq = t_; }
                             if (kind == kSweepScreen && !was_active) {           // add_active_set (:294-304)
                                 if (ps.A >= a.max_active_size) ps.error = kErrMaxActive;
                                 else {

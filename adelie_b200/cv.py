@@ -35,8 +35,8 @@ class CVGrpnetResult:
 
 def cv_grpnet(X, glm, *, n_threads: int = 1, early_exit: bool = False, min_ratio: float = 1e-1, lmda_path_size: int = 100,
               n_folds: int = 5, seed: int = None, **grpnet_params):
-    if getattr(glm, "is_multi", False):
-        raise RuntimeError("adelie_b200: cv_grpnet supports single-response families.")
+    # multi-response families (adelie/cv.py:92, is_multi): betas are (L, p K), intercepts (L, K), etas (L, n, K); everything below is
+    # shape-agnostic (diagnostic.predict / coefficient handle both layouts)
     if isinstance(X, np.ndarray):
         X = _matrix.dense(X, method="naive", n_threads=n_threads)        # uploaded once, shared by every solve below
     assert isinstance(X, _matrix.MatrixNaiveBase)
@@ -67,7 +67,7 @@ def cv_grpnet(X, glm, *, n_threads: int = 1, early_exit: bool = False, min_ratio
         pairs = [coefficient(lmda=lm, betas=state.betas, intercepts=state.intercepts, lmdas=state.lmdas) for lm in full_lmdas]
         etas = predict(X=X, betas=scipy.sparse.vstack([b for b, _ in pairs]), intercepts=np.array([b0 for _, b0 in pairs]),
                        offsets=state._offsets, n_threads=n_threads)
-        etas = np.ascontiguousarray(etas, dtype=glm.dtype)
+        etas = np.ascontiguousarray(etas, dtype=glm.dtype)                 # (L, n) or (L, n, K): one contiguous eta per lambda
         full_losses = np.array([glm.loss(eta) for eta in etas])
         train_losses = weights_sum * np.array([glm_c.loss(eta) for eta in etas])
         cv_losses[fold] = (full_losses - train_losses) / held_weight if held_weight > 0 else 0

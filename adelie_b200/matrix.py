@@ -573,9 +573,16 @@ class _KroneckerEye(MatrixNaiveBase):
             self.ctmul(j + c, v[c], out)
 
     def mul(self, v, weights, out):
-        tmp = np.empty(self._mat.cols(), dtype=self.dtype)
+        base = self._mat
+        if (isinstance(base, _DeviceMatrix) and not isinstance(base, (_Sparse, _DeviceSparse)) and self._K <= 16 and isinstance(out, np.ndarray)
+                and out.dtype == self.dtype and out.flags.c_contiguous):
+            # one device pass for all K classes (packed genotypes: the INT8 tensor-core kernel)
+            v = np.ascontiguousarray(v, dtype=self.dtype); weights = np.ascontiguousarray(weights, dtype=self.dtype)
+            _lib.check(_lib.load().ab_matrix_mul_multi(base._core(), self._K, _lib.ptr(v), _lib.ptr(weights), _lib.ptr(out)))
+            return
+        tmp = np.empty(base.cols(), dtype=self.dtype)
         for l in range(self._K):
-            self._mat.mul(self._sl(v, l), self._sl(weights, l), tmp)
+            base.mul(self._sl(v, l), self._sl(weights, l), tmp)
             out[l::self._K] = tmp
 
     def cov(self, j, q, sqrt_weights, out):

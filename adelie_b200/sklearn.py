@@ -70,11 +70,12 @@ class GroupElasticNet(BaseEstimator, RegressorMixin):
         """R^2 of the (last-lambda) linear predictions for the regression families; accuracy for the classification families."""
         self._check_fitted()
         pred = self.predict(X)
-        pred = pred[-1] if pred.ndim > np.ndim(y) else pred
         y = np.asarray(y)
         if self.family in ("binomial", "multinomial"):
             labels = y if y.ndim == 1 else np.argmax(y, axis=-1)
+            pred = pred[-1] if pred.ndim > labels.ndim else pred       # grpnet solver: one prediction per lambda, score the last
             return float(np.mean(pred == labels))
+        pred = pred[-1] if pred.ndim > y.ndim else pred
         w = np.ones(y.shape[0]) if sample_weight is None else np.asarray(sample_weight)
         w = w.reshape((-1,) + (1,) * (y.ndim - 1))
         ss_res = np.sum(w * (y - pred) ** 2); ss_tot = np.sum(w * (y - np.average(y, axis=0, weights=w.ravel())) ** 2)

@@ -122,6 +122,10 @@ int ab_matrix_ctmul(ab_matrix* m, int64_t j, double v, void* out);              
 int ab_matrix_bmul(ab_matrix* m, int64_t j, int64_t q, const void* v, const void* w, void* out);        /* X[:,j:j+q]^T (v*w) */
 int ab_matrix_btmul(ab_matrix* m, int64_t j, int64_t q, const void* v, void* out);                      /* out += X[:,j:j+q] v */
 int ab_matrix_mul(ab_matrix* m, const void* v, const void* w, void* out);                               /* X^T (v*w) */
+/* `mul` of kron(X, I_K) (MatrixNaiveKroneckerEye::mul, adelie_core/matrix/matrix_naive_kronecker_eye.ipp:29-352) in ONE pass over X:
+ * v, w (n, K) row-major, out (p, K) row-major: out[j, l] = sum_i X[i, j] v[i, l] w[i, l].  Dense and snp matrices; packed genotypes in
+ * float32 with 2 <= K <= 8 run on the INT8 tensor-core kernel (csrc/snp_tc.cuh). */
+int ab_matrix_mul_multi(ab_matrix* m, int64_t K, const void* v, const void* w, void* out);
 /* Weighted Gram of a window of columns, out[s * ncol + u] = sum_i w_i X[i, cols[s]] X[i, cols[u]] for s < n_src <= 64, u < ncol <= 128
  * (row-major n_src x ncol, double): the Gram-panel kernel of the batched sweep exposed for parity tests.  Generalises cov()
  * (matrix_naive_base.hpp:101-105) to a column list.  use_tc = 1: tcgen05 tensor cores with TF32 operands, 0: fp32 CUDA cores.

@@ -44,7 +44,7 @@ for rep in range(2):
         cw = ["wait_panel", "wait_gready", "prox", "corr+book", "batch_ovh", "sweep_bdry"]
         dw = ["wait_full", "dot", "bar+publish", "wait_prox", "update", "sweep_wait"]
         print(f"  CW cycles/group (CTA0, cumulative): " + " ".join(f"{nm}={stt[i]/groups_:.0f}" for i, nm in enumerate(cw)) + f" groups={groups_:.0f} batches={batches_:.0f}")
-        px = ["pre", "grad_rot", "rootfind", "sums", "rot_back", "newton_its", "unchanged"]
+        px = ["pre", "grad_rot", "rootfind", "sums", "rot_back", "newton_its", "unchanged", "apply_corr"]
         print(f"  prox cycles/group: " + " ".join(f"{nm}={stt[16+i]/groups_:.2f}" for i, nm in enumerate(px)))
         print(f"  DW cycles/group (CTA0, cumulative): " + " ".join(f"{nm}={stt[8+i]/groups_:.0f}" for i, nm in enumerate(dw)))
     elif int(os.environ.get("PROF", 0)):

@@ -144,6 +144,49 @@ def test_cv_grpnet_vs_oracle_procedure(family):
     np.testing.assert_allclose(res.avg_losses, ref.mean(axis=0), rtol=1e-5, atol=1e-8)
 
 
+def test_cv_grpnet_multigaussian_vs_oracle_procedure():
+    """Multi-response CV (adelie/cv.py:92 is_multi): the K-fold procedure on a multigaussian problem against the same procedure on the oracle."""
+    rng = np.random.default_rng(4)
+    n, p, K, n_folds, L, min_ratio = 500, 20, 3, 4, 10, 0.2
+    X = np.asfortranarray(rng.normal(size=(n, p)))
+    Bt = np.zeros((p, K)); Bt[:4] = rng.normal(size=(4, K))
+    Y = np.ascontiguousarray(X @ Bt + 0.5 + rng.normal(size=(n, K)))
+    kw = dict(tol=1e-13)
+    res = ad.cv_grpnet(X, ad.glm.multigaussian(Y), n_folds=n_folds, seed=5, min_ratio=min_ratio, lmda_path_size=L, **kw)
+    # the procedure restated on the oracle
+    np.random.seed(5)
+    order = np.random.choice(n, n, replace=False)
+    fold_size, remaining = divmod(n, n_folds)
+    w = np.full(n, 1 / n)
+    loss = lambda eta, ww: np.sum(ww[:, None] * (0.5 * eta ** 2 - Y * eta)) / K          # glm_multigaussian.ipp:17-68
+    lm0 = orc.grpnet(X, orc.glm_spec("multigaussian", Y, w), lmda_path_size=1, **kw).lmda_max
+    full = lm0 * np.logspace(0, np.log10(min_ratio), L)
+    ref = np.empty((n_folds, L))
+    for fold in range(n_folds):
+        begin = (fold_size + 1) * min(fold, remaining) + max(fold - remaining, 0) * fold_size
+        held = order[begin:begin + fold_size + (fold < remaining)]
+        wf = w.copy(); wf[held] = 0; ws = wf.sum(); wf /= ws
+        spec = orc.glm_spec("multigaussian", Y, wf)
+        lmf = orc.grpnet(X, spec, lmda_path_size=1, **kw).lmda_max
+        cur = lmf * np.logspace(0, np.log10(min_ratio), L)
+        aug = np.sort(np.concatenate([full, cur[cur > full[0]]]))[::-1]
+        st = orc.grpnet(X, spec, lmda_path=aug, early_exit=False, **kw)
+        B = np.asarray(st.betas.todense()); b0 = np.asarray(st.intercepts); lm = np.asarray(st.lmdas)
+        for i, l in enumerate(full):
+            k = int(np.argmin(np.abs(lm - l)))
+            eta = X @ B[k].reshape(p, K) + b0[k][None]
+            ref[fold, i] = (loss(eta, w) - ws * loss(eta, wf)) / w[held].sum()
+    np.testing.assert_allclose(res.lmdas, full, rtol=1e-9)
+    np.testing.assert_allclose(res.losses, ref, rtol=1e-5, atol=1e-8)
+    assert res.best_idx == int(np.argmin(ref.mean(axis=0)))
+    # sklearn front-end: multinomial score uses the last lambda's prediction (ADVICE r1)
+    labels = rng.integers(0, K, size=n); onehot = np.eye(K)[labels]
+    est = ad.sklearn.GroupElasticNet(solver="grpnet", family="multinomial").fit(X, onehot, lmda_path_size=5, min_ratio=0.5)
+    sc = est.score(X, onehot)
+    last = np.argmax(np.asarray(ad.diagnostic.predict(X, est.coef_, est.intercept_))[-1], axis=-1)
+    assert sc == float(np.mean(last == labels))
+
+
 @pytest.mark.parametrize("dtype,atol", [(np.float64, 1e-12), (np.float32, 2e-5)])
 def test_standardize_snp_unphased_view(dtype, atol):
     """standardize(snp_unphased): a view on the packed genotypes (nothing materialised), every operator and the path vs the NumPy equivalent"""

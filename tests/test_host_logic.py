@@ -134,3 +134,35 @@ def test_matrices_are_freed_by_refcount_not_by_the_cyclic_gc():
             assert w() is None
     finally:
         gc.enable()
+
+
+def test_snpdat_reader_rejects_malformed_headers(tmp_path):
+    """crafted headers must not overflow size computations or walk outside the buffer; the reader raises instead."""
+    import struct
+    rng = np.random.default_rng(0)
+    n, p = 300, 7
+    cd = np.asfortranarray(rng.choice([-9, 0, 1, 2], size=(n, p), p=[0.1, 0.6, 0.2, 0.1]).astype(np.int8))
+    fn = str(tmp_path / "ok.snpdat")
+    h = ad.io.snp_unphased(fn)
+    h.write(cd)
+    h.read()
+    D = h.to_dense()
+    assert np.array_equal(D, cd)
+    raw = bytearray(open(fn, "rb").read())
+    pre = 1 + 16 + p * 24
+    def attempt(mut, match):
+        b = bytearray(raw); mut(b)
+        f2 = str(tmp_path / "bad.snpdat"); open(f2, "wb").write(b)
+        g = ad.io.snp_unphased(f2)
+        with pytest.raises(RuntimeError, match=match):
+            g.read(); g.to_dense()
+    attempt(lambda b: b.__setitem__(slice(9, 17), struct.pack("<Q", 2 ** 61)), "too short")                 # snps * 24 would overflow
+    attempt(lambda b: b.__setitem__(slice(9, 17), struct.pack("<Q", 2 ** 64 - 1)), "too short")
+    attempt(lambda b: b.__setitem__(slice(pre, pre + 8), struct.pack("<Q", 3)), "header")                   # outer[0] inside the preamble
+    attempt(lambda b: b.__setitem__(slice(pre + 16, pre + 24), struct.pack("<Q", 40)), "monotone|header")   # outer goes backwards
+    attempt(lambda b: b.__setitem__(slice(pre + 8 * p, pre + 8 * p + 8), struct.pack("<Q", len(raw) + 99)), "past the end")
+    col0 = struct.unpack("<Q", raw[pre:pre + 8])[0]
+    attempt(lambda b: b.__setitem__(slice(col0, col0 + 8), struct.pack("<Q", 10 ** 9)), "malformed")        # category offset outside the column
+    off1 = struct.unpack("<Q", raw[col0 + 8:col0 + 16])[0]
+    attempt(lambda b: b.__setitem__(slice(col0 + off1, col0 + off1 + 4), struct.pack("<I", 10 ** 6)), "malformed")    # chunk count runs off the column
+    attempt(lambda b: b.__setitem__(slice(col0 + off1 + 4, col0 + off1 + 8), struct.pack("<I", 10 ** 5)), "malformed")  # row index out of range
