@@ -237,7 +237,12 @@ cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovIt
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool ones = it.col < 0;
     const T* Xg = X + (int64_t)(ones ? 0 : it.col) * ld;
-    double acc[NP];
+    // accumulator type: the value type for float32 (a thread adds a few hundred terms; the reference's float templates accumulate in float
+    // too), double for float64.  On the GLM path every screen group is re-decomposed in every IRLS iteration and this kernel was bound by
+    // the FP64 pipe (78 DFMA per row for GSP = 12) and by its 156 accumulator registers, not by HBM (round 2: config-3 shard, 7.7 ms per
+    // IRLS iteration at 26 % of the HBM peak).
+    using ACC = typename std::conditional<std::is_same<T, float>::value, float, double>::type;
+    ACC acc[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) acc[q] = 0;
     for (int64_t i = row0 + (int64_t)tid * VN; i < row1; i += 256 * VN) {
@@ -265,15 +270,15 @@ cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovIt
             int q = 0;
 #pragma unroll
             for (int a = 0; a < GSP; ++a) {
-                const double xw = (double)(x[a][k] * wv[k]);
+                const ACC xw = (ACC)(x[a][k] * wv[k]);
 #pragma unroll
-                for (int b = 0; b <= a; ++b, ++q) acc[q] += xw * (double)x[b][k];
+                for (int b = 0; b <= a; ++b, ++q) acc[q] += xw * (ACC)x[b][k];
             }
         }
     }
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-        const double t = dev::warp_sum(acc[q]);
+        const double t = dev::warp_sum((double)acc[q]);
         if (lane == 0) s_red[warp][q] = t;
     }
     __syncthreads();

@@ -444,7 +444,8 @@ struct DenseMatrix {
         if (n_rb > 1) { part.reserve_keep((size_t)n_rb * c_total, stream); out = part.p; }
         if (gs_max >= 1 && gs_max <= 4) cov_small_launch<4>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
         else if (gs_max > 4 && gs_max <= 8) cov_small_launch<8>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
-        else if (gs_max > 8 && gs_max <= 12) cov_small_launch<12>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
+        else if (gs_max > 8 && gs_max <= 10) cov_small_launch<10>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
+        else if (gs_max > 10 && gs_max <= 12) cov_small_launch<12>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
         else cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, out, c_total, rows_per_block, K);
         if (n_rb > 1) sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
         AB_CUDA(cudaGetLastError());
