@@ -219,31 +219,34 @@ __device__ __forceinline__ int prox_post(const LanePre<P, GSP>& pre, int gs, P g
         at = (on && gt != P(0)) ? gt / (pre.A + l2k) : P(0);
     } else {
         const P tol_eff = fmax(tol, ProxEps<P>::floor_tol());
-        // One evaluation site.  mode 0: phi(0), doubles as the ||v|| <= l1 test (newton.hpp:62-66); 1: warm start; 2: Newton
+        // Start: phi(0) -- which doubles as the ||v|| <= l1 test (newton.hpp:62-66) -- and phi at the warm start travel through ONE
+        // butterfly (round 2: they were two dependent evaluations, ~250 cycles of the control warp's chain per group update).
         const P hw = (pre.h0sq > P(0)) ? FM::sqrt_(pre.h0sq) : P(0);
-        P h = 0, t_keep = 0, sd_keep = 0, u = 0;
-        int mode = 0; bool zero = false;
+        P h = 0, u = FM::rcp(l1k), t, sd;
+        bool zero = false;
+        {
+            const P uw = FM::rcp(D * hw + l1k);
+            const P q0 = gt * u, qw = gt * uw;
+            P v4s[4] = {q0 * q0, q0 * q0 * D * u, qw * qw, qw * qw * D * uw};
+            seg16_allsum<4>(v4s);
+            t = v4s[0]; sd = v4s[1];
+            if (!(t > P(1))) zero = true;
+            else if (hw > P(0) && (v4s[2] - P(1) >= -tol_eff)) { h = hw; u = uw; t = v4s[2]; sd = v4s[3]; }   // left of the root: monotone from here
+        }
+        if (!zero) {
 #pragma unroll 1
-        while (true) {
-            u = FM::rcp(D * h + l1k);
-            const P qq = gt * u;
-            const P xx = qq * qq;
-            P v2[2] = {xx, xx * D * u};
-            seg16_allsum<2>(v2);
-            P t = v2[0], sd = v2[1];
-            if (mode == 0) {
-                if (!(t > P(1))) { zero = true; break; }
-                if (hw > P(0)) { t_keep = t; sd_keep = sd; h = hw; mode = 1; continue; }
-                mode = 2;
-            } else if (mode == 1) {
-                mode = 2;
-                if (!(t - P(1) >= -tol_eff)) { h = 0; t = t_keep; sd = sd_keep; u = FM::rcp(l1k); }   // right of the root: restart from 0
+            while (fabs(t - P(1)) > tol_eff && nit < max_iters) {
+                // h - fh / dfh with dfh = -sd (1 + sqrt t) / t   (optimization/newton.hpp:56-63), one reciprocal
+                const P hn = fmax(h + (t - P(1)) * t * FM::rcp(sd * (P(1) + FM::sqrt_(t))), P(0));
+                if (hn == h) break;                                   // no representable progress left
+                h = hn; ++nit;
+                u = FM::rcp(D * h + l1k);
+                const P qq = gt * u;
+                const P xx = qq * qq;
+                P v2[2] = {xx, xx * D * u};
+                seg16_allsum<2>(v2);
+                t = v2[0]; sd = v2[1];
             }
-            if (!(fabs(t - P(1)) > tol_eff) || nit >= max_iters) break;
-            // h - fh / dfh with dfh = -sd (1 + sqrt t) / t   (optimization/newton.hpp:56-63), one reciprocal
-            const P hn = fmax(h + (t - P(1)) * t * FM::rcp(sd * (P(1) + FM::sqrt_(t))), P(0));
-            if (hn == h) break;                                   // no representable progress left
-            h = hn; ++nit;
         }
         at = (on && !zero) ? h * gt * u : P(0);                   // x = h v / (D h + l1)   (newton.hpp:109)
     }
@@ -254,8 +257,8 @@ __device__ __forceinline__ int prox_post(const LanePre<P, GSP>& pre, int gs, P g
     const P d = at - pre.ao;
     P v4[4] = {d * d, pre.A * d * d, d * (2 * gt0 - d * pre.A), -pre.xmt * d};
     seg16_allsum<4>(v4);
-    if (sqrt(v4[0]) <= dbeta_tol * sqrt((P)gs)) { if (pp) ++pp[6]; return 0; }      // :146-147
-    ps.cm = fmax(ps.cm, (double)(v4[1] / gs));
+    if (v4[0] <= dbeta_tol * dbeta_tol * (P)gs) { if (pp) ++pp[6]; return 0; }      // ||d|| <= dbeta_tol sqrt(gs) (:146-147), squared
+    ps.cm = fmax(ps.cm, (double)(v4[1] * FM::rcp((P)gs)));
     ps.rsq += (double)v4[2];
     ps.resid_sum += (double)v4[3];
     // ---- back to the original basis: del = a_old - a_new = V (ao - at) = -V d

@@ -24,7 +24,7 @@ ad.set_configs("sweep_batch", int(os.environ.get("BATCH", 0)))
 ad.set_configs("sweep_xchg", int(os.environ.get("XCHG", 1)))
 for rep in range(2):
     t = time.time()
-    st = ad.grpnet(X, ad.glm.gaussian(y, dtype=dtype), groups=groups, early_exit=False, lmda_path_size=L, progress_bar=False)
+    st = ad.grpnet(X, ad.glm.gaussian(y, dtype=dtype), groups=groups, early_exit=False, lmda_path_size=L, progress_bar=False, newton_tol=float(os.environ.get('NEWTON_TOL', 1e-12)), tol=float(os.environ.get('TOL', 1e-7)))
     wall = time.time() - t
     print(f"rep {rep}: wall {wall:.3f}s solve {st.total_time:.3f}s err='{st.error}' nl={len(st.lmdas)} sweeps={st.n_sweeps} "
           f"updates={st.n_group_updates} kernel_time={st.time_sweep_kernel:.3f}s pin_solves={st.n_pin_solves} "
