@@ -18,7 +18,7 @@ from . import matrix
 from . import solver
 from . import state
 from .configs import set_configs
-from .solver import grpnet
+from .solver import grpnet, gaussian_cov
 from .cv import cv_grpnet
 
 __version__ = "0.1.0"

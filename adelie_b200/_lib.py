@@ -44,6 +44,28 @@ class StateArgs(C.Structure):
     ]
 
 
+class CovStateArgs(C.Structure):
+    """Mirror of ``ab_cov_state_args`` (include/adelie_b200.h)."""
+    _fields_ = [
+        ("dtype", C.c_int32),
+        ("v", c_vp),
+        ("groups", c_vp), ("group_sizes", c_vp), ("G", c_i64), ("alpha", C.c_double), ("penalty", c_vp),
+        ("lmda_path", c_vp), ("lmda_path_len", c_i64), ("lmda_max", C.c_double), ("min_ratio", C.c_double),
+        ("lmda_path_size", c_i64),
+        ("setup_lmda_max", C.c_int32), ("setup_lmda_path", C.c_int32),
+        ("max_screen_size", c_i64), ("max_active_size", c_i64), ("pivot_subset_ratio", C.c_double),
+        ("pivot_subset_min", c_i64), ("pivot_slack_ratio", C.c_double),
+        ("screen_rule", C.c_int32),
+        ("max_iters", c_i64), ("tol", C.c_double), ("rdev_tol", C.c_double), ("newton_tol", C.c_double),
+        ("newton_max_iters", c_i64),
+        ("early_exit", C.c_int32), ("n_threads", c_i64),
+        ("screen_set", c_vp), ("screen_set_size", c_i64), ("screen_beta", c_vp), ("screen_beta_size", c_i64),
+        ("screen_is_active", c_vp), ("active_set_size", c_i64), ("active_set", c_vp),
+        ("rsq", C.c_double), ("lmda", C.c_double), ("grad", c_vp),
+        ("screen_grad", c_vp),
+    ]
+
+
 EXIT_COND_T = C.CFUNCTYPE(C.c_int, c_vp)
 CHECK_SIGNALS_T = C.CFUNCTYPE(C.c_int)
 
@@ -69,6 +91,10 @@ SYMBOLS = [
     "ab_state_create", "ab_state_free", "ab_state_solve", "ab_state_get_scalar", "ab_state_get_vec_f64",
     "ab_state_get_vec_i64", "ab_state_get_betas", "ab_state_get_screen_transform",
     "ab_pin_naive_solve",
+    "ab_matrix_cov_dense_create", "ab_matrix_cov_lazy_create", "ab_matrix_cov_free", "ab_matrix_cov_cols", "ab_matrix_cov_bmul",
+    "ab_matrix_cov_mul", "ab_matrix_cov_to_dense", "ab_matrix_cov_cache_info",
+    "ab_cov_state_create", "ab_cov_state_free", "ab_cov_state_solve", "ab_cov_pin_solve", "ab_cov_state_get_scalar",
+    "ab_cov_state_get_vec_f64", "ab_cov_state_get_vec_i64", "ab_cov_state_get_betas", "ab_cov_state_get_screen_transform",
     "ab_bcd_solve", "ab_bcd_root_lower_bound", "ab_bcd_root_upper_bound", "ab_bcd_root_function",
 ]
 
@@ -141,6 +167,23 @@ def load():
     L.ab_state_get_vec_i64.argtypes = [c_vp, C.c_char_p, c_vp, c_i64, C.POINTER(c_i64)]
     L.ab_state_get_betas.argtypes = [c_vp, c_vp, c_vp, c_vp, C.POINTER(c_i64), C.POINTER(c_i64)]
     L.ab_state_get_screen_transform.argtypes = [c_vp, c_i64, c_vp, c_i64, C.POINTER(c_i64)]
+    L.ab_matrix_cov_dense_create.argtypes = [C.c_int, c_vp, c_i64, C.c_int, c_i64, C.c_int, C.POINTER(c_vp)]
+    L.ab_matrix_cov_lazy_create.argtypes = [C.c_int, c_vp, c_i64, c_i64, C.c_int, c_i64, C.c_int, C.POINTER(c_vp)]
+    L.ab_matrix_cov_free.argtypes = [c_vp]
+    L.ab_matrix_cov_cols.argtypes = [c_vp, C.POINTER(c_i64)]
+    L.ab_matrix_cov_bmul.argtypes = [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]
+    L.ab_matrix_cov_mul.argtypes = [c_vp, c_vp, c_vp, c_i64, c_vp]
+    L.ab_matrix_cov_to_dense.argtypes = [c_vp, c_i64, c_i64, c_vp]
+    L.ab_matrix_cov_cache_info.argtypes = [c_vp, C.POINTER(c_i64)]
+    L.ab_cov_state_create.argtypes = [C.POINTER(CovStateArgs), c_vp, C.POINTER(c_vp)]
+    L.ab_cov_state_free.argtypes = [c_vp]
+    L.ab_cov_state_solve.argtypes = [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_double)]
+    L.ab_cov_pin_solve.argtypes = [c_vp, c_vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_double)]
+    L.ab_cov_state_get_scalar.argtypes = [c_vp, C.c_char_p, C.POINTER(C.c_double)]
+    L.ab_cov_state_get_vec_f64.argtypes = [c_vp, C.c_char_p, c_vp, c_i64, C.POINTER(c_i64)]
+    L.ab_cov_state_get_vec_i64.argtypes = [c_vp, C.c_char_p, c_vp, c_i64, C.POINTER(c_i64)]
+    L.ab_cov_state_get_betas.argtypes = [c_vp, c_vp, c_vp, c_vp, C.POINTER(c_i64), C.POINTER(c_i64)]
+    L.ab_cov_state_get_screen_transform.argtypes = [c_vp, c_i64, c_vp, c_i64, C.POINTER(c_i64)]
     L.ab_configs_set.argtypes = [C.c_char_p, C.c_double]
     L.ab_configs_get.argtypes = [C.c_char_p, C.POINTER(C.c_double)]
     L.ab_bcd_solve.argtypes = [C.c_int, c_i64, c_vp, c_vp, C.c_double, C.c_double, C.c_double, c_i64, c_vp, C.POINTER(c_i64)]

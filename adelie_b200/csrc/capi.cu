@@ -11,6 +11,7 @@
 #include "cox.cuh"
 #include "solver.cuh"
 #include "solver_glm.cuh"
+#include "cov.cuh"
 #include <memory>
 
 using namespace ab;
@@ -21,6 +22,8 @@ struct ab_matrix { int dtype; DenseMatrix<float>* f32 = nullptr; DenseMatrix<dou
 struct ab_glm { int dtype; int family; Glm<float>* f32 = nullptr; Glm<double>* f64 = nullptr; };
 struct ab_io_snp { SnpUnphasedIO io; ab_io_snp(const char* f, const char* m) : io(f, m) {} };
 struct ab_io_snp_pa { SnpPhasedAncestryIO io; ab_io_snp_pa(const char* f, const char* m) : io(f, m) {} };
+struct ab_cov_matrix { int dtype; CovMatrix<float>* f32 = nullptr; CovMatrix<double>* f64 = nullptr; };
+struct ab_cov_state { int dtype; CovPathState<float>* f32 = nullptr; CovPathState<double>* f64 = nullptr; std::string error; double total_time = 0; };
 struct ab_state { int dtype; PathState<float>* f32 = nullptr; PathState<double>* f64 = nullptr; std::string error; double total_time = 0; };
 
 #define AB_TRY try {
@@ -96,6 +99,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "snp_tc_min_k") Configs::snp_tc_min_k = (int)value;
     else if (s == "kkt_skip_screen") Configs::kkt_skip_screen = (int)value;
     else if (s == "glm_batched") Configs::glm_batched = (int)value;
+    else if (s == "cov_cluster") Configs::cov_cluster = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -120,6 +124,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "snp_tc_min_k") *value = Configs::snp_tc_min_k;
     else if (s == "kkt_skip_screen") *value = Configs::kkt_skip_screen;
     else if (s == "glm_batched") *value = Configs::glm_batched;
+    else if (s == "cov_cluster") *value = Configs::cov_cluster;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -1083,6 +1088,224 @@ int ab_pin_naive_solve(ab_state* s, int (*check_signals)(void), char* err, size_
     if (total_time) *total_time = s->total_time;
     if (err && errlen) { std::strncpy(err, s->error.c_str(), errlen - 1); err[errlen - 1] = 0; }
     return AB_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------ covariance method
+template <class T>
+static CovPathState<T>* make_cov_state(const ab_cov_state_args* a, CovMatrix<T>* A) {
+    auto st = std::make_unique<CovPathState<T>>();
+    auto& s = *st;
+    s.A = A; s.p = A->cols(); s.G = a->G;
+    if (a->G < 1) throw core_error("groups must be non-empty.");
+    s.groups.assign(a->groups, a->groups + a->G);
+    s.group_sizes.assign(a->group_sizes, a->group_sizes + a->G);
+    s.alpha = (T)a->alpha;
+    s.penalty.assign((const T*)a->penalty, (const T*)a->penalty + a->G);
+    if (a->v) s.v.assign((const T*)a->v, (const T*)a->v + s.p); else s.v.assign(s.p, T(0));
+    s.min_ratio = (T)a->min_ratio; s.lmda_path_size = a->lmda_path_size; s.max_screen_size = a->max_screen_size; s.max_active_size = a->max_active_size;
+    s.pivot_subset_ratio = (T)a->pivot_subset_ratio; s.pivot_subset_min = a->pivot_subset_min; s.pivot_slack_ratio = (T)a->pivot_slack_ratio;
+    s.screen_rule = a->screen_rule; s.max_iters = a->max_iters; s.tol = (T)a->tol; s.rdev_tol = (T)a->rdev_tol;
+    s.newton_tol = (T)a->newton_tol; s.newton_max_iters = a->newton_max_iters; s.early_exit = a->early_exit;
+    s.setup_lmda_max = a->setup_lmda_max; s.setup_lmda_path = a->setup_lmda_path; s.n_threads = a->n_threads;
+    s.lmda_max = (T)a->lmda_max; s.lmda = (T)a->lmda; s.rsq = (T)a->rsq;
+    if (a->lmda_path && a->lmda_path_len > 0) s.lmda_path.assign((const T*)a->lmda_path, (const T*)a->lmda_path + a->lmda_path_len);
+    s.screen_set.assign(a->screen_set, a->screen_set + a->screen_set_size);
+    s.screen_beta.assign((const T*)a->screen_beta, (const T*)a->screen_beta + a->screen_beta_size);
+    s.screen_is_active.assign(a->screen_is_active, a->screen_is_active + a->screen_set_size);
+    s.active_set_size = a->active_set_size;
+    s.active_set.assign(a->active_set, a->active_set + a->G);
+    if (a->grad) s.grad.assign((const T*)a->grad, (const T*)a->grad + s.p); else s.grad.assign(s.p, T(0));
+    for (int64_t g : s.screen_set) if (g < 0 || g >= a->G) throw core_error("screen_set entries must be in [0, G).");
+    s.validate_and_init();
+    if (a->screen_grad) {                                         // pin state: the gradient on the screen values is an input
+        if ((size_t)a->screen_beta_size != s.screen_grad.size()) throw core_error("screen_grad must be (bs,) where screen_beta is (bs,).");
+        s.screen_grad.assign((const T*)a->screen_grad, (const T*)a->screen_grad + a->screen_beta_size);
+    }
+    return st.release();
+}
+
+template <class T>
+static int cov_state_vec_f64(const CovPathState<T>& s, const std::string& nm, double* out, int64_t cap, int64_t* len) {
+    if (nm == "lmda_path") return copy_vec<T>(s.lmda_path, out, cap, len);
+    if (nm == "screen_beta") return copy_vec<T>(s.screen_beta, out, cap, len);
+    if (nm == "screen_grad") return copy_vec<T>(s.screen_grad, out, cap, len);
+    if (nm == "screen_vars") return copy_vec<T>(s.screen_vars, out, cap, len);
+    if (nm == "grad") return copy_vec<T>(s.grad, out, cap, len);
+    if (nm == "abs_grad") return copy_vec<T>(s.abs_grad, out, cap, len);
+    if (nm == "v") return copy_vec<T>(s.v, out, cap, len);
+    if (nm == "devs") return copy_vec<T>(s.devs, out, cap, len);
+    if (nm == "lmdas") return copy_vec<T>(s.lmdas, out, cap, len);
+    if (nm == "rsqs") return copy_vec<T>(s.rsqs, out, cap, len);
+    if (nm == "intercepts") return copy_vec<T>(s.intercepts, out, cap, len);
+    if (nm == "penalty") return copy_vec<T>(s.penalty, out, cap, len);
+    if (nm == "benchmark_screen") return copy_vec<double>(s.benchmark_screen, out, cap, len);
+    if (nm == "benchmark_fit_screen") return copy_vec<double>(s.benchmark_fit_screen, out, cap, len);
+    if (nm == "benchmark_fit_active") return copy_vec<double>(s.benchmark_fit_active, out, cap, len);
+    if (nm == "benchmark_kkt") return copy_vec<double>(s.benchmark_kkt, out, cap, len);
+    if (nm == "benchmark_invariance") return copy_vec<double>(s.benchmark_invariance, out, cap, len);
+    g_last_error = "adelie_core: unknown state vector " + nm;
+    return AB_ERR_ARG;
+}
+template <class T>
+static int cov_state_vec_i64(const CovPathState<T>& s, const std::string& nm, int64_t* out, int64_t cap, int64_t* len) {
+    if (nm == "groups") return copy_ivec(s.groups, out, cap, len);
+    if (nm == "group_sizes") return copy_ivec(s.group_sizes, out, cap, len);
+    if (nm == "screen_set") return copy_ivec(s.screen_set, out, cap, len);
+    if (nm == "screen_begins") return copy_ivec(s.screen_begins, out, cap, len);
+    if (nm == "screen_is_active") return copy_ivec(s.screen_is_active, out, cap, len);
+    if (nm == "active_set") return copy_ivec(s.active_set, out, cap, len);
+    if (nm == "screen_subset_order") return copy_ivec(s.screen_subset_order, out, cap, len);
+    if (nm == "screen_subset_ordered") return copy_ivec(s.screen_subset_ordered, out, cap, len);
+    if (nm == "n_valid_solutions") return copy_ivec(s.n_valid_solutions, out, cap, len);
+    if (nm == "active_sizes") return copy_ivec(s.active_sizes, out, cap, len);
+    if (nm == "screen_sizes") return copy_ivec(s.screen_sizes, out, cap, len);
+    g_last_error = "adelie_core: unknown state vector " + nm;
+    return AB_ERR_ARG;
+}
+template <class T>
+static int cov_state_scalar(const CovPathState<T>& s, const std::string& nm, double* out) {
+    if (nm == "lmda_max") *out = s.lmda_max; else if (nm == "lmda") *out = s.lmda;
+    else if (nm == "rsq") *out = s.rsq; else if (nm == "active_set_size") *out = (double)s.active_set_size;
+    else if (nm == "alpha") *out = s.alpha; else if (nm == "tol") *out = s.tol; else if (nm == "rdev_tol") *out = s.rdev_tol;
+    else if (nm == "n_sweeps") *out = (double)s.n_sweeps; else if (nm == "n_group_updates") *out = (double)s.n_group_updates;
+    else if (nm == "n_col_updates") *out = (double)s.n_col_updates; else if (nm == "n_pin_solves") *out = (double)s.n_pin_solves;
+    else if (nm == "n_kernel_launches") *out = (double)s.n_kernel_launches; else if (nm == "time_sweep_kernel") *out = s.time_sweep_kernel;
+    else if (nm == "cov_cluster") *out = s.last_cluster; else if (nm == "cov_smem_bytes") *out = s.last_smem;
+    else if (nm == "setup_lmda_max") *out = s.setup_lmda_max; else if (nm == "setup_lmda_path") *out = s.setup_lmda_path;
+    else { g_last_error = "adelie_core: unknown state scalar " + nm; return AB_ERR_ARG; }
+    return AB_OK;
+}
+
+extern "C" {
+
+int ab_matrix_cov_dense_create(int dtype, const void* host, int64_t p, int order, int64_t ldh, int n_threads, ab_cov_matrix** out) {
+    AB_TRY
+    if (p < 1) throw core_error("mat must be (p, p).");
+    auto* m = new ab_cov_matrix{dtype};
+    try {
+        if (dtype == AB_F32) m->f32 = CovMatrix<float>::make_dense((const float*)host, p, order, ldh, n_threads);
+        else m->f64 = CovMatrix<double>::make_dense((const double*)host, p, order, ldh, n_threads);
+    } catch (...) { delete m; throw; }
+    *out = m;
+    AB_CATCH
+}
+int ab_matrix_cov_lazy_create(int dtype, const void* host, int64_t n, int64_t p, int order, int64_t ldh, int n_threads, ab_cov_matrix** out) {
+    AB_TRY
+    if (n < 1 || p < 1) throw core_error("mat must be (n, p).");
+    auto* m = new ab_cov_matrix{dtype};
+    try {
+        if (dtype == AB_F32) m->f32 = CovMatrix<float>::make_lazy((const float*)host, n, p, order, ldh, n_threads);
+        else m->f64 = CovMatrix<double>::make_lazy((const double*)host, n, p, order, ldh, n_threads);
+    } catch (...) { delete m; throw; }
+    *out = m;
+    AB_CATCH
+}
+int ab_matrix_cov_free(ab_cov_matrix* m) { if (m) { delete m->f32; delete m->f64; delete m; } return AB_OK; }
+int ab_matrix_cov_cols(const ab_cov_matrix* m, int64_t* out) { *out = m->dtype == AB_F32 ? m->f32->p : m->f64->p; return AB_OK; }
+int ab_matrix_cov_bmul(ab_cov_matrix* m, const int64_t* subset, int64_t s, const int64_t* indices, const void* values, int64_t k, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) m->f32->bmul(subset, s, indices, (const float*)values, k, (float*)out);
+    else m->f64->bmul(subset, s, indices, (const double*)values, k, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_cov_mul(ab_cov_matrix* m, const int64_t* indices, const void* values, int64_t k, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) m->f32->mul(indices, (const float*)values, k, (float*)out);
+    else m->f64->mul(indices, (const double*)values, k, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_cov_to_dense(ab_cov_matrix* m, int64_t i, int64_t q, void* out) {
+    AB_TRY
+    if (m->dtype == AB_F32) m->f32->to_dense(i, q, (float*)out); else m->f64->to_dense(i, q, (double*)out);
+    AB_CATCH
+}
+int ab_matrix_cov_cache_info(const ab_cov_matrix* m, int64_t* cached_rows) {
+    *cached_rows = m->dtype == AB_F32 ? m->f32->cached_rows : m->f64->cached_rows;
+    return AB_OK;
+}
+
+int ab_cov_state_create(const ab_cov_state_args* args, ab_cov_matrix* A, ab_cov_state** out) {
+    AB_TRY
+    if (A->dtype != args->dtype) throw core_error("dtype mismatch between state and matrix.");
+    auto* s = new ab_cov_state{args->dtype};
+    try {
+        if (args->dtype == AB_F32) s->f32 = make_cov_state<float>(args, A->f32);
+        else s->f64 = make_cov_state<double>(args, A->f64);
+    } catch (...) { delete s; throw; }
+    *out = s;
+    AB_CATCH
+}
+int ab_cov_state_free(ab_cov_state* s) { if (s) { delete s->f32; delete s->f64; delete s; } return AB_OK; }
+
+static int cov_run(ab_cov_state* s, bool pin, int (*exit_cond)(void*), void* ctx, int (*check_signals)(void), char* err, size_t errlen, double* total_time) {
+    g_last_error.clear();
+    s->error.clear();
+    const double t0 = now_s();
+    auto run = [&](auto* ps) {
+        if (exit_cond) ps->exit_cond = [=]() { return exit_cond(ctx) != 0; };
+        if (check_signals) ps->check_interrupt = [=]() { if (check_signals() != 0) throw solver_error("interrupted."); };
+        try { if (pin) ps->solve_pin(); else ps->solve(); }
+        catch (const std::exception& e) { s->error = e.what(); }       // py_state.cpp:83-90: message returned, state stays valid
+        ps->exit_cond = nullptr; ps->check_interrupt = nullptr;
+    };
+    if (s->dtype == AB_F32) run(s->f32); else run(s->f64);
+    s->total_time = now_s() - t0;
+    if (total_time) *total_time = s->total_time;
+    if (err && errlen) { std::strncpy(err, s->error.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return AB_OK;
+}
+int ab_cov_state_solve(ab_cov_state* s, int display_progress_bar, int (*exit_cond)(void*), void* ctx, int (*check_signals)(void),
+                       char* err, size_t errlen, double* total_time) {
+    (void)display_progress_bar;
+    return cov_run(s, false, exit_cond, ctx, check_signals, err, errlen, total_time);
+}
+int ab_cov_pin_solve(ab_cov_state* s, int (*check_signals)(void), char* err, size_t errlen, double* total_time) {
+    return cov_run(s, true, nullptr, nullptr, check_signals, err, errlen, total_time);
+}
+int ab_cov_state_get_scalar(const ab_cov_state* s, const char* name, double* out) {
+    AB_TRY
+    if (std::string(name) == "total_time") { *out = s->total_time; return AB_OK; }
+    return s->dtype == AB_F32 ? cov_state_scalar(*s->f32, name, out) : cov_state_scalar(*s->f64, name, out);
+    AB_CATCH
+}
+int ab_cov_state_get_vec_f64(const ab_cov_state* s, const char* name, double* out, int64_t cap, int64_t* len) {
+    AB_TRY
+    return s->dtype == AB_F32 ? cov_state_vec_f64(*s->f32, name, out, cap, len) : cov_state_vec_f64(*s->f64, name, out, cap, len);
+    AB_CATCH
+}
+int ab_cov_state_get_vec_i64(const ab_cov_state* s, const char* name, int64_t* out, int64_t cap, int64_t* len) {
+    AB_TRY
+    return s->dtype == AB_F32 ? cov_state_vec_i64(*s->f32, name, out, cap, len) : cov_state_vec_i64(*s->f64, name, out, cap, len);
+    AB_CATCH
+}
+int ab_cov_state_get_betas(const ab_cov_state* s, int64_t* indptr, int64_t* indices, double* values, int64_t* nnz, int64_t* L) {
+    AB_TRY
+    auto get = [&](const auto& st) {
+        int64_t tot = 0;
+        if (indptr) indptr[0] = 0;
+        for (size_t l = 0; l < st.betas.size(); ++l) {
+            const auto& b = st.betas[l];
+            for (size_t k = 0; k < b.idx.size(); ++k) { if (indices) indices[tot + k] = b.idx[k]; if (values) values[tot + k] = b.val[k]; }
+            tot += (int64_t)b.idx.size();
+            if (indptr) indptr[l + 1] = tot;
+        }
+        *nnz = tot; *L = (int64_t)st.betas.size();
+    };
+    if (s->dtype == AB_F32) get(*s->f32); else get(*s->f64);
+    AB_CATCH
+}
+int ab_cov_state_get_screen_transform(const ab_cov_state* s, int64_t i, double* out, int64_t cap, int64_t* len) {
+    AB_TRY
+    auto get = [&](auto& st) {
+        if (i < 0 || i >= (int64_t)st.screen_transforms.size()) throw core_error("screen_transforms index out of range.");
+        const auto& v = st.screen_transforms[i];
+        *len = (int64_t)v.size();
+        if (out) for (int64_t k = 0; k < std::min<int64_t>(cap, *len); ++k) out[k] = (double)v[k];
+    };
+    if (s->dtype == AB_F32) get(*s->f32); else get(*s->f64);
+    AB_CATCH
 }
 
 } // extern "C"

@@ -478,6 +478,166 @@ def subset(mat, indices: np.ndarray, *, axis: int = 0, n_threads: int = 1):
     return out
 
 
+
+class MatrixCovBase:
+    """Covariance-method matrix (reference: adelie/matrix.py MatrixCovBase{32,64}; CORE/matrix/matrix_cov_base.hpp:20-63): a (p, p) positive
+    semi-definite matrix behind ``bmul`` / ``mul`` / ``to_dense`` / ``cols``.  Resident in HBM; the device copy is made on first use."""
+    def __init__(self, dtype, p, n_threads):
+        if n_threads < 1:
+            raise RuntimeError("adelie_core: n_threads must be >= 1.")
+        self.dtype = np.dtype(dtype).type
+        self._p = int(p)
+        self._n_threads = n_threads
+        self._handle = None
+
+    def cols(self):
+        return self._p
+
+    def rows(self):
+        return self._p
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def shape(self):
+        return (self._p, self._p)
+
+    def _make_handle(self):
+        raise NotImplementedError
+
+    def _core(self):
+        if self._handle is None:
+            self._handle = self._make_handle()
+        return self._handle
+
+    def close(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None:
+            try:
+                _lib.load().ab_matrix_cov_free(h)
+            except Exception:
+                pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        self.close()
+
+    def _idx(self, a):
+        return np.ascontiguousarray(a, dtype=np.int64)
+
+    def _vec(self, a, name, fn):
+        if not isinstance(a, np.ndarray) or a.dtype != self.dtype or a.ndim != 1 or not a.flags.c_contiguous:
+            raise TypeError(f"{fn}(): {name} must be a 1-D contiguous array of dtype {np.dtype(self.dtype).name}")
+        return a
+
+    def bmul(self, subset, indices, values, out):
+        """out[k] = sum_i values[i] * A[indices[i], subset[k]] (matrix_cov_base.hpp:33-47)."""
+        subset = self._idx(subset); indices = self._idx(indices)
+        values = self._vec(values, "values", "bmul"); out = self._vec(out, "out", "bmul")
+        p = self._p
+        s, i, v, o = subset.size, indices.size, values.size, out.size
+        if (s > p) or (i > p) or (i != v) or (o != s):
+            raise RuntimeError(f"adelie_core: bmul() is given inconsistent inputs! Invoked check_bmul(s={s}, i={i}, v={v}, o={o}, r={p}, c={p})")
+        _lib.check(_lib.load().ab_matrix_cov_bmul(self._core(), _lib.ptr(subset), s, _lib.ptr(indices), _lib.ptr(values), i, _lib.ptr(out)))
+
+    def mul(self, indices, values, out):
+        """out = A[indices].T @ values (matrix_cov_base.hpp:49-57)."""
+        indices = self._idx(indices)
+        values = self._vec(values, "values", "mul"); out = self._vec(out, "out", "mul")
+        p = self._p
+        i, v, o = indices.size, values.size, out.size
+        if (i > p) or (i != v) or (o != p):
+            raise RuntimeError(f"adelie_core: mul() is given inconsistent inputs! Invoked check_mul(i={i}, v={v}, o={o}, r={p}, c={p})")
+        _lib.check(_lib.load().ab_matrix_cov_mul(self._core(), _lib.ptr(indices), _lib.ptr(values), i, _lib.ptr(out)))
+
+    def to_dense(self, i, p, out):
+        """out = A[i:i+p, i:i+p] (matrix_cov_base.hpp:59-62); out is an F-contiguous (p, p) array."""
+        r = self._p
+        if (i < 0 or i > r - p) or out.shape != (p, p):
+            raise RuntimeError(f"adelie_core: to_dense() is given inconsistent inputs! Invoked check_to_dense(i={i}, p={p}, o_r={out.shape[0]}, o_c={out.shape[-1]}, r={r}, c={r})")
+        if out.dtype != self.dtype or not out.flags.f_contiguous:
+            raise TypeError("to_dense(): out must be an F-contiguous (p, p) array of the matrix dtype")
+        _lib.check(_lib.load().ab_matrix_cov_to_dense(self._core(), i, p, _lib.ptr(out)))
+
+
+class MatrixCovBase32(MatrixCovBase):
+    pass
+
+
+class MatrixCovBase64(MatrixCovBase):
+    pass
+
+
+def _cov_class(base, dtype):
+    mark = MatrixCovBase64 if np.dtype(dtype) == np.float64 else MatrixCovBase32
+    return type(base.__name__, (base, mark), {})
+
+
+class _CovDense(MatrixCovBase):
+    """adelie.matrix.dense(method="cov") -> MatrixCovDense{32,64}{C,F} (CORE/matrix/matrix_cov_dense.ipp:8-84)."""
+    def __init__(self, mat, n_threads):
+        if mat.shape[0] != mat.shape[1]:
+            raise RuntimeError("adelie_core: mat must be (p, p).")
+        MatrixCovBase.__init__(self, mat.dtype, mat.shape[1], n_threads)
+        self._mat = mat
+
+    def _make_handle(self):
+        m = self._mat
+        h = C.c_void_p()
+        order = 0 if m.flags.f_contiguous else 1
+        _lib.check(_lib.load().ab_matrix_cov_dense_create(_lib.dtype_code(self.dtype), _lib.ptr(m), m.shape[1], order, m.shape[0],
+                                                          self._n_threads, C.byref(h)))
+        return h
+
+
+class _CovLazy(MatrixCovBase):
+    """adelie.matrix.lazy_cov -> MatrixCovLazyCov{32,64}{C,F} (CORE/matrix/matrix_cov_lazy_cov.ipp:8-190): A = X^T X, rows of A are computed
+    on the device the first time they are needed and kept in HBM."""
+    def __init__(self, mat, n_threads):
+        MatrixCovBase.__init__(self, mat.dtype, mat.shape[1], n_threads)
+        self._mat = mat
+
+    def _make_handle(self):
+        m = self._mat
+        h = C.c_void_p()
+        order = 0 if m.flags.f_contiguous else 1
+        ldh = m.shape[0] if order == 0 else m.shape[1]
+        _lib.check(_lib.load().ab_matrix_cov_lazy_create(_lib.dtype_code(self.dtype), _lib.ptr(m), m.shape[0], m.shape[1], order, ldh,
+                                                         self._n_threads, C.byref(h)))
+        return h
+
+    def cached_rows(self):
+        out = C.c_int64()
+        _lib.check(_lib.load().ab_matrix_cov_cache_info(self._core(), C.byref(out)))
+        return out.value
+
+
+def _check_dense_input(mat):
+    if not isinstance(mat, np.ndarray) or mat.ndim != 2:
+        raise RuntimeError("mat must be a 2-dimensional numpy array.")
+    if mat.dtype not in (np.float32, np.float64):
+        raise RuntimeError("mat must be of type numpy.float32 or numpy.float64.")
+    if not (mat.flags.f_contiguous or mat.flags.c_contiguous):
+        mat = np.asfortranarray(mat)
+    return mat
+
+
+def lazy_cov(mat: np.ndarray, *, copy: bool = False, n_threads: int = 1):
+    """Lazy covariance matrix ``mat.T @ mat`` (adelie/matrix.py:1003-1080).  Only works with the covariance method."""
+    mat = _check_dense_input(mat)
+    if copy:
+        mat = mat.copy(order="K")
+    return _cov_class(_CovLazy, mat.dtype)(mat, n_threads)
+
+
 def sparse(mat, *, method: str = "naive", copy: bool = False, n_threads: int = 1):
     """Sparse matrix (adelie/matrix.py ``sparse``): a scipy CSC matrix (anything else is converted), float32 / float64."""
     import scipy.sparse as _sp
@@ -503,9 +663,14 @@ def sparse_device_random(n: int, p: int, nnz_per_col: int, *, dtype=np.float32, 
 
 
 def dense(mat: np.ndarray, *, method: str = "naive", copy: bool = False, n_threads: int = 1):
-    """Dense matrix (adelie/matrix.py:549-680).  Only ``method="naive"`` is on the hot path."""
+    """Dense matrix (adelie/matrix.py:549-680): ``method="naive"`` -> MatrixNaiveDense, ``method="cov"`` -> MatrixCovDense."""
+    if method == "cov":
+        mat = _check_dense_input(mat)
+        if copy:
+            mat = mat.copy(order="K")
+        return _cov_class(_CovDense, mat.dtype)(mat, n_threads)
     if method != "naive":
-        raise RuntimeError("adelie_b200: only method='naive' is in scope (covariance matrices are not on the hot path).")
+        raise RuntimeError("method must be one of 'naive', 'cov'.")
     if not isinstance(mat, np.ndarray) or mat.ndim != 2:
         raise RuntimeError("mat must be a 2-dimensional numpy array.")
     if mat.dtype not in (np.float32, np.float64):

@@ -52,6 +52,10 @@ def _render_inputs(*, groups, lmda_max, lmda_path, lmda_path_size, max_screen_si
 class base:
     """Common wrapper (adelie/state.py:79-176)."""
     _is_multi = False
+    _api = "ab_state"        # prefix of the C-ABI entry points behind this state ("ab_cov_state" for the covariance-method states)
+
+    def _fn(self, suffix):
+        return getattr(_lib.load(), self._api + suffix)
 
     def _build_core(self):
         a = _lib.StateArgs()
@@ -76,7 +80,7 @@ class base:
         h, self._handle = self.__dict__.get("_handle"), None
         if h is not None:
             try:
-                _lib.load().ab_state_free(h)
+                self._fn("_free")(h)
             except Exception:
                 pass
 
@@ -86,15 +90,15 @@ class base:
     # ---- output accessors ------------------------------------------------------------------
     def _scalar(self, name):
         out = C.c_double()
-        _lib.check(_lib.load().ab_state_get_scalar(self._core(), name.encode(), C.byref(out)))
+        _lib.check(self._fn("_get_scalar")(self._core(), name.encode(), C.byref(out)))
         return out.value
 
     def _vec_f(self, name, dtype=None):
         L = _lib.load()
         n = C.c_int64()
-        _lib.check(L.ab_state_get_vec_f64(self._core(), name.encode(), None, 0, C.byref(n)))
+        _lib.check(self._fn("_get_vec_f64")(self._core(), name.encode(), None, 0, C.byref(n)))
         buf = np.empty(n.value, dtype=np.float64)
-        _lib.check(L.ab_state_get_vec_f64(self._core(), name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
+        _lib.check(self._fn("_get_vec_f64")(self._core(), name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
         if name.startswith("benchmark") or name == "sweep_stats":
             return buf
         return buf.astype(self._dtype if dtype is None else dtype)
@@ -102,9 +106,9 @@ class base:
     def _vec_i(self, name):
         L = _lib.load()
         n = C.c_int64()
-        _lib.check(L.ab_state_get_vec_i64(self._core(), name.encode(), None, 0, C.byref(n)))
+        _lib.check(self._fn("_get_vec_i64")(self._core(), name.encode(), None, 0, C.byref(n)))
         buf = np.empty(n.value, dtype=np.int64)
-        _lib.check(L.ab_state_get_vec_i64(self._core(), name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
+        _lib.check(self._fn("_get_vec_i64")(self._core(), name.encode(), _lib.ptr(buf), n.value, C.byref(n)))
         return buf
 
     def __getattr__(self, name):
@@ -159,9 +163,9 @@ class base:
         out = []
         for i in range(self.screen_set.shape[0]):
             n = C.c_int64()
-            _lib.check(L.ab_state_get_screen_transform(self._core(), i, None, 0, C.byref(n)))
+            _lib.check(self._fn("_get_screen_transform")(self._core(), i, None, 0, C.byref(n)))
             buf = np.empty(n.value, dtype=np.float64)
-            _lib.check(L.ab_state_get_screen_transform(self._core(), i, _lib.ptr(buf), n.value, C.byref(n)))
+            _lib.check(self._fn("_get_screen_transform")(self._core(), i, _lib.ptr(buf), n.value, C.byref(n)))
             gs = int(round(np.sqrt(n.value)))
             out.append(buf.astype(self._dtype).reshape(gs, gs))
         return out
@@ -171,11 +175,11 @@ class base:
         """(L, p) scipy CSR with int64 indices (py_state.cpp:9-60)."""
         L = _lib.load()
         nnz, nl = C.c_int64(), C.c_int64()
-        _lib.check(L.ab_state_get_betas(self._core(), None, None, None, C.byref(nnz), C.byref(nl)))
+        _lib.check(self._fn("_get_betas")(self._core(), None, None, None, C.byref(nnz), C.byref(nl)))
         indptr = np.empty(nl.value + 1, dtype=np.int64)
         indices = np.empty(nnz.value, dtype=np.int64)
         values = np.empty(nnz.value, dtype=np.float64)
-        _lib.check(L.ab_state_get_betas(self._core(), _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values), C.byref(nnz), C.byref(nl)))
+        _lib.check(self._fn("_get_betas")(self._core(), _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values), C.byref(nnz), C.byref(nl)))
         p = self._p_cols
         B = scipy.sparse.csr_matrix((values.astype(self._dtype), indices, indptr), shape=(nl.value, p))
         B.indices = B.indices.astype(np.int64); B.indptr = B.indptr.astype(np.int64)     # int64 like the reference (py_state.cpp:9-60)
@@ -208,7 +212,7 @@ class base:
                 return 1
             return 0
         cb_sig = _lib.CHECK_SIGNALS_T(_poll)
-        rc = L.ab_state_solve(new._handle, int(progress_bar), C.cast(cb_exit, C.c_void_p) if cb_exit else None, None,
+        rc = self._fn("_solve")(new._handle, int(progress_bar), C.cast(cb_exit, C.c_void_p) if cb_exit else None, None,
                               C.cast(cb_sig, C.c_void_p), err, len(err), C.byref(total))
         if pending:
             raise pending[0]
@@ -761,3 +765,244 @@ def gaussian_pin_naive(*, X, y_mean, y_var, constraints, groups, alpha, penalty,
                newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=False, intercept=intercept,
                n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float("inf"))
     return _Pin(X=X, glm_obj=glm_obj, use_glm=False, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=p)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# covariance method: StateGaussianCov / StateGaussianPinCov
+# ------------------------------------------------------------------------------------------------------------------
+_COV_VEC_F = ["rsqs", "lmda_path", "screen_beta", "screen_grad", "screen_vars", "grad", "abs_grad", "v", "devs", "lmdas",
+              "benchmark_screen", "benchmark_fit_screen", "benchmark_fit_active", "benchmark_kkt", "benchmark_invariance"]
+_COV_VEC_I = ["screen_set", "screen_begins", "screen_is_active", "active_set", "screen_subset_order", "screen_subset_ordered",
+              "n_valid_solutions", "active_sizes", "screen_sizes"]
+_COV_INT = ("active_set_size", "n_sweeps", "n_group_updates", "n_col_updates", "n_pin_solves", "n_kernel_launches", "cov_cluster",
+            "cov_smem_bytes")
+_COV_SCALARS = ["lmda_max", "lmda", "rsq", "time_sweep_kernel"] + list(_COV_INT)
+
+
+class _Cov(base):
+    """Gaussian covariance-method state (adelie/state.py:1128-1420 gaussian_cov; core StateGaussianCov{32,64}, solve =
+    gaussian::cov::solve, CORE/solver/solver_gaussian_cov.hpp:359-457)."""
+    _api = "ab_cov_state"
+
+    def __init__(self, *, A, dtype, cfg, arrays):
+        self._A = A
+        self._dtype = np.dtype(dtype).type
+        self._cfg = cfg
+        self._p_cols = A.cols()
+        for k, v in arrays.items():
+            setattr(self, "_" + k, v)
+        self._handle = None
+        self._handle = self._build_core()
+
+    def _build_core(self):
+        c = self._cfg
+        a = _lib.CovStateArgs()
+        a.dtype = _lib.dtype_code(self._dtype)
+        a.v = _lib.ptr(self._v)
+        a.groups = _lib.ptr(self._groups); a.group_sizes = _lib.ptr(self._group_sizes); a.G = self._groups.shape[0]
+        a.alpha = c["alpha"]; a.penalty = _lib.ptr(self._penalty)
+        a.lmda_path = _lib.ptr(self._lmda_path); a.lmda_path_len = self._lmda_path.shape[0]
+        a.lmda_max = c["lmda_max"]; a.min_ratio = c["min_ratio"]; a.lmda_path_size = c["lmda_path_size"]
+        a.setup_lmda_max = int(c["setup_lmda_max"]); a.setup_lmda_path = int(c["setup_lmda_path"])
+        a.max_screen_size = c["max_screen_size"]; a.max_active_size = c["max_active_size"]
+        a.pivot_subset_ratio = c["pivot_subset_ratio"]; a.pivot_subset_min = c["pivot_subset_min"]
+        a.pivot_slack_ratio = c["pivot_slack_ratio"]
+        rules = {"strong": 0, "pivot": 1}
+        if c["screen_rule"] not in rules:
+            raise RuntimeError("adelie_core: Invalid screen rule type: " + str(c["screen_rule"]))
+        a.screen_rule = rules[c["screen_rule"]]
+        a.max_iters = c["max_iters"]; a.tol = c["tol"]; a.rdev_tol = c["rdev_tol"]
+        a.newton_tol = c["newton_tol"]; a.newton_max_iters = c["newton_max_iters"]
+        a.early_exit = int(c["early_exit"]); a.n_threads = c["n_threads"]
+        a.screen_set = _lib.ptr(self._screen_set); a.screen_set_size = self._screen_set.shape[0]
+        a.screen_beta = _lib.ptr(self._screen_beta); a.screen_beta_size = self._screen_beta.shape[0]
+        a.screen_is_active = _lib.ptr(self._screen_is_active_i8); a.active_set_size = c["active_set_size"]
+        a.active_set = _lib.ptr(self._active_set)
+        a.rsq = c["rsq"]; a.lmda = c["lmda"]; a.grad = _lib.ptr(self._grad)
+        a.screen_grad = _lib.ptr(self.__dict__.get("_screen_grad_in"))
+        h = C.c_void_p()
+        _lib.check(_lib.load().ab_cov_state_create(C.byref(a), self._A._core(), C.byref(h)))
+        return h
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        cfg = self.__dict__.get("_cfg", {})
+        if name in ("min_ratio", "lmda_path_size", "max_screen_size", "max_active_size", "pivot_subset_ratio", "pivot_subset_min",
+                    "pivot_slack_ratio", "screen_rule", "max_iters", "tol", "rdev_tol", "newton_tol", "newton_max_iters", "early_exit",
+                    "setup_lmda_max", "setup_lmda_path", "n_threads") and name in cfg:
+            return cfg[name]
+        if name in _COV_SCALARS:
+            v = self._scalar(name)
+            return int(v) if name in _COV_INT else (v if name == "time_sweep_kernel" else self._dtype(v))
+        if name in _COV_VEC_F:
+            return self._vec_f(name)
+        if name in _COV_VEC_I:
+            v = self._vec_i(name)
+            if name == "screen_is_active":
+                return v.astype(bool)
+            if name in ("n_valid_solutions", "active_sizes", "screen_sizes"):
+                return v.astype(np.int32)
+            return v
+        raise AttributeError(name)
+
+    @property
+    def A(self):
+        return self._A
+
+    @property
+    def X(self):
+        raise AttributeError("covariance-method states have no X")
+
+    @property
+    def v(self):
+        return self._v
+
+    @property
+    def constraints(self):
+        return None
+
+    @property
+    def dual_groups(self):
+        return np.zeros(len(self._groups), dtype=int)
+
+    def check(self, method=None, logger=logger):
+        """The reference's gaussian_cov state inherits the no-op base check (adelie/state.py:92-116); here the index layout plus the
+        covariance-method invariants grad = v - A beta and screen_grad = grad on the screen values are re-derived."""
+        p = self._p_cols
+        vs = self._check_layout(method, logger, p)
+        c = lambda ok, msg: self._check(bool(ok), msg, method, logger)
+        c(isinstance(self._A, (_matrix.MatrixCovBase32, _matrix.MatrixCovBase64)), "check A type")
+        sb = self.screen_beta
+        c(len(sb) == vs, "check screen_beta size")
+        S, gsz, groups = self.screen_set, self.group_sizes, self.groups
+        subset = np.concatenate([np.arange(groups[i], groups[i] + gsz[i]) for i in S]) if len(S) else np.zeros(0, dtype=int)
+        order = np.argsort(subset)
+        out = np.empty(p, dtype=self._dtype)
+        self._A.mul(subset[order], np.ascontiguousarray(sb[order], dtype=self._dtype), out)
+        grad = self._v - out
+        tol = 1e-10 if self._dtype == np.float64 else 1e-3
+        c(np.allclose(self.grad, grad, rtol=tol, atol=tol * max(1.0, float(np.max(np.abs(self._v), initial=0)))), "check grad = v - A beta")
+
+
+class _PinCov(_Cov):
+    """Gaussian pin covariance-method state (adelie/state.py:723-1000; core StateGaussianPinCov{32,64}, solve = gaussian::pin::cov::solve,
+    CORE/solver/solver_gaussian_pin_cov.hpp:529-725): solves its own ``lmda_path`` on a FIXED screen set."""
+
+    def solve(self, progress_bar: bool = False, exit_cond=None):
+        new = self._clone()
+        err = C.create_string_buffer(4096)
+        total = C.c_double()
+        pending = []
+        def _poll():
+            try:
+                C.pythonapi.PyErr_CheckSignals()
+            except BaseException as e:          # noqa: BLE001
+                pending.append(e)
+                return 1
+            return 0
+        cb_sig = _lib.CHECK_SIGNALS_T(_poll)
+        rc = _lib.load().ab_cov_pin_solve(new._handle, C.cast(cb_sig, C.c_void_p), err, len(err), C.byref(total))
+        if pending:
+            raise pending[0]
+        _lib.check(rc)
+        new.error = err.value.decode()
+        new.total_time = total.value
+        if new.error != "":
+            (logger.error if new.error.startswith("adelie_core solver: ") else logger.warning)(RuntimeError(new.error))
+        return new
+
+    @property
+    def iters(self):
+        return self.n_sweeps
+
+    @property
+    def benchmark_screen(self):
+        return self._vec_f("benchmark_fit_screen")
+
+    @property
+    def benchmark_active(self):
+        return self._vec_f("benchmark_fit_active")
+
+    def check(self, method=None, logger=logger):
+        vs = self._check_layout(method, logger, self._p_cols)
+        c = lambda ok, msg: self._check(bool(ok), msg, method, logger)
+        c(isinstance(self._A, (_matrix.MatrixCovBase32, _matrix.MatrixCovBase64)), "check A type")
+        c(len(self.screen_beta) == vs and len(self.screen_grad) == vs, "check screen_beta / screen_grad size")
+
+
+def _cov_arrays(*, groups, group_sizes, penalty, lmda_path, screen_set, screen_beta, screen_is_active, active_set, grad, v, dtype):
+    G = groups.shape[0]
+    act = np.zeros(G, dtype=np.int64)
+    active_set = np.asarray(active_set)
+    act[: min(G, active_set.shape[0])] = active_set[:G]
+    return dict(
+        groups=np.array(groups, copy=True, dtype=np.int64),
+        group_sizes=np.array(group_sizes, copy=True, dtype=np.int64),
+        penalty=np.array(penalty, copy=True, dtype=dtype),
+        lmda_path=np.ascontiguousarray(lmda_path, dtype=dtype),
+        screen_set=np.ascontiguousarray(screen_set, dtype=np.int64),
+        screen_beta=np.ascontiguousarray(screen_beta, dtype=dtype),
+        screen_is_active_i8=np.ascontiguousarray(screen_is_active, dtype=np.int8),
+        active_set=act,
+        grad=np.ascontiguousarray(grad, dtype=dtype),
+        v=np.array(v, copy=True, dtype=dtype),
+    )
+
+
+def gaussian_cov(*, A, v, constraints, groups, group_sizes, alpha, penalty, screen_set, screen_beta, screen_is_active, active_set_size,
+                 active_set, rsq, lmda, grad, lmda_path=None, lmda_max=None, max_iters=int(1e5), tol=1e-7, rdev_tol=1e-4, newton_tol=1e-12,
+                 newton_max_iters=1000, n_threads=1, early_exit=True, screen_rule="pivot", min_ratio=1e-2, lmda_path_size=100,
+                 max_screen_size=None, max_active_size=None, pivot_subset_ratio=0.1, pivot_subset_min=1, pivot_slack_ratio=1.25):
+    """Gaussian covariance-method state (adelie/state.py:1128-1420; core StateGaussianCov{32,64})."""
+    _check_constraints(constraints)
+    if isinstance(A, np.ndarray):
+        A = _matrix.dense(A, method="cov", n_threads=n_threads)
+    if not isinstance(A, (_matrix.MatrixCovBase32, _matrix.MatrixCovBase64)):
+        raise ValueError("A must be an instance of MatrixCovBase32, MatrixCovBase64, or np.ndarray.")
+    dtype = A.dtype
+    groups = np.asarray(groups)
+    if np.asarray(v).shape != (A.cols(),):
+        raise RuntimeError("adelie_core: v must be (p,) where A is (p, p).")          # state_gaussian_cov.ipp:11-13
+    if np.asarray(grad).shape != (A.cols(),):
+        raise RuntimeError("adelie_core: grad must be (p,) where A is (p, p).")
+    (max_screen_size, max_active_size, lmda_path_size, setup_lmda_max, setup_lmda_path, lmda_max, lmda_path) = _render_inputs(
+        groups=groups, lmda_max=lmda_max, lmda_path=lmda_path, lmda_path_size=lmda_path_size,
+        max_screen_size=max_screen_size, max_active_size=max_active_size, dtype=dtype)
+    arrays = _cov_arrays(groups=groups, group_sizes=group_sizes, penalty=penalty, lmda_path=lmda_path, screen_set=screen_set,
+                         screen_beta=screen_beta, screen_is_active=screen_is_active, active_set=active_set, grad=grad, v=v, dtype=dtype)
+    cfg = dict(alpha=float(alpha), rsq=float(rsq), lmda_max=float(lmda_max), min_ratio=min_ratio, lmda_path_size=int(lmda_path_size),
+               setup_lmda_max=setup_lmda_max, setup_lmda_path=setup_lmda_path, max_screen_size=max_screen_size,
+               max_active_size=max_active_size, pivot_subset_ratio=pivot_subset_ratio, pivot_subset_min=pivot_subset_min,
+               pivot_slack_ratio=pivot_slack_ratio, screen_rule=screen_rule, max_iters=int(max_iters), tol=tol, rdev_tol=rdev_tol,
+               newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=early_exit, n_threads=int(n_threads),
+               active_set_size=int(active_set_size), lmda=float(lmda))
+    return _Cov(A=A, dtype=dtype, cfg=cfg, arrays=arrays)
+
+
+def gaussian_pin_cov(*, A, constraints, groups, alpha, penalty, screen_set, lmda_path, rsq, screen_beta, screen_grad, screen_is_active,
+                     active_set_size, active_set, max_active_size=None, max_iters=int(1e5), tol=1e-7, rdev_tol=1e-4, newton_tol=1e-12,
+                     newton_max_iters=1000, n_threads=1):
+    """Gaussian pin covariance-method state (adelie/state.py:739-1000; core StateGaussianPinCov{32,64}).  ``screen_vars``,
+    ``screen_transforms`` and ``screen_subset_order`` are derived from the diagonal blocks of ``A`` when the core state is built
+    (the reference wrapper does the same with ``A.to_dense`` + ``numpy.linalg.eigh``, :912-936)."""
+    _check_constraints(constraints)
+    if not isinstance(A, (_matrix.MatrixCovBase32, _matrix.MatrixCovBase64)):
+        raise ValueError("A must be an instance of MatrixCovBase32 or MatrixCovBase64.")
+    dtype = A.dtype
+    p = A.cols()
+    groups = np.asarray(groups)
+    G = groups.shape[0]
+    group_sizes = np.concatenate([groups, [p]], dtype=int)
+    group_sizes = group_sizes[1:] - group_sizes[:-1]
+    arrays = _cov_arrays(groups=groups, group_sizes=group_sizes, penalty=penalty, lmda_path=np.array(lmda_path, copy=True, dtype=dtype),
+                         screen_set=screen_set, screen_beta=screen_beta, screen_is_active=screen_is_active, active_set=active_set,
+                         grad=np.zeros(p, dtype=dtype), v=np.zeros(p, dtype=dtype), dtype=dtype)
+    arrays["screen_grad_in"] = np.array(screen_grad, copy=True, dtype=dtype)
+    max_active_size = G if max_active_size is None else int(np.minimum(max_active_size, G))
+    cfg = dict(alpha=float(alpha), rsq=float(rsq), lmda_max=-1.0, min_ratio=1e-2, lmda_path_size=len(arrays["lmda_path"]),
+               setup_lmda_max=False, setup_lmda_path=False, max_screen_size=G, max_active_size=max_active_size, pivot_subset_ratio=0.1,
+               pivot_subset_min=1, pivot_slack_ratio=1.25, screen_rule="pivot", max_iters=int(max_iters), tol=tol, rdev_tol=rdev_tol,
+               newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=False, n_threads=int(n_threads),
+               active_set_size=int(active_set_size), lmda=float("inf"))
+    return _PinCov(A=A, dtype=dtype, cfg=cfg, arrays=arrays)

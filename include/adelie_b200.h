@@ -21,6 +21,8 @@ extern "C" {
 typedef struct ab_matrix ab_matrix;   /* adelie_core.matrix.MatrixNaive* handle */
 typedef struct ab_glm ab_glm;         /* adelie_core.glm.Glm* handle */
 typedef struct ab_state ab_state;     /* adelie_core.state.State*Naive handle */
+typedef struct ab_cov_matrix ab_cov_matrix; /* adelie_core.matrix.MatrixCov* handle */
+typedef struct ab_cov_state ab_cov_state;   /* adelie_core.state.StateGaussianCov / StateGaussianPinCov handle */
 typedef struct ab_io_snp ab_io_snp;   /* adelie_core.io.IOSNPUnphased handle */
 typedef struct ab_io_snp_pa ab_io_snp_pa; /* adelie_core.io.IOSNPPhasedAncestry handle */
 
@@ -206,6 +208,50 @@ int ab_state_get_screen_transform(const ab_state* s, int64_t i, double* out, int
  *      "n_sweeps" = iters, "benchmark_fit_screen" / "benchmark_fit_active" = benchmark_screen / benchmark_active). */
 int ab_pin_naive_solve(ab_state* s, int (*check_signals)(void), char* err, size_t errlen, double* total_time);
 
+/* ---- covariance method ----------------------------------------------------------------------------------
+ * MatrixCov: adelie/src/py_matrix.cpp MatrixCovBase{32,64} (bmul / mul / to_dense / cols, adelie_core/matrix/matrix_cov_base.hpp:20-63),
+ * MatrixCovDense{32,64}{C,F} (adelie.matrix.dense(method="cov"), matrix_cov_dense.ipp:8-84) and MatrixCovLazyCov{32,64}{C,F}
+ * (adelie.matrix.lazy_cov, matrix_cov_lazy_cov.ipp:8-190: A = X^T X, rows computed on first use and kept in HBM).
+ * order: 0 = column-major, 1 = row-major; host arrays of the matrix dtype; indices / subset are int64. */
+int ab_matrix_cov_dense_create(int dtype, const void* host, int64_t p, int order, int64_t ldh, int n_threads, ab_cov_matrix** out);
+int ab_matrix_cov_lazy_create(int dtype, const void* host, int64_t n, int64_t p, int order, int64_t ldh, int n_threads, ab_cov_matrix** out);
+int ab_matrix_cov_free(ab_cov_matrix* m);
+int ab_matrix_cov_cols(const ab_cov_matrix* m, int64_t* out);
+int ab_matrix_cov_bmul(ab_cov_matrix* m, const int64_t* subset, int64_t s, const int64_t* indices, const void* values, int64_t k, void* out /* (s,) */);
+int ab_matrix_cov_mul(ab_cov_matrix* m, const int64_t* indices, const void* values, int64_t k, void* out /* (p,) */);
+int ab_matrix_cov_to_dense(ab_cov_matrix* m, int64_t i, int64_t q, void* out /* q*q column-major */);
+int ab_matrix_cov_cache_info(const ab_cov_matrix* m, int64_t* cached_rows);     /* lazy_cov: rows of A held in HBM */
+/* States: StateGaussianCov{32,64} (adelie/src/py_state.cpp, adelie/state.py:1128-1420; solve = gaussian::cov::solve,
+ * adelie_core/solver/solver_gaussian_cov.hpp:359-457) and StateGaussianPinCov{32,64} (adelie/state.py:739-1000; solve =
+ * gaussian::pin::cov::solve, solver_gaussian_pin_cov.hpp:529-725).  One argument block for both: the path state reads v / grad /
+ * lmda / lmda_max / the screening configuration, the pin state reads screen_grad and solves lmda_path on the FIXED screen_set
+ * (screen_vars / screen_transforms / screen_subset_order are derived from A like the Python wrapper does, state.py:912-936). */
+typedef struct ab_cov_state_args {
+    int32_t dtype;
+    const void* v;                                   /* (p,) linear term (path state) */
+    const int64_t* groups; const int64_t* group_sizes; int64_t G; double alpha; const void* penalty;
+    const void* lmda_path; int64_t lmda_path_len; double lmda_max, min_ratio; int64_t lmda_path_size;
+    int32_t setup_lmda_max, setup_lmda_path;
+    int64_t max_screen_size, max_active_size; double pivot_subset_ratio; int64_t pivot_subset_min; double pivot_slack_ratio;
+    int32_t screen_rule;                             /* 0 strong, 1 pivot */
+    int64_t max_iters; double tol, rdev_tol, newton_tol; int64_t newton_max_iters;
+    int32_t early_exit; int64_t n_threads;
+    const int64_t* screen_set; int64_t screen_set_size; const void* screen_beta; int64_t screen_beta_size;
+    const int8_t* screen_is_active; int64_t active_set_size; const int64_t* active_set;
+    double rsq, lmda; const void* grad;             /* grad (p,): path state */
+    const void* screen_grad;                         /* (screen_beta_size,): pin state; NULL for the path state */
+} ab_cov_state_args;
+int ab_cov_state_create(const ab_cov_state_args* args, ab_cov_matrix* A, ab_cov_state** out);
+int ab_cov_state_free(ab_cov_state* s);
+/* same contract as ab_state_solve / ab_pin_naive_solve: never throws, the solver error string goes to `err` */
+int ab_cov_state_solve(ab_cov_state* s, int display_progress_bar, int (*exit_cond)(void*), void* ctx, int (*check_signals)(void),
+                       char* err, size_t errlen, double* total_time);
+int ab_cov_pin_solve(ab_cov_state* s, int (*check_signals)(void), char* err, size_t errlen, double* total_time);
+int ab_cov_state_get_scalar(const ab_cov_state* s, const char* name, double* out);
+int ab_cov_state_get_vec_f64(const ab_cov_state* s, const char* name, double* out, int64_t cap, int64_t* len);
+int ab_cov_state_get_vec_i64(const ab_cov_state* s, const char* name, int64_t* out, int64_t cap, int64_t* len);
+int ab_cov_state_get_betas(const ab_cov_state* s, int64_t* indptr, int64_t* indices, double* values, int64_t* nnz, int64_t* L);
+int ab_cov_state_get_screen_transform(const ab_cov_state* s, int64_t i, double* out, int64_t cap, int64_t* len);
 /* ---- bcd prox: adelie/src/py_bcd.cpp:15-243 (double only, like the reference) --------------- */
 /* solver: 0 newton, 1 newton_abs */
 int ab_bcd_solve(int solver, int64_t q, const double* quad, const double* linear, double l1, double l2, double tol, int64_t max_iters,

@@ -72,6 +72,24 @@ class _PinArgs(C.Structure):
     ]
 
 
+class _CovArgs(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int32), ("matrix_kind", C.c_int32),
+        ("M", C.c_void_p), ("n", C.c_int64), ("p", C.c_int64), ("ld", C.c_int64), ("row_major", C.c_int32),
+        ("v", C.c_void_p),
+        ("groups", C.c_void_p), ("group_sizes", C.c_void_p), ("G", C.c_int64), ("penalty", C.c_void_p), ("alpha", C.c_double),
+        ("screen_set", C.c_void_p), ("S", C.c_int64), ("screen_beta", C.c_void_p), ("screen_beta_size", C.c_int64),
+        ("screen_is_active", C.c_void_p), ("active_set_size", C.c_int64), ("active_set", C.c_void_p),
+        ("rsq", C.c_double), ("lmda", C.c_double), ("lmda_max", C.c_double), ("grad", C.c_void_p),
+        ("screen_grad", C.c_void_p),
+        ("lmda_path", C.c_void_p), ("lmda_path_len", C.c_int64), ("setup_lmda_max", C.c_int32), ("setup_lmda_path", C.c_int32),
+        ("min_ratio", C.c_double), ("lmda_path_size", C.c_int64), ("max_screen_size", C.c_int64), ("max_active_size", C.c_int64),
+        ("pivot_subset_ratio", C.c_double), ("pivot_subset_min", C.c_int64), ("pivot_slack_ratio", C.c_double), ("screen_rule", C.c_int32),
+        ("max_iters", C.c_int64), ("tol", C.c_double), ("rdev_tol", C.c_double), ("newton_tol", C.c_double),
+        ("newton_max_iters", C.c_int64), ("early_exit", C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -117,6 +135,12 @@ def lib():
         L.orc_search_pivot.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_jacobi_eigh.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_config.argtypes = [C.c_char_p, C.c_double]
+        L.orc_cov_path_solve.restype = C.c_void_p
+        L.orc_cov_path_solve.argtypes = [C.POINTER(_CovArgs)]
+        L.orc_cov_pin_solve.restype = C.c_void_p
+        L.orc_cov_pin_solve.argtypes = [C.POINTER(_CovArgs)]
+        L.orc_cov_matrix_op.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -518,4 +542,137 @@ def grpnet(X, glm, *, groups=None, alpha=1.0, penalty=None, offsets=None, lmda_p
             out.betas = sp.csr_matrix(B[:, K:])
         else:
             out.intercepts = np.zeros((out.betas.shape[0], K), dtype=dtype)
+    return out
+
+
+# --------------------------------------------------------------------------
+# covariance method (oracle/cov_oracle.hpp): MatrixCov operators, gaussian_pin_cov, gaussian_cov
+# --------------------------------------------------------------------------
+class _cov_matrix:
+    """MatrixCovDense / MatrixCovLazyCov restated (CORE/matrix/matrix_cov_{dense,lazy_cov}.ipp).  The lazy cache lives for one call."""
+
+    def __init__(self, mat, kind):
+        mat = np.asarray(mat)
+        if not (mat.flags.c_contiguous or mat.flags.f_contiguous):
+            mat = np.asfortranarray(mat)
+        self.mat = mat
+        self.kind = kind
+        self.dtype = mat.dtype
+        self.row_major = bool(mat.flags.c_contiguous and not (mat.flags.f_contiguous and mat.shape[0] != 1 and mat.shape[1] != 1))
+        self.n, self.p = (mat.shape if kind == 1 else (0, mat.shape[1]))
+        self.ld = mat.shape[1] if self.row_major else mat.shape[0]
+
+    def cols(self):
+        return self.p
+
+    def _op(self, op, subset, indices, values, i0, q, out):
+        subset = None if subset is None else np.ascontiguousarray(subset, dtype=np.int64)
+        indices = None if indices is None else np.ascontiguousarray(indices, dtype=np.int64)
+        values = None if values is None else np.ascontiguousarray(values, dtype=self.dtype)
+        lib().orc_cov_matrix_op(_dt(self.dtype), self.kind, _p(self.mat), self.n, self.p, self.ld, int(self.row_major), op,
+                                _p(subset), 0 if subset is None else subset.size, _p(indices), _p(values),
+                                0 if indices is None else indices.size, i0, q, _p(out))
+
+    def bmul(self, subset, indices, values, out):
+        self._op(0, subset, indices, values, 0, 0, out)
+
+    def mul(self, indices, values, out):
+        self._op(1, None, indices, values, 0, 0, out)
+
+    def to_dense(self, i, q, out):
+        tmp = np.empty(q * q, dtype=self.dtype)
+        self._op(2, None, None, None, i, q, tmp)
+        out[...] = tmp.reshape(q, q, order="F")
+
+
+def cov_dense(A):
+    return _cov_matrix(A, 0)
+
+
+def cov_lazy(X):
+    return _cov_matrix(X, 1)
+
+
+def _cov_args(A, keep, *, groups, alpha, penalty, max_iters, tol, rdev_tol, newton_tol, newton_max_iters,
+              max_active_size=None, max_screen_size=None):
+    if isinstance(A, np.ndarray):
+        A = cov_dense(A)
+    dtype = A.dtype
+    p = A.cols()
+    def P(arr):
+        keep.append(arr); return _p(arr)
+    groups = np.arange(p, dtype=np.int64) if groups is None else np.ascontiguousarray(groups, dtype=np.int64)
+    G = groups.size
+    group_sizes = np.diff(np.concatenate([groups, [p]])).astype(np.int64)
+    penalty = np.sqrt(group_sizes).astype(dtype) if penalty is None else np.ascontiguousarray(penalty, dtype=dtype)
+    a = _CovArgs()
+    a.dtype = _dt(dtype); a.matrix_kind = A.kind; a.M = P(A.mat); a.n = A.n; a.p = p; a.ld = A.ld; a.row_major = int(A.row_major)
+    a.groups = P(groups); a.group_sizes = P(group_sizes); a.G = G; a.penalty = P(penalty); a.alpha = alpha
+    a.max_iters = max_iters; a.tol = tol; a.rdev_tol = rdev_tol; a.newton_tol = newton_tol; a.newton_max_iters = newton_max_iters
+    a.max_screen_size = G if max_screen_size is None else min(max_screen_size, G)
+    a.max_active_size = G if max_active_size is None else min(max_active_size, G)
+    a.pivot_subset_ratio = 0.1; a.pivot_subset_min = 1; a.pivot_slack_ratio = 1.25; a.screen_rule = 1
+    a.min_ratio = 1e-2; a.lmda_path_size = 100
+    return A, a, P, groups, group_sizes, penalty, dtype, p, G
+
+
+def gaussian_pin_cov(A, *, groups, alpha, penalty, screen_set, lmda_path, rsq, screen_beta, screen_grad, screen_is_active,
+                     active_set_size, active_set, max_active_size=None, max_iters=int(1e5), tol=1e-7, rdev_tol=1e-4,
+                     newton_tol=1e-12, newton_max_iters=1000):
+    """StateGaussianPinCov.solve: the gaussian_pin_cov wrapper (adelie/state.py:739-1000) + pin::cov::solve
+    (CORE/solver/solver_gaussian_pin_cov.hpp:529-777)."""
+    keep = []
+    A, a, P, groups, group_sizes, penalty, dtype, p, G = _cov_args(
+        A, keep, groups=groups, alpha=alpha, penalty=penalty, max_iters=max_iters, tol=tol, rdev_tol=rdev_tol,
+        newton_tol=newton_tol, newton_max_iters=newton_max_iters, max_active_size=max_active_size)
+    screen_set = np.ascontiguousarray(screen_set, dtype=np.int64)
+    act = np.zeros(G, dtype=np.int64)
+    act[:active_set_size] = np.asarray(active_set)[:active_set_size]
+    sb = np.ascontiguousarray(screen_beta, dtype=dtype)
+    a.screen_set = P(screen_set); a.S = screen_set.size; a.screen_beta = P(sb); a.screen_beta_size = sb.size
+    a.screen_is_active = P(np.ascontiguousarray(screen_is_active, dtype=np.int8)); a.active_set_size = active_set_size; a.active_set = P(act)
+    a.rsq = rsq; a.lmda = np.inf; a.lmda_max = -1.0
+    a.screen_grad = P(np.ascontiguousarray(screen_grad, dtype=dtype))
+    lp = np.ascontiguousarray(lmda_path, dtype=dtype)
+    a.lmda_path = P(lp); a.lmda_path_len = lp.size
+    h = lib().orc_cov_pin_solve(C.byref(a))
+    out = _collect(h, p, dtype)
+    out.screen_is_active = out.screen_is_active.astype(bool)
+    return out
+
+
+def gaussian_cov(A, v, *, groups=None, alpha=1.0, penalty=None, lmda_path=None, max_iters=int(1e5), tol=1e-7, rdev_tol=1e-3,
+                 newton_tol=1e-12, newton_max_iters=1000, early_exit=True, screen_rule="pivot", min_ratio=1e-2, lmda_path_size=100,
+                 max_screen_size=None, max_active_size=None, pivot_subset_ratio=0.1, pivot_subset_min=1, pivot_slack_ratio=1.25):
+    """adelie.solver.gaussian_cov (adelie/solver.py:39-352: initial invariants) + gaussian::cov::solve
+    (CORE/solver/solver_gaussian_cov.hpp:359-457)."""
+    keep = []
+    A, a, P, groups, group_sizes, penalty, dtype, p, G = _cov_args(
+        A, keep, groups=groups, alpha=alpha, penalty=penalty, max_iters=max_iters, tol=tol, rdev_tol=rdev_tol,
+        newton_tol=newton_tol, newton_max_iters=newton_max_iters, max_active_size=max_active_size, max_screen_size=max_screen_size)
+    if lmda_path is not None:
+        lmda_path = np.array(np.flip(np.sort(lmda_path)), dtype=dtype)
+    v = np.ascontiguousarray(v, dtype=dtype)
+    screen_set = np.arange(G)[(penalty <= 0) | (alpha <= 0)].astype(np.int64)
+    screen_beta = np.zeros(int(np.sum(group_sizes[screen_set])), dtype=dtype)
+    screen_is_active = np.ones(screen_set.shape[0], dtype=np.int8)
+    active_set = np.zeros(G, dtype=np.int64)
+    active_set[:screen_set.size] = np.arange(screen_set.size)
+    grad = v.copy()                                                               # v - A @ 0
+    a.v = P(v); a.grad = P(grad)
+    a.screen_set = P(screen_set); a.S = screen_set.size; a.screen_beta = P(screen_beta); a.screen_beta_size = screen_beta.size
+    a.screen_is_active = P(screen_is_active); a.active_set_size = screen_set.size; a.active_set = P(active_set)
+    a.rsq = 0.0; a.lmda = np.inf; a.lmda_max = -1.0; a.setup_lmda_max = 1
+    if lmda_path is None:
+        a.setup_lmda_path = 1; a.lmda_path = None; a.lmda_path_len = 0
+    else:
+        a.setup_lmda_path = 0; a.lmda_path = P(lmda_path); a.lmda_path_len = lmda_path.size
+    a.min_ratio = min_ratio; a.lmda_path_size = lmda_path_size
+    a.pivot_subset_ratio = pivot_subset_ratio; a.pivot_subset_min = pivot_subset_min; a.pivot_slack_ratio = pivot_slack_ratio
+    a.screen_rule = {"strong": 0, "pivot": 1}[screen_rule]
+    a.early_exit = int(early_exit)
+    h = lib().orc_cov_path_solve(C.byref(a))
+    out = _collect(h, p, dtype)
+    out.groups = groups; out.group_sizes = group_sizes; out.penalty = penalty
+    out.screen_is_active = out.screen_is_active.astype(bool)
     return out

@@ -4,6 +4,7 @@
 #include "oracle_capi.h"
 #include "adelie_oracle.hpp"
 #include "cox_oracle.hpp"
+#include "cov_oracle.hpp"
 #include <map>
 #include <memory>
 
@@ -248,6 +249,117 @@ double glm_eval(int family, int op, idx_t n, idx_t K, const void* y, const void*
     return 0;
 }
 
+
+// ---- covariance method -----------------------------------------------------------------------
+template <class T>
+std::unique_ptr<MatrixCovBase<T>> make_cov_matrix(int kind, const void* M, idx_t n, idx_t p, idx_t ld, bool row_major) {
+    if (kind == ORC_COV_DENSE) return std::make_unique<MatrixCovDense<T>>((const T*)M, p, ld, row_major);
+    return std::make_unique<MatrixCovLazyCov<T>>((const T*)M, n, p, ld, row_major);
+}
+
+template <class T>
+void fill_cov_state(const orc_cov_args* a, CovPathState<T>& s, MatrixCovBase<T>* A) {
+    s.A = A; s.v = (const T*)a->v; s.p = a->p; s.n = 0; s.G = a->G;
+    s.groups = a->groups; s.group_sizes = a->group_sizes; s.alpha = (T)a->alpha; s.penalty = (const T*)a->penalty;
+    s.rsq = (T)a->rsq; s.lmda = (T)a->lmda; s.lmda_max = (T)a->lmda_max;
+    s.min_ratio = (T)a->min_ratio; s.lmda_path_size = a->lmda_path_size;
+    s.max_screen_size = a->max_screen_size; s.max_active_size = a->max_active_size;
+    s.pivot_subset_ratio = (T)a->pivot_subset_ratio; s.pivot_subset_min = a->pivot_subset_min; s.pivot_slack_ratio = (T)a->pivot_slack_ratio;
+    s.screen_rule = a->screen_rule; s.max_iters = a->max_iters; s.tol = (T)a->tol; s.rdev_tol = (T)a->rdev_tol;
+    s.newton_tol = (T)a->newton_tol; s.newton_max_iters = a->newton_max_iters;
+    s.early_exit = a->early_exit; s.setup_lmda_max = a->setup_lmda_max; s.setup_lmda_path = a->setup_lmda_path;
+    s.intercept = false;
+    if (a->lmda_path && a->lmda_path_len > 0) s.lmda_path.assign((const T*)a->lmda_path, (const T*)a->lmda_path + a->lmda_path_len);
+    s.screen_set.assign(a->screen_set, a->screen_set + a->S);
+    s.screen_beta.assign((const T*)a->screen_beta, (const T*)a->screen_beta + a->screen_beta_size);
+    s.screen_is_active.assign(a->screen_is_active, a->screen_is_active + a->S);
+    s.active_set_size = a->active_set_size;
+    s.active_set.assign(a->active_set, a->active_set + a->G);
+    if (a->grad) s.grad.assign((const T*)a->grad, (const T*)a->grad + a->p); else s.grad.assign(a->p, T(0));
+}
+
+template <class T>
+void collect_cov_common(const CovPathState<T>& s, Result& R) {
+    R.scalars["rsq"] = s.rsq; R.scalars["active_set_size"] = (double)s.active_set_size;
+    R.vecs["screen_beta"] = to_d<T>(s.screen_beta); R.vecs["screen_grad"] = to_d<T>(s.screen_grad); R.vecs["screen_vars"] = to_d<T>(s.screen_vars);
+    { std::vector<double> flat; for (const auto& V : s.screen_transforms) flat.insert(flat.end(), V.begin(), V.end()); R.vecs["screen_transforms_flat"] = flat; }
+    R.ivecs["screen_set"] = std::vector<int64_t>(s.screen_set.begin(), s.screen_set.end());
+    R.ivecs["screen_begins"] = std::vector<int64_t>(s.screen_begins.begin(), s.screen_begins.end());
+    R.ivecs["screen_is_active"] = std::vector<int64_t>(s.screen_is_active.begin(), s.screen_is_active.end());
+    R.ivecs["active_set"] = std::vector<int64_t>(s.active_set.begin(), s.active_set.begin() + s.active_set_size);
+}
+
+template <class T>
+void run_cov_path(const orc_cov_args* a, Result& R) {
+    auto A = make_cov_matrix<T>(a->matrix_kind, a->M, a->n, a->p, a->ld, a->row_major != 0);
+    CovPathState<T> s;
+    fill_cov_state(a, s, A.get());
+    const double t0 = now_s();
+    try { init_cov_path_state(s); solve_path_cov(s); }
+    catch (const std::exception& e) { R.error = e.what(); }
+    R.scalars["total_time"] = now_s() - t0;
+    R.scalars["lmda_max"] = s.lmda_max; R.scalars["lmda"] = s.lmda;
+    R.scalars["n_sweeps"] = (double)s.n_sweeps; R.scalars["n_group_updates"] = (double)s.n_group_updates;
+    collect_cov_common(s, R);
+    R.vecs["lmda_path"] = to_d<T>(s.lmda_path); R.vecs["lmdas"] = to_d<T>(s.lmdas); R.vecs["devs"] = to_d<T>(s.devs);
+    R.vecs["intercepts"] = to_d<T>(s.intercepts); R.vecs["grad"] = to_d<T>(s.grad); R.vecs["abs_grad"] = to_d<T>(s.abs_grad);
+    R.vecs["benchmark_screen"] = s.benchmark_screen; R.vecs["benchmark_fit_screen"] = s.benchmark_fit_screen;
+    R.vecs["benchmark_fit_active"] = s.benchmark_fit_active; R.vecs["benchmark_kkt"] = s.benchmark_kkt;
+    R.vecs["benchmark_invariance"] = s.benchmark_invariance;
+    R.ivecs["n_valid_solutions"] = std::vector<int64_t>(s.n_valid_solutions.begin(), s.n_valid_solutions.end());
+    R.ivecs["active_sizes"] = std::vector<int64_t>(s.active_sizes.begin(), s.active_sizes.end());
+    R.ivecs["screen_sizes"] = std::vector<int64_t>(s.screen_sizes.begin(), s.screen_sizes.end());
+    R.indptr.push_back(0);
+    for (size_t l = 0; l < s.beta_idx.size(); ++l) {
+        for (size_t k = 0; k < s.beta_idx[l].size(); ++k) { R.indices.push_back(s.beta_idx[l][k]); R.values.push_back((double)s.beta_val[l][k]); }
+        R.indptr.push_back((int64_t)R.indices.size());
+    }
+}
+
+// gaussian_pin_cov wrapper (PY/state.py:739-1000: screen_vars / screen_transforms / screen_subset_order derived from A) + pin::cov::solve
+template <class T>
+void run_cov_pin(const orc_cov_args* a, Result& R) {
+    auto A = make_cov_matrix<T>(a->matrix_kind, a->M, a->n, a->p, a->ld, a->row_major != 0);
+    CovPathState<T> s;
+    fill_cov_state(a, s, A.get());
+    CovPinState<T> ps;
+    const double t0 = now_s();
+    try {
+        cov_update_screen_derived(s);
+        s.screen_grad.assign((const T*)a->screen_grad, (const T*)a->screen_grad + s.screen_subset.size());
+        ps.A = s.A; ps.groups = s.groups; ps.group_sizes = s.group_sizes; ps.G = s.G; ps.alpha = s.alpha; ps.penalty = s.penalty;
+        ps.screen_set = s.screen_set.data(); ps.screen_begins = s.screen_begins.data(); ps.S = (idx_t)s.screen_set.size();
+        ps.screen_vars = s.screen_vars.data(); ps.screen_transforms = &s.screen_transforms;
+        ps.screen_subset_order = s.screen_subset_order.data(); ps.screen_subset_ordered = s.screen_subset_ordered.data(); ps.m = (idx_t)s.screen_subset.size();
+        ps.lmda_path = s.lmda_path;
+        ps.max_active_size = s.max_active_size; ps.max_iters = s.max_iters; ps.tol = s.tol; ps.rdev_tol = s.rdev_tol;
+        ps.newton_tol = s.newton_tol; ps.newton_max_iters = s.newton_max_iters;
+        ps.rsq = s.rsq; ps.screen_beta = s.screen_beta.data(); ps.screen_grad = s.screen_grad.data(); ps.screen_is_active = s.screen_is_active.data();
+        ps.active_set_size = s.active_set_size; ps.active_set = s.active_set.data();
+        cov_pin_solve(ps);
+    } catch (const std::exception& e) { R.error = e.what(); }
+    s.rsq = ps.rsq; s.active_set_size = ps.active_set_size;
+    R.scalars["total_time"] = now_s() - t0;
+    R.scalars["iters"] = (double)ps.iters; R.scalars["n_group_updates"] = (double)ps.n_group_updates;
+    collect_cov_common(s, R);
+    R.vecs["rsqs"] = to_d<T>(ps.rsqs); R.vecs["lmdas"] = to_d<T>(ps.lmdas); R.vecs["intercepts"] = to_d<T>(ps.intercepts);
+    R.vecs["benchmark_screen"] = ps.benchmark_screen; R.vecs["benchmark_active"] = ps.benchmark_active;
+    R.indptr.push_back(0);
+    for (size_t l = 0; l < ps.beta_idx.size(); ++l) {
+        for (size_t k = 0; k < ps.beta_idx[l].size(); ++k) { R.indices.push_back(ps.beta_idx[l][k]); R.values.push_back((double)ps.beta_val[l][k]); }
+        R.indptr.push_back((int64_t)R.indices.size());
+    }
+}
+
+template <class T>
+void cov_matrix_op(int kind, const void* M, idx_t n, idx_t p, idx_t ld, bool row_major, int op, const int64_t* subset, idx_t s,
+                   const int64_t* indices, const void* values, idx_t k, idx_t i0, idx_t q, void* out) {
+    auto A = make_cov_matrix<T>(kind, M, n, p, ld, row_major);
+    if (op == 0) A->bmul(subset, s, indices, (const T*)values, k, (T*)out);
+    else if (op == 1) A->mul(indices, (const T*)values, k, (T*)out);
+    else A->to_dense(i0, q, (T*)out);
+}
+
 } // namespace
 
 extern "C" {
@@ -265,6 +377,25 @@ void* orc_pin_solve(orc_pin_args* a) {
         if (a->dtype == ORC_F32) run_pin<float>(a, *R); else run_pin<double>(a, *R);
     } catch (const std::exception& e) { R->error = e.what(); }
     return R;
+}
+
+void* orc_cov_path_solve(const orc_cov_args* a) {
+    auto* R = new Result();
+    try { if (a->dtype == ORC_F32) run_cov_path<float>(a, *R); else run_cov_path<double>(a, *R); }
+    catch (const std::exception& e) { R->error = e.what(); }
+    return R;
+}
+void* orc_cov_pin_solve(const orc_cov_args* a) {
+    auto* R = new Result();
+    try { if (a->dtype == ORC_F32) run_cov_pin<float>(a, *R); else run_cov_pin<double>(a, *R); }
+    catch (const std::exception& e) { R->error = e.what(); }
+    return R;
+}
+void orc_cov_matrix_op(int dtype, int kind, const void* M, int64_t n, int64_t p, int64_t ld, int row_major, int op,
+                       const int64_t* subset, int64_t s, const int64_t* indices, const void* values, int64_t k,
+                       int64_t i0, int64_t q, void* out) {
+    if (dtype == ORC_F32) cov_matrix_op<float>(kind, M, n, p, ld, row_major != 0, op, subset, s, indices, values, k, i0, q, out);
+    else cov_matrix_op<double>(kind, M, n, p, ld, row_major != 0, op, subset, s, indices, values, k, i0, q, out);
 }
 void orc_result_free(void* h) { delete (Result*)h; }
 const char* orc_result_error(void* h) { return ((Result*)h)->error.c_str(); }

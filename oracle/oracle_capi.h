@@ -93,6 +93,29 @@ int orc_search_pivot(int64_t n, const double* x, const double* y, double* mses);
 void orc_jacobi_eigh(int64_t q, double* A, double* D, double* V);
 void orc_set_config(const char* name, double value);
 
+/* ---- covariance method (oracle/cov_oracle.hpp): gaussian_cov path solve, gaussian_pin_cov solve, MatrixCov operators ---- */
+enum { ORC_COV_DENSE = 0, ORC_COV_LAZY = 1 };
+typedef struct orc_cov_args {
+    int32_t dtype; int32_t matrix_kind;      /* ORC_COV_DENSE: M = A (p x p); ORC_COV_LAZY: M = X (n x p), A = X^T X */
+    const void* M; int64_t n, p, ld; int32_t row_major;
+    const void* v;                            /* (p,) linear term (path solve) */
+    const int64_t* groups; const int64_t* group_sizes; int64_t G; const void* penalty; double alpha;
+    const int64_t* screen_set; int64_t S; const void* screen_beta; int64_t screen_beta_size;
+    const int8_t* screen_is_active; int64_t active_set_size; const int64_t* active_set;
+    double rsq, lmda, lmda_max; const void* grad;             /* grad (p,): path solve */
+    const void* screen_grad;                                   /* pin solve: gradient on the screen values */
+    const void* lmda_path; int64_t lmda_path_len; int32_t setup_lmda_max, setup_lmda_path;
+    double min_ratio; int64_t lmda_path_size, max_screen_size, max_active_size;
+    double pivot_subset_ratio; int64_t pivot_subset_min; double pivot_slack_ratio; int32_t screen_rule;
+    int64_t max_iters; double tol, rdev_tol, newton_tol; int64_t newton_max_iters; int32_t early_exit;
+} orc_cov_args;
+void* orc_cov_path_solve(const orc_cov_args* args);
+void* orc_cov_pin_solve(const orc_cov_args* args);
+/* op 0 bmul (subset s, indices/values k -> out (s,)), 1 mul (indices/values k -> out (p,)), 2 to_dense (i0, q -> out q*q col-major) */
+void orc_cov_matrix_op(int dtype, int kind, const void* M, int64_t n, int64_t p, int64_t ld, int row_major, int op,
+                       const int64_t* subset, int64_t s, const int64_t* indices, const void* values, int64_t k,
+                       int64_t i0, int64_t q, void* out);
+
 #ifdef __cplusplus
 }
 #endif
