@@ -1145,6 +1145,15 @@ static int cov_state_vec_f64(const CovPathState<T>& s, const std::string& nm, do
     if (nm == "benchmark_fit_active") return copy_vec<double>(s.benchmark_fit_active, out, cap, len);
     if (nm == "benchmark_kkt") return copy_vec<double>(s.benchmark_kkt, out, cap, len);
     if (nm == "benchmark_invariance") return copy_vec<double>(s.benchmark_invariance, out, cap, len);
+    if (nm == "sweep_stats") {
+        *len = 8;
+        if (out) {
+            std::vector<long long> h(8, 0);
+            if (s.d_stats.n) { s.d_stats.download(h.data(), 8); AB_CUDA(cudaStreamSynchronize(0)); }
+            for (int64_t i = 0; i < std::min<int64_t>(cap, 8); ++i) out[i] = (double)h[i];
+        }
+        return AB_OK;
+    }
     g_last_error = "adelie_core: unknown state vector " + nm;
     return AB_ERR_ARG;
 }

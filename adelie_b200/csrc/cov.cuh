@@ -8,13 +8,14 @@
 // so a group update costs (screen values) x gs multiply-adds whatever n is.
 //
 // Device design.  ONE thread-block cluster of up to 8 CTAs owns the whole solve (persistent, one launch per lambda):
-//   * the screen gradient lives in DISTRIBUTED SHARED MEMORY: CTA r holds the slice [r L, (r + 1) L) of the screen values;
-//   * every CTA replicates the proximal update (same inputs, same instructions => identical coefficients, no broadcast of the
-//     result), reading the gs gradient values of the group from their owner's slice over DSMEM (~215 cycles);
-//   * every CTA then applies the rank-gs update to ITS slice, gathering rows of A through L2 (the rows of the screen groups are
-//     ~(screen values)^2 elements, i.e. L2-resident for the sizes the covariance method is meant for);
-//   * two cluster barrier phases per group update order the DSMEM reads against the slice updates ("reads done" is released
-//     before the Newton iteration and acquired after it, so it costs nothing; "updates done" is the one exposed barrier).
+//   * the screen gradient lives in DISTRIBUTED SHARED MEMORY: CTA r holds the slice [r L, (r + 1) L) of the screen values, about one
+//     value per thread;
+//   * every CTA replicates the proximal update (same inputs, same instructions => identical coefficients, nothing to broadcast
+//     afterwards); the gs gradient values it needs are PUSHED by their owner threads into every CTA's shared memory over DSMEM one
+//     group ahead, right after the owner updated them;
+//   * every thread then applies the rank-gs update to its screen values from a compact Gram of the screen set (gathered from A once per
+//     screen-set change, laid out so that the gs entries of one update are contiguous): one L2 round trip per update;
+//   * ONE cluster barrier (release / acquire) per group update publishes the updated slices and the pushed values.
 // Active-set sweeps update only the active positions and the inactive ones are brought up to date once, when the active set has
 // converged (solve_active, :390-527), exactly like the reference.
 #pragma once
@@ -26,6 +27,7 @@ namespace ab {
 
 constexpr int kCovThreads = 512;
 constexpr int kCovClusterMax = 8;
+constexpr int kCovPre = kGsMax / 32;           // group elements per lane of the prox warp (group sizes up to kGsMax)
 
 // ---------------------------------------------------------------------------------------------------------------
 // small kernels of the MatrixCov operators
@@ -225,10 +227,17 @@ struct CovMatrix {
 // ---------------------------------------------------------------------------------------------------------------
 // the fused pin solve: pin::cov::solve (solver_gaussian_pin_cov.hpp:529-725) for ONE lambda
 // ---------------------------------------------------------------------------------------------------------------
+// G[b * ldg + b'] = A(vcol[b], vcol[b']) = vrow[b][vcol[b']]: the Gram of the screen values in screen order, so that a group update reads
+// gs ROWS (the group's values b) at the columns of the threads' own screen values b' -- coalesced across a warp, no index lookups.
+template <class T>
+__global__ void cov_gather_gram_kernel(const T* const* __restrict__ vrow, const int32_t* __restrict__ vcol, int m, int64_t ldg, T* __restrict__ G) {
+    const int bp = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (bp < m) G[(int64_t)b * ldg + bp] = vrow[b][vcol[bp]];
+}
+
 template <class T>
 struct CovKernelArgs {
-    const T* const* vrow;          // [m] row of A behind screen value b: vrow[b][j] = A(vcol[b], j)
-    const int32_t* vcol;           // [m] column (= row) index of screen value b
+    const T* gram; int64_t ldg;    // [m][ldg] screen Gram, gram[b ldg + b'] = A(col_b, col_b')
     const GroupMeta* meta; int S;  // per screen position: col, gs, begin (first screen value), rec_off, pen
     const T* grec;                 // records [A(gs) | 0 | 0 | V(gs x gs, (r, c) -> r gs + c)]
     const T* beta_in; T* beta_rep; T* beta_old_rep; int64_t beta_stride;     // per-CTA replicas of screen_beta (replica 0 = output)
@@ -239,20 +248,24 @@ struct CovKernelArgs {
     int m, L;                      // screen values, slice length per CTA (multiple of 32, L * cluster size >= m)
     double lmda, alpha, tol, newton_tol, dbeta_tol; long long max_iters; int newton_max_iters, max_active_size;
     int gs_cap;                    // >= largest group size, multiple of 4
+    int rec_cap;                   // elements of one staged record slot (multiple of 4); 0: records are read from global memory (groups above 32 columns)
+    long long* stats;              // optional [8] cycle counters of CTA 0 / thread 0 (Configs::sweep_profile): prox, sync, update + push, barrier, -, -, groups
 };
 
 struct CovCtrl { int changed, next, error, was_active; };
 
 template <class T>
 struct CovSmem {
-    // ctrl (64 B) | gsum[gs_cap] f64 | prox scratch 6 x [gs_cap] + 128 (double-sized) | del [gs_cap] (double-sized) | rowp[gs_cap] (8 B) |
-    // sg[L] (T) | pact[L] (int8)
-    __host__ __device__ static size_t fixed_bytes(int gs_cap) { return 64 + sizeof(double) * ((size_t)gs_cap * 9 + 128); }
-    __host__ __device__ static size_t total(int gs_cap, int L) { return (fixed_bytes(gs_cap) + (size_t)L * (sizeof(T) + 1) + 15) / 16 * 16; }
+    // ctrl (64 B) | gsum[gs_cap] f64 | prox scratch 6 x [gs_cap] + 128 (double-sized) | del [gs_cap] (double-sized) | gbuf[2][gs_cap] (double-sized) |
+    // rec[2][rec_cap] (T) | sg[L] (T) | pact[L] (int8)
+    __host__ __device__ static size_t fixed_bytes(int gs_cap, int rec_cap) { return 64 + sizeof(double) * ((size_t)gs_cap * 10 + 128) + sizeof(T) * (size_t)2 * rec_cap; }
+    __host__ __device__ static size_t total(int gs_cap, int rec_cap, int L) { return (fixed_bytes(gs_cap, rec_cap) + (size_t)L * (sizeof(T) + 1) + 15) / 16 * 16; }
 };
 
-enum { kCovNextActive = 0, kCovNextScreen = 1, kCovNextDone = 2 };
-
+// Persistent solve of one lambda by one cluster.  Protocol of a group update (ONE cluster barrier):
+//   [the group's gradient sits in every CTA's local gbuf]  warp 0: prox (replicated)  ->  __syncthreads  ->  every thread: rank-gs update of
+//   its screen values from the Gram, and the owners of the NEXT group's values push them into every CTA's other gbuf slot over DSMEM
+//   ->  cluster barrier (release / acquire).
 template <class T>
 __global__ void __launch_bounds__(kCovThreads, 1)
 cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
@@ -260,15 +273,16 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
     namespace cg = cooperative_groups;
     using P = T;
     cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank();
+    const int rank = (int)cluster.block_rank(), NC = (int)cluster.num_blocks();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CovCtrl* ctrl = reinterpret_cast<CovCtrl*>(smem_raw);
     double* gsum = reinterpret_cast<double*>(smem_raw + 64);                 // [gs_cap]
     double* pscr = gsum + a.gs_cap;                                          // 6 x [gs_cap] + 128
     double* del_raw = pscr + 6 * a.gs_cap + 128;                             // [gs_cap]
-    const T** rowp = reinterpret_cast<const T**>(del_raw + a.gs_cap);        // [gs_cap]
-    T* sg = reinterpret_cast<T*>(smem_raw + CovSmem<T>::fixed_bytes(a.gs_cap));   // [L]
+    double* gbuf_raw = del_raw + a.gs_cap;                                   // [2][gs_cap] (T)
+    T* rec_s = reinterpret_cast<T*>(gbuf_raw + 2 * a.gs_cap);                // [2][rec_cap]: the record of the group in flight and of the next one
+    T* sg = reinterpret_cast<T*>(smem_raw + CovSmem<T>::fixed_bytes(a.gs_cap, a.rec_cap));   // [L]
     int8_t* pact = reinterpret_cast<int8_t*>(sg + a.L);                      // [L]
     P* p_aold = reinterpret_cast<P*>(pscr);
     P* p_A = reinterpret_cast<P*>(pscr + a.gs_cap);
@@ -278,6 +292,7 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
     P* p_at = reinterpret_cast<P*>(pscr + 5 * a.gs_cap);
     P* p_scr = reinterpret_cast<P*>(pscr + 6 * a.gs_cap);
     T* s_del = reinterpret_cast<T*>(del_raw);
+    T* gbuf = reinterpret_cast<T*>(gbuf_raw);                                // slot s at gbuf + s * gs_cap
 
     const int L = a.L, m = a.m;
     const int s0 = rank * L;                                  // first screen value of this CTA's slice
@@ -299,8 +314,7 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
         const GroupMeta mm = a.meta[ss];
         for (int c = 0; c < mm.gs; ++c) { const int b = mm.begin + c - s0; if (b >= 0 && b < L) pact[b] = 1; }
     }
-    __syncthreads();
-    cluster.barrier_arrive();                                  // protocol: "updates done" is in the arrived state between group updates
+    cluster.sync();                                            // every CTA of the cluster is up before the first DSMEM store
 
     const P l1 = (P)(a.lmda * a.alpha), l2 = (P)(a.lmda * (1.0 - a.alpha));
     ProxState ps;                                              // replicated solver scalars (meaningful in warp 0)
@@ -309,31 +323,49 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
     int n_active = ps.A;                                       // every thread tracks the active-set size (updated through ctrl)
     int final_error = 0;
 
-    // One sweep (coordinate_descent, :243-385) over the active list (kind 0) or the whole screen set (kind 1)
+    // the owner of a screen value of group (gb0, ggs) stores it into slot `slot` of EVERY CTA's gbuf (DSMEM)
+    auto push_value = [&](int bl, int gb0, int ggs, int slot) {
+        const int c = s0 + bl - gb0;
+        if (c >= 0 && c < ggs) {
+            const T val = sg[bl];
+            T* dst = gbuf + slot * a.gs_cap + c;
+            for (int r = 0; r < NC; ++r) *cluster.map_shared_rank(dst, r) = val;
+        }
+    };
+
+    // One sweep (coordinate_descent, :243-385) over the active list (kind 0) or the whole screen set (kind 1).  The descriptor, the
+    // record and the current coefficients of a group are fetched ONE GROUP AHEAD (a group never changes another group's coefficients).
     auto sweep = [&](int kind, int count) {
         if (warp == 0) ps.cm = 0;
+        if (count <= 0) return;
+        int ss = (kind == 0) ? a.active_set[0] : 0;
+        GroupMeta mm = a.meta[ss];
+        int cur = 0;                                           // gbuf / record slot of the group in flight
+        const bool prof = a.stats != nullptr && rank == 0 && tid == 0;
+        long long pt[7] = {0, 0, 0, 0, 0, 0, 0}; long long tc = prof ? clock64() : 0;
+#define COV_TICK(k) do { if (prof) { const long long t_ = clock64(); pt[k] += t_ - tc; tc = t_; } } while (0)
+        if (a.rec_cap && warp == 1) for (int e = lane; e < mm.rec_elems; e += 32) rec_s[e] = a.grec[mm.rec_off + e];
+        for (int bl = tid; bl < Lm; bl += kCovThreads) push_value(bl, mm.begin, mm.gs, 0);
+        T nold[kCovPre] = {};                                  // warp 0: old coefficients of the group, element lane + 32 k
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < kCovPre; ++k) { const int c = lane + 32 * k; nold[k] = (c < mm.gs) ? my_beta[mm.begin + c] : T(0); }
+        }
+        cluster.sync();
 #pragma unroll 1
         for (int idx = 0; idx < count; ++idx) {
-            const int ss = (kind == 0) ? a.active_set[idx] : idx;
-            const GroupMeta mm = a.meta[ss];
             const int gs = mm.gs, b0 = mm.begin;
-            cluster.barrier_wait();                            // every slice holds the previous group's update
+            const bool has_next = idx + 1 < count;
+            const int ss_n = has_next ? ((kind == 0) ? a.active_set[idx + 1] : idx + 1) : ss;
+            const GroupMeta mm_n = a.meta[ss_n];               // (consumed after the prox)
+            COV_TICK(3);
             if (warp == 0) {
-                // the group's gradient from its owner slice(s) over DSMEM, its old coefficients from the replica
-#pragma unroll 1
-                for (int c = lane; c < gs; c += 32) {
-                    const int b = b0 + c, owner = b / L;
-                    const T* remote = cluster.map_shared_rank(sg + (b - owner * L), owner);
-                    gsum[c] = (double)*remote;
-                    p_aold[c] = (P)my_beta[b];
-                    rowp[c] = a.vrow[b];
-                }
+                const T* gcur = gbuf + cur * a.gs_cap;
+#pragma unroll
+                for (int k = 0; k < kCovPre; ++k) { const int c = lane + 32 * k; if (c < gs) { gsum[c] = (double)gcur[c]; p_aold[c] = (P)nold[k]; } }
                 __syncwarp();
-            }
-            cluster.barrier_arrive();                          // "reads done" (released before the prox, acquired after it)
-            if (warp == 0) {
                 int changed = 0;
-                const T* rec = a.grec + mm.rec_off;
+                const T* rec = a.rec_cap ? rec_s + (size_t)cur * a.rec_cap : a.grec + mm.rec_off;
                 const P pk = (P)mm.pen;
                 if (gs == 1) {                                 // :291-322
                     const P ak_old = p_aold[0], A_kk = (P)rec[0];
@@ -351,7 +383,12 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
                     }
                 } else {
                     const ProxCtx<T, P> px{p_aold, p_A, p_gk, p_gt, p_atold, p_at, p_scr, s_del, gsum, my_beta};
-                    changed = prox_group<T, P>(px, rec, gs, b0, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters, (P)a.dbeta_tol, 0, ps, lane, nullptr);
+                    if (gs <= 32) {                            // one coefficient per lane, record in shared memory
+                        const ProxPre<P> pre = prox_small_pre<T, P>(rec, gs, p_aold, lane);
+                        changed = prox_small_post<T, P>(px, pre, rec, gs, b0, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters, (P)a.dbeta_tol, 0, ps, lane, nullptr);
+                    } else {
+                        changed = prox_group<T, P>(px, rec, gs, b0, l1 * pk, l2 * pk, (P)a.newton_tol, a.newton_max_iters, (P)a.dbeta_tol, 0, ps, lane, nullptr);
+                    }
                 }
                 int was_active = 1;
                 if (changed && kind == 1) {                    // add_active_set (:617-628)
@@ -367,31 +404,63 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
                 ++n_updates; n_cols += gs;
                 __syncwarp();
                 if (lane == 0) { ctrl->changed = changed; ctrl->was_active = was_active; ctrl->error = ps.error; }
+                if (has_next) {                                // the next group's coefficients: the loads complete behind the slice update
+#pragma unroll
+                    for (int k = 0; k < kCovPre; ++k) { const int c = lane + 32 * k; nold[k] = (c < mm_n.gs) ? my_beta[mm_n.begin + c] : T(0); }
+                }
+            } else if (warp == 1 && a.rec_cap && has_next) {   // stage the next group's record while warp 0 solves this one
+                T* dst = rec_s + (size_t)(cur ^ 1) * a.rec_cap;
+                for (int e = lane; e < mm_n.rec_elems; e += 32) dst[e] = a.grec[mm_n.rec_off + e];
             }
-            cluster.barrier_wait();                            // nobody still reads the old gradient of this group
-            __syncthreads();                                   // del / ctrl of this CTA's warp 0
+            COV_TICK(0);
+            __syncthreads();                                   // del / ctrl of this CTA's warp 0, the staged record
             const int changed = ctrl->changed;
-            if (changed) {
-                // rank-gs update of this CTA's slice: sg[b'] -= sum_c del_c A(col_k + c, col_b'), del = new - old = -s_del
+            COV_TICK(1);
+            // rank-gs update of this CTA's slice: sg[b'] -= sum_c del_c A(col_k + c, col_b'), del = new - old = -s_del (two values of the thread
+            // in flight, gs contiguous Gram entries each); then the owners of the next group's values publish them to every CTA
+            const int nb0 = mm_n.begin, ngs = has_next ? mm_n.gs : 0;
 #pragma unroll 1
-                for (int bl = tid; bl < Lm; bl += kCovThreads) {
-                    if (kind == 0 && !pact[bl]) continue;
-                    const int j = a.vcol[s0 + bl];
-                    T acc = 0;
-#pragma unroll 4
-                    for (int c = 0; c < gs; ++c) acc -= s_del[c] * rowp[c][j];
-                    sg[bl] -= acc;
+            for (int bl = tid; bl < Lm; bl += 2 * kCovThreads) {
+                const int bl2 = bl + kCovThreads;
+                const bool in2 = bl2 < Lm;
+                const bool on1 = changed && !(kind == 0 && !pact[bl]);
+                const bool on2 = changed && in2 && !(kind == 0 && !pact[bl2]);
+                if (on1 || on2) {
+                    const T* g1 = a.gram + (size_t)b0 * a.ldg + (s0 + bl);            // column b' of the group's rows
+                    const int off2 = in2 ? kCovThreads : 0;
+                    T acc1 = 0, acc2 = 0;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < gs; c0 += 12) {                             // (groups of <= 12: every load of the update in flight at once)
+                        T x[12], y[12];
+#pragma unroll
+                        for (int u = 0; u < 12; ++u) {
+                            const bool in = c0 + u < gs;
+                            const T* gr = g1 + (size_t)(c0 + u) * a.ldg;
+                            x[u] = (in && on1) ? gr[0] : T(0);
+                            y[u] = (in && on2) ? gr[off2] : T(0);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 12; ++u) if (c0 + u < gs) { const T d = s_del[c0 + u]; acc1 -= d * x[u]; acc2 -= d * y[u]; }
+                    }
+                    if (on1) sg[bl] -= acc1;
+                    if (on2) sg[bl2] -= acc2;
                 }
-                if (!ctrl->was_active) {
-                    ++n_active;
-                    for (int c = tid; c < gs; c += kCovThreads) { const int b = b0 + c - s0; if (b >= 0 && b < L) pact[b] = 1; }
-                }
+                if (ngs) { push_value(bl, nb0, ngs, cur ^ 1); if (in2) push_value(bl2, nb0, ngs, cur ^ 1); }
+            }
+            if (changed && !ctrl->was_active) {
+                ++n_active;
+                for (int c = tid; c < gs; c += kCovThreads) { const int b = b0 + c - s0; if (b >= 0 && b < L) pact[b] = 1; }
             }
             const int err = ctrl->error;
-            __syncthreads();                                   // slice + pact written; ctrl may be overwritten by the next group
-            cluster.barrier_arrive();                          // "updates done"
+            COV_TICK(2);
+            cluster.sync();                                    // updates + pushed values visible everywhere (also the CTA barrier that frees ctrl / del)
+            if (prof) ++pt[6];
             if (err) { final_error = err; break; }
+            ss = ss_n; mm = mm_n; cur ^= 1;
         }
+        COV_TICK(3);
+        if (prof) for (int k = 0; k < 7; ++k) a.stats[k] += pt[k];
+#undef COV_TICK
     };
 
     // pin::cov::solve (:632-700): { solve_active; screen sweep } until the screen sweep converges
@@ -412,13 +481,13 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
             if (nx == 1) break;
         }
         if (final_error) break;
-        // ---- gradient of the inactive screen values for the whole active-set move (:500-526)
+        // ---- gradient of the inactive screen values for the whole active-set move (:500-526); slices are only read remotely through
+        //      the pushes of their own threads, so this is CTA-local work
         if (A0 > 0 && A0 < a.S) {
-            cluster.barrier_wait();                            // (nobody reads a slice outside a group update; the arrive below publishes this one)
 #pragma unroll 1
             for (int bl = tid; bl < Lm; bl += kCovThreads) {
                 if (pact[bl]) continue;
-                const int j = a.vcol[s0 + bl];
+                const T* g = a.gram + (s0 + bl);
                 T acc = 0;
 #pragma unroll 1
                 for (int ai = 0; ai < A0; ++ai) {
@@ -427,13 +496,12 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
                     for (int c = 0; c < ma.gs; ++c) {
                         const int b = ma.begin + c;
                         const T d = my_beta[b] - my_old[b];
-                        if (d != T(0)) acc += d * a.vrow[b][j];
+                        if (d != T(0)) acc += d * g[(size_t)b * a.ldg];
                     }
                 }
                 sg[bl] -= acc;
             }
             __syncthreads();
-            cluster.barrier_arrive();
         }
         // ---- one sweep over the screen set (:636-667)
         if (warp == 0) ++iters;
@@ -446,16 +514,14 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
         if (nx < 0) { final_error = -nx; break; }
         if (nx == 1) break;
     }
-    cluster.barrier_wait();                                    // balances the last arrive: every slice is final, nobody reads remotely any more
     for (int i = tid; i < Lm; i += kCovThreads) a.sgrad[s0 + i] = sg[i];
     if (rank == 0 && tid == 0) {
         a.sc->rsq = ps.rsq; a.sc->active_set_size = ps.A; a.sc->iters = iters;
         a.sc->n_group_updates = n_updates; a.sc->n_col_updates = n_cols; a.sc->error = final_error;
         a.sc->newton_iters_max = ps.newton_iters_max;
     }
-    cluster.sync();                                            // no CTA exits while a peer could still touch its shared memory
+    cluster.sync();                                            // no CTA exits while a peer could still store into its shared memory
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // StateGaussianCov / StateGaussianPinCov on the host: gaussian::cov::solve (solver_gaussian_cov.hpp:359-457) = solve_core
@@ -496,8 +562,8 @@ struct CovPathState {
     HostTimers timers;
     // ---------------- device
     DevBuf<T> d_v, d_grad, d_grec, d_beta_in, d_beta_rep, d_beta_old, d_sgrad;
-    DevBuf<GroupMeta> d_meta; DevBuf<const T*> d_vrow; DevBuf<int32_t> d_vcol, d_active_set;
-    DevBuf<int8_t> d_act_in, d_act_rep; DevBuf<PinScalars> d_sc; PinnedBuf<PinScalars> h_sc;
+    DevBuf<GroupMeta> d_meta; DevBuf<const T*> d_vrow; DevBuf<int32_t> d_vcol, d_active_set; DevBuf<T> d_gram;
+    DevBuf<int8_t> d_act_in, d_act_rep; DevBuf<PinScalars> d_sc; PinnedBuf<PinScalars> h_sc; DevBuf<long long> d_stats;
     std::vector<GroupMeta> h_meta; std::vector<T> h_grec; std::vector<const T*> h_vrow; std::vector<int32_t> h_vcol;
     size_t tables_uploaded_S = (size_t)-1;
     int gs_max_screen = 1;
@@ -636,7 +702,17 @@ struct CovPathState {
         d_meta.reserve_keep(S + 1); d_grec.reserve_keep(h_grec.size() + 4); d_vcol.reserve_keep(m + 1); d_vrow.reserve_keep(m + 1);
         if (S) d_meta.upload(h_meta.data(), S);
         if (!h_grec.empty()) d_grec.upload(h_grec.data(), h_grec.size());
-        if (m) { d_vcol.upload(h_vcol.data(), m); d_vrow.upload(h_vrow.data(), m); }
+        if (m) {
+            d_vcol.upload(h_vcol.data(), m); d_vrow.upload(h_vrow.data(), m);
+            // compact Gram of the screen values (rebuilt whenever the screen set grew: m^2 gathered elements, well under a millisecond
+            // for the screen sets the covariance method is used with)
+            if ((double)m * (double)m * sizeof(T) > 64e9) throw core_error("the screen set is too large for the device covariance solver (screen Gram above 64 GB).");
+            if (d_gram.n < m * m) { d_gram.free(); d_gram.alloc(m * m); }
+            dim3 grid((unsigned)((m + 255) / 256), (unsigned)m);
+            cov_gather_gram_kernel<T><<<grid, 256, 0, 0>>>(d_vrow.p, d_vcol.p, (int)m, (int64_t)m, d_gram.p);
+            AB_CUDA(cudaGetLastError());
+            ++n_kernel_launches;
+        }
         tables_uploaded_S = S;
     }
 
@@ -648,14 +724,15 @@ struct CovPathState {
         upload_tables();
         const DeviceInfo& di = DeviceInfo::get();
         const int gs_cap = (std::max(gs_max_screen, 1) + 3) / 4 * 4;
-        // cluster size: enough CTAs that every thread owns about two screen values, slices a multiple of 32
+        // cluster size: enough CTAs that every thread owns about one screen value, slices a multiple of 32
         int NC = 1;
-        while (NC < kCovClusterMax && (size_t)NC * 2 * kCovThreads < m) NC *= 2;
+        while (NC < kCovClusterMax && (size_t)NC * kCovThreads < m) NC *= 2;
         if (Configs::cov_cluster == 1 || Configs::cov_cluster == 2 || Configs::cov_cluster == 4 || Configs::cov_cluster == 8) NC = Configs::cov_cluster;
         int L = (int)((((m + NC - 1) / NC) + 31) / 32 * 32);
         L = std::max(L, 32);
-        size_t smem = CovSmem<T>::total(gs_cap, L);
-        while (smem > di.smem_optin && NC < kCovClusterMax) { NC *= 2; L = std::max<int>(32, (int)((((m + NC - 1) / NC) + 31) / 32 * 32)); smem = CovSmem<T>::total(gs_cap, L); }
+        const int rec_cap = gs_cap <= 32 ? (3 * gs_cap + gs_cap * gs_cap + 3) / 4 * 4 : 0;     // records staged in shared memory (one coefficient per lane)
+        size_t smem = CovSmem<T>::total(gs_cap, rec_cap, L);
+        while (smem > di.smem_optin && NC < kCovClusterMax) { NC *= 2; L = std::max<int>(32, (int)((((m + NC - 1) / NC) + 31) / 32 * 32)); smem = CovSmem<T>::total(gs_cap, rec_cap, L); }
         if (smem > di.smem_optin) throw core_error("the screen set is too large for the device covariance solver (screen gradient does not fit the cluster's shared memory).");
         last_cluster = NC; last_smem = (int)smem;
         const size_t stride = std::max<size_t>(m, 1), astride = std::max<size_t>(S, 1);
@@ -671,13 +748,15 @@ struct CovPathState {
         *h_sc.p = sc;
         d_sc.upload(h_sc.p, 1);
         CovKernelArgs<T> a{};
-        a.vrow = d_vrow.p; a.vcol = d_vcol.p; a.meta = d_meta.p; a.S = (int)S; a.grec = d_grec.p;
+        a.gram = d_gram.p; a.ldg = (int64_t)m; a.meta = d_meta.p; a.S = (int)S; a.grec = d_grec.p;
         a.beta_in = d_beta_in.p; a.beta_rep = d_beta_rep.p; a.beta_old_rep = d_beta_old.p; a.beta_stride = (int64_t)stride;
         a.sgrad = d_sgrad.p; a.is_active_in = d_act_in.p; a.act_rep = d_act_rep.p; a.act_stride = (int64_t)astride;
         a.active_set = d_active_set.p; a.sc = d_sc.p; a.m = (int)m; a.L = L;
         a.lmda = (double)lmda_; a.alpha = (double)alpha; a.tol = (double)tol; a.newton_tol = (double)newton_tol; a.dbeta_tol = Configs::dbeta_tol;
         a.max_iters = (long long)max_iters_left; a.newton_max_iters = (int)std::min<size_t>(newton_max_iters, (size_t)1 << 30);
-        a.max_active_size = (int)std::min<size_t>(max_active_size, (size_t)G); a.gs_cap = gs_cap;
+        a.max_active_size = (int)std::min<size_t>(max_active_size, (size_t)G); a.gs_cap = gs_cap; a.rec_cap = rec_cap;
+        if (Configs::sweep_profile && d_stats.n == 0) d_stats.alloc(8);
+        a.stats = Configs::sweep_profile ? d_stats.p : nullptr;
         AB_CUDA(cudaFuncSetAttribute(cov_pin_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(NC); cfg.blockDim = dim3(kCovThreads); cfg.dynamicSmemBytes = smem; cfg.stream = 0;

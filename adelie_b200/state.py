@@ -770,7 +770,7 @@ def gaussian_pin_naive(*, X, y_mean, y_var, constraints, groups, alpha, penalty,
 # ------------------------------------------------------------------------------------------------------------------
 # covariance method: StateGaussianCov / StateGaussianPinCov
 # ------------------------------------------------------------------------------------------------------------------
-_COV_VEC_F = ["rsqs", "lmda_path", "screen_beta", "screen_grad", "screen_vars", "grad", "abs_grad", "v", "devs", "lmdas",
+_COV_VEC_F = ["sweep_stats", "rsqs", "lmda_path", "screen_beta", "screen_grad", "screen_vars", "grad", "abs_grad", "v", "devs", "lmdas",
               "benchmark_screen", "benchmark_fit_screen", "benchmark_fit_active", "benchmark_kkt", "benchmark_invariance"]
 _COV_VEC_I = ["screen_set", "screen_begins", "screen_is_active", "active_set", "screen_subset_order", "screen_subset_ordered",
               "n_valid_solutions", "active_sizes", "screen_sizes"]

@@ -15,6 +15,8 @@ y = X @ beta + np.linalg.norm(beta) * rng.standard_normal(n).astype(np.float32)
 A = np.asfortranarray((X.T @ X) / n).astype(np.float32)
 v = (X.T @ y / n).astype(np.float32)
 groups = np.arange(0, p, gs)
+if os.environ.get("COV_PROF", "0") == "1":
+    ad.configs.set_configs("sweep_profile", 1)
 kw = dict(groups=groups, tol=1e-7, newton_tol=1e-6, early_exit=False, min_ratio=1e-2, lmda_path_size=100)
 for rep in range(2):
     Ad = ad.matrix.dense(A, method="cov")
@@ -24,6 +26,10 @@ for rep in range(2):
     print(f"gpu rep {rep}: {t1 - t0:.3f} s total, kernel {st.time_sweep_kernel:.3f} s, sweeps {st.n_sweeps}, group updates {st.n_group_updates}, "
           f"{st.n_group_updates / max(st.time_sweep_kernel, 1e-9):.0f} updates/s, screen {len(st.screen_set)}, active {st.active_set_size}, "
           f"cluster {st.cov_cluster}, err={st.error!r}")
+    if os.environ.get("COV_PROF", "0") == "1":
+        ss = st.sweep_stats
+        names = ["prox", "sync", "update_push", "barrier"]
+        print("  cycles per group update:", {k: round(ss[i] / max(ss[6], 1)) for i, k in enumerate(names)}, "groups", int(ss[6]))
     Ad.close()
 if os.environ.get("COV_CPU", "1") == "1":
     from oracle import oracle as orc
