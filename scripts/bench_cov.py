@@ -18,7 +18,7 @@ groups = np.arange(0, p, gs)
 if os.environ.get("COV_PROF", "0") == "1":
     ad.configs.set_configs("sweep_profile", 1)
 kw = dict(groups=groups, tol=1e-7, newton_tol=1e-6, early_exit=False, min_ratio=1e-2, lmda_path_size=100)
-for rep in range(2):
+for rep in range(int(os.environ.get("COV_REPS", "2"))):
     Ad = ad.matrix.dense(A, method="cov")
     t0 = time.time()
     st = ad.gaussian_cov(A=Ad, v=v, progress_bar=False, **kw)
