@@ -66,6 +66,19 @@ class CovStateArgs(C.Structure):
     ]
 
 
+GLM_CB2 = C.CFUNCTYPE(C.c_int, c_vp, c_vp, c_vp)                      # gradient / inv_link (ctx, eta, out)
+GLM_CB3 = C.CFUNCTYPE(C.c_int, c_vp, c_vp, c_vp, c_vp)                # hessian (ctx, eta, grad, hess)
+GLM_CB4 = C.CFUNCTYPE(C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp)          # inv_hessian_gradient (ctx, eta, grad, hess, out)
+GLM_CBL = C.CFUNCTYPE(C.c_int, c_vp, c_vp, C.POINTER(C.c_double))     # loss (ctx, eta, out)
+GLM_CBF = C.CFUNCTYPE(C.c_int, c_vp, C.POINTER(C.c_double))           # loss_full (ctx, out)
+
+
+class GlmCallbacks(C.Structure):
+    """Mirror of ``ab_glm_callbacks`` (include/adelie_b200.h)."""
+    _fields_ = [("ctx", c_vp), ("gradient", GLM_CB2), ("hessian", GLM_CB3), ("inv_hessian_gradient", GLM_CB4), ("loss", GLM_CBL),
+                ("loss_full", GLM_CBF), ("inv_link", GLM_CB2)]
+
+
 EXIT_COND_T = C.CFUNCTYPE(C.c_int, c_vp)
 CHECK_SIGNALS_T = C.CFUNCTYPE(C.c_int)
 
@@ -86,7 +99,7 @@ SYMBOLS = [
     "ab_io_snp_phased_ancestry_info", "ab_io_snp_phased_ancestry_get", "ab_io_snp_phased_ancestry_to_dense", "ab_matrix_snp_phased_ancestry_create",
     "ab_matrix_free", "ab_matrix_rows", "ab_matrix_cols", "ab_matrix_cmul", "ab_matrix_ctmul", "ab_matrix_bmul",
     "ab_matrix_btmul", "ab_matrix_mul", "ab_matrix_cov", "ab_matrix_window_gram", "ab_matrix_mul_multi", "ab_matrix_sq_mul", "ab_matrix_sp_tmul",
-    "ab_glm_create", "ab_glm_free", "ab_glm_gradient", "ab_glm_hessian", "ab_glm_inv_hessian_gradient", "ab_glm_loss",
+    "ab_glm_create", "ab_glm_create_callback", "ab_glm_free", "ab_glm_gradient", "ab_glm_hessian", "ab_glm_inv_hessian_gradient", "ab_glm_loss",
     "ab_glm_loss_full", "ab_glm_inv_link",
     "ab_state_create", "ab_state_free", "ab_state_solve", "ab_state_get_scalar", "ab_state_get_vec_f64",
     "ab_state_get_vec_i64", "ab_state_get_betas", "ab_state_get_screen_transform",
@@ -152,6 +165,7 @@ def load():
     L.ab_matrix_sp_tmul.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.ab_glm_create.argtypes = [C.c_int, C.c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, C.POINTER(c_vp)]
     L.ab_glm_free.argtypes = [c_vp]
+    L.ab_glm_create_callback.argtypes = [C.c_int, c_i64, c_i64, C.c_int, C.POINTER(GlmCallbacks), C.POINTER(c_vp)]
     L.ab_glm_gradient.argtypes = [c_vp, c_vp, c_vp]
     L.ab_glm_hessian.argtypes = [c_vp, c_vp, c_vp, c_vp]
     L.ab_glm_inv_hessian_gradient.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]

@@ -756,6 +756,53 @@ static Glm<T>* make_glm(int family, int64_t n, int64_t K, const void* y, const v
     throw core_error("unsupported GLM family.");
 }
 
+// User-defined GLM behind C callbacks (PyGlmBase / PyGlmMultiBase trampolines, py_glm.cpp:8-92, 240-330): device vectors are staged
+// through pinned host memory around every call.
+template <class T>
+struct GlmCallback : Glm<T> {
+    using B = Glm<T>;
+    ab_glm_callbacks cb;
+    PinnedBuf<T> h_eta, h_grad, h_hess, h_out;
+    GlmCallback(int64_t n_rows, int64_t K_, bool multi, const ab_glm_callbacks& c) : cb(c) {
+        B::name = "callback"; B::is_multi = multi; B::K = multi ? K_ : 1; B::n = multi ? n_rows * K_ : n_rows;
+        if (!c.gradient || !c.hessian || !c.loss || !c.loss_full) throw core_error("user-defined GLM: gradient, hessian, loss and loss_full callbacks are required.");
+        if (DistContext::get().active()) throw core_error("user-defined GLMs are not supported in row-sharded multi-GPU mode.");
+        h_eta.alloc(B::n); h_grad.alloc(B::n); h_hess.alloc(B::n); h_out.alloc(B::n);
+    }
+    void down(const T* d, PinnedBuf<T>& h) { AB_CUDA(cudaMemcpyAsync(h.p, d, B::n * sizeof(T), cudaMemcpyDeviceToHost, 0)); }
+    void up(const PinnedBuf<T>& h, T* d) { AB_CUDA(cudaMemcpyAsync(d, h.p, B::n * sizeof(T), cudaMemcpyHostToDevice, 0)); AB_CUDA(cudaStreamSynchronize(0)); }
+    static void chk(int rc, const char* what) { if (rc) throw solver_error(std::string("user-defined GLM: ") + what + "() raised an exception."); }
+    void gradient(const T* eta, T* grad) override {
+        down(eta, h_eta); AB_CUDA(cudaStreamSynchronize(0));
+        chk(cb.gradient(cb.ctx, h_eta.p, h_out.p), "gradient");
+        up(h_out, grad);
+    }
+    void hessian(const T* eta, const T* grad, T* hess) override {
+        down(eta, h_eta); down(grad, h_grad); AB_CUDA(cudaStreamSynchronize(0));
+        chk(cb.hessian(cb.ctx, h_eta.p, h_grad.p, h_out.p), "hessian");
+        up(h_out, hess);
+    }
+    void inv_hessian_gradient(const T* eta, const T* grad, const T* hess, T* out) override {
+        if (!cb.inv_hessian_gradient) { B::inv_hessian_gradient(eta, grad, hess, out); return; }
+        down(eta, h_eta); down(grad, h_grad); down(hess, h_hess); AB_CUDA(cudaStreamSynchronize(0));
+        chk(cb.inv_hessian_gradient(cb.ctx, h_eta.p, h_grad.p, h_hess.p, h_out.p), "inv_hessian_gradient");
+        up(h_out, out);
+    }
+    T loss(const T* eta) override {
+        down(eta, h_eta); AB_CUDA(cudaStreamSynchronize(0));
+        double out = 0;
+        chk(cb.loss(cb.ctx, h_eta.p, &out), "loss");
+        return (T)out;
+    }
+    T loss_full() override { double out = 0; chk(cb.loss_full(cb.ctx, &out), "loss_full"); return (T)out; }
+    void inv_link(const T* eta, T* out) override {
+        if (!cb.inv_link) throw core_error("user-defined GLM: inv_link() is not implemented.");
+        down(eta, h_eta); AB_CUDA(cudaStreamSynchronize(0));
+        chk(cb.inv_link(cb.ctx, h_eta.p, h_out.p), "inv_link");
+        up(h_out, out);
+    }
+};
+
 template <class T>
 struct GlmHost {
     static int64_t padn(Glm<T>& g) { return g.is_multi ? pad_rows(g.n / g.K) * g.K : pad_rows(g.n); }
@@ -772,6 +819,18 @@ int ab_glm_create(int dtype, int family, int64_t n, int64_t K, const void* y, co
     try {
         if (dtype == AB_F32) g->f32 = make_glm<float>(family, n, K, y, weights, cox_start, cox_stop, cox_strata, cox_tie_efron);
         else g->f64 = make_glm<double>(family, n, K, y, weights, cox_start, cox_stop, cox_strata, cox_tie_efron);
+    } catch (...) { delete g; throw; }
+    *out = g;
+    AB_CATCH
+}
+int ab_glm_create_callback(int dtype, int64_t n, int64_t K, int is_multi, const ab_glm_callbacks* callbacks, ab_glm** out) {
+    AB_TRY
+    if (!callbacks) throw core_error("user-defined GLM: callbacks must not be NULL.");
+    if (n < 1 || (is_multi && K < 1)) throw core_error("user-defined GLM: invalid shape.");
+    auto* g = new ab_glm{dtype, 0};
+    try {
+        if (dtype == AB_F32) g->f32 = new GlmCallback<float>(n, K, is_multi != 0, *callbacks);
+        else g->f64 = new GlmCallback<double>(n, K, is_multi != 0, *callbacks);
     } catch (...) { delete g; throw; }
     *out = g;
     AB_CATCH

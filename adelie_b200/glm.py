@@ -114,6 +114,109 @@ class GlmMultiBase(GlmBase):
     is_multi = True
 
 
+
+class _UserGlm(GlmBase):
+    """A GLM defined in Python (reference: subclass ``adelie.glm.GlmBase64`` / ``GlmMultiBase64`` and override the virtuals; the pybind
+    trampolines PyGlmBase / PyGlmMultiBase, adelie/src/py_glm.cpp:8-92, 240-330).  The subclass implements ``gradient(eta, grad)``,
+    ``hessian(eta, grad, hess)``, ``loss(eta)``, ``loss_full()`` and optionally ``inv_hessian_gradient`` / ``inv_link`` on NumPy arrays; the
+    device solver calls them once per IRLS iteration through ``ab_glm_create_callback`` (eta / grad / hess travel through pinned host
+    memory), the coordinate descent itself stays on the device."""
+    _user_dtype = None
+    opt = False
+
+    def __init__(self, name, y, weights):
+        y = np.asarray(y)
+        dtype = self._user_dtype
+        K = y.shape[1] if self.is_multi else 1
+        self._init_common(str(name), np.asarray(y, dtype=dtype), weights, dtype, K=K)
+        self._cb_keep = None
+
+    # the reference's pure virtuals
+    def gradient(self, eta, grad):
+        raise NotImplementedError("gradient() must be implemented by the user-defined GLM.")
+
+    def hessian(self, eta, grad, hess):
+        raise NotImplementedError("hessian() must be implemented by the user-defined GLM.")
+
+    def loss(self, eta):
+        raise NotImplementedError("loss() must be implemented by the user-defined GLM.")
+
+    def loss_full(self):
+        raise NotImplementedError("loss_full() must be implemented by the user-defined GLM.")
+
+    def inv_hessian_gradient(self, eta, grad, hess, inv_hess_grad):
+        """adelie_core/glm/glm_base.ipp:25-36"""
+        from . import configs as _configs
+        hmin = _configs._DEFAULTS["hessian_min"]
+        inv_hess_grad[...] = grad / (np.maximum(hess, 0) + hmin * (hess <= 0))
+
+    def inv_link(self, eta, out):
+        raise NotImplementedError("inv_link() is not implemented by the user-defined GLM.")
+
+    def _core(self):
+        if self._handle is None:
+            shape = self.y.shape
+            n_el = int(np.prod(shape))
+            dt = np.dtype(self.dtype)
+            cty = C.c_float if dt == np.float32 else C.c_double
+            self._cb_errors = []
+
+            def view(p, writable=True):
+                a = np.ctypeslib.as_array(C.cast(p, C.POINTER(cty)), shape=(n_el,)).reshape(shape)
+                return a
+
+            def guard(fn):
+                def wrapped(*args):
+                    try:
+                        fn(*args)
+                        return 0
+                    except BaseException as e:      # noqa: BLE001 -- reported through the solver's error string, re-raised by solve()
+                        self._cb_errors.append(e)
+                        return 1
+                return wrapped
+
+            def _loss(ctx, eta, out):
+                out[0] = float(self.loss(view(eta)))
+
+            def _loss_full(ctx, out):
+                out[0] = float(self.loss_full())
+            own_ihg = type(self).inv_hessian_gradient is not _UserGlm.inv_hessian_gradient
+            own_inv_link = type(self).inv_link is not _UserGlm.inv_link
+            cb = _lib.GlmCallbacks(
+                None,
+                _lib.GLM_CB2(guard(lambda ctx, eta, grad: self.gradient(view(eta), view(grad)))),
+                _lib.GLM_CB3(guard(lambda ctx, eta, grad, hess: self.hessian(view(eta), view(grad), view(hess)))),
+                _lib.GLM_CB4(guard(lambda ctx, eta, grad, hess, out: self.inv_hessian_gradient(view(eta), view(grad), view(hess), view(out))))
+                if own_ihg else _lib.GLM_CB4(),
+                _lib.GLM_CBL(guard(_loss)),
+                _lib.GLM_CBF(guard(_loss_full)),
+                _lib.GLM_CB2(guard(lambda ctx, eta, out: self.inv_link(view(eta), view(out)))) if own_inv_link else _lib.GLM_CB2(),
+            )
+            self._cb_keep = cb                       # the function pointers must outlive the core object
+            h = C.c_void_p()
+            _lib.check(_lib.load().ab_glm_create_callback(_lib.dtype_code(self.dtype), shape[0], self._K, int(self.is_multi), C.byref(cb), C.byref(h)))
+            self._handle = h
+        return self._handle
+
+
+class GlmBase64(_UserGlm):
+    _user_dtype = np.float64
+
+
+class GlmBase32(_UserGlm):
+    _user_dtype = np.float32
+
+
+class GlmMultiBase64(_UserGlm):
+    _user_dtype = np.float64
+    is_multi = True
+
+
+class GlmMultiBase32(_UserGlm):
+    _user_dtype = np.float32
+    is_multi = True
+
+
 class _Gaussian(GlmBase):
     def __init__(self, y, weights, dtype, opt):
         if y.ndim != 1:

@@ -89,6 +89,86 @@ class MatrixNaiveBase:
         return out.T
 
 
+class _UserMatrix(MatrixNaiveBase):
+    """A matrix defined in Python (reference: subclass ``adelie.matrix.MatrixNaiveBase64`` and override the virtuals; the pybind trampoline
+    PyMatrixNaiveBase, adelie/src/py_matrix.cpp:627-825).  The subclass implements ``rows()``, ``cols()`` and the operators on NumPy
+    arrays; Python-side callers (``grpnet``'s initial ``mul`` passes, ``@``) use them directly.  The device solver needs the entries in
+    HBM: the first time a state asks for the core handle the matrix is MATERIALISED through its own ``ctmul`` (column j = ctmul(j, 1, 0),
+    one call per column) into a dense device matrix -- a Python round trip per group update inside the fused sweep is not an option."""
+    _user_dtype = None
+
+    def __init__(self, n_threads=1):
+        MatrixNaiveBase.__init__(self, n_threads)
+        self._materialized = None
+
+    @property
+    def dtype(self):
+        return self._user_dtype
+
+    def rows(self):
+        raise NotImplementedError("rows() must be implemented by the user-defined matrix.")
+
+    def cols(self):
+        raise NotImplementedError("cols() must be implemented by the user-defined matrix.")
+
+    def ctmul(self, j, v, out):
+        raise NotImplementedError("ctmul() must be implemented by the user-defined matrix.")
+
+    def to_dense(self):
+        n, p = self.rows(), self.cols()
+        out = np.zeros((n, p), dtype=self._user_dtype, order="F")
+        for j in range(p):
+            self.ctmul(j, 1, out[:, j])
+        return out
+
+    def _dev(self):
+        if getattr(self, "_materialized", None) is None:
+            self._materialized = _Dense(self.to_dense(), getattr(self, "_n_threads", 1))
+        return self._materialized
+
+    def _core(self):
+        return self._dev()._core()
+
+    # operators the subclass did not override run on the materialised device copy
+    def cmul(self, j, v, weights):
+        return self._dev().cmul(j, v, weights)
+
+    cmul_safe = cmul
+
+    def bmul(self, j, q, v, weights, out):
+        self._dev().bmul(j, q, v, weights, out)
+
+    bmul_safe = bmul
+
+    def btmul(self, j, q, v, out):
+        self._dev().btmul(j, q, v, out)
+
+    def mul(self, v, weights, out):
+        self._dev().mul(v, weights, out)
+
+    def cov(self, j, q, sqrt_weights, out):
+        self._dev().cov(j, q, sqrt_weights, out)
+
+    def sq_mul(self, weights, out):
+        self._dev().sq_mul(weights, out)
+
+    def sp_tmul(self, v, out):
+        self._dev().sp_tmul(v, out)
+
+    def close(self):
+        m, self._materialized = getattr(self, "_materialized", None), None
+        if m is not None:
+            m.close()
+
+
+class MatrixNaiveBase64(_UserMatrix):
+    _user_dtype = np.float64
+
+
+class MatrixNaiveBase32(_UserMatrix):
+    _user_dtype = np.float32
+
+
 class _DeviceMatrix(MatrixNaiveBase):
     """Host-pointer operator front-end over an ``ab_matrix`` handle."""
     def __init__(self, dtype, n, p, n_threads):

@@ -145,6 +145,22 @@ enum { AB_GLM_GAUSSIAN = 1, AB_GLM_BINOMIAL_LOGIT = 2, AB_GLM_MULTIGAUSSIAN = 3,
 /* y: (n,) or (n,K) row-major; weights (n,) summing to 1.  Cox: y = status, plus start/stop/strata, tie 1 = efron, 0 = breslow */
 int ab_glm_create(int dtype, int family, int64_t n, int64_t K, const void* y, const void* weights,
                   const void* cox_start, const void* cox_stop, const int64_t* cox_strata, int cox_tie_efron, ab_glm** out);
+/* User-defined GLM (the pybind trampoline PyGlmBase / PyGlmMultiBase, adelie/src/py_glm.cpp:8-92, 240-330: a Python subclass of
+ * adelie.glm.GlmBase{32,64} / GlmMultiBase{32,64} overriding the virtuals).  The callbacks receive HOST arrays of n (single response) or
+ * n*K (multi-response, (n, K) row-major) elements of the state's dtype and return 0, or non-zero when the callee raised (the solve then
+ * stops with a solver error).  The library moves eta / grad / hess between HBM and pinned host memory around every call: one round trip
+ * per IRLS iteration, the coordinate descent itself stays on the device.  inv_hessian_gradient / inv_link may be NULL (inv_hessian_gradient
+ * then uses the base-class formula grad / max(hess, hessian_min), adelie_core/glm/glm_base.ipp:25-36). */
+typedef struct ab_glm_callbacks {
+    void* ctx;
+    int (*gradient)(void* ctx, const void* eta, void* grad);
+    int (*hessian)(void* ctx, const void* eta, const void* grad, void* hess);
+    int (*inv_hessian_gradient)(void* ctx, const void* eta, const void* grad, const void* hess, void* out);
+    int (*loss)(void* ctx, const void* eta, double* out);
+    int (*loss_full)(void* ctx, double* out);
+    int (*inv_link)(void* ctx, const void* eta, void* out);
+} ab_glm_callbacks;
+int ab_glm_create_callback(int dtype, int64_t n, int64_t K, int is_multi, const ab_glm_callbacks* callbacks, ab_glm** out);
 int ab_glm_free(ab_glm* g);
 int ab_glm_gradient(ab_glm* g, const void* eta, void* grad);
 int ab_glm_hessian(ab_glm* g, const void* eta, const void* grad, void* hess);

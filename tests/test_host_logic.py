@@ -166,3 +166,49 @@ def test_snpdat_reader_rejects_malformed_headers(tmp_path):
     off1 = struct.unpack("<Q", raw[col0 + 8:col0 + 16])[0]
     attempt(lambda b: b.__setitem__(slice(col0 + off1, col0 + off1 + 4), struct.pack("<I", 10 ** 6)), "malformed")    # chunk count runs off the column
     attempt(lambda b: b.__setitem__(slice(col0 + off1 + 4, col0 + off1 + 8), struct.pack("<I", 10 ** 5)), "malformed")  # row index out of range
+
+
+def test_user_defined_base_classes_host_side():
+    """User-defined GLM / matrix base classes (trampoline counterparts): construction, defaults and materialisation need no GPU."""
+    import numpy as np
+    import adelie_b200 as ad
+
+    class G(ad.glm.GlmBase64):
+        def __init__(self, y, w):
+            ad.glm.GlmBase64.__init__(self, "mine", y, w)
+
+    y = np.arange(5, dtype=np.float32)
+    g = G(y, np.ones(5))
+    assert g.dtype == np.float64 and g.y.dtype == np.float64 and not g.is_multi and g.opt is False
+    np.testing.assert_allclose(g.weights, 0.2)
+    for call in (lambda: g.gradient(y, y), lambda: g.hessian(y, y, y), lambda: g.loss(y), lambda: g.loss_full(), lambda: g.inv_link(y, y)):
+        try:
+            call()
+            raise AssertionError("expected NotImplementedError")
+        except NotImplementedError:
+            pass
+    hess = np.array([2.0, 0.0, -1.0, 4.0, 1.0]); grad = np.ones(5); out = np.empty(5)
+    g.inv_hessian_gradient(grad, grad, hess, out)                      # glm_base.ipp:25-36
+    np.testing.assert_allclose(out, [0.5, 1e24, 1e24, 0.25, 1.0])
+    assert ad.glm.GlmMultiBase32.is_multi and ad.glm.GlmMultiBase32._user_dtype == np.float32
+
+    class M(ad.matrix.MatrixNaiveBase32):
+        def __init__(self, Z):
+            ad.matrix.MatrixNaiveBase32.__init__(self)
+            self.Z = Z
+
+        def rows(self):
+            return self.Z.shape[0]
+
+        def cols(self):
+            return self.Z.shape[1]
+
+        def ctmul(self, j, v, out):
+            out += v * self.Z[:, j]
+
+    Z = np.arange(12, dtype=np.float32).reshape(4, 3)
+    m = M(Z)
+    assert m.dtype == np.float32 and m.shape == (4, 3) and isinstance(m, ad.matrix.MatrixNaiveBase)
+    D = m.to_dense()
+    assert D.flags.f_contiguous and D.dtype == np.float32
+    np.testing.assert_array_equal(D, Z)
