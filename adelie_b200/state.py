@@ -61,7 +61,7 @@ class base:
         a = _lib.StateArgs()
         keep = self._fill_args(a)
         h = C.c_void_p()
-        X = self._X
+        X = self.__dict__.get("_X_core") or self._X      # sparse multi-response states solve on the expanded CSC matrix
         glm_handle = self._glm._core() if self._use_glm else None
         _lib.check(_lib.load().ab_state_create(C.byref(a), X._core(), glm_handle, C.byref(h)))
         del keep
@@ -312,7 +312,10 @@ class _Naive(base):
             a.loss_null = 0.0 if c["loss_null"] is None else c["loss_null"]
             a.irls_max_iters = c["irls_max_iters"]; a.irls_tol = c["irls_tol"]
         a.resid = _lib.ptr(self._resid)
-        a.n_classes = c.get("n_classes", 1); a.multi_intercept = int(c.get("multi_intercept", False))
+        if c.get("core_expanded", False):      # [kron(1, I_K) | kron(X, I_K)] was materialised (sparse X): the core sees a single response
+            a.n_classes = 1; a.multi_intercept = 0
+        else:
+            a.n_classes = c.get("n_classes", 1); a.multi_intercept = int(c.get("multi_intercept", False))
         a.lmda_path = _lib.ptr(self._lmda_path); a.lmda_path_len = self._lmda_path.shape[0]
         a.lmda_max = c["lmda_max"]; a.min_ratio = c["min_ratio"]; a.lmda_path_size = c["lmda_path_size"]
         a.setup_lmda_max = int(c["setup_lmda_max"]); a.setup_lmda_path = int(c["setup_lmda_path"])
@@ -563,6 +566,24 @@ def _render_multi_inputs(*, X, offsets, intercept, n_threads, dtype):
     return Xe, offsets
 
 
+def _expand_sparse_multi(X, K, intercept, n_threads):
+    """Sparse X in a multi-response problem: [kron(1, I_K) | kron(X, I_K)] (adelie/state.py:1100-1125) is itself a sparse matrix with K
+    times the non-zeros.  The reference wraps X in generic kronecker_eye / concatenate views (matrix_naive_kronecker_eye.ipp:29-352); the
+    sparse device kernels are single-response, so the expanded CSC matrix is built once and the core state runs with n_classes = 1 on it
+    (same problem, same iterates: the multi-response layout is exactly this reformulation)."""
+    import scipy.sparse as sp
+    M = X._mat
+    n = M.shape[0]
+    blocks = []
+    if intercept:
+        blocks.append(sp.kron(np.ones((n, 1), dtype=M.dtype), sp.identity(K, dtype=M.dtype, format="csc"), format="csc"))
+    blocks.append(sp.kron(M, sp.identity(K, dtype=M.dtype, format="csc"), format="csc"))
+    Xs = sp.hstack(blocks, format="csc") if len(blocks) > 1 else blocks[0]
+    Xs = sp.csc_matrix(Xs, dtype=M.dtype)
+    Xs.sum_duplicates(); Xs.sort_indices()
+    return _matrix.sparse(Xs, n_threads=n_threads)
+
+
 def multigaussian_naive(*, X, y, X_means, y_var, resid, resid_sum, constraints, groups, group_sizes, alpha, penalty, weights,
                         offsets, screen_set, screen_beta, screen_is_active, active_set_size, active_set, rsq, lmda, grad,
                         lmda_path=None, lmda_max=None, max_iters=int(1e5), tol=1e-7, adev_tol=0.9, ddev_tol=0, newton_tol=1e-12,
@@ -590,6 +611,9 @@ def multigaussian_naive(*, X, y, X_means, y_var, resid, resid_sum, constraints, 
     arrays["X_means"] = np.array(X_means, copy=True, dtype=dtype)
     arrays["offsets"] = np.array(offsets, copy=True, dtype=dtype)
     arrays["X_expanded"] = Xe
+    expanded = isinstance(X, _matrix._Sparse)
+    if expanded:
+        arrays["X_core"] = _expand_sparse_multi(X, K, intercept, n_threads)
     # not the actual y_mean: a value that yields the right loss_null / loss_full (state.py:2339-2343)
     y_mean = np.linalg.norm(np.asarray(_dist_sum(np.sum(glm_obj.weights[:, None] * (y - offsets), axis=0))) / K)
     cfg = dict(alpha=float(alpha), y_mean=float(y_mean), y_var=float(y_var), resid_sum=float(resid_sum), rsq=float(rsq),
@@ -599,7 +623,7 @@ def multigaussian_naive(*, X, y, X_means, y_var, resid, resid_sum, constraints, 
                screen_rule=screen_rule, max_iters=int(max_iters), tol=tol, adev_tol=adev_tol, ddev_tol=ddev_tol,
                newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=early_exit, intercept=False,
                n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float(lmda), n_classes=int(K),
-               multi_intercept=bool(intercept))
+               multi_intercept=bool(intercept), core_expanded=expanded)
     return _MultiNaive(X=X, glm_obj=glm_obj, use_glm=False, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=Xe.cols())
 
 
@@ -636,6 +660,21 @@ def multiglm_naive(*, X, glm, constraints, groups, group_sizes, alpha, penalty, 
     arrays["offsets"] = np.array(np.asarray(offsets).ravel(), copy=True, dtype=dtype)
     arrays["eta"] = np.array(np.asarray(eta).ravel(), copy=True, dtype=dtype)
     arrays["X_expanded"] = Xe
+    expanded = isinstance(X, _matrix._Sparse)
+    if expanded:
+        arrays["X_core"] = _expand_sparse_multi(X, K, intercept, n_threads)
+        if loss_null is None:
+            # the null model of a multi-response GLM fits the K intercepts (update_loss_null of solver_multiglm_naive.hpp:99-186); the
+            # single-response core on the expanded matrix would take the loss at the offsets instead, so it is computed here, by the
+            # multi-response core on a one-column zero matrix (the null model does not involve X)
+            from .solver import grpnet as _grpnet
+            null = _grpnet(np.zeros((glm.y.shape[0], 1), dtype=dtype, order="F"), glm, offsets=np.asarray(offsets).reshape(glm.y.shape),
+                           lmda_path_size=1, intercept=intercept, irls_max_iters=irls_max_iters, irls_tol=irls_tol, early_exit=False,
+                           progress_bar=False)
+            if null.error != "":
+                raise RuntimeError(null.error)
+            loss_null = float(null.loss_null)
+            null.close()
     cfg = dict(alpha=float(alpha), beta0=0.0, loss_null=None if loss_null is None else float(loss_null),
                loss_full=float(loss_full), irls_max_iters=int(irls_max_iters), irls_tol=irls_tol,
                lmda_max=float(lmda_max), min_ratio=min_ratio, lmda_path_size=int(lmda_path_size), setup_lmda_max=setup_lmda_max,
@@ -644,7 +683,7 @@ def multiglm_naive(*, X, glm, constraints, groups, group_sizes, alpha, penalty, 
                screen_rule=screen_rule, max_iters=int(max_iters), tol=tol, adev_tol=adev_tol, ddev_tol=ddev_tol,
                newton_tol=newton_tol, newton_max_iters=int(newton_max_iters), early_exit=early_exit, intercept=False,
                n_threads=int(n_threads), active_set_size=int(active_set_size), lmda=float(lmda), n_classes=int(K),
-               multi_intercept=bool(intercept))
+               multi_intercept=bool(intercept), core_expanded=expanded)
     return _MultiNaive(X=X, glm_obj=glm, use_glm=True, dtype=dtype, cfg=cfg, arrays=arrays, p_cols=Xe.cols())
 
 

@@ -126,3 +126,34 @@ def test_device_generated_sparse_matrix():
     v = np.ones(5000, dtype=np.float32); out = np.empty(64, dtype=np.float32)
     X.mul(v, v, out)
     np.testing.assert_allclose(out, np.asarray(M.sum(axis=0)).ravel(), atol=1e-3)
+
+
+@pytest.mark.parametrize("intercept", [True, False])
+@pytest.mark.parametrize("family", ["multigaussian", "multinomial"])
+def test_sparse_multi_response_vs_dense(family, intercept):
+    """Multi-response on sparse X (reference: the generic kronecker_eye / concatenate views work on any matrix,
+    matrix_naive_kronecker_eye.ipp:29-352): the expanded CSC matrix [kron(1, I_K) | kron(X, I_K)] runs on the single-response sparse
+    kernels; the path must equal the one of the dense matrix on the multi-response kernels."""
+    n, p, K = 600, 30, 3
+    M = _rand_csc(n, p, 0.25, np.float64, seed=5)
+    rng = np.random.default_rng(6)
+    B = np.zeros((p, K)); B[:4] = rng.normal(size=(4, K))
+    eta = np.asarray(M @ B)
+    if family == "multigaussian":
+        y = eta + rng.normal(size=(n, K))
+        glm = lambda: ad.glm.multigaussian(y)
+        kw = dict(tol=1e-12)
+    else:
+        P = np.exp(eta - eta.max(axis=1, keepdims=True)); P /= P.sum(axis=1, keepdims=True)
+        y = np.array([rng.multinomial(1, P[i]) for i in range(n)], dtype=np.float64)
+        glm = lambda: ad.glm.multinomial(y)
+        kw = dict(tol=1e-12, irls_tol=1e-10)
+    kw.update(alpha=0.7, intercept=intercept, groups=np.arange(0, p, 3), early_exit=False, lmda_path_size=10, min_ratio=0.2, progress_bar=False)
+    st = ad.grpnet(ad.matrix.sparse(M), glm(), **kw)
+    dn = ad.grpnet(np.asfortranarray(M.todense()), glm(), **kw)
+    assert st.error == "" and dn.error == ""
+    assert st.betas.shape == dn.betas.shape == (10, p * K)
+    np.testing.assert_allclose(st.lmdas, dn.lmdas, rtol=1e-9)
+    assert _rel(np.asarray(st.betas.todense()), np.asarray(dn.betas.todense())) <= 1e-6
+    np.testing.assert_allclose(st.intercepts, dn.intercepts, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(st.devs, dn.devs, rtol=1e-6, atol=1e-9)
