@@ -63,6 +63,7 @@ struct BatchKernelArgs {
     int units_base, units_rem, rows_stride;
     int n_stages, stage_elems;
     int ch;                                              // columns per ring item (a group is streamed in ceil(gs / ch) <= 2 items)
+    int u_prefetch;                                      // 1: update tiles of active-set sweeps are prefetched ahead of the proximal updates
     int rec_stride;                                      // elements between the records inside a panel slot
     int pslot_elems;                                     // elements per panel slot = Ccap * 2 Ccap + B * rec_stride
     long long* stats;
@@ -501,14 +502,21 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                     ++pitem;
                 }
                 if (b >= 0) {
-                    // ---- U items of batch b, each as soon as its group's proximal update is done (and only if it moved)
+                    // ---- U items of batch b.  Active-set sweeps: PREFETCHED without waiting for the proximal updates (the tile does not
+                    // depend on them; almost every active group moves, and a tile that turns out to be unneeded is consumed and dropped by the
+                    // data warps), so the L2 -> shared-memory latency of the update tiles and the start of the next batch's HBM stream are no
+                    // longer exposed behind every proximal update.  Screen sweeps (most groups do not move): issued per group once it moved.
                     const int p0 = b * B, nbg = min(B, count - p0);
                     const int upar = ubatch & 1;
                     for (int k = 0; k < nbg && running; ++k) {
                         const int ss = (kind == kSweepActive) ? dev::ld_cg(a.active_set + p0 + k) : p0 + k;
                         const GroupMeta m = a.meta[ss];
-                        if (!dev::mbar_wait(&prox_bar[upar * kBatchMax + k], (uint32_t)(ubatch >> 1) & 1u, abort_flag, halt)) { running = false; break; }
-                        if (*reinterpret_cast<volatile int*>(&ctrl->changed[upar][k]))
+                        bool fetch = true;
+                        if (kind != kSweepActive || !a.u_prefetch) {
+                            if (!dev::mbar_wait(&prox_bar[upar * kBatchMax + k], (uint32_t)(ubatch >> 1) & 1u, abort_flag, halt)) { running = false; break; }
+                            fetch = *reinterpret_cast<volatile int*>(&ctrl->changed[upar][k]) != 0;
+                        }
+                        if (fetch)
                             for (int c0 = 0; c0 < m.gs && running; c0 += a.ch) running = issue_item(m.col + c0, min(a.ch, m.gs - c0), pol_done);
                     }
                     ++ubatch;
@@ -796,13 +804,14 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                 const int gs = __shfl_sync(0xffffffffu, gs_l, k);
                 if (!dev::mbar_wait(&prox_bar[upar * kBatchMax + k], (uint32_t)(ubatch >> 1) & 1u, abort_flag, halt)) return false;
                 ABB_TICK(3);
-                if (ctrl->changed[upar][k]) {
+                const bool moved = ctrl->changed[upar][k] != 0;
+                if (moved || (kind == kSweepActive && a.u_prefetch)) {     // (prefetched tiles of unmoved groups are consumed and dropped)
                     const T* dl = del + (size_t)upar * Ccap + off;
                     for (int c0 = 0; c0 < gs; c0 += a.ch) {
                         const T* xs; int stage;
                         if (!next_item(xs, stage)) return false;
                         ABB_TICK(0);
-                        axpy_item(xs, min(a.ch, gs - c0), dl + c0);
+                        if (moved) axpy_item(xs, min(a.ch, gs - c0), dl + c0);
                         release_item(stage);
                         ABB_TICK(4);
                     }

@@ -718,11 +718,56 @@ def lazy_cov(mat: np.ndarray, *, copy: bool = False, n_threads: int = 1):
     return _cov_class(_CovLazy, mat.dtype)(mat, n_threads)
 
 
+def block_diag(mats: list, *, method: str = "naive", n_threads: int = 1):
+    """Block-diagonal matrix of the given matrices (adelie/matrix.py:198-290).  Only ``method="cov"`` (MatrixCovBlockDiag{32,64},
+    CORE/matrix/matrix_cov_block_diag.ipp:8-211) is built: the device solver addresses A through full rows, so the blocks are assembled
+    into one dense (p, p) device matrix from each block's ``to_dense`` (memory p^2 instead of the sum of the blocks' squares)."""
+    if method != "cov":
+        raise RuntimeError("adelie_b200: block_diag is only available with method='cov'.")
+    mats = [dense(m, method="cov", n_threads=1) if isinstance(m, np.ndarray) else m for m in mats]
+    if len(mats) == 0:
+        raise RuntimeError("mats must be non-empty.")
+    dtype = mats[0].dtype
+    for m in mats:
+        if not isinstance(m, MatrixCovBase) or m.dtype != dtype:
+            raise RuntimeError("All matrices must be covariance matrices of the same underlying data type.")
+    sizes = [m.cols() for m in mats]
+    p = int(np.sum(sizes))
+    A = np.zeros((p, p), dtype=dtype, order="F")
+    off = 0
+    for m, q in zip(mats, sizes):
+        if isinstance(m, _CovDense):
+            blk = m._mat                       # host copy at hand: no device round trip
+        else:
+            blk = np.empty((q, q), dtype=dtype, order="F")
+            m.to_dense(0, q, blk)
+        A[off:off + q, off:off + q] = blk
+        off += q
+    out = _cov_class(_CovDense, dtype)(A, n_threads)
+    out._mats = mats
+    return out
+
+
+def _sparse_cov(mat, copy, n_threads):
+    """adelie.matrix.sparse(method="cov") -> MatrixCovSparse{32,64}F (CORE/matrix/matrix_cov_sparse.ipp:8-92): a sparse PSD matrix.  The
+    device solver reads full rows of A, so the matrix is densified on upload (p^2 elements in HBM)."""
+    import scipy.sparse as _sp
+    if not _sp.issparse(mat):
+        raise RuntimeError("mat must be a scipy sparse matrix.")
+    if mat.dtype not in (np.float32, np.float64):
+        raise RuntimeError("mat must be of type numpy.float32 or numpy.float64.")
+    if mat.shape[0] != mat.shape[1]:
+        raise RuntimeError("adelie_core: mat must be (p, p).")
+    return _cov_class(_CovDense, mat.dtype)(np.asfortranarray(mat.toarray()), n_threads)
+
+
 def sparse(mat, *, method: str = "naive", copy: bool = False, n_threads: int = 1):
     """Sparse matrix (adelie/matrix.py ``sparse``): a scipy CSC matrix (anything else is converted), float32 / float64."""
     import scipy.sparse as _sp
+    if method == "cov":
+        return _sparse_cov(mat, copy, n_threads)
     if method != "naive":
-        raise RuntimeError("adelie_b200: only method='naive' is in scope (covariance matrices are not on the hot path).")
+        raise RuntimeError("method must be one of 'naive', 'cov'.")
     if not _sp.issparse(mat):
         raise RuntimeError("mat must be a scipy sparse matrix.")
     if mat.dtype not in (np.float32, np.float64):

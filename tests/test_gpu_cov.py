@@ -193,3 +193,36 @@ def test_gaussian_cov_errors_and_warm_start():
     calls = []
     s5 = ad.gaussian_cov(A=A, v=v, groups=groups, early_exit=False, exit_cond=lambda s: calls.append(1) or len(calls) >= 3, progress_bar=False)
     assert len(s5.lmdas) <= 4
+
+
+def test_block_diag_and_sparse_cov_matrices():
+    """adelie.matrix.block_diag(method="cov") and adelie.matrix.sparse(method="cov") (matrix_cov_block_diag.ipp, matrix_cov_sparse.ipp):
+    operators vs the dense block matrix, and a path on the block-diagonal problem equals the two independent paths."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(11)
+    blocks = []
+    for q in (7, 12, 5):
+        Z = rng.standard_normal((40, q))
+        blocks.append(np.asfortranarray(Z.T @ Z / 40))
+    D = np.asfortranarray(sp.block_diag(blocks).toarray())
+    p = D.shape[0]
+    for M in (ad.matrix.block_diag([blocks[0], ad.matrix.dense(blocks[1], method="cov"), blocks[2]], method="cov"),
+              ad.matrix.sparse(sp.csc_matrix(D), method="cov")):
+        assert isinstance(M, ad.matrix.MatrixCovBase64) and M.cols() == p
+        idx = np.array([1, 2, 9, 20]); vals = rng.standard_normal(4); sub = np.array([0, 2, 8, 9, 23])
+        out = np.empty(sub.size); M.bmul(sub, idx, vals, out)
+        np.testing.assert_allclose(out, vals @ D[idx][:, sub], atol=1e-12)
+        out = np.empty(p); M.mul(idx, vals, out)
+        np.testing.assert_allclose(out, vals @ D[idx], atol=1e-12)
+        blk = np.empty((6, 6), order="F"); M.to_dense(5, 6, blk)
+        np.testing.assert_allclose(blk, D[5:11, 5:11], atol=1e-12)
+    v = rng.standard_normal(p)
+    lm = np.array([0.5, 0.3, 0.2, 0.1])
+    full = ad.gaussian_cov(A=ad.matrix.block_diag(blocks, method="cov"), v=v, lmda_path=lm, tol=1e-12, early_exit=False, progress_bar=False)
+    assert full.error == ""
+    off = 0
+    for Bk in blocks:
+        q = Bk.shape[0]
+        part = ad.gaussian_cov(A=Bk, v=v[off:off + q], lmda_path=lm, tol=1e-12, early_exit=False, progress_bar=False)
+        np.testing.assert_allclose(full.betas.toarray()[:, off:off + q], part.betas.toarray(), rtol=1e-6, atol=1e-9)
+        off += q
