@@ -226,3 +226,20 @@ def test_block_diag_and_sparse_cov_matrices():
         part = ad.gaussian_cov(A=Bk, v=v[off:off + q], lmda_path=lm, tol=1e-12, early_exit=False, progress_bar=False)
         np.testing.assert_allclose(full.betas.toarray()[:, off:off + q], part.betas.toarray(), rtol=1e-6, atol=1e-9)
         off += q
+
+
+def test_gaussian_cov_large_groups():
+    """Groups above 32 columns take the generic prox (record read from global memory, shared-memory reductions)."""
+    n, p = 300, 120
+    rng = np.random.default_rng(13)
+    X = rng.standard_normal((n, p)); y = X[:, :8] @ rng.standard_normal(8) + rng.standard_normal(n)
+    A = np.asfortranarray(X.T @ X) / n; v = X.T @ y / n
+    groups = np.array([0, 40, 50, 110])
+    kw = dict(groups=groups, alpha=0.9, tol=1e-12, lmda_path_size=12, min_ratio=0.05, early_exit=False)
+    for cluster in (1, 4):
+        ad.configs.set_configs("cov_cluster", cluster)
+        st = ad.gaussian_cov(A=A, v=v, progress_bar=False, **kw)
+        so = orc.gaussian_cov(A, v, **kw)
+        assert st.error == "" and so.error == ""
+        np.testing.assert_allclose(st.betas.toarray(), so.betas.toarray(), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(st.devs, so.devs, rtol=1e-6, atol=1e-10)
