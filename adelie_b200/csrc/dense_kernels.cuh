@@ -160,7 +160,7 @@ axpy_cols_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, int64_t j0,
 //   C_part[rb][out_off + a*gs+b] = sum_{i in rb} X[i,col+a] X[i,col+b] w[i]
 // grid = (n_groups, n_row_blocks); each CTA streams its (rows x gs) tile once per 4x4 pair block
 // (re-reads hit L1/L2), so HBM traffic is one pass over X_g.
-struct CovItem { int32_t col, gs; int64_t out_off; int32_t cls, pad; };   // out_off: element offset of this group's gs*gs block; col < 0: the column of ones
+struct CovItem { int32_t col, gs; int64_t out_off; int32_t cls, pad; };   // pad: 1 + offset of the group's weighted column sums in the optional means output (0: none)   // out_off: element offset of this group's gs*gs block; col < 0: the column of ones
                                                                           // cls: class whose weights w[i*K + cls] are used (multi-response)
 
 template <class T>
@@ -224,11 +224,12 @@ cov_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovItem* __
 template <class T, int GSP>
 __global__ void __launch_bounds__(256)
 cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovItem* __restrict__ items,
-                 const T* __restrict__ w, int w_is_sqrt, double* __restrict__ C_part, int64_t c_total, int rows_per_block, int K)
+                 const T* __restrict__ w, int w_is_sqrt, double* __restrict__ C_part, int64_t c_total, int rows_per_block, int K,
+                 double* __restrict__ M_part = nullptr, int64_t m_total = 0)
 {
     constexpr int VN = VecT<T>::N;
     constexpr int NP = GSP * (GSP + 1) / 2;
-    __shared__ double s_red[8][NP];
+    __shared__ double s_red[8][NP + GSP];
     const CovItem it = items[blockIdx.x];
     const int gs = it.gs;
     const int rb = blockIdx.y;
@@ -245,6 +246,12 @@ cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovIt
     ACC acc[NP];
 #pragma unroll
     for (int q = 0; q < NP; ++q) acc[q] = 0;
+    // optional second output of the same pass: the weighted column sums X_g^T w (the IRLS-weighted column means of the GLM path, which
+    // otherwise cost a separate pass over the same columns in every IRLS iteration)
+    const bool want_m = M_part != nullptr && it.pad > 0;
+    ACC macc[GSP];
+#pragma unroll
+    for (int a = 0; a < GSP; ++a) macc[a] = 0;
     for (int64_t i = row0 + (int64_t)tid * VN; i < row1; i += 256 * VN) {
         T wv[VN];
         if (K == 1) vec_load<T>(w + i, wv);
@@ -271,6 +278,7 @@ cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovIt
 #pragma unroll
             for (int a = 0; a < GSP; ++a) {
                 const ACC xw = (ACC)(x[a][k] * wv[k]);
+                macc[a] += xw;
 #pragma unroll
                 for (int b = 0; b <= a; ++b, ++q) acc[q] += xw * (ACC)x[b][k];
             }
@@ -281,6 +289,13 @@ cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovIt
         const double t = dev::warp_sum((double)acc[q]);
         if (lane == 0) s_red[warp][q] = t;
     }
+    if (want_m) {
+#pragma unroll
+        for (int a = 0; a < GSP; ++a) {
+            const double t = dev::warp_sum((double)macc[a]);
+            if (lane == 0) s_red[warp][NP + a] = t;
+        }
+    }
     __syncthreads();
     if (tid < NP) {
         double t = 0;
@@ -290,6 +305,13 @@ cov_small_kernel(const T* __restrict__ X, int64_t ld, int64_t n_pad, const CovIt
         if (a < gs) {
             double* Cout = C_part + (size_t)rb * c_total + it.out_off;
             Cout[a * gs + b] = t; Cout[b * gs + a] = t;
+        }
+    } else if (want_m && tid >= 128 && tid < 128 + GSP) {
+        const int a = tid - 128;
+        if (a < gs) {
+            double t = 0;
+            for (int wi = 0; wi < 8; ++wi) t += s_red[wi][NP + a];
+            M_part[(size_t)rb * m_total + (it.pad - 1) + a] = t;
         }
     }
 }

@@ -423,11 +423,16 @@ struct DenseMatrix {
     // Batched Gram: C[out_off + a*gs + b] = X_g^T diag(w or w^2) X_g, device doubles (c_total entries)
     // gs_max: largest group among the items when the caller knows it (<= 12 selects the single-pass register kernel), 0 = unknown
     template <int GSP>
-    void cov_small_launch(dim3 grid, const CovItem* items_dev, const T* w, bool w_is_sqrt, double* out, int64_t c_total, int rows_per_block, int K) {
-        cov_small_kernel<T, GSP><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, out, c_total, rows_per_block, K);
+    void cov_small_launch(dim3 grid, const CovItem* items_dev, const T* w, bool w_is_sqrt, double* out, int64_t c_total, int rows_per_block, int K,
+                          double* m_out = nullptr, int64_t m_total = 0) {
+        cov_small_kernel<T, GSP><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, out, c_total, rows_per_block, K, m_out, m_total);
     }
-    void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out, int K = 1, int gs_max = 0) {
+    // can d_cov also produce the weighted column sums of the groups (CovItem::pad) in the same pass?  (single-pass register kernel only)
+    bool cov_can_fuse_means(int K, int gs_max, bool w_is_sqrt) const { return !sparse && K == 1 && !w_is_sqrt && gs_max >= 1 && gs_max <= 12; }
+    void d_cov(const CovItem* items_dev, int n_items, int64_t c_total, const T* w, bool w_is_sqrt, double* C_out, int K = 1, int gs_max = 0,
+               double* M_out = nullptr, int64_t m_total = 0) {
         if (n_items <= 0) return;
+        if (M_out && !cov_can_fuse_means(K, gs_max, w_is_sqrt)) throw core_error("internal: fused column sums requested from a Gram kernel that cannot produce them.");
         if (sparse) {
             if (K != 1) throw core_error("multi-response problems are not supported on sparse matrices.");
             spcov_kernel<T><<<n_items, 256, 0, stream>>>(csc(), items_dev, w, w_is_sqrt ? 1 : 0, C_out);
@@ -440,14 +445,21 @@ struct DenseMatrix {
         rows_per_block = (rows_per_block + kRowAlign - 1) / kRowAlign * kRowAlign;
         n_rb = (int)((ld + rows_per_block - 1) / rows_per_block);
         dim3 grid(n_items, n_rb);
-        double* out = C_out;
-        if (n_rb > 1) { part.reserve_keep((size_t)n_rb * c_total, stream); out = part.p; }
-        if (gs_max >= 1 && gs_max <= 4) cov_small_launch<4>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
-        else if (gs_max > 4 && gs_max <= 8) cov_small_launch<8>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
-        else if (gs_max > 8 && gs_max <= 10) cov_small_launch<10>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
-        else if (gs_max > 10 && gs_max <= 12) cov_small_launch<12>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K);
+        double* out = C_out; double* mout = M_out;
+        if (n_rb > 1) {
+            part.reserve_keep((size_t)n_rb * (c_total + (M_out ? m_total : 0)), stream);
+            out = part.p; if (M_out) mout = part.p + (size_t)n_rb * c_total;
+        }
+        if (M_out) AB_CUDA(cudaMemsetAsync(mout, 0, sizeof(double) * (size_t)n_rb * m_total, stream));      // (positions of groups outside `items` stay 0)
+        if (gs_max >= 1 && gs_max <= 4) cov_small_launch<4>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K, mout, m_total);
+        else if (gs_max > 4 && gs_max <= 8) cov_small_launch<8>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K, mout, m_total);
+        else if (gs_max > 8 && gs_max <= 10) cov_small_launch<10>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K, mout, m_total);
+        else if (gs_max > 10 && gs_max <= 12) cov_small_launch<12>(grid, items_dev, w, w_is_sqrt, out, c_total, rows_per_block, K, mout, m_total);
         else cov_kernel<T><<<grid, 256, 0, stream>>>(X, ld, ld, items_dev, w, w_is_sqrt ? 1 : 0, out, c_total, rows_per_block, K);
-        if (n_rb > 1) sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
+        if (n_rb > 1) {
+            sum_parts_kernel<<<(unsigned)((c_total + 255) / 256), 256, 0, stream>>>(part.p, n_rb, c_total, C_out);
+            if (M_out) sum_parts_kernel<<<(unsigned)((m_total + 255) / 256), 256, 0, stream>>>(mout, n_rb, m_total, M_out);
+        }
         AB_CUDA(cudaGetLastError());
     }
 

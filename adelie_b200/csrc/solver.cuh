@@ -303,10 +303,18 @@ struct PathState {
     // Computes (A, V, xm) for screen positions [begin, end) from the weighted Gram of each group
     // (solver_gaussian_naive.hpp:53-125): device batched Gram -> host Jacobi -> packed records.
     // `w` device weights (not sqrt), `xmeans_host(col)` gives the weighted column mean.
+    // fuse_means: the weighted column means come out of the Gram pass itself (`xmean` is then not called); only when
+    // screen_means_fusable() says the Gram kernel can do it.
+    bool screen_means_fusable(size_t begin, size_t end) const {
+        if (!Configs::glm_fuse_means || K != 1) return false;
+        int gm_ = 0;
+        for (size_t i = begin; i < end; ++i) gm_ = std::max(gm_, (int)group_sizes[screen_set[i]]);
+        return X->cov_can_fuse_means(K, gm_, false);
+    }
     template <class MeanF>
     void compute_screen_records(size_t begin, size_t end, const T* d_w, MeanF xmean,
                                 std::vector<T>& sXm, std::vector<T>& sv, std::vector<std::vector<T>>& st,
-                                std::vector<GroupMeta>& meta, std::vector<T>& grec)
+                                std::vector<GroupMeta>& meta, std::vector<T>& grec, bool fuse_means = false)
     {
         const size_t S = screen_set.size();
         const size_t vs = S ? (screen_begins.back() + group_sizes[screen_set.back()]) : 0;
@@ -322,7 +330,7 @@ struct PathState {
             GInfo gi{}; gi.item0 = items.size();
             if (K == 1) {
                 gi.f0 = (int)X->phys_col(groups[g], gs); gi.k0 = 0; gi.nfeat = gs; gi.icpt = false;      // physical column (SNP: slot of the decoded-column cache)
-                items.push_back(CovItem{(int32_t)gi.f0, gs, c_total, 0, 0});
+                items.push_back(CovItem{(int32_t)gi.f0, gs, c_total, 0, fuse_means ? (int32_t)(screen_begins[i] + 1) : 0});
                 c_total += (int64_t)gs * gs;
             } else if (groups[g] < n_int) {
                 if (gs != 1) throw core_error("multi-response intercept columns must be groups of size 1.");
@@ -344,17 +352,26 @@ struct PathState {
         d_cov_items.reserve_keep(items.size()); d_cov_out.reserve_keep(c_total);
         d_cov_items.upload(items.data(), items.size());
         int cov_gs_max = 0; for (const CovItem& ci : items) cov_gs_max = std::max(cov_gs_max, (int)ci.gs);
-        X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p, K, cov_gs_max);
+        if (fuse_means) d_cov_means.reserve_keep(vs + 1);
+        X->d_cov(d_cov_items.p, (int)items.size(), c_total, d_w, false, d_cov_out.p, K, cov_gs_max, fuse_means ? d_cov_means.p : nullptr, (int64_t)vs);
         DistContext::get().allreduce<double>(d_cov_out.p, c_total);            // row-sharded: sum the local Gram blocks over ranks
-        std::vector<double> C(c_total);
+        std::vector<double>& C = scr_C;                 // persistent scratch: fresh multi-megabyte vectors per IRLS iteration cost more in page faults than the work
+        C.resize(c_total);
         d_cov_out.download(C.data(), c_total);
+        if (fuse_means) {
+            DistContext::get().allreduce<double>(d_cov_means.p, (int64_t)vs);
+            scr_M.resize(vs);
+            d_cov_means.download(scr_M.data(), vs);
+        }
         AB_CUDA(cudaStreamSynchronize(0));
         timers.slot("cov_device") += now_s() - t_cov0;
         n_kernel_launches += 2;
         meta.resize(S);
-        std::vector<double> Cg;
         // ---- phase 1: centred Gram of every group, packed back to back (eig_in), offsets per group
-        std::vector<double> eig_in, eig_V, eig_D; std::vector<EigItem> eig_items; std::vector<int64_t> eig_slot(end - begin, -1);
+        std::vector<double>& eig_in = scr_eig_in; std::vector<double>& eig_V = scr_eig_V; std::vector<double>& eig_D = scr_eig_D;
+        std::vector<EigItem>& eig_items = scr_eig_items; std::vector<int64_t>& eig_slot = scr_eig_slot;
+        eig_items.clear(); eig_slot.assign(end - begin, -1);
+        double t_ph = now_s();
         {
             int64_t off = 0, d_off = 0;
             for (size_t i = begin; i < end; ++i) {
@@ -363,25 +380,32 @@ struct PathState {
             }
             eig_in.resize(off); eig_V.resize(off); eig_D.resize(d_off);
         }
-        for (size_t i = begin; i < end; ++i) {
+        // (independent per group: every group writes its own slice of sXm / eig_in; on the GLM path this runs for ALL screen groups in every
+        // IRLS iteration -- 1.3 s per config-3 shard path when it was a sequential loop)
+        const long long p1_begin = (long long)begin, p1_end = (long long)end;
+#pragma omp parallel for schedule(static) if (p1_end - p1_begin >= 256)
+        for (long long ii = p1_begin; ii < p1_end; ++ii) {
+            const size_t i = (size_t)ii;
             const idx_t g = screen_set[i]; const int gs = (int)group_sizes[g]; const idx_t sb = screen_begins[i];
             const GInfo& gi = ginfo[i - begin];
-            for (int c = 0; c < gs; ++c) sXm[sb + c] = xmean(groups[g] + c);
+            if (fuse_means) { for (int c = 0; c < gs; ++c) sXm[sb + c] = (T)scr_M[sb + c]; }
+            else for (int c = 0; c < gs; ++c) sXm[sb + c] = xmean(groups[g] + c);
             if (gs == 1) continue;
+            double* dst = eig_in.data() + eig_items[eig_slot[i - begin]].off;
             if (K == 1 || gi.icpt) {
                 const CovItem& it = items[gi.item0];
-                Cg.assign(C.begin() + it.out_off, C.begin() + it.out_off + (size_t)gs * gs);
+                std::copy(C.begin() + it.out_off, C.begin() + it.out_off + (size_t)gs * gs, dst);
             } else {
-                Cg.assign((size_t)gs * gs, 0.0);
+                std::fill(dst, dst + (size_t)gs * gs, 0.0);
                 for (int a = 0; a < gs; ++a) for (int b = 0; b < gs; ++b) {
                     const int fa = (gi.k0 + a) / K, ka = (gi.k0 + a) % K, fb = (gi.k0 + b) / K, kb = (gi.k0 + b) % K;
-                    if (ka == kb) Cg[(size_t)a * gs + b] = C[items[gi.item0 + ka].out_off + (size_t)fa * gi.nfeat + fb];
+                    if (ka == kb) dst[(size_t)a * gs + b] = C[items[gi.item0 + ka].out_off + (size_t)fa * gi.nfeat + fb];
                 }
             }
             if (intercept)
-                for (int a = 0; a < gs; ++a) for (int b = 0; b < gs; ++b) Cg[(size_t)a * gs + b] -= (double)sXm[sb + a] * (double)sXm[sb + b];
-            std::copy(Cg.begin(), Cg.end(), eig_in.begin() + eig_items[eig_slot[i - begin]].off);
+                for (int a = 0; a < gs; ++a) for (int b = 0; b < gs; ++b) dst[(size_t)a * gs + b] -= (double)sXm[sb + a] * (double)sXm[sb + b];
         }
+        timers.slot("rec_phase1") += now_s() - t_ph;
         // ---- phase 2: eigendecompositions -- one batched launch on the device (groups of <= 32 columns), host Jacobi otherwise
         bool eig_on_device = false;
         if (Configs::device_eigh && eig_items.size() >= 16) {
@@ -403,6 +427,7 @@ struct PathState {
         // ---- phase 3: records.  Offsets first (sequential), then every group fills its own slice of grec / sv / st / meta: the loop is
         // embarrassingly parallel over groups and runs on the host cores (OpenMP) -- on the GLM path it is executed for ALL screen
         // groups in every IRLS iteration.
+        t_ph = now_s();
         std::vector<size_t> rec_off_v(end - begin), ext_off_v(end - begin);
         {
             size_t sz = grec.size();
@@ -471,6 +496,7 @@ struct PathState {
             m.pen = (double)penalty[g];
             meta[i] = m;
         }
+        timers.slot("rec_phase3") += now_s() - t_ph;
     }
 
     // solver_gaussian_naive.hpp:134-176 (new screen positions only; weights are static)
@@ -902,6 +928,9 @@ struct PathState {
     // StateGaussianPinNaive, adelie/src/py_state.cpp:389-411).  `tol` is used as given (the path driver passes tol * y_var, :314),
     // `iters` and max_iters are cumulative over the lambdas (:201, :327), outputs are betas / intercepts / rsqs / lmdas and the
     // per-lambda timers (benchmark_screen / benchmark_active live in benchmark_fit_screen / benchmark_fit_active).
+    DevBuf<double> d_cov_means; std::vector<double> scr_M;
+    std::vector<double> scr_C, scr_eig_in, scr_eig_V, scr_eig_D; std::vector<EigItem> scr_eig_items; std::vector<int64_t> scr_eig_slot;     // compute_screen_records
+    std::vector<GroupMeta> glm_meta; std::vector<T> glm_grec, glm_sXm, glm_sv; std::vector<std::vector<T>> glm_stv;                          // fit_glm, per IRLS iteration
     std::vector<T> rsqs;
     void solve_pin() {
         if (is_glm) throw core_error("the pin state is a Gaussian state.");

@@ -136,6 +136,7 @@ PinResult PathState<T>::fit_glm(T lmda_) {
         }
 
         // ---- IRLS-weighted column means of every screen column (:361-372), one batched launch
+        double t_means0 = now_s();
         const size_t S = screen_set.size();
         const size_t vs = S ? (screen_begins.back() + group_sizes[screen_set.back()]) : 0;
         std::vector<int32_t> cols(vs), pcols(vs);     // logical columns / physical columns (SNP: slots of the decoded-column cache)
@@ -145,7 +146,9 @@ PinResult PathState<T>::fit_glm(T lmda_) {
             for (idx_t c = 0; c < group_sizes[g]; ++c) { cols[screen_begins[i] + c] = (int32_t)(groups[g] + c); pcols[screen_begins[i] + c] = pc + (int32_t)c; }
         }
         std::vector<T> sx_means(vs);
-        if (vs && K == 1) {           // multi-response runs with the state-level intercept off: the means are never used (left 0)
+        // the means come out of the Gram pass below when its kernel can produce them (one pass over the screen columns instead of two)
+        const bool fuse_means = vs && screen_means_fusable(0, S);
+        if (vs && K == 1 && !fuse_means) {           // multi-response runs with the state-level intercept off: the means are never used (left 0)
             d_cols.reserve_keep(vs); d_tmp.reserve_keep(vs);
             d_cols.upload(pcols.data(), vs);
             X->d_gemv_t(0, d_cols.p, (int)vs, X->d_ones(), d_irls_w.p, d_tmp.p);
@@ -153,18 +156,21 @@ PinResult PathState<T>::fit_glm(T lmda_) {
             d_tmp.download(sx_means.data(), vs);
             AB_CUDA(cudaStreamSynchronize(0));
         }
+        timers.slot("glm_means") += now_s() - t_means0;
         // ---- screen-derived quantities for ALL screen groups with the IRLS weights (:376-385)
-        std::vector<GroupMeta> meta; std::vector<T> grec;
-        std::vector<T> sXm, sv; std::vector<std::vector<T>> stv;
+        std::vector<GroupMeta>& meta = glm_meta; std::vector<T>& grec = glm_grec;         // persistent scratch (capacity kept across IRLS iterations)
+        std::vector<T>& sXm = glm_sXm; std::vector<T>& sv = glm_sv; std::vector<std::vector<T>>& stv = glm_stv;
+        meta.clear(); grec.clear(); sXm.clear(); sv.clear();
         {
             // xmean lookup by column: build a small map column -> value position
             std::vector<T>& gm = X_means;       // (p,) scratch: only screen columns are defined (GlmNaiveBufferPack::X_means)
             if ((idx_t)gm.size() != p) gm.assign(p, 0);
             for (size_t k = 0; k < vs; ++k) gm[cols[k]] = sx_means[k];
             gs_max_screen = 1; rec_max_screen = 4;
-            compute_screen_records(0, S, d_irls_w.p, [&](idx_t c) { return gm[c]; }, sXm, sv, stv, meta, grec);
+            compute_screen_records(0, S, d_irls_w.p, [&](idx_t c) { return gm[c]; }, sXm, sv, stv, meta, grec, fuse_means);
+            if (fuse_means) for (size_t k = 0; k < vs; ++k) gm[cols[k]] = sXm[k];
         }
-        upload_screen_tables(meta, grec, true);
+        { AB_TIME(timers, "rec_upload"); upload_screen_tables(meta, grec, true); AB_CUDA(cudaStreamSynchronize(0)); }
         n_kernel_launches += 6;
 
         // ---- weighted Gaussian pin solve on the working response (:389-423)

@@ -42,5 +42,5 @@ for rep in range(int(os.environ.get("REPS", 2))):
         print(f"rep {rep}: wall {wall:.3f}s solve {st.total_time:.3f}s err='{st.error}' nl={len(st.lmdas)} sweeps={st.n_sweeps} updates={st.n_group_updates} "
               f"irls={getattr(st, 'n_irls', 0)} kernel_time={st.time_sweep_kernel:.3f}s sweeps/s={st.n_sweeps / st.total_time:.1f} "
               f"active_last={st.active_sizes[-1] if len(st.active_sizes) else 0} screen_last={st.screen_sizes[-1] if len(st.screen_sizes) else 0} dev_last={st.devs[-1]:.4f}", flush=True)
-        print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["run_pin", "invariance", "screen_records", "cov_device", "eigh_device", "panels", "pin_launch", "pin_sync", "pin_download", "screen_host"])
+        print("  host timers: " + " ".join(f"{k}={getattr(st, 't_' + k):.3f}" for k in ["run_pin", "invariance", "screen_records", "cov_device", "eigh_device", "panels", "pin_launch", "pin_sync", "pin_download", "screen_host", "rec_phase1", "rec_phase3", "rec_upload", "glm_means"])
               + f" batched_launches={st.n_batched_launches} batch={st.sweep_batch} ctas={st.sweep_ncta} stages={st.sweep_stages}", flush=True)
