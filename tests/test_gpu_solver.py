@@ -79,3 +79,32 @@ def test_gaussian_glm_irls_matches_opt():
     np.testing.assert_allclose(a.lmdas, b.lmdas, rtol=1e-8)
     assert _rel(np.asarray(b.betas.todense()), np.asarray(a.betas.todense())) < 1e-6
     np.testing.assert_allclose(a.intercepts, b.intercepts, rtol=1e-6, atol=1e-9)
+
+
+def test_glm_fused_means_equals_separate_pass():
+    """The IRLS-weighted column means of the screen groups out of the diagonal-Gram pass (Configs::glm_fuse_means, default) give the path of
+    the separate GEMV pass (solver_glm_naive.hpp:361-372 computes them per IRLS iteration), dense and snp_unphased, float64 and float32."""
+    import adelie_b200 as ad
+    rng = np.random.default_rng(21)
+    n, p = 3000, 60
+    X = np.asfortranarray(rng.standard_normal((n, p)) + 0.5)
+    beta = np.zeros(p); beta[:6] = rng.standard_normal(6)
+    y = (rng.uniform(size=n) < 1 / (1 + np.exp(-(X @ beta - 1.0)))).astype(np.float64)
+    w = rng.uniform(1, 2, n); w /= w.sum()
+    for dtype, rtol in ((np.float64, 1e-9), (np.float32, 1e-4)):
+        kw = dict(groups=np.arange(0, p, 5), alpha=0.6, tol=1e-10 if dtype == np.float64 else 1e-7, irls_tol=1e-10 if dtype == np.float64 else 1e-7,
+                  newton_tol=1e-12 if dtype == np.float64 else 1e-6, lmda_path_size=12, min_ratio=0.05, early_exit=False, progress_bar=False)
+        Xd = np.asfortranarray(X, dtype=dtype)
+        out = []
+        for fuse in (1, 0):
+            ad.configs.set_configs("glm_fuse_means", fuse)
+            try:
+                st = ad.grpnet(Xd, ad.glm.binomial(y.astype(dtype), weights=w.astype(dtype)), **kw)
+            finally:
+                ad.configs.set_configs("glm_fuse_means", None)
+            assert st.error == ""
+            out.append((st.betas.toarray(), st.intercepts, st.devs))
+        scale = np.max(np.abs(out[1][0])) + 1e-30
+        assert np.max(np.abs(out[0][0] - out[1][0])) / scale <= rtol
+        np.testing.assert_allclose(out[0][1], out[1][1], rtol=10 * rtol, atol=10 * rtol)
+        np.testing.assert_allclose(out[0][2], out[1][2], rtol=10 * rtol, atol=10 * rtol)
