@@ -212,3 +212,50 @@ def test_user_defined_base_classes_host_side():
     D = m.to_dense()
     assert D.flags.f_contiguous and D.dtype == np.float32
     np.testing.assert_array_equal(D, Z)
+
+
+def test_expanded_sparse_multi_matrix_layout():
+    """[kron(1, I_K) | kron(X, I_K)] as the sparse multi-response states materialise it (adelie/state.py:1100-1125 layout): row i*K + l,
+    column n_int + j*K + l holds X[i, j]; the intercept block has ones at (i*K + l, l)."""
+    import numpy as np
+    import scipy.sparse as sp
+    from adelie_b200 import state as st, matrix as mx
+    rng = np.random.default_rng(0)
+    n, p, K = 7, 5, 3
+    D = rng.standard_normal((n, p)) * (rng.uniform(size=(n, p)) < 0.5)
+    X = mx.sparse(sp.csc_matrix(D))
+    for intercept in (True, False):
+        E = st._expand_sparse_multi(X, K, intercept, 1)
+        M = E._mat.toarray()
+        n_int = K if intercept else 0
+        assert M.shape == (n * K, n_int + p * K)
+        ref = np.zeros_like(M)
+        for i in range(n):
+            for l in range(K):
+                if intercept:
+                    ref[i * K + l, l] = 1
+                for j in range(p):
+                    ref[i * K + l, n_int + j * K + l] = D[i, j]
+        np.testing.assert_array_equal(M, ref)
+        assert E._mat.has_sorted_indices
+
+
+def test_block_diag_cov_assembly_host_side():
+    """matrix.block_diag(method="cov") of dense blocks assembles the (p, p) matrix on the host (no device round trip)."""
+    import numpy as np
+    import adelie_b200 as ad
+    B1 = np.array([[2.0, 0.5], [0.5, 1.0]]); B2 = np.array([[3.0]]); B3 = np.eye(2) * 4
+    M = ad.matrix.block_diag([B1, ad.matrix.dense(B2, method="cov"), B3], method="cov")
+    assert isinstance(M, ad.matrix.MatrixCovBase64) and M.cols() == 5 and M.shape == (5, 5)
+    ref = np.zeros((5, 5)); ref[:2, :2] = B1; ref[2, 2] = 3; ref[3:, 3:] = B3
+    np.testing.assert_array_equal(M._mat, ref)
+    try:
+        ad.matrix.block_diag([B1], method="naive")
+        raise AssertionError("expected RuntimeError")
+    except RuntimeError:
+        pass
+    try:
+        ad.matrix.dense(np.zeros((2, 3)), method="cov")
+        raise AssertionError("expected RuntimeError")
+    except RuntimeError as e:
+        assert "mat must be (p, p)" in str(e)
