@@ -22,6 +22,7 @@ _DEFAULTS = {
     "panel_tc": 1.0,                 # whole Gram panels on the tensor cores (tcgen05 / TMEM, TF32 operands): 1 = on, 0 = CUDA-core panel kernel
     "panel_gemm": 0.0,               # Gram panels: 1 = whole panels in one pass (fp32; experimental, currently slower), 0 = one block per pair of groups
     "sweep_xchg": 1.0,               # per-group kernel's intra-GPU exchange: 1 = one hop through L2 atomics, 0 = two-level flagged lines
+    "sweep_l2_prefetch": 0.0,        # batched sweep kernel: L2 prefetch of the tiles of batch b + 2 (experiment)
     "sweep_u_prefetch": 1.0,         # batched sweep kernel: update tiles of active-set sweeps prefetched ahead of the proximal updates
     "glm_fuse_means": 1.0,           # GLM path: IRLS-weighted column means of the screen groups out of the Gram pass (0 = separate GEMV pass)
     "cov_cluster": 0.0,              # CTAs of the covariance-method solver's thread-block cluster (0 = auto, else 1 / 2 / 4 / 8)

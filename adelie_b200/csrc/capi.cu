@@ -102,6 +102,7 @@ int ab_configs_set(const char* name, double value) {
     else if (s == "cov_cluster") Configs::cov_cluster = (int)value;
     else if (s == "sweep_u_prefetch") Configs::sweep_u_prefetch = (int)value;
     else if (s == "glm_fuse_means") Configs::glm_fuse_means = (int)value;
+    else if (s == "sweep_l2_prefetch") Configs::sweep_l2_prefetch = (int)value;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }
@@ -129,6 +130,7 @@ int ab_configs_get(const char* name, double* value) {
     else if (s == "cov_cluster") *value = Configs::cov_cluster;
     else if (s == "sweep_u_prefetch") *value = Configs::sweep_u_prefetch;
     else if (s == "glm_fuse_means") *value = Configs::glm_fuse_means;
+    else if (s == "sweep_l2_prefetch") *value = Configs::sweep_l2_prefetch;
     else { g_last_error = "adelie_core: unknown config " + s; return AB_ERR_ARG; }
     return AB_OK;
 }

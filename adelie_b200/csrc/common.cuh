@@ -58,6 +58,7 @@ struct Configs {
     static inline int panel_gemm = 0;          // Gram panels of the batched kernel: 1 = whole panels in one pass (fp32; parity-tested but measured slower), 0 = one block per pair of groups
     static inline int sweep_batch = 0;         // groups per batch of the look-ahead sweep kernel: 0 = auto (up to 6), 1 = off (per-group kernel)
     static inline int device_eigh = 1;         // batched Jacobi on device (0 = host Jacobi)
+    static inline int sweep_l2_prefetch = 0;   // batched sweep kernel: L2 prefetch of the tiles of batch b + 2 by the producer warp (experiment)
     static inline int sweep_u_prefetch = 1;    // batched sweep kernel: residual-update tiles of active-set sweeps prefetched ahead of the proximal updates (0 = issued once the group moved)
     static inline int glm_fuse_means = 1;      // GLM path: IRLS-weighted column means of the screen groups from the Gram pass itself (0 = separate GEMV pass)
     static inline int cov_cluster = 0;         // CTAs of the covariance-method solver's cluster: 0 = auto (about two screen values per thread), else 1 / 2 / 4 / 8

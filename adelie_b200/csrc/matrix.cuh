@@ -566,7 +566,7 @@ struct DenseMatrix {
         a.max_iters = L.max_iters; a.newton_max_iters = L.newton_max_iters; a.max_active_size = L.max_active_size; a.intercept = L.intercept;
         a.start_phase = bl.start_phase;
         a.units_base = g.units_base; a.units_rem = g.units_rem; a.rows_stride = g.rows_stride;
-        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.rec_stride = g.rec_stride; a.pslot_elems = g.pslot_elems; a.ch = g.ch; a.u_prefetch = Configs::sweep_u_prefetch ? 1 : 0;
+        a.n_stages = g.n_stages; a.stage_elems = g.stage_elems; a.rec_stride = g.rec_stride; a.pslot_elems = g.pslot_elems; a.ch = g.ch; a.u_prefetch = Configs::sweep_u_prefetch ? 1 : 0; a.l2_prefetch = Configs::sweep_l2_prefetch ? 1 : 0;
         if (Configs::sweep_profile) { if (!stats.n) stats.alloc(32 + 8 * 160); a.stats = stats.p; } else a.stats = nullptr;
         void* kargs[] = {&a};
         const void* fn = !a.stats ? (const void*)pin_solve_batched_kernel<T, 0> : (Configs::sweep_profile >= 2 ? (const void*)pin_solve_batched_kernel<T, 2> : (const void*)pin_solve_batched_kernel<T, 1>);

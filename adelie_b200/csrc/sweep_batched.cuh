@@ -63,6 +63,7 @@ struct BatchKernelArgs {
     int units_base, units_rem, rows_stride;
     int n_stages, stage_elems;
     int ch;                                              // columns per ring item (a group is streamed in ceil(gs / ch) <= 2 items)
+    int l2_prefetch;                                     // 1: the producer warp prefetches the tiles of batch b + 2 into L2 while batch b + 1 streams
     int u_prefetch;                                      // 1: update tiles of active-set sweeps are prefetched ahead of the proximal updates
     int rec_stride;                                      // elements between the records inside a panel slot
     int pslot_elems;                                     // elements per panel slot = Ccap * 2 Ccap + B * rec_stride
@@ -111,6 +112,10 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
 __device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// L2 prefetch of a contiguous global range (16-byte multiple): no destination, no completion to wait for
+__device__ __forceinline__ void prefetch_l2_bulk(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void ld_hint(const float* p, float (&v)[4], uint64_t pol) {
     asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
@@ -476,6 +481,18 @@ pin_solve_batched_kernel(const __grid_constant__ BatchKernelArgs<T> a)
                         for (int c0 = 0; c0 < m.gs && running; c0 += a.ch) running = issue_item(m.col + c0, min(a.ch, m.gs - c0), pol_keep);
                     }
                     if (!running) break;
+                    // ---- L2 prefetch of the tiles of batch b + 2 (Configs::sweep_l2_prefetch): its dot phase can only start when batch b is
+                    // completely solved, and with four ring stages a CTA keeps too few bytes in flight to stream it at the HBM rate; issued
+                    // one batch ahead, the HBM reads overlap the proximal chain and the dot phase streams from L2
+                    if (a.l2_prefetch && b + 2 < nb) {
+                        const int q0 = (b + 2) * B, nq = min(B, count - q0);
+                        const uint32_t col_bytes = (uint32_t)rows * sizeof(T);
+                        for (int k = 0; k < nq; ++k) {
+                            const int ss2 = (kind == kSweepActive) ? dev::ld_cg(a.active_set + q0 + k) : q0 + k;
+                            const GroupMeta m2 = a.meta[ss2];
+                            if (lane < m2.gs) dev::prefetch_l2_bulk(a.X + (int64_t)(m2.col + lane) * a.ld + r0, col_bytes);
+                        }
+                    }
                     // ---- panel + records of batch b + 1
                     const int slot = pitem & 1;
                     const uint32_t use = pitem >> 1;

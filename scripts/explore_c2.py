@@ -23,6 +23,7 @@ ad.set_configs("sweep_profile", int(os.environ.get("PROF", 0)))
 ad.set_configs("sweep_batch", int(os.environ.get("BATCH", 0)))
 ad.set_configs("sweep_xchg", int(os.environ.get("XCHG", 1)))
 ad.set_configs("sweep_u_prefetch", int(os.environ.get("UPRE", 1)))
+ad.set_configs("sweep_l2_prefetch", int(os.environ.get("L2PRE", 0)))
 for rep in range(2):
     t = time.time()
     st = ad.grpnet(X, ad.glm.gaussian(y, dtype=dtype), groups=groups, early_exit=False, lmda_path_size=L, progress_bar=False, newton_tol=float(os.environ.get('NEWTON_TOL', 1e-12)), tol=float(os.environ.get('TOL', 1e-7)))
