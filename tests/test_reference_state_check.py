@@ -139,3 +139,42 @@ def test_oracle_pin_state_passes_the_reference_check(n, p, G, S):
     s.active_order = np.argsort(s.groups[s.screen_set[a]], kind="stable").astype(int)
     s.betas = ref.betas; s.rsqs = ref.rsqs; s.lmdas = ref.lmdas; s.resid = ref.resid
     REF_STATE.gaussian_pin_naive_base.check(s, method="assert", logger=Silent())
+
+
+@pytest.mark.parametrize("n, p, G, S", [[10, 100, 20, 13], [100, 23, 4, 3], [100, 100, 50, 20]])
+def test_oracle_pin_cov_state_passes_the_reference_check(n, p, G, S):
+    """The covariance-method pin state of the oracle (oracle/cov_oracle.hpp) under the reference's OWN `gaussian_pin_cov_base.check`
+    (adelie/state.py:723-736 -> gaussian_pin_base.check :179-398: screen / active bookkeeping, screen_vars vs screen_transforms sizes,
+    betas / rsqs / lmdas shapes and signs), plus the invariant the cov method maintains: screen_grad = (v - A beta) on the screen values."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from cov_data import create_data_gaussian_pin_cov
+    args, ex = create_data_gaussian_pin_cov(n, p, G, S)
+    a = {k: v for k, v in args.items() if k != "constraints"}
+    ref = orc.gaussian_pin_cov(orc.cov_dense(np.asfortranarray(ex["A"])), **a, tol=1e-12)
+    assert ref.error == ""
+    group_sizes = ex["group_sizes"]
+    s = object.__new__(type("PinCovDuck", (REF_STATE.gaussian_pin_cov_base,), {}))
+    s.A = REF_MATRIX.MatrixCovBase64()
+    s.groups = args["groups"].astype(int); s.group_sizes = group_sizes.astype(int); s.penalty = args["penalty"]
+    s.screen_set = args["screen_set"].astype(int); s.screen_begins = ref.screen_begins.astype(int); s.screen_vars = ref.screen_vars
+    flat, st, o = ref.screen_transforms_flat, [], 0
+    for i in s.screen_set:
+        gs = int(group_sizes[i]); st.append(flat[o:o + gs * gs].reshape(gs, gs)); o += gs * gs
+    s.screen_transforms = st; s.lmda_path = np.asarray(args["lmda_path"])
+    s.active_set_size = int(ref.active_set_size); s.active_set = np.asarray(ref.active_set).astype(int)
+    s.screen_is_active = np.asarray(ref.screen_is_active).astype(bool)
+    act = s.active_set[: s.active_set_size]
+    s.active_begins = np.cumsum(np.concatenate([[0], group_sizes[s.screen_set[act]]]).astype(int))[:-1]
+    s.active_order = np.argsort(s.groups[s.screen_set[act]], kind="stable").astype(int)
+    s.betas = ref.betas; s.rsqs = ref.rsqs; s.lmdas = ref.lmdas
+    REF_STATE.gaussian_pin_cov_base.check(s, method="assert", logger=Silent())
+    # screen_grad of the solved state = v - A beta on the screen values (what coordinate_descent keeps up to date, :243-385)
+    beta = ref.betas.toarray()[-1]
+    grad = ex["v"] - ex["A"] @ beta
+    sg = np.concatenate([grad[g:g + gs] for g, gs in zip(args["groups"][args["screen_set"]], group_sizes[args["screen_set"]])])
+    np.testing.assert_allclose(ref.screen_grad, sg, atol=1e-10)
+    # eigen-decomposition invariant of the screen groups: V diag(vars) V^T = A_gg
+    for i, ss in enumerate(s.screen_set):
+        g, gs = args["groups"][ss], group_sizes[ss]
+        b = s.screen_begins[i]
+        np.testing.assert_allclose(st[i] @ np.diag(ref.screen_vars[b:b + gs]) @ st[i].T, ex["A"][g:g + gs, g:g + gs], atol=1e-10)
