@@ -358,6 +358,22 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
             const bool has_next = idx + 1 < count;
             const int ss_n = has_next ? ((kind == 0) ? a.active_set[idx + 1] : idx + 1) : ss;
             const GroupMeta mm_n = a.meta[ss_n];               // (consumed after the prox)
+            // The Gram entries of this update (rows of the group, columns of the thread's first two screen values; the first 12 rows) do not
+            // depend on the proximal solve: they are loaded NOW and consumed after it, so that their L2 / HBM latency hides behind the solve.
+            constexpr bool kPre2 = sizeof(T) == 4;             // (float64: a second value's entries would spill; it is loaded on demand)
+            const int pl1 = tid, pl2 = tid + kCovThreads;
+            const bool pre1 = pl1 < Lm && !(kind == 0 && !pact[pl1]);
+            const bool pre2 = kPre2 && pl2 < Lm && !(kind == 0 && !pact[pl2]);
+            T px[12], py[12];
+            {
+                const T* g1 = a.gram + (size_t)b0 * a.ldg + (s0 + (pre1 ? pl1 : 0));
+                const T* g2 = a.gram + (size_t)b0 * a.ldg + (s0 + (pre2 ? pl2 : 0));
+#pragma unroll
+                for (int u = 0; u < 12; ++u) {
+                    px[u] = (u < gs && pre1) ? g1[(size_t)u * a.ldg] : T(0);
+                    py[u] = (u < gs && pre2) ? g2[(size_t)u * a.ldg] : T(0);
+                }
+            }
             COV_TICK(3);
             if (warp == 0) {
                 const T* gcur = gbuf + cur * a.gs_cap;
@@ -419,8 +435,25 @@ cov_pin_kernel(const __grid_constant__ CovKernelArgs<T> a)
             // rank-gs update of this CTA's slice: sg[b'] -= sum_c del_c A(col_k + c, col_b'), del = new - old = -s_del (two values of the thread
             // in flight, gs contiguous Gram entries each); then the owners of the next group's values publish them to every CTA
             const int nb0 = mm_n.begin, ngs = has_next ? mm_n.gs : 0;
+            // the thread's first value(s): from the prefetched entries (+ the rows of a group beyond the first 12)
+            if (changed && (pre1 || pre2)) {
+                T acc1 = 0, acc2 = 0;
+#pragma unroll
+                for (int u = 0; u < 12; ++u) if (u < gs) { const T d = s_del[u]; acc1 -= d * px[u]; acc2 -= d * py[u]; }
 #pragma unroll 1
-            for (int bl = tid; bl < Lm; bl += 2 * kCovThreads) {
+                for (int c = 12; c < gs; ++c) {
+                    const T d = s_del[c];
+                    const T* gr = a.gram + (size_t)(b0 + c) * a.ldg + s0;
+                    if (pre1) acc1 -= d * gr[pl1];
+                    if (pre2) acc2 -= d * gr[pl2];
+                }
+                if (pre1) sg[pl1] -= acc1;
+                if (pre2) sg[pl2] -= acc2;
+            }
+            if (ngs) { if (pl1 < Lm) push_value(pl1, nb0, ngs, cur ^ 1); if (kPre2 && pl2 < Lm) push_value(pl2, nb0, ngs, cur ^ 1); }
+            // further values of the thread (slices above 512 / 1024 values): loaded on demand
+#pragma unroll 1
+            for (int bl = tid + (kPre2 ? 2 : 1) * kCovThreads; bl < Lm; bl += 2 * kCovThreads) {
                 const int bl2 = bl + kCovThreads;
                 const bool in2 = bl2 < Lm;
                 const bool on1 = changed && !(kind == 0 && !pact[bl]);
